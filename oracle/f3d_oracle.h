@@ -1,0 +1,110 @@
+/*
+ * oracle/f3d_oracle.h -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE)
+ *
+ * Plain-C f32 restatement of forge3d's path-traced DEM snapshot path
+ * (`HybridPathTracer::render_terrain_reference` + WGSL `main_terrain`,
+ * `main_terrain_gbuffer`, `pt_restir_temporal::main`, `pt_restir_spatial::main`).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library.  The product path
+ * (forge3d_b200/csrc + libforge3d_b200.so) never links or calls it.
+ *
+ * Parity pin status: PINNED against the reference's own artefacts --
+ *   tests/golden/hybrid_terrain/mini_dem_reference.png (drift gate SSIM>=0.995,
+ *   mean-abs<=2.0 of tests/test_hybrid_terrain_pt.py:818-859), the AOV analytic
+ *   gates (:290-380), the conservative-descent KAT of
+ *   src/path_tracing/hybrid_compute/terrain_heightfield.rs:2001-2127 and the
+ *   pyramid unit tests (:528-612).  See tests/test_oracle_*.py.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * /root/reference).  The numerics contract (operation order, no FMA
+ * contraction, pinned sin/cos/atan2/acos) is stated in DESIGN.md section 4.
+ */
+#ifndef F3D_ORACLE_H
+#define F3D_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirrors TerrainReferenceDesc, src/path_tracing/hybrid_compute/render_terrain.rs:239-282 */
+typedef struct f3do_desc {
+    const float* heights;        /* row-major dem_h x dem_w */
+    uint32_t dem_w, dem_h;
+    float spacing[2];
+    float exaggeration;
+    float albedo[3];
+    float cam_origin[3], cam_look_at[3], cam_up[3];
+    float fov_y_deg, exposure;
+    float sun_az_deg, sun_el_deg, sun_intensity, sun_color[3];
+    double observer_lat_deg, observer_lon_deg;
+    int32_t earth_model;         /* 0 flat, 1 sphere, 2 ellipsoid */
+    double sphere_radius_m;
+    int32_t refraction_model;    /* 0 none, 1 bennett, 2 saemundsson, 3 effective_radius */
+    double refraction_k, pressure_mbar, temperature_c;
+    const float* env_rgb;        /* env_h x env_w x 3 or NULL */
+    uint32_t env_w, env_h;
+    float env_intensity;
+    const float* mesh_xyz;       /* nverts x 3 or NULL */
+    uint32_t mesh_nverts;
+    const uint32_t* mesh_idx;    /* ntris x 3 */
+    uint32_t mesh_ntris;
+    uint32_t width, height, seed, spp, max_frames, min_frames;
+    float variance_threshold;
+    int32_t compat_512mib_gate;  /* 1 = enforce the reference's 512 MiB working-set gate */
+} f3do_desc;
+
+/* Mirrors TerrainReferenceOutput, render_terrain.rs:285-299 (+ ray counters). */
+typedef struct f3do_out {
+    uint8_t* rgba;     /* W*H*4, caller allocated */
+    float* albedo;     /* W*H*3 */
+    float* normal;     /* W*H*3 */
+    float* depth;      /* W*H   */
+    float* accum;      /* optional W*H*4 linear accumulation (rgb sum, frame count) or NULL */
+    uint32_t frames;
+    float variance;
+    int32_t converged;
+    uint64_t minmax_pyramid_bytes;
+    uint64_t rays_primary, rays_shadow, rays_ibl;
+    uint64_t nodes_popped;   /* terrain_trace stack pops inside the frame loop */
+} f3do_out;
+
+/* 0 = ok; otherwise an error class (1 render, 2 upload); message via f3do_last_error(). */
+int f3do_render(const f3do_desc* desc, f3do_out* out);
+const char* f3do_last_error(void);
+void f3do_set_threads(int n);   /* OpenMP threads used by f3do_render (0 = default) */
+int f3do_get_threads(void);
+
+/* build_minmax_mips, terrain_heightfield.rs:132-202.  On success returns the number of
+ * levels and fills dims[2*l], dims[2*l+1] (caller provides >= 2*32 entries) and, when
+ * `levels_out` is non-NULL, the concatenated levels (finest first, [min,max] pairs). */
+int f3do_build_minmax(const float* heights, uint32_t w, uint32_t h,
+                      uint32_t* dims, float* levels_out, uint64_t levels_capacity_floats);
+
+/* Batch ray KAT interface over terrain_trace (hybrid_terrain_traversal.wgsl:254-372).
+ * rays: n x 8 floats (origin.xyz, tmin, direction.xyz, tmax).  origin_xz = world xz of
+ * texel (0,0).  Outputs: hit[n] (0/1), t[n], normal[n*3] (may be NULL). */
+int f3do_trace_rays(const float* heights, uint32_t w, uint32_t h,
+                    const float spacing[2], const float origin_xz[2], float exaggeration,
+                    float inv_two_r_prime, int curvature_enabled,
+                    const float* rays, uint64_t n, int any_hit, int apply_curvature,
+                    uint8_t* hit, float* t, float* normal);
+
+/* effective_radius_m / EarthCurvatureUniforms::new, src/geo/refraction.rs:121-130,
+ * terrain_heightfield.rs:52-84.  Returns 0 ok; fills inv_two_r_prime and enabled. */
+int f3do_earth_curvature(int earth_model, double lat_deg, double sphere_radius_m,
+                         int refraction_model, double k, double pressure_mbar, double temperature_c,
+                         double azimuth_deg, float* inv_two_r_prime, uint32_t* enabled);
+
+/* Pinned elementary functions of the numerics contract (exposed for unit tests). */
+void  f3do_sincos(float x, float* s, float* c);
+float f3do_atan2(float y, float x);
+float f3do_acos(float x);
+uint16_t f3do_f32_to_f16(float v);
+float f3do_f16_to_f32(uint16_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

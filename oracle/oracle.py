@@ -1,0 +1,262 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE -- never imported by forge3d_b200).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.  It exposes the oracle through the same keyword surface as the
+reference's native seam (src/py_functions/path_tracing/terrain_reference.rs:224-288).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "libf3d_oracle.so"
+
+EARTH_MODELS = {"flat": 0, "sphere": 1, "ellipsoid": 2, "wgs84": 2}
+REFRACTION_MODELS = {"none": 0, "bennett": 1, "saemundsson": 2, "effective_radius": 3}
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+class _Desc(C.Structure):
+    _fields_ = [
+        ("heights", C.POINTER(C.c_float)), ("dem_w", C.c_uint32), ("dem_h", C.c_uint32),
+        ("spacing", C.c_float * 2), ("exaggeration", C.c_float), ("albedo", C.c_float * 3),
+        ("cam_origin", C.c_float * 3), ("cam_look_at", C.c_float * 3), ("cam_up", C.c_float * 3),
+        ("fov_y_deg", C.c_float), ("exposure", C.c_float),
+        ("sun_az_deg", C.c_float), ("sun_el_deg", C.c_float), ("sun_intensity", C.c_float),
+        ("sun_color", C.c_float * 3),
+        ("observer_lat_deg", C.c_double), ("observer_lon_deg", C.c_double),
+        ("earth_model", C.c_int32), ("sphere_radius_m", C.c_double),
+        ("refraction_model", C.c_int32), ("refraction_k", C.c_double),
+        ("pressure_mbar", C.c_double), ("temperature_c", C.c_double),
+        ("env_rgb", C.POINTER(C.c_float)), ("env_w", C.c_uint32), ("env_h", C.c_uint32),
+        ("env_intensity", C.c_float),
+        ("mesh_xyz", C.POINTER(C.c_float)), ("mesh_nverts", C.c_uint32),
+        ("mesh_idx", C.POINTER(C.c_uint32)), ("mesh_ntris", C.c_uint32),
+        ("width", C.c_uint32), ("height", C.c_uint32), ("seed", C.c_uint32), ("spp", C.c_uint32),
+        ("max_frames", C.c_uint32), ("min_frames", C.c_uint32),
+        ("variance_threshold", C.c_float), ("compat_512mib_gate", C.c_int32),
+    ]
+
+
+class _Out(C.Structure):
+    _fields_ = [
+        ("rgba", C.POINTER(C.c_uint8)), ("albedo", C.POINTER(C.c_float)),
+        ("normal", C.POINTER(C.c_float)), ("depth", C.POINTER(C.c_float)),
+        ("accum", C.POINTER(C.c_float)),
+        ("frames", C.c_uint32), ("variance", C.c_float), ("converged", C.c_int32),
+        ("minmax_pyramid_bytes", C.c_uint64),
+        ("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_ibl", C.c_uint64),
+        ("nodes_popped", C.c_uint64),
+    ]
+
+
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    """Compile the oracle with the committed Makefile (gcc, no FMA contraction)."""
+    src_mtime = max((_HERE / n).stat().st_mtime for n in ("f3d_oracle.c", "f3d_oracle.h", "Makefile"))
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src_mtime:
+        env = dict(os.environ)
+        env.pop("CC", None)
+        subprocess.run(["make", "-C", str(_HERE), "-B", "libf3d_oracle.so"], check=True, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(_LIB_PATH))
+        L.f3do_render.argtypes = [C.POINTER(_Desc), C.POINTER(_Out)]
+        L.f3do_render.restype = C.c_int
+        L.f3do_last_error.restype = C.c_char_p
+        L.f3do_set_threads.argtypes = [C.c_int]
+        L.f3do_get_threads.restype = C.c_int
+        L.f3do_build_minmax.argtypes = [C.POINTER(C.c_float), C.c_uint32, C.c_uint32,
+                                        C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.c_uint64]
+        L.f3do_build_minmax.restype = C.c_int
+        L.f3do_trace_rays.argtypes = [C.POINTER(C.c_float), C.c_uint32, C.c_uint32,
+                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
+                                      C.c_float, C.c_int, C.POINTER(C.c_float), C.c_uint64,
+                                      C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float)]
+        L.f3do_trace_rays.restype = C.c_int
+        L.f3do_earth_curvature.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,
+                                           C.c_double, C.c_double, C.c_double,
+                                           C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+        L.f3do_earth_curvature.restype = C.c_int
+        L.f3do_sincos.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.f3do_atan2.argtypes = [C.c_float, C.c_float]
+        L.f3do_atan2.restype = C.c_float
+        L.f3do_acos.argtypes = [C.c_float]
+        L.f3do_acos.restype = C.c_float
+        L.f3do_f32_to_f16.argtypes = [C.c_float]
+        L.f3do_f32_to_f16.restype = C.c_uint16
+        L.f3do_f16_to_f32.argtypes = [C.c_uint16]
+        L.f3do_f16_to_f32.restype = C.c_float
+        _lib = L
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def set_threads(n: int) -> None:
+    lib().f3do_set_threads(int(n))
+
+
+def get_threads() -> int:
+    return int(lib().f3do_get_threads())
+
+
+def render(heightmap, width, height, cam=None, *, spacing=(1.0, 1.0), exaggeration=1.0,
+           albedo=(0.6, 0.6, 0.6), sun_azimuth_deg=315.0, sun_elevation_deg=45.0, sun_intensity=2.5,
+           env_map=None, env_intensity=0.35, mesh_vertices=None, mesh_indices=None, spp=1,
+           max_frames=512, min_frames=32, variance_threshold=1e-3, seed=7, sun_color=None,
+           observer_latitude_deg=0.0, observer_longitude_deg=0.0, earth_model="ellipsoid",
+           sphere_radius_m=6371008.8, refraction_model="bennett", refraction_k=0.13,
+           pressure_mbar=1013.25, temperature_c=15.0, compat_512mib_gate=False, want_accum=False):
+    """Oracle render with the native seam's keyword surface; returns the reference's result dict
+    (terrain_reference.rs:437-450) plus ray counters."""
+    L = lib()
+    cam = dict(cam or {})
+    dem = np.ascontiguousarray(heightmap, dtype=np.float32)
+    if dem.ndim != 2:
+        raise ValueError(f"heightmap must be 2D (H, W), got shape {dem.shape}")
+    if earth_model not in EARTH_MODELS:
+        raise ValueError(f"unsupported earth_model {earth_model!r}")
+    if refraction_model not in REFRACTION_MODELS:
+        raise ValueError(f"unsupported refraction_model {refraction_model!r}")
+    d = _Desc()
+    d.heights = _fp(dem)
+    d.dem_h, d.dem_w = dem.shape
+    d.spacing = (C.c_float * 2)(*map(float, spacing))
+    d.exaggeration = float(exaggeration)
+    d.albedo = (C.c_float * 3)(*map(float, albedo))
+    d.cam_origin = (C.c_float * 3)(*map(float, cam.get("origin", (0.0, 50.0, 120.0))))
+    d.cam_look_at = (C.c_float * 3)(*map(float, cam.get("look_at", (0.0, 0.0, 0.0))))
+    d.cam_up = (C.c_float * 3)(*map(float, cam.get("up", (0.0, 1.0, 0.0))))
+    d.fov_y_deg = float(cam.get("fov_y", 45.0))
+    d.exposure = float(cam.get("exposure", 1.0))
+    d.sun_az_deg = float(sun_azimuth_deg)
+    d.sun_el_deg = float(sun_elevation_deg)
+    d.sun_intensity = float(sun_intensity)
+    d.sun_color = (C.c_float * 3)(*map(float, sun_color if sun_color is not None else (1.0, 0.97, 0.92)))
+    d.observer_lat_deg = float(observer_latitude_deg)
+    d.observer_lon_deg = float(observer_longitude_deg)
+    d.earth_model = EARTH_MODELS[earth_model]
+    d.sphere_radius_m = float(sphere_radius_m)
+    d.refraction_model = REFRACTION_MODELS[refraction_model]
+    d.refraction_k = float(refraction_k)
+    d.pressure_mbar = float(pressure_mbar)
+    d.temperature_c = float(temperature_c)
+    keep = [dem]
+    if env_map is not None:
+        env = np.ascontiguousarray(env_map, dtype=np.float32)
+        keep.append(env)
+        d.env_rgb = _fp(env)
+        d.env_h, d.env_w = env.shape[0], env.shape[1]
+    d.env_intensity = float(env_intensity)
+    if mesh_vertices is not None:
+        mv = np.ascontiguousarray(mesh_vertices, dtype=np.float32)
+        mi = np.ascontiguousarray(mesh_indices, dtype=np.uint32)
+        keep += [mv, mi]
+        d.mesh_xyz = _fp(mv)
+        d.mesh_nverts = mv.shape[0]
+        d.mesh_idx = mi.ctypes.data_as(C.POINTER(C.c_uint32))
+        d.mesh_ntris = mi.shape[0]
+    d.width, d.height, d.seed, d.spp = int(width), int(height), int(seed), int(spp)
+    d.max_frames, d.min_frames = int(max_frames), int(min_frames)
+    d.variance_threshold = float(variance_threshold)
+    d.compat_512mib_gate = int(bool(compat_512mib_gate))
+
+    H, W = int(height), int(width)
+    rgba = np.zeros((H, W, 4), np.uint8)
+    alb = np.zeros((H, W, 3), np.float32)
+    nrm = np.zeros((H, W, 3), np.float32)
+    dep = np.zeros((H, W), np.float32)
+    acc = np.zeros((H, W, 4), np.float32) if want_accum else None
+    o = _Out()
+    o.rgba = rgba.ctypes.data_as(C.POINTER(C.c_uint8))
+    o.albedo, o.normal, o.depth = _fp(alb), _fp(nrm), _fp(dep)
+    if acc is not None:
+        o.accum = _fp(acc)
+    rc = L.f3do_render(C.byref(d), C.byref(o))
+    if rc != 0:
+        raise OracleError(L.f3do_last_error().decode("utf-8", "replace"))
+    res = dict(rgba=rgba, albedo=alb, normal=nrm, depth=dep, frames=int(o.frames),
+               variance=float(o.variance), converged=bool(o.converged),
+               minmax_pyramid_bytes=int(o.minmax_pyramid_bytes),
+               rays_primary=int(o.rays_primary), rays_shadow=int(o.rays_shadow),
+               rays_ibl=int(o.rays_ibl), nodes_popped=int(o.nodes_popped),
+               sun_source="manual_angles", solar_azimuth_deg=float(sun_azimuth_deg),
+               solar_elevation_deg=float(sun_elevation_deg))
+    if acc is not None:
+        res["accum"] = acc
+    return res
+
+
+def build_minmax(heights):
+    """build_minmax_mips -> (list of (h, w, 2) float32 levels finest first, cell_w, cell_h)."""
+    L = lib()
+    dem = np.ascontiguousarray(heights, dtype=np.float32)
+    h, w = dem.shape
+    dims = (C.c_uint32 * 64)()
+    n = L.f3do_build_minmax(_fp(dem), w, h, dims, None, 0)
+    if n < 0:
+        raise OracleError(L.f3do_last_error().decode())
+    total = sum(dims[2 * i] * dims[2 * i + 1] * 2 for i in range(n))
+    buf = np.zeros(total, np.float32)
+    n = L.f3do_build_minmax(_fp(dem), w, h, dims, _fp(buf), total)
+    levels, off = [], 0
+    for i in range(n):
+        lw, lh = dims[2 * i], dims[2 * i + 1]
+        levels.append(buf[off:off + lw * lh * 2].reshape(lh, lw, 2))
+        off += lw * lh * 2
+    return levels, w - 1, h - 1
+
+
+def trace_rays(heights, spacing, origin_xz, exaggeration, rays, *, any_hit, apply_curvature,
+               inv_two_r_prime=0.0, curvature_enabled=False):
+    """terrain_trace over a ray batch; rays is (n, 8): origin.xyz, tmin, direction.xyz, tmax."""
+    L = lib()
+    dem = np.ascontiguousarray(heights, dtype=np.float32)
+    r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+    n = r.shape[0]
+    hit = np.zeros(n, np.uint8)
+    t = np.zeros(n, np.float32)
+    nrm = np.zeros((n, 3), np.float32)
+    sp = (C.c_float * 2)(*map(float, spacing))
+    og = (C.c_float * 2)(*map(float, origin_xz))
+    rc = L.f3do_trace_rays(_fp(dem), dem.shape[1], dem.shape[0], sp, og, float(exaggeration),
+                           float(inv_two_r_prime), int(bool(curvature_enabled)), _fp(r), n,
+                           int(bool(any_hit)), int(bool(apply_curvature)),
+                           hit.ctypes.data_as(C.POINTER(C.c_uint8)), _fp(t), _fp(nrm))
+    if rc != 0:
+        raise OracleError(L.f3do_last_error().decode())
+    return hit.astype(bool), t, nrm
+
+
+def earth_curvature(earth_model="ellipsoid", lat_deg=0.0, sphere_radius_m=6371008.8,
+                    refraction_model="bennett", k=0.13, pressure_mbar=1013.25, temperature_c=15.0,
+                    azimuth_deg=0.0):
+    L = lib()
+    inv = C.c_float()
+    en = C.c_uint32()
+    rc = L.f3do_earth_curvature(EARTH_MODELS[earth_model], lat_deg, sphere_radius_m,
+                                REFRACTION_MODELS[refraction_model], k, pressure_mbar, temperature_c,
+                                azimuth_deg, C.byref(inv), C.byref(en))
+    if rc != 0:
+        raise OracleError(L.f3do_last_error().decode())
+    return float(inv.value), bool(en.value)
