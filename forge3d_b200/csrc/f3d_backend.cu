@@ -1,0 +1,794 @@
+// forge3d_b200/csrc/f3d_backend.cu
+// Host side of libforge3d_b200.so: trust-boundary validation, uniform setup, device memory, the
+// accumulate-until-converged driver loop and the C ABI declared in include/forge3d_b200.h.
+// This is the C++ stand-in for the reference's Rust driver
+// /root/reference/src/path_tracing/hybrid_compute/render_terrain.rs:474-1434 (+ terrain_heightfield.rs
+// :52-84,:224-369 and src/geo/refraction.rs): Rust is not available in this image, so the layer that
+// is Rust in the reference is C++ here and exports the C ABI a Rust `extern "C"` shim would bind.
+// There is no CPU fallback anywhere in this file: every path that cannot reach a CUDA device fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/forge3d_b200.h"
+#include "f3d_kernels.cuh"
+
+using namespace f3d;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[640];
+
+static int fail(int cls, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return cls;
+}
+
+#define CUDA_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            return fail(F3D_ERR_DEVICE, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(_e), __FILE__,     \
+                        __LINE__, cudaGetErrorString(_e));                                                 \
+    } while (0)
+
+extern "C" const char* f3d_last_error(void) { return g_err; }
+extern "C" int f3d_abi_version(void) { return F3D_ABI_VERSION; }
+extern "C" int f3d_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host math mirroring glam 0.24.2 / Rust f32 (render_terrain.rs:635-661)
+// ------------------------------------------------------------------------------------------------
+struct hv3 { float x, y, z; };
+static inline hv3 HV(const float* p) { return hv3{p[0], p[1], p[2]}; }
+static inline hv3 hsub(hv3 a, hv3 b) { return hv3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline float hdot(hv3 a, hv3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+static inline hv3 hcross(hv3 a, hv3 b) { return hv3{a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+static inline float hlen(hv3 a) { return sqrtf(hdot(a, a)); }
+static inline hv3 hnorm(hv3 a) { float inv = 1.0f / hlen(a); return hv3{a.x * inv, a.y * inv, a.z * inv}; }
+static inline bool finite3(const float* v) { return isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]); }
+static inline float clamp_radiometric(float v) { return fminf(fmaxf(v, 0.0f), 65504.0f); }  // :571-576
+static inline float to_radians_f32(float d) { return d * (3.14159274101257324f / 180.0f); }
+static inline double deg2rad(double d) { return d * (3.14159265358979323846 / 180.0); }
+
+// validate_desc, render_terrain.rs:474-557 (same order, same message text)
+static int validate_desc(const f3d_terrain_desc* d) {
+    if (!d->heights) return fail(F3D_ERR_ARGUMENT, "heights pointer is null");
+    if (d->width == 0 || d->height == 0 || d->max_frames == 0)
+        return fail(F3D_ERR_RENDER, "terrain reference requires non-zero width/height/max_frames");
+    if (d->min_frames > d->max_frames)
+        return fail(F3D_ERR_RENDER, "min_frames (%u) must be <= max_frames (%u)", d->min_frames, d->max_frames);
+    if (d->spp == 0 || d->spp > 64) return fail(F3D_ERR_RENDER, "spp must be in 1..=64, got %u", d->spp);
+    if (!(isfinite(d->exaggeration) && d->exaggeration > 0.0f))
+        return fail(F3D_ERR_RENDER, "terrain exaggeration must be finite and > 0");
+    if (!(finite3(d->cam_origin) && finite3(d->cam_look_at) && finite3(d->cam_up)))
+        return fail(F3D_ERR_RENDER, "camera origin/look_at/up must be finite");
+    hv3 fwd = hsub(HV(d->cam_look_at), HV(d->cam_origin));
+    if (hlen(fwd) < 1e-6f) return fail(F3D_ERR_RENDER, "camera look_at must differ from origin");
+    if (hlen(hcross(hnorm(fwd), HV(d->cam_up))) < 1e-6f)
+        return fail(F3D_ERR_RENDER, "camera up vector must not be parallel to the view direction");
+    if (!(isfinite(d->fov_y_deg) && d->fov_y_deg > 0.0f && d->fov_y_deg < 180.0f))
+        return fail(F3D_ERR_RENDER, "fov_y must be finite and in (0, 180) degrees, got %g", d->fov_y_deg);
+    if (!(isfinite(d->exposure) && d->exposure > 0.0f)) return fail(F3D_ERR_RENDER, "exposure must be finite and > 0");
+    if (!(isfinite(d->sun_az_deg) && isfinite(d->sun_el_deg)))
+        return fail(F3D_ERR_RENDER, "sun azimuth/elevation must be finite");
+    if (!(isfinite(d->sun_intensity) && d->sun_intensity >= 0.0f))
+        return fail(F3D_ERR_RENDER, "sun intensity must be finite and >= 0");
+    if (!finite3(d->sun_color) || d->sun_color[0] < 0 || d->sun_color[1] < 0 || d->sun_color[2] < 0)
+        return fail(F3D_ERR_RENDER, "sun color must have three finite non-negative components");
+    if (!(isfinite(d->env_intensity) && d->env_intensity >= 0.0f))
+        return fail(F3D_ERR_RENDER, "env intensity must be finite and >= 0");
+    if (!(isfinite(d->variance_threshold) && d->variance_threshold > 0.0f))
+        return fail(F3D_ERR_RENDER, "variance threshold must be finite and > 0");
+    if (!(isfinite(d->spacing[0]) && d->spacing[0] > 0.0f && isfinite(d->spacing[1]) && d->spacing[1] > 0.0f))
+        return fail(F3D_ERR_RENDER, "terrain spacing must be finite and > 0, got (%g, %g)", d->spacing[0], d->spacing[1]);
+    if (d->mesh_xyz || d->mesh_idx) {
+        if (!d->mesh_xyz || d->mesh_nverts == 0)
+            return fail(F3D_ERR_RENDER, "mesh vertices must be a non-empty flat [x,y,z] list");
+        if (!d->mesh_idx || d->mesh_ntris == 0)
+            return fail(F3D_ERR_RENDER, "mesh indices must be a non-empty multiple of 3");
+        for (size_t i = 0; i < (size_t)d->mesh_nverts * 3; i++)
+            if (!isfinite(d->mesh_xyz[i])) return fail(F3D_ERR_RENDER, "mesh vertices contain non-finite values");
+        for (size_t i = 0; i < (size_t)d->mesh_ntris * 3; i++)
+            if (d->mesh_idx[i] >= d->mesh_nverts)
+                return fail(F3D_ERR_RENDER, "mesh indices reference out-of-bounds vertices");
+    }
+    // TerrainPtScene::new, terrain_heightfield.rs:402-421
+    if (!(isfinite(d->albedo[0]) && d->albedo[0] >= 0 && isfinite(d->albedo[1]) && d->albedo[1] >= 0 &&
+          isfinite(d->albedo[2]) && d->albedo[2] >= 0))
+        return fail(F3D_ERR_UPLOAD, "terrain albedo must be finite and >= 0");
+    // build_minmax_mips, terrain_heightfield.rs:133-137 (the non-finite scan runs on the device)
+    if (d->dem_w < 2 || d->dem_h < 2)
+        return fail(F3D_ERR_UPLOAD, "terrain heightfield must be at least 2x2 texels, got %ux%u", d->dem_w, d->dem_h);
+    if (d->dem_w - 1 > 8192 || d->dem_h - 1 > 8192)
+        return fail(F3D_ERR_UPLOAD, "terrain heightfield exceeds 8192 cells per axis (13-bit node packing), got %ux%u",
+                    d->dem_w, d->dem_h);
+    if (d->env_rgb) {
+        if (d->env_w == 0 || d->env_h == 0) return fail(F3D_ERR_UPLOAD, "env map dims do not match data length");
+        for (size_t i = 0; i < (size_t)d->env_w * d->env_h * 3; i++)
+            if (!isfinite(d->env_rgb[i])) return fail(F3D_ERR_UPLOAD, "env map contains non-finite samples");
+    }
+    if (d->part_world > 1 && d->part_rank >= d->part_world)
+        return fail(F3D_ERR_ARGUMENT, "part_rank (%u) must be < part_world (%u)", d->part_rank, d->part_world);
+    return 0;
+}
+
+// effective_radius_m + EarthCurvatureUniforms::new (src/geo/refraction.rs:57-144, terrain_heightfield.rs:52-84)
+static int earth_curvature(const f3d_terrain_desc* d, float* inv_two_r_prime, uint32_t* enabled) {
+    if (!(isfinite(d->observer_lat_deg) && d->observer_lat_deg >= -90.0 && d->observer_lat_deg <= 90.0 &&
+          isfinite(d->observer_lon_deg) && d->observer_lon_deg >= -180.0 && d->observer_lon_deg <= 180.0))
+        return fail(F3D_ERR_RENDER, "ray-origin latitude/longitude must be finite and in [-90,90]/[-180,180]");
+    if (d->earth_model < 0 || d->earth_model > 2) return fail(F3D_ERR_ARGUMENT, "unsupported earth_model %d", d->earth_model);
+    if (d->refraction_model < 0 || d->refraction_model > 3)
+        return fail(F3D_ERR_ARGUMENT, "unsupported refraction_model %d", d->refraction_model);
+    if (d->earth_model == F3D_EARTH_FLAT && d->refraction_model != F3D_REFRACTION_NONE)
+        return fail(F3D_ERR_RENDER, "flat earth only supports refraction_model='none'");
+    const double az_deg = (double)d->sun_az_deg;
+    if (!isfinite(az_deg)) return fail(F3D_ERR_RENDER, "azimuth must be finite");
+    double radius;
+    if (d->earth_model == F3D_EARTH_FLAT) radius = INFINITY;
+    else if (d->earth_model == F3D_EARTH_SPHERE) {
+        if (!(isfinite(d->sphere_radius_m) && d->sphere_radius_m > 0.0))
+            return fail(F3D_ERR_RENDER, "sphere radius must be finite and positive");
+        radius = d->sphere_radius_m;
+    } else {
+        const double a_m = 6378137.0, e2 = 6.6943799901413165e-3;
+        double phi = deg2rad(d->observer_lat_deg), sp = sin(phi);
+        double w = sqrt(1.0 - e2 * (sp * sp));
+        double meridional = a_m * (1.0 - e2) / (w * w * w), prime_vertical = a_m / w;
+        double az = deg2rad(az_deg), ca = cos(az), sa = sin(az);
+        radius = 1.0 / ((ca * ca) / meridional + (sa * sa) / prime_vertical);
+    }
+    double k;
+    if (d->refraction_model == F3D_REFRACTION_NONE) k = 0.0;
+    else if (d->refraction_model == F3D_REFRACTION_EFFECTIVE_RADIUS) k = d->refraction_k;
+    else {
+        if (!isfinite(d->pressure_mbar) || d->pressure_mbar <= 0.0 || d->temperature_c <= -273.15)
+            return fail(F3D_ERR_RENDER, "pressure must be positive and temperature above absolute zero");
+        double base = d->refraction_model == F3D_REFRACTION_BENNETT ? 0.13 : 1.0 / 7.0;
+        k = base * (d->pressure_mbar / 1013.25) * (288.15 / (273.15 + d->temperature_c));
+    }
+    if (!(isfinite(k) && k < 1.0)) return fail(F3D_ERR_RENDER, "refraction k must be finite and less than 1");
+    double eff = radius / (1.0 - k);
+    bool en = isfinite(eff);
+    *inv_two_r_prime = en ? (float)(0.5 / eff) : 0.0f;
+    *enabled = en ? 1u : 0u;
+    return 0;
+}
+
+static uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+// ------------------------------------------------------------------------------------------------
+// device terrain: packed cells + min-max levels
+// ------------------------------------------------------------------------------------------------
+struct DeviceTerrain {
+    float4* cells = nullptr;
+    float2* mm_base = nullptr;
+    int nlevels = 0;
+    uint32_t dims[kMaxLevels][2] = {};
+    size_t level_off[kMaxLevels] = {};   // in float2 units
+    size_t mm_total = 0;                 // float2 count
+    uint32_t cell_w = 0, cell_h = 0;
+    uint64_t bytes = 0;
+
+    void release() {
+        if (cells) cudaFree(cells);
+        if (mm_base) cudaFree(mm_base);
+        cells = nullptr; mm_base = nullptr;
+    }
+};
+
+// Uploads the DEM, scans it for non-finite samples, and builds cells + pyramid on the device.
+static int build_device_terrain(const float* h_heights, uint32_t w, uint32_t h, float ex, cudaStream_t stream,
+                                DeviceTerrain* T, uint64_t* launches) {
+    const uint32_t cw = w - 1, ch = h - 1;
+    uint32_t lw = next_pow2(cw), lh = next_pow2(ch);
+    T->cell_w = cw; T->cell_h = ch;
+    T->nlevels = 0; T->mm_total = 0;
+    while (true) {
+        if (T->nlevels >= kMaxLevels) return fail(F3D_ERR_UPLOAD, "min-max pyramid exceeds %d levels", kMaxLevels);
+        T->dims[T->nlevels][0] = lw; T->dims[T->nlevels][1] = lh;
+        T->level_off[T->nlevels] = T->mm_total;
+        T->mm_total += (size_t)lw * lh;
+        T->nlevels++;
+        if (lw == 1 && lh == 1) break;
+        lw = std::max(lw / 2, 1u); lh = std::max(lh / 2, 1u);
+    }
+    float* d_h = nullptr;
+    uint32_t* d_flag = nullptr;
+    const size_t n = (size_t)w * h;
+    CUDA_TRY(cudaMalloc(&d_h, n * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&d_flag, sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&T->cells, (size_t)cw * ch * sizeof(float4)));
+    CUDA_TRY(cudaMalloc(&T->mm_base, T->mm_total * sizeof(float2)));
+    CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), stream));
+    CUDA_TRY(cudaMemcpyAsync(d_h, h_heights, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    k_check_finite<<<(unsigned)std::min<size_t>((n + 255) / 256, 1184), 256, 0, stream>>>(d_h, n, d_flag);
+    dim3 blk(32, 8);
+    dim3 g0((T->dims[0][0] + 31) / 32, (T->dims[0][1] + 7) / 8);
+    k_build_level0<<<g0, blk, 0, stream>>>(d_h, w, h, T->dims[0][0], T->dims[0][1], ex, T->cells, T->mm_base);
+    *launches += 2;
+    for (int l = 1; l < T->nlevels; l++) {
+        dim3 g((T->dims[l][0] + 31) / 32, (T->dims[l][1] + 7) / 8);
+        k_reduce_level<<<g, blk, 0, stream>>>(T->mm_base + T->level_off[l - 1], T->dims[l - 1][0], T->dims[l - 1][1],
+                                              T->mm_base + T->level_off[l], T->dims[l][0], T->dims[l][1]);
+        (*launches)++;
+    }
+    uint32_t flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof flag, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaGetLastError());
+    cudaFree(d_h);
+    cudaFree(d_flag);
+    if (flag) return fail(F3D_ERR_UPLOAD, "terrain heightfield contains non-finite samples");
+    T->bytes = (uint64_t)cw * ch * sizeof(float4) + T->mm_total * sizeof(float2);
+    return 0;
+}
+
+static void fill_scene_terrain(SceneParams* S, const DeviceTerrain& T) {
+    S->cells = T.cells;
+    S->cell_w = T.cell_w; S->cell_h = T.cell_h;
+    S->mip_count = (uint32_t)T.nlevels;
+    for (int l = 0; l < kMaxLevels; l++) {
+        S->mm[l] = l < T.nlevels ? T.mm_base + T.level_off[l] : nullptr;
+        S->mm_pitch[l] = l < T.nlevels ? T.dims[l][0] : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// session
+// ------------------------------------------------------------------------------------------------
+struct f3d_session {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    FrameParams P{};
+    DeviceTerrain terrain;
+    float4* d_env = nullptr;
+    float4* d_mesh_v = nullptr;
+    uint32_t* d_mesh_i = nullptr;
+    float4* d_accum = nullptr;
+    float2* d_welford = nullptr;
+    float4* d_resv[2] = {nullptr, nullptr};
+    uint8_t* d_pixflags = nullptr;
+    ushort4* d_aov_normal = nullptr;
+    float* d_aov_depth = nullptr;
+    unsigned long long* d_counters = nullptr;
+    uint32_t* d_gate = nullptr;       // [0] vmax bits, [1] non-finite, [2] validity non-finite, [3] validity any
+    uint32_t* h_gate = nullptr;       // pinned
+    // output staging (host-facing resolve)
+    uint8_t* d_rgba = nullptr; float* d_albedo = nullptr; float* d_normal = nullptr; float* d_depth = nullptr;
+    void* h_stage = nullptr; size_t h_stage_bytes = 0;
+    // peers
+    void* peer_ptrs[8 * F3D_IPC_HANDLES_PER_RANK] = {};
+    int n_peer_ptrs = 0;
+    // bookkeeping
+    uint32_t frames = 0;
+    uint32_t max_frames = 0, min_frames = 0;
+    float variance_threshold = 0;
+    float sun_el_deg = 0, sun_intensity = 0, sun_color[3] = {0, 0, 0};
+    uint64_t gpu_bytes = 0, host_visible_bytes = 0, pyramid_bytes_ref = 0, launches = 0;
+    double setup_ms = 0, frames_ms = 0, readback_ms = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    dim3 grid;
+};
+
+static void session_free(f3d_session* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (int i = 0; i < s->n_peer_ptrs; i++)
+        if (s->peer_ptrs[i]) cudaIpcCloseMemHandle(s->peer_ptrs[i]);
+    s->terrain.release();
+    cudaFree(s->d_env); cudaFree(s->d_mesh_v); cudaFree(s->d_mesh_i);
+    cudaFree(s->d_accum); cudaFree(s->d_welford); cudaFree(s->d_resv[0]); cudaFree(s->d_resv[1]);
+    cudaFree(s->d_pixflags); cudaFree(s->d_aov_normal); cudaFree(s->d_aov_depth); cudaFree(s->d_counters);
+    cudaFree(s->d_gate);
+    cudaFree(s->d_rgba); cudaFree(s->d_albedo); cudaFree(s->d_normal); cudaFree(s->d_depth);
+    if (s->h_gate) cudaFreeHost(s->h_gate);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+template <typename T>
+static int dmalloc(f3d_session* s, T** p, size_t count, bool zero) {
+    CUDA_TRY(cudaMalloc(p, count * sizeof(T)));
+    s->gpu_bytes += count * sizeof(T);
+    if (zero) CUDA_TRY(cudaMemsetAsync(*p, 0, count * sizeof(T), s->stream));
+    return 0;
+}
+
+static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d_session* s) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(F3D_ERR_DEVICE, "no CUDA device available: forge3d_b200 has no CPU fallback");
+    }
+    if (d->device < 0 || d->device >= ndev) return fail(F3D_ERR_DEVICE, "CUDA device %d out of range (%d devices)", d->device, ndev);
+    s->device = d->device;
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (cuda_stream) s->stream = (cudaStream_t)cuda_stream;
+    else { CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
+    CUDA_TRY(cudaEventCreate(&s->ev0));
+    CUDA_TRY(cudaEventCreate(&s->ev1));
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+
+    const uint32_t W = d->width, H = d->height;
+    const size_t npx = (size_t)W * H;
+    FrameParams& P = s->P;
+    SceneParams& S = P.scene;
+
+    // ---- clamp radiometric scalars, camera basis, light (render_terrain.rs:571-576,635-661,697-708) ----
+    const float exposure = clamp_radiometric(d->exposure);
+    const float sun_intensity = clamp_radiometric(d->sun_intensity);
+    const float sun_color[3] = {clamp_radiometric(d->sun_color[0]), clamp_radiometric(d->sun_color[1]),
+                                clamp_radiometric(d->sun_color[2])};
+    const float env_intensity = clamp_radiometric(d->env_intensity);
+    hv3 origin = HV(d->cam_origin);
+    hv3 forward = hnorm(hsub(HV(d->cam_look_at), origin));
+    hv3 right = hnorm(hcross(forward, HV(d->cam_up)));
+    hv3 up = hnorm(hcross(right, forward));
+    const float az = to_radians_f32(d->sun_az_deg), el = to_radians_f32(d->sun_el_deg);
+    P.W = W; P.H = H; P.frame_index = 0; P.spp = std::max(d->spp, 1u); P.window = 32u;  // WELFORD_WINDOW :236
+    memcpy(P.cam_origin, d->cam_origin, sizeof P.cam_origin);
+    P.cam_right[0] = right.x; P.cam_right[1] = right.y; P.cam_right[2] = right.z;
+    P.cam_up[0] = up.x; P.cam_up[1] = up.y; P.cam_up[2] = up.z;
+    P.cam_forward[0] = forward.x; P.cam_forward[1] = forward.y; P.cam_forward[2] = forward.z;
+    const float fov = to_radians_f32(d->fov_y_deg);
+    P.half_h = tanf(0.5f * fov);                              // hybrid_terrain_traversal.wgsl:469
+    P.half_w = ((float)W / (float)H) * P.half_h;              // cam_aspect * half_h
+    P.exposure = exposure;
+    P.seed_hi = d->seed;
+    P.seed_lo = d->seed ^ 0x85EBCA6Bu;                        // render_terrain.rs:658-659
+    P.light_dir[0] = cosf(az) * cosf(el); P.light_dir[1] = sinf(el); P.light_dir[2] = sinf(az) * cosf(el);
+    for (int c = 0; c < 3; c++) P.light_color[c] = sun_intensity * sun_color[c];
+    s->sun_el_deg = d->sun_el_deg; s->sun_intensity = sun_intensity;
+    memcpy(s->sun_color, sun_color, sizeof sun_color);
+    s->max_frames = d->max_frames; s->min_frames = d->min_frames; s->variance_threshold = d->variance_threshold;
+
+    // ---- partition ----
+    P.part_world = std::max(d->part_world, 1u);
+    P.part_rank = P.part_world > 1 ? d->part_rank : 0u;
+    uint32_t block_rows = d->part_block_rows ? d->part_block_rows : 32u;
+    block_rows = ((block_rows + kTileH - 1) / kTileH) * kTileH;
+    if (P.part_world == 1) block_rows = ((H + kTileH - 1) / kTileH) * kTileH;   // one block = whole image
+    P.block_rows = block_rows;
+    P.tiles_per_block = block_rows / kTileH;
+    P.nblocks = (H + block_rows - 1) / block_rows;
+    const uint32_t owned_blocks = P.nblocks > P.part_rank ? (P.nblocks - P.part_rank + P.part_world - 1) / P.part_world : 0;
+    s->grid = dim3((W + kTileW - 1) / kTileW, std::max(owned_blocks * P.tiles_per_block, 1u));
+
+    // ---- terrain scene ----
+    int rc = earth_curvature(d, &S.inv_two_r_prime, &S.curvature_enabled);
+    if (rc) return rc;
+    rc = build_device_terrain(d->heights, d->dem_w, d->dem_h, d->exaggeration, s->stream, &s->terrain, &s->launches);
+    if (rc) return rc;
+    s->gpu_bytes += s->terrain.bytes;
+    fill_scene_terrain(&S, s->terrain);
+    S.sx = d->spacing[0]; S.sz = d->spacing[1];
+    S.ox = -0.5f * ((float)d->dem_w - 1.0f) * S.sx;           // terrain_heightfield.rs:359-360
+    S.oz = -0.5f * ((float)d->dem_h - 1.0f) * S.sz;
+    memcpy(S.albedo, d->albedo, sizeof S.albedo);
+    S.env_intensity = env_intensity;
+    {   // reference-compatible diagnostic: DEM R32F + RG32F chain (terrain_heightfield.rs:292-314)
+        uint64_t b = (uint64_t)d->dem_w * d->dem_h * 4;
+        for (int l = 0; l < s->terrain.nlevels; l++) b += (uint64_t)s->terrain.dims[l][0] * s->terrain.dims[l][1] * 8;
+        s->pyramid_bytes_ref = b;
+    }
+    if (d->env_rgb) {
+        const size_t ne = (size_t)d->env_w * d->env_h;
+        std::vector<float4> rgba(ne);
+        for (size_t i = 0; i < ne; i++) rgba[i] = make_float4(d->env_rgb[3 * i], d->env_rgb[3 * i + 1], d->env_rgb[3 * i + 2], 1.0f);
+        rc = dmalloc(s, &s->d_env, ne, false);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s->d_env, rgba.data(), ne * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        S.env = s->d_env; S.env_w = d->env_w; S.env_h = d->env_h;
+    }
+    S.traversal_mode = 3u;
+    if (d->mesh_xyz) {
+        std::vector<float4> v(d->mesh_nverts);
+        for (uint32_t i = 0; i < d->mesh_nverts; i++) v[i] = make_float4(d->mesh_xyz[3 * i], d->mesh_xyz[3 * i + 1], d->mesh_xyz[3 * i + 2], 0.0f);
+        rc = dmalloc(s, &s->d_mesh_v, (size_t)d->mesh_nverts, false);
+        if (rc) return rc;
+        rc = dmalloc(s, &s->d_mesh_i, (size_t)d->mesh_ntris * 3, false);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s->d_mesh_v, v.data(), v.size() * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->d_mesh_i, d->mesh_idx, (size_t)d->mesh_ntris * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        S.mesh_v = s->d_mesh_v; S.mesh_i = s->d_mesh_i;
+        S.mesh_index_count = d->mesh_ntris * 3u; S.mesh_nverts = d->mesh_nverts;
+        S.traversal_mode = 0u;                                   // TraversalMode::Hybrid, render_terrain.rs:681-685
+    }
+
+    // ---- the reference's 512 MiB working-set gate, opt-in (render_terrain.rs:785-888) ----
+    if (d->compat_512mib_gate) {
+        uint64_t total = (uint64_t)npx * (16 + 8 + 80 * 3 + 16 * 2 + 8 + 48) + s->pyramid_bytes_ref +
+                         (d->env_rgb ? (uint64_t)d->env_w * d->env_h * 16 : 16) + (uint64_t)d->mesh_nverts * 16 +
+                         (uint64_t)d->mesh_ntris * 12 + 96 + 32 + 80 + 96 + 24 + 32 + 32 + 48;
+        const uint64_t limit = 512ull * 1024 * 1024;
+        if (total > limit)
+            return fail(F3D_ERR_BUDGET,
+                        "terrain PT exceeds the memory budget before rendering: tracked total %llu (host-visible %llu) > limit %llu",
+                        (unsigned long long)total, 0ull, (unsigned long long)limit);
+    }
+
+    // ---- per-pixel state ----
+    if ((rc = dmalloc(s, &s->d_accum, npx, true))) return rc;
+    if ((rc = dmalloc(s, &s->d_welford, npx, true))) return rc;
+    if ((rc = dmalloc(s, &s->d_resv[0], npx, true))) return rc;
+    if ((rc = dmalloc(s, &s->d_resv[1], npx, true))) return rc;
+    if ((rc = dmalloc(s, &s->d_pixflags, npx, true))) return rc;
+    if ((rc = dmalloc(s, &s->d_aov_normal, npx, true))) return rc;
+    if ((rc = dmalloc(s, &s->d_aov_depth, npx, true))) return rc;
+    if ((rc = dmalloc(s, &s->d_counters, (size_t)4, true))) return rc;
+    if ((rc = dmalloc(s, &s->d_gate, (size_t)4, true))) return rc;
+    CUDA_TRY(cudaMallocHost(&s->h_gate, 4 * sizeof(uint32_t)));
+    s->host_visible_bytes += 4 * sizeof(uint32_t);
+    P.accum = s->d_accum; P.welford = s->d_welford; P.pixflags = s->d_pixflags; P.counters = s->d_counters;
+    P.resv_in = s->d_resv[1]; P.resv_out = s->d_resv[0];
+    P.peer_up = nullptr; P.peer_down = nullptr;
+
+    // ---- one-shot G-buffer / centre-ray AOV pass (render_terrain.rs:1091-1121) ----
+    GbufferOut G{s->d_pixflags, s->d_aov_normal, s->d_aov_depth};
+    k_gbuffer<<<s->grid, kTileW * kTileH, 0, s->stream>>>(P, G);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->setup_ms = ms;
+    return 0;
+}
+
+extern "C" int f3d_session_create(const f3d_terrain_desc* desc, void* cuda_stream, f3d_session** out_session) {
+    g_err[0] = 0;
+    if (!desc || !out_session) return fail(F3D_ERR_ARGUMENT, "null argument");
+    *out_session = nullptr;
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    f3d_session* s = new f3d_session();
+    rc = session_create_impl(desc, cuda_stream, s);
+    if (rc) { session_free(s); return rc; }
+    *out_session = s;
+    return 0;
+}
+
+extern "C" void f3d_session_destroy(f3d_session* s) { session_free(s); }
+
+extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
+    if (!s) return fail(F3D_ERR_ARGUMENT, "null session");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    for (uint32_t i = 0; i < n; i++) {
+        FrameParams& P = s->P;
+        P.frame_index = s->frames;
+        P.resv_in = s->d_resv[(s->frames + 1u) & 1u];
+        P.resv_out = s->d_resv[s->frames & 1u];
+        if (s->n_peer_ptrs) {
+            // peer images of the buffer being written this frame (see f3d_session_ipc_import)
+            const uint32_t up = (P.part_rank + P.part_world - 1u) % P.part_world, down = (P.part_rank + 1u) % P.part_world;
+            P.peer_up = (float4*)s->peer_ptrs[up * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
+            P.peer_down = (float4*)s->peer_ptrs[down * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
+        }
+        k_frame<<<s->grid, kTileW * kTileH, 0, s->stream>>>(P);
+        s->launches++;
+        s->frames++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    return 0;
+}
+
+extern "C" int f3d_session_sync(f3d_session* s) {
+    if (!s) return fail(F3D_ERR_ARGUMENT, "null session");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int f3d_session_last_frames_ms(f3d_session* s, double* ms) {
+    if (!s || !ms) return fail(F3D_ERR_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaEventSynchronize(s->ev1));
+    float f = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, s->ev0, s->ev1));
+    *ms = f;
+    return 0;
+}
+
+extern "C" int f3d_session_frames(const f3d_session* s, uint32_t* frames) {
+    if (!s || !frames) return fail(F3D_ERR_ARGUMENT, "null argument");
+    *frames = s->frames;
+    return 0;
+}
+
+extern "C" int f3d_session_variance(f3d_session* s, float* vmax, int32_t* nonfinite) {
+    if (!s || !vmax || !nonfinite) return fail(F3D_ERR_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (s->frames == 0) return fail(F3D_ERR_ARGUMENT, "no frames rendered");
+    const uint32_t n_window = ((s->frames - 1u) % 32u) + 1u;   // render_terrain.rs:1208
+    CUDA_TRY(cudaMemsetAsync(s->d_gate, 0, 2 * sizeof(uint32_t), s->stream));
+    k_variance<<<s->grid, kTileW * kTileH, 0, s->stream>>>(s->P, (float)n_window, s->d_gate);
+    s->launches++;
+    CUDA_TRY(cudaMemcpyAsync(s->h_gate, s->d_gate, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    memcpy(vmax, &s->h_gate[0], 4);
+    *nonfinite = (int32_t)s->h_gate[1];
+    return 0;
+}
+
+static int resolve_device_impl(f3d_session* s, void* d_rgba, void* d_albedo, void* d_normal, void* d_depth,
+                               int32_t check_validity) {
+    if (s->frames == 0) return fail(F3D_ERR_ARGUMENT, "no frames rendered");
+    FrameParams P = s->P;
+    P.resv_in = s->d_resv[(s->frames + 1u) & 1u];   // out of the last frame
+    ResolveOut R{};
+    R.rgba = (uint8_t*)d_rgba; R.albedo = (float*)d_albedo; R.normal = (float*)d_normal; R.depth = (float*)d_depth;
+    R.aov_normal = s->d_aov_normal; R.aov_depth = s->d_aov_depth;
+    R.validity = s->d_gate + 2;
+    R.last_frame = s->frames - 1u;
+    CUDA_TRY(cudaMemsetAsync(s->d_gate + 2, 0, 2 * sizeof(uint32_t), s->stream));
+    k_resolve<<<s->grid, kTileW * kTileH, 0, s->stream>>>(P, R);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (check_validity) {
+        CUDA_TRY(cudaMemcpyAsync(s->h_gate + 2, s->d_gate + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (s->h_gate[2]) return fail(F3D_ERR_RENDER, "terrain PT reservoir bookkeeping produced non-finite values");
+        const bool require = s->sun_el_deg > 0.0f && s->sun_intensity > 0.0f &&
+                             (s->sun_color[0] > 0.0f || s->sun_color[1] > 0.0f || s->sun_color[2] > 0.0f);
+        // With a row partition a rank may own only sky; the launcher ORs validity across ranks.
+        if (require && !s->h_gate[3] && s->P.part_world == 1)
+            return fail(F3D_ERR_RENDER,
+                        "terrain PT ReSTIR reuse chain produced no valid reservoirs for a sun-lit scene — temporal/spatial reuse is broken");
+    }
+    return 0;
+}
+
+extern "C" int f3d_session_resolve_device(f3d_session* s, void* d_rgba, void* d_albedo, void* d_normal, void* d_depth,
+                                          int32_t check_validity) {
+    if (!s) return fail(F3D_ERR_ARGUMENT, "null session");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return resolve_device_impl(s, d_rgba, d_albedo, d_normal, d_depth, check_validity);
+}
+
+static int fill_stats(f3d_session* s, f3d_terrain_out* out) {
+    unsigned long long c[4];
+    CUDA_TRY(cudaMemcpyAsync(c, s->d_counters, sizeof c, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    out->rays_primary = c[0]; out->rays_shadow = c[1]; out->rays_ibl = c[2]; out->nodes_popped = c[3];
+    out->frames = s->frames;
+    out->minmax_pyramid_bytes = s->pyramid_bytes_ref;
+    out->gpu_resource_bytes = s->gpu_bytes;
+    out->peak_host_visible_bytes = s->host_visible_bytes;
+    out->setup_ms = s->setup_ms; out->frames_ms = s->frames_ms; out->readback_ms = s->readback_ms;
+    out->kernel_launches = s->launches;
+    return 0;
+}
+
+extern "C" int f3d_session_stats(f3d_session* s, f3d_terrain_out* out) {
+    if (!s || !out) return fail(F3D_ERR_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    return fill_stats(s, out);
+}
+
+extern "C" int f3d_session_resolve_host(f3d_session* s, f3d_terrain_out* out) {
+    if (!s || !out) return fail(F3D_ERR_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t npx = (size_t)s->P.W * s->P.H;
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    int rc;
+    if (out->rgba && !s->d_rgba && (rc = dmalloc(s, &s->d_rgba, npx * 4, false))) return rc;
+    if (out->albedo && !s->d_albedo && (rc = dmalloc(s, &s->d_albedo, npx * 3, false))) return rc;
+    if (out->normal && !s->d_normal && (rc = dmalloc(s, &s->d_normal, npx * 3, false))) return rc;
+    if (out->depth && !s->d_depth && (rc = dmalloc(s, &s->d_depth, npx, false))) return rc;
+    rc = resolve_device_impl(s, out->rgba ? s->d_rgba : nullptr, out->albedo ? s->d_albedo : nullptr,
+                             out->normal ? s->d_normal : nullptr, out->depth ? s->d_depth : nullptr, 1);
+    if (rc) return rc;
+    // pinned staging (the "host-visible" allocation of this backend), then plain memcpy into the caller's arrays
+    const size_t need = npx * 16;
+    if (s->h_stage_bytes < need) {
+        if (s->h_stage) cudaFreeHost(s->h_stage);
+        CUDA_TRY(cudaMallocHost(&s->h_stage, need));
+        s->h_stage_bytes = need;
+        s->host_visible_bytes = std::max<uint64_t>(s->host_visible_bytes, need + 16);
+    }
+    auto pull = [&](void* host, const void* dev, size_t bytes) -> int {
+        if (!host) return 0;
+        CUDA_TRY(cudaMemcpyAsync(s->h_stage, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        memcpy(host, s->h_stage, bytes);
+        return 0;
+    };
+    if ((rc = pull(out->rgba, s->d_rgba, npx * 4))) return rc;
+    if ((rc = pull(out->albedo, s->d_albedo, npx * 12))) return rc;
+    if ((rc = pull(out->normal, s->d_normal, npx * 12))) return rc;
+    if ((rc = pull(out->depth, s->d_depth, npx * 4))) return rc;
+    if ((rc = pull(out->accum, s->d_accum, npx * 16))) return rc;
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->readback_ms = ms;
+    return fill_stats(s, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NVLink peer halo exchange
+// ------------------------------------------------------------------------------------------------
+extern "C" int f3d_session_ipc_export(f3d_session* s, uint8_t* handles) {
+    if (!s || !handles) return fail(F3D_ERR_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == F3D_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, s->d_resv[0]));
+    memcpy(handles, &h, sizeof h);
+    CUDA_TRY(cudaIpcGetMemHandle(&h, s->d_resv[1]));
+    memcpy(handles + F3D_IPC_HANDLE_BYTES, &h, sizeof h);
+    memset(handles + 2 * F3D_IPC_HANDLE_BYTES, 0, F3D_IPC_HANDLE_BYTES);   // reserved
+    return 0;
+}
+
+extern "C" int f3d_session_ipc_import(f3d_session* s, const uint8_t* all) {
+    if (!s || !all) return fail(F3D_ERR_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const uint32_t world = s->P.part_world;
+    if (world < 2) return 0;
+    if (world > 8) return fail(F3D_ERR_ARGUMENT, "part_world > 8 not supported");
+    for (uint32_t r = 0; r < world; r++) {
+        if (r == s->P.part_rank) continue;
+        const uint32_t up = (s->P.part_rank + world - 1u) % world, down = (s->P.part_rank + 1u) % world;
+        if (r != up && r != down) continue;
+        for (int k = 0; k < 2; k++) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all + ((size_t)r * F3D_IPC_HANDLES_PER_RANK + k) * F3D_IPC_HANDLE_BYTES, sizeof h);
+            void* p = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            s->peer_ptrs[r * F3D_IPC_HANDLES_PER_RANK + k] = p;
+        }
+    }
+    s->n_peer_ptrs = (int)world * F3D_IPC_HANDLES_PER_RANK;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-call drop-in: the driver loop of render_terrain.rs:1123-1244
+// ------------------------------------------------------------------------------------------------
+extern "C" int f3d_terrain_reference_render(const f3d_terrain_desc* desc, f3d_terrain_out* out) {
+    g_err[0] = 0;
+    if (!desc || !out) return fail(F3D_ERR_ARGUMENT, "null argument");
+    f3d_session* s = nullptr;
+    int rc = f3d_session_create(desc, nullptr, &s);
+    if (rc) return rc;
+    float variance = INFINITY;
+    bool converged = false;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    cudaEventRecord(t0, s->stream);
+    while (s->frames < desc->max_frames) {
+        // run up to the next gate: frames % 32 == 0 or frames == max_frames (:1206-1207)
+        uint32_t to_gate = 32u - (s->frames % 32u);
+        uint32_t n = std::min(to_gate, desc->max_frames - s->frames);
+        rc = f3d_session_render_frames(s, n);
+        if (rc) break;
+        const uint32_t n_window = ((s->frames - 1u) % 32u) + 1u;
+        if (n_window >= 2u) {
+            int32_t bad = 0;
+            rc = f3d_session_variance(s, &variance, &bad);
+            if (rc) break;
+            if (bad) { rc = fail(F3D_ERR_RENDER, "terrain PT produced non-finite variance (NaN in accumulation)"); break; }
+            if (s->frames >= desc->min_frames && variance < desc->variance_threshold) { converged = true; break; }
+        }
+    }
+    if (!rc) {
+        cudaEventRecord(t1, s->stream);
+        cudaStreamSynchronize(s->stream);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        s->frames_ms = ms;
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    if (!rc && !converged)
+        rc = fail(F3D_ERR_RENDER,
+                  "terrain PT did not converge: per-pixel luminance variance %.3e over the last 32-frame window after %u frames (threshold %.1e); raise max_frames or simplify the scene — refusing to return a fake reference",
+                  (double)variance, s->frames, (double)desc->variance_threshold);
+    if (!rc) rc = f3d_session_resolve_host(s, out);
+    if (!rc) { out->variance = variance; out->converged = 1; }
+    f3d_session_destroy(s);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KAT seams
+// ------------------------------------------------------------------------------------------------
+static int select_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(F3D_ERR_DEVICE, "no CUDA device available: forge3d_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(F3D_ERR_DEVICE, "CUDA device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    return 0;
+}
+
+extern "C" int f3d_build_minmax(const float* heights, uint32_t w, uint32_t h, int32_t device, uint32_t* dims,
+                                float* levels_out, uint64_t cap) {
+    g_err[0] = 0;
+    if (!heights || !dims) { fail(F3D_ERR_ARGUMENT, "null argument"); return -F3D_ERR_ARGUMENT; }
+    if (w < 2 || h < 2) { fail(F3D_ERR_UPLOAD, "terrain heightfield must be at least 2x2 texels, got %ux%u", w, h); return -F3D_ERR_UPLOAD; }
+    int rc = select_device(device);
+    if (rc) return -rc;
+    DeviceTerrain T;
+    uint64_t launches = 0;
+    rc = build_device_terrain(heights, w, h, 1.0f, nullptr, &T, &launches);
+    if (rc) { T.release(); return -rc; }
+    for (int l = 0; l < T.nlevels; l++) { dims[2 * l] = T.dims[l][0]; dims[2 * l + 1] = T.dims[l][1]; }
+    if (levels_out) {
+        if (cap < T.mm_total * 2) { T.release(); fail(F3D_ERR_ARGUMENT, "levels_out too small"); return -F3D_ERR_ARGUMENT; }
+        if (cudaMemcpy(levels_out, T.mm_base, T.mm_total * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            T.release(); fail(F3D_ERR_DEVICE, "copy failed"); return -F3D_ERR_DEVICE;
+        }
+    }
+    int n = T.nlevels;
+    T.release();
+    return n;
+}
+
+extern "C" int f3d_trace_rays(const float* heights, uint32_t w, uint32_t h, const float spacing[2], const float origin_xz[2],
+                              float exaggeration, float inv_two_r_prime, int32_t curvature_enabled, const float* rays,
+                              uint64_t n, int32_t any_hit, int32_t apply_curvature, int32_t device, uint8_t* hit, float* t,
+                              float* normal) {
+    g_err[0] = 0;
+    if (!heights || !rays || !hit || !t) return fail(F3D_ERR_ARGUMENT, "null argument");
+    if (w < 2 || h < 2) return fail(F3D_ERR_UPLOAD, "terrain heightfield must be at least 2x2 texels, got %ux%u", w, h);
+    int rc = select_device(device);
+    if (rc) return rc;
+    DeviceTerrain T;
+    uint64_t launches = 0;
+    rc = build_device_terrain(heights, w, h, exaggeration, nullptr, &T, &launches);
+    if (rc) { T.release(); return rc; }
+    SceneParams S{};
+    fill_scene_terrain(&S, T);
+    S.ox = origin_xz[0]; S.oz = origin_xz[1]; S.sx = spacing[0]; S.sz = spacing[1];
+    S.inv_two_r_prime = inv_two_r_prime; S.curvature_enabled = curvature_enabled ? 1u : 0u;
+    S.traversal_mode = 3u;
+    float4* d_rays = nullptr; uint8_t* d_hit = nullptr; float* d_t = nullptr; float* d_n = nullptr;
+    auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_hit); cudaFree(d_t); cudaFree(d_n); T.release(); };
+    if (n) {
+        if (cudaMalloc(&d_rays, n * 32) != cudaSuccess || cudaMalloc(&d_hit, n) != cudaSuccess ||
+            cudaMalloc(&d_t, n * 4) != cudaSuccess || cudaMalloc(&d_n, n * 12) != cudaSuccess) {
+            cleanup();
+            return fail(F3D_ERR_DEVICE, "device allocation failed");
+        }
+        cudaMemcpy(d_rays, rays, n * 32, cudaMemcpyHostToDevice);
+        k_trace_rays<<<(unsigned)((n + 127) / 128), 128>>>(S, d_rays, n, any_hit, apply_curvature, d_hit, d_t, normal ? d_n : nullptr);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { cleanup(); return fail(F3D_ERR_DEVICE, "trace kernel failed: %s", cudaGetErrorString(e)); }
+        cudaMemcpy(hit, d_hit, n, cudaMemcpyDeviceToHost);
+        cudaMemcpy(t, d_t, n * 4, cudaMemcpyDeviceToHost);
+        if (normal) cudaMemcpy(normal, d_n, n * 12, cudaMemcpyDeviceToHost);
+    }
+    cleanup();
+    return 0;
+}

@@ -1,0 +1,491 @@
+// forge3d_b200/csrc/f3d_kernels.cuh
+// CUDA kernels of the B200 terrain path tracer.  What the reference does in four WGSL dispatches
+// per frame (main_terrain -> pt_restir_temporal -> pt_restir_spatial, plus a one-off
+// main_terrain_gbuffer) is restructured here into ONE fused frame kernel:
+//
+//   k_frame(f):  prev  = spatial_reuse(out_{f-1})      [pt_restir_spatial.wgsl:158-224, frame f-1's pass]
+//                prev  = M-clamp(prev)                 [hybrid_terrain_traversal.wgsl:452-462]
+//                spp x (primary, sun shadow, IBL occlusion) rays, candidate reservoir   [:467-555]
+//                out_f = temporal_reuse(prev, cand)    [pt_restir_temporal.wgsl:54-109]
+//                accum += mean radiance; windowed Welford                               [:557-574]
+//
+// so the `prev` and `curr` reservoir buffers of the reference never exist in HBM, and `out` is a
+// 16-byte record per pixel instead of 80 bytes: on this path every populated LightSample is the
+// one directional sun (direction == normalize(light_dir) bit-for-bit, light_index 0, intensity
+// constant), `position` is never read by anything that reaches an output, and the receiving
+// pixel's G-buffer test N.wi > 0 (pt_restir_spatial.wgsl:73-75) is a per-pixel constant that is
+// folded into one bit by k_gbuffer.  The RGBA16F beauty store of every frame (:576-579) is dead
+// until the last frame and is done once by k_resolve.  All arithmetic that reaches an output
+// follows the numerics contract, so results are bit-identical to the CPU oracle.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "f3d_trace.cuh"
+
+namespace f3d {
+
+constexpr int kTileW = 16, kTileH = 16;      // CTA pixel tile; warps own 8x4 sub-tiles
+constexpr int kMaxPeers = 2;                 // row-block neighbours (above / below)
+
+struct FrameParams {
+    SceneParams scene;
+    uint32_t W, H, frame_index, spp, window;
+    float cam_origin[3], cam_right[3], cam_up[3], cam_forward[3];
+    float half_w, half_h, exposure;
+    uint32_t seed_hi, seed_lo;
+    float light_dir[3], light_color[3];
+    // image-row partition: this device owns row blocks b with b % world == rank
+    uint32_t part_rank, part_world, block_rows, tiles_per_block, nblocks;
+    // per-pixel state (full-image arrays, only owned rows + 3-row halos are touched)
+    float4* accum;
+    float2* welford;
+    const float4* resv_in;     // out_{f-1}: (w_sum, weight, target_pdf, bits(m | type<<31))
+    float4* resv_out;          // out_f
+    const uint8_t* pixflags;   // bit0: G-buffer normal faces the sun; bits1-2: centre-ray hit type
+    unsigned long long* counters;  // primary, shadow, ibl, nodes
+    // NVLink halo push: peer images of resv_out for the rank above / below (NULL = none)
+    float4* peer_up;
+    float4* peer_down;
+};
+
+__device__ __forceinline__ v3 ld3(const float* p) { return V3(p[0], p[1], p[2]); }
+
+// Camera ray, hybrid_terrain_traversal.wgsl:480-485 (and :584-588, :628-632 with zero jitter).
+__device__ __forceinline__ Ray camera_ray(const FrameParams& P, uint32_t gx, uint32_t gy, float jx, float jy) {
+    float ndc_x = fdiv((float)gx + 0.5f + jx, (float)P.W) * 2.0f - 1.0f;
+    float ndc_y = (1.0f - fdiv((float)gy + 0.5f + jy, (float)P.H)) * 2.0f - 1.0f;
+    v3 rd = normalize3(V3(ndc_x * P.half_w, ndc_y * P.half_h, -1.0f));
+    rd = normalize3((ld3(P.cam_right) * rd.x + ld3(P.cam_up) * rd.y) + (-ld3(P.cam_forward)) * rd.z);
+    Ray r;
+    r.o = ld3(P.cam_origin);
+    r.tmin = 1e-3f;
+    r.d = rd;
+    r.tmax = 1e30f;
+    return r;
+}
+
+// Maps (blockIdx, threadIdx) to a pixel of an owned row block.  Returns false when out of range.
+__device__ __forceinline__ bool owned_pixel(const FrameParams& P, uint32_t& gx, uint32_t& gy) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
+    const uint32_t lx = (warp & 1u) * 8u + (lane & 7u);
+    const uint32_t ly = (warp >> 1) * 4u + (lane >> 3);
+    const uint32_t owned_block = blockIdx.y / P.tiles_per_block;
+    const uint32_t tile_in_block = blockIdx.y % P.tiles_per_block;
+    const uint32_t b = owned_block * P.part_world + P.part_rank;
+    const uint32_t in_block_y = tile_in_block * kTileH + ly;
+    gx = blockIdx.x * kTileW + lx;
+    gy = b * P.block_rows + in_block_y;
+    return gx < P.W && gy < P.H && in_block_y < P.block_rows && b < P.nblocks;
+}
+
+struct Resv { float w_sum, weight, target_pdf; uint32_t m; bool type1; };
+
+__device__ __forceinline__ Resv unpack_resv(float4 v) {
+    Resv r;
+    r.w_sum = v.x; r.weight = v.y; r.target_pdf = v.z;
+    uint32_t b = __float_as_uint(v.w);
+    r.m = b & 0x7FFFFFFFu;
+    r.type1 = (b >> 31) != 0u;
+    return r;
+}
+__device__ __forceinline__ float4 pack_resv(const Resv& r) {
+    return make_float4(r.w_sum, r.weight, r.target_pdf, __uint_as_float(r.m | (r.type1 ? 0x80000000u : 0u)));
+}
+
+// consider_candidate (directional branch), pt_restir_spatial.wgsl:45-117.  One sun with importance 1:
+// p_sel = 1/max(1,1e-8) = 1 exactly.
+__device__ __forceinline__ void consider_candidate(const Resv& r, bool facing, float& Wsum, bool& chosen_type1,
+                                                   float& chosen_pdf, uint32_t& seed) {
+    if (r.m == 0u) return;
+    if (!r.type1) return;
+    if (!facing) return;
+    const float p_curr = 1.0f;
+    if (r.target_pdf <= 0.0f) return;
+    float w = r.w_sum * fdiv(p_curr, fmaxf(r.target_pdf, 1e-6f));
+    if (w <= 0.0f) return;
+    Wsum = Wsum + w;
+    float u = xorshift32(seed);
+    if (u < fdiv(w, Wsum)) {
+        chosen_type1 = true;
+        chosen_pdf = p_curr;
+    }
+}
+
+// pt_restir_spatial::main, pt_restir_spatial.wgsl:158-224, reading the compact `out` records.
+__device__ __forceinline__ Resv spatial_reuse(const FrameParams& P, const float4* __restrict__ resv, uint32_t x,
+                                              uint32_t y, bool facing, uint32_t pass_frame) {
+    const uint32_t W = P.W, H = P.H;
+    const uint32_t idx = y * W + x;
+    uint32_t seed = (P.seed_hi ^ pass_frame) + idx * 1664525u + 1013904223u;
+    const Resv r_self = unpack_resv(__ldcg(resv + idx));
+    bool chosen_type1 = r_self.type1;
+    float chosen_pdf = r_self.target_pdf;
+    float Wsum = 0.0f;
+    uint32_t m_total = 0u;
+    consider_candidate(r_self, facing, Wsum, chosen_type1, chosen_pdf, seed);
+    m_total += r_self.m;
+#pragma unroll 1
+    for (uint32_t i = 0; i < 8u; i++) {
+        int rx = (int)floorf(xorshift32(seed) * 7.0f) - 3;
+        int ry = (int)floorf(xorshift32(seed) * 7.0f) - 3;
+        if (rx == 0 && ry == 0) continue;
+        int nxi = min(max((int)x + rx, 0), (int)W - 1);
+        int nyi = min(max((int)y + ry, 0), (int)H - 1);
+        const Resv rn = unpack_resv(__ldcg(resv + (uint32_t)nyi * W + (uint32_t)nxi));
+        consider_candidate(rn, facing, Wsum, chosen_type1, chosen_pdf, seed);
+        m_total += rn.m;
+    }
+    Resv o;
+    o.type1 = chosen_type1;
+    o.target_pdf = chosen_pdf;
+    o.w_sum = Wsum;
+    o.m = m_total;
+    o.weight = (o.w_sum > 0.0f && o.target_pdf > 0.0f) ? fdiv(o.w_sum, (float)o.m * o.target_pdf) : 0.0f;
+    return o;
+}
+
+// pt_restir_temporal::main, pt_restir_temporal.wgsl:54-109
+__device__ __forceinline__ Resv temporal_reuse(const Resv& rp, const Resv& rc) {
+    const bool prev_valid = rp.m > 0u && rp.weight > 0.0f && rp.target_pdf > 0.0f;
+    const bool curr_valid = rc.m > 0u && rc.weight > 0.0f && rc.target_pdf > 0.0f;
+    if (!prev_valid) return rc;
+    if (!curr_valid) return rp;
+    Resv ro;
+    const bool choose_prev = rp.weight > rc.weight;
+    ro.type1 = choose_prev ? rp.type1 : rc.type1;
+    ro.target_pdf = choose_prev ? rp.target_pdf : rc.target_pdf;
+    ro.m = rp.m + rc.m;
+    ro.w_sum = rp.w_sum + rc.w_sum;
+    ro.weight = (ro.w_sum > 0.0f && ro.target_pdf > 0.0f) ? fdiv(ro.w_sum, (float)ro.m * ro.target_pdf) : 0.0f;
+    return ro;
+}
+
+__device__ __forceinline__ void warp_add_counters(unsigned long long* counters, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                  uint32_t c3) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        c0 += __shfl_xor_sync(0xFFFFFFFFu, c0, off);
+        c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, off);
+        c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, off);
+        c3 += __shfl_xor_sync(0xFFFFFFFFu, c3, off);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        if (c0) atomicAdd(counters + 0, (unsigned long long)c0);
+        if (c1) atomicAdd(counters + 1, (unsigned long long)c1);
+        if (c2) atomicAdd(counters + 2, (unsigned long long)c2);
+        if (c3) atomicAdd(counters + 3, (unsigned long long)c3);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_frame: one accumulation frame (see the file header).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTileW* kTileH) k_frame(const __grid_constant__ FrameParams P) {
+    uint32_t gx, gy;
+    const bool active = owned_pixel(P, gx, gy);
+    uint32_t n_primary = 0, n_shadow = 0, n_ibl = 0, n_nodes = 0;
+    if (active) {
+        const SceneParams& S = P.scene;
+        const uint32_t pix = gy * P.W + gx;
+        const bool facing = (P.pixflags[pix] & 1u) != 0u;
+
+        // ---- merged reservoir from last frame's reuse chain + M-clamp (:452-465) ----
+        Resv prev_r;
+        prev_r.w_sum = 0.0f; prev_r.weight = 0.0f; prev_r.target_pdf = 0.0f; prev_r.m = 0u; prev_r.type1 = false;
+        if (P.frame_index > 0u) prev_r = spatial_reuse(P, P.resv_in, gx, gy, facing, P.frame_index - 1u);
+        if (prev_r.m > 512u) {
+            float scale = fdiv(512.0f, (float)prev_r.m);
+            prev_r.w_sum = prev_r.w_sum * scale;
+            prev_r.m = 512u;
+            if (prev_r.target_pdf > 0.0f) prev_r.weight = fdiv(prev_r.w_sum, (float)prev_r.m * prev_r.target_pdf);
+        }
+        const bool prev_valid = P.frame_index > 0u && prev_r.m > 0u && prev_r.weight > 0.0f &&
+                                prev_r.target_pdf > 0.0f && prev_r.type1;
+
+        uint32_t rng = P.seed_hi ^ (gx * 1664525u) ^ (gy * 1013904223u) ^ (P.frame_index * 92837111u) ^ P.seed_lo;
+        const uint32_t spp = max(P.spp, 1u);
+        const v3 light_color = ld3(P.light_color);
+        const v3 wi = normalize3(ld3(P.light_dir));
+        // every populated sample stores direction == wi; the shader re-normalises it (:520)
+        const v3 sun_dir = prev_valid ? normalize3(wi) : wi;
+        const float reuse_w = prev_valid ? clampf(prev_r.weight, 0.0f, 4.0f) : 1.0f;
+
+        v3 frame_radiance = V3(0, 0, 0);
+        Resv cand;
+        cand.w_sum = 0.0f; cand.weight = 0.0f; cand.target_pdf = 0.0f; cand.m = 0u; cand.type1 = false;
+
+#pragma unroll 1
+        for (uint32_t s = 0; s < spp; s++) {
+            const float jx = tent_offset(xorshift32(rng)) * 0.5f;
+            const float jy = tent_offset(xorshift32(rng)) * 0.5f;
+            const Ray ray = camera_ray(P, gx, gy, jx, jy);
+            n_primary++;
+            const Hit hit = intersect_hybrid(S, ray, n_nodes);
+            if (hit.hit == 0u) {
+                frame_radiance = frame_radiance + env_radiance(S, ray.d);
+                continue;
+            }
+            const v3 n = hit.normal;
+            const v3 albedo = hit.hit_type == 3u ? ld3(S.albedo) : V3(0.7f, 0.7f, 0.8f);
+
+            const float ndotl = fmaxf(dot3(n, wi), 0.0f);
+            const float target_pdf = luminance((albedo * light_color) * ndotl);
+            if (target_pdf > 0.0f) {
+                cand.type1 = true;
+                cand.w_sum = cand.w_sum + target_pdf;
+                cand.m = cand.m + 1u;
+                cand.target_pdf = target_pdf;
+            }
+
+            v3 sun = V3(0, 0, 0);
+            const float nd = fmaxf(dot3(n, sun_dir), 0.0f);
+            const v3 shade_o = hit.point + n * 1e-3f;
+            if (nd > 0.0f) {
+                Ray sray;
+                sray.o = shade_o; sray.tmin = 1e-3f; sray.d = sun_dir; sray.tmax = 1e30f;
+                n_shadow++;
+                const float vis = occluded<true>(S, sray, n_nodes) ? 0.0f : 1.0f;
+                sun = (((albedo * light_color) * nd) * vis) * reuse_w;
+            }
+
+            const float u1 = xorshift32(rng);
+            const float u2 = xorshift32(rng);
+            const v3 ei = cosine_dir(n, u1, u2);
+            Ray eray;
+            eray.o = shade_o; eray.tmin = 1e-3f; eray.d = ei; eray.tmax = 1e30f;
+            n_ibl++;
+            const float env_vis = occluded<false>(S, eray, n_nodes) ? 0.0f : 1.0f;
+            const v3 ibl = (albedo * env_radiance(S, ei)) * env_vis;
+
+            frame_radiance = (frame_radiance + sun) + ibl;
+        }
+        const float fspp = (float)spp;
+        frame_radiance = V3(fdiv(frame_radiance.x, fspp), fdiv(frame_radiance.y, fspp), fdiv(frame_radiance.z, fspp));
+
+        // ---- finalise candidate, temporal reuse, publish out_f (+ NVLink halo push) ----
+        if (cand.m > 0u && cand.w_sum > 0.0f && cand.target_pdf > 0.0f)
+            cand.weight = fdiv(cand.w_sum, (float)cand.m * cand.target_pdf);
+        const float4 out_rec = pack_resv(temporal_reuse(prev_r, cand));
+        __stcg(P.resv_out + pix, out_rec);
+        if (P.part_world > 1u) {
+            const uint32_t b = gy / P.block_rows, in_y = gy - b * P.block_rows;
+            if (in_y < 3u && b > 0u && P.peer_up) __stcg(P.peer_up + pix, out_rec);
+            if (in_y + 3u >= P.block_rows && b + 1u < P.nblocks && P.peer_down) __stcg(P.peer_down + pix, out_rec);
+        }
+
+        // ---- accumulate + windowed Welford over the running-mean luminance (:557-574) ----
+        float4 acc = P.accum[pix];
+        acc.x = acc.x + frame_radiance.x;
+        acc.y = acc.y + frame_radiance.y;
+        acc.z = acc.z + frame_radiance.z;
+        acc.w = acc.w + 1.0f;
+        P.accum[pix] = acc;
+
+        const uint32_t window = max(P.window, 2u);
+        float2 wf = P.welford[pix];
+        if (P.frame_index % window == 0u) wf = make_float2(0.0f, 0.0f);
+        const float mean_lum = luminance(V3(fdiv(acc.x, acc.w), fdiv(acc.y, acc.w), fdiv(acc.z, acc.w)));
+        const float k = (float)(P.frame_index % window) + 1.0f;
+        const float delta = mean_lum - wf.x;
+        const float mean = wf.x + fdiv(delta, k);
+        const float m2 = wf.y + delta * (mean_lum - mean);
+        P.welford[pix] = make_float2(mean, m2);
+    }
+    warp_add_counters(P.counters, n_primary, n_shadow, n_ibl, n_nodes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_gbuffer: unjittered centre ray per pixel.  Serves both main_terrain_gbuffer (:619-644) and the
+// frame-0 AOV block of main_terrain (:583-609), which trace the identical ray.
+// ---------------------------------------------------------------------------------------------
+struct GbufferOut {
+    uint8_t* pixflags;     // bit0 facing, bits1-2 hit type (0 miss, 1 terrain, 2 mesh)
+    ushort4* aov_normal;   // RGBA16F normal (alpha unused)
+    float* aov_depth;      // R32F, qNaN 0x7fc00000 on miss
+};
+
+__global__ void __launch_bounds__(kTileW* kTileH) k_gbuffer(const __grid_constant__ FrameParams P, GbufferOut G) {
+    uint32_t gx, gy;
+    if (!owned_pixel(P, gx, gy)) return;
+    const uint32_t pix = gy * P.W + gx;
+    uint32_t nodes = 0;
+    const Ray ray = camera_ray(P, gx, gy, 0.0f, 0.0f);
+    const Hit hit = intersect_hybrid(P.scene, ray, nodes);
+    // ReSTIR G-buffer record: hit -> (normal, 1); miss -> (0,0,1,1)  (:635-643)
+    const v3 nr = hit.hit ? hit.normal : V3(0.0f, 0.0f, 1.0f);
+    const v3 N = normalize3(nr);
+    const v3 wi_s = normalize3(normalize3(ld3(P.light_dir)));   // normalize(r.sample.direction), sample dir = wi
+    const bool facing = fmaxf(dot3(N, wi_s), 0.0f) > 0.0f;
+    uint8_t flags = facing ? 1u : 0u;
+    if (hit.hit) flags |= (hit.hit_type == 3u ? 1u : 2u) << 1;
+    G.pixflags[pix] = flags;
+    ushort4 n16;
+    n16.x = __half_as_ushort(__float2half_rn(hit.hit ? hit.normal.x : 0.0f));
+    n16.y = __half_as_ushort(__float2half_rn(hit.hit ? hit.normal.y : 0.0f));
+    n16.z = __half_as_ushort(__float2half_rn(hit.hit ? hit.normal.z : 0.0f));
+    n16.w = __half_as_ushort(__float2half_rn(1.0f));
+    G.aov_normal[pix] = n16;
+    G.aov_depth[pix] = hit.hit ? hit.t : __uint_as_float(0x7fc00000u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_variance: the convergence read-back of render_terrain.rs:1206-1233 reduced on the device:
+// out[0] = bits(max over owned pixels of m2/(n-1)) (non-negative floats order as uints),
+// out[1] != 0 when any m2 is non-finite.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTileW* kTileH) k_variance(const __grid_constant__ FrameParams P, float n_window,
+                                                             uint32_t* __restrict__ out) {
+    uint32_t gx, gy;
+    float v = 0.0f;
+    uint32_t bad = 0u;
+    if (owned_pixel(P, gx, gy)) {
+        const float m2 = P.welford[gy * P.W + gx].y;
+        if (!isfinite(m2)) bad = 1u;
+        else v = fmaxf(0.0f, fdiv(m2, n_window - 1.0f));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, off));
+        bad |= __shfl_xor_sync(0xFFFFFFFFu, bad, off);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        if (v > 0.0f) atomicMax(out + 0, __float_as_uint(v));
+        if (bad) atomicOr(out + 1, 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_resolve: last frame's reuse pass + reservoir validity (render_terrain.rs:1313-1337), beauty
+// resolve mean -> Reinhard -> RGBA16F -> u8 (hybrid_kernel.wgsl:109-112, render_terrain.rs:1358-1366)
+// and AOV decode (albedo/normal f16 -> f32, depth f32).
+// ---------------------------------------------------------------------------------------------
+struct ResolveOut {
+    uint8_t* rgba;       // W*H*4 or NULL
+    float* albedo;       // W*H*3 or NULL
+    float* normal;       // W*H*3 or NULL
+    float* depth;        // W*H   or NULL
+    const ushort4* aov_normal;
+    const float* aov_depth;
+    uint32_t* validity;  // [0] |= 1 non-finite bookkeeping, [1] |= 1 some valid reservoir
+    uint32_t last_frame; // frames - 1
+};
+
+__device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
+
+__global__ void __launch_bounds__(kTileW* kTileH) k_resolve(const __grid_constant__ FrameParams P, ResolveOut R) {
+    uint32_t gx, gy;
+    uint32_t nonfinite = 0u, valid = 0u;
+    if (owned_pixel(P, gx, gy)) {
+        const uint32_t pix = gy * P.W + gx;
+        const uint8_t flags = P.pixflags[pix];
+        const Resv r = spatial_reuse(P, P.resv_in, gx, gy, (flags & 1u) != 0u, R.last_frame);
+        if (!(isfinite(r.w_sum) && isfinite(r.weight) && isfinite(r.target_pdf))) nonfinite = 1u;
+        if (r.m > 0u && r.weight > 0.0f && r.target_pdf > 0.0f) valid = 1u;
+        if (R.rgba) {
+            const float4 acc = P.accum[pix];
+            const float ch[3] = {acc.x, acc.y, acc.z};
+            uchar4 px;
+            uint8_t* pc = &px.x;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float mean = fdiv(ch[c], acc.w);
+                float exposed = mean * P.exposure;
+                float ldr = fdiv(exposed, 1.0f + exposed);
+                float v = f16_round(ldr);
+                pc[c] = (uint8_t)(clampf(v, 0.0f, 1.0f) * 255.0f + 0.5f);
+            }
+            px.w = 255;
+            reinterpret_cast<uchar4*>(R.rgba)[pix] = px;
+        }
+        const uint32_t hit_type = (flags >> 1) & 3u;
+        if (R.albedo) {
+            v3 a = hit_type == 1u ? ld3(P.scene.albedo) : (hit_type == 2u ? V3(0.7f, 0.7f, 0.8f) : V3(0, 0, 0));
+            R.albedo[3 * (size_t)pix + 0] = f16_round(a.x);
+            R.albedo[3 * (size_t)pix + 1] = f16_round(a.y);
+            R.albedo[3 * (size_t)pix + 2] = f16_round(a.z);
+        }
+        if (R.normal) {
+            const ushort4 n16 = R.aov_normal[pix];
+            R.normal[3 * (size_t)pix + 0] = __half2float(__ushort_as_half(n16.x));
+            R.normal[3 * (size_t)pix + 1] = __half2float(__ushort_as_half(n16.y));
+            R.normal[3 * (size_t)pix + 2] = __half2float(__ushort_as_half(n16.z));
+        }
+        if (R.depth) R.depth[pix] = R.aov_depth[pix];
+    }
+    nonfinite = __any_sync(0xFFFFFFFFu, nonfinite);
+    valid = __any_sync(0xFFFFFFFFu, valid);
+    if ((threadIdx.x & 31u) == 0u) {
+        if (nonfinite) atomicOr(R.validity + 0, 1u);
+        if (valid) atomicOr(R.validity + 1, 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pyramid build on the GPU (replaces the CPU loops of build_minmax_mips,
+// terrain_heightfield.rs:132-202).  min/max are exact, so the levels equal the CPU build bit for bit.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_build_level0(const float* __restrict__ heights, uint32_t w, uint32_t h, uint32_t pw, uint32_t ph,
+                               float ex, float4* __restrict__ cells, float2* __restrict__ mm0) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= pw || y >= ph) return;
+    const uint32_t cw = w - 1u, ch = h - 1u;
+    float2 mm = make_float2(__int_as_float(0x7f800000), __int_as_float(0xff800000));
+    if (x < cw && y < ch) {
+        const size_t i00 = (size_t)y * w + x;
+        const float a = heights[i00] * ex, b = heights[i00 + 1] * ex, c = heights[i00 + w] * ex, d = heights[i00 + w + 1] * ex;
+        cells[(size_t)y * cw + x] = make_float4(a, b, c, d);
+        mm.x = fminf(fminf(fminf(a, b), c), d);
+        mm.y = fmaxf(fmaxf(fmaxf(a, b), c), d);
+    }
+    mm0[(size_t)y * pw + x] = mm;
+}
+
+__global__ void k_reduce_level(const float2* __restrict__ prev, uint32_t lw, uint32_t lh, float2* __restrict__ next,
+                               uint32_t nw, uint32_t nh) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nw || y >= nh) return;
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+#pragma unroll
+    for (uint32_t dy = 0; dy < 2u; dy++)
+#pragma unroll
+        for (uint32_t dx = 0; dx < 2u; dx++) {
+            const uint32_t sx = min(2u * x + dx, lw - 1u), sy = min(2u * y + dy, lh - 1u);
+            const float2 v = prev[(size_t)sy * lw + sx];
+            mn = fminf(mn, v.x);
+            mx = fmaxf(mx, v.y);
+        }
+    next[(size_t)y * nw + x] = make_float2(mn, mx);
+}
+
+// Non-finite scan of the uploaded heightfield (trust boundary of build_minmax_mips, :144-148).
+__global__ void k_check_finite(const float* __restrict__ v, size_t n, uint32_t* __restrict__ flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    uint32_t bad = 0u;
+    for (; i < n; i += stride)
+        if (!isfinite(v[i])) bad = 1u;
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31u) == 0u) atomicOr(flag, 1u);
+}
+
+// KAT seam: terrain_trace over a ray batch (terrain_heightfield.rs:1646-1671 test entry).
+__global__ void k_trace_rays(SceneParams S, const float4* __restrict__ rays, uint64_t n, int any_hit, int apply_curv,
+                             uint8_t* __restrict__ hit, float* __restrict__ t, float* __restrict__ normal) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = rays[2 * i], b = rays[2 * i + 1];
+    Ray r;
+    r.o = V3(a.x, a.y, a.z); r.tmin = a.w; r.d = V3(b.x, b.y, b.z); r.tmax = b.w;
+    uint32_t nodes = 0;
+    Hit h;
+    const bool curv = apply_curv && S.curvature_enabled;
+    if (any_hit) h = curv ? terrain_trace<true, true>(S, r, nodes) : terrain_trace<true, false>(S, r, nodes);
+    else h = curv ? terrain_trace<false, true>(S, r, nodes) : terrain_trace<false, false>(S, r, nodes);
+    hit[i] = (uint8_t)h.hit;
+    t[i] = h.t;
+    if (normal) { normal[3 * i] = h.normal.x; normal[3 * i + 1] = h.normal.y; normal[3 * i + 2] = h.normal.z; }
+}
+
+}  // namespace f3d

@@ -1,0 +1,158 @@
+/*
+ * include/forge3d_b200.h -- C ABI of libforge3d_b200.so, the B200-native backend for forge3d's
+ * path-traced DEM snapshot path.
+ *
+ * The reference has no C ABI on this path; its seam is the two Rust lines
+ *     let tracer = HybridPathTracer::new()?;
+ *     let out = tracer.render_terrain_reference(&desc)?;
+ * at /root/reference/src/py_functions/path_tracing/terrain_reference.rs:416-417.  Everything behind
+ * those lines (src/path_tracing/hybrid_compute/render_terrain.rs:563-1434 and the WGSL kernels it
+ * dispatches) is what this library replaces; everything above them (PyO3 marshalling, Python
+ * validation) stays.  INTEGRATION.md shows the Rust `extern "C"` shim a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only, no C++/torch types.  Inputs are borrowed for the
+ * duration of a call; outputs are caller-allocated.  Every function returns 0 on success or an
+ * f3d_status error class; the message (reference-compatible text, see
+ * tests/test_hybrid_terrain_pt.py:411-458 for the pinned substrings) is read with f3d_last_error(),
+ * which is thread-local.  There is NO CPU fallback: without a CUDA device every entry point fails
+ * with F3D_ERR_DEVICE.
+ */
+#ifndef FORGE3D_B200_H
+#define FORGE3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F3D_ABI_VERSION 1
+
+/* Error classes; mirror RenderError::{Render,Upload,Device,Budget}, src/core/error.rs:10-32. */
+typedef enum f3d_status {
+    F3D_OK = 0,
+    F3D_ERR_RENDER = 1,
+    F3D_ERR_UPLOAD = 2,
+    F3D_ERR_DEVICE = 3,
+    F3D_ERR_BUDGET = 4,
+    F3D_ERR_ARGUMENT = 5
+} f3d_status;
+
+/* EarthModel / RefractionModel::from_name, src/geo/refraction.rs:44-54,79-99 */
+enum { F3D_EARTH_FLAT = 0, F3D_EARTH_SPHERE = 1, F3D_EARTH_ELLIPSOID = 2 };
+enum { F3D_REFRACTION_NONE = 0, F3D_REFRACTION_BENNETT = 1, F3D_REFRACTION_SAEMUNDSSON = 2,
+       F3D_REFRACTION_EFFECTIVE_RADIUS = 3 };
+
+/* Replaces TerrainReferenceDesc, render_terrain.rs:239-282.  `atmosphere` (AETHER post) is a
+ * SURVEY section 8f "next" row and is not part of this ABI version. */
+typedef struct f3d_terrain_desc {
+    const float* heights;          /* host, row-major dem_h x dem_w (desc.heights) */
+    uint32_t dem_w, dem_h;
+    float spacing[2];
+    float exaggeration;
+    float albedo[3];
+    float cam_origin[3], cam_look_at[3], cam_up[3];
+    float fov_y_deg, exposure;
+    float sun_az_deg, sun_el_deg, sun_intensity, sun_color[3];
+    double observer_lat_deg, observer_lon_deg;   /* observer_geodetic_deg */
+    int32_t earth_model;           /* F3D_EARTH_* */
+    double sphere_radius_m;
+    int32_t refraction_model;      /* F3D_REFRACTION_* */
+    double refraction_k, pressure_mbar, temperature_c;
+    const float* env_rgb;          /* host, env_h x env_w x 3, or NULL (constant env) */
+    uint32_t env_w, env_h;
+    float env_intensity;
+    const float* mesh_xyz;         /* host, mesh_nverts x 3, or NULL */
+    uint32_t mesh_nverts;
+    const uint32_t* mesh_idx;      /* host, mesh_ntris x 3 */
+    uint32_t mesh_ntris;
+    uint32_t width, height, seed, spp, max_frames, min_frames;
+    float variance_threshold;
+    /* ---- extensions (zero = reference behaviour on one GPU) ---- */
+    int32_t device;                /* CUDA device ordinal */
+    int32_t compat_512mib_gate;    /* 1 = enforce the reference's 512 MiB working-set gate
+                                      (src/core/memory_tracker.rs:16, render_terrain.rs:875-888) */
+    uint32_t part_rank, part_world;/* image-row partition: this process renders row blocks
+                                      b with b % part_world == part_rank (world 0/1 = whole image) */
+    uint32_t part_block_rows;      /* rows per block (0 = default 32) */
+} f3d_terrain_desc;
+
+/* Replaces TerrainReferenceOutput, render_terrain.rs:285-299. */
+typedef struct f3d_terrain_out {
+    uint8_t* rgba;     /* host, W*H*4, caller allocated */
+    float* albedo;     /* host, W*H*3 */
+    float* normal;     /* host, W*H*3 */
+    float* depth;      /* host, W*H (NaN 0x7fc00000 = miss) */
+    float* accum;      /* optional host W*H*4 linear accumulation (rgb sum, frame count) or NULL */
+    uint32_t frames;
+    float variance;
+    int32_t converged;
+    uint64_t peak_host_visible_bytes, minmax_pyramid_bytes, gpu_resource_bytes;
+    /* measurement extensions */
+    uint64_t rays_primary, rays_shadow, rays_ibl, nodes_popped;
+    double setup_ms, frames_ms, readback_ms;
+    uint64_t kernel_launches;
+} f3d_terrain_out;
+
+/* One-call drop-in: validate, upload, build pyramid, accumulate until the windowed-variance
+ * gate passes (or error), resolve, read back.  == HybridPathTracer::render_terrain_reference. */
+int f3d_terrain_reference_render(const f3d_terrain_desc* desc, f3d_terrain_out* out);
+
+const char* f3d_last_error(void);
+int f3d_abi_version(void);
+int f3d_device_count(void);
+
+/* ---- session API: the same render split at the reference driver-loop's joints, so a host
+ * (bench, multi-GPU launcher) can keep inputs resident and time the frame loop alone. ---- */
+typedef struct f3d_session f3d_session;
+
+/* TerrainPtScene::new + uniform/buffer setup + main_terrain_gbuffer (render_terrain.rs:581-1121).
+ * `cuda_stream` is a cudaStream_t (NULL = the library's own stream). */
+int f3d_session_create(const f3d_terrain_desc* desc, void* cuda_stream, f3d_session** out_session);
+/* Enqueue `n` accumulation frames (one pass of render_terrain.rs:1127-1204 each); asynchronous. */
+int f3d_session_render_frames(f3d_session* s, uint32_t n);
+/* The convergence read-back (render_terrain.rs:1206-1233): max over owned pixels of m2/(n-1).
+ * Synchronises the stream.  *nonfinite != 0 means NaN/inf variance. */
+int f3d_session_variance(f3d_session* s, float* vmax, int32_t* nonfinite);
+/* Final reuse pass + reservoir validity (render_terrain.rs:1313-1337) + resolve of owned rows
+ * into DEVICE buffers (any may be NULL): rgba8 W*H*4, albedo/normal W*H*3 f32, depth W*H f32.
+ * Rows not owned by this partition are left untouched.  Asynchronous on the session stream,
+ * except that validity is checked (synchronises) when check_validity != 0. */
+int f3d_session_resolve_device(f3d_session* s, void* d_rgba, void* d_albedo, void* d_normal, void* d_depth,
+                               int32_t check_validity);
+/* Same, then copies to host buffers of `out` and fills the scalar fields. */
+int f3d_session_resolve_host(f3d_session* s, f3d_terrain_out* out);
+int f3d_session_frames(const f3d_session* s, uint32_t* frames);
+int f3d_session_stats(f3d_session* s, f3d_terrain_out* stats_only);   /* counters/bytes only; syncs */
+int f3d_session_sync(f3d_session* s);
+/* Device time (CUDA events on the session stream) of the most recent f3d_session_render_frames
+ * call; synchronises. */
+int f3d_session_last_frames_ms(f3d_session* s, double* ms);
+void f3d_session_destroy(f3d_session* s);
+
+/* ---- multi-GPU halo exchange over NVLink peer memory (exact mode) ----
+ * Each rank exports one 64-byte CUDA IPC handle per shared allocation; the launcher all-gathers
+ * them (any transport) and hands every rank the full table.  After import, the frame kernel
+ * stores the border rows of its temporal-reuse records directly into the neighbours' images. */
+#define F3D_IPC_HANDLE_BYTES 64
+#define F3D_IPC_HANDLES_PER_RANK 3
+int f3d_session_ipc_export(f3d_session* s, uint8_t* handles /* F3D_IPC_HANDLES_PER_RANK*64 bytes */);
+int f3d_session_ipc_import(f3d_session* s, const uint8_t* all_handles /* part_world * per-rank bytes */);
+
+/* ---- KAT seam (== the reference's test-only entry main_helios_production_terrain_trace_proof,
+ * src/path_tracing/hybrid_compute/terrain_heightfield.rs:1646-1671): run terrain_trace over a
+ * host ray batch (n x 8 floats: origin.xyz, tmin, direction.xyz, tmax) on the GPU. */
+int f3d_trace_rays(const float* heights, uint32_t dem_w, uint32_t dem_h, const float spacing[2],
+                   const float origin_xz[2], float exaggeration, float inv_two_r_prime,
+                   int32_t curvature_enabled, const float* rays, uint64_t n, int32_t any_hit,
+                   int32_t apply_curvature, int32_t device, uint8_t* hit, float* t, float* normal);
+
+/* GPU min-max pyramid build (== build_minmax_mips, terrain_heightfield.rs:132-202), copied back
+ * to the host for parity checks: dims[2*l..] and levels finest first, [min,max] pairs. */
+int f3d_build_minmax(const float* heights, uint32_t dem_w, uint32_t dem_h, int32_t device,
+                     uint32_t* dims, float* levels_out, uint64_t levels_capacity_floats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

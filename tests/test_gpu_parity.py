@@ -1,0 +1,161 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Everything here is exact: the numerics contract makes oracle and kernels agree
+bit for bit, so the comparisons are np.array_equal, not tolerances.  The only statistical check is
+the reference's own golden-image drift gate."""
+import numpy as np
+import pytest
+
+import _helpers as H
+from forge3d_b200 import _native, hybrid_render_terrain_reference
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _assert_same_render(got, ref, label=""):
+    assert got["frames"] == ref["frames"], label
+    assert np.array_equal(_bits(got["accum"]), _bits(ref["accum"])), f"{label}: accumulation differs"
+    assert np.array_equal(got["rgba"], ref["rgba"]), f"{label}: rgba differs"
+    assert np.array_equal(_bits(got["albedo"]), _bits(ref["albedo"])), f"{label}: albedo AOV differs"
+    assert np.array_equal(_bits(got["normal"]), _bits(ref["normal"])), f"{label}: normal AOV differs"
+    assert np.array_equal(_bits(got["depth"]), _bits(ref["depth"])), f"{label}: depth AOV differs"
+    for key in ("rays_primary", "rays_shadow", "rays_ibl", "nodes_popped"):
+        assert got[key] == ref[key], (label, key, got[key], ref[key])
+    assert np.float32(got["variance"]) == np.float32(ref["variance"]), label
+
+
+def _both(dem, w, h, cam, **kw):
+    got = _native.hybrid_render_terrain_reference(dem, w, h, cam, **kw, want_accum=True)
+    ref = oracle.render(dem, w, h, cam, **kw, want_accum=True)
+    return got, ref
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (37, 100), (2, 2), (3, 9), (129, 65)])
+def test_pyramid_bit_exact(shape):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    dem = (rng.standard_normal(shape) * 100).astype(np.float32)
+    g_levels, gcw, gch = _native.build_minmax(dem)
+    o_levels, ocw, och = oracle.build_minmax(dem)
+    assert (gcw, gch) == (ocw, och) and len(g_levels) == len(o_levels)
+    for g, o in zip(g_levels, o_levels):
+        assert g.shape == o.shape and np.array_equal(_bits(g), _bits(o))
+
+
+@pytest.mark.parametrize("any_hit,curv", [(True, True), (True, False), (False, False), (False, True)])
+def test_kat_rays_bit_exact(any_hit, curv):
+    h = H.curvature_fixture()
+    arb, mask = H.kat_rays(h)
+    rays = np.concatenate([arb, mask[::3]])
+    kw = dict(any_hit=any_hit, apply_curvature=curv, inv_two_r_prime=float(H.PROOF_INV_TWO_R), curvature_enabled=True)
+    gh, gt, gn = _native.trace_rays(h, (500.0, 500.0), (0.0, 0.0), 1.0, rays, **kw)
+    oh, ot, on = oracle.trace_rays(h, (500.0, 500.0), (0.0, 0.0), 1.0, rays, **kw)
+    assert np.array_equal(gh, oh)
+    assert np.array_equal(_bits(gt), _bits(ot))
+    assert np.array_equal(_bits(gn), _bits(on))
+    if any_hit and curv:  # the reference's KAT thresholds on the GPU path itself
+        brute = H.brute_2d_hit(h, arb)
+        assert int((brute & ~gh[:10_000]).sum()) == 0
+        assert int((~brute & gh[:10_000]).sum()) / 10_000.0 < 0.001
+
+
+def test_render_bit_exact_small():
+    dem = H.golden_dem()
+    kw = {**H.scene_kwargs(dem), "max_frames": 8, "min_frames": 8, "variance_threshold": 1e30}
+    got, ref = _both(dem, 64, 64, H.CAM, **kw)
+    _assert_same_render(got, ref, "64x64x8")
+    # non-multiple-of-tile image, non-square
+    got, ref = _both(dem, 75, 41, H.CAM, **kw)
+    _assert_same_render(got, ref, "75x41x8")
+
+
+def test_render_bit_exact_spp_and_window():
+    dem = H.golden_dem()
+    kw = {**H.scene_kwargs(dem), "max_frames": 40, "min_frames": 40, "variance_threshold": 1e30, "spp": 3}
+    got, ref = _both(dem, 96, 64, H.CAM, **kw)   # crosses a Welford window boundary (frame 32)
+    _assert_same_render(got, ref, "96x64 spp3 x40")
+
+
+def test_render_bit_exact_sine_dem_flat_earth():
+    dem = H.sine_dem(128)   # BASELINE.json configs[0] DEM
+    kw = dict(spacing=(100.0 / 127, 100.0 / 127), exaggeration=20.0, albedo=H.ALBEDO, sun_azimuth_deg=315.0,
+              sun_elevation_deg=12.0, max_frames=6, min_frames=6, variance_threshold=1e30, earth_model="flat",
+              refraction_model="none")
+    got, ref = _both(dem, 128, 128, H.CAM, **kw)
+    _assert_same_render(got, ref, "sine flat-earth")
+
+
+def test_render_bit_exact_mesh_and_env():
+    dem = H.golden_dem()
+    quad_v = np.array([[-18.0, 22.0, -6.0], [18.0, 22.0, -6.0], [18.0, 40.0, -6.0], [-18.0, 40.0, -6.0]], np.float32)
+    quad_i = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    rng = np.random.default_rng(5)
+    env = rng.uniform(0.0, 2.0, (16, 32, 3)).astype(np.float32)
+    kw = {**H.scene_kwargs(dem), "max_frames": 6, "min_frames": 6, "variance_threshold": 1e30}
+    got, ref = _both(dem, 96, 96, H.CAM, **kw, mesh_vertices=quad_v, mesh_indices=quad_i)
+    _assert_same_render(got, ref, "mesh")
+    closer = np.isfinite(got["depth"]) & (got["albedo"][..., 2] > 0.75)
+    assert closer.mean() > 0.01     # the quad is visible and carries the mesh albedo (0.7,0.7,0.8)
+    got, ref = _both(dem, 96, 96, H.CAM, **kw, env_map=env)
+    _assert_same_render(got, ref, "env map")
+    got, ref = _both(dem, 64, 64, H.CAM, **kw, env_map=env, mesh_vertices=quad_v, mesh_indices=quad_i)
+    _assert_same_render(got, ref, "mesh + env map")
+
+
+def test_render_bit_exact_large_relief_dem():
+    # Rainier-shaped closed-form DEM at reduced size: metres-scale coordinates,
+    # curvature active on the sun rays, deep pyramid (10 levels), orbit camera outside the DEM.
+    n = 512
+    dem = H.rainier_dem(n)
+    spacing = 10.0 * 2048 / n
+    cam = H.rainier_camera(n, spacing, dem)
+    kw = dict(spacing=(spacing, spacing), exaggeration=1.0, albedo=H.ALBEDO, sun_azimuth_deg=302.0,
+              sun_elevation_deg=24.0, max_frames=4, min_frames=4, variance_threshold=1e30)
+    got, ref = _both(dem, 160, 90, cam, **kw)
+    _assert_same_render(got, ref, "rainier 512")
+    assert np.isfinite(got["depth"]).mean() > 0.2
+
+
+def test_golden_scene_converges_and_matches_reference_golden():
+    dem = H.golden_dem()
+    got, ref = _both(dem, H.SIZE, H.SIZE, H.CAM, **H.scene_kwargs(dem))
+    _assert_same_render(got, ref, "golden 256x256")
+    assert got["converged"] is True and got["variance"] < 1e-3
+    gold = H.golden_png()
+    rgba = got["rgba"]
+    mean_abs = float(np.mean(np.abs(rgba[..., :3].astype(np.float32) - gold[..., :3].astype(np.float32))))
+    score = H.ssim(rgba[..., :3], gold[..., :3], 255.0)
+    print(f"CUDA vs reference golden: SSIM {score:.6f}, mean abs {mean_abs:.4f}, frames {got['frames']}")
+    assert score >= 0.995 and mean_abs <= 2.0          # tests/test_hybrid_terrain_pt.py:853-859
+    rmse = float(np.sqrt(np.mean((rgba.astype(np.float64) / 255.0 - ref["rgba"].astype(np.float64) / 255.0) ** 2)))
+    assert rmse <= 1e-3                                  # BASELINE.json north_star tolerance (here exactly 0)
+
+
+def test_public_api_contracts_on_gpu():
+    dem = H.golden_dem()
+    kw = H.scene_kwargs(dem)
+    out = hybrid_render_terrain_reference(dem, 64, 64, H.CAM, **{**kw, "max_frames": 32, "min_frames": 2,
+                                                                  "variance_threshold": 1e30})
+    for key in ("rgba", "albedo", "normal", "depth", "frames", "variance", "converged", "peak_host_visible_bytes",
+                "minmax_pyramid_bytes", "gpu_resource_bytes", "sun_source", "solar_azimuth_deg", "solar_elevation_deg"):
+        assert key in out
+    assert out["rgba"].shape == (64, 64, 4) and out["rgba"].dtype == np.uint8
+    assert out["albedo"].shape == (64, 64, 3) and out["depth"].shape == (64, 64)
+    assert out["gpu_resource_bytes"] > out["minmax_pyramid_bytes"] > 0
+    assert out["sun_source"] == "manual_angles" and out["solar_azimuth_deg"] == 225.0
+    with pytest.raises(Exception, match="did not converge"):
+        hybrid_render_terrain_reference(dem, 128, 128, H.CAM, **{**kw, "max_frames": 8, "min_frames": 2,
+                                                                  "variance_threshold": 1e-12})
+    with pytest.raises(Exception, match="look_at"):
+        hybrid_render_terrain_reference(dem, 64, 64, {**H.CAM, "look_at": H.CAM["origin"]}, **kw)
+    with pytest.raises(Exception, match="fov"):
+        hybrid_render_terrain_reference(dem, 64, 64, {**H.CAM, "fov_y": 0.0}, **kw)
+    with pytest.raises(MemoryError, match="memory budget"):
+        _native.hybrid_render_terrain_reference(dem, 1920, 1080, H.CAM, **kw, compat_512mib_gate=True)
+    # zero sun: renders, no valid-reservoir requirement (render_terrain.rs:465-471)
+    z = hybrid_render_terrain_reference(dem, 32, 32, H.CAM, **{**kw, "max_frames": 4, "min_frames": 2,
+                                                                "variance_threshold": 1e30, "sun_color": (0, 0, 0)})
+    assert z["frames"] == 4
