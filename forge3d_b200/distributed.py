@@ -1,0 +1,153 @@
+"""Image-row partition of one frame across the GPUs of a node (one process per GPU, torch.distributed).
+
+The reference is single-device (no NCCL/MPI anywhere); this is new work specified by
+BASELINE.json's north_star and SURVEY section 8e.  Design:
+
+  * rows are dealt to ranks in interleaved blocks (block b -> rank b % world) so sky and terrain
+    rows balance; every index/seed computation uses GLOBAL pixel coordinates, so a partitioned
+    render is bit-identical to the single-GPU render;
+  * the only per-frame cross-pixel dependency is the spatial reuse pass reading temporal records
+    within +-3 px (pt_restir_spatial.wgsl:170-171).  k_frame stores the 3 border rows of each owned
+    block straight into the neighbours' images over NVLink peer memory (CUDA IPC mappings) while it
+    computes -- no staging copy, no separate exchange kernel;
+  * a frame may only start when the neighbours' previous frame (and its halo stores) completed:
+    one 4-byte NCCL all-reduce per frame on the render stream acts as the cross-GPU barrier;
+  * the convergence gate needs max over ranks of the windowed variance: one NCCL MAX all-reduce per
+    32-frame window; validity flags are OR-reduced the same way;
+  * the framebuffer is assembled by ONE NCCL all-gather of the packed owned rows (RGBA8 + AOVs).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+TILE_H = 16  # kTileH in csrc/f3d_kernels.cuh: block_rows is rounded up to a multiple of it
+
+
+def effective_block_rows(block_rows: int, height: int, world: int) -> int:
+    """Mirrors session_create_impl (csrc/f3d_backend.cu): default 32, multiple of 16; one block when world == 1."""
+    if world <= 1:
+        return ((height + TILE_H - 1) // TILE_H) * TILE_H
+    b = block_rows if block_rows else 32
+    return ((b + TILE_H - 1) // TILE_H) * TILE_H
+
+
+def owned_rows(height: int, world: int, rank: int, block_rows: int = 0) -> np.ndarray:
+    """Global row indices rendered by `rank` (ascending)."""
+    br = effective_block_rows(block_rows, height, world)
+    rows = np.arange(height)
+    return rows[(rows // br) % max(world, 1) == rank]
+
+
+def row_counts(height: int, world: int, block_rows: int = 0) -> List[int]:
+    return [int(owned_rows(height, world, r, block_rows).size) for r in range(world)]
+
+
+def pack_rows(image, rows):
+    """image: (H, ...) tensor/array; returns the owned rows as one contiguous block."""
+    return image[rows]
+
+
+def assemble(gathered, height: int, world: int, block_rows: int = 0):
+    """gathered[r]: (max_rows, ...) block of rank r (padded); returns the (H, ...) image."""
+    first = gathered[0]
+    if hasattr(first, "new_zeros"):
+        out = first.new_zeros((height,) + tuple(first.shape[1:]))
+    else:
+        out = np.zeros((height,) + tuple(first.shape[1:]), dtype=first.dtype)
+    for r in range(world):
+        rows = owned_rows(height, world, r, block_rows)
+        if hasattr(first, "new_zeros"):
+            import torch
+
+            out[torch.as_tensor(rows, device=first.device)] = gathered[r][: rows.size]
+        else:
+            out[rows] = gathered[r][: rows.size]
+    return out
+
+
+def gather_rows(local_image, height: int, group=None, block_rows: int = 0):
+    """ONE all-gather of every rank's packed owned rows; every rank returns the assembled image.
+    Works on CUDA tensors (NCCL) and CPU tensors (gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    counts = row_counts(height, world, block_rows)
+    mx = max(counts)
+    rows = torch.as_tensor(owned_rows(height, world, rank, block_rows), device=local_image.device)
+    packed = local_image.new_zeros((mx,) + tuple(local_image.shape[1:]))
+    packed[: rows.numel()] = local_image[rows]
+    out = local_image.new_empty((world * mx,) + tuple(local_image.shape[1:]))
+    dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
+    return assemble([out[r * mx:(r + 1) * mx] for r in range(world)], height, world, block_rows)
+
+
+class PartitionedRender:
+    """One rank's share of a partitioned render (CUDA + NCCL)."""
+
+    def __init__(self, heightmap, width, height, cam=None, *, block_rows: int = 0, group=None, **scene_kw):
+        import torch
+        import torch.distributed as dist
+
+        from .session import Session
+
+        self.torch, self.dist, self.group = torch, dist, group
+        initialised = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if initialised else 1
+        self.rank = dist.get_rank(group) if initialised else 0
+        self.width, self.height, self.block_rows = int(width), int(height), int(block_rows)
+        self.device = torch.cuda.current_device()
+        self.stream = torch.cuda.current_stream()
+        self.session = Session(heightmap, width, height, cam, device=self.device,
+                               cuda_stream=self.stream.cuda_stream, part_rank=self.rank, part_world=self.world,
+                               part_block_rows=block_rows, **scene_kw)
+        self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.session.ipc_export(), group=group)
+            self.session.ipc_import(b"".join(handles))
+            dist.barrier(group=group)
+
+    def render_frames(self, n: int) -> None:
+        """n accumulation frames; with world > 1 a 4-byte all-reduce after every frame orders the
+        neighbours' halo stores before the next frame's reuse pass."""
+        if self.world == 1:
+            self.session.render_frames(n)
+            return
+        for _ in range(n):
+            self.session.render_frames(1)
+            self.dist.all_reduce(self._token, group=self.group)
+
+    def variance(self) -> Tuple[float, bool]:
+        v, bad = self.session.variance()
+        if self.world > 1:
+            t = self.torch.tensor([v, 1.0 if bad else 0.0], dtype=self.torch.float32, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+            v, bad = float(t[0]), bool(t[1] > 0)
+        return v, bad
+
+    def resolve(self, aovs: bool = True) -> Dict[str, "np.ndarray"]:
+        """Resolve owned rows on the device, then ONE all-gather per output; returns numpy images
+        on every rank (rank 0 is the consumer)."""
+        torch = self.torch
+        H, W = self.height, self.width
+        rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
+        bufs = {"rgba": rgba}
+        if aovs:
+            bufs["albedo"] = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+            bufs["normal"] = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+            bufs["depth"] = torch.zeros((H, W), dtype=torch.float32, device="cuda")
+        self.session.resolve_device(rgba.data_ptr(), bufs["albedo"].data_ptr() if aovs else 0,
+                                    bufs["normal"].data_ptr() if aovs else 0,
+                                    bufs["depth"].data_ptr() if aovs else 0, check_validity=True)
+        out = {}
+        for k, t in bufs.items():
+            full = gather_rows(t, H, self.group, self.block_rows) if self.world > 1 else t
+            out[k] = full.cpu().numpy()
+        return out
+
+    def close(self):
+        self.session.close()

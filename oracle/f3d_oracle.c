@@ -33,6 +33,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -58,6 +59,12 @@ int f3do_get_threads(void) {
 #else
     return 1;
 #endif
+}
+
+static double now_seconds(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -1029,6 +1036,7 @@ static inline float to_radians_f32(float d) { return d * (3.14159274101257324f /
 /* ------------------------------------------------------------------------- */
 int f3do_render(const f3do_desc* d, f3do_out* out) {
     g_err[0] = 0;
+    const double t_start = now_seconds();
     int rc = validate_desc(d);
     if (rc) return rc;
     const uint32_t W = d->width, H = d->height;
@@ -1134,6 +1142,7 @@ int f3do_render(const f3do_desc* d, f3do_out* out) {
     for (int64_t y = 0; y < (int64_t)H; y++)
         for (uint32_t x = 0; x < W; x++) gbuffer_pixel(&S, &U, &B, x, (uint32_t)y);
 
+    const double t_loop = now_seconds();
     uint32_t frames = 0;
     float variance = INFINITY;
     int converged = 0;
@@ -1173,6 +1182,8 @@ int f3do_render(const f3do_desc* d, f3do_out* out) {
             }
         }
     }
+    out->setup_seconds = t_loop - t_start;
+    out->frames_seconds = now_seconds() - t_loop;
     if (!converged) {
         result = fail(1, "terrain PT did not converge: per-pixel luminance variance %.3e over the last 32-frame window after %u frames (threshold %.1e); raise max_frames or simplify the scene — refusing to return a fake reference",
                       (double)variance, frames, (double)d->variance_threshold);

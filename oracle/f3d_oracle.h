@@ -68,6 +68,8 @@ typedef struct f3do_out {
     uint64_t minmax_pyramid_bytes;
     uint64_t rays_primary, rays_shadow, rays_ibl;
     uint64_t nodes_popped;   /* terrain_trace stack pops inside the frame loop */
+    double setup_seconds;    /* validation + pyramid build + G-buffer pass (wall clock) */
+    double frames_seconds;   /* the accumulation loop incl. convergence checks (wall clock) */
 } f3do_out;
 
 /* 0 = ok; otherwise an error class (1 render, 2 upload); message via f3do_last_error(). */

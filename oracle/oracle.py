@@ -55,6 +55,7 @@ class _Out(C.Structure):
         ("minmax_pyramid_bytes", C.c_uint64),
         ("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_ibl", C.c_uint64),
         ("nodes_popped", C.c_uint64),
+        ("setup_seconds", C.c_double), ("frames_seconds", C.c_double),
     ]
 
 
@@ -200,6 +201,7 @@ def render(heightmap, width, height, cam=None, *, spacing=(1.0, 1.0), exaggerati
                minmax_pyramid_bytes=int(o.minmax_pyramid_bytes),
                rays_primary=int(o.rays_primary), rays_shadow=int(o.rays_shadow),
                rays_ibl=int(o.rays_ibl), nodes_popped=int(o.nodes_popped),
+               setup_seconds=float(o.setup_seconds), frames_seconds=float(o.frames_seconds),
                sun_source="manual_angles", solar_azimuth_deg=float(sun_azimuth_deg),
                solar_elevation_deg=float(sun_elevation_deg))
     if acc is not None:
