@@ -101,8 +101,10 @@ class PartitionedRender:
         self.width, self.height, self.block_rows = int(width), int(height), int(block_rows)
         self.device = torch.cuda.current_device()
         self.stream = torch.cuda.current_stream()
+        # torch's default stream has handle 0, which the C ABI reads as "create your own stream":
+        # pass cudaStreamLegacy (0x1) so kernels, torch events and NCCL share one stream.
         self.session = Session(heightmap, width, height, cam, device=self.device,
-                               cuda_stream=self.stream.cuda_stream, part_rank=self.rank, part_world=self.world,
+                               cuda_stream=self.stream.cuda_stream or 1, part_rank=self.rank, part_world=self.world,
                                part_block_rows=block_rows, **scene_kw)
         self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
         if self.world > 1:

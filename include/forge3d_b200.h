@@ -107,7 +107,8 @@ int f3d_device_count(void);
 typedef struct f3d_session f3d_session;
 
 /* TerrainPtScene::new + uniform/buffer setup + main_terrain_gbuffer (render_terrain.rs:581-1121).
- * `cuda_stream` is a cudaStream_t (NULL = the library's own stream). */
+ * `cuda_stream` is a cudaStream_t; NULL = the library creates its own non-blocking stream
+ * (pass cudaStreamLegacy = (void*)1 to run on the legacy default stream). */
 int f3d_session_create(const f3d_terrain_desc* desc, void* cuda_stream, f3d_session** out_session);
 /* Enqueue `n` accumulation frames (one pass of render_terrain.rs:1127-1204 each); asynchronous. */
 int f3d_session_render_frames(f3d_session* s, uint32_t n);
