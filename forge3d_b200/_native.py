@@ -99,7 +99,8 @@ def lib():
     L.f3d_session_ipc_export.argtypes = [vp, u8p]
     L.f3d_session_ipc_import.argtypes = [vp, u8p]
     L.f3d_trace_rays.argtypes = [fp, C.c_uint32, C.c_uint32, fp, fp, C.c_float, C.c_float, C.c_int32,
-                                 fp, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, u8p, fp, fp]
+                                 fp, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, u8p, fp, fp,
+                                 C.POINTER(C.c_uint64)]
     L.f3d_build_minmax.argtypes = [fp, C.c_uint32, C.c_uint32, C.c_int32, u32p, fp, C.c_uint64]
     for name in EXPORTS:   # fail at load time, not at first call, if the ABI drifted
         getattr(L, name)
@@ -279,8 +280,9 @@ def hybrid_render_terrain_reference(heightmap, width, height, cam, spacing=(1.0,
 
 
 def trace_rays(heights, spacing, origin_xz, exaggeration, rays, *, any_hit, apply_curvature,
-               inv_two_r_prime=0.0, curvature_enabled=False, device=0):
-    """GPU terrain_trace over a ray batch (KAT seam, terrain_heightfield.rs:1646-1671)."""
+               inv_two_r_prime=0.0, curvature_enabled=False, device=0, variant=0, want_nodes=False):
+    """GPU terrain_trace over a ray batch (KAT seam, terrain_heightfield.rs:1646-1671).
+    variant 0 = production traversal, 1 = literal restatement of the WGSL loop."""
     dem = np.ascontiguousarray(heights, dtype=np.float32)
     r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
     n = r.shape[0]
@@ -289,10 +291,13 @@ def trace_rays(heights, spacing, origin_xz, exaggeration, rays, *, any_hit, appl
     nrm = np.zeros((n, 3), np.float32)
     sp = (C.c_float * 2)(float(spacing[0]), float(spacing[1]))
     og = (C.c_float * 2)(float(origin_xz[0]), float(origin_xz[1]))
+    nodes = C.c_uint64()
     check(lib().f3d_trace_rays(_fp(dem), dem.shape[1], dem.shape[0], sp, og, float(exaggeration),
                                float(inv_two_r_prime), int(bool(curvature_enabled)), _fp(r), n,
-                               int(bool(any_hit)), int(bool(apply_curvature)), int(device),
-                               hit.ctypes.data_as(C.POINTER(C.c_uint8)), _fp(t), _fp(nrm)))
+                               int(bool(any_hit)), int(bool(apply_curvature)), int(device), int(variant),
+                               hit.ctypes.data_as(C.POINTER(C.c_uint8)), _fp(t), _fp(nrm), C.byref(nodes)))
+    if want_nodes:
+        return hit.astype(bool), t, nrm, int(nodes.value)
     return hit.astype(bool), t, nrm
 
 

@@ -184,17 +184,28 @@ struct DeviceTerrain {
     size_t mm_total = 0;                 // float2 count
     uint32_t cell_w = 0, cell_h = 0;
     uint64_t bytes = 0;
+    // quad-packed copy of levels 0..nlevels-2 for the production traversal (f3d_trace_fast.cuh)
+    float2* quad_base = nullptr;
+    size_t quad_off[kMaxLevels] = {};
+    uint32_t quad_pitch[kMaxLevels] = {}, quad_ph[kMaxLevels] = {};
+    size_t quad_total = 0;
+    float2 root_mm = {0.0f, 0.0f};
 
+    void release_plain() {
+        if (mm_base) cudaFree(mm_base);
+        mm_base = nullptr;
+    }
     void release() {
         if (cells) cudaFree(cells);
-        if (mm_base) cudaFree(mm_base);
-        cells = nullptr; mm_base = nullptr;
+        if (quad_base) cudaFree(quad_base);
+        cells = nullptr; quad_base = nullptr;
+        release_plain();
     }
 };
 
 // Uploads the DEM, scans it for non-finite samples, and builds cells + pyramid on the device.
 static int build_device_terrain(const float* h_heights, uint32_t w, uint32_t h, float ex, cudaStream_t stream,
-                                DeviceTerrain* T, uint64_t* launches) {
+                                DeviceTerrain* T, uint64_t* launches, bool keep_plain) {
     const uint32_t cw = w - 1, ch = h - 1;
     uint32_t lw = next_pow2(cw), lh = next_pow2(ch);
     T->cell_w = cw; T->cell_h = ch;
@@ -228,14 +239,32 @@ static int build_device_terrain(const float* h_heights, uint32_t w, uint32_t h, 
                                               T->mm_base + T->level_off[l], T->dims[l][0], T->dims[l][1]);
         (*launches)++;
     }
+    // quad-packed levels: level l (< root) grouped by its level l+1 parent
+    T->quad_total = 0;
+    for (int l = 0; l + 1 < T->nlevels; l++) {
+        T->quad_pitch[l] = T->dims[l + 1][0];
+        T->quad_ph[l] = T->dims[l + 1][1];
+        T->quad_off[l] = T->quad_total;
+        T->quad_total += (size_t)T->quad_pitch[l] * T->quad_ph[l] * 4;
+    }
+    CUDA_TRY(cudaMalloc(&T->quad_base, std::max<size_t>(T->quad_total, 1) * sizeof(float2)));
+    for (int l = 0; l + 1 < T->nlevels; l++) {
+        dim3 g((2 * T->quad_pitch[l] + 31) / 32, (2 * T->quad_ph[l] + 7) / 8);
+        k_pack_quads<<<g, blk, 0, stream>>>(T->mm_base + T->level_off[l], T->dims[l][0], T->dims[l][1],
+                                            T->quad_base + T->quad_off[l], T->quad_pitch[l], T->quad_ph[l]);
+        (*launches)++;
+    }
     uint32_t flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof flag, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(&T->root_mm, T->mm_base + T->level_off[T->nlevels - 1], sizeof(float2), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaGetLastError());
     cudaFree(d_h);
     cudaFree(d_flag);
     if (flag) return fail(F3D_ERR_UPLOAD, "terrain heightfield contains non-finite samples");
-    T->bytes = (uint64_t)cw * ch * sizeof(float4) + T->mm_total * sizeof(float2);
+    if (!keep_plain) T->release_plain();
+    T->bytes = (uint64_t)cw * ch * sizeof(float4) + T->quad_total * sizeof(float2) +
+               (keep_plain ? T->mm_total * sizeof(float2) : 0);
     return 0;
 }
 
@@ -244,9 +273,29 @@ static void fill_scene_terrain(SceneParams* S, const DeviceTerrain& T) {
     S->cell_w = T.cell_w; S->cell_h = T.cell_h;
     S->mip_count = (uint32_t)T.nlevels;
     for (int l = 0; l < kMaxLevels; l++) {
-        S->mm[l] = l < T.nlevels ? T.mm_base + T.level_off[l] : nullptr;
+        S->mm[l] = (l < T.nlevels && T.mm_base) ? T.mm_base + T.level_off[l] : nullptr;
         S->mm_pitch[l] = l < T.nlevels ? T.dims[l][0] : 0;
     }
+}
+
+static void fill_fast_scene(FastScene* F, const SceneParams& S, const DeviceTerrain& T) {
+    F->ox = S.ox; F->oz = S.oz; F->sx = S.sx; F->sz = S.sz;
+    F->cell_w = T.cell_w; F->cell_h = T.cell_h; F->mip_count = (uint32_t)T.nlevels;
+    F->cells = T.cells;
+    for (int l = 0; l < kMaxLevels; l++) {
+        F->q.lv[l] = l + 1 < T.nlevels ? T.quad_base + T.quad_off[l] : nullptr;
+        F->q.parent_pitch[l] = l + 1 < T.nlevels ? T.quad_pitch[l] : 0;
+    }
+    F->root_mm = T.root_mm;
+    F->inv_two_r_prime = S.inv_two_r_prime;
+}
+
+static uint32_t stack_depth_for(int nlevels) { return 3u * (uint32_t)nlevels + 2u; }
+
+template <typename K>
+static int allow_smem(K kernel, size_t bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -285,6 +334,7 @@ struct f3d_session {
     double setup_ms = 0, frames_ms = 0, readback_ms = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     dim3 grid;
+    size_t smem_bytes = 0;
 };
 
 static void session_free(f3d_session* s) {
@@ -377,13 +427,18 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     // ---- terrain scene ----
     int rc = earth_curvature(d, &S.inv_two_r_prime, &S.curvature_enabled);
     if (rc) return rc;
-    rc = build_device_terrain(d->heights, d->dem_w, d->dem_h, d->exaggeration, s->stream, &s->terrain, &s->launches);
+    rc = build_device_terrain(d->heights, d->dem_w, d->dem_h, d->exaggeration, s->stream, &s->terrain, &s->launches, false);
     if (rc) return rc;
     s->gpu_bytes += s->terrain.bytes;
     fill_scene_terrain(&S, s->terrain);
     S.sx = d->spacing[0]; S.sz = d->spacing[1];
     S.ox = -0.5f * ((float)d->dem_w - 1.0f) * S.sx;           // terrain_heightfield.rs:359-360
     S.oz = -0.5f * ((float)d->dem_h - 1.0f) * S.sz;
+    fill_fast_scene(&P.fast, S, s->terrain);
+    P.stack_depth = stack_depth_for(s->terrain.nlevels);
+    s->smem_bytes = frame_smem_bytes(P.stack_depth);
+    if ((rc = allow_smem(k_frame, s->smem_bytes))) return rc;
+    if ((rc = allow_smem(k_gbuffer, s->smem_bytes))) return rc;
     memcpy(S.albedo, d->albedo, sizeof S.albedo);
     S.env_intensity = env_intensity;
     {   // reference-compatible diagnostic: DEM R32F + RG32F chain (terrain_heightfield.rs:292-314)
@@ -447,7 +502,7 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
 
     // ---- one-shot G-buffer / centre-ray AOV pass (render_terrain.rs:1091-1121) ----
     GbufferOut G{s->d_pixflags, s->d_aov_normal, s->d_aov_depth};
-    k_gbuffer<<<s->grid, kTileW * kTileH, 0, s->stream>>>(P, G);
+    k_gbuffer<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P, G);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
@@ -488,7 +543,7 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             P.peer_up = (float4*)s->peer_ptrs[up * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
             P.peer_down = (float4*)s->peer_ptrs[down * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
         }
-        k_frame<<<s->grid, kTileW * kTileH, 0, s->stream>>>(P);
+        k_frame<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P);
         s->launches++;
         s->frames++;
     }
@@ -741,7 +796,7 @@ extern "C" int f3d_build_minmax(const float* heights, uint32_t w, uint32_t h, in
     if (rc) return -rc;
     DeviceTerrain T;
     uint64_t launches = 0;
-    rc = build_device_terrain(heights, w, h, 1.0f, nullptr, &T, &launches);
+    rc = build_device_terrain(heights, w, h, 1.0f, nullptr, &T, &launches, true);
     if (rc) { T.release(); return -rc; }
     for (int l = 0; l < T.nlevels; l++) { dims[2 * l] = T.dims[l][0]; dims[2 * l + 1] = T.dims[l][1]; }
     if (levels_out) {
@@ -757,8 +812,8 @@ extern "C" int f3d_build_minmax(const float* heights, uint32_t w, uint32_t h, in
 
 extern "C" int f3d_trace_rays(const float* heights, uint32_t w, uint32_t h, const float spacing[2], const float origin_xz[2],
                               float exaggeration, float inv_two_r_prime, int32_t curvature_enabled, const float* rays,
-                              uint64_t n, int32_t any_hit, int32_t apply_curvature, int32_t device, uint8_t* hit, float* t,
-                              float* normal) {
+                              uint64_t n, int32_t any_hit, int32_t apply_curvature, int32_t device, int32_t variant,
+                              uint8_t* hit, float* t, float* normal, uint64_t* nodes_popped) {
     g_err[0] = 0;
     if (!heights || !rays || !hit || !t) return fail(F3D_ERR_ARGUMENT, "null argument");
     if (w < 2 || h < 2) return fail(F3D_ERR_UPLOAD, "terrain heightfield must be at least 2x2 texels, got %ux%u", w, h);
@@ -766,28 +821,39 @@ extern "C" int f3d_trace_rays(const float* heights, uint32_t w, uint32_t h, cons
     if (rc) return rc;
     DeviceTerrain T;
     uint64_t launches = 0;
-    rc = build_device_terrain(heights, w, h, exaggeration, nullptr, &T, &launches);
+    rc = build_device_terrain(heights, w, h, exaggeration, nullptr, &T, &launches, true);
     if (rc) { T.release(); return rc; }
     SceneParams S{};
     fill_scene_terrain(&S, T);
     S.ox = origin_xz[0]; S.oz = origin_xz[1]; S.sx = spacing[0]; S.sz = spacing[1];
     S.inv_two_r_prime = inv_two_r_prime; S.curvature_enabled = curvature_enabled ? 1u : 0u;
     S.traversal_mode = 3u;
+    FastScene F{};
+    fill_fast_scene(&F, S, T);
+    const uint32_t depth = stack_depth_for(T.nlevels);
+    const size_t smem = (size_t)depth * kTraceThreads * 4;
     float4* d_rays = nullptr; uint8_t* d_hit = nullptr; float* d_t = nullptr; float* d_n = nullptr;
-    auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_hit); cudaFree(d_t); cudaFree(d_n); T.release(); };
+    unsigned long long* d_nodes = nullptr;
+    auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_hit); cudaFree(d_t); cudaFree(d_n); cudaFree(d_nodes); T.release(); };
+    if (nodes_popped) *nodes_popped = 0;
     if (n) {
         if (cudaMalloc(&d_rays, n * 32) != cudaSuccess || cudaMalloc(&d_hit, n) != cudaSuccess ||
-            cudaMalloc(&d_t, n * 4) != cudaSuccess || cudaMalloc(&d_n, n * 12) != cudaSuccess) {
+            cudaMalloc(&d_t, n * 4) != cudaSuccess || cudaMalloc(&d_n, n * 12) != cudaSuccess ||
+            cudaMalloc(&d_nodes, 8) != cudaSuccess) {
             cleanup();
             return fail(F3D_ERR_DEVICE, "device allocation failed");
         }
+        cudaMemset(d_nodes, 0, 8);
         cudaMemcpy(d_rays, rays, n * 32, cudaMemcpyHostToDevice);
-        k_trace_rays<<<(unsigned)((n + 127) / 128), 128>>>(S, d_rays, n, any_hit, apply_curvature, d_hit, d_t, normal ? d_n : nullptr);
+        if ((rc = allow_smem(k_trace_rays, smem))) { cleanup(); return rc; }
+        k_trace_rays<<<(unsigned)((n + kTraceThreads - 1) / kTraceThreads), kTraceThreads, smem>>>(
+            S, F, depth, variant, d_rays, n, any_hit, apply_curvature, d_hit, d_t, normal ? d_n : nullptr, d_nodes);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { cleanup(); return fail(F3D_ERR_DEVICE, "trace kernel failed: %s", cudaGetErrorString(e)); }
         cudaMemcpy(hit, d_hit, n, cudaMemcpyDeviceToHost);
         cudaMemcpy(t, d_t, n * 4, cudaMemcpyDeviceToHost);
         if (normal) cudaMemcpy(normal, d_n, n * 12, cudaMemcpyDeviceToHost);
+        if (nodes_popped) { unsigned long long v = 0; cudaMemcpy(&v, d_nodes, 8, cudaMemcpyDeviceToHost); *nodes_popped = v; }
     }
     cleanup();
     return 0;

@@ -20,7 +20,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
-#include "f3d_trace.cuh"
+#include "f3d_trace_fast.cuh"
 
 namespace f3d {
 
@@ -28,7 +28,9 @@ constexpr int kTileW = 16, kTileH = 16;      // CTA pixel tile; warps own 8x4 su
 constexpr int kMaxPeers = 2;                 // row-block neighbours (above / below)
 
 struct FrameParams {
-    SceneParams scene;
+    SceneParams scene;          // env / mesh / albedo (+ the plain pyramid when the KAT seam keeps it)
+    FastScene fast;             // quad-packed pyramid for the production traversal
+    uint32_t stack_depth;       // shared-memory stack entries per thread (3 * mip_count + 2)
     uint32_t W, H, frame_index, spp, window;
     float cam_origin[3], cam_right[3], cam_up[3], cam_forward[3];
     float half_w, half_h, exposure;
@@ -179,87 +181,231 @@ __device__ __forceinline__ void warp_add_counters(unsigned long long* counters, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_frame: one accumulation frame (see the file header).
+// Shared-memory plan of k_frame / k_gbuffer (dynamic, sized by the host):
+//   stack   : stack_depth x 256 u32   traversal stacks, [depth][thread]
+//   ray_o   : 3 x 256 f32             secondary-ray origin of each pixel (shared by its two rays)
+//   ray_e   : 3 x 256 f32             IBL direction of each pixel
+//   q_sun   : 256 u8, q_ibl : 256 u8  compacted lists of pixel slots that need a sun / IBL ray
+//   occl    : 2 x 256 u8              results, indexed by pixel slot
+//   counts  : 2 u32
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileW* kTileH) k_frame(const __grid_constant__ FrameParams P) {
+constexpr int kThreads = kTileW * kTileH;
+
+__host__ __device__ inline size_t frame_smem_bytes(uint32_t stack_depth) {
+    return (size_t)stack_depth * kThreads * 4 + 6 * kThreads * 4 + 4 * kThreads + 16;
+}
+
+struct SmemPlan {
+    uint32_t* stack;
+    float* ray_o;
+    float* ray_e;
+    uint8_t* q_sun;
+    uint8_t* q_ibl;
+    uint8_t* occl_sun;
+    uint8_t* occl_ibl;
+    uint32_t* counts;
+};
+
+__device__ __forceinline__ SmemPlan smem_plan(unsigned char* raw, uint32_t stack_depth) {
+    SmemPlan p;
+    p.stack = reinterpret_cast<uint32_t*>(raw);
+    p.ray_o = reinterpret_cast<float*>(p.stack + (size_t)stack_depth * kThreads);
+    p.ray_e = p.ray_o + 3 * kThreads;
+    p.q_sun = reinterpret_cast<uint8_t*>(p.ray_e + 3 * kThreads);
+    p.q_ibl = p.q_sun + kThreads;
+    p.occl_sun = p.q_ibl + kThreads;
+    p.occl_ibl = p.occl_sun + kThreads;
+    p.counts = reinterpret_cast<uint32_t*>(p.occl_ibl + kThreads);
+    return p;
+}
+
+// intersect_hybrid (hybrid_traversal.wgsl:175-201) on the production traversal.
+struct PrimaryHit { bool hit; uint32_t hit_type; float t; v3 point, normal; };
+
+__device__ __forceinline__ PrimaryHit primary_hit(const FrameParams& P, const Ray& ray, const SmemStack st, uint32_t& nodes) {
+    PrimaryHit ph;
+    ph.hit = false; ph.hit_type = 0u; ph.t = ray.tmax; ph.point = V3(0, 0, 0); ph.normal = V3(0, 0, 0);
+    Ray tr = ray;
+    if (P.scene.traversal_mode == 0u) {
+        const Hit mh = intersect_mesh(P.scene, ray);
+        if (mh.hit && mh.t < ph.t) { ph.hit = true; ph.hit_type = 0u; ph.t = mh.t; ph.point = mh.point; ph.normal = mh.normal; }
+        tr.tmax = ph.t;
+    }
+    const FastHit fh = trace_fast<false>(P.fast, tr, false, st, nodes);
+    if (fh.hit && fh.t < ph.t) {
+        ph.hit = true; ph.hit_type = 3u; ph.t = fh.t;
+        finish_hit(P.fast, tr, fh, ph.point, ph.normal);
+    }
+    return ph;
+}
+
+// intersect_hybrid_optimized(ray, 0.01, curv) + `hit && t < 1e30` (hybrid_traversal.wgsl:204-259)
+__device__ __forceinline__ bool occluded_fast(const FrameParams& P, const Ray& ray, bool curv, const SmemStack st, uint32_t& nodes) {
+    const float max_distance = 1e30f;
+    float best_t = ray.tmax;
+    bool best_hit = false;
+    if (P.scene.traversal_mode == 0u) {
+        const Hit mh = intersect_mesh(P.scene, ray);
+        if (mh.hit && mh.t < 0.01f) return mh.t < max_distance;
+        if (mh.hit && mh.t < best_t) { best_t = mh.t; best_hit = true; }
+    }
+    Ray tr = ray;
+    tr.tmax = best_t;
+    const FastHit fh = trace_fast<true>(P.fast, tr, curv && P.scene.curvature_enabled != 0u, st, nodes);
+    if (fh.hit && fh.t < best_t) { best_t = fh.t; best_hit = true; }
+    return best_hit && best_t < max_distance;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_frame: one accumulation frame (see the file header).  Per CTA = one 16x16 pixel tile:
+//   phase 0  per pixel : spatial reuse of last frame's records, M-clamp
+//   per sample:
+//   phase 1  per pixel : primary ray (closest hit), all lanes busy, coherent
+//   phase 2  per pixel : shading set-up; pixels that need a sun / IBL ray append their slot to the
+//                        CTA's compacted ray lists (warp ballot + prefix sum)
+//   phase 3  per ray   : any-hit traversal over the compacted lists -- sky pixels and back-facing
+//                        hits no longer idle lanes next to lanes that trace
+//   phase 4  per pixel : combine, accumulate
+//   then temporal reuse, halo push, accumulation and Welford.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_frame(const __grid_constant__ FrameParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemPlan sm = smem_plan(smem_raw, P.stack_depth);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    SmemStack st;
+    st.base = sm.stack + tid;
+    st.stride = kThreads;
+
     uint32_t gx, gy;
     const bool active = owned_pixel(P, gx, gy);
+    const uint32_t pix = active ? gy * P.W + gx : 0u;
     uint32_t n_primary = 0, n_shadow = 0, n_ibl = 0, n_nodes = 0;
-    if (active) {
-        const SceneParams& S = P.scene;
-        const uint32_t pix = gy * P.W + gx;
-        const bool facing = (P.pixflags[pix] & 1u) != 0u;
 
-        // ---- merged reservoir from last frame's reuse chain + M-clamp (:452-465) ----
-        Resv prev_r;
-        prev_r.w_sum = 0.0f; prev_r.weight = 0.0f; prev_r.target_pdf = 0.0f; prev_r.m = 0u; prev_r.type1 = false;
+    const SceneParams& S = P.scene;
+    const v3 light_color = ld3(P.light_color);
+    const v3 wi = normalize3(ld3(P.light_dir));
+
+    // ---- phase 0: merged reservoir from last frame's reuse chain + M-clamp (:452-465) ----
+    Resv prev_r;
+    prev_r.w_sum = 0.0f; prev_r.weight = 0.0f; prev_r.target_pdf = 0.0f; prev_r.m = 0u; prev_r.type1 = false;
+    bool prev_valid = false;
+    uint32_t rng = 0u;
+    if (active) {
+        const bool facing = (P.pixflags[pix] & 1u) != 0u;
         if (P.frame_index > 0u) prev_r = spatial_reuse(P, P.resv_in, gx, gy, facing, P.frame_index - 1u);
         if (prev_r.m > 512u) {
-            float scale = fdiv(512.0f, (float)prev_r.m);
+            const float scale = fdiv(512.0f, (float)prev_r.m);
             prev_r.w_sum = prev_r.w_sum * scale;
             prev_r.m = 512u;
             if (prev_r.target_pdf > 0.0f) prev_r.weight = fdiv(prev_r.w_sum, (float)prev_r.m * prev_r.target_pdf);
         }
-        const bool prev_valid = P.frame_index > 0u && prev_r.m > 0u && prev_r.weight > 0.0f &&
-                                prev_r.target_pdf > 0.0f && prev_r.type1;
+        prev_valid = P.frame_index > 0u && prev_r.m > 0u && prev_r.weight > 0.0f && prev_r.target_pdf > 0.0f && prev_r.type1;
+        rng = P.seed_hi ^ (gx * 1664525u) ^ (gy * 1013904223u) ^ (P.frame_index * 92837111u) ^ P.seed_lo;
+    }
+    // every populated sample stores direction == wi; the shader re-normalises it (:520)
+    const v3 sun_dir_reuse = normalize3(wi);
+    const v3 sun_dir = prev_valid ? sun_dir_reuse : wi;
+    const float reuse_w = prev_valid ? clampf(prev_r.weight, 0.0f, 4.0f) : 1.0f;
 
-        uint32_t rng = P.seed_hi ^ (gx * 1664525u) ^ (gy * 1013904223u) ^ (P.frame_index * 92837111u) ^ P.seed_lo;
-        const uint32_t spp = max(P.spp, 1u);
-        const v3 light_color = ld3(P.light_color);
-        const v3 wi = normalize3(ld3(P.light_dir));
-        // every populated sample stores direction == wi; the shader re-normalises it (:520)
-        const v3 sun_dir = prev_valid ? normalize3(wi) : wi;
-        const float reuse_w = prev_valid ? clampf(prev_r.weight, 0.0f, 4.0f) : 1.0f;
-
-        v3 frame_radiance = V3(0, 0, 0);
-        Resv cand;
-        cand.w_sum = 0.0f; cand.weight = 0.0f; cand.target_pdf = 0.0f; cand.m = 0u; cand.type1 = false;
+    v3 frame_radiance = V3(0, 0, 0);
+    Resv cand;
+    cand.w_sum = 0.0f; cand.weight = 0.0f; cand.target_pdf = 0.0f; cand.m = 0u; cand.type1 = false;
+    const uint32_t spp = max(P.spp, 1u);
 
 #pragma unroll 1
-        for (uint32_t s = 0; s < spp; s++) {
+    for (uint32_t s = 0; s < spp; s++) {
+        if (tid < 2u) sm.counts[tid] = 0u;
+        __syncthreads();
+        // ---- phase 1: primary ray ----
+        bool want_sun = false, want_ibl = false;
+        v3 sun_pre = V3(0, 0, 0), ibl_pre = V3(0, 0, 0);    // contributions before the visibility factor
+        if (active) {
             const float jx = tent_offset(xorshift32(rng)) * 0.5f;
             const float jy = tent_offset(xorshift32(rng)) * 0.5f;
             const Ray ray = camera_ray(P, gx, gy, jx, jy);
             n_primary++;
-            const Hit hit = intersect_hybrid(S, ray, n_nodes);
-            if (hit.hit == 0u) {
+            const PrimaryHit hit = primary_hit(P, ray, st, n_nodes);
+            if (!hit.hit) {
                 frame_radiance = frame_radiance + env_radiance(S, ray.d);
-                continue;
+            } else {
+                // ---- phase 2: shading set-up ----
+                const v3 n = hit.normal;
+                const v3 albedo = hit.hit_type == 3u ? ld3(S.albedo) : V3(0.7f, 0.7f, 0.8f);
+                const float ndotl = fmaxf(dot3(n, wi), 0.0f);
+                const float target_pdf = luminance((albedo * light_color) * ndotl);
+                if (target_pdf > 0.0f) {
+                    cand.type1 = true;
+                    cand.w_sum = cand.w_sum + target_pdf;
+                    cand.m = cand.m + 1u;
+                    cand.target_pdf = target_pdf;
+                }
+                const float nd = fmaxf(dot3(n, sun_dir), 0.0f);
+                const v3 shade_o = hit.point + n * 1e-3f;
+                sm.ray_o[tid] = shade_o.x; sm.ray_o[kThreads + tid] = shade_o.y; sm.ray_o[2 * kThreads + tid] = shade_o.z;
+                if (nd > 0.0f) {
+                    want_sun = true;
+                    sun_pre = (albedo * light_color) * nd;
+                    sm.occl_sun[tid] = prev_valid ? 2u : 0u;   // tells phase 3 which sun direction this pixel uses
+                }
+                const float u1 = xorshift32(rng);
+                const float u2 = xorshift32(rng);
+                const v3 ei = cosine_dir(n, u1, u2);
+                sm.ray_e[tid] = ei.x; sm.ray_e[kThreads + tid] = ei.y; sm.ray_e[2 * kThreads + tid] = ei.z;
+                want_ibl = true;
+                ibl_pre = albedo * env_radiance(S, ei);
             }
-            const v3 n = hit.normal;
-            const v3 albedo = hit.hit_type == 3u ? ld3(S.albedo) : V3(0.7f, 0.7f, 0.8f);
-
-            const float ndotl = fmaxf(dot3(n, wi), 0.0f);
-            const float target_pdf = luminance((albedo * light_color) * ndotl);
-            if (target_pdf > 0.0f) {
-                cand.type1 = true;
-                cand.w_sum = cand.w_sum + target_pdf;
-                cand.m = cand.m + 1u;
-                cand.target_pdf = target_pdf;
-            }
-
-            v3 sun = V3(0, 0, 0);
-            const float nd = fmaxf(dot3(n, sun_dir), 0.0f);
-            const v3 shade_o = hit.point + n * 1e-3f;
-            if (nd > 0.0f) {
-                Ray sray;
-                sray.o = shade_o; sray.tmin = 1e-3f; sray.d = sun_dir; sray.tmax = 1e30f;
-                n_shadow++;
-                const float vis = occluded<true>(S, sray, n_nodes) ? 0.0f : 1.0f;
-                sun = (((albedo * light_color) * nd) * vis) * reuse_w;
-            }
-
-            const float u1 = xorshift32(rng);
-            const float u2 = xorshift32(rng);
-            const v3 ei = cosine_dir(n, u1, u2);
-            Ray eray;
-            eray.o = shade_o; eray.tmin = 1e-3f; eray.d = ei; eray.tmax = 1e30f;
-            n_ibl++;
-            const float env_vis = occluded<false>(S, eray, n_nodes) ? 0.0f : 1.0f;
-            const v3 ibl = (albedo * env_radiance(S, ei)) * env_vis;
-
-            frame_radiance = (frame_radiance + sun) + ibl;
         }
+        // compaction: append this pixel's slot to the sun / IBL lists
+        {
+            const uint32_t m_sun = __ballot_sync(0xFFFFFFFFu, want_sun), m_ibl = __ballot_sync(0xFFFFFFFFu, want_ibl);
+            uint32_t b_sun = 0u, b_ibl = 0u;
+            if (lane == 0u) {
+                if (m_sun) b_sun = atomicAdd(&sm.counts[0], (uint32_t)__popc(m_sun));
+                if (m_ibl) b_ibl = atomicAdd(&sm.counts[1], (uint32_t)__popc(m_ibl));
+            }
+            b_sun = __shfl_sync(0xFFFFFFFFu, b_sun, 0);
+            b_ibl = __shfl_sync(0xFFFFFFFFu, b_ibl, 0);
+            const uint32_t lt = (1u << lane) - 1u;
+            if (want_sun) sm.q_sun[b_sun + __popc(m_sun & lt)] = (uint8_t)tid;
+            if (want_ibl) sm.q_ibl[b_ibl + __popc(m_ibl & lt)] = (uint8_t)tid;
+        }
+        __syncthreads();
+        // ---- phase 3: any-hit rays over the compacted lists ----
+        {
+            const uint32_t n_sun = sm.counts[0], n_all = n_sun + sm.counts[1];
+            for (uint32_t i = tid; i < n_all; i += kThreads) {
+                const bool is_sun = i < n_sun;
+                const uint32_t slot = is_sun ? sm.q_sun[i] : sm.q_ibl[i - n_sun];
+                Ray sr;
+                sr.o = V3(sm.ray_o[slot], sm.ray_o[kThreads + slot], sm.ray_o[2 * kThreads + slot]);
+                sr.tmin = 1e-3f;
+                sr.tmax = 1e30f;
+                // the sun ray of a pixel uses that pixel's sun_dir (reuse-normalised or not): recompute from its flag
+                if (is_sun) sr.d = (sm.occl_sun[slot] & 2u) ? sun_dir_reuse : wi;
+                else sr.d = V3(sm.ray_e[slot], sm.ray_e[kThreads + slot], sm.ray_e[2 * kThreads + slot]);
+                const bool occ = occluded_fast(P, sr, is_sun, st, n_nodes);
+                if (is_sun) { sm.occl_sun[slot] = occ ? 1u : 0u; n_shadow++; }
+                else { sm.occl_ibl[slot] = occ ? 1u : 0u; n_ibl++; }
+            }
+        }
+        __syncthreads();
+        // ---- phase 4: combine (:523-547) ----
+        if (active) {
+            v3 sun = V3(0, 0, 0), ibl = V3(0, 0, 0);
+            if (want_sun) {
+                const float vis = sm.occl_sun[tid] ? 0.0f : 1.0f;
+                sun = (sun_pre * vis) * reuse_w;
+            }
+            if (want_ibl) {
+                const float env_vis = sm.occl_ibl[tid] ? 0.0f : 1.0f;
+                ibl = ibl_pre * env_vis;
+                frame_radiance = (frame_radiance + sun) + ibl;
+            }
+        }
+        __syncthreads();
+    }
+
+    if (active) {
         const float fspp = (float)spp;
         frame_radiance = V3(fdiv(frame_radiance.x, fspp), fdiv(frame_radiance.y, fspp), fdiv(frame_radiance.z, fspp));
 
@@ -305,13 +451,18 @@ struct GbufferOut {
     float* aov_depth;      // R32F, qNaN 0x7fc00000 on miss
 };
 
-__global__ void __launch_bounds__(kTileW* kTileH) k_gbuffer(const __grid_constant__ FrameParams P, GbufferOut G) {
+__global__ void __launch_bounds__(kThreads) k_gbuffer(const __grid_constant__ FrameParams P, GbufferOut G) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemPlan sm = smem_plan(smem_raw, P.stack_depth);
+    SmemStack st;
+    st.base = sm.stack + threadIdx.x;
+    st.stride = kThreads;
     uint32_t gx, gy;
     if (!owned_pixel(P, gx, gy)) return;
     const uint32_t pix = gy * P.W + gx;
     uint32_t nodes = 0;
     const Ray ray = camera_ray(P, gx, gy, 0.0f, 0.0f);
-    const Hit hit = intersect_hybrid(P.scene, ray, nodes);
+    const PrimaryHit hit = primary_hit(P, ray, st, nodes);
     // ReSTIR G-buffer record: hit -> (normal, 1); miss -> (0,0,1,1)  (:635-643)
     const v3 nr = hit.hit ? hit.normal : V3(0.0f, 0.0f, 1.0f);
     const v3 N = normalize3(nr);
@@ -334,7 +485,7 @@ __global__ void __launch_bounds__(kTileW* kTileH) k_gbuffer(const __grid_constan
 // out[0] = bits(max over owned pixels of m2/(n-1)) (non-negative floats order as uints),
 // out[1] != 0 when any m2 is non-finite.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTileW* kTileH) k_variance(const __grid_constant__ FrameParams P, float n_window,
+__global__ void __launch_bounds__(kThreads) k_variance(const __grid_constant__ FrameParams P, float n_window,
                                                              uint32_t* __restrict__ out) {
     uint32_t gx, gy;
     float v = 0.0f;
@@ -373,7 +524,7 @@ struct ResolveOut {
 
 __device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
 
-__global__ void __launch_bounds__(kTileW* kTileH) k_resolve(const __grid_constant__ FrameParams P, ResolveOut R) {
+__global__ void __launch_bounds__(kThreads) k_resolve(const __grid_constant__ FrameParams P, ResolveOut R) {
     uint32_t gx, gy;
     uint32_t nonfinite = 0u, valid = 0u;
     if (owned_pixel(P, gx, gy)) {
@@ -460,6 +611,19 @@ __global__ void k_reduce_level(const float2* __restrict__ prev, uint32_t lw, uin
     next[(size_t)y * nw + x] = make_float2(mn, mx);
 }
 
+// Quad-packs one plain level for the production traversal: slot (x, y) of the level goes to
+// quads[((y>>1) * parent_pitch + (x>>1)) * 4 + ((y&1)*2 + (x&1))]; slots outside the level hold the
+// (+inf, -inf) sentinel (never visited: their cells lie outside the DEM).
+__global__ void k_pack_quads(const float2* __restrict__ plain, uint32_t lw, uint32_t lh, float2* __restrict__ quads,
+                             uint32_t parent_pitch, uint32_t parent_h) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= 2u * parent_pitch || y >= 2u * parent_h) return;
+    float2 v = make_float2(__int_as_float(0x7f800000), __int_as_float(0xff800000));
+    if (x < lw && y < lh) v = plain[(size_t)y * lw + x];
+    quads[((size_t)(y >> 1) * parent_pitch + (x >> 1)) * 4u + ((y & 1u) * 2u + (x & 1u))] = v;
+}
+
 // Non-finite scan of the uploaded heightfield (trust boundary of build_minmax_mips, :144-148).
 __global__ void k_check_finite(const float* __restrict__ v, size_t n, uint32_t* __restrict__ flag) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -471,21 +635,46 @@ __global__ void k_check_finite(const float* __restrict__ v, size_t n, uint32_t* 
 }
 
 // KAT seam: terrain_trace over a ray batch (terrain_heightfield.rs:1646-1671 test entry).
-__global__ void k_trace_rays(SceneParams S, const float4* __restrict__ rays, uint64_t n, int any_hit, int apply_curv,
-                             uint8_t* __restrict__ hit, float* __restrict__ t, float* __restrict__ normal) {
+// variant 0 = production traversal (trace_fast), 1 = literal restatement of the WGSL loop.
+// The production traversal serves closest-hit only without curvature (the only combination the
+// renderer uses, hybrid_traversal.wgsl:248-259 / hybrid_terrain_traversal.wgsl:374-376); a
+// closest-hit + curvature request is routed to the literal loop.
+constexpr int kTraceThreads = 128;
+
+__global__ void __launch_bounds__(kTraceThreads) k_trace_rays(SceneParams S, FastScene F, uint32_t stack_depth, int variant,
+                                                              const float4* __restrict__ rays, uint64_t n, int any_hit,
+                                                              int apply_curv, uint8_t* __restrict__ hit, float* __restrict__ t,
+                                                              float* __restrict__ normal, unsigned long long* __restrict__ nodes_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 a = rays[2 * i], b = rays[2 * i + 1];
     Ray r;
     r.o = V3(a.x, a.y, a.z); r.tmin = a.w; r.d = V3(b.x, b.y, b.z); r.tmax = b.w;
     uint32_t nodes = 0;
-    Hit h;
     const bool curv = apply_curv && S.curvature_enabled;
-    if (any_hit) h = curv ? terrain_trace<true, true>(S, r, nodes) : terrain_trace<true, false>(S, r, nodes);
-    else h = curv ? terrain_trace<false, true>(S, r, nodes) : terrain_trace<false, false>(S, r, nodes);
-    hit[i] = (uint8_t)h.hit;
-    t[i] = h.t;
-    if (normal) { normal[3 * i] = h.normal.x; normal[3 * i + 1] = h.normal.y; normal[3 * i + 2] = h.normal.z; }
+    bool h_hit;
+    float h_t;
+    v3 h_n = V3(0, 0, 0);
+    if (variant == 0 && (any_hit || !curv)) {
+        SmemStack st;
+        st.base = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
+        st.stride = kTraceThreads;
+        FastHit fh;
+        if (any_hit) fh = trace_fast<true>(F, r, curv, st, nodes);
+        else fh = trace_fast<false>(F, r, false, st, nodes);
+        h_hit = fh.hit; h_t = fh.t;
+        if (fh.hit) { v3 p; finish_hit(F, r, fh, p, h_n); }
+    } else {
+        Hit h;
+        if (any_hit) h = curv ? terrain_trace<true, true>(S, r, nodes) : terrain_trace<true, false>(S, r, nodes);
+        else h = curv ? terrain_trace<false, true>(S, r, nodes) : terrain_trace<false, false>(S, r, nodes);
+        h_hit = h.hit != 0u; h_t = h.t; h_n = h.normal;
+    }
+    hit[i] = h_hit ? 1 : 0;
+    t[i] = h_t;
+    if (normal) { normal[3 * i] = h_n.x; normal[3 * i + 1] = h_n.y; normal[3 * i + 2] = h_n.z; }
+    if (nodes_out) atomicAdd(nodes_out, (unsigned long long)nodes);
 }
 
 }  // namespace f3d

@@ -146,7 +146,9 @@ int f3d_session_ipc_import(f3d_session* s, const uint8_t* all_handles /* part_wo
 int f3d_trace_rays(const float* heights, uint32_t dem_w, uint32_t dem_h, const float spacing[2],
                    const float origin_xz[2], float exaggeration, float inv_two_r_prime,
                    int32_t curvature_enabled, const float* rays, uint64_t n, int32_t any_hit,
-                   int32_t apply_curvature, int32_t device, uint8_t* hit, float* t, float* normal);
+                   int32_t apply_curvature, int32_t device,
+                   int32_t variant /* 0 = production traversal, 1 = literal restatement of the WGSL loop */,
+                   uint8_t* hit, float* t, float* normal, uint64_t* nodes_popped /* may be NULL */);
 
 /* GPU min-max pyramid build (== build_minmax_mips, terrain_heightfield.rs:132-202), copied back
  * to the host for parity checks: dims[2*l..] and levels finest first, [min,max] pairs. */
