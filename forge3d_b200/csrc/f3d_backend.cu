@@ -334,7 +334,13 @@ struct f3d_session {
     double setup_ms = 0, frames_ms = 0, readback_ms = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     dim3 grid;
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0;          // stack smem of the per-pixel kernels (kThreads)
+    size_t trace_smem_bytes = 0;    // stack smem of k_trace (kTraceCtaThreads)
+    int trace_grid = 0;             // persistent CTAs of k_trace
+    float4* d_rec = nullptr;
+    uint8_t* d_occl_sun = nullptr; uint8_t* d_occl_ibl = nullptr;
+    uint32_t* d_q_sun = nullptr; uint32_t* d_q_ibl = nullptr; uint32_t* d_q_counts = nullptr;
+    float4* d_sstate = nullptr;
 };
 
 static void session_free(f3d_session* s) {
@@ -347,6 +353,8 @@ static void session_free(f3d_session* s) {
     cudaFree(s->d_accum); cudaFree(s->d_welford); cudaFree(s->d_resv[0]); cudaFree(s->d_resv[1]);
     cudaFree(s->d_pixflags); cudaFree(s->d_aov_normal); cudaFree(s->d_aov_depth); cudaFree(s->d_counters);
     cudaFree(s->d_gate);
+    cudaFree(s->d_rec); cudaFree(s->d_occl_sun); cudaFree(s->d_occl_ibl);
+    cudaFree(s->d_q_sun); cudaFree(s->d_q_ibl); cudaFree(s->d_q_counts); cudaFree(s->d_sstate);
     cudaFree(s->d_rgba); cudaFree(s->d_albedo); cudaFree(s->d_normal); cudaFree(s->d_depth);
     if (s->h_gate) cudaFreeHost(s->h_gate);
     if (s->h_stage) cudaFreeHost(s->h_stage);
@@ -436,9 +444,19 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     S.oz = -0.5f * ((float)d->dem_h - 1.0f) * S.sz;
     fill_fast_scene(&P.fast, S, s->terrain);
     P.stack_depth = stack_depth_for(s->terrain.nlevels);
-    s->smem_bytes = frame_smem_bytes(P.stack_depth);
-    if ((rc = allow_smem(k_frame, s->smem_bytes))) return rc;
+    s->smem_bytes = stack_smem_bytes(P.stack_depth, kThreads);
+    s->trace_smem_bytes = stack_smem_bytes(P.stack_depth, kTraceCtaThreads);
+    if ((rc = allow_smem(k_primary, s->smem_bytes))) return rc;
     if ((rc = allow_smem(k_gbuffer, s->smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<true, true>, s->trace_smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<true, false>, s->trace_smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<false, false>, s->trace_smem_bytes))) return rc;
+    {   // persistent grid: every SM filled to the occupancy the traversal kernel reaches
+        int per_sm = 0, sms = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, true>, kTraceCtaThreads, s->trace_smem_bytes));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+        s->trace_grid = std::max(per_sm, 1) * std::max(sms, 1);
+    }
     memcpy(S.albedo, d->albedo, sizeof S.albedo);
     S.env_intensity = env_intensity;
     {   // reference-compatible diagnostic: DEM R32F + RG32F chain (terrain_heightfield.rs:292-314)
@@ -496,6 +514,16 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     if ((rc = dmalloc(s, &s->d_gate, (size_t)4, true))) return rc;
     CUDA_TRY(cudaMallocHost(&s->h_gate, 4 * sizeof(uint32_t)));
     s->host_visible_bytes += 4 * sizeof(uint32_t);
+    if ((rc = dmalloc(s, &s->d_rec, npx * 4, true))) return rc;
+    if ((rc = dmalloc(s, &s->d_occl_sun, npx, true))) return rc;
+    if ((rc = dmalloc(s, &s->d_occl_ibl, npx, true))) return rc;
+    if ((rc = dmalloc(s, &s->d_q_sun, npx, false))) return rc;
+    if ((rc = dmalloc(s, &s->d_q_ibl, npx, false))) return rc;
+    if ((rc = dmalloc(s, &s->d_q_counts, (size_t)4, true))) return rc;
+    if (P.spp > 1u && (rc = dmalloc(s, &s->d_sstate, npx * 3, true))) return rc;
+    P.rec = s->d_rec; P.occl_sun = s->d_occl_sun; P.occl_ibl = s->d_occl_ibl;
+    P.q_sun = s->d_q_sun; P.q_ibl = s->d_q_ibl; P.q_counts = s->d_q_counts; P.sstate = s->d_sstate;
+    P.sample_index = 0u;
     P.accum = s->d_accum; P.welford = s->d_welford; P.pixflags = s->d_pixflags; P.counters = s->d_counters;
     P.resv_in = s->d_resv[1]; P.resv_out = s->d_resv[0];
     P.peer_up = nullptr; P.peer_down = nullptr;
@@ -543,8 +571,17 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             P.peer_up = (float4*)s->peer_ptrs[up * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
             P.peer_down = (float4*)s->peer_ptrs[down * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
         }
-        k_frame<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P);
-        s->launches++;
+        for (uint32_t smp = 0; smp < P.spp; smp++) {
+            P.sample_index = smp;
+            k_primary<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P);
+            if (P.scene.curvature_enabled)
+                k_trace<true, true><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, s->stream>>>(P);
+            else
+                k_trace<true, false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, s->stream>>>(P);
+            k_trace<false, false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, s->stream>>>(P);
+            k_accum<<<s->grid, kThreads, 0, s->stream>>>(P);
+            s->launches += 4;
+        }
         s->frames++;
     }
     CUDA_TRY(cudaGetLastError());

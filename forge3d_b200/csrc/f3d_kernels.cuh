@@ -1,22 +1,27 @@
 // forge3d_b200/csrc/f3d_kernels.cuh
-// CUDA kernels of the B200 terrain path tracer.  What the reference does in four WGSL dispatches
-// per frame (main_terrain -> pt_restir_temporal -> pt_restir_spatial, plus a one-off
-// main_terrain_gbuffer) is restructured here into ONE fused frame kernel:
+// CUDA kernels of the B200 terrain path tracer.  The reference runs four WGSL dispatches per frame
+// (main_terrain -> pt_restir_temporal -> pt_restir_spatial, plus a one-off main_terrain_gbuffer) with
+// one thread per pixel doing primary + shadow + IBL rays back to back.  Here a frame is a wavefront:
 //
-//   k_frame(f):  prev  = spatial_reuse(out_{f-1})      [pt_restir_spatial.wgsl:158-224, frame f-1's pass]
-//                prev  = M-clamp(prev)                 [hybrid_terrain_traversal.wgsl:452-462]
-//                spp x (primary, sun shadow, IBL occlusion) rays, candidate reservoir   [:467-555]
-//                out_f = temporal_reuse(prev, cand)    [pt_restir_temporal.wgsl:54-109]
-//                accum += mean radiance; windowed Welford                               [:557-574]
+//   k_primary (per pixel)   prev  = spatial_reuse(out_{f-1})      [pt_restir_spatial.wgsl:158-224, frame f-1's pass]
+//                           prev  = M-clamp(prev)                 [hybrid_terrain_traversal.wgsl:452-462]
+//                           primary ray (closest hit), shading set-up, candidate reservoir      [:467-512]
+//                           out_f = temporal_reuse(prev, cand)    [pt_restir_temporal.wgsl:54-109]
+//                           pixels that need a sun / IBL ray append their index to two COMPACTED
+//                           global ray lists (warp ballot + prefix sum, one atomic per warp)
+//   k_trace<sun>, k_trace<ibl> (persistent, per ray)  any-hit traversal [:514-545]; every lane pulls its
+//                           next ray from the list as soon as its current one finishes, so sky pixels,
+//                           back-facing hits and short rays never idle lanes next to long rays
+//   k_accum (per pixel)     combine, accumulate, windowed Welford                               [:547-574]
 //
-// so the `prev` and `curr` reservoir buffers of the reference never exist in HBM, and `out` is a
-// 16-byte record per pixel instead of 80 bytes: on this path every populated LightSample is the
-// one directional sun (direction == normalize(light_dir) bit-for-bit, light_index 0, intensity
-// constant), `position` is never read by anything that reaches an output, and the receiving
-// pixel's G-buffer test N.wi > 0 (pt_restir_spatial.wgsl:73-75) is a per-pixel constant that is
-// folded into one bit by k_gbuffer.  The RGBA16F beauty store of every frame (:576-579) is dead
-// until the last frame and is done once by k_resolve.  All arithmetic that reaches an output
-// follows the numerics contract, so results are bit-identical to the CPU oracle.
+// The `prev` and `curr` reservoir buffers of the reference never exist in HBM, and `out` is a 16-byte
+// record per pixel instead of 80 bytes: on this path every populated LightSample is the one
+// directional sun (direction == normalize(light_dir) bit-for-bit, light_index 0, intensity constant),
+// `position` is never read by anything that reaches an output, and the receiving pixel's G-buffer test
+// N.wi > 0 (pt_restir_spatial.wgsl:73-75) is a per-pixel constant folded into one bit by k_gbuffer.
+// The RGBA16F beauty store of every frame (:576-579) is dead until the last frame and is done once by
+// k_resolve.  All arithmetic that reaches an output follows the numerics contract, so results are
+// bit-identical to the CPU oracle.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -45,6 +50,15 @@ struct FrameParams {
     float4* resv_out;          // out_f
     const uint8_t* pixflags;   // bit0: G-buffer normal faces the sun; bits1-2: centre-ray hit type
     unsigned long long* counters;  // primary, shadow, ibl, nodes
+    // wavefront state
+    uint32_t sample_index;     // 0 .. spp-1 (one k_primary/k_trace/k_accum round per camera sample)
+    float4* rec;               // 4 x float4 per pixel, see PixelRec
+    uint8_t* occl_sun;         // per pixel: sun ray occluded
+    uint8_t* occl_ibl;         // per pixel: IBL ray occluded
+    uint32_t* q_sun;           // compacted pixel indices that need a sun ray
+    uint32_t* q_ibl;           // compacted pixel indices that need an IBL ray
+    uint32_t* q_counts;        // [0] n_sun [1] n_ibl [2] next_sun [3] next_ibl
+    float4* sstate;            // spp > 1 only: 3 x float4 per pixel (rng+cand, prev, partial radiance)
     // NVLink halo push: peer images of resv_out for the rank above / below (NULL = none)
     float4* peer_up;
     float4* peer_down;
@@ -180,44 +194,20 @@ __device__ __forceinline__ void warp_add_counters(unsigned long long* counters, 
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Shared-memory plan of k_frame / k_gbuffer (dynamic, sized by the host):
-//   stack   : stack_depth x 256 u32   traversal stacks, [depth][thread]
-//   ray_o   : 3 x 256 f32             secondary-ray origin of each pixel (shared by its two rays)
-//   ray_e   : 3 x 256 f32             IBL direction of each pixel
-//   q_sun   : 256 u8, q_ibl : 256 u8  compacted lists of pixel slots that need a sun / IBL ray
-//   occl    : 2 x 256 u8              results, indexed by pixel slot
-//   counts  : 2 u32
-// ---------------------------------------------------------------------------------------------
 constexpr int kThreads = kTileW * kTileH;
 
-__host__ __device__ inline size_t frame_smem_bytes(uint32_t stack_depth) {
-    return (size_t)stack_depth * kThreads * 4 + 6 * kThreads * 4 + 4 * kThreads + 16;
+// Dynamic shared memory of every traversal kernel: stack_depth x blockDim u32, [depth][thread].
+__host__ __device__ inline size_t stack_smem_bytes(uint32_t stack_depth, int threads) {
+    return (size_t)stack_depth * threads * 4;
 }
 
-struct SmemPlan {
-    uint32_t* stack;
-    float* ray_o;
-    float* ray_e;
-    uint8_t* q_sun;
-    uint8_t* q_ibl;
-    uint8_t* occl_sun;
-    uint8_t* occl_ibl;
-    uint32_t* counts;
-};
-
-__device__ __forceinline__ SmemPlan smem_plan(unsigned char* raw, uint32_t stack_depth) {
-    SmemPlan p;
-    p.stack = reinterpret_cast<uint32_t*>(raw);
-    p.ray_o = reinterpret_cast<float*>(p.stack + (size_t)stack_depth * kThreads);
-    p.ray_e = p.ray_o + 3 * kThreads;
-    p.q_sun = reinterpret_cast<uint8_t*>(p.ray_e + 3 * kThreads);
-    p.q_ibl = p.q_sun + kThreads;
-    p.occl_sun = p.q_ibl + kThreads;
-    p.occl_ibl = p.occl_sun + kThreads;
-    p.counts = reinterpret_cast<uint32_t*>(p.occl_ibl + kThreads);
-    return p;
-}
+// Per-pixel record written by k_primary (4 x float4, 128-bit accesses):
+//   rec[4*pix+0] = (shade_o.xyz, bits(flags))   shade_o = hit.point + n * 1e-3   (:526,:540)
+//   rec[4*pix+1] = (ei.xyz, reuse_w)            IBL direction, clamped reuse weight (:521,:539)
+//   rec[4*pix+2] = (sun_pre.xyz, ibl_pre.x)     sun_pre = albedo*light_color*nd (:531 before vis)
+//   rec[4*pix+3] = (ibl_pre.yz, 0, 0)           ibl_pre = albedo*env(ei) (:545 before env_vis); for a
+//                                               miss the slots hold the sky radiance (:489)
+constexpr uint32_t kRecHit = 1u, kRecSun = 2u, kRecSunReuseDir = 4u;
 
 // intersect_hybrid (hybrid_traversal.wgsl:175-201) on the production traversal.
 struct PrimaryHit { bool hit; uint32_t hit_type; float t; v3 point, normal; };
@@ -231,7 +221,7 @@ __device__ __forceinline__ PrimaryHit primary_hit(const FrameParams& P, const Ra
         if (mh.hit && mh.t < ph.t) { ph.hit = true; ph.hit_type = 0u; ph.t = mh.t; ph.point = mh.point; ph.normal = mh.normal; }
         tr.tmax = ph.t;
     }
-    const FastHit fh = trace_fast<false>(P.fast, tr, false, st, nodes);
+    const FastHit fh = trace_fast<false, false>(P.fast, tr, st, nodes);
     if (fh.hit && fh.t < ph.t) {
         ph.hit = true; ph.hit_type = 3u; ph.t = fh.t;
         finish_hit(P.fast, tr, fh, ph.point, ph.normal);
@@ -239,206 +229,280 @@ __device__ __forceinline__ PrimaryHit primary_hit(const FrameParams& P, const Ra
     return ph;
 }
 
-// intersect_hybrid_optimized(ray, 0.01, curv) + `hit && t < 1e30` (hybrid_traversal.wgsl:204-259)
-__device__ __forceinline__ bool occluded_fast(const FrameParams& P, const Ray& ray, bool curv, const SmemStack st, uint32_t& nodes) {
-    const float max_distance = 1e30f;
-    float best_t = ray.tmax;
-    bool best_hit = false;
-    if (P.scene.traversal_mode == 0u) {
-        const Hit mh = intersect_mesh(P.scene, ray);
-        if (mh.hit && mh.t < 0.01f) return mh.t < max_distance;
-        if (mh.hit && mh.t < best_t) { best_t = mh.t; best_hit = true; }
-    }
-    Ray tr = ray;
-    tr.tmax = best_t;
-    const FastHit fh = trace_fast<true>(P.fast, tr, curv && P.scene.curvature_enabled != 0u, st, nodes);
-    if (fh.hit && fh.t < best_t) { best_t = fh.t; best_hit = true; }
-    return best_hit && best_t < max_distance;
-}
-
 // ---------------------------------------------------------------------------------------------
-// k_frame: one accumulation frame (see the file header).  Per CTA = one 16x16 pixel tile:
-//   phase 0  per pixel : spatial reuse of last frame's records, M-clamp
-//   per sample:
-//   phase 1  per pixel : primary ray (closest hit), all lanes busy, coherent
-//   phase 2  per pixel : shading set-up; pixels that need a sun / IBL ray append their slot to the
-//                        CTA's compacted ray lists (warp ballot + prefix sum)
-//   phase 3  per ray   : any-hit traversal over the compacted lists -- sky pixels and back-facing
-//                        hits no longer idle lanes next to lanes that trace
-//   phase 4  per pixel : combine, accumulate
-//   then temporal reuse, halo push, accumulation and Welford.
+// k_primary: per pixel, one camera sample.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_frame(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemPlan sm = smem_plan(smem_raw, P.stack_depth);
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     SmemStack st;
-    st.base = sm.stack + tid;
+    st.base = reinterpret_cast<uint32_t*>(smem_raw) + tid;
     st.stride = kThreads;
 
     uint32_t gx, gy;
     const bool active = owned_pixel(P, gx, gy);
     const uint32_t pix = active ? gy * P.W + gx : 0u;
-    uint32_t n_primary = 0, n_shadow = 0, n_ibl = 0, n_nodes = 0;
+    uint32_t n_primary = 0, n_nodes = 0;
+    bool want_sun = false, want_ibl = false;
+    const uint32_t spp = max(P.spp, 1u), s = P.sample_index;
+    const bool multi = spp > 1u;
 
-    const SceneParams& S = P.scene;
-    const v3 light_color = ld3(P.light_color);
+    if (active) {
+        const SceneParams& S = P.scene;
+        const v3 light_color = ld3(P.light_color);
+        const v3 wi = normalize3(ld3(P.light_dir));
+
+        // ---- merged reservoir from last frame's reuse chain + M-clamp (:452-465) ----
+        Resv prev_r;
+        uint32_t rng;
+        Resv cand;
+        cand.w_sum = 0.0f; cand.weight = 0.0f; cand.target_pdf = 0.0f; cand.m = 0u; cand.type1 = false;
+        if (s == 0u) {
+            prev_r.w_sum = 0.0f; prev_r.weight = 0.0f; prev_r.target_pdf = 0.0f; prev_r.m = 0u; prev_r.type1 = false;
+            const bool facing = (P.pixflags[pix] & 1u) != 0u;
+            if (P.frame_index > 0u) prev_r = spatial_reuse(P, P.resv_in, gx, gy, facing, P.frame_index - 1u);
+            if (prev_r.m > 512u) {
+                const float scale = fdiv(512.0f, (float)prev_r.m);
+                prev_r.w_sum = prev_r.w_sum * scale;
+                prev_r.m = 512u;
+                if (prev_r.target_pdf > 0.0f) prev_r.weight = fdiv(prev_r.w_sum, (float)prev_r.m * prev_r.target_pdf);
+            }
+            rng = P.seed_hi ^ (gx * 1664525u) ^ (gy * 1013904223u) ^ (P.frame_index * 92837111u) ^ P.seed_lo;
+            if (multi) P.sstate[3 * (size_t)pix + 1] = pack_resv(prev_r);
+        } else {
+            const float4 a = P.sstate[3 * (size_t)pix + 0];
+            rng = __float_as_uint(a.x);
+            cand.w_sum = a.y;
+            const uint32_t mb = __float_as_uint(a.z);
+            cand.m = mb & 0x7FFFFFFFu; cand.type1 = (mb >> 31) != 0u;
+            cand.target_pdf = a.w;
+            prev_r = unpack_resv(P.sstate[3 * (size_t)pix + 1]);
+        }
+        const bool prev_valid = P.frame_index > 0u && prev_r.m > 0u && prev_r.weight > 0.0f &&
+                                prev_r.target_pdf > 0.0f && prev_r.type1;
+        // every populated sample stores direction == wi; the shader re-normalises it (:520)
+        const v3 sun_dir = prev_valid ? normalize3(wi) : wi;
+        const float reuse_w = prev_valid ? clampf(prev_r.weight, 0.0f, 4.0f) : 1.0f;
+
+        // ---- primary ray (:476-491) ----
+        const float jx = tent_offset(xorshift32(rng)) * 0.5f;
+        const float jy = tent_offset(xorshift32(rng)) * 0.5f;
+        const Ray ray = camera_ray(P, gx, gy, jx, jy);
+        n_primary++;
+        const PrimaryHit hit = primary_hit(P, ray, st, n_nodes);
+        float4* rec = P.rec + 4 * (size_t)pix;
+        if (!hit.hit) {
+            const v3 sky = env_radiance(S, ray.d);
+            rec[0] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+            rec[2] = make_float4(0.0f, 0.0f, 0.0f, sky.x);
+            rec[3] = make_float4(sky.y, sky.z, 0.0f, 0.0f);
+        } else {
+            // ---- shading set-up (:492-545 without the two visibility factors) ----
+            const v3 n = hit.normal;
+            const v3 albedo = hit.hit_type == 3u ? ld3(S.albedo) : V3(0.7f, 0.7f, 0.8f);
+            const float ndotl = fmaxf(dot3(n, wi), 0.0f);
+            const float target_pdf = luminance((albedo * light_color) * ndotl);
+            if (target_pdf > 0.0f) {
+                cand.type1 = true;
+                cand.w_sum = cand.w_sum + target_pdf;
+                cand.m = cand.m + 1u;
+                cand.target_pdf = target_pdf;
+            }
+            const float nd = fmaxf(dot3(n, sun_dir), 0.0f);
+            const v3 shade_o = hit.point + n * 1e-3f;
+            v3 sun_pre = V3(0, 0, 0);
+            uint32_t flags = kRecHit;
+            if (nd > 0.0f) {
+                want_sun = true;
+                sun_pre = (albedo * light_color) * nd;
+                flags |= kRecSun | (prev_valid ? kRecSunReuseDir : 0u);
+            }
+            const float u1 = xorshift32(rng);
+            const float u2 = xorshift32(rng);
+            const v3 ei = cosine_dir(n, u1, u2);
+            want_ibl = true;
+            const v3 ibl_pre = albedo * env_radiance(S, ei);
+            rec[0] = make_float4(shade_o.x, shade_o.y, shade_o.z, __uint_as_float(flags));
+            rec[1] = make_float4(ei.x, ei.y, ei.z, reuse_w);
+            rec[2] = make_float4(sun_pre.x, sun_pre.y, sun_pre.z, ibl_pre.x);
+            rec[3] = make_float4(ibl_pre.y, ibl_pre.z, 0.0f, 0.0f);
+        }
+
+        if (s + 1u < spp) {
+            P.sstate[3 * (size_t)pix + 0] = make_float4(__uint_as_float(rng), cand.w_sum,
+                                                        __uint_as_float(cand.m | (cand.type1 ? 0x80000000u : 0u)), cand.target_pdf);
+        } else {
+            // ---- finalise candidate, temporal reuse, publish out_f (+ NVLink halo push) (:551-555) ----
+            if (cand.m > 0u && cand.w_sum > 0.0f && cand.target_pdf > 0.0f)
+                cand.weight = fdiv(cand.w_sum, (float)cand.m * cand.target_pdf);
+            const float4 out_rec = pack_resv(temporal_reuse(prev_r, cand));
+            __stcg(P.resv_out + pix, out_rec);
+            if (P.part_world > 1u) {
+                const uint32_t b = gy / P.block_rows, in_y = gy - b * P.block_rows;
+                if (in_y < 3u && b > 0u && P.peer_up) __stcg(P.peer_up + pix, out_rec);
+                if (in_y + 3u >= P.block_rows && b + 1u < P.nblocks && P.peer_down) __stcg(P.peer_down + pix, out_rec);
+            }
+        }
+    }
+    // ---- ray compaction: append this pixel to the global sun / IBL lists ----
+    {
+        const uint32_t m_sun = __ballot_sync(0xFFFFFFFFu, want_sun), m_ibl = __ballot_sync(0xFFFFFFFFu, want_ibl);
+        uint32_t b_sun = 0u, b_ibl = 0u;
+        if (lane == 0u) {
+            if (m_sun) b_sun = atomicAdd(P.q_counts + 0, (uint32_t)__popc(m_sun));
+            if (m_ibl) b_ibl = atomicAdd(P.q_counts + 1, (uint32_t)__popc(m_ibl));
+        }
+        b_sun = __shfl_sync(0xFFFFFFFFu, b_sun, 0);
+        b_ibl = __shfl_sync(0xFFFFFFFFu, b_ibl, 0);
+        const uint32_t lt = (1u << lane) - 1u;
+        if (want_sun) P.q_sun[b_sun + __popc(m_sun & lt)] = pix;
+        if (want_ibl) P.q_ibl[b_ibl + __popc(m_ibl & lt)] = pix;
+    }
+    warp_add_counters(P.counters, n_primary, 0u, 0u, n_nodes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_trace<IS_SUN, CURV>: persistent any-hit traversal over one compacted ray list
+// (intersect_shadow_ray / intersect_ibl_occlusion_ray, hybrid_traversal.wgsl:204-259).
+// Each lane owns one ray at a time; when fewer than kRefillBelow lanes of a warp still traverse,
+// the idle lanes pull fresh rays (one atomic per warp).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTraceCtaThreads = 256;
+constexpr int kRefillBelow = 24;
+
+template <bool IS_SUN, bool CURV>
+__global__ void __launch_bounds__(kTraceCtaThreads) k_trace(const __grid_constant__ FrameParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    SmemStack st;
+    st.base = reinterpret_cast<uint32_t*>(smem_raw) + tid;
+    st.stride = kTraceCtaThreads;
+    const FastScene& F = P.fast;
+    const uint32_t n = P.q_counts[IS_SUN ? 0 : 1];
+    const uint32_t* __restrict__ queue = IS_SUN ? P.q_sun : P.q_ibl;
+    uint32_t* next = P.q_counts + (IS_SUN ? 2 : 3);
+    uint8_t* __restrict__ occl = IS_SUN ? P.occl_sun : P.occl_ibl;
     const v3 wi = normalize3(ld3(P.light_dir));
+    const v3 wi_reuse = normalize3(wi);
+    const bool has_mesh = P.scene.traversal_mode == 0u;
 
-    // ---- phase 0: merged reservoir from last frame's reuse chain + M-clamp (:452-465) ----
-    Resv prev_r;
-    prev_r.w_sum = 0.0f; prev_r.weight = 0.0f; prev_r.target_pdf = 0.0f; prev_r.m = 0u; prev_r.type1 = false;
-    bool prev_valid = false;
-    uint32_t rng = 0u;
-    if (active) {
-        const bool facing = (P.pixflags[pix] & 1u) != 0u;
-        if (P.frame_index > 0u) prev_r = spatial_reuse(P, P.resv_in, gx, gy, facing, P.frame_index - 1u);
-        if (prev_r.m > 512u) {
-            const float scale = fdiv(512.0f, (float)prev_r.m);
-            prev_r.w_sum = prev_r.w_sum * scale;
-            prev_r.m = 512u;
-            if (prev_r.target_pdf > 0.0f) prev_r.weight = fdiv(prev_r.w_sum, (float)prev_r.m * prev_r.target_pdf);
-        }
-        prev_valid = P.frame_index > 0u && prev_r.m > 0u && prev_r.weight > 0.0f && prev_r.target_pdf > 0.0f && prev_r.type1;
-        rng = P.seed_hi ^ (gx * 1664525u) ^ (gy * 1013904223u) ^ (P.frame_index * 92837111u) ^ P.seed_lo;
-    }
-    // every populated sample stores direction == wi; the shader re-normalises it (:520)
-    const v3 sun_dir_reuse = normalize3(wi);
-    const v3 sun_dir = prev_valid ? sun_dir_reuse : wi;
-    const float reuse_w = prev_valid ? clampf(prev_r.weight, 0.0f, 4.0f) : 1.0f;
+    TraceState T;
+    T.sp = 0u;
+    bool busy = false, mesh_occl = false;
+    uint32_t pix = 0u;
+    bool exhausted = false;
+    uint32_t n_rays = 0, n_nodes = 0;
 
-    v3 frame_radiance = V3(0, 0, 0);
-    Resv cand;
-    cand.w_sum = 0.0f; cand.weight = 0.0f; cand.target_pdf = 0.0f; cand.m = 0u; cand.type1 = false;
-    const uint32_t spp = max(P.spp, 1u);
-
-#pragma unroll 1
-    for (uint32_t s = 0; s < spp; s++) {
-        if (tid < 2u) sm.counts[tid] = 0u;
-        __syncthreads();
-        // ---- phase 1: primary ray ----
-        bool want_sun = false, want_ibl = false;
-        v3 sun_pre = V3(0, 0, 0), ibl_pre = V3(0, 0, 0);    // contributions before the visibility factor
-        if (active) {
-            const float jx = tent_offset(xorshift32(rng)) * 0.5f;
-            const float jy = tent_offset(xorshift32(rng)) * 0.5f;
-            const Ray ray = camera_ray(P, gx, gy, jx, jy);
-            n_primary++;
-            const PrimaryHit hit = primary_hit(P, ray, st, n_nodes);
-            if (!hit.hit) {
-                frame_radiance = frame_radiance + env_radiance(S, ray.d);
-            } else {
-                // ---- phase 2: shading set-up ----
-                const v3 n = hit.normal;
-                const v3 albedo = hit.hit_type == 3u ? ld3(S.albedo) : V3(0.7f, 0.7f, 0.8f);
-                const float ndotl = fmaxf(dot3(n, wi), 0.0f);
-                const float target_pdf = luminance((albedo * light_color) * ndotl);
-                if (target_pdf > 0.0f) {
-                    cand.type1 = true;
-                    cand.w_sum = cand.w_sum + target_pdf;
-                    cand.m = cand.m + 1u;
-                    cand.target_pdf = target_pdf;
+    while (true) {
+        // ---- refill idle lanes ----
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        if (idle != 0u && !exhausted) {
+            const uint32_t n_idle = (uint32_t)__popc(idle);
+            uint32_t base = 0u;
+            if (lane == 0u) base = atomicAdd(next, n_idle);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base + n_idle >= n) exhausted = true;
+            if (!busy) {
+                const uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    pix = __ldg(queue + idx);
+                    const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix);
+                    Ray r;
+                    r.o = V3(r0.x, r0.y, r0.z);
+                    r.tmin = 1e-3f;
+                    r.tmax = 1e30f;
+                    if (IS_SUN) r.d = (__float_as_uint(r0.w) & kRecSunReuseDir) ? wi_reuse : wi;
+                    else { const float4 r1 = __ldcg(P.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
+                    n_rays++;
+                    mesh_occl = false;
+                    bool decided = false;
+                    if (has_mesh) {                      // intersect_hybrid_optimized :213-221
+                        const Hit mh = intersect_mesh(P.scene, r);
+                        if (mh.hit && mh.t < 0.01f) { occl[pix] = 1u; decided = true; }
+                        else if (mh.hit && mh.t < r.tmax) { r.tmax = mh.t; mesh_occl = true; }
+                    }
+                    if (!decided) {
+                        trace_begin<CURV>(F, r, T, st);
+                        if (T.sp == 0u) occl[pix] = mesh_occl ? 1u : 0u;
+                        else busy = true;
+                    }
                 }
-                const float nd = fmaxf(dot3(n, sun_dir), 0.0f);
-                const v3 shade_o = hit.point + n * 1e-3f;
-                sm.ray_o[tid] = shade_o.x; sm.ray_o[kThreads + tid] = shade_o.y; sm.ray_o[2 * kThreads + tid] = shade_o.z;
-                if (nd > 0.0f) {
-                    want_sun = true;
-                    sun_pre = (albedo * light_color) * nd;
-                    sm.occl_sun[tid] = prev_valid ? 2u : 0u;   // tells phase 3 which sun direction this pixel uses
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, busy) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- traverse until enough lanes have gone idle ----
+        while (true) {
+            while (busy && T.sp != 0u && !top_is_leaf(T, st)) { expand_top<true, CURV>(F, T, st); n_nodes++; }
+            if (busy) {
+                bool done = false, hit = false;
+                if (T.sp == 0u) done = true;
+                else {
+                    n_nodes++;
+                    hit = leaf_top<true, CURV>(F, T, st);
+                    done = hit || T.sp == 0u;
                 }
-                const float u1 = xorshift32(rng);
-                const float u2 = xorshift32(rng);
-                const v3 ei = cosine_dir(n, u1, u2);
-                sm.ray_e[tid] = ei.x; sm.ray_e[kThreads + tid] = ei.y; sm.ray_e[2 * kThreads + tid] = ei.z;
-                want_ibl = true;
-                ibl_pre = albedo * env_radiance(S, ei);
+                if (done) { occl[pix] = (hit || mesh_occl) ? 1u : 0u; busy = false; }
             }
+            const uint32_t live = __ballot_sync(0xFFFFFFFFu, busy);
+            if (live == 0u) break;
+            if (!exhausted && __popc(live) < kRefillBelow) break;
         }
-        // compaction: append this pixel's slot to the sun / IBL lists
-        {
-            const uint32_t m_sun = __ballot_sync(0xFFFFFFFFu, want_sun), m_ibl = __ballot_sync(0xFFFFFFFFu, want_ibl);
-            uint32_t b_sun = 0u, b_ibl = 0u;
-            if (lane == 0u) {
-                if (m_sun) b_sun = atomicAdd(&sm.counts[0], (uint32_t)__popc(m_sun));
-                if (m_ibl) b_ibl = atomicAdd(&sm.counts[1], (uint32_t)__popc(m_ibl));
-            }
-            b_sun = __shfl_sync(0xFFFFFFFFu, b_sun, 0);
-            b_ibl = __shfl_sync(0xFFFFFFFFu, b_ibl, 0);
-            const uint32_t lt = (1u << lane) - 1u;
-            if (want_sun) sm.q_sun[b_sun + __popc(m_sun & lt)] = (uint8_t)tid;
-            if (want_ibl) sm.q_ibl[b_ibl + __popc(m_ibl & lt)] = (uint8_t)tid;
-        }
-        __syncthreads();
-        // ---- phase 3: any-hit rays over the compacted lists ----
-        {
-            const uint32_t n_sun = sm.counts[0], n_all = n_sun + sm.counts[1];
-            for (uint32_t i = tid; i < n_all; i += kThreads) {
-                const bool is_sun = i < n_sun;
-                const uint32_t slot = is_sun ? sm.q_sun[i] : sm.q_ibl[i - n_sun];
-                Ray sr;
-                sr.o = V3(sm.ray_o[slot], sm.ray_o[kThreads + slot], sm.ray_o[2 * kThreads + slot]);
-                sr.tmin = 1e-3f;
-                sr.tmax = 1e30f;
-                // the sun ray of a pixel uses that pixel's sun_dir (reuse-normalised or not): recompute from its flag
-                if (is_sun) sr.d = (sm.occl_sun[slot] & 2u) ? sun_dir_reuse : wi;
-                else sr.d = V3(sm.ray_e[slot], sm.ray_e[kThreads + slot], sm.ray_e[2 * kThreads + slot]);
-                const bool occ = occluded_fast(P, sr, is_sun, st, n_nodes);
-                if (is_sun) { sm.occl_sun[slot] = occ ? 1u : 0u; n_shadow++; }
-                else { sm.occl_ibl[slot] = occ ? 1u : 0u; n_ibl++; }
-            }
-        }
-        __syncthreads();
-        // ---- phase 4: combine (:523-547) ----
-        if (active) {
-            v3 sun = V3(0, 0, 0), ibl = V3(0, 0, 0);
-            if (want_sun) {
-                const float vis = sm.occl_sun[tid] ? 0.0f : 1.0f;
-                sun = (sun_pre * vis) * reuse_w;
-            }
-            if (want_ibl) {
-                const float env_vis = sm.occl_ibl[tid] ? 0.0f : 1.0f;
-                ibl = ibl_pre * env_vis;
-                frame_radiance = (frame_radiance + sun) + ibl;
-            }
-        }
-        __syncthreads();
     }
+    warp_add_counters(P.counters, 0u, IS_SUN ? n_rays : 0u, IS_SUN ? 0u : n_rays, n_nodes);
+}
 
-    if (active) {
-        const float fspp = (float)spp;
-        frame_radiance = V3(fdiv(frame_radiance.x, fspp), fdiv(frame_radiance.y, fspp), fdiv(frame_radiance.z, fspp));
-
-        // ---- finalise candidate, temporal reuse, publish out_f (+ NVLink halo push) ----
-        if (cand.m > 0u && cand.w_sum > 0.0f && cand.target_pdf > 0.0f)
-            cand.weight = fdiv(cand.w_sum, (float)cand.m * cand.target_pdf);
-        const float4 out_rec = pack_resv(temporal_reuse(prev_r, cand));
-        __stcg(P.resv_out + pix, out_rec);
-        if (P.part_world > 1u) {
-            const uint32_t b = gy / P.block_rows, in_y = gy - b * P.block_rows;
-            if (in_y < 3u && b > 0u && P.peer_up) __stcg(P.peer_up + pix, out_rec);
-            if (in_y + 3u >= P.block_rows && b + 1u < P.nblocks && P.peer_down) __stcg(P.peer_down + pix, out_rec);
+// ---------------------------------------------------------------------------------------------
+// k_accum: per pixel, combine one camera sample (:523-549) and, after the last sample, accumulate
+// and update the windowed Welford statistics (:557-574).  Also re-arms the ray-list counters.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_accum(const __grid_constant__ FrameParams P) {
+    uint32_t gx, gy;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4u) P.q_counts[threadIdx.x] = 0u;
+    if (!owned_pixel(P, gx, gy)) return;
+    const uint32_t pix = gy * P.W + gx;
+    const uint32_t spp = max(P.spp, 1u), s = P.sample_index;
+    const float4* rec = P.rec + 4 * (size_t)pix;
+    const float4 r0 = __ldcg(rec), r2 = __ldcg(rec + 2), r3 = __ldcg(rec + 3);
+    const uint32_t flags = __float_as_uint(r0.w);
+    v3 fr = V3(0, 0, 0);
+    if (s > 0u) { const float4 c = P.sstate[3 * (size_t)pix + 2]; fr = V3(c.x, c.y, c.z); }
+    if (!(flags & kRecHit)) {
+        fr = fr + V3(r2.w, r3.x, r3.y);                       // sky radiance (:489)
+    } else {
+        const float4 r1 = __ldcg(rec + 1);
+        v3 sun = V3(0, 0, 0);
+        if (flags & kRecSun) {
+            const float vis = P.occl_sun[pix] ? 0.0f : 1.0f;
+            sun = (V3(r2.x, r2.y, r2.z) * vis) * r1.w;           // albedo*light_color*nd*vis*reuse_w (:531)
         }
-
-        // ---- accumulate + windowed Welford over the running-mean luminance (:557-574) ----
-        float4 acc = P.accum[pix];
-        acc.x = acc.x + frame_radiance.x;
-        acc.y = acc.y + frame_radiance.y;
-        acc.z = acc.z + frame_radiance.z;
-        acc.w = acc.w + 1.0f;
-        P.accum[pix] = acc;
-
-        const uint32_t window = max(P.window, 2u);
-        float2 wf = P.welford[pix];
-        if (P.frame_index % window == 0u) wf = make_float2(0.0f, 0.0f);
-        const float mean_lum = luminance(V3(fdiv(acc.x, acc.w), fdiv(acc.y, acc.w), fdiv(acc.z, acc.w)));
-        const float k = (float)(P.frame_index % window) + 1.0f;
-        const float delta = mean_lum - wf.x;
-        const float mean = wf.x + fdiv(delta, k);
-        const float m2 = wf.y + delta * (mean_lum - mean);
-        P.welford[pix] = make_float2(mean, m2);
+        const float env_vis = P.occl_ibl[pix] ? 0.0f : 1.0f;
+        const v3 ibl = V3(r2.w, r3.x, r3.y) * env_vis;           // albedo*env(ei)*env_vis (:545)
+        fr = (fr + sun) + ibl;
     }
-    warp_add_counters(P.counters, n_primary, n_shadow, n_ibl, n_nodes);
+    if (s + 1u < spp) {
+        P.sstate[3 * (size_t)pix + 2] = make_float4(fr.x, fr.y, fr.z, 0.0f);
+        return;
+    }
+    const float fspp = (float)spp;
+    fr = V3(fdiv(fr.x, fspp), fdiv(fr.y, fspp), fdiv(fr.z, fspp));
+    float4 acc = P.accum[pix];
+    acc.x = acc.x + fr.x;
+    acc.y = acc.y + fr.y;
+    acc.z = acc.z + fr.z;
+    acc.w = acc.w + 1.0f;
+    P.accum[pix] = acc;
+    const uint32_t window = max(P.window, 2u);
+    float2 wf = P.welford[pix];
+    if (P.frame_index % window == 0u) wf = make_float2(0.0f, 0.0f);
+    const float mean_lum = luminance(V3(fdiv(acc.x, acc.w), fdiv(acc.y, acc.w), fdiv(acc.z, acc.w)));
+    const float k = (float)(P.frame_index % window) + 1.0f;
+    const float delta = mean_lum - wf.x;
+    const float mean = wf.x + fdiv(delta, k);
+    const float m2 = wf.y + delta * (mean_lum - mean);
+    P.welford[pix] = make_float2(mean, m2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -453,9 +517,8 @@ struct GbufferOut {
 
 __global__ void __launch_bounds__(kThreads) k_gbuffer(const __grid_constant__ FrameParams P, GbufferOut G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SmemPlan sm = smem_plan(smem_raw, P.stack_depth);
     SmemStack st;
-    st.base = sm.stack + threadIdx.x;
+    st.base = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
     st.stride = kThreads;
     uint32_t gx, gy;
     if (!owned_pixel(P, gx, gy)) return;
@@ -661,8 +724,8 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_rays(SceneParams S, Fas
         st.base = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
         st.stride = kTraceThreads;
         FastHit fh;
-        if (any_hit) fh = trace_fast<true>(F, r, curv, st, nodes);
-        else fh = trace_fast<false>(F, r, false, st, nodes);
+        if (any_hit) fh = curv ? trace_fast<true, true>(F, r, st, nodes) : trace_fast<true, false>(F, r, st, nodes);
+        else fh = trace_fast<false, false>(F, r, st, nodes);
         h_hit = fh.hit; h_t = fh.t;
         if (fh.hit) { v3 p; finish_hit(F, r, fh, p, h_n); }
     } else {

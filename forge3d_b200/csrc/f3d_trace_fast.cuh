@@ -13,13 +13,15 @@
 //    return at their first hit, so for them it always is.  A closest-hit ray marks every entry
 //    already on the stack as STALE when it records a hit; stale entries are re-tested at pop with
 //    the new best_t (their own [min,max] is re-read), exactly what the WGSL does for every entry.
+//    (Closest-hit rays never carry the curvature term on this path -- hybrid_traversal.wgsl:248-259,
+//    hybrid_terrain_traversal.wgsl:374-376 -- so the production closest-hit instance is CURV=false.)
 //  * Each node's six slab planes (x0, xm, x1, z0, zm, z1) are computed once; the 4 children's
 //    spans are min/max combinations of those six ray parameters -- the identical float
 //    expressions the WGSL evaluates 16 times (4 children x 4 planes).
 //  * The stack holds 32-bit node ids in SHARED memory, laid out [depth][thread] (conflict-free),
 //    not in a per-thread local array.
-//  * while-while: a warp keeps expanding internal nodes until every lane either holds a leaf on
-//    top of its stack or is finished, then all those lanes run the bilinear-patch solve together.
+//  * The traversal is a resumable state machine (TraceState + expand_top / leaf_top) so that the
+//    persistent k_trace kernel can refill idle lanes with new rays between steps.
 //  * The hit point / normal are computed after the loop from the winning cell (same expressions).
 #pragma once
 #include "f3d_trace.cuh"
@@ -28,7 +30,7 @@ namespace f3d {
 
 struct FastHit { float t; uint32_t cx, cz; bool hit; };
 
-// Shared-memory stack accessor: entry (depth, thread) at base[depth * stride + lane_slot].
+// Shared-memory stack accessor: entry `depth` of this thread at base[depth * stride].
 struct SmemStack {
     uint32_t* base;      // already offset to this thread's column
     uint32_t stride;     // threads per CTA
@@ -51,210 +53,238 @@ struct FastScene {
     float inv_two_r_prime;
 };
 
+// Per-ray traversal state.
+struct TraceState {
+    v3 o, d;
+    float tmin, tmax;
+    float inv_x, inv_z;      // terrain_safe_inv of the direction (:88-91)
+    float hd2;               // dot(dir.xz, dir.xz)
+    float vertex;            // parameter of the curved ray's lowest point (:120), CURV only
+    bool use_vertex;         // CURV && a > 0 (:119)
+    float best_t;            // res.t
+    uint32_t best_cx, best_cz;
+    bool hit;
+    uint32_t sp;             // entries on the stack
+    uint32_t stale_sp;       // closest-hit only: entries below this index predate the last hit
+};
+
+template <bool CURV>
+__device__ __forceinline__ float ray_height(const FastScene& S, const TraceState& T, float t) {   // :95-103
+    float corr = 0.0f;
+    if (CURV) corr = (t * t * T.hd2) * S.inv_two_r_prime;
+    return T.o.y + t * T.d.y + corr;
+}
+
+template <bool CURV>
+__device__ __forceinline__ bool band_ok(const FastScene& S, const TraceState& T, float tl, float th, float2 mm) {  // :303-304, :108-127
+    const float y0 = ray_height<CURV>(S, T, tl), y1 = ray_height<CURV>(S, T, th);
+    float lo = fminf(y0, y1);
+    if (CURV) {
+        if (T.use_vertex && T.vertex >= tl && T.vertex <= th) lo = fminf(lo, ray_height<true>(S, T, T.vertex));
+    }
+    const float hi = fmaxf(y0, y1);
+    return !(lo > mm.y || hi < mm.x);
+}
+
+// Sets up a ray and performs the root's pop-time tests (:288-304); leaves the root on the stack if it
+// survives.
+template <bool CURV>
+__device__ __forceinline__ void trace_begin(const FastScene& S, const Ray& r, TraceState& T, const SmemStack st) {
+    T.o = r.o; T.d = r.d; T.tmin = r.tmin; T.tmax = r.tmax;
+    T.inv_x = safe_inv(r.d.x); T.inv_z = safe_inv(r.d.z);
+    T.hd2 = dot2(r.d.x, r.d.z, r.d.x, r.d.z);
+    T.use_vertex = false; T.vertex = 0.0f;
+    if (CURV) {
+        const float a = T.hd2 * S.inv_two_r_prime;
+        T.use_vertex = a > 0.0f;
+        if (T.use_vertex) T.vertex = fdiv(-r.d.y, 2.0f * a);
+    }
+    T.best_t = r.tmax; T.best_cx = 0u; T.best_cz = 0u; T.hit = false;
+    T.sp = 0u; T.stale_sp = 0u;
+    const uint32_t level = S.mip_count - 1u;
+    const uint32_t cx1 = min(1u << level, S.cell_w), cz1 = min(1u << level, S.cell_h);
+    // ox + f32(0) * sx == ox exactly
+    const float a0 = (S.ox - T.o.x) * T.inv_x, a1 = ((S.ox + (float)cx1 * S.sx) - T.o.x) * T.inv_x;
+    const float b0 = (S.oz - T.o.z) * T.inv_z, b1 = ((S.oz + (float)cz1 * S.sz) - T.o.z) * T.inv_z;
+    const float s0 = fmaxf(fminf(a0, a1), fminf(b0, b1)), s1 = fminf(fmaxf(a0, a1), fmaxf(b0, b1));
+    const float tl = fmaxf(s0, T.tmin), th = fminf(s1, fminf(T.tmax, T.best_t));
+    if (tl <= th && band_ok<CURV>(S, T, tl, th, S.root_mm)) { st.at(0) = pack_node(level, 0u, 0u); T.sp = 1u; }
+}
+
+__device__ __forceinline__ bool top_is_leaf(const TraceState& T, const SmemStack st) {
+    return (st.at(T.sp - 1u) >> 26) == 0u;
+}
+
 // One sorting-network comparator for the (t desc, original index asc) total order that the
-// WGSL's stable insertion sort (:351-363) realises.  a must end up "before" b.
+// WGSL's stable insertion sort (:351-363) realises.
 __device__ __forceinline__ void cmpswap(float& ta, uint32_t& ia, float& tb, uint32_t& ib) {
-    // swap when b should come before a: tb > ta, or equal keys with smaller original index
-    const bool sw = (tb > ta) || (tb == ta && (ib & 3u) < (ia & 3u));
+    const bool sw = (tb > ta) || (tb == ta && ib < ia);
     const float t0 = sw ? tb : ta, t1 = sw ? ta : tb;
     const uint32_t i0 = sw ? ib : ia, i1 = sw ? ia : ib;
     ta = t0; tb = t1; ia = i0; ib = i1;
 }
 
-template <bool ANY_HIT>
-__device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, const bool curv, const SmemStack st,
-                                              uint32_t& nodes) {
-    FastHit res;
-    res.hit = false;
-    res.t = r.tmax;
-    res.cx = 0; res.cz = 0;
-    const float inv_x = safe_inv(r.d.x), inv_z = safe_inv(r.d.z);
-    const float hd2 = dot2(r.d.x, r.d.z, r.d.x, r.d.z);
-    const float ca = curv ? hd2 * S.inv_two_r_prime : 0.0f;       // curvature coefficient `a` (:118)
-    const bool use_vertex = curv && ca > 0.0f;
-    const float vertex = use_vertex ? fdiv(-r.d.y, 2.0f * ca) : 0.0f;
+// Pops the internal node on top of the stack and pushes its surviving children (:320-369 with the
+// children's pop tests of :281-304 folded in).  Precondition: sp > 0 and the top is not a leaf.
+template <bool ANY_HIT, bool CURV>
+__device__ __forceinline__ void expand_top(const FastScene& S, TraceState& T, const SmemStack st) {
+    T.sp--;
+    const uint32_t node = st.at(T.sp);
+    const uint32_t level = node >> 26, ny = (node >> 13) & 0x1FFFu, nx = node & 0x1FFFu;
+    const uint32_t cl = level - 1u;
     const uint32_t cell_w = S.cell_w, cell_h = S.cell_h;
-
-    auto height = [&](float t) -> float {                          // terrain_curved_height :95-103
-        const float corr = curv ? (t * t * hd2) * S.inv_two_r_prime : 0.0f;
-        return r.o.y + t * r.d.y + corr;
-    };
-    auto band_ok = [&](float tl, float th, float2 mm) -> bool {    // :303-304 with :108-127
-        const float y0 = height(tl), y1 = height(th);
-        float lo = fminf(y0, y1);
-        if (use_vertex && vertex >= tl && vertex <= th) lo = fminf(lo, height(vertex));
-        const float hi = fmaxf(y0, y1);
-        return !(lo > mm.y || hi < mm.x);
-    };
-
-    uint32_t sp = 0;          // entries on the stack
-    uint32_t stale_sp = 0;    // entries below this index predate the last recorded hit
-    // ---- root: the pop-time tests of :288-304 done once, then it is a fresh entry ----
-    {
-        const uint32_t level = S.mip_count - 1u;
-        const uint32_t cx1 = min(1u << level, cell_w), cz1 = min(1u << level, cell_h);
-        const float a0 = (S.ox - r.o.x) * inv_x, a1 = ((S.ox + (float)cx1 * S.sx) - r.o.x) * inv_x;
-        const float b0 = (S.oz - r.o.z) * inv_z, b1 = ((S.oz + (float)cz1 * S.sz) - r.o.z) * inv_z;
-        // note: ox + f32(0)*sx == ox exactly
-        const float s0 = fmaxf(fminf(a0, a1), fminf(b0, b1)), s1 = fminf(fmaxf(a0, a1), fmaxf(b0, b1));
-        const float tl = fmaxf(s0, r.tmin), th = fminf(s1, fminf(r.tmax, res.t));
-        if (tl <= th && band_ok(tl, th, S.root_mm)) { st.at(0) = pack_node(level, 0u, 0u); sp = 1; }
-    }
-
-    while (sp != 0u) {
-        // ================= phase A: expand internal nodes until a leaf is on top =================
-        while (sp != 0u) {
-            const uint32_t node = st.at(sp - 1u);
-            const uint32_t level = node >> 26;
-            if (level == 0u) break;
-            sp--;
-            nodes++;
-            const uint32_t ny = (node >> 13) & 0x1FFFu, nx = node & 0x1FFFu;
-            const uint32_t cl = level - 1u;
-            // integer cell planes of this node and its mid-lines (children's gx0/gx1, :330-334)
-            const uint32_t cx0 = nx << level, cz0 = ny << level;
-            const uint32_t cx1 = min((nx + 1u) << level, cell_w), cz1 = min((ny + 1u) << level, cell_h);
-            const uint32_t mxu = (2u * nx + 1u) << cl, mzu = (2u * ny + 1u) << cl;
-            const bool has_x1 = mxu < cell_w, has_z1 = mzu < cell_h;       // child column/row 1 exists (:332)
-            const uint32_t cxm = min(mxu, cell_w), czm = min(mzu, cell_h);
-            // ray parameters at the six planes
-            const float a0 = ((S.ox + (float)cx0 * S.sx) - r.o.x) * inv_x;
-            const float am = ((S.ox + (float)cxm * S.sx) - r.o.x) * inv_x;
-            const float a1 = ((S.ox + (float)cx1 * S.sx) - r.o.x) * inv_x;
-            const float b0 = ((S.oz + (float)cz0 * S.sz) - r.o.z) * inv_z;
-            const float bm = ((S.oz + (float)czm * S.sz) - r.o.z) * inv_z;
-            const float b1 = ((S.oz + (float)cz1 * S.sz) - r.o.z) * inv_z;
-            // this node's own clipped span (:288-297); needed to clip the children (:342-343)
-            const float tcap = fminf(r.tmax, res.t);
-            const float t_lo = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), r.tmin);
-            const float t_hi = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), tcap);
-            if (!ANY_HIT) {
-                if (sp < stale_sp) {              // entry predates the last hit: redo the pop tests (:297-304)
-                    stale_sp = sp;
-                    if (t_lo > t_hi) continue;
-                    float2 mm;
-                    if (level == S.mip_count - 1u) mm = S.root_mm;
-                    else mm = __ldg(S.q.lv[level] + (((size_t)(ny >> 1) * S.q.parent_pitch[level] + (nx >> 1)) * 4u + ((ny & 1u) * 2u + (nx & 1u))));
-                    if (!band_ok(t_lo, t_hi, mm)) continue;
-                }
-            }
-            // children's [min,max]: one 32-byte quad
-            const float4* qp = reinterpret_cast<const float4*>(S.q.lv[cl] + ((size_t)ny * S.q.parent_pitch[cl] + nx) * 4u);
-            const float4 q01 = __ldg(qp), q23 = __ldg(qp + 1);
-            // per-axis child spans
-            const float xlo0 = fminf(a0, am), xhi0 = fmaxf(a0, am), xlo1 = fminf(am, a1), xhi1 = fmaxf(am, a1);
-            const float zlo0 = fminf(b0, bm), zhi0 = fmaxf(b0, bm), zlo1 = fminf(bm, b1), zhi1 = fmaxf(bm, b1);
-            float kt[4];
-            bool ok[4];
-#pragma unroll
-            for (uint32_t c = 0; c < 4u; c++) {
-                const uint32_t cxi = c & 1u, cy = c >> 1;
-                const float c0 = fmaxf(cxi ? xlo1 : xlo0, cy ? zlo1 : zlo0);
-                const float c1 = fminf(cxi ? xhi1 : xhi0, cy ? zhi1 : zhi0);
-                const float ct_lo = fmaxf(c0, t_lo), ct_hi = fminf(c1, t_hi);     // push test (:342-344)
-                const float tl = fmaxf(c0, r.tmin), th = fminf(c1, tcap);        // the child's own pop span (:295-297)
-                const float2 mm = c == 0u ? make_float2(q01.x, q01.y) : c == 1u ? make_float2(q01.z, q01.w)
-                                : c == 2u ? make_float2(q23.x, q23.y) : make_float2(q23.z, q23.w);
-                bool v = (cxi ? has_x1 : true) && (cy ? has_z1 : true) && ct_lo <= ct_hi && tl <= th;
-                v = v && band_ok(tl, th, mm);
-                ok[c] = v;
-                kt[c] = v ? ct_lo : __int_as_float(0x7f800000);   // rejected children sort to the front, never pushed
-            }
-            // order: descending t_enter, ties by original child index (== the stable insertion sort)
-            uint32_t ord[4] = {0u, 1u, 2u, 3u};
-            {
-                float t0 = kt[0], t1 = kt[1], t2 = kt[2], t3 = kt[3];
-                uint32_t i0 = 0u, i1 = 1u, i2 = 2u, i3 = 3u;
-                cmpswap(t0, i0, t1, i1); cmpswap(t2, i2, t3, i3);
-                cmpswap(t0, i0, t2, i2); cmpswap(t1, i1, t3, i3);
-                cmpswap(t1, i1, t2, i2);
-                ord[0] = i0; ord[1] = i1; ord[2] = i2; ord[3] = i3;
-            }
-#pragma unroll
-            for (uint32_t k = 0; k < 4u; k++) {
-                const uint32_t c = ord[k];
-                const bool v = c == 0u ? ok[0] : c == 1u ? ok[1] : c == 2u ? ok[2] : ok[3];
-                if (v) {
-                    const uint32_t id = pack_node(cl, nx * 2u + (c & 1u), ny * 2u + (c >> 1));
-                    st.at(sp) = id;
-                    sp++;
-                }
-            }
-        }
-        if (sp == 0u) break;
-        // ================= phase B: the leaf on top of the stack =================
-        {
-            sp--;
-            nodes++;
-            const uint32_t node = st.at(sp);
-            const uint32_t cz = (node >> 13) & 0x1FFFu, cx = node & 0x1FFFu;
-            const float a0 = ((S.ox + (float)cx * S.sx) - r.o.x) * inv_x;
-            const float a1 = ((S.ox + (float)min(cx + 1u, cell_w) * S.sx) - r.o.x) * inv_x;
-            const float b0 = ((S.oz + (float)cz * S.sz) - r.o.z) * inv_z;
-            const float b1 = ((S.oz + (float)min(cz + 1u, cell_h) * S.sz) - r.o.z) * inv_z;
-            const float t_lo = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), r.tmin);
-            const float t_hi = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(r.tmax, res.t));
-            const float4 h = __ldg(S.cells + (size_t)cz * cell_w + cx);
-            bool live = true;
-            if (!ANY_HIT) {
-                if (sp < stale_sp) {
-                    stale_sp = sp;
-                    live = t_lo <= t_hi;
-                    if (live) {
-                        const float2 mm = make_float2(fminf(fminf(fminf(h.x, h.y), h.z), h.w), fmaxf(fmaxf(fmaxf(h.x, h.y), h.z), h.w));
-                        live = band_ok(t_lo, t_hi, mm);
-                    }
-                }
-            }
-            if (live) {
-                // terrain_leaf_intersect :167-235
-                const float tm = 0.5f * (t_lo + t_hi);
-                float d3[3];
-                const float fcx = (float)cx, fcz = (float)cz;
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    const float t = i == 0 ? t_lo : (i == 1 ? tm : t_hi);
-                    const float px = r.o.x + t * r.d.x, pz = r.o.z + t * r.d.z;
-                    const float u = clampf(fdiv(px - S.ox, S.sx) - fcx, 0.0f, 1.0f);
-                    const float v = clampf(fdiv(pz - S.oz, S.sz) - fcz, 0.0f, 1.0f);
-                    const float hh = mixf(mixf(h.x, h.y, u), mixf(h.z, h.w, u), v);
-                    d3[i] = height(t) - hh;
-                }
-                const float cc = d3[0];
-                const float a = 2.0f * d3[2] + 2.0f * d3[0] - 4.0f * d3[1];
-                const float b = d3[2] - d3[0] - a;
-                float s_hit = 1e30f;
-                if (ANY_HIT && cc <= 0.0f) s_hit = 0.0f;
-                else if (fabsf(a) < 1e-12f) {
-                    if (fabsf(b) > 1e-12f) {
-                        const float s = fdiv(-cc, b);
-                        if (s >= 0.0f && s <= 1.0f) s_hit = s;
-                    }
-                } else {
-                    const float disc = b * b - 4.0f * a * cc;
-                    if (disc >= 0.0f) {
-                        const float sq = fsqrt(disc);
-                        const float q = -0.5f * (b + (b >= 0.0f ? sq : -sq));
-                        float r0 = fdiv(q, a);
-                        float r1 = fabsf(q) < 1e-30f ? 1e30f : fdiv(cc, q);
-                        if (r0 > r1) { const float tmp = r0; r0 = r1; r1 = tmp; }
-                        if (r0 >= 0.0f && r0 <= 1.0f) s_hit = r0;
-                        else if (r1 >= 0.0f && r1 <= 1.0f) s_hit = r1;
-                    }
-                }
-                if (s_hit <= 1.0f) {
-                    const float t = t_lo + s_hit * (t_hi - t_lo);
-                    if (t > r.tmin && t < r.tmax && t < res.t) {
-                        res.hit = true;
-                        res.t = t;
-                        res.cx = cx; res.cz = cz;
-                        if (ANY_HIT) return res;
-                        stale_sp = sp;            // everything still stacked was tested against the old best_t
-                    }
-                }
-            }
+    // integer cell planes of this node and its mid-lines (the children's gx0/gx1, :330-334)
+    const uint32_t cx0 = nx << level, cz0 = ny << level;
+    const uint32_t cx1 = min((nx + 1u) << level, cell_w), cz1 = min((ny + 1u) << level, cell_h);
+    const uint32_t mxu = (2u * nx + 1u) << cl, mzu = (2u * ny + 1u) << cl;
+    const bool has_x1 = mxu < cell_w, has_z1 = mzu < cell_h;       // child column / row 1 exists (:332)
+    const uint32_t cxm = min(mxu, cell_w), czm = min(mzu, cell_h);
+    // children's [min,max]: one 32-byte quad, issued before the arithmetic that hides its latency
+    const float4* qp = reinterpret_cast<const float4*>(S.q.lv[cl] + ((size_t)ny * S.q.parent_pitch[cl] + nx) * 4u);
+    const float4 q01 = __ldg(qp), q23 = __ldg(qp + 1);
+    // ray parameters at the six planes
+    const float a0 = ((S.ox + (float)cx0 * S.sx) - T.o.x) * T.inv_x;
+    const float am = ((S.ox + (float)cxm * S.sx) - T.o.x) * T.inv_x;
+    const float a1 = ((S.ox + (float)cx1 * S.sx) - T.o.x) * T.inv_x;
+    const float b0 = ((S.oz + (float)cz0 * S.sz) - T.o.z) * T.inv_z;
+    const float bm = ((S.oz + (float)czm * S.sz) - T.o.z) * T.inv_z;
+    const float b1 = ((S.oz + (float)cz1 * S.sz) - T.o.z) * T.inv_z;
+    // this node's own clipped span (:288-297); needed to clip the children (:342-343)
+    const float tcap = fminf(T.tmax, T.best_t);
+    const float t_lo = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), T.tmin);
+    const float t_hi = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), tcap);
+    if (!ANY_HIT) {
+        if (T.sp < T.stale_sp) {              // entry predates the last hit: redo the pop tests (:297-304)
+            T.stale_sp = T.sp;
+            if (t_lo > t_hi) return;
+            float2 mm;
+            if (level == S.mip_count - 1u) mm = S.root_mm;
+            else mm = __ldg(S.q.lv[level] + (((size_t)(ny >> 1) * S.q.parent_pitch[level] + (nx >> 1)) * 4u + ((ny & 1u) * 2u + (nx & 1u))));
+            if (!band_ok<CURV>(S, T, t_lo, t_hi, mm)) return;
         }
     }
+    // per-axis child spans
+    const float xlo0 = fminf(a0, am), xhi0 = fmaxf(a0, am), xlo1 = fminf(am, a1), xhi1 = fmaxf(am, a1);
+    const float zlo0 = fminf(b0, bm), zhi0 = fmaxf(b0, bm), zlo1 = fminf(bm, b1), zhi1 = fmaxf(bm, b1);
+    float kt[4];
+    bool ok[4];
+#pragma unroll
+    for (uint32_t c = 0; c < 4u; c++) {
+        const uint32_t cxi = c & 1u, cy = c >> 1;
+        const float c0 = fmaxf(cxi ? xlo1 : xlo0, cy ? zlo1 : zlo0);
+        const float c1 = fminf(cxi ? xhi1 : xhi0, cy ? zhi1 : zhi0);
+        const float ct_lo = fmaxf(c0, t_lo), ct_hi = fminf(c1, t_hi);     // push test (:342-344)
+        const float tl = fmaxf(c0, T.tmin), th = fminf(c1, tcap);         // the child's own pop span (:295-297)
+        const float2 mm = c == 0u ? make_float2(q01.x, q01.y) : c == 1u ? make_float2(q01.z, q01.w)
+                        : c == 2u ? make_float2(q23.x, q23.y) : make_float2(q23.z, q23.w);
+        const bool exists = (cxi ? has_x1 : true) && (cy ? has_z1 : true);
+        const bool band = band_ok<CURV>(S, T, tl, th, mm);                 // evaluated unconditionally: no divergence
+        const bool v = exists & (ct_lo <= ct_hi) & (tl <= th) & band;
+        ok[c] = v;
+        kt[c] = v ? ct_lo : __int_as_float(0x7f800000);   // rejected children sort to the front, never pushed
+    }
+    // order: descending t_enter, ties by original child index (== the stable insertion sort)
+    float t0 = kt[0], t1 = kt[1], t2 = kt[2], t3 = kt[3];
+    uint32_t i0 = 0u, i1 = 1u, i2 = 2u, i3 = 3u;
+    cmpswap(t0, i0, t1, i1); cmpswap(t2, i2, t3, i3);
+    cmpswap(t0, i0, t2, i2); cmpswap(t1, i1, t3, i3);
+    cmpswap(t1, i1, t2, i2);
+    const uint32_t okmask = (ok[0] ? 1u : 0u) | (ok[1] ? 2u : 0u) | (ok[2] ? 4u : 0u) | (ok[3] ? 8u : 0u);
+    const uint32_t base_id = pack_node(cl, nx * 2u, ny * 2u);
+    const uint32_t ord[4] = {i0, i1, i2, i3};
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; k++) {
+        const uint32_t c = ord[k];
+        if ((okmask >> c) & 1u) {
+            st.at(T.sp) = base_id + (c & 1u) + ((c >> 1) << 13);
+            T.sp++;
+        }
+    }
+}
+
+// Pops the leaf on top of the stack and runs the exact ray / bilinear-patch solve (:167-235).
+// Returns true when the ray is finished (any-hit rays stop at their first hit).
+template <bool ANY_HIT, bool CURV>
+__device__ __forceinline__ bool leaf_top(const FastScene& S, TraceState& T, const SmemStack st) {
+    T.sp--;
+    const uint32_t node = st.at(T.sp);
+    const uint32_t cz = (node >> 13) & 0x1FFFu, cx = node & 0x1FFFu;
+    const float4 h = __ldg(S.cells + (size_t)cz * S.cell_w + cx);
+    const float a0 = ((S.ox + (float)cx * S.sx) - T.o.x) * T.inv_x;
+    const float a1 = ((S.ox + (float)min(cx + 1u, S.cell_w) * S.sx) - T.o.x) * T.inv_x;
+    const float b0 = ((S.oz + (float)cz * S.sz) - T.o.z) * T.inv_z;
+    const float b1 = ((S.oz + (float)min(cz + 1u, S.cell_h) * S.sz) - T.o.z) * T.inv_z;
+    const float t_lo = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), T.tmin);
+    const float t_hi = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(T.tmax, T.best_t));
+    if (!ANY_HIT) {
+        if (T.sp < T.stale_sp) {
+            T.stale_sp = T.sp;
+            if (t_lo > t_hi) return false;
+            const float2 mm = make_float2(fminf(fminf(fminf(h.x, h.y), h.z), h.w), fmaxf(fmaxf(fmaxf(h.x, h.y), h.z), h.w));
+            if (!band_ok<CURV>(S, T, t_lo, t_hi, mm)) return false;
+        }
+    }
+    const float tm = 0.5f * (t_lo + t_hi);
+    float d3[3];
+    const float fcx = (float)cx, fcz = (float)cz;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float t = i == 0 ? t_lo : (i == 1 ? tm : t_hi);
+        const float px = T.o.x + t * T.d.x, pz = T.o.z + t * T.d.z;
+        const float u = clampf(fdiv(px - S.ox, S.sx) - fcx, 0.0f, 1.0f);
+        const float v = clampf(fdiv(pz - S.oz, S.sz) - fcz, 0.0f, 1.0f);
+        const float hh = mixf(mixf(h.x, h.y, u), mixf(h.z, h.w, u), v);
+        d3[i] = ray_height<CURV>(S, T, t) - hh;
+    }
+    const float cc = d3[0];
+    const float a = 2.0f * d3[2] + 2.0f * d3[0] - 4.0f * d3[1];
+    const float b = d3[2] - d3[0] - a;
+    float s_hit = 1e30f;
+    if (ANY_HIT && cc <= 0.0f) s_hit = 0.0f;
+    else if (fabsf(a) < 1e-12f) {
+        if (fabsf(b) > 1e-12f) {
+            const float s = fdiv(-cc, b);
+            if (s >= 0.0f && s <= 1.0f) s_hit = s;
+        }
+    } else {
+        const float disc = b * b - 4.0f * a * cc;
+        if (disc >= 0.0f) {
+            const float sq = fsqrt(disc);
+            const float q = -0.5f * (b + (b >= 0.0f ? sq : -sq));
+            float r0 = fdiv(q, a);
+            float r1 = fabsf(q) < 1e-30f ? 1e30f : fdiv(cc, q);
+            if (r0 > r1) { const float tmp = r0; r0 = r1; r1 = tmp; }
+            if (r0 >= 0.0f && r0 <= 1.0f) s_hit = r0;
+            else if (r1 >= 0.0f && r1 <= 1.0f) s_hit = r1;
+        }
+    }
+    if (s_hit <= 1.0f) {
+        const float t = t_lo + s_hit * (t_hi - t_lo);
+        if (t > T.tmin && t < T.tmax && t < T.best_t) {
+            T.hit = true;
+            T.best_t = t;
+            T.best_cx = cx; T.best_cz = cz;
+            if (ANY_HIT) return true;
+            T.stale_sp = T.sp;            // everything still stacked was tested against the old best_t
+        }
+    }
+    return false;
+}
+
+// Whole-ray traversal (while-while): a warp keeps expanding internal nodes until every lane holds a
+// leaf on top of its stack or is finished, then those lanes run the patch solve together.
+template <bool ANY_HIT, bool CURV>
+__device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, const SmemStack st, uint32_t& nodes) {
+    TraceState T;
+    trace_begin<CURV>(S, r, T, st);
+    while (T.sp != 0u) {
+        while (T.sp != 0u && !top_is_leaf(T, st)) { expand_top<ANY_HIT, CURV>(S, T, st); nodes++; }
+        if (T.sp == 0u) break;
+        nodes++;
+        if (leaf_top<ANY_HIT, CURV>(S, T, st)) break;
+    }
+    FastHit res;
+    res.hit = T.hit; res.t = T.best_t; res.cx = T.best_cx; res.cz = T.best_cz;
     return res;
 }
 
