@@ -212,16 +212,17 @@ constexpr uint32_t kRecHit = 1u, kRecSun = 2u, kRecSunReuseDir = 4u;
 // intersect_hybrid (hybrid_traversal.wgsl:175-201) on the production traversal.
 struct PrimaryHit { bool hit; uint32_t hit_type; float t; v3 point, normal; };
 
-__device__ __forceinline__ PrimaryHit primary_hit(const FrameParams& P, const Ray& ray, const SmemStack st, uint32_t& nodes) {
+// Warp-cooperative: call from converged code; `valid` = this lane has a ray.
+__device__ __forceinline__ PrimaryHit primary_hit(const FrameParams& P, const Ray& ray, bool valid, const SmemStack st, uint32_t& nodes) {
     PrimaryHit ph;
     ph.hit = false; ph.hit_type = 0u; ph.t = ray.tmax; ph.point = V3(0, 0, 0); ph.normal = V3(0, 0, 0);
     Ray tr = ray;
-    if (P.scene.traversal_mode == 0u) {
+    if (valid && P.scene.traversal_mode == 0u) {
         const Hit mh = intersect_mesh(P.scene, ray);
         if (mh.hit && mh.t < ph.t) { ph.hit = true; ph.hit_type = 0u; ph.t = mh.t; ph.point = mh.point; ph.normal = mh.normal; }
         tr.tmax = ph.t;
     }
-    const FastHit fh = trace_fast<false, false>(P.fast, tr, st, nodes);
+    const FastHit fh = trace_fast<false, false>(P.fast, tr, valid, st, nodes);
     if (fh.hit && fh.t < ph.t) {
         ph.hit = true; ph.hit_type = 3u; ph.t = fh.t;
         finish_hit(P.fast, tr, fh, ph.point, ph.normal);
@@ -247,18 +248,22 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ Fr
     const uint32_t spp = max(P.spp, 1u), s = P.sample_index;
     const bool multi = spp > 1u;
 
+    const SceneParams& S = P.scene;
+    const v3 light_color = ld3(P.light_color);
+    const v3 wi = normalize3(ld3(P.light_dir));
+    Resv prev_r, cand;
+    uint32_t rng = 0u;
+    bool prev_valid = false;
+    v3 sun_dir = wi;
+    float reuse_w = 1.0f;
+    Ray ray;
+    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.tmin = 1e-3f; ray.tmax = 1e30f;
+    prev_r.w_sum = 0.0f; prev_r.weight = 0.0f; prev_r.target_pdf = 0.0f; prev_r.m = 0u; prev_r.type1 = false;
+    cand = prev_r;
     if (active) {
-        const SceneParams& S = P.scene;
-        const v3 light_color = ld3(P.light_color);
-        const v3 wi = normalize3(ld3(P.light_dir));
 
         // ---- merged reservoir from last frame's reuse chain + M-clamp (:452-465) ----
-        Resv prev_r;
-        uint32_t rng;
-        Resv cand;
-        cand.w_sum = 0.0f; cand.weight = 0.0f; cand.target_pdf = 0.0f; cand.m = 0u; cand.type1 = false;
         if (s == 0u) {
-            prev_r.w_sum = 0.0f; prev_r.weight = 0.0f; prev_r.target_pdf = 0.0f; prev_r.m = 0u; prev_r.type1 = false;
             const bool facing = (P.pixflags[pix] & 1u) != 0u;
             if (P.frame_index > 0u) prev_r = spatial_reuse(P, P.resv_in, gx, gy, facing, P.frame_index - 1u);
             if (prev_r.m > 512u) {
@@ -278,18 +283,20 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ Fr
             cand.target_pdf = a.w;
             prev_r = unpack_resv(P.sstate[3 * (size_t)pix + 1]);
         }
-        const bool prev_valid = P.frame_index > 0u && prev_r.m > 0u && prev_r.weight > 0.0f &&
+        prev_valid = P.frame_index > 0u && prev_r.m > 0u && prev_r.weight > 0.0f &&
                                 prev_r.target_pdf > 0.0f && prev_r.type1;
         // every populated sample stores direction == wi; the shader re-normalises it (:520)
-        const v3 sun_dir = prev_valid ? normalize3(wi) : wi;
-        const float reuse_w = prev_valid ? clampf(prev_r.weight, 0.0f, 4.0f) : 1.0f;
+        sun_dir = prev_valid ? normalize3(wi) : wi;
+        reuse_w = prev_valid ? clampf(prev_r.weight, 0.0f, 4.0f) : 1.0f;
 
         // ---- primary ray (:476-491) ----
         const float jx = tent_offset(xorshift32(rng)) * 0.5f;
         const float jy = tent_offset(xorshift32(rng)) * 0.5f;
-        const Ray ray = camera_ray(P, gx, gy, jx, jy);
+        ray = camera_ray(P, gx, gy, jx, jy);
         n_primary++;
-        const PrimaryHit hit = primary_hit(P, ray, st, n_nodes);
+    }
+    const PrimaryHit hit = primary_hit(P, ray, active, st, n_nodes);   // warp-cooperative
+    if (active) {
         float4* rec = P.rec + 4 * (size_t)pix;
         if (!hit.hit) {
             const v3 sky = env_radiance(S, ray.d);
@@ -433,18 +440,24 @@ __global__ void __launch_bounds__(kTraceCtaThreads) k_trace(const __grid_constan
             if (exhausted) break;
             continue;
         }
-        // ---- traverse until enough lanes have gone idle ----
+        // ---- traverse until enough lanes have gone idle (bounded while-while, see trace_fast) ----
         while (true) {
-            while (busy && T.sp != 0u && !top_is_leaf(T, st)) { expand_top<true, CURV>(F, T, st); n_nodes++; }
-            if (busy) {
-                bool done = false, hit = false;
-                if (T.sp == 0u) done = true;
-                else {
+            while (true) {
+                const bool can_expand = busy && !top_is_leaf(T, st);
+                if (can_expand) {
+                    expand_top<true, CURV>(F, T, st);
                     n_nodes++;
-                    hit = leaf_top<true, CURV>(F, T, st);
-                    done = hit || T.sp == 0u;
+                    if (T.sp == 0u) { occl[pix] = mesh_occl ? 1u : 0u; busy = false; }
                 }
-                if (done) { occl[pix] = (hit || mesh_occl) ? 1u : 0u; busy = false; }
+                const bool expandable = busy && !top_is_leaf(T, st);
+                const uint32_t m_exp = __ballot_sync(0xFFFFFFFFu, expandable);
+                const uint32_t m_leaf = __ballot_sync(0xFFFFFFFFu, busy && !expandable);
+                if (m_exp == 0u || __popc(m_leaf) >= kLeafBatch) break;
+            }
+            if (busy && top_is_leaf(T, st)) {
+                n_nodes++;
+                const bool hit = leaf_top<true, CURV>(F, T, st);
+                if (hit || T.sp == 0u) { occl[pix] = (hit || mesh_occl) ? 1u : 0u; busy = false; }
             }
             const uint32_t live = __ballot_sync(0xFFFFFFFFu, busy);
             if (live == 0u) break;
@@ -521,11 +534,14 @@ __global__ void __launch_bounds__(kThreads) k_gbuffer(const __grid_constant__ Fr
     st.base = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
     st.stride = kThreads;
     uint32_t gx, gy;
-    if (!owned_pixel(P, gx, gy)) return;
-    const uint32_t pix = gy * P.W + gx;
+    const bool active = owned_pixel(P, gx, gy);
+    const uint32_t pix = active ? gy * P.W + gx : 0u;
     uint32_t nodes = 0;
-    const Ray ray = camera_ray(P, gx, gy, 0.0f, 0.0f);
-    const PrimaryHit hit = primary_hit(P, ray, st, nodes);
+    Ray ray;
+    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.tmin = 1e-3f; ray.tmax = 1e30f;
+    if (active) ray = camera_ray(P, gx, gy, 0.0f, 0.0f);
+    const PrimaryHit hit = primary_hit(P, ray, active, st, nodes);   // warp-cooperative
+    if (!active) return;
     // ReSTIR G-buffer record: hit -> (normal, 1); miss -> (0,0,1,1)  (:635-643)
     const v3 nr = hit.hit ? hit.normal : V3(0.0f, 0.0f, 1.0f);
     const v3 N = normalize3(nr);
@@ -710,10 +726,13 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_rays(SceneParams S, Fas
                                                               float* __restrict__ normal, unsigned long long* __restrict__ nodes_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 a = rays[2 * i], b = rays[2 * i + 1];
+    const bool valid = i < n;
     Ray r;
-    r.o = V3(a.x, a.y, a.z); r.tmin = a.w; r.d = V3(b.x, b.y, b.z); r.tmax = b.w;
+    r.o = V3(0, 0, 0); r.tmin = 0.0f; r.d = V3(0, 0, 1); r.tmax = 0.0f;
+    if (valid) {
+        const float4 a = rays[2 * i], b = rays[2 * i + 1];
+        r.o = V3(a.x, a.y, a.z); r.tmin = a.w; r.d = V3(b.x, b.y, b.z); r.tmax = b.w;
+    }
     uint32_t nodes = 0;
     const bool curv = apply_curv && S.curvature_enabled;
     bool h_hit;
@@ -724,8 +743,8 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_rays(SceneParams S, Fas
         st.base = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
         st.stride = kTraceThreads;
         FastHit fh;
-        if (any_hit) fh = curv ? trace_fast<true, true>(F, r, st, nodes) : trace_fast<true, false>(F, r, st, nodes);
-        else fh = trace_fast<false, false>(F, r, st, nodes);
+        if (any_hit) fh = curv ? trace_fast<true, true>(F, r, valid, st, nodes) : trace_fast<true, false>(F, r, valid, st, nodes);
+        else fh = trace_fast<false, false>(F, r, valid, st, nodes);
         h_hit = fh.hit; h_t = fh.t;
         if (fh.hit) { v3 p; finish_hit(F, r, fh, p, h_n); }
     } else {
@@ -734,6 +753,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace_rays(SceneParams S, Fas
         else h = curv ? terrain_trace<false, true>(S, r, nodes) : terrain_trace<false, false>(S, r, nodes);
         h_hit = h.hit != 0u; h_t = h.t; h_n = h.normal;
     }
+    if (!valid) return;
     hit[i] = h_hit ? 1 : 0;
     t[i] = h_t;
     if (normal) { normal[3 * i] = h_n.x; normal[3 * i + 1] = h_n.y; normal[3 * i + 2] = h_n.z; }

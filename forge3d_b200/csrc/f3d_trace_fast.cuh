@@ -111,6 +111,7 @@ __device__ __forceinline__ void trace_begin(const FastScene& S, const Ray& r, Tr
     if (tl <= th && band_ok<CURV>(S, T, tl, th, S.root_mm)) { st.at(0) = pack_node(level, 0u, 0u); T.sp = 1u; }
 }
 
+// Precondition: T.sp > 0.
 __device__ __forceinline__ bool top_is_leaf(const TraceState& T, const SmemStack st) {
     return (st.at(T.sp - 1u) >> 26) == 0u;
 }
@@ -271,17 +272,36 @@ __device__ __forceinline__ bool leaf_top(const FastScene& S, TraceState& T, cons
     return false;
 }
 
-// Whole-ray traversal (while-while): a warp keeps expanding internal nodes until every lane holds a
-// leaf on top of its stack or is finished, then those lanes run the patch solve together.
+// Whole-ray traversal, warp-cooperative: must be called by all 32 lanes of a converged warp
+// (`valid` = this lane really has a ray).  Scheduling is a bounded while-while: lanes keep expanding
+// internal nodes until at least kLeafBatch lanes of the warp hold a leaf on top of their stacks (or
+// nobody can expand any more); then those lanes run the patch solve together.  A lane's own sequence
+// of expansions and leaf tests is unchanged by the scheduling, so results do not depend on it.
+constexpr int kLeafBatch = 8;
+
 template <bool ANY_HIT, bool CURV>
-__device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, const SmemStack st, uint32_t& nodes) {
+__device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, bool valid, const SmemStack st, uint32_t& nodes) {
     TraceState T;
-    trace_begin<CURV>(S, r, T, st);
-    while (T.sp != 0u) {
-        while (T.sp != 0u && !top_is_leaf(T, st)) { expand_top<ANY_HIT, CURV>(S, T, st); nodes++; }
-        if (T.sp == 0u) break;
-        nodes++;
-        if (leaf_top<ANY_HIT, CURV>(S, T, st)) break;
+    T.sp = 0u; T.hit = false; T.best_t = r.tmax; T.best_cx = 0u; T.best_cz = 0u;
+    if (valid) trace_begin<CURV>(S, r, T, st);
+    bool busy = T.sp != 0u;
+    while (__ballot_sync(0xFFFFFFFFu, busy) != 0u) {
+        while (true) {
+            const bool can_expand = busy && !top_is_leaf(T, st);
+            if (can_expand) {
+                expand_top<ANY_HIT, CURV>(S, T, st);
+                nodes++;
+                if (T.sp == 0u) busy = false;
+            }
+            const bool expandable = busy && !top_is_leaf(T, st);
+            const uint32_t m_exp = __ballot_sync(0xFFFFFFFFu, expandable);
+            const uint32_t m_leaf = __ballot_sync(0xFFFFFFFFu, busy && !expandable);
+            if (m_exp == 0u || __popc(m_leaf) >= kLeafBatch) break;
+        }
+        if (busy && top_is_leaf(T, st)) {
+            nodes++;
+            if (leaf_top<ANY_HIT, CURV>(S, T, st) || T.sp == 0u) busy = false;
+        }
     }
     FastHit res;
     res.hit = T.hit; res.t = T.best_t; res.cx = T.best_cx; res.cz = T.best_cz;
