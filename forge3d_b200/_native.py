@@ -8,12 +8,14 @@ device is visible, calls raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libforge3d_b200.so"
+# F3D_B200_LIB: developer override used only for tuning experiments (alternative builds of the same sources)
+LIB_PATH = Path(os.environ["F3D_B200_LIB"]) if os.environ.get("F3D_B200_LIB") else _PKG / "libforge3d_b200.so"
 
 EARTH_MODELS = {"flat": 0, "sphere": 1, "ellipsoid": 2, "wgs84": 2}
 REFRACTION_MODELS = {"none": 0, "bennett": 1, "saemundsson": 2, "effective_radius": 3}

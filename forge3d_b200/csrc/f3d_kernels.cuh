@@ -374,11 +374,17 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ Fr
 // Each lane owns one ray at a time; when fewer than kRefillBelow lanes of a warp still traverse,
 // the idle lanes pull fresh rays (one atomic per warp).
 // ---------------------------------------------------------------------------------------------
+#ifndef F3D_REFILL_BELOW
+#define F3D_REFILL_BELOW 24
+#endif
+#ifndef F3D_TRACE_MIN_CTAS
+#define F3D_TRACE_MIN_CTAS 1
+#endif
 constexpr int kTraceCtaThreads = 256;
-constexpr int kRefillBelow = 24;
+constexpr int kRefillBelow = F3D_REFILL_BELOW;
 
 template <bool IS_SUN, bool CURV>
-__global__ void __launch_bounds__(kTraceCtaThreads) k_trace(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     SmemStack st;

@@ -277,7 +277,10 @@ __device__ __forceinline__ bool leaf_top(const FastScene& S, TraceState& T, cons
 // internal nodes until at least kLeafBatch lanes of the warp hold a leaf on top of their stacks (or
 // nobody can expand any more); then those lanes run the patch solve together.  A lane's own sequence
 // of expansions and leaf tests is unchanged by the scheduling, so results do not depend on it.
-constexpr int kLeafBatch = 8;
+#ifndef F3D_LEAF_BATCH
+#define F3D_LEAF_BATCH 4
+#endif
+constexpr int kLeafBatch = F3D_LEAF_BATCH;
 
 template <bool ANY_HIT, bool CURV>
 __device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, bool valid, const SmemStack st, uint32_t& nodes) {

@@ -1,0 +1,75 @@
+"""Multi-GPU image partition on real devices (NCCL): a render dealt to 2 ranks in interleaved row blocks,
+with halo rows pushed over NVLink peer memory inside k_primary, must be BIT-IDENTICAL to the
+single-GPU render (SURVEY section 8e "exact mode").  Skipped when fewer than 2 GPUs are visible."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import _helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, frames, width, height, block_rows, q):
+    import torch
+    import torch.distributed as dist
+
+    from forge3d_b200.distributed import PartitionedRender
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        dem = H.golden_dem()
+        kw = {**H.scene_kwargs(dem), "max_frames": frames, "min_frames": frames, "variance_threshold": 1e30}
+        pr = PartitionedRender(dem, width, height, H.CAM, block_rows=block_rows, **kw)
+        pr.render_frames(frames)
+        var, bad = pr.variance()
+        out = pr.resolve(aovs=True)
+        pr.close()
+        if rank == 0:
+            q.put({"rgba": out["rgba"], "depth": out["depth"], "normal": out["normal"], "albedo": out["albedo"],
+                   "variance": var, "bad": bad})
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("width,height,block_rows,frames", [(96, 80, 16, 40), (64, 50, 32, 6)])
+def test_two_gpu_partition_is_bit_identical(width, height, block_rows, frames):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from forge3d_b200 import _native
+
+    dem = H.golden_dem()
+    kw = {**H.scene_kwargs(dem), "max_frames": frames, "min_frames": frames, "variance_threshold": 1e30}
+    ref = _native.hybrid_render_terrain_reference(dem, width, height, H.CAM, **kw)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, frames, width, height, block_rows, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.array_equal(got["rgba"], ref["rgba"])
+    assert np.array_equal(got["depth"].view(np.uint32), ref["depth"].view(np.uint32))
+    assert np.array_equal(got["normal"], ref["normal"]) and np.array_equal(got["albedo"], ref["albedo"])
+    assert np.float32(got["variance"]) == np.float32(ref["variance"]) and not got["bad"]
