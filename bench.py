@@ -73,7 +73,7 @@ class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.stamps = index, [], None, []
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -81,7 +81,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -89,15 +89,18 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+            self.stamps.append(time.time())
 
-    def stop(self):
+    def stop(self, t_begin=0.0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_end = time.time()
+        time.sleep(0.06)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for r, ts in zip(self.rows, self.stamps) if t_begin - 0.02 <= ts <= t_end + 0.05] or self.rows[-3:]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -168,6 +171,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("F3D_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
 
@@ -199,13 +203,15 @@ def main():
 
     # ---------------- resident-scene timing (value) ----------------
     pr = PartitionedRender(dem, W, Hh, cam, **kw, **fixed)
-    pr.render_frames(Wm)
-    torch.cuda.synchronize()
-    s0 = pr.session.stats()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)            # nvidia-smi start-up; samples before the timed region are dropped below
+    pr.render_frames(Wm)
+    torch.cuda.synchronize()
+    s0 = pr.session.stats()
     barrier()
+    t_region0 = time.time()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -213,7 +219,7 @@ def main():
     ev1.record()
     torch.cuda.synchronize()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0) if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
     all_reduce(ms, dist.ReduceOp.MAX)
     s1 = pr.session.stats()
@@ -243,6 +249,7 @@ def main():
             d2h = out["rgba"].nbytes + out["albedo"].nbytes + out["normal"].nbytes + out["depth"].nbytes
             e2e = {"value": r / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": dem_host.nbytes / K,
                    "d2h_bytes_per_step": d2h / K, "call_ms": dt * 1e3, "frames": K,
+                   "setup_ms": out["setup_ms"], "frames_ms": out["frames_ms"], "readback_ms": out["readback_ms"],
                    "note": "one hybrid_render_terrain_reference call = K steps; bytes are per call / K"}
         else:
             # partitioned call: per-rank DEM upload + pyramid build + K frames + resolve + NCCL gather + D2H
@@ -276,7 +283,7 @@ def main():
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
             try:
-                traffic = json.loads(tp.read_text()).get("k_frame_dram_bytes_per_launch")
+                traffic = json.loads(tp.read_text()).get("frame_dram_bytes")
             except Exception:
                 traffic = None
         line = {
@@ -285,15 +292,16 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"rainier-shaped {DEM_N}x{DEM_N} DEM (SURVEY 8d C2), {W}x{Hh}, spp=1 per frame, "
                                    f"{K} frames timed (256 = the 256-spp snapshot)",
-                       "step": "one accumulation frame (one fused k_frame launch over the image)",
+                       "step": "one accumulation frame = k_primary + k_trace<sun> + k_trace<ibl> + k_accum over the image",
                        "l2": "per-frame working set (state 118 MB + DEM cells/pyramid 108 MB) exceeds the 126 MB L2; no flush",
                        "partition": f"interleaved 32-row blocks over {world} GPU(s)", "ms_per_frame": ms_per_step,
                        "rays_per_frame": total_rays / K, "f_shadow": n_shadow / max(n_primary, 1),
                        "f_ibl": n_ibl / max(n_primary, 1), "nodes_per_ray": n_nodes / max(total_rays, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_frame,
-                         "bytes_per_ray": b_frame / (total_rays / K), "kernel": "k_frame"},
-            "clocks": clocks, "gpu_launches": K, "e2e": e2e,
+                         "bytes_per_ray": b_frame / (total_rays / K),
+                         "kernel": "frame = k_primary + k_trace<sun> + k_trace<ibl> + k_accum (dominant: k_trace<sun>)"},
+            "clocks": clocks, "gpu_launches": 4 * K * kw["spp"], "e2e": e2e,
             "image_mean_rgb": float(images["rgba"][..., :3].mean()),
         }
         if not args.no_cpu_baseline and world == 1:
