@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -456,6 +457,9 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, true>, kTraceCtaThreads, s->trace_smem_bytes));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
         s->trace_grid = std::max(per_sm, 1) * std::max(sms, 1);
+        if (getenv("F3D_B200_DEBUG"))
+            fprintf(stderr, "[forge3d_b200] k_trace: %d CTAs/SM x %d SMs, %zu B smem/CTA, stack depth %u\n", per_sm, sms,
+                    s->trace_smem_bytes, P.stack_depth);
     }
     memcpy(S.albedo, d->albedo, sizeof S.albedo);
     S.env_intensity = env_intensity;

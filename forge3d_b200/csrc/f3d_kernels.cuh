@@ -380,7 +380,10 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ Fr
 #ifndef F3D_TRACE_MIN_CTAS
 #define F3D_TRACE_MIN_CTAS 1
 #endif
-constexpr int kTraceCtaThreads = 256;
+#ifndef F3D_TRACE_THREADS
+#define F3D_TRACE_THREADS 128
+#endif
+constexpr int kTraceCtaThreads = F3D_TRACE_THREADS;
 constexpr int kRefillBelow = F3D_REFILL_BELOW;
 
 template <bool IS_SUN, bool CURV>

@@ -60,6 +60,7 @@ struct TraceState {
     float inv_x, inv_z;      // terrain_safe_inv of the direction (:88-91)
     float hd2;               // dot(dir.xz, dir.xz)
     float vertex;            // parameter of the curved ray's lowest point (:120), CURV only
+    float y_vertex;          // terrain_curved_height(ray, vertex, true) (:122), constant per ray
     bool use_vertex;         // CURV && a > 0 (:119)
     float best_t;            // res.t
     uint32_t best_cx, best_cz;
@@ -80,7 +81,7 @@ __device__ __forceinline__ bool band_ok(const FastScene& S, const TraceState& T,
     const float y0 = ray_height<CURV>(S, T, tl), y1 = ray_height<CURV>(S, T, th);
     float lo = fminf(y0, y1);
     if (CURV) {
-        if (T.use_vertex && T.vertex >= tl && T.vertex <= th) lo = fminf(lo, ray_height<true>(S, T, T.vertex));
+        if (T.use_vertex && T.vertex >= tl && T.vertex <= th) lo = fminf(lo, T.y_vertex);
     }
     const float hi = fmaxf(y0, y1);
     return !(lo > mm.y || hi < mm.x);
@@ -93,11 +94,11 @@ __device__ __forceinline__ void trace_begin(const FastScene& S, const Ray& r, Tr
     T.o = r.o; T.d = r.d; T.tmin = r.tmin; T.tmax = r.tmax;
     T.inv_x = safe_inv(r.d.x); T.inv_z = safe_inv(r.d.z);
     T.hd2 = dot2(r.d.x, r.d.z, r.d.x, r.d.z);
-    T.use_vertex = false; T.vertex = 0.0f;
+    T.use_vertex = false; T.vertex = 0.0f; T.y_vertex = 0.0f;
     if (CURV) {
         const float a = T.hd2 * S.inv_two_r_prime;
         T.use_vertex = a > 0.0f;
-        if (T.use_vertex) T.vertex = fdiv(-r.d.y, 2.0f * a);
+        if (T.use_vertex) { T.vertex = fdiv(-r.d.y, 2.0f * a); T.y_vertex = ray_height<true>(S, T, T.vertex); }
     }
     T.best_t = r.tmax; T.best_cx = 0u; T.best_cz = 0u; T.hit = false;
     T.sp = 0u; T.stale_sp = 0u;
