@@ -171,6 +171,79 @@ static int earth_curvature(const f3d_terrain_desc* d, float* inv_two_r_prime, ui
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mesh BVH (replaces the reference's unused upload of accel::build_bvh output, render_terrain.rs:597-632,
+// and makes hybrid_traversal.wgsl:137-172's O(#tris) sweep O(log #tris) with identical hits).
+// Median split on the widest centroid axis, leaves of <= 4 triangles, boxes padded against rounding.
+// ------------------------------------------------------------------------------------------------
+struct MeshBvh {
+    std::vector<float4> nodes;      // 2 per node
+    std::vector<uint32_t> tris;     // triangle ids in leaf order
+};
+
+static void bvh_build_rec(MeshBvh& B, std::vector<uint32_t>& ids, size_t lo, size_t hi, const std::vector<float>& tb /*6 per tri*/,
+                          const std::vector<float>& cen /*3 per tri*/, size_t node) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    float cmn[3] = {INFINITY, INFINITY, INFINITY}, cmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t k = lo; k < hi; k++) {
+        const uint32_t t = ids[k];
+        for (int a = 0; a < 3; a++) {
+            mn[a] = fminf(mn[a], tb[6 * t + a]); mx[a] = fmaxf(mx[a], tb[6 * t + 3 + a]);
+            cmn[a] = fminf(cmn[a], cen[3 * t + a]); cmx[a] = fmaxf(cmx[a], cen[3 * t + a]);
+        }
+    }
+    const size_t count = hi - lo;
+    if (count <= 4) {
+        B.nodes[2 * node] = make_float4(mn[0], mn[1], mn[2], 0.0f);
+        B.nodes[2 * node + 1] = make_float4(mx[0], mx[1], mx[2], 0.0f);
+        const uint32_t first = (uint32_t)B.tris.size(), cnt = (uint32_t)count;
+        for (size_t k = lo; k < hi; k++) B.tris.push_back(ids[k]);
+        memcpy(&B.nodes[2 * node].w, &first, 4);
+        memcpy(&B.nodes[2 * node + 1].w, &cnt, 4);
+        return;
+    }
+    int axis = 0;
+    if (cmx[1] - cmn[1] > cmx[axis] - cmn[axis]) axis = 1;
+    if (cmx[2] - cmn[2] > cmx[axis] - cmn[axis]) axis = 2;
+    const size_t mid = lo + count / 2;
+    std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](uint32_t a, uint32_t b) {
+        const float ca = cen[3 * a + axis], cb = cen[3 * b + axis];
+        return ca < cb || (ca == cb && a < b);
+    });
+    const uint32_t left = (uint32_t)(B.nodes.size() / 2), zero = 0u;
+    B.nodes.resize(B.nodes.size() + 4);
+    B.nodes[2 * node] = make_float4(mn[0], mn[1], mn[2], 0.0f);
+    B.nodes[2 * node + 1] = make_float4(mx[0], mx[1], mx[2], 0.0f);
+    memcpy(&B.nodes[2 * node].w, &left, 4);
+    memcpy(&B.nodes[2 * node + 1].w, &zero, 4);
+    bvh_build_rec(B, ids, lo, mid, tb, cen, left);
+    bvh_build_rec(B, ids, mid, hi, tb, cen, left + 1);
+}
+
+static void build_mesh_bvh(const float* xyz, const uint32_t* idx, uint32_t ntris, MeshBvh* B) {
+    std::vector<float> tb((size_t)ntris * 6), cen((size_t)ntris * 3);
+    std::vector<uint32_t> ids(ntris);
+    for (uint32_t t = 0; t < ntris; t++) {
+        ids[t] = t;
+        float ext = 0.0f, scale = 0.0f;
+        for (int a = 0; a < 3; a++) {
+            const float p0 = xyz[3 * (size_t)idx[3 * t] + a], p1 = xyz[3 * (size_t)idx[3 * t + 1] + a], p2 = xyz[3 * (size_t)idx[3 * t + 2] + a];
+            const float lo = fminf(p0, fminf(p1, p2)), hi = fmaxf(p0, fmaxf(p1, p2));
+            tb[6 * t + a] = lo; tb[6 * t + 3 + a] = hi;
+            cen[3 * t + a] = 0.5f * (lo + hi);
+            ext = fmaxf(ext, hi - lo);
+            scale = fmaxf(scale, fmaxf(fabsf(lo), fabsf(hi)));
+        }
+        // pad: Moeller-Trumbore's rounding error is ~1e-6 of the triangle's size / coordinates; 1e-3 is ample
+        const float pad = 1e-3f * ext + 1e-5f * scale + 1e-6f;
+        for (int a = 0; a < 3; a++) { tb[6 * t + a] -= pad; tb[6 * t + 3 + a] += pad; }
+    }
+    B->nodes.assign(2, make_float4(0, 0, 0, 0));
+    B->tris.clear();
+    B->tris.reserve(ntris);
+    bvh_build_rec(*B, ids, 0, ntris, tb, cen, 0);
+}
+
 static uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
 // ------------------------------------------------------------------------------------------------
@@ -311,6 +384,8 @@ struct f3d_session {
     float4* d_env = nullptr;
     float4* d_mesh_v = nullptr;
     uint32_t* d_mesh_i = nullptr;
+    float4* d_bvh_nodes = nullptr;
+    uint32_t* d_bvh_tris = nullptr;
     float4* d_accum = nullptr;
     float2* d_welford = nullptr;
     float4* d_resv[2] = {nullptr, nullptr};
@@ -350,7 +425,7 @@ static void session_free(f3d_session* s) {
     for (int i = 0; i < s->n_peer_ptrs; i++)
         if (s->peer_ptrs[i]) cudaIpcCloseMemHandle(s->peer_ptrs[i]);
     s->terrain.release();
-    cudaFree(s->d_env); cudaFree(s->d_mesh_v); cudaFree(s->d_mesh_i);
+    cudaFree(s->d_env); cudaFree(s->d_mesh_v); cudaFree(s->d_mesh_i); cudaFree(s->d_bvh_nodes); cudaFree(s->d_bvh_tris);
     cudaFree(s->d_accum); cudaFree(s->d_welford); cudaFree(s->d_resv[0]); cudaFree(s->d_resv[1]);
     cudaFree(s->d_pixflags); cudaFree(s->d_aov_normal); cudaFree(s->d_aov_depth); cudaFree(s->d_counters);
     cudaFree(s->d_gate);
@@ -491,6 +566,16 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         S.mesh_v = s->d_mesh_v; S.mesh_i = s->d_mesh_i;
         S.mesh_index_count = d->mesh_ntris * 3u; S.mesh_nverts = d->mesh_nverts;
+        if (d->mesh_ntris > 8u && !getenv("F3D_B200_NO_MESH_BVH")) {
+            MeshBvh bvh;
+            build_mesh_bvh(d->mesh_xyz, d->mesh_idx, d->mesh_ntris, &bvh);
+            if ((rc = dmalloc(s, &s->d_bvh_nodes, bvh.nodes.size(), false))) return rc;
+            if ((rc = dmalloc(s, &s->d_bvh_tris, bvh.tris.size(), false))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(s->d_bvh_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(cudaMemcpyAsync(s->d_bvh_tris, bvh.tris.data(), bvh.tris.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            S.bvh_nodes = s->d_bvh_nodes; S.bvh_tris = s->d_bvh_tris;
+        }
         S.traversal_mode = 0u;                                   // TraversalMode::Hybrid, render_terrain.rs:681-685
     }
 

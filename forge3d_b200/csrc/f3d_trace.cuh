@@ -36,6 +36,9 @@ struct SceneParams {
     const float4* mesh_v;
     const uint32_t* mesh_i;
     uint32_t mesh_index_count, mesh_nverts;
+    // mesh BVH (csrc/f3d_backend.cu::build_mesh_bvh); NULL = index-order sweep
+    const float4* bvh_nodes;         // 2 x float4 per node: (bmin, left|first) (bmax, count)
+    const uint32_t* bvh_tris;        // triangle ids referenced by the leaves
     uint32_t traversal_mode;         // 0 hybrid, 3 terrain only
 };
 
@@ -260,7 +263,29 @@ __device__ __forceinline__ bool ray_triangle(const Ray& r, v3 v0, v3 v1, v3 v2, 
     return false;
 }
 
-// intersect_mesh (index-order sweep, strict '<' keeps the earliest triangle on ties), :137-172
+// One triangle of the mesh against the ray; keeps the lexicographically smallest (t, triangle index),
+// which is exactly what the reference's index-order sweep with a strict '<' produces (:150-169).
+__device__ __forceinline__ void mesh_test_triangle(const SceneParams& S, const Ray& r, uint32_t tri_id, Hit& res, uint32_t& best_id) {
+    const uint32_t tri = tri_id * 3u;
+    const uint32_t i0 = __ldg(S.mesh_i + tri), i1 = __ldg(S.mesh_i + tri + 1), i2 = __ldg(S.mesh_i + tri + 2);
+    if (i0 >= S.mesh_nverts || i1 >= S.mesh_nverts || i2 >= S.mesh_nverts) return;
+    const float4 a = __ldg(S.mesh_v + i0), b = __ldg(S.mesh_v + i1), c = __ldg(S.mesh_v + i2);
+    float t;
+    v3 n;
+    if (ray_triangle(r, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), t, n) &&
+        (t < res.t || (t == res.t && res.hit && tri_id < best_id))) {
+        res.hit = 1u;
+        res.t = t;
+        res.point = r.o + r.d * t;
+        res.normal = n;
+        best_id = tri_id;
+    }
+}
+
+// intersect_mesh, hybrid_traversal.wgsl:137-172.  The reference sweeps every triangle in index order
+// (its uploaded BVH is never traversed); here a BVH prunes the sweep.  Each candidate triangle runs the
+// identical Moeller-Trumbore test against the same ray, boxes are padded so that rounding can never cull
+// the winning triangle, and ties resolve to the lowest triangle index, so the closest hit is identical.
 __device__ __noinline__ Hit intersect_mesh(const SceneParams& S, const Ray& r) {
     Hit res;
     res.hit = 0u;
@@ -270,17 +295,30 @@ __device__ __noinline__ Hit intersect_mesh(const SceneParams& S, const Ray& r) {
     res.normal = V3(0, 0, 0);
     const uint32_t ic = S.mesh_index_count;
     if (ic < 3u) return res;
-    for (uint32_t tri = 0; tri + 2u < ic; tri += 3u) {
-        const uint32_t i0 = __ldg(S.mesh_i + tri), i1 = __ldg(S.mesh_i + tri + 1), i2 = __ldg(S.mesh_i + tri + 2);
-        if (i0 >= S.mesh_nverts || i1 >= S.mesh_nverts || i2 >= S.mesh_nverts) continue;
-        const float4 a = __ldg(S.mesh_v + i0), b = __ldg(S.mesh_v + i1), c = __ldg(S.mesh_v + i2);
-        float t;
-        v3 n;
-        if (ray_triangle(r, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), t, n) && t < res.t) {
-            res.hit = 1u;
-            res.t = t;
-            res.point = r.o + r.d * t;
-            res.normal = n;
+    uint32_t best_id = 0xFFFFFFFFu;
+    if (S.bvh_nodes == nullptr) {
+        for (uint32_t tri = 0; tri + 2u < ic; tri += 3u) mesh_test_triangle(S, r, tri / 3u, res, best_id);
+        return res;
+    }
+    const float ix = frcp(r.d.x), iy = frcp(r.d.y), iz = frcp(r.d.z);   // +-inf for axis-parallel rays: handled by fmin/fmax
+    uint32_t stack[48];
+    uint32_t sp = 0;
+    stack[sp++] = 0u;
+    while (sp) {
+        const uint32_t ni = stack[--sp];
+        const float4 n0 = __ldg(S.bvh_nodes + 2 * (size_t)ni), n1 = __ldg(S.bvh_nodes + 2 * (size_t)ni + 1);
+        const float tx0 = (n0.x - r.o.x) * ix, tx1 = (n1.x - r.o.x) * ix;
+        const float ty0 = (n0.y - r.o.y) * iy, ty1 = (n1.y - r.o.y) * iy;
+        const float tz0 = (n0.z - r.o.z) * iz, tz1 = (n1.z - r.o.z) * iz;
+        const float tnear = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), r.tmin));
+        const float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), res.t));
+        if (!(tnear <= tfar)) continue;
+        const uint32_t first = __float_as_uint(n0.w), count = __float_as_uint(n1.w);
+        if (count) {
+            for (uint32_t k = 0; k < count; k++) mesh_test_triangle(S, r, __ldg(S.bvh_tris + first + k), res, best_id);
+        } else if (sp + 2u <= 48u) {
+            stack[sp++] = first;
+            stack[sp++] = first + 1u;
         }
     }
     return res;

@@ -143,6 +143,27 @@ def test_render_bit_exact_mesh_and_env():
     _assert_same_render(got, ref, "mesh + env map")
 
 
+def test_mesh_bvh_matches_index_order_sweep(monkeypatch):
+    # 1500 random triangles (plus exact duplicates to force closest-hit ties) hovering over the DEM: the
+    # GPU walks a BVH, the oracle sweeps every triangle in index order like hybrid_traversal.wgsl:137-172.
+    dem = H.golden_dem()
+    rng = np.random.default_rng(21)
+    ntri = 1500
+    centers = np.stack([rng.uniform(-45, 45, ntri), rng.uniform(12, 45, ntri), rng.uniform(-45, 45, ntri)], 1)
+    verts = (centers[:, None, :] + rng.normal(0, 2.5, (ntri, 3, 3))).reshape(-1, 3).astype(np.float32)
+    idx = np.arange(ntri * 3, dtype=np.uint32).reshape(ntri, 3)
+    idx = np.concatenate([idx, idx[100:140]])            # duplicated triangles: ties must pick the lower index
+    kw = {**H.scene_kwargs(dem), "max_frames": 4, "min_frames": 4, "variance_threshold": 1e30}
+    got, ref = _both(dem, 128, 96, H.CAM, **kw, mesh_vertices=verts, mesh_indices=idx)
+    _assert_same_render(got, ref, "mesh bvh vs sweep")
+    mesh_px = np.isfinite(got["depth"]) & (got["albedo"][..., 2] > 0.75)
+    assert mesh_px.mean() > 0.05
+    monkeypatch.setenv("F3D_B200_NO_MESH_BVH", "1")
+    sweep = _native.hybrid_render_terrain_reference(dem, 128, 96, H.CAM, **kw, mesh_vertices=verts, mesh_indices=idx,
+                                                    want_accum=True)
+    assert np.array_equal(_bits(sweep["accum"]), _bits(got["accum"]))
+
+
 def test_render_bit_exact_large_relief_dem():
     # Rainier-shaped closed-form DEM at reduced size: metres-scale coordinates,
     # curvature active on the sun rays, deep pyramid (10 levels), orbit camera outside the DEM.
