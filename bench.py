@@ -292,7 +292,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"rainier-shaped {DEM_N}x{DEM_N} DEM (SURVEY 8d C2), {W}x{Hh}, spp=1 per frame, "
                                    f"{K} frames timed (256 = the 256-spp snapshot)",
-                       "step": "one accumulation frame = k_primary + k_trace<sun> + k_trace<ibl> + k_accum over the image",
+                       "step": "one accumulation frame = k_primary + k_trace (sun list, then IBL list) + k_accum over the image",
                        "l2": "per-frame working set (state 118 MB + DEM cells/pyramid 108 MB) exceeds the 126 MB L2; no flush",
                        "partition": f"interleaved 32-row blocks over {world} GPU(s)", "ms_per_frame": ms_per_step,
                        "rays_per_frame": total_rays / K, "f_shadow": n_shadow / max(n_primary, 1),
@@ -300,8 +300,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_frame,
                          "bytes_per_ray": b_frame / (total_rays / K),
-                         "kernel": "frame = k_primary + k_trace<sun> + k_trace<ibl> + k_accum (dominant: k_trace<sun>)"},
-            "clocks": clocks, "gpu_launches": 4 * K * kw["spp"], "e2e": e2e,
+                         "kernel": "frame = k_primary + k_trace + k_accum (dominant: k_trace)"},
+            "clocks": clocks, "gpu_launches": 3 * K * kw["spp"], "e2e": e2e,
             "image_mean_rgb": float(images["rgba"][..., :3].mean()),
         }
         if not args.no_cpu_baseline and world == 1:

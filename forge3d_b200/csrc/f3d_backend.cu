@@ -524,12 +524,11 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     s->trace_smem_bytes = stack_smem_bytes(P.stack_depth, kTraceCtaThreads);
     if ((rc = allow_smem(k_primary, s->smem_bytes))) return rc;
     if ((rc = allow_smem(k_gbuffer, s->smem_bytes))) return rc;
-    if ((rc = allow_smem(k_trace<true, true>, s->trace_smem_bytes))) return rc;
-    if ((rc = allow_smem(k_trace<true, false>, s->trace_smem_bytes))) return rc;
-    if ((rc = allow_smem(k_trace<false, false>, s->trace_smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<true>, s->trace_smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<false>, s->trace_smem_bytes))) return rc;
     {   // persistent grid: every SM filled to the occupancy the traversal kernel reaches
         int per_sm = 0, sms = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, true>, kTraceCtaThreads, s->trace_smem_bytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, kTraceCtaThreads, s->trace_smem_bytes));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
         s->trace_grid = std::max(per_sm, 1) * std::max(sms, 1);
         if (getenv("F3D_B200_DEBUG"))
@@ -664,12 +663,11 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             P.sample_index = smp;
             k_primary<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P);
             if (P.scene.curvature_enabled)
-                k_trace<true, true><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, s->stream>>>(P);
+                k_trace<true><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, s->stream>>>(P);
             else
-                k_trace<true, false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, s->stream>>>(P);
-            k_trace<false, false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, s->stream>>>(P);
+                k_trace<false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, s->stream>>>(P);
             k_accum<<<s->grid, kThreads, 0, s->stream>>>(P);
-            s->launches += 4;
+            s->launches += 3;
         }
         s->frames++;
     }

@@ -9,7 +9,7 @@
 //                           out_f = temporal_reuse(prev, cand)    [pt_restir_temporal.wgsl:54-109]
 //                           pixels that need a sun / IBL ray append their index to two COMPACTED
 //                           global ray lists (warp ballot + prefix sum, one atomic per warp)
-//   k_trace<sun>, k_trace<ibl> (persistent, per ray)  any-hit traversal [:514-545]; every lane pulls its
+//   k_trace (persistent, per ray: sun list then IBL list)  any-hit traversal [:514-545]; every lane pulls its
 //                           next ray from the list as soon as its current one finishes, so sky pixels,
 //                           back-facing hits and short rays never idle lanes next to long rays
 //   k_accum (per pixel)     combine, accumulate, windowed Welford                               [:547-574]
@@ -387,12 +387,8 @@ constexpr int kTraceCtaThreads = F3D_TRACE_THREADS;
 constexpr int kRefillBelow = F3D_REFILL_BELOW;
 
 template <bool IS_SUN, bool CURV>
-__global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(const __grid_constant__ FrameParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    SmemStack st;
-    st.base = reinterpret_cast<uint32_t*>(smem_raw) + tid;
-    st.stride = kTraceCtaThreads;
+__device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack st) {
+    const uint32_t lane = threadIdx.x & 31u;
     const FastScene& F = P.fast;
     const uint32_t n = P.q_counts[IS_SUN ? 0 : 1];
     const uint32_t* __restrict__ queue = IS_SUN ? P.q_sun : P.q_ibl;
@@ -474,6 +470,18 @@ __global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(
         }
     }
     warp_add_counters(P.counters, 0u, IS_SUN ? n_rays : 0u, IS_SUN ? 0u : n_rays, n_nodes);
+}
+
+// One persistent launch walks the sun list, then the IBL list: a warp that runs out of sun rays moves
+// straight on to IBL rays, so there is no kernel-boundary tail between the two.
+template <bool CURV_SUN>
+__global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(const __grid_constant__ FrameParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemStack st;
+    st.base = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
+    st.stride = kTraceCtaThreads;
+    trace_list<true, CURV_SUN>(P, st);
+    trace_list<false, false>(P, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -178,6 +178,21 @@ def test_render_bit_exact_large_relief_dem():
     assert np.isfinite(got["depth"]).mean() > 0.2
 
 
+def test_full_size_config3_bit_exact():
+    # BASELINE.json configs[2] shape at full size: 4096x4096 DEM (13-level pyramid), 3840x2160 image, a few
+    # samples: ~60 M rays through 67 M DEM cells, compared bit for bit with the oracle (host cores, ~10-20 s).
+    n = 4096
+    dem = H.rainier_dem(n)
+    spacing = 10.0
+    cam = H.rainier_camera(n, spacing, dem)
+    kw = dict(spacing=(spacing, spacing), exaggeration=1.0, albedo=H.ALBEDO, sun_azimuth_deg=302.0,
+              sun_elevation_deg=24.0, max_frames=2, min_frames=2, variance_threshold=1e30, spp=3)
+    got, ref = _both(dem, 3840, 2160, cam, **kw)
+    _assert_same_render(got, ref, "config 3 full size")
+    assert got["rays_primary"] == 3840 * 2160 * 3 * 2
+    assert np.isfinite(got["depth"]).mean() > 0.2
+
+
 def test_golden_scene_converges_and_matches_reference_golden():
     dem = H.golden_dem()
     got, ref = _both(dem, H.SIZE, H.SIZE, H.CAM, **H.scene_kwargs(dem))
