@@ -209,6 +209,41 @@ __host__ __device__ inline size_t stack_smem_bytes(uint32_t stack_depth, int thr
 //                                               miss the slots hold the sky radiance (:489)
 constexpr uint32_t kRecHit = 1u, kRecSun = 2u, kRecSunReuseDir = 4u;
 
+// Cache policy switch for once-per-frame per-pixel state.  Streaming (evict-first) accesses were measured
+// SLOWER (1.43 vs 1.36 ms/frame: the records are re-read from L2 by the next kernel), so the default is
+// ordinary L2-cached accesses; pinning the pyramid with an L2 access-policy window made no difference.
+#ifndef F3D_STREAMING_STATE
+#define F3D_STREAMING_STATE 0
+#endif
+__device__ __forceinline__ void st_stream(float4* p, float4 v) {
+#if F3D_STREAMING_STATE
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ void st_stream(float2* p, float2 v) {
+#if F3D_STREAMING_STATE
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+#if F3D_STREAMING_STATE
+    return __ldcs(p);
+#else
+    return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ float2 ld_stream(const float2* p) {
+#if F3D_STREAMING_STATE
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+
 // intersect_hybrid (hybrid_traversal.wgsl:175-201) on the production traversal.
 struct PrimaryHit { bool hit; uint32_t hit_type; float t; v3 point, normal; };
 
@@ -233,7 +268,10 @@ __device__ __forceinline__ PrimaryHit primary_hit(const FrameParams& P, const Ra
 // ---------------------------------------------------------------------------------------------
 // k_primary: per pixel, one camera sample.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ FrameParams P) {
+#ifndef F3D_PRIMARY_MIN_CTAS
+#define F3D_PRIMARY_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     SmemStack st;
@@ -300,9 +338,9 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ Fr
         float4* rec = P.rec + 4 * (size_t)pix;
         if (!hit.hit) {
             const v3 sky = env_radiance(S, ray.d);
-            rec[0] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
-            rec[2] = make_float4(0.0f, 0.0f, 0.0f, sky.x);
-            rec[3] = make_float4(sky.y, sky.z, 0.0f, 0.0f);
+            st_stream(rec + 0, make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u)));
+            st_stream(rec + 2, make_float4(0.0f, 0.0f, 0.0f, sky.x));
+            st_stream(rec + 3, make_float4(sky.y, sky.z, 0.0f, 0.0f));
         } else {
             // ---- shading set-up (:492-545 without the two visibility factors) ----
             const v3 n = hit.normal;
@@ -329,10 +367,10 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ Fr
             const v3 ei = cosine_dir(n, u1, u2);
             want_ibl = true;
             const v3 ibl_pre = albedo * env_radiance(S, ei);
-            rec[0] = make_float4(shade_o.x, shade_o.y, shade_o.z, __uint_as_float(flags));
-            rec[1] = make_float4(ei.x, ei.y, ei.z, reuse_w);
-            rec[2] = make_float4(sun_pre.x, sun_pre.y, sun_pre.z, ibl_pre.x);
-            rec[3] = make_float4(ibl_pre.y, ibl_pre.z, 0.0f, 0.0f);
+            __stcg(rec + 0, make_float4(shade_o.x, shade_o.y, shade_o.z, __uint_as_float(flags)));   // re-read by k_trace
+            __stcg(rec + 1, make_float4(ei.x, ei.y, ei.z, reuse_w));
+            st_stream(rec + 2, make_float4(sun_pre.x, sun_pre.y, sun_pre.z, ibl_pre.x));
+            st_stream(rec + 3, make_float4(ibl_pre.y, ibl_pre.z, 0.0f, 0.0f));
         }
 
         if (s + 1u < spp) {
@@ -378,7 +416,7 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ Fr
 #define F3D_REFILL_BELOW 24
 #endif
 #ifndef F3D_TRACE_MIN_CTAS
-#define F3D_TRACE_MIN_CTAS 1
+#define F3D_TRACE_MIN_CTAS 6
 #endif
 #ifndef F3D_TRACE_THREADS
 #define F3D_TRACE_THREADS 128
@@ -495,14 +533,14 @@ __global__ void __launch_bounds__(kThreads) k_accum(const __grid_constant__ Fram
     const uint32_t pix = gy * P.W + gx;
     const uint32_t spp = max(P.spp, 1u), s = P.sample_index;
     const float4* rec = P.rec + 4 * (size_t)pix;
-    const float4 r0 = __ldcg(rec), r2 = __ldcg(rec + 2), r3 = __ldcg(rec + 3);
+    const float4 r0 = ld_stream(rec), r2 = ld_stream(rec + 2), r3 = ld_stream(rec + 3);
     const uint32_t flags = __float_as_uint(r0.w);
     v3 fr = V3(0, 0, 0);
     if (s > 0u) { const float4 c = P.sstate[3 * (size_t)pix + 2]; fr = V3(c.x, c.y, c.z); }
     if (!(flags & kRecHit)) {
         fr = fr + V3(r2.w, r3.x, r3.y);                       // sky radiance (:489)
     } else {
-        const float4 r1 = __ldcg(rec + 1);
+        const float4 r1 = ld_stream(rec + 1);
         v3 sun = V3(0, 0, 0);
         if (flags & kRecSun) {
             const float vis = P.occl_sun[pix] ? 0.0f : 1.0f;
@@ -518,21 +556,21 @@ __global__ void __launch_bounds__(kThreads) k_accum(const __grid_constant__ Fram
     }
     const float fspp = (float)spp;
     fr = V3(fdiv(fr.x, fspp), fdiv(fr.y, fspp), fdiv(fr.z, fspp));
-    float4 acc = P.accum[pix];
+    float4 acc = ld_stream(P.accum + pix);
     acc.x = acc.x + fr.x;
     acc.y = acc.y + fr.y;
     acc.z = acc.z + fr.z;
     acc.w = acc.w + 1.0f;
-    P.accum[pix] = acc;
+    st_stream(P.accum + pix, acc);
     const uint32_t window = max(P.window, 2u);
-    float2 wf = P.welford[pix];
+    float2 wf = ld_stream(P.welford + pix);
     if (P.frame_index % window == 0u) wf = make_float2(0.0f, 0.0f);
     const float mean_lum = luminance(V3(fdiv(acc.x, acc.w), fdiv(acc.y, acc.w), fdiv(acc.z, acc.w)));
     const float k = (float)(P.frame_index % window) + 1.0f;
     const float delta = mean_lum - wf.x;
     const float mean = wf.x + fdiv(delta, k);
     const float m2 = wf.y + delta * (mean_lum - mean);
-    P.welford[pix] = make_float2(mean, m2);
+    st_stream(P.welford + pix, make_float2(mean, m2));
 }
 
 // ---------------------------------------------------------------------------------------------

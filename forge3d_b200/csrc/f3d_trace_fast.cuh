@@ -282,6 +282,10 @@ __device__ __forceinline__ bool leaf_top(const FastScene& S, TraceState& T, cons
 #define F3D_LEAF_BATCH 4
 #endif
 constexpr int kLeafBatch = F3D_LEAF_BATCH;
+#ifndef F3D_LEAF_BATCH_COOP
+#define F3D_LEAF_BATCH_COOP F3D_LEAF_BATCH
+#endif
+constexpr int kLeafBatchCoop = F3D_LEAF_BATCH_COOP;   // static-lane traversal (primary / G-buffer rays)
 
 template <bool ANY_HIT, bool CURV>
 __device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, bool valid, const SmemStack st, uint32_t& nodes) {
@@ -300,7 +304,7 @@ __device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, 
             const bool expandable = busy && !top_is_leaf(T, st);
             const uint32_t m_exp = __ballot_sync(0xFFFFFFFFu, expandable);
             const uint32_t m_leaf = __ballot_sync(0xFFFFFFFFu, busy && !expandable);
-            if (m_exp == 0u || __popc(m_leaf) >= kLeafBatch) break;
+            if (m_exp == 0u || __popc(m_leaf) >= kLeafBatchCoop) break;
         }
         if (busy && top_is_leaf(T, st)) {
             nodes++;
