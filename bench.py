@@ -123,6 +123,8 @@ def calibrate_oracle_threads(dem, cam, kw):
         n = os.cpu_count() or 1
     w, h, _ = CPU_SAMPLE
     best, best_t = n, None
+    oracle.set_threads(n)
+    oracle.render(dem, w, h, cam, **kw, max_frames=3, min_frames=3, variance_threshold=1e30)   # warm threads + page cache
     for cand in sorted({max(n, 1), max(n // 2, 1), max(n // 4, 1)}, reverse=True):
         oracle.set_threads(cand)
         out = oracle.render(dem, w, h, cam, **kw, max_frames=6, min_frames=6, variance_threshold=1e30)
