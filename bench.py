@@ -17,8 +17,9 @@ primary / sun-shadow / IBL rays + temporal reuse + accumulate + Welford) over th
 `--impl reference` times the reference algorithm's CPU implementation (the oracle port: the Rust+wgpu
 reference cannot be built in this image) on the same workload at a bounded sample size.
 
-N > 1 (torchrun): the image is dealt to ranks in interleaved 32-row blocks; halo rows travel over
-NVLink peer stores inside k_frame; one NCCL all-gather assembles the frame.  scaling = "strong".
+N > 1 (torchrun): the image is dealt to ranks in interleaved 16-row blocks; halo rows and the per-frame
+cross-GPU barrier travel over NVLink peer stores inside k_primary; one NCCL all-gather assembles the frame.
+scaling = "strong".
 """
 from __future__ import annotations
 
@@ -321,7 +322,7 @@ def main():
                                    f"{K} frames timed (256 = the 256-spp snapshot)",
                        "step": "one accumulation frame = k_primary + k_trace (sun list, then IBL list) + k_accum over the image",
                        "l2": "per-frame working set (state 118 MB + DEM cells/pyramid 108 MB) exceeds the 126 MB L2; no flush",
-                       "partition": f"interleaved 32-row blocks over {world} GPU(s)", "ms_per_frame": ms_per_step,
+                       "partition": f"interleaved 16-row blocks over {world} GPU(s)", "ms_per_frame": ms_per_step,
                        "rays_per_frame": total_rays / K, "f_shadow": n_shadow / max(n_primary, 1),
                        "f_ibl": n_ibl / max(n_primary, 1), "nodes_per_ray": n_nodes / max(total_rays, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -474,6 +474,7 @@ struct f3d_session {
     // peers
     void* peer_ptrs[8 * F3D_IPC_HANDLES_PER_RANK] = {};
     int n_peer_ptrs = 0;
+    uint32_t* d_sync = nullptr;     // [0] CTA counter, [1]/[2] neighbours' completed frames, [3] timeout flag (IPC-shared)
     // bookkeeping
     uint32_t frames = 0;
     uint32_t max_frames = 0, min_frames = 0;
@@ -498,6 +499,7 @@ static void session_free(f3d_session* s) {
     for (int i = 0; i < s->n_peer_ptrs; i++)
         if (s->peer_ptrs[i]) cudaIpcCloseMemHandle(s->peer_ptrs[i]);
     if (s->stream) cudaStreamSynchronize(s->stream);      // nothing may still touch buffers that get parked
+    if (s->d_sync) cudaFree(s->d_sync);
     const int dv = s->device;
     const bool ipc = s->P.part_world > 1u;                  // resv images may be mapped by peers: never park them
     s->terrain.release();
@@ -577,7 +579,7 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     // ---- partition ----
     P.part_world = std::max(d->part_world, 1u);
     P.part_rank = P.part_world > 1 ? d->part_rank : 0u;
-    uint32_t block_rows = d->part_block_rows ? d->part_block_rows : 32u;
+    uint32_t block_rows = d->part_block_rows ? d->part_block_rows : 16u;
     block_rows = ((block_rows + kTileH - 1) / kTileH) * kTileH;
     if (P.part_world == 1) block_rows = ((H + kTileH - 1) / kTileH) * kTileH;   // one block = whole image
     P.block_rows = block_rows;
@@ -693,6 +695,13 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     P.accum = s->d_accum; P.welford = s->d_welford; P.pixflags = s->d_pixflags; P.counters = s->d_counters;
     P.resv_in = s->d_resv[1]; P.resv_out = s->d_resv[0];
     P.peer_up = nullptr; P.peer_down = nullptr;
+    P.sync_local = nullptr; P.peer_sync_up = nullptr; P.peer_sync_down = nullptr; P.sync_error = nullptr;
+    if (P.part_world > 1u) {
+        CUDA_TRY(cudaMalloc(&s->d_sync, 8 * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemsetAsync(s->d_sync, 0, 8 * sizeof(uint32_t), s->stream));
+        P.sync_local = s->d_sync;
+        P.sync_error = s->d_sync + 3;
+    }
 
     // ---- one-shot G-buffer / centre-ray AOV pass (render_terrain.rs:1091-1121) ----
     GbufferOut G{s->d_pixflags, s->d_aov_normal, s->d_aov_depth};
@@ -736,6 +745,8 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             const uint32_t up = (P.part_rank + P.part_world - 1u) % P.part_world, down = (P.part_rank + 1u) % P.part_world;
             P.peer_up = (float4*)s->peer_ptrs[up * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
             P.peer_down = (float4*)s->peer_ptrs[down * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
+            P.peer_sync_up = (uint32_t*)s->peer_ptrs[up * F3D_IPC_HANDLES_PER_RANK + 2];
+            P.peer_sync_down = (uint32_t*)s->peer_ptrs[down * F3D_IPC_HANDLES_PER_RANK + 2];
         }
         for (uint32_t smp = 0; smp < P.spp; smp++) {
             P.sample_index = smp;
@@ -803,12 +814,18 @@ static int resolve_device_impl(f3d_session* s, void* d_rgba, void* d_albedo, voi
     R.validity = s->d_gate + 2;
     R.last_frame = s->frames - 1u;
     CUDA_TRY(cudaMemsetAsync(s->d_gate + 2, 0, 2 * sizeof(uint32_t), s->stream));
+    if (s->n_peer_ptrs) { k_wait_peers<<<1, 32, 0, s->stream>>>(P, s->frames); s->launches++; }
     k_resolve<<<s->grid, kTileW * kTileH, 0, s->stream>>>(P, R);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     if (check_validity) {
         CUDA_TRY(cudaMemcpyAsync(s->h_gate + 2, s->d_gate + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (s->d_sync) {
+            uint32_t timed_out = 0;
+            CUDA_TRY(cudaMemcpy(&timed_out, s->d_sync + 3, sizeof timed_out, cudaMemcpyDeviceToHost));
+            if (timed_out) return fail(F3D_ERR_DEVICE, "multi-GPU frame barrier timed out waiting for a neighbour rank (peer died?)");
+        }
         if (s->h_gate[2]) return fail(F3D_ERR_RENDER, "terrain PT reservoir bookkeeping produced non-finite values");
         const bool require = s->sun_el_deg > 0.0f && s->sun_intensity > 0.0f &&
                              (s->sun_color[0] > 0.0f || s->sun_color[1] > 0.0f || s->sun_color[2] > 0.0f);
@@ -895,7 +912,10 @@ extern "C" int f3d_session_ipc_export(f3d_session* s, uint8_t* handles) {
     memcpy(handles, &h, sizeof h);
     CUDA_TRY(cudaIpcGetMemHandle(&h, s->d_resv[1]));
     memcpy(handles + F3D_IPC_HANDLE_BYTES, &h, sizeof h);
-    memset(handles + 2 * F3D_IPC_HANDLE_BYTES, 0, F3D_IPC_HANDLE_BYTES);   // reserved
+    if (s->d_sync) {
+        CUDA_TRY(cudaIpcGetMemHandle(&h, s->d_sync));
+        memcpy(handles + 2 * F3D_IPC_HANDLE_BYTES, &h, sizeof h);
+    } else memset(handles + 2 * F3D_IPC_HANDLE_BYTES, 0, F3D_IPC_HANDLE_BYTES);
     return 0;
 }
 
@@ -909,7 +929,7 @@ extern "C" int f3d_session_ipc_import(f3d_session* s, const uint8_t* all) {
         if (r == s->P.part_rank) continue;
         const uint32_t up = (s->P.part_rank + world - 1u) % world, down = (s->P.part_rank + 1u) % world;
         if (r != up && r != down) continue;
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < 3; k++) {
             cudaIpcMemHandle_t h;
             memcpy(&h, all + ((size_t)r * F3D_IPC_HANDLES_PER_RANK + k) * F3D_IPC_HANDLE_BYTES, sizeof h);
             void* p = nullptr;

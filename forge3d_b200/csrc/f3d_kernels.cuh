@@ -62,7 +62,51 @@ struct FrameParams {
     // NVLink halo push: peer images of resv_out for the rank above / below (NULL = none)
     float4* peer_up;
     float4* peer_down;
+    // Cross-GPU frame barrier in peer memory (no host, no NCCL): sync_local[0] counts finished CTAs of the
+    // current k_primary, sync_local[1] / [2] = frames completed by the rank above / below (written by THEM).
+    // The last CTA of k_primary(f) stores f+1 into the neighbours' slots after a system-scope fence.
+    uint32_t* sync_local;
+    uint32_t* peer_sync_up;     // the up neighbour's sync array (I am its "below" rank -> slot 2)
+    uint32_t* peer_sync_down;   // the down neighbour's sync array (I am its "above" rank -> slot 1)
+    uint32_t* sync_error;       // set to 1 if a wait timed out (host raises)
 };
+
+// Spin until both neighbours have completed `need` frames.  One thread per CTA polls local memory; a
+// 2-second clock budget turns a dead peer into an error instead of a hung GPU.
+__device__ __forceinline__ void wait_neighbours(const FrameParams& P, uint32_t need) {
+    if (P.part_world > 1u && need > 0u && P.sync_local != nullptr) {
+        if (threadIdx.x == 0) {
+            const volatile uint32_t* f = P.sync_local;
+            const long long t0 = clock64();
+            while (f[1] < need || f[2] < need) {
+                if (clock64() - t0 > 4000000000ll) { atomicExch(P.sync_error, 1u); break; }
+                __nanosleep(200);
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+}
+
+// Called by every CTA when its stores (incl. NVLink halo stores) are issued; the last CTA publishes
+// "frame_index + 1 frames done" to both neighbours.
+__device__ __forceinline__ void signal_neighbours(const FrameParams& P) {
+    if (P.part_world > 1u && P.sync_local != nullptr) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const uint32_t total = gridDim.x * gridDim.y;
+            const uint32_t old = atomicAdd(P.sync_local + 0, 1u);
+            if (old == total - 1u) {
+                P.sync_local[0] = 0u;
+                __threadfence_system();
+                if (P.peer_sync_up) *(volatile uint32_t*)(P.peer_sync_up + 2) = P.frame_index + 1u;
+                if (P.peer_sync_down) *(volatile uint32_t*)(P.peer_sync_down + 1) = P.frame_index + 1u;
+                __threadfence_system();
+            }
+        }
+    }
+}
 
 __device__ __forceinline__ v3 ld3(const float* p) { return V3(p[0], p[1], p[2]); }
 
@@ -284,6 +328,7 @@ __global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(cons
     uint32_t n_primary = 0, n_nodes = 0;
     bool want_sun = false, want_ibl = false;
     const uint32_t spp = max(P.spp, 1u), s = P.sample_index;
+    if (s == 0u) wait_neighbours(P, P.frame_index);   // the spatial pass reads halo rows the neighbours pushed last frame
     const bool multi = spp > 1u;
 
     const SceneParams& S = P.scene;
@@ -404,7 +449,11 @@ __global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(cons
         if (want_ibl) P.q_ibl[b_ibl + __popc(m_ibl & lt)] = pix;
     }
     warp_add_counters(P.counters, n_primary, 0u, 0u, n_nodes);
+    if (s + 1u == spp) signal_neighbours(P);
 }
+
+// Orders the final reuse pass (k_resolve) after the neighbours' last halo stores.
+__global__ void k_wait_peers(const __grid_constant__ FrameParams P, uint32_t need) { wait_neighbours(P, need); }
 
 // ---------------------------------------------------------------------------------------------
 // k_trace<IS_SUN, CURV>: persistent any-hit traversal over one compacted ray list

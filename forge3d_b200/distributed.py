@@ -10,8 +10,10 @@ BASELINE.json's north_star and SURVEY section 8e.  Design:
     within +-3 px (pt_restir_spatial.wgsl:170-171).  k_frame stores the 3 border rows of each owned
     block straight into the neighbours' images over NVLink peer memory (CUDA IPC mappings) while it
     computes -- no staging copy, no separate exchange kernel;
-  * a frame may only start when the neighbours' previous frame (and its halo stores) completed:
-    one 4-byte NCCL all-reduce per frame on the render stream acts as the cross-GPU barrier;
+  * a frame may only start when the neighbours' previous frame (and its halo stores) completed: the
+    last CTA of k_primary publishes "frame f done" into the neighbours' memory after a system-scope
+    fence and the next k_primary spins on its local copy (csrc/f3d_kernels.cuh: wait_neighbours /
+    signal_neighbours) -- no host round trip and no NCCL call inside the frame loop;
   * the convergence gate needs max over ranks of the windowed variance: one NCCL MAX all-reduce per
     32-frame window; validity flags are OR-reduced the same way;
   * the framebuffer is assembled by ONE NCCL all-gather of the packed owned rows (RGBA8 + AOVs).
@@ -26,10 +28,10 @@ TILE_H = 16  # kTileH in csrc/f3d_kernels.cuh: block_rows is rounded up to a mul
 
 
 def effective_block_rows(block_rows: int, height: int, world: int) -> int:
-    """Mirrors session_create_impl (csrc/f3d_backend.cu): default 32, multiple of 16; one block when world == 1."""
+    """Mirrors session_create_impl (csrc/f3d_backend.cu): default 16, multiple of 16; one block when world == 1."""
     if world <= 1:
         return ((height + TILE_H - 1) // TILE_H) * TILE_H
-    b = block_rows if block_rows else 32
+    b = block_rows if block_rows else 16
     return ((b + TILE_H - 1) // TILE_H) * TILE_H
 
 
@@ -114,14 +116,9 @@ class PartitionedRender:
             dist.barrier(group=group)
 
     def render_frames(self, n: int) -> None:
-        """n accumulation frames; with world > 1 a 4-byte all-reduce after every frame orders the
-        neighbours' halo stores before the next frame's reuse pass."""
-        if self.world == 1:
-            self.session.render_frames(n)
-            return
-        for _ in range(n):
-            self.session.render_frames(1)
-            self.dist.all_reduce(self._token, group=self.group)
+        """n accumulation frames, enqueued back to back; with world > 1 the cross-GPU ordering is done
+        on the devices by k_primary's peer-memory frame barrier."""
+        self.session.render_frames(n)
 
     def variance(self) -> Tuple[float, bool]:
         v, bad = self.session.variance()
@@ -152,4 +149,8 @@ class PartitionedRender:
         return out
 
     def close(self):
+        # peers store halo rows and barrier flags into this rank's memory: nobody may free before everybody is done
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
         self.session.close()

@@ -74,7 +74,7 @@ typedef struct f3d_terrain_desc {
                                       (src/core/memory_tracker.rs:16, render_terrain.rs:875-888) */
     uint32_t part_rank, part_world;/* image-row partition: this process renders row blocks
                                       b with b % part_world == part_rank (world 0/1 = whole image) */
-    uint32_t part_block_rows;      /* rows per block (0 = default 32) */
+    uint32_t part_block_rows;      /* rows per block (0 = default 16; rounded up to a multiple of 16) */
 } f3d_terrain_desc;
 
 /* Replaces TerrainReferenceOutput, render_terrain.rs:285-299. */

@@ -1,6 +1,6 @@
-"""Multi-GPU image partition on real devices (NCCL): a render dealt to 2 ranks in interleaved row blocks,
-with halo rows pushed over NVLink peer memory inside k_primary, must be BIT-IDENTICAL to the
-single-GPU render (SURVEY section 8e "exact mode").  Skipped when fewer than 2 GPUs are visible."""
+"""Multi-GPU image partition on real devices (NCCL): a render dealt to N ranks in interleaved row blocks,
+with halo rows and the frame barrier pushed over NVLink peer memory inside k_primary, must be
+BIT-IDENTICAL to the single-GPU render (SURVEY section 8e "exact mode").  Skipped when too few GPUs are visible."""
 import os
 import socket
 
@@ -46,12 +46,13 @@ def _worker(rank, world, port, frames, width, height, block_rows, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("width,height,block_rows,frames", [(96, 80, 16, 40), (64, 50, 32, 6)])
-def test_two_gpu_partition_is_bit_identical(width, height, block_rows, frames):
+@pytest.mark.parametrize("world,width,height,block_rows,frames", [(2, 96, 80, 16, 40), (2, 64, 50, 32, 6),
+                                                                      (4, 96, 120, 16, 24), (3, 80, 100, 16, 8)])
+def test_partition_is_bit_identical(world, width, height, block_rows, frames):
     import torch
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
 
     from forge3d_b200 import _native
@@ -62,7 +63,7 @@ def test_two_gpu_partition_is_bit_identical(width, height, block_rows, frames):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, frames, width, height, block_rows, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, frames, width, height, block_rows, q)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=300)
