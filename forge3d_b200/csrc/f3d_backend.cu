@@ -487,9 +487,24 @@ struct f3d_session {
     size_t smem_bytes = 0;          // stack smem of the per-pixel kernels (kThreads)
     size_t trace_smem_bytes = 0;    // stack smem of k_trace (kTraceCtaThreads)
     int trace_grid = 0;             // persistent CTAs of k_trace
-    float4* d_rec = nullptr;
-    uint8_t* d_occl_sun = nullptr; uint8_t* d_occl_ibl = nullptr;
-    uint32_t* d_q_sun = nullptr; uint32_t* d_q_ibl = nullptr; uint32_t* d_q_counts = nullptr;
+    // Frame pipelining: k_primary(step+1) only depends on k_primary(step) (reservoir records) and on its
+    // wavefront buffers being free; k_trace(step) only on k_primary(step); k_accum(step) on k_trace(step)
+    // and k_accum(step-1).  The primary kernels run on the session stream, k_trace/k_accum of step i on
+    // the stream of buffer slot i % n_slots, so consecutive frames overlap and the tail of one kernel is
+    // filled by the next step's work instead of idling SMs.
+    struct Slot {
+        float4* rec = nullptr;
+        uint8_t* occl_sun = nullptr; uint8_t* occl_ibl = nullptr;
+        uint32_t* q_sun = nullptr; uint32_t* q_ibl = nullptr; uint32_t* q_counts = nullptr;
+        cudaEvent_t primary_done = nullptr, accum_done = nullptr;
+        cudaStream_t stream = nullptr;     // k_trace / k_accum of the steps that use this slot
+        bool used = false;
+    };
+    static constexpr int kMaxSlots = 4;
+    Slot slots[kMaxSlots];
+    int n_slots = 1;
+    uint64_t steps = 0;
+    cudaEvent_t join_ev = nullptr;
     float4* d_sstate = nullptr;
 };
 
@@ -509,8 +524,15 @@ static void session_free(f3d_session* s) {
     cached_free(s->d_resv[0], dv, !ipc); cached_free(s->d_resv[1], dv, !ipc);
     cached_free(s->d_pixflags, dv); cached_free(s->d_aov_normal, dv); cached_free(s->d_aov_depth, dv);
     cached_free(s->d_counters, dv); cached_free(s->d_gate, dv);
-    cached_free(s->d_rec, dv); cached_free(s->d_occl_sun, dv); cached_free(s->d_occl_ibl, dv);
-    cached_free(s->d_q_sun, dv); cached_free(s->d_q_ibl, dv); cached_free(s->d_q_counts, dv); cached_free(s->d_sstate, dv);
+    for (auto& sl : s->slots) {
+        if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+        cached_free(sl.rec, dv); cached_free(sl.occl_sun, dv); cached_free(sl.occl_ibl, dv);
+        cached_free(sl.q_sun, dv); cached_free(sl.q_ibl, dv); cached_free(sl.q_counts, dv);
+        if (sl.primary_done) cudaEventDestroy(sl.primary_done);
+        if (sl.accum_done) cudaEventDestroy(sl.accum_done);
+    }
+    if (s->join_ev) cudaEventDestroy(s->join_ev);
+    cached_free(s->d_sstate, dv);
     cached_free(s->d_rgba, dv); cached_free(s->d_albedo, dv); cached_free(s->d_normal, dv); cached_free(s->d_depth, dv);
     if (s->h_gate) cudaFreeHost(s->h_gate);
     if (s->h_stage) cudaFreeHost(s->h_stage);
@@ -610,6 +632,7 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
         int per_sm = 0, sms = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, kTraceCtaThreads, s->trace_smem_bytes));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+        if (const char* e = getenv("F3D_B200_TRACE_CTAS")) per_sm = std::min(std::max(atoi(e), 1), std::max(per_sm, 1));
         s->trace_grid = std::max(per_sm, 1) * std::max(sms, 1);
         if (getenv("F3D_B200_DEBUG"))
             fprintf(stderr, "[forge3d_b200] k_trace: %d CTAs/SM x %d SMs, %zu B smem/CTA, stack depth %u\n", per_sm, sms,
@@ -682,15 +705,28 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     if ((rc = dmalloc(s, &s->d_gate, (size_t)4, true))) return rc;
     CUDA_TRY(cudaMallocHost(&s->h_gate, 4 * sizeof(uint32_t)));
     s->host_visible_bytes += 4 * sizeof(uint32_t);
-    if ((rc = dmalloc(s, &s->d_rec, npx * 4, true))) return rc;
-    if ((rc = dmalloc(s, &s->d_occl_sun, npx, true))) return rc;
-    if ((rc = dmalloc(s, &s->d_occl_ibl, npx, true))) return rc;
-    if ((rc = dmalloc(s, &s->d_q_sun, npx, false))) return rc;
-    if ((rc = dmalloc(s, &s->d_q_ibl, npx, false))) return rc;
-    if ((rc = dmalloc(s, &s->d_q_counts, (size_t)4, true))) return rc;
+    {
+        // default: 4 steps in flight, fewer when the per-slot buffers (74 B/pixel) would exceed 6 GB in total
+        const char* e = getenv("F3D_B200_PIPELINE");
+        const int by_memory = (int)std::max<uint64_t>(1, (6ull << 30) / std::max<uint64_t>(1, (uint64_t)npx * 74));
+        s->n_slots = e ? std::min(std::max(atoi(e), 1), (int)f3d_session::kMaxSlots)
+                       : std::min((int)f3d_session::kMaxSlots, by_memory);
+    }
+    for (int k = 0; k < s->n_slots; k++) {
+        f3d_session::Slot& sl = s->slots[k];
+        if ((rc = dmalloc(s, &sl.rec, npx * 4, true))) return rc;
+        if ((rc = dmalloc(s, &sl.occl_sun, npx, true))) return rc;
+        if ((rc = dmalloc(s, &sl.occl_ibl, npx, true))) return rc;
+        if ((rc = dmalloc(s, &sl.q_sun, npx, false))) return rc;
+        if ((rc = dmalloc(s, &sl.q_ibl, npx, false))) return rc;
+        if ((rc = dmalloc(s, &sl.q_counts, (size_t)4, true))) return rc;
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.primary_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.accum_done, cudaEventDisableTiming));
+        if (s->n_slots > 1) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    }
+    if (s->n_slots > 1) CUDA_TRY(cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming));
     if (P.spp > 1u && (rc = dmalloc(s, &s->d_sstate, npx * 3, true))) return rc;
-    P.rec = s->d_rec; P.occl_sun = s->d_occl_sun; P.occl_ibl = s->d_occl_ibl;
-    P.q_sun = s->d_q_sun; P.q_ibl = s->d_q_ibl; P.q_counts = s->d_q_counts; P.sstate = s->d_sstate;
+    P.sstate = s->d_sstate;
     P.sample_index = 0u;
     P.accum = s->d_accum; P.welford = s->d_welford; P.pixflags = s->d_pixflags; P.counters = s->d_counters;
     P.resv_in = s->d_resv[1]; P.resv_out = s->d_resv[0];
@@ -735,6 +771,11 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
     if (!s) return fail(F3D_ERR_ARGUMENT, "null session");
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    const bool pipelined = s->n_slots > 1;
+    if (pipelined) {   // the slot streams start after whatever is already queued on the session stream
+        CUDA_TRY(cudaEventRecord(s->join_ev, s->stream));
+        for (int k = 0; k < s->n_slots; k++) CUDA_TRY(cudaStreamWaitEvent(s->slots[k].stream, s->join_ev, 0));
+    }
     for (uint32_t i = 0; i < n; i++) {
         FrameParams& P = s->P;
         P.frame_index = s->frames;
@@ -750,16 +791,32 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
         }
         for (uint32_t smp = 0; smp < P.spp; smp++) {
             P.sample_index = smp;
+            f3d_session::Slot& sl = s->slots[s->steps % (uint64_t)s->n_slots];
+            P.rec = sl.rec; P.occl_sun = sl.occl_sun; P.occl_ibl = sl.occl_ibl;
+            P.q_sun = sl.q_sun; P.q_ibl = sl.q_ibl; P.q_counts = sl.q_counts;
+            cudaStream_t ts = pipelined ? sl.stream : s->stream;
+            f3d_session::Slot& prev = s->slots[(s->steps + (uint64_t)s->n_slots - 1u) % (uint64_t)s->n_slots];
+            if (pipelined && sl.used) CUDA_TRY(cudaStreamWaitEvent(s->stream, sl.accum_done, 0));   // buffer set free again
             k_primary<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P);
+            if (pipelined) {
+                CUDA_TRY(cudaEventRecord(sl.primary_done, s->stream));
+                CUDA_TRY(cudaStreamWaitEvent(ts, sl.primary_done, 0));
+            }
             if (P.scene.curvature_enabled)
-                k_trace<true><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, s->stream>>>(P);
+                k_trace<true><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
             else
-                k_trace<false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, s->stream>>>(P);
-            k_accum<<<s->grid, kThreads, 0, s->stream>>>(P);
+                k_trace<false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+            if (pipelined && prev.used) CUDA_TRY(cudaStreamWaitEvent(ts, prev.accum_done, 0));     // accumulate in frame order
+            k_accum<<<s->grid, kThreads, 0, ts>>>(P);
+            if (pipelined) { CUDA_TRY(cudaEventRecord(sl.accum_done, ts)); sl.used = true; }
             s->launches += 3;
+            s->steps++;
         }
         s->frames++;
     }
+    if (pipelined)   // everything that follows on the session stream (variance, resolve, timing) sees all frames
+        for (int k = 0; k < s->n_slots; k++)
+            if (s->slots[k].used) CUDA_TRY(cudaStreamWaitEvent(s->stream, s->slots[k].accum_done, 0));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
     return 0;

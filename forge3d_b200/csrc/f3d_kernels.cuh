@@ -74,7 +74,7 @@ struct FrameParams {
 // Spin until both neighbours have completed `need` frames.  One thread per CTA polls local memory; a
 // 2-second clock budget turns a dead peer into an error instead of a hung GPU.
 __device__ __forceinline__ void wait_neighbours(const FrameParams& P, uint32_t need) {
-    if (P.part_world > 1u && need > 0u && P.sync_local != nullptr) {
+    if (P.part_world > 1u && need > 0u && P.sync_local != nullptr && (P.peer_sync_up != nullptr || P.peer_sync_down != nullptr)) {
         if (threadIdx.x == 0) {
             const volatile uint32_t* f = P.sync_local;
             const long long t0 = clock64();
