@@ -470,7 +470,6 @@ struct f3d_session {
     uint32_t* h_gate = nullptr;       // pinned
     // output staging (host-facing resolve)
     uint8_t* d_rgba = nullptr; float* d_albedo = nullptr; float* d_normal = nullptr; float* d_depth = nullptr;
-    void* h_stage = nullptr; size_t h_stage_bytes = 0;
     // peers
     void* peer_ptrs[8 * F3D_IPC_HANDLES_PER_RANK] = {};
     int n_peer_ptrs = 0;
@@ -535,7 +534,6 @@ static void session_free(f3d_session* s) {
     cached_free(s->d_sstate, dv);
     cached_free(s->d_rgba, dv); cached_free(s->d_albedo, dv); cached_free(s->d_normal, dv); cached_free(s->d_depth, dv);
     if (s->h_gate) cudaFreeHost(s->h_gate);
-    if (s->h_stage) cudaFreeHost(s->h_stage);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);

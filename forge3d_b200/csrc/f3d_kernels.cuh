@@ -30,7 +30,6 @@
 namespace f3d {
 
 constexpr int kTileW = 16, kTileH = 16;      // CTA pixel tile; warps own 8x4 sub-tiles
-constexpr int kMaxPeers = 2;                 // row-block neighbours (above / below)
 
 struct FrameParams {
     SceneParams scene;          // env / mesh / albedo (+ the plain pyramid when the KAT seam keeps it)
@@ -328,7 +327,6 @@ __global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(cons
     uint32_t n_primary = 0, n_nodes = 0;
     bool want_sun = false, want_ibl = false;
     const uint32_t spp = max(P.spp, 1u), s = P.sample_index;
-    if (s == 0u) wait_neighbours(P, P.frame_index);   // the spatial pass reads halo rows the neighbours pushed last frame
     const bool multi = spp > 1u;
 
     const SceneParams& S = P.scene;
@@ -336,16 +334,29 @@ __global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(cons
     const v3 wi = normalize3(ld3(P.light_dir));
     Resv prev_r, cand;
     uint32_t rng = 0u;
-    bool prev_valid = false;
-    v3 sun_dir = wi;
-    float reuse_w = 1.0f;
     Ray ray;
     ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.tmin = 1e-3f; ray.tmax = 1e30f;
     prev_r.w_sum = 0.0f; prev_r.weight = 0.0f; prev_r.target_pdf = 0.0f; prev_r.m = 0u; prev_r.type1 = false;
     cand = prev_r;
     if (active) {
+        // ---- primary ray (:467-485): its RNG stream does not depend on the reuse chain ----
+        if (s == 0u) rng = P.seed_hi ^ (gx * 1664525u) ^ (gy * 1013904223u) ^ (P.frame_index * 92837111u) ^ P.seed_lo;
+        else rng = __float_as_uint(P.sstate[3 * (size_t)pix + 0].x);
+        const float jx = tent_offset(xorshift32(rng)) * 0.5f;
+        const float jy = tent_offset(xorshift32(rng)) * 0.5f;
+        ray = camera_ray(P, gx, gy, jx, jy);
+        n_primary++;
+    }
+    const PrimaryHit hit = primary_hit(P, ray, active, st, n_nodes);   // warp-cooperative
 
-        // ---- merged reservoir from last frame's reuse chain + M-clamp (:452-465) ----
+    // ---- merged reservoir from last frame's reuse chain + M-clamp (:452-465).  Done AFTER the primary
+    // traversal: only the shading below needs it, so the wait for the neighbour GPUs' halo rows (and the
+    // 9 record loads) overlaps with the traversal instead of preceding it. ----
+    if (s == 0u) wait_neighbours(P, P.frame_index);
+    bool prev_valid = false;
+    v3 sun_dir = wi;
+    float reuse_w = 1.0f;
+    if (active) {
         if (s == 0u) {
             const bool facing = (P.pixflags[pix] & 1u) != 0u;
             if (P.frame_index > 0u) prev_r = spatial_reuse(P, P.resv_in, gx, gy, facing, P.frame_index - 1u);
@@ -355,31 +366,19 @@ __global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(cons
                 prev_r.m = 512u;
                 if (prev_r.target_pdf > 0.0f) prev_r.weight = fdiv(prev_r.w_sum, (float)prev_r.m * prev_r.target_pdf);
             }
-            rng = P.seed_hi ^ (gx * 1664525u) ^ (gy * 1013904223u) ^ (P.frame_index * 92837111u) ^ P.seed_lo;
             if (multi) P.sstate[3 * (size_t)pix + 1] = pack_resv(prev_r);
         } else {
             const float4 a = P.sstate[3 * (size_t)pix + 0];
-            rng = __float_as_uint(a.x);
             cand.w_sum = a.y;
             const uint32_t mb = __float_as_uint(a.z);
             cand.m = mb & 0x7FFFFFFFu; cand.type1 = (mb >> 31) != 0u;
             cand.target_pdf = a.w;
             prev_r = unpack_resv(P.sstate[3 * (size_t)pix + 1]);
         }
-        prev_valid = P.frame_index > 0u && prev_r.m > 0u && prev_r.weight > 0.0f &&
-                                prev_r.target_pdf > 0.0f && prev_r.type1;
+        prev_valid = P.frame_index > 0u && prev_r.m > 0u && prev_r.weight > 0.0f && prev_r.target_pdf > 0.0f && prev_r.type1;
         // every populated sample stores direction == wi; the shader re-normalises it (:520)
         sun_dir = prev_valid ? normalize3(wi) : wi;
         reuse_w = prev_valid ? clampf(prev_r.weight, 0.0f, 4.0f) : 1.0f;
-
-        // ---- primary ray (:476-491) ----
-        const float jx = tent_offset(xorshift32(rng)) * 0.5f;
-        const float jy = tent_offset(xorshift32(rng)) * 0.5f;
-        ray = camera_ray(P, gx, gy, jx, jy);
-        n_primary++;
-    }
-    const PrimaryHit hit = primary_hit(P, ray, active, st, n_nodes);   // warp-cooperative
-    if (active) {
         float4* rec = P.rec + 4 * (size_t)pix;
         if (!hit.hit) {
             const v3 sky = env_radiance(S, ray.d);

@@ -1,6 +1,7 @@
 // forge3d_b200/csrc/f3d_trace.cuh
-// Scene parameters + ray traversal device functions: min-max quadtree descent over the DEM with the
-// exact ray/bilinear-patch leaf solve, triangle mesh test, hybrid closest-hit and any-hit wrappers.
+// Scene parameters + the LITERAL restatement of the WGSL traversal (terrain_trace: kept as the on-device
+// cross-check of the production traversal in f3d_trace_fast.cuh, reachable through f3d_trace_rays
+// variant 1), the triangle-mesh test with its BVH, and the environment lookup.
 // Replaces /root/reference/src/shaders/hybrid_terrain_traversal.wgsl:88-383 and
 // hybrid_traversal.wgsl:86-259.  Arithmetic follows the numerics contract (f3d_math.cuh) so the
 // results are bit-identical to oracle/f3d_oracle.c; the data layout is B200-native:
@@ -322,44 +323,6 @@ __device__ __noinline__ Hit intersect_mesh(const SceneParams& S, const Ray& r) {
         }
     }
     return res;
-}
-
-// intersect_hybrid, hybrid_traversal.wgsl:175-201
-__device__ __forceinline__ Hit intersect_hybrid(const SceneParams& S, const Ray& r, uint32_t& nodes) {
-    Hit best;
-    best.hit = 0u;
-    best.t = r.tmax;
-    best.hit_type = 0u;
-    best.point = V3(0, 0, 0);
-    best.normal = V3(0, 0, 0);
-    if (S.traversal_mode == 0u) {
-        Hit mh = intersect_mesh(S, r);
-        if (mh.hit && mh.t < best.t) best = mh;
-    }
-    Ray tr = r;
-    tr.tmax = best.t;
-    Hit th = terrain_trace<false, false>(S, tr, nodes);
-    if (th.hit && th.t < best.t) best = th;
-    return best;
-}
-
-// intersect_hybrid_optimized(ray, 0.01, curv) + `hit.hit != 0 && hit.t < 1e30`, :204-259
-template <bool CURV>
-__device__ __forceinline__ bool occluded(const SceneParams& S, const Ray& r, uint32_t& nodes) {
-    const float max_distance = 1e30f;
-    float best_t = r.tmax;
-    bool best_hit = false;
-    if (S.traversal_mode == 0u) {
-        Hit mh = intersect_mesh(S, r);
-        if (mh.hit && mh.t < 0.01f) return mh.t < max_distance;
-        if (mh.hit && mh.t < best_t) { best_t = mh.t; best_hit = true; }
-    }
-    Ray tr = r;
-    tr.tmax = best_t;
-    Hit th = CURV && S.curvature_enabled ? terrain_trace<true, true>(S, tr, nodes)
-                                         : terrain_trace<true, false>(S, tr, nodes);
-    if (th.hit && th.t < best_t) { best_t = th.t; best_hit = true; }
-    return best_hit && best_t < max_distance;
 }
 
 // terrain_env_radiance :392-405

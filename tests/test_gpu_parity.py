@@ -110,6 +110,64 @@ def test_render_bit_exact_small():
     _assert_same_render(got, ref, "75x41x8")
 
 
+@pytest.mark.parametrize("shape,size", [((2, 2), (33, 20)), ((3, 9), (40, 24)), ((37, 100), (64, 48)), ((129, 65), (48, 48))])
+def test_render_bit_exact_tiny_and_ragged_dems(shape, size):
+    # smallest legal DEM (one cell = a 1-level pyramid whose root is a leaf), ragged non-power-of-two cell
+    # counts and non-square DEMs: exercises the sentinel padding and the collapsed-axis levels
+    rng = np.random.default_rng(shape[0] * 131 + shape[1])
+    dem = rng.uniform(0.0, 1.0, shape).astype(np.float32)
+    span = 80.0
+    kw = dict(spacing=(span / max(shape[1] - 1, 1), span / max(shape[0] - 1, 1)), exaggeration=12.0, albedo=H.ALBEDO,
+              sun_azimuth_deg=140.0, sun_elevation_deg=30.0, max_frames=5, min_frames=5, variance_threshold=1e30, spp=2)
+    got, ref = _both(dem, size[0], size[1], H.CAM, **kw)
+    _assert_same_render(got, ref, f"dem {shape}")
+    assert np.isfinite(got["depth"]).any()
+
+
+def test_native_seam_error_paths_on_gpu():
+    # errors raised below the Python facade (device-side non-finite scan, C++ validate_desc)
+    bad = np.full((16, 16), np.nan, np.float32)
+    with pytest.raises(RuntimeError, match="non-finite"):
+        _native.hybrid_render_terrain_reference(bad, 32, 32, H.CAM, max_frames=4, min_frames=2)
+    dem = H.golden_dem()
+    with pytest.raises(RuntimeError, match="at least 2x2"):
+        _native.hybrid_render_terrain_reference(np.zeros((1, 5), np.float32), 32, 32, H.CAM, max_frames=4, min_frames=2)
+    with pytest.raises(RuntimeError, match="min_frames"):
+        _native.hybrid_render_terrain_reference(dem, 32, 32, H.CAM, max_frames=4, min_frames=8)
+    with pytest.raises(RuntimeError, match="spp"):
+        _native.hybrid_render_terrain_reference(dem, 32, 32, H.CAM, max_frames=4, min_frames=2, spp=65)
+    with pytest.raises(RuntimeError, match="exaggeration"):
+        _native.hybrid_render_terrain_reference(dem, 32, 32, H.CAM, max_frames=4, min_frames=2, exaggeration=0.0)
+    with pytest.raises(RuntimeError, match="flat earth only supports"):
+        _native.hybrid_render_terrain_reference(dem, 32, 32, H.CAM, max_frames=4, min_frames=2, earth_model="flat")
+    with pytest.raises(RuntimeError, match="out-of-bounds"):
+        _native.hybrid_render_terrain_reference(dem, 32, 32, H.CAM, max_frames=4, min_frames=2,
+                                                mesh_vertices=np.zeros((3, 3), np.float32),
+                                                mesh_indices=np.array([[0, 1, 7]], np.uint32))
+    # a session survives an error in a previous call (no poisoned global state)
+    ok = _native.hybrid_render_terrain_reference(dem, 32, 32, H.CAM, **{**H.scene_kwargs(dem), "max_frames": 4, "min_frames": 2,
+                                                                        "variance_threshold": 1e30})
+    assert ok["frames"] == 4
+
+
+def test_session_api_matches_one_call_path():
+    from forge3d_b200.session import Session
+
+    dem = H.golden_dem()
+    kw = {**H.scene_kwargs(dem), "max_frames": 64, "min_frames": 64, "variance_threshold": 1e30}
+    one = _native.hybrid_render_terrain_reference(dem, 80, 60, H.CAM, **kw, want_accum=True)
+    with Session(dem, 80, 60, H.CAM, **kw) as s:
+        s.render_frames(20)
+        s.render_frames(12)
+        v32, bad = s.variance()          # the gate value at the first window boundary
+        s.render_frames(32)
+        v64, bad2 = s.variance()
+        out = s.resolve_host(want_accum=True)
+        assert s.frames == 64 and not bad and not bad2
+    assert np.array_equal(_bits(out["accum"]), _bits(one["accum"])) and np.array_equal(out["rgba"], one["rgba"])
+    assert np.float32(v64) == np.float32(one["variance"]) and v32 > v64
+
+
 def test_render_bit_exact_spp_and_window():
     dem = H.golden_dem()
     kw = {**H.scene_kwargs(dem), "max_frames": 40, "min_frames": 40, "variance_threshold": 1e30, "spp": 3}
