@@ -42,7 +42,7 @@ struct FrameParams {
     float light_dir[3], light_color[3];
     // image-row partition: this device owns row blocks b with b % world == rank
     uint32_t part_rank, part_world, block_rows, tiles_per_block, nblocks;
-    // per-pixel state (full-image arrays, only owned rows + 3-row halos are touched)
+    // per-pixel state (full-image arrays, only owned rows + 3/4-row halos are touched)
     float4* accum;
     float2* welford;
     const float4* resv_in;     // out_{f-1}: (w_sum, weight, target_pdf, bits(m | type<<31))
@@ -428,7 +428,10 @@ __global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(cons
             __stcg(P.resv_out + pix, out_rec);
             if (P.part_world > 1u) {
                 const uint32_t b = gy / P.block_rows, in_y = gy - b * P.block_rows;
-                if (in_y < 3u && b > 0u && P.peer_up) __stcg(P.peer_up + pix, out_rec);
+                // The spatial pass draws offsets floor(u*7)-3 with u in [0,1]: xorshift32 can return exactly 1.0
+                // (SURVEY section 9.3), so offsets span [-3, +4]: the block ABOVE needs our first FOUR rows, the
+                // block below our last three.
+                if (in_y < 4u && b > 0u && P.peer_up) __stcg(P.peer_up + pix, out_rec);
                 if (in_y + 3u >= P.block_rows && b + 1u < P.nblocks && P.peer_down) __stcg(P.peer_down + pix, out_rec);
             }
         }

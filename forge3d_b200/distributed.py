@@ -7,7 +7,8 @@ BASELINE.json's north_star and SURVEY section 8e.  Design:
     rows balance; every index/seed computation uses GLOBAL pixel coordinates, so a partitioned
     render is bit-identical to the single-GPU render;
   * the only per-frame cross-pixel dependency is the spatial reuse pass reading temporal records
-    within +-3 px (pt_restir_spatial.wgsl:170-171).  k_frame stores the 3 border rows of each owned
+    within -3..+4 px (pt_restir_spatial.wgsl:170-171; +4 because xorshift32 can return exactly 1.0).
+    k_primary stores the 4 top / 3 bottom border rows of each owned
     block straight into the neighbours' images over NVLink peer memory (CUDA IPC mappings) while it
     computes -- no staging copy, no separate exchange kernel;
   * a frame may only start when the neighbours' previous frame (and its halo stores) completed: the
