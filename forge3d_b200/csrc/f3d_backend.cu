@@ -14,7 +14,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/forge3d_b200.h"
@@ -49,10 +52,6 @@ static int fail(int cls, const char* fmt, ...) {
 // 350 ms render.  Freed blocks are parked per device and handed back to the next session that asks
 // for a similar size.  Buffers exported over CUDA IPC are never cached.
 // ------------------------------------------------------------------------------------------------
-#include <map>
-#include <mutex>
-#include <unordered_map>
-
 namespace {
 struct DevCache {
     std::mutex mu;

@@ -76,3 +76,19 @@ def test_gather_rows_gloo(world, height, block_rows):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(results) == [(r, True) for r in range(world)]
+
+
+def test_spatial_offsets_reach_plus_four_and_kernel_halo_covers_it():
+    """pt_restir_spatial.wgsl:199-200 draws floor(u*7)-3 with u = f32(x)/2^32.  u32 -> f32 rounds to nearest, so
+    x >= 0xFFFFFF80 gives u == 1.0 and the offset +4 (never -4): the multi-GPU halo must be 4 rows towards the
+    block above and 3 towards the block below.  Checked against the constants compiled into k_primary."""
+    import re
+    from pathlib import Path
+
+    x = np.array([0xFFFFFF7F, 0xFFFFFF80, 0xFFFFFFFF, 0, 1], dtype=np.uint32)
+    u = x.astype(np.float32) / np.float32(4294967296.0)
+    off = np.floor(u * np.float32(7.0)).astype(np.int64) - 3
+    assert list(off) == [3, 4, 4, -3, -3] and u[1] == np.float32(1.0)
+    src = (Path(__file__).resolve().parent.parent / "forge3d_b200" / "csrc" / "f3d_kernels.cuh").read_text()
+    assert re.search(r"in_y < 4u && b > 0u && P\.peer_up", src), "upward halo must be 4 rows"
+    assert re.search(r"in_y \+ 3u >= P\.block_rows && b \+ 1u < P\.nblocks && P\.peer_down", src), "downward halo must be 3 rows"
