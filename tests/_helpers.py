@@ -237,3 +237,73 @@ def brute_2d_hit(h: np.ndarray, rays: np.ndarray) -> np.ndarray:
         t[idx] = nxt + 1e-7
         alive[idx[t[idx] > ei]] = False
     return hit
+
+
+def _first_root_in_span(a, b, c, t0, t1):
+    """Smallest root of a t^2 + b t + c in [t0, t1] (f64, vectorised); NaN where there is none."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lin = np.abs(a) < 1e-18
+        rl = np.where(np.abs(b) > 0, -c / b, np.nan)
+        disc = b * b - 4 * a * c
+        sq = np.sqrt(np.maximum(disc, 0.0))
+        q = -0.5 * (b + np.copysign(sq, b))
+        r0 = np.where(disc >= 0, q / a, np.nan)
+        r1 = np.where((disc >= 0) & (np.abs(q) > 0), c / q, np.nan)
+    lo = np.fmin(r0, r1); hi = np.fmax(r0, r1)
+    in0 = (lo >= t0) & (lo <= t1); in1 = (hi >= t0) & (hi <= t1)
+    quad = np.where(in0, lo, np.where(in1, hi, np.nan))
+    linr = np.where((rl >= t0) & (rl <= t1), rl, np.nan)
+    return np.where(lin, linr, quad)
+
+
+def brute_first_hit_t(h: np.ndarray, rays: np.ndarray, spacing: float = PROOF_SPACING) -> np.ndarray:
+    """Independent f64 closest-hit distance of straight rays (no curvature) against the bilinear heightfield with
+    texel (0,0) at the world origin: cell-by-cell DDA + exact patch quadratic.  NaN = miss."""
+    r = rays.astype(np.float64)
+    o = r[:, 0:3]; d = r[:, 4:7]; tmin = r[:, 3]; tmax = r[:, 7]
+    hh, ww = h.shape
+    ex, ez = (ww - 1) * spacing, (hh - 1) * spacing
+    n = r.shape[0]
+
+    def axis(o_, d_, extent):
+        par = np.abs(d_) < 1e-300
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a = (0.0 - o_) / d_; b = (extent - o_) / d_
+        return (np.where(par, -np.inf, np.minimum(a, b)), np.where(par, np.inf, np.maximum(a, b)),
+                np.where(par, (o_ >= 0.0) & (o_ <= extent), True))
+
+    lx, hx, okx = axis(o[:, 0], d[:, 0], ex)
+    lz, hz, okz = axis(o[:, 2], d[:, 2], ez)
+    t = np.maximum(np.maximum(lx, lz), tmin)
+    end = np.minimum(np.minimum(hx, hz), tmax)
+    alive = okx & okz & (t <= end)
+    out = np.full(n, np.nan)
+    h64 = h.astype(np.float64)
+    for _ in range(4 * max(hh, ww)):
+        idx = np.nonzero(alive)[0]
+        if idx.size == 0:
+            break
+        ti, ei = t[idx], end[idx]
+        probe = np.minimum(ti + 1e-7 * np.maximum(1.0, np.abs(ti)), ei)
+        x = o[idx, 0] + probe * d[idx, 0]; z = o[idx, 2] + probe * d[idx, 2]
+        cx = np.clip(np.floor(x / spacing), 0, ww - 2).astype(np.int64)
+        cz = np.clip(np.floor(z / spacing), 0, hh - 2).astype(np.int64)
+        dx, dz = d[idx, 0], d[idx, 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            nx = np.where(dx > 0, ((cx + 1) * spacing - o[idx, 0]) / dx, np.where(dx < 0, (cx * spacing - o[idx, 0]) / dx, np.inf))
+            nz = np.where(dz > 0, ((cz + 1) * spacing - o[idx, 2]) / dz, np.where(dz < 0, (cz * spacing - o[idx, 2]) / dz, np.inf))
+        nxt = np.minimum(np.minimum(nx, nz), ei)
+        h00 = h64[cz, cx]; hx_ = h64[cz, cx + 1] - h00; hz_ = h64[cz + 1, cx] - h00
+        hxz = h64[cz + 1, cx + 1] - h00 - hx_ - hz_
+        u0 = o[idx, 0] / spacing - cx; v0 = o[idx, 2] / spacing - cz
+        du = dx / spacing; dv = dz / spacing
+        ta = hxz * du * dv
+        tb = hx_ * du + hz_ * dv + hxz * (u0 * dv + v0 * du)
+        tc = h00 + hx_ * u0 + hz_ * v0 + hxz * u0 * v0
+        root = _first_root_in_span(-ta, d[idx, 1] - tb, o[idx, 1] - tc, ti, nxt)
+        got = np.isfinite(root)
+        out[idx[got]] = root[got]
+        done = got | (nxt >= ei)
+        alive[idx[done]] = False
+        t[idx] = nxt
+    return out

@@ -50,6 +50,26 @@ def test_struct_layout_matches_c():
                     C.sizeof(O), O.kernel_launches.offset]
 
 
+def _build_c_consumer():
+    exe = Path("/tmp/f3d_abi_smoke")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I", str(ROOT / "include"), str(ROOT / "tests" / "c" / "abi_smoke.c"),
+                    "-o", str(exe), "-L", str(ROOT / "forge3d_b200"), "-lforge3d_b200",
+                    f"-Wl,-rpath,{ROOT / 'forge3d_b200'}"], check=True)
+    return exe
+
+
+def test_plain_c_consumer_links_and_fails_loudly_without_gpu():
+    """The boundary is a real C ABI: a C99 program links libforge3d_b200.so with nothing but the header."""
+    fbuild.build()
+    exe = _build_c_consumer()
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    if _native.lib().f3d_device_count() > 0:
+        assert res.returncode == 0 and "frames=4" in res.stdout, res.stdout + res.stderr
+    else:
+        assert res.returncode == 3, (res.returncode, res.stdout, res.stderr)       # F3D_ERR_DEVICE
+        assert "no CUDA device" in res.stdout and "no CPU fallback" in res.stdout
+
+
 def test_no_gpu_fails_loudly():
     L = _native.lib()
     if L.f3d_device_count() > 0:

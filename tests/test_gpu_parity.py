@@ -150,6 +150,15 @@ def test_native_seam_error_paths_on_gpu():
     assert ok["frames"] == 4
 
 
+def test_plain_c_consumer_renders_on_gpu():
+    import subprocess
+
+    from test_abi import _build_c_consumer
+
+    res = subprocess.run([str(_build_c_consumer())], capture_output=True, text=True)
+    assert res.returncode == 0 and "frames=4" in res.stdout and "alpha=255" in res.stdout, res.stdout + res.stderr
+
+
 def test_session_api_matches_one_call_path():
     from forge3d_b200.session import Session
 
