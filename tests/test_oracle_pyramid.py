@@ -114,3 +114,30 @@ def test_pinned_elementary_functions():
         assert L.f3do_f32_to_f16(float(v)) == int(np.float16(v).view(np.uint16)), v
     for hbits in range(0, 0x7C00, 37):
         assert L.f3do_f16_to_f32(hbits) == float(np.uint16(hbits).view(np.float16))
+
+
+def test_oracle_build_has_no_fma_contraction():
+    """The numerics contract forbids FMA contraction; the oracle is compiled with -ffp-contract=off.  Check the
+    machine code: no fused multiply-add instruction may appear in the shared object."""
+    import shutil
+    import subprocess
+
+    if shutil.which("objdump") is None:
+        import pytest
+
+        pytest.skip("objdump not available")
+    path = oracle.build()
+    asm = subprocess.run(["objdump", "-d", str(path)], capture_output=True, text=True, check=True).stdout
+    fused = [l for l in asm.splitlines() if any(m in l for m in ("vfmadd", "vfmsub", "vfnmadd", "vfnmsub"))]
+    assert not fused, fused[:5]
+    flags = (path.parent / "Makefile").read_text()
+    assert "-ffp-contract=off" in flags and "-ffast-math" not in flags.replace("-fno-fast-math", "")
+
+
+def test_cuda_build_flags_pin_the_numerics_contract():
+    from forge3d_b200 import build as fbuild
+
+    flags = " ".join(fbuild.NVCC_FLAGS)
+    for needed in ("-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "arch=compute_100a,code=sm_100a", "-lineinfo"):
+        assert needed in flags
+    assert "--use_fast_math" not in flags and "-use_fast_math" not in flags

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage (under gpurun): bash tools_gpu_check.sh <tag> -- parity tests, bench line, per-kernel ncu durations
+# developer helper, usage (under gpurun, from the repo root): bash tools/gpu_check.sh <tag> -- parity tests, bench line, per-kernel ncu durations
 TAG=${1:-x}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
