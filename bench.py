@@ -3,8 +3,8 @@
 
 Workload (BASELINE.json configs[1]): the Rainier-shaped closed-form 2048x2048
 DEM, 1920x1080 image, spp=1 per accumulation frame; 256 frames = the "256 spp" snapshot.
-A STEP is one accumulation frame = one pass of the hot path (one k_frame launch: spatial reuse +
-primary / sun-shadow / IBL rays + temporal reuse + accumulate + Welford) over the whole image.
+A STEP is one accumulation frame = one pass of the hot path (k_primary -> k_trace -> k_accum: spatial reuse,
+primary / sun-shadow / IBL rays, temporal reuse, accumulate, Welford) over the whole image.
 `--steps 256` (the default) therefore times exactly the 1920x1080x256spp render.
 
   value      Mrays/s with the scene resident in HBM (CUDA events around the K timed frames)
