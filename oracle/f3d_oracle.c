@@ -1201,6 +1201,21 @@ int f3do_render(const f3do_desc* d, f3do_out* out) {
             }
             if (r->m > 0 && r->weight > 0.0f && r->target_pdf > 0.0f) any_valid = 1;
         }
+        out->prev_m_max = 0; out->prev_weight_max = 0.0f; out->prev_w_sum_max = 0.0f;
+        for (int a = 0; a < 3; a++) { out->prev_dir_min[a] = INFINITY; out->prev_dir_max[a] = -INFINITY; }
+        for (size_t i = 0; i < npx; i++) {
+            const reservoir* r = &B.prev[i];
+            if (r->m > out->prev_m_max) out->prev_m_max = r->m;
+            if (r->weight > out->prev_weight_max) out->prev_weight_max = r->weight;
+            if (r->w_sum > out->prev_w_sum_max) out->prev_w_sum_max = r->w_sum;
+            if (r->m > 0 && r->weight > 0.0f && r->target_pdf > 0.0f) {
+                const float dv[3] = {r->direction.x, r->direction.y, r->direction.z};
+                for (int a = 0; a < 3; a++) {
+                    if (dv[a] < out->prev_dir_min[a]) out->prev_dir_min[a] = dv[a];
+                    if (dv[a] > out->prev_dir_max[a]) out->prev_dir_max[a] = dv[a];
+                }
+            }
+        }
         int require = d->sun_el_deg > 0.0f && sun_intensity > 0.0f &&
                       (sun_color[0] > 0.0f || sun_color[1] > 0.0f || sun_color[2] > 0.0f);
         if (require && !any_valid) {

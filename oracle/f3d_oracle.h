@@ -70,6 +70,11 @@ typedef struct f3do_out {
     uint64_t nodes_popped;   /* terrain_trace stack pops inside the frame loop */
     double setup_seconds;    /* validation + pyramid build + G-buffer pass (wall clock) */
     double frames_seconds;   /* the accumulation loop incl. convergence checks (wall clock) */
+    /* diagnostics of the merged reservoirs after the last reuse pass (render_terrain.rs:1313-1337,
+     * runtime contract :175-232) */
+    uint32_t prev_m_max;
+    float prev_weight_max, prev_w_sum_max;
+    float prev_dir_min[3], prev_dir_max[3];   /* over valid reservoirs */
 } f3do_out;
 
 /* 0 = ok; otherwise an error class (1 render, 2 upload); message via f3do_last_error(). */

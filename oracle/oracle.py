@@ -56,6 +56,8 @@ class _Out(C.Structure):
         ("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_ibl", C.c_uint64),
         ("nodes_popped", C.c_uint64),
         ("setup_seconds", C.c_double), ("frames_seconds", C.c_double),
+        ("prev_m_max", C.c_uint32), ("prev_weight_max", C.c_float), ("prev_w_sum_max", C.c_float),
+        ("prev_dir_min", C.c_float * 3), ("prev_dir_max", C.c_float * 3),
     ]
 
 
@@ -202,6 +204,8 @@ def render(heightmap, width, height, cam=None, *, spacing=(1.0, 1.0), exaggerati
                rays_primary=int(o.rays_primary), rays_shadow=int(o.rays_shadow),
                rays_ibl=int(o.rays_ibl), nodes_popped=int(o.nodes_popped),
                setup_seconds=float(o.setup_seconds), frames_seconds=float(o.frames_seconds),
+               prev_m_max=int(o.prev_m_max), prev_weight_max=float(o.prev_weight_max),
+               prev_w_sum_max=float(o.prev_w_sum_max), prev_dir_min=tuple(o.prev_dir_min), prev_dir_max=tuple(o.prev_dir_max),
                sun_source="manual_angles", solar_azimuth_deg=float(sun_azimuth_deg),
                solar_elevation_deg=float(sun_elevation_deg))
     if acc is not None:

@@ -132,14 +132,22 @@ def test_seed_only_perturbs_spatial_pass():
 
 
 def test_contract_fixture_ranges():
-    # tests/test_shader_proofs.py:101-128 + render_terrain.rs:56-230: 8x8 image of a 4x4 zero DEM,
-    # camera (0,3,8), 4 frames: accumulations stay finite and inside the recorded value ranges.
-    out = oracle.render(np.zeros((4, 4), np.float32), 8, 8, {"origin": (0.0, 3.0, 8.0), "look_at": (0.0, 0.0, 0.0)},
-                        max_frames=4, min_frames=4, variance_threshold=1e30, want_accum=True)
+    # tests/test_shader_proofs.py:101-128 + the runtime contract render_terrain.rs:56-230 /
+    # shaders/contracts/hybrid_terrain_traversal.toml: 8x8 image of a 4x4 zero DEM, camera (0,3,8), 4 frames.
+    # The reference asserts that the observed values of that run lie inside these ranges.
+    cam = {"origin": (0.0, 3.0, 8.0), "look_at": (0.0, 0.0, 0.0), "up": (0.0, 1.0, 0.0), "fov_y": 45.0, "exposure": 1.0}
+    out = oracle.render(np.zeros((4, 4), np.float32), 8, 8, cam, sun_intensity=2.5, max_frames=4, min_frames=2,
+                        variance_threshold=1e30, want_accum=True)
     acc = out["accum"]
-    assert np.isfinite(acc).all() and (acc[..., 3] == 4.0).all()
-    assert acc[..., :3].min() >= 0.0 and acc[..., :3].max() <= 131026.0
-    assert out["frames"] == 4
+    assert out["frames"] == 4 and np.isfinite(acc).all() and (acc[..., 3] == 4.0).all()
+    assert acc[..., :3].min() >= 0.0 and acc[..., :3].max() <= 131026.0            # accum_hdr.samples
+    assert 0 < out["prev_m_max"] <= 512                                            # terrain_reservoirs_prev.m
+    assert 0.0 <= out["prev_weight_max"] <= 65536.0 and 0.0 <= out["prev_w_sum_max"] <= 65536.0
+    lo, hi = out["prev_dir_min"], out["prev_dir_max"]                             # ...prev.direction.{x,y,z}
+    assert 0.49 <= lo[0] <= hi[0] <= 0.51 and 0.70 <= lo[1] <= hi[1] <= 0.72 and -0.51 <= lo[2] <= hi[2] <= -0.49
+    rgb = out["rgba"][..., :3].astype(np.float32) / 255.0
+    assert rgb.min() >= 0.0 and rgb.max() <= 1.0                                   # out_tex.samples
+    assert out["minmax_pyramid_bytes"] == 4 * 4 * 4 + (16 + 4 + 1) * 8             # 4x4 DEM, 3 mips (terrain.mips.x = 3)
 
 
 def test_mixed_scene_mesh_and_terrain():
