@@ -150,6 +150,25 @@ def test_native_seam_error_paths_on_gpu():
     assert ok["frames"] == 4
 
 
+def test_curved_and_flat_earth_models_share_the_memory_footprint():
+    # reference: tests/test_shadow_tip.py:248-430 (HELIOS memory gate): the curved-earth shadow policy must not
+    # cost memory relative to the flat baseline; both models render the same workload.
+    from PIL import Image  # noqa: F401  (same environment as the golden tests)
+
+    dem = H.golden_dem()[::2, ::2].copy()
+    spacing = 100.0 / (dem.shape[1] - 1)
+    kw = dict(spacing=(spacing, spacing), exaggeration=20.0, albedo=H.ALBEDO, sun_azimuth_deg=225.0, sun_elevation_deg=35.0,
+              observer_latitude_deg=46.5, observer_longitude_deg=7.5, spp=1, min_frames=32, max_frames=32,
+              variance_threshold=1e9, seed=7)
+    res = {}
+    for mode, (earth, refr) in {"flat_baseline": ("flat", "none"), "helios": ("ellipsoid", "effective_radius")}.items():
+        got, ref = _both(dem, 64, 64, H.CAM, **kw, earth_model=earth, refraction_model=refr)
+        _assert_same_render(got, ref, mode)
+        res[mode] = got
+    for key in ("peak_host_visible_bytes", "gpu_resource_bytes", "minmax_pyramid_bytes"):
+        assert res["flat_baseline"][key] == res["helios"][key] > 0
+
+
 def test_plain_c_consumer_renders_on_gpu():
     import subprocess
 
