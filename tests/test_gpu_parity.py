@@ -153,8 +153,6 @@ def test_native_seam_error_paths_on_gpu():
 def test_curved_and_flat_earth_models_share_the_memory_footprint():
     # reference: tests/test_shadow_tip.py:248-430 (HELIOS memory gate): the curved-earth shadow policy must not
     # cost memory relative to the flat baseline; both models render the same workload.
-    from PIL import Image  # noqa: F401  (same environment as the golden tests)
-
     dem = H.golden_dem()[::2, ::2].copy()
     spacing = 100.0 / (dem.shape[1] - 1)
     kw = dict(spacing=(spacing, spacing), exaggeration=20.0, albedo=H.ALBEDO, sun_azimuth_deg=225.0, sun_elevation_deg=35.0,
