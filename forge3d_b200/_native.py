@@ -66,7 +66,7 @@ class TerrainOut(C.Structure):
 EXPORTS = [
     "f3d_terrain_reference_render", "f3d_last_error", "f3d_abi_version", "f3d_device_count",
     "f3d_session_create", "f3d_session_render_frames", "f3d_session_variance",
-    "f3d_session_resolve_device", "f3d_session_resolve_host", "f3d_session_frames",
+    "f3d_session_resolve_device", "f3d_session_validity", "f3d_session_resolve_host", "f3d_session_frames",
     "f3d_session_stats", "f3d_session_sync", "f3d_session_last_frames_ms", "f3d_session_destroy",
     "f3d_session_ipc_export", "f3d_session_ipc_import", "f3d_trace_rays", "f3d_build_minmax",
 ]
@@ -91,6 +91,7 @@ def lib():
     L.f3d_session_render_frames.argtypes = [vp, C.c_uint32]
     L.f3d_session_variance.argtypes = [vp, fp, C.POINTER(C.c_int32)]
     L.f3d_session_resolve_device.argtypes = [vp, vp, vp, vp, vp, C.c_int32]
+    L.f3d_session_validity.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.f3d_session_resolve_host.argtypes = [vp, C.POINTER(TerrainOut)]
     L.f3d_session_frames.argtypes = [vp, u32p]
     L.f3d_session_stats.argtypes = [vp, C.POINTER(TerrainOut)]

@@ -891,6 +891,15 @@ static int resolve_device_impl(f3d_session* s, void* d_rgba, void* d_albedo, voi
     return 0;
 }
 
+extern "C" int f3d_session_validity(const f3d_session* s, int32_t* any_valid, int32_t* required) {
+    if (!s) return fail(F3D_ERR_ARGUMENT, "null session");
+    if (any_valid) *any_valid = s->h_gate[3] != 0;
+    if (required)
+        *required = s->sun_el_deg > 0.0f && s->sun_intensity > 0.0f &&
+                    (s->sun_color[0] > 0.0f || s->sun_color[1] > 0.0f || s->sun_color[2] > 0.0f);
+    return 0;
+}
+
 extern "C" int f3d_session_resolve_device(f3d_session* s, void* d_rgba, void* d_albedo, void* d_normal, void* d_depth,
                                           int32_t check_validity) {
     if (!s) return fail(F3D_ERR_ARGUMENT, "null session");

@@ -88,6 +88,25 @@ def gather_rows(local_image, height: int, group=None, block_rows: int = 0):
     return assemble([out[r * mx:(r + 1) * mx] for r in range(world)], height, world, block_rows)
 
 
+NO_VALID_RESERVOIRS = ("terrain PT ReSTIR reuse chain produced no valid reservoirs for a sun-lit scene "
+                       "\u2014 temporal/spatial reuse is broken")
+
+
+def check_validity_across_ranks(any_valid: bool, required: bool, group=None, device="cpu") -> None:
+    """The reference's end-of-render reservoir check (render_terrain.rs:1313-1337) for a row partition: a rank
+    may legitimately own only sky, so the per-rank flags are OR-reduced (one MAX all-reduce of one int32) and
+    every rank raises the reference's error together when the scene is sun-lit and no rank holds a valid
+    reservoir.  Works over NCCL (device="cuda") and gloo (device="cpu")."""
+    import torch
+    import torch.distributed as dist
+
+    flag = torch.tensor([1 if any_valid else 0], dtype=torch.int32, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if required and int(flag.item()) == 0:
+        raise RuntimeError(NO_VALID_RESERVOIRS)
+
+
 class PartitionedRender:
     """One rank's share of a partitioned render (CUDA + NCCL)."""
 
@@ -143,6 +162,8 @@ class PartitionedRender:
         self.session.resolve_device(rgba.data_ptr(), bufs["albedo"].data_ptr() if aovs else 0,
                                     bufs["normal"].data_ptr() if aovs else 0,
                                     bufs["depth"].data_ptr() if aovs else 0, check_validity=True)
+        if self.world > 1:   # world == 1: the session itself raised
+            check_validity_across_ranks(*self.session.validity(), group=self.group, device="cuda")
         out = {}
         for k, t in bufs.items():
             full = gather_rows(t, H, self.group, self.block_rows) if self.world > 1 else t

@@ -69,6 +69,12 @@ class Session:
         _native.check(self._L.f3d_session_resolve_device(self._h, p(rgba), p(albedo), p(normal), p(depth),
                                                          int(bool(check_validity))))
 
+    def validity(self):
+        """(any_valid, required) of the last resolve_device(check_validity=True): see f3d_session_validity."""
+        any_valid, required = C.c_int32(), C.c_int32()
+        _native.check(self._L.f3d_session_validity(self._h, C.byref(any_valid), C.byref(required)))
+        return bool(any_valid.value), bool(required.value)
+
     def resolve_host(self, want_accum=False) -> dict:
         o, arrays = _native.alloc_outputs(self.width, self.height, want_accum)
         _native.check(self._L.f3d_session_resolve_host(self._h, C.byref(o)))

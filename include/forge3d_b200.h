@@ -121,6 +121,12 @@ int f3d_session_variance(f3d_session* s, float* vmax, int32_t* nonfinite);
  * except that validity is checked (synchronises) when check_validity != 0. */
 int f3d_session_resolve_device(f3d_session* s, void* d_rgba, void* d_albedo, void* d_normal, void* d_depth,
                                int32_t check_validity);
+/* Reservoir validity seen by the last f3d_session_resolve_device(check_validity != 0) call, for launchers that
+ * partition the image: *required != 0 when the scene is sun-lit (render_terrain.rs:465-471), *any_valid != 0
+ * when an owned pixel holds a valid reservoir (:1313-1337).  A partitioned session never raises the
+ * "no valid reservoirs" error itself (a rank may own only sky); the launcher ORs any_valid over ranks and
+ * raises when required && !any.  No device work. */
+int f3d_session_validity(const f3d_session* s, int32_t* any_valid, int32_t* required);
 /* Same, then copies to host buffers of `out` and fills the scalar fields. */
 int f3d_session_resolve_host(f3d_session* s, f3d_terrain_out* out);
 int f3d_session_frames(const f3d_session* s, uint32_t* frames);

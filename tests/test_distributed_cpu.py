@@ -92,3 +92,52 @@ def test_spatial_offsets_reach_plus_four_and_kernel_halo_covers_it():
     src = (Path(__file__).resolve().parent.parent / "forge3d_b200" / "csrc" / "f3d_kernels.cuh").read_text()
     assert re.search(r"in_y < 4u && b > 0u && P\.peer_up", src), "upward halo must be 4 rows"
     assert re.search(r"in_y \+ 3u >= P\.block_rows && b \+ 1u < P\.nblocks && P\.peer_down", src), "downward halo must be 3 rows"
+
+
+def _validity_worker(rank, world, port, flags, required, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        try:
+            D.check_validity_across_ranks(flags[rank], required)
+            q.put((rank, "ok"))
+        except RuntimeError as exc:
+            q.put((rank, str(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("flags,required,raises", [
+    ((False, True), True, False),     # rank 0 owns only sky: fine, rank 1 has valid reservoirs
+    ((False, False), True, True),     # sun-lit scene and nobody has one: every rank raises the reference's error
+    ((False, False), False, False),   # sun off / below horizon: the check does not apply
+])
+def test_reservoir_validity_is_or_reduced_over_ranks_gloo(flags, required, raises):
+    """render_terrain.rs:1313-1337 under a row partition: OR over ranks, same error text."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_validity_worker, args=(r, 2, port, flags, required, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in range(2):
+        if raises:
+            assert "produced no valid reservoirs for a sun-lit scene" in results[rank]
+        else:
+            assert results[rank] == "ok"
+
+
+def test_validity_check_without_a_process_group_is_the_single_rank_rule():
+    D.check_validity_across_ranks(True, True)
+    D.check_validity_across_ranks(False, False)
+    with pytest.raises(RuntimeError, match="no valid reservoirs"):
+        D.check_validity_across_ranks(False, True)

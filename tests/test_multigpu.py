@@ -104,3 +104,61 @@ def test_plus4_offset_needs_a_four_row_halo():
         assert p.exitcode == 0
     assert np.array_equal(got["rgba"], ref["rgba"])
     assert np.float32(got["variance"]) == np.float32(ref["variance"])
+
+
+def _validity_worker(rank, world, port, cam, height, q):
+    import torch
+    import torch.distributed as dist
+
+    from forge3d_b200.distributed import PartitionedRender
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        dem = H.golden_dem()
+        kw = {**H.scene_kwargs(dem), "max_frames": 4, "min_frames": 4, "variance_threshold": 1e30}
+        pr = PartitionedRender(dem, 64, height, cam, block_rows=16, **kw)
+        pr.render_frames(4)
+        try:
+            out = pr.resolve(aovs=True)
+            q.put((rank, "ok", int(np.isfinite(out["depth"][:16]).sum()), int(np.isfinite(out["depth"][16:]).sum())))
+        except RuntimeError as exc:
+            q.put((rank, str(exc), 0, 0))
+        pr.close()
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["rank0_owns_only_sky", "all_sky"])
+def test_reservoir_validity_is_checked_across_ranks(case):
+    """render_terrain.rs:1313-1337 under the row partition: a rank that owns only sky rows must not fail the
+    render, and a sun-lit render in which NO rank holds a valid reservoir raises the reference's error on every rank."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    ox, oy, oz = H.CAM["origin"]
+    if case == "all_sky":
+        cam = {**H.CAM, "look_at": (ox, oy + 100.0, oz - 1.0)}       # straight up
+    else:
+        cam = {**H.CAM, "look_at": (0.0, oy, 0.0), "fov_y": 70.0}     # level view: horizon at mid-height
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_validity_worker, args=(r, 2, port, cam, 32, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, status, top_hits, bottom_hits in results:
+        if case == "all_sky":
+            assert "produced no valid reservoirs for a sun-lit scene" in status
+        else:
+            assert status == "ok" and top_hits == 0 and bottom_hits > 0, (status, top_hits, bottom_hits)
