@@ -1,0 +1,59 @@
+"""Builds and loads tests/c/emu/trace_emu.cpp: the product's DEVICE traversal headers compiled with g++ and run on the
+CPU as a one-lane warp (see tests/c/emu/cuda_runtime.h).  Test infrastructure."""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+EMU = ROOT / "tests" / "c" / "emu"
+CSRC = ROOT / "forge3d_b200" / "csrc"
+BUILD = EMU / "_build"
+
+
+def build(defines=()) -> Path:
+    tag = hashlib.sha1(" ".join(sorted(defines)).encode()).hexdigest()[:10]
+    out = BUILD / f"libtrace_emu_{tag}.so"
+    deps = [EMU / "trace_emu.cpp", EMU / "cuda_runtime.h"] + sorted(CSRC.glob("f3d_*.cuh"))
+    if out.exists() and out.stat().st_mtime >= max(p.stat().st_mtime for p in deps):
+        return out
+    BUILD.mkdir(exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", f"-I{EMU}", f"-I{CSRC}",
+           *[f"-D{d}" for d in defines], "-o", str(out), str(EMU / "trace_emu.cpp")]
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError(f"g++ failed:\n{' '.join(cmd)}\n{res.stdout}")
+    return out
+
+
+def trace_rays(heights, spacing, origin_xz, exaggeration, rays, *, any_hit, apply_curvature, inv_two_r_prime=0.0,
+               curvature_enabled=False, defines=()):
+    """Same contract as oracle.trace_rays / _native.trace_rays; returns (hit, t, normal, nodes_popped)."""
+    L = C.CDLL(str(build(defines)))
+    fp = C.POINTER(C.c_float)
+    L.emu_trace_rays.argtypes = [fp, C.c_uint32, C.c_uint32, fp, fp, C.c_float, C.c_float, C.c_int32, fp, C.c_uint64,
+                                 C.c_int32, C.c_int32, C.POINTER(C.c_uint8), fp, fp, C.POINTER(C.c_uint64)]
+    dem = np.ascontiguousarray(heights, np.float32)
+    r = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    n = r.shape[0]
+    hit = np.zeros(n, np.uint8)
+    t = np.zeros(n, np.float32)
+    nrm = np.zeros((n, 3), np.float32)
+    nodes = C.c_uint64()
+    f = lambda a: a.ctypes.data_as(fp)
+    sp = (C.c_float * 2)(*map(float, spacing))
+    og = (C.c_float * 2)(*map(float, origin_xz))
+    rc = L.emu_trace_rays(f(dem), dem.shape[1], dem.shape[0], sp, og, float(exaggeration), float(inv_two_r_prime),
+                          int(bool(curvature_enabled)), f(r), n, int(bool(any_hit)), int(bool(apply_curvature)),
+                          hit.ctypes.data_as(C.POINTER(C.c_uint8)), f(t), f(nrm), C.byref(nodes))
+    if rc != 0:
+        raise RuntimeError(f"emu_trace_rays failed ({rc})")
+    return hit.astype(bool), t, nrm, int(nodes.value)
