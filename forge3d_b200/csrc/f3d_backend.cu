@@ -193,6 +193,8 @@ static int validate_desc(const f3d_terrain_desc* d) {
         for (size_t i = 0; i < (size_t)d->env_w * d->env_h * 3; i++)
             if (!isfinite(d->env_rgb[i])) return fail(F3D_ERR_UPLOAD, "env map contains non-finite samples");
     }
+    if ((uint64_t)d->width * d->height > (1ull << 31))   // kernels index pixels with 32-bit integers
+        return fail(F3D_ERR_ARGUMENT, "image of %ux%u pixels exceeds the 2^31-pixel addressing limit", d->width, d->height);
     if (d->part_world > 1 && d->part_rank >= d->part_world)
         return fail(F3D_ERR_ARGUMENT, "part_rank (%u) must be < part_world (%u)", d->part_rank, d->part_world);
     return 0;
@@ -368,6 +370,10 @@ static int build_device_terrain(const float* h_heights, uint32_t w, uint32_t h, 
     uint32_t* d_flag = nullptr;
     const size_t n = (size_t)w * h;
     CUDA_TRY(cudaGetDevice(&T->device));
+    struct Scratch {   // upload staging + finite flag: released on every return path, after the stream drained
+        float*& h; uint32_t*& f; cudaStream_t st; int dev;
+        ~Scratch() { if (h || f) cudaStreamSynchronize(st); cached_free(h, dev); cached_free(f, dev); }
+    } scratch{d_h, d_flag, stream, T->device};
     CUDA_TRY(cached_malloc((void**)&d_h, n * sizeof(float), T->device));
     CUDA_TRY(cached_malloc((void**)&d_flag, sizeof(uint32_t), T->device));
     CUDA_TRY(cached_malloc((void**)&T->cells, (size_t)cw * ch * sizeof(float4), T->device));
@@ -405,8 +411,6 @@ static int build_device_terrain(const float* h_heights, uint32_t w, uint32_t h, 
     CUDA_TRY(cudaMemcpyAsync(&T->root_mm, T->mm_base + T->level_off[T->nlevels - 1], sizeof(float2), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     CUDA_TRY(cudaGetLastError());
-    cached_free(d_h, T->device);
-    cached_free(d_flag, T->device);
     if (flag) return fail(F3D_ERR_UPLOAD, "terrain heightfield contains non-finite samples");
     if (!keep_plain) T->release_plain();
     T->bytes = (uint64_t)cw * ch * sizeof(float4) + T->quad_total * sizeof(float2) +
@@ -511,7 +515,11 @@ static void session_free(f3d_session* s) {
     cudaSetDevice(s->device);
     for (int i = 0; i < s->n_peer_ptrs; i++)
         if (s->peer_ptrs[i]) cudaIpcCloseMemHandle(s->peer_ptrs[i]);
-    if (s->stream) cudaStreamSynchronize(s->stream);      // nothing may still touch buffers that get parked
+    // nothing may still touch buffers that get parked (render_frames joins the slot streams into the session
+    // stream, but an error return in the middle of it does not)
+    for (auto& sl : s->slots)
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+    if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->d_sync) cudaFree(s->d_sync);
     const int dv = s->device;
     const bool ipc = s->P.part_world > 1u;                  // resv images may be mapped by peers: never park them

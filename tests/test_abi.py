@@ -81,6 +81,20 @@ def test_no_gpu_fails_loudly():
                            any_hit=True, apply_curvature=False)
 
 
+def test_native_validation_runs_before_any_device_work():
+    # the trust-boundary checks of validate_desc (render_terrain.rs:474-557) need no GPU, so they are testable here;
+    # the 2^31-pixel limit is this backend's own (32-bit pixel indices in the kernels)
+    dem = np.zeros((4, 4), np.float32)
+    with pytest.raises(ValueError, match="2\\^31-pixel addressing limit"):
+        _native.hybrid_render_terrain_reference(dem, 65536, 65536, {}, max_frames=2, min_frames=2)
+    with pytest.raises(RuntimeError, match="spp must be in 1..=64"):
+        _native.hybrid_render_terrain_reference(dem, 8, 8, {}, spp=65, max_frames=2, min_frames=2)
+    with pytest.raises(RuntimeError, match="min_frames .* must be <= max_frames"):
+        _native.hybrid_render_terrain_reference(dem, 8, 8, {}, max_frames=2, min_frames=3)
+    with pytest.raises(RuntimeError, match="camera look_at must differ from origin"):
+        _native.hybrid_render_terrain_reference(dem, 8, 8, {"origin": (0, 1, 0), "look_at": (0, 1, 0)}, max_frames=2, min_frames=2)
+
+
 def test_product_never_touches_the_oracle():
     for path in (ROOT / "forge3d_b200").rglob("*"):
         if path.suffix in (".py", ".cu", ".cuh", ".cpp", ".h"):
