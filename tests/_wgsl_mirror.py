@@ -291,6 +291,144 @@ class Scene:
         return hit, best_t, point, normal
 
 
+def atan_pos(x):                                       # numerics contract: Cephes atanf
+    if x > f(2.414213562373095):
+        y, x = f(1.5707963267948966), -(ONE / x)
+    elif x > f(0.4142135623730950):
+        y, x = f(0.7853981633974483), (x - ONE) / (x + ONE)
+    else:
+        y = ZERO
+    z = x * x
+    return y + ((((f(8.05374449538e-2) * z - f(1.38776856032e-1)) * z + f(1.99777106478e-1)) * z
+                 - f(3.33329491539e-1)) * z * x + x)
+
+
+def atan2_pinned(y, x):
+    pi, half_pi = f(3.14159265358979323846), f(1.5707963267948966)
+    if x == ZERO:
+        return half_pi if y > ZERO else (-half_pi if y < ZERO else ZERO)
+    q = y / x
+    a = atan_pos(abs(q))
+    if q < ZERO:
+        a = -a
+    if x < ZERO:
+        a = a + pi if y >= ZERO else a - pi
+    return a
+
+
+def asin_core(x):
+    a = abs(x)
+    if a > f(0.5):
+        z = f(0.5) * (ONE - a)
+        w, flag = np.sqrt(z), True
+    else:
+        w, flag = a, False
+        z = w * w
+    p = ((((f(4.2163199048e-2) * z + f(2.4181311049e-2)) * z + f(4.5470025998e-2)) * z
+          + f(7.4953002686e-2)) * z + f(1.6666752422e-1)) * z * w + w
+    if flag:
+        p = p + p
+        p = f(1.5707963267948966) - p
+    return -p if x < ZERO else p
+
+
+def acos_pinned(x):
+    if x < f(-0.5):
+        return f(3.14159265358979323846) - f(2.0) * asin_core(np.sqrt(f(0.5) * (ONE + x)))
+    if x > f(0.5):
+        return f(2.0) * asin_core(np.sqrt(f(0.5) * (ONE - x)))
+    return f(1.5707963267948966) - asin_core(x)
+
+
+class Hybrid:
+    """intersect_hybrid / intersect_hybrid_optimized / get_surface_properties / terrain_env_radiance
+    (hybrid_traversal.wgsl:84-259, hybrid_terrain_traversal.wgsl:384-402) over a Scene plus an optional triangle mesh
+    and equirect environment map."""
+
+    MESH_ALBEDO = (f(0.7), f(0.7), f(0.8))
+
+    def __init__(self, scene, mesh_vertices=None, mesh_indices=None, env_map=None):
+        self.S = scene
+        self.verts = None if mesh_vertices is None else np.asarray(mesh_vertices, np.float32)
+        self.tris = None if mesh_indices is None else np.asarray(mesh_indices, np.uint32).reshape(-1, 3)
+        self.env = None if env_map is None else np.asarray(env_map, np.float32)
+
+    def ray_triangle(self, o, d, tmin, tmax, v0, v1, v2):          # hybrid_traversal.wgsl:84-131
+        e1 = tuple(v1[i] - v0[i] for i in range(3))
+        e2 = tuple(v2[i] - v0[i] for i in range(3))
+        h = cross(d, e2)
+        a = dot3(e1, h)
+        if abs(a) < f(1e-7):
+            return None
+        inv = ONE / a
+        s = tuple(o[i] - v0[i] for i in range(3))
+        u = inv * dot3(s, h)
+        if u < ZERO or u > ONE:
+            return None
+        q = cross(s, e1)
+        v = inv * dot3(d, q)
+        if v < ZERO or u + v > ONE:
+            return None
+        t = inv * dot3(e2, q)
+        if tmin < t < tmax:
+            return t, normalize(cross(e1, e2))
+        return None
+
+    def intersect_mesh(self, o, d, tmin, tmax):                     # :136-172, index-order sweep
+        best_t, best = tmax, None
+        if self.tris is None:
+            return None
+        for tri in self.tris:
+            v = [tuple(f(c) for c in self.verts[int(i)]) for i in tri]
+            r = self.ray_triangle(o, d, tmin, tmax, *v)
+            if r is not None and r[0] < best_t:
+                best_t, best = r[0], r
+        if best is None:
+            return None
+        t, n = best
+        return t, tuple(o[i] + d[i] * t for i in range(3)), n
+
+    def closest(self, o, d, tmin, tmax):                            # intersect_hybrid :175-201
+        """-> (hit, t, point, normal, hit_type) with hit_type 0 = mesh, 3 = terrain."""
+        best = (False, tmax, None, None, 3)
+        m = self.intersect_mesh(o, d, tmin, tmax)
+        if m is not None and m[0] < best[1]:
+            best = (True, m[0], m[1], m[2], 0)
+        hit, t, p, n = self.S.trace(o, d, tmin, best[1], False, False)
+        if hit and t < best[1]:
+            best = (True, t, p, n, 3)
+        return best
+
+    def occluded(self, o, d, tmin, tmax, apply_curvature):          # intersect_hybrid_optimized :204-233 + :248-259
+        best_t = tmax
+        m = self.intersect_mesh(o, d, tmin, tmax)
+        if m is not None:
+            if m[0] < f(0.01):
+                return m[0] < f(1e30)
+            if m[0] < best_t:
+                best_t = m[0]
+        hit, t, *_ = self.S.trace(o, d, tmin, best_t, True, apply_curvature)
+        if hit and t < best_t:
+            best_t = t
+            return best_t < f(1e30)
+        return m is not None and best_t < f(1e30)
+
+    def surface_albedo(self, hit_type):                             # get_surface_properties :238-245
+        return self.S.albedo if hit_type == 3 else self.MESH_ALBEDO
+
+    def env_radiance(self, d):                                      # terrain_env_radiance :384-402
+        if self.env is None:
+            return (self.S.env, self.S.env, self.S.env)
+        eh, ew = self.env.shape[:2]
+        d = normalize(d)
+        pi = f(3.14159265358979323846)
+        uu = (atan2_pinned(d[2], d[0]) / (f(2.0) * pi)) + f(0.5)
+        vv = acos_pinned(clamp(d[1], f(-1.0), ONE)) / pi
+        px = min(int(uu * f(ew)), ew - 1)
+        py = min(int(vv * f(eh)), eh - 1)
+        return tuple(f(self.env[py, px, c]) * self.S.env for c in range(3))
+
+
 def cosine_dir(n, u1, u2):                            # :421-431
     sign = f(-1.0) if n[2] < ZERO else ONE
     a = f(-1.0) / (sign + n[2])
@@ -306,9 +444,12 @@ def cosine_dir(n, u1, u2):                            # :421-431
 
 
 def render(dem, width, height, cam, *, spacing, exaggeration, albedo, sun_azimuth_deg, sun_elevation_deg,
-           sun_intensity, sun_color, env_intensity, spp, frames, seed, inv_two_r_prime, curvature_enabled):
-    """Fixed-frame render; returns (accum[H,W,4] float32, depth[H,W] float32 with NaN on miss)."""
+           sun_intensity, sun_color, env_intensity, spp, frames, seed, inv_two_r_prime, curvature_enabled, aovs=None,
+           mesh_vertices=None, mesh_indices=None, env_map=None):
+    """Fixed-frame render; returns (accum[H,W,4] float32, depth[H,W] float32 with NaN on miss); `aovs`, when given a
+    dict, is filled with rgba (uint8), normal and albedo (float32 after the rgba16float round trip)."""
     S = Scene(dem, spacing, exaggeration, albedo, env_intensity, inv_two_r_prime, curvature_enabled)
+    X = Hybrid(S, mesh_vertices, mesh_indices, env_map)
     W, H = width, height
     # render_terrain.rs:635-661
     origin = tuple(f(v) for v in cam["origin"])
@@ -340,13 +481,17 @@ def render(dem, width, height, cam, *, spacing, exaggeration, albedo, sun_azimut
     accum = np.zeros((H, W, 4), np.float32)
     depth = np.full((H, W), np.nan, np.float32)
     gb_n = [None] * npx
-    for gy in range(H):                               # main_terrain_gbuffer :619-644
+    aov_normal = np.zeros((H, W, 3), np.float32)
+    aov_albedo = np.zeros((H, W, 3), np.float32)
+    for gy in range(H):                               # main_terrain_gbuffer :619-644 == the frame-0 AOV block :576-606
         for gx in range(W):
             rd = cam_ray(gx, gy, ZERO, ZERO)
-            hit, t, p, n = S.trace(origin, rd, f(1e-3), f(1e30), False, False)
+            hit, t, p, n, kind = X.closest(origin, rd, f(1e-3), f(1e30))
             gb_n[gy * W + gx] = n if hit else (ZERO, ZERO, ONE)
             if hit:
                 depth[gy, gx] = t
+                aov_normal[gy, gx] = n
+                aov_albedo[gy, gx] = X.surface_albedo(kind)
     for frame in range(frames):
         curr = [None] * npx
         for gy in range(H):                           # main_terrain :445-610
@@ -367,11 +512,12 @@ def render(dem, width, height, cam, *, spacing, exaggeration, albedo, sun_azimut
                     jx = tent(rng.next()) * f(0.5)
                     jy = tent(rng.next()) * f(0.5)
                     rd = cam_ray(gx, gy, jx, jy)
-                    hit, t, p, n = S.trace(origin, rd, f(1e-3), f(1e30), False, False)
+                    hit, t, p, n, kind = X.closest(origin, rd, f(1e-3), f(1e30))
                     if not hit:
-                        fr = tuple(fr[i] + S.env for i in range(3))
+                        sky = X.env_radiance(rd)
+                        fr = tuple(fr[i] + sky[i] for i in range(3))
                         continue
-                    alb = S.albedo
+                    alb = X.surface_albedo(kind)
                     ndotl = fmax(dot3(n, wi), ZERO)
                     tp = lum(tuple(alb[i] * light_color[i] * ndotl for i in range(3)))
                     if tp > ZERO:
@@ -388,15 +534,16 @@ def render(dem, width, height, cam, *, spacing, exaggeration, albedo, sun_azimut
                     nd = fmax(dot3(n, sun_dir), ZERO)
                     so = tuple(p[i] + n[i] * f(1e-3) for i in range(3))
                     if nd > ZERO:
-                        occ, *_ = S.trace(so, sun_dir, f(1e-3), f(1e30), True, True)
+                        occ = X.occluded(so, sun_dir, f(1e-3), f(1e30), True)
                         vis = ZERO if occ else ONE
                         sun = tuple(alb[i] * light_color[i] * nd * vis * reuse_w for i in range(3))
                     u1 = rng.next()
                     u2 = rng.next()
                     ei = cosine_dir(n, u1, u2)
-                    occ, *_ = S.trace(so, ei, f(1e-3), f(1e30), True, False)
+                    occ = X.occluded(so, ei, f(1e-3), f(1e30), False)
                     ev = ZERO if occ else ONE
-                    ibl = tuple(alb[i] * S.env * ev for i in range(3))
+                    env_rgb = X.env_radiance(ei)
+                    ibl = tuple(alb[i] * env_rgb[i] * ev for i in range(3))
                     fr = tuple(fr[i] + sun[i] + ibl[i] for i in range(3))
                 fr = tuple(fr[i] / f(spp) for i in range(3))
                 if cand["m"] > 0 and cand["w_sum"] > ZERO and cand["tpdf"] > ZERO:
@@ -463,4 +610,20 @@ def render(dem, width, height, cam, *, spacing, exaggeration, albedo, sun_azimut
                 o["weight"] = o["w_sum"] / (f(o["m"]) * o["tpdf"])
             new_prev[i] = o
         prev = new_prev
+    if aovs is not None:
+        # resolve :570-573 + hybrid_kernel.wgsl:109-112 into rgba16float, read back as u8 (render_terrain.rs:1355-1366)
+        exposure = fmin(fmax(f(cam.get("exposure", 1.0)), ZERO), f(65504.0))
+        rgba = np.zeros((H, W, 4), np.uint8)
+        for gy in range(H):
+            for gx in range(W):
+                for c in range(3):
+                    mean = accum[gy, gx, c] / accum[gy, gx, 3]
+                    exposed = mean * exposure
+                    ldr = exposed / (ONE + exposed)
+                    v = f(np.float16(ldr))
+                    rgba[gy, gx, c] = int(clamp(v, ZERO, ONE) * f(255.0) + f(0.5))
+                rgba[gy, gx, 3] = 255
+        aovs["rgba"] = rgba
+        aovs["normal"] = aov_normal.astype(np.float16).astype(np.float32)     # rgba16float AOV textures
+        aovs["albedo"] = aov_albedo.astype(np.float16).astype(np.float32)
     return accum, depth

@@ -27,20 +27,37 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
+def _mesh_and_env():
+    """A slanted quad and a small pyramid floating over the DEM (visible, shadow-casting, partly behind terrain) and a
+    smooth 8x4 equirect environment."""
+    verts = np.array([[-3.0, 9.0, -2.0], [3.5, 9.5, -2.5], [3.0, 7.0, 3.0], [-3.5, 7.5, 2.5],
+                      [5.0, 4.0, 6.0], [8.0, 4.0, 6.0], [6.5, 4.0, 9.0], [6.5, 8.0, 7.0]], np.float32)
+    tris = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 7], [5, 6, 7], [6, 4, 7], [4, 6, 5]], np.uint32)
+    yy, xx = np.mgrid[0:4, 0:8].astype(np.float32)
+    env = np.stack([0.6 + 0.4 * np.sin(xx), 0.5 + 0.1 * yy, 0.9 - 0.08 * xx], axis=-1).astype(np.float32)
+    return verts, tris, env
+
+
+@pytest.mark.parametrize("name", sorted(CASES) + ["mesh_and_env_map"])
 def test_oracle_matches_independent_wgsl_restatement(name):
+    extra = {}
+    if name == "mesh_and_env_map":
+        verts, tris, env = _mesh_and_env()
+        extra = dict(mesh_vertices=verts, mesh_indices=tris, env_map=env)
+        name = "flat_multi_frame"
     rows, cols, W, H, spp, frames, earth, radius, az, el, seed = CASES[name]
     dem = _bumpy_dem(rows, cols, seed=rows * 100 + cols)
     spacing = (2.0, 3.0)
-    cam = dict(origin=(1.5, 14.0, 22.0), look_at=(0.5, 1.0, 0.0), up=(0.0, 1.0, 0.0), fov_y=50.0)
+    cam = dict(origin=(1.5, 14.0, 22.0), look_at=(0.5, 1.0, 0.0), up=(0.0, 1.0, 0.0), fov_y=50.0, exposure=1.3)
     common = dict(spacing=spacing, exaggeration=1.25, albedo=(0.55, 0.6, 0.45), sun_azimuth_deg=az,
                   sun_elevation_deg=el, sun_intensity=2.0, sun_color=(1.0, 0.9, 0.8), env_intensity=0.4,
                   spp=spp, seed=seed)
     k, enabled = oracle.earth_curvature(earth, 0.0, radius, "none", 0.13, 1013.25, 15.0, azimuth_deg=az)
     want = oracle.render(dem, W, H, cam, max_frames=frames, min_frames=frames, variance_threshold=1e30,
-                         earth_model=earth, sphere_radius_m=radius, refraction_model="none", want_accum=True, **common)
+                         earth_model=earth, sphere_radius_m=radius, refraction_model="none", want_accum=True, **common, **extra)
     assert want["frames"] == frames
-    accum, depth = mirror.render(dem, W, H, cam, frames=frames, inv_two_r_prime=k, curvature_enabled=enabled, **common)
+    aovs = {}
+    accum, depth = mirror.render(dem, W, H, cam, frames=frames, inv_two_r_prime=k, curvature_enabled=enabled, aovs=aovs, **common, **extra)
 
     hits = np.isfinite(depth)
     assert hits.any() and (~hits).any(), "the scene must contain terrain and sky pixels"
@@ -49,6 +66,13 @@ def test_oracle_matches_independent_wgsl_restatement(name):
     np.testing.assert_array_equal(np.isnan(want["depth"]), ~hits)
     np.testing.assert_array_equal(want["depth"].view(np.uint32)[hits], depth.view(np.uint32)[hits])
     np.testing.assert_array_equal(want["accum"].view(np.uint32), accum.view(np.uint32))
+    # the resolved image and the f16 AOVs (tonemap, rgba16float round trip, u8 quantisation)
+    np.testing.assert_array_equal(want["rgba"], aovs["rgba"])
+    np.testing.assert_array_equal(want["normal"].view(np.uint32), aovs["normal"].view(np.uint32))
+    np.testing.assert_array_equal(want["albedo"].view(np.uint32), aovs["albedo"].view(np.uint32))
+    if extra:   # mesh pixels exist (their albedo AOV is the legacy constant) and the sky is not constant
+        assert (np.abs(aovs["albedo"][..., 2] - 0.8) < 1e-3).sum() >= 4
+        assert np.unique(accum[~hits][:, 0]).size > 1
     # the chain was exercised: shading differs between pixels and frames actually accumulated
     assert float(accum[..., 3].min()) == frames and np.unique(accum[..., 0]).size > 8
 
