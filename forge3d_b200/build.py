@@ -41,7 +41,10 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
+    # F3D_B200_DEFINES="F3D_ANYHIT_SIGN_ORDER=1 ..." builds a compile-time variant of the kernels (A/B runs; see
+    # csrc/f3d_trace_fast.cuh and tests/test_traversal_emulation.py); unset = the validated default
+    defines = [f"-D{d}" for d in os.environ.get("F3D_B200_DEFINES", "").split()]
+    cmd = [_nvcc(), *NVCC_FLAGS, *defines, "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -26,6 +26,20 @@
 #pragma once
 #include "f3d_trace.cuh"
 
+// Compile-time variants of the traversal.  Every variant must leave the outputs bit-identical to the oracle: checked
+// on the CPU by tests/test_traversal_emulation.py (this header compiled for the host) before it is measured on the GPU.
+//
+// F3D_ANYHIT_SIGN_ORDER = 1: any-hit rays push the surviving children far-to-near by the SIGNS of the ray direction
+//   instead of sorting them by entry parameter.  The occlusion flag cannot depend on the visit order: until the first
+//   hit an any-hit ray never changes res.t (hybrid_terrain_traversal.wgsl:297,306-314), so the set of nodes that pass
+//   the span / band tests is a fixed tree and the flag is the OR of the leaf tests over that tree.  (Which hit is
+//   found FIRST - its t - may differ in exact ties of the sort key; no caller reads the t of an any-hit ray:
+//   hybrid_traversal.wgsl:248-259 compare it with 1e30 only.)  The sign order is a valid front-to-back order of a
+//   quadtree's children, so early exit is as early as with the sort.  Closest-hit rays keep the reference order.
+#ifndef F3D_ANYHIT_SIGN_ORDER
+#define F3D_ANYHIT_SIGN_ORDER 0
+#endif
+
 namespace f3d {
 
 struct FastHit { float t; uint32_t cx, cz; bool hit; };
@@ -185,6 +199,23 @@ __device__ __forceinline__ void expand_top(const FastScene& S, TraceState& T, co
         ok[c] = v;
         kt[c] = v ? ct_lo : __int_as_float(0x7f800000);   // rejected children sort to the front, never pushed
     }
+#if F3D_ANYHIT_SIGN_ORDER
+    if (ANY_HIT) {
+        // nearest child = the one on the side the ray comes from; push far first so that it is popped first.
+        // Child j of the sign-mirrored node is child j ^ flip of the real one; node ids of the four children differ
+        // from base_id (even x, even y) only in the low bit of the x and y fields, so mirroring is one XOR.
+        const uint32_t fx = T.d.x < 0.0f ? 1u : 0u, fz = T.d.z < 0.0f ? 1u : 0u;
+        uint32_t okm = (ok[0] ? 1u : 0u) | (ok[1] ? 2u : 0u) | (ok[2] ? 4u : 0u) | (ok[3] ? 8u : 0u);
+        if (fx) okm = ((okm & 0x5u) << 1) | ((okm >> 1) & 0x5u);     // swap columns
+        if (fz) okm = ((okm & 0x3u) << 2) | (okm >> 2);              // swap rows
+        const uint32_t bid = pack_node(cl, nx * 2u, ny * 2u) ^ (fx | (fz << 13));
+        if (okm & 8u) { st.at(T.sp) = bid ^ (1u | (1u << 13)); T.sp++; }
+        if (okm & 4u) { st.at(T.sp) = bid ^ (1u << 13); T.sp++; }
+        if (okm & 2u) { st.at(T.sp) = bid ^ 1u; T.sp++; }
+        if (okm & 1u) { st.at(T.sp) = bid; T.sp++; }
+        return;
+    }
+#endif
     // order: descending t_enter, ties by original child index (== the stable insertion sort)
     float t0 = kt[0], t1 = kt[1], t2 = kt[2], t3 = kt[3];
     uint32_t i0 = 0u, i1 = 1u, i2 = 2u, i3 = 3u;
