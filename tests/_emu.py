@@ -57,3 +57,51 @@ def trace_rays(heights, spacing, origin_xz, exaggeration, rays, *, any_hit, appl
     if rc != 0:
         raise RuntimeError(f"emu_trace_rays failed ({rc})")
     return hit.astype(bool), t, nrm, int(nodes.value)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Whole backend under the SIMT interpreter: the product's host driver (f3d_backend.cu, launches rewritten by
+# tests/c/emu/gen_backend.py) and ALL its kernels compiled by g++; every CUDA thread is a fiber (tests/c/emu/simt.h).
+# ---------------------------------------------------------------------------------------------------------------
+def build_backend(defines=()) -> Path:
+    tag = hashlib.sha1(" ".join(sorted(defines)).encode()).hexdigest()[:10]
+    out = BUILD / f"libforge3d_b200_emu_{tag}.so"
+    deps = [EMU / n for n in ("gen_backend.py", "simt.cpp", "simt.h", "cuda_runtime.h", "cuda_fake_runtime.h", "cuda_fp16.h")]
+    deps += sorted(CSRC.glob("f3d_*.cu*")) + [ROOT / "include" / "forge3d_b200.h"]
+    if out.exists() and out.stat().st_mtime >= max(p.stat().st_mtime for p in deps):
+        return out
+    BUILD.mkdir(exist_ok=True)
+    gen = BUILD / f"f3d_backend_emu_{tag}.cpp"
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    import sys
+    subprocess.run([sys.executable, str(EMU / "gen_backend.py"), str(CSRC / "f3d_backend.cu"), str(gen)], check=True, env=env)
+    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-DEMU_SIMT", f"-I{EMU}",
+           f"-I{CSRC}", f"-I{ROOT / 'include'}", *[f"-D{d}" for d in defines], "-o", str(out), str(gen), str(EMU / "simt.cpp")]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError(f"g++ failed:\n{' '.join(cmd)}\n{res.stdout}")
+    return out
+
+
+class emulated_backend:
+    """Context manager: forge3d_b200._native talks to the emulated library instead of libforge3d_b200.so.  Only tests
+    do this (the product has no such switch): it is how the CPU suite runs the real host driver + kernels."""
+
+    def __init__(self, defines=()):
+        self.defines = tuple(defines)
+
+    def __enter__(self):
+        from forge3d_b200 import _native
+
+        self._native = _native
+        self._saved = (_native.LIB_PATH, _native._lib)
+        _native.LIB_PATH = build_backend(self.defines)
+        _native._lib = None
+        _native.lib()
+        return _native
+
+    def __exit__(self, *exc):
+        self._native.LIB_PATH, self._native._lib = self._saved
+        return False

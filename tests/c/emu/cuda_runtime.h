@@ -7,6 +7,15 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#ifdef __cplusplus   /* libstdc++ spells attributes __noinline__ etc.: parse it before the CUDA keywords become macros */
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#endif
 
 #define __device__
 #define __host__
@@ -55,10 +64,15 @@ static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 
+#ifdef EMU_SIMT
+#include "simt.h"          /* 32-lane warps and CTAs as fibers; defines the *_sync collectives and dim3 */
+#include "cuda_fake_runtime.h"
+#else
 /* a warp of one lane */
 static inline uint32_t __ballot_sync(uint32_t, int pred) { return pred ? 1u : 0u; }
 static inline uint32_t __activemask() { return 1u; }
-static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
-static inline int __ffs(int x) { return __builtin_ffs(x); }
 template <class T> static inline T __shfl_sync(uint32_t, T v, int, int = 32) { return v; }
 static inline void __syncwarp(uint32_t = 0xFFFFFFFFu) {}
+#endif
+static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }

@@ -1,0 +1,79 @@
+"""The product's CUDA source on the CPU: host driver (csrc/f3d_backend.cu) + every kernel (csrc/*.cuh) compiled by g++
+and executed by the cooperative SIMT interpreter in tests/c/emu (CTAs of fibers, real 32-lane warp collectives), compared
+bit for bit with the oracle.  This is NOT a product path (the product has no CPU fallback and never loads this library);
+it is the pre-flight check that lets kernel restructurings be proven exact - and free of warp-synchronisation deadlocks -
+without GPU time.  The -m gpu tests make the same comparisons on the device."""
+import numpy as np
+import pytest
+
+import _emu
+import _helpers as H
+from oracle import oracle
+
+VARIANTS = {"default": (), "anyhit_sign_order": ("F3D_ANYHIT_SIGN_ORDER=1",)}
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+def _same_render(g, o):
+    for k in ("rgba", "depth", "normal", "albedo", "accum"):
+        assert np.array_equal(_bits(g[k]), _bits(o[k])), k
+    assert g["frames"] == o["frames"] and g["converged"] == o["converged"]
+    assert np.float32(g["variance"]) == np.float32(o["variance"])
+    for k in ("rays_primary", "rays_shadow", "rays_ibl", "minmax_pyramid_bytes"):
+        assert g[k] == o[k], k
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_emulated_render_is_bit_identical_to_the_oracle(variant):
+    dem = H.golden_dem()
+    kw = {**H.scene_kwargs(dem), "max_frames": 5, "min_frames": 5, "variance_threshold": 1e30}
+    o = oracle.render(dem, 56, 40, H.CAM, want_accum=True, **kw)
+    with _emu.emulated_backend(VARIANTS[variant]) as native:
+        g = native.hybrid_render_terrain_reference(dem, 56, 40, H.CAM, want_accum=True, **kw)
+    _same_render(g, o)
+    assert o["rays_shadow"] > 1000 and np.isfinite(o["depth"]).any() and np.isnan(o["depth"]).any()
+
+
+def test_emulated_render_with_mesh_env_map_spp_and_curvature():
+    dem = H.sine_dem(64)
+    rng = np.random.default_rng(2)
+    env = rng.random((8, 16, 3), dtype=np.float32) + 0.2
+    verts = np.array([[-8, 14, -6], [9, 15, -5], [8, 11, 7], [-9, 12, 6], [0, 22, 0]], np.float32)
+    tris = np.array([[0, 1, 2], [0, 2, 3], [0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4], [0, 2, 1], [1, 3, 2], [2, 0, 3]], np.uint32)
+    kw = dict(spacing=(1.5, 1.5), exaggeration=1.0, albedo=(0.5, 0.55, 0.45), sun_azimuth_deg=290.0, sun_elevation_deg=18.0,
+              env_map=env, mesh_vertices=verts, mesh_indices=tris, spp=3, seed=99, max_frames=3, min_frames=3,
+              variance_threshold=1e30, earth_model="sphere", sphere_radius_m=5000.0, refraction_model="none")
+    cam = {"origin": (0.0, 30.0, 70.0), "look_at": (0.0, 6.0, 0.0), "up": (0.0, 1.0, 0.0), "fov_y": 45.0}
+    o = oracle.render(dem, 40, 32, cam, want_accum=True, **kw)
+    with _emu.emulated_backend() as native:
+        g = native.hybrid_render_terrain_reference(dem, 40, 32, cam, want_accum=True, **kw)
+    _same_render(g, o)
+
+
+def test_emulated_seams_pyramid_and_cooperative_ray_batches():
+    rng = np.random.default_rng(4)
+    dem = (rng.standard_normal((37, 70)) * 30).astype(np.float32)
+    h = H.curvature_fixture()
+    arb, _ = H.kat_rays(h)
+    rays = arb[:4096]
+    with _emu.emulated_backend() as native:
+        g_levels, gcw, gch = native.build_minmax(dem)
+        got = {}
+        for any_hit, curv in [(True, True), (False, False)]:
+            kw = dict(any_hit=any_hit, apply_curvature=curv, inv_two_r_prime=float(H.PROOF_INV_TWO_R), curvature_enabled=True)
+            got[any_hit] = (native.trace_rays(h, (500.0, 500.0), (0.0, 0.0), 1.0, rays, variant=0, **kw),
+                            native.trace_rays(h, (500.0, 500.0), (0.0, 0.0), 1.0, rays, variant=1, **kw),
+                            oracle.trace_rays(h, (500.0, 500.0), (0.0, 0.0), 1.0, rays, **kw))
+    o_levels, ocw, och = oracle.build_minmax(dem)
+    assert (gcw, gch) == (ocw, och) and len(g_levels) == len(o_levels)
+    for a, b in zip(g_levels, o_levels):
+        assert np.array_equal(_bits(a), _bits(b))
+    for any_hit, (fast, literal, want) in got.items():
+        for have in (fast, literal):          # 32-lane cooperative production traversal and the literal loop
+            assert np.array_equal(have[0], want[0])
+            assert np.array_equal(_bits(have[1]), _bits(want[1]))
+            if not any_hit:
+                assert np.array_equal(_bits(have[2]), _bits(want[2]))
