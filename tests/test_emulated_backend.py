@@ -77,3 +77,42 @@ def test_emulated_seams_pyramid_and_cooperative_ray_batches():
             assert np.array_equal(_bits(have[1]), _bits(want[1]))
             if not any_hit:
                 assert np.array_equal(_bits(have[2]), _bits(want[2]))
+
+
+@pytest.mark.parametrize("world,width,height,frames", [(2, 48, 72, 6), (3, 40, 100, 4)])
+def test_emulated_row_partition_is_bit_identical_to_one_session(world, width, height, frames):
+    """SURVEY section 8e on the CPU: `world` sessions (one per rank) in ONE process, stepped frame by frame in rank order.
+    Their peer pointers are real pointers here, so k_primary's halo stores (4 rows up / 3 rows down) and the in-kernel
+    frame barrier (wait_neighbours / signal_neighbours) run exactly as over NVLink; every rank resolves its owned rows into
+    the same buffers.  The result must equal the unpartitioned session bit for bit."""
+    from forge3d_b200.session import Session
+
+    dem = H.golden_dem()
+    kw = {**H.scene_kwargs(dem), "max_frames": frames, "min_frames": frames, "variance_threshold": 1e30}
+    outs = {}
+    with _emu.emulated_backend():
+        for tag, nranks in (("single", 1), ("split", world)):
+            sessions = [Session(dem, width, height, H.CAM, part_rank=r, part_world=nranks, part_block_rows=16, **kw)
+                        for r in range(nranks)]
+            if nranks > 1:
+                table = b"".join(s.ipc_export() for s in sessions)
+                for s in sessions:
+                    s.ipc_import(table)
+            for _ in range(frames):
+                for s in sessions:
+                    s.render_frames(1)
+            rgba = np.zeros((height, width, 4), np.uint8)
+            depth = np.zeros((height, width), np.float32)
+            normal = np.zeros((height, width, 3), np.float32)
+            albedo = np.zeros((height, width, 3), np.float32)
+            variances = []
+            for s in sessions:
+                variances.append(s.variance()[0])
+                s.resolve_device(rgba.ctypes.data, albedo.ctypes.data, normal.ctypes.data, depth.ctypes.data, check_validity=True)
+            outs[tag] = (rgba, depth, normal, albedo, max(variances))
+            for s in sessions:
+                s.close()
+    for a, b in zip(outs["single"][:4], outs["split"][:4]):
+        assert np.array_equal(_bits(a), _bits(b))
+    assert np.float32(outs["single"][4]) == np.float32(outs["split"][4])
+    assert outs["single"][0][..., :3].max() > 0
