@@ -16,11 +16,19 @@ CSRC = ROOT / "forge3d_b200" / "csrc"
 BUILD = EMU / "_build"
 
 
+def _tag(defines, deps) -> str:
+    """Build products are keyed by the CONTENT of everything they are made from (mtimes lie after a checkout)."""
+    h = hashlib.sha1(" ".join(sorted(defines)).encode())
+    for p in deps:
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()[:12]
+
+
 def build(defines=()) -> Path:
-    tag = hashlib.sha1(" ".join(sorted(defines)).encode()).hexdigest()[:10]
-    out = BUILD / f"libtrace_emu_{tag}.so"
     deps = [EMU / "trace_emu.cpp", EMU / "cuda_runtime.h"] + sorted(CSRC.glob("f3d_*.cuh"))
-    if out.exists() and out.stat().st_mtime >= max(p.stat().st_mtime for p in deps):
+    out = BUILD / f"libtrace_emu_{_tag(defines, deps)}.so"
+    if out.exists():
         return out
     BUILD.mkdir(exist_ok=True)
     cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", f"-I{EMU}", f"-I{CSRC}",
@@ -64,11 +72,11 @@ def trace_rays(heights, spacing, origin_xz, exaggeration, rays, *, any_hit, appl
 # tests/c/emu/gen_backend.py) and ALL its kernels compiled by g++; every CUDA thread is a fiber (tests/c/emu/simt.h).
 # ---------------------------------------------------------------------------------------------------------------
 def build_backend(defines=()) -> Path:
-    tag = hashlib.sha1(" ".join(sorted(defines)).encode()).hexdigest()[:10]
-    out = BUILD / f"libforge3d_b200_emu_{tag}.so"
     deps = [EMU / n for n in ("gen_backend.py", "simt.cpp", "simt.h", "cuda_runtime.h", "cuda_fake_runtime.h", "cuda_fp16.h")]
     deps += sorted(CSRC.glob("f3d_*.cu*")) + [ROOT / "include" / "forge3d_b200.h"]
-    if out.exists() and out.stat().st_mtime >= max(p.stat().st_mtime for p in deps):
+    tag = _tag(defines, deps)
+    out = BUILD / f"libforge3d_b200_emu_{tag}.so"
+    if out.exists():
         return out
     BUILD.mkdir(exist_ok=True)
     gen = BUILD / f"f3d_backend_emu_{tag}.cpp"
