@@ -29,7 +29,7 @@
 // Compile-time variants of the traversal.  Every variant must leave the outputs bit-identical to the oracle: checked
 // on the CPU by tests/test_traversal_emulation.py (this header compiled for the host) before it is measured on the GPU.
 //
-// F3D_ANYHIT_SIGN_ORDER = 1: any-hit rays push the surviving children far-to-near by the SIGNS of the ray direction
+// F3D_ANYHIT_SIGN_ORDER = 1 (default; 0 restores the reference's sort for any-hit rays too): any-hit rays push the surviving children far-to-near by the SIGNS of the ray direction
 //   instead of sorting them by entry parameter.  The occlusion flag cannot depend on the visit order: until the first
 //   hit an any-hit ray never changes res.t (hybrid_terrain_traversal.wgsl:297,306-314), so the set of nodes that pass
 //   the span / band tests is a fixed tree and the flag is the OR of the leaf tests over that tree.  (Which hit is
@@ -37,7 +37,7 @@
 //   hybrid_traversal.wgsl:248-259 compare it with 1e30 only.)  The sign order is a valid front-to-back order of a
 //   quadtree's children, so early exit is as early as with the sort.  Closest-hit rays keep the reference order.
 #ifndef F3D_ANYHIT_SIGN_ORDER
-#define F3D_ANYHIT_SIGN_ORDER 0
+#define F3D_ANYHIT_SIGN_ORDER 1
 #endif
 
 namespace f3d {

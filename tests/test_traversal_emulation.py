@@ -10,9 +10,9 @@ import _helpers as H
 from oracle import oracle
 
 # compile-time variants of the traversal that must all be exact (the default build is the first one)
-VARIANTS = {"default": (), "anyhit_sign_order": ("F3D_ANYHIT_SIGN_ORDER=1",)}
+VARIANTS = {"default": (), "anyhit_sorted": ("F3D_ANYHIT_SIGN_ORDER=0",)}
 # variants whose any-hit rays may report a different (equally valid) first hit: flags are compared, not t
-FLAG_ONLY_ANYHIT = {"anyhit_sign_order"}
+FLAG_ONLY_ANYHIT = {"default"}
 
 
 def _bits(a):
