@@ -23,6 +23,35 @@ IPC_HANDLE_BYTES = 64
 IPC_HANDLES_PER_RANK = 3
 
 
+class Atmosphere(C.Structure):
+    """f3d_atmosphere (include/forge3d_b200.h)."""
+    _fields_ = [
+        ("transmittance", C.POINTER(C.c_uint16)), ("scattering", C.POINTER(C.c_uint16)), ("aerial", C.POINTER(C.c_uint16)),
+        ("transmittance_mu", C.c_uint32), ("transmittance_height", C.c_uint32),
+        ("scattering_mu_view", C.c_uint32), ("scattering_mu_sun", C.c_uint32),
+        ("scattering_height", C.c_uint32), ("scattering_nu", C.c_uint32),
+        ("aerial_distance", C.c_uint32), ("aerial_mu_view", C.c_uint32), ("aerial_height", C.c_uint32),
+        ("bottom_radius_m", C.c_float), ("top_radius_m", C.c_float), ("max_aerial_distance_m", C.c_float),
+        ("ozone_du", C.c_float), ("mie_g", C.c_float), ("turbidity", C.c_float),
+        ("rayleigh_scale_height_m", C.c_float), ("mie_scale_height_m", C.c_float), ("ground_albedo", C.c_float),
+    ]
+
+
+def make_atmosphere(handle) -> tuple:
+    """AtmosphereLutHandle (forge3d_b200.atmosphere) -> (f3d_atmosphere, keepalive)."""
+    a = Atmosphere()
+    u16 = lambda arr: arr.ctypes.data_as(C.POINTER(C.c_uint16))
+    a.transmittance, a.scattering, a.aerial = u16(handle.transmittance), u16(handle.scattering), u16(handle.aerial)
+    cfg, d = handle.config, handle.config.dimensions
+    for name in ("transmittance_mu", "transmittance_height", "scattering_mu_view", "scattering_mu_sun", "scattering_height",
+                 "scattering_nu", "aerial_distance", "aerial_mu_view", "aerial_height"):
+        setattr(a, name, int(getattr(d, name)))
+    for name in ("bottom_radius_m", "top_radius_m", "max_aerial_distance_m", "ozone_du", "mie_g", "turbidity",
+                 "rayleigh_scale_height_m", "mie_scale_height_m", "ground_albedo"):
+        setattr(a, name, float(getattr(cfg, name)))
+    return a, [handle, a]
+
+
 class TerrainDesc(C.Structure):
     """f3d_terrain_desc (include/forge3d_b200.h)."""
     _fields_ = [
@@ -44,6 +73,7 @@ class TerrainDesc(C.Structure):
         ("max_frames", C.c_uint32), ("min_frames", C.c_uint32), ("variance_threshold", C.c_float),
         ("device", C.c_int32), ("compat_512mib_gate", C.c_int32),
         ("part_rank", C.c_uint32), ("part_world", C.c_uint32), ("part_block_rows", C.c_uint32),
+        ("atmosphere", C.POINTER(Atmosphere)),
     ]
 
 
@@ -136,7 +166,7 @@ def make_desc(heightmap, width, height, cam, *, spacing, exaggeration, albedo, s
               max_frames, min_frames, variance_threshold, seed, sun_color, observer_latitude_deg,
               observer_longitude_deg, earth_model, sphere_radius_m, refraction_model, refraction_k,
               pressure_mbar, temperature_c, device=0, compat_512mib_gate=False, part_rank=0, part_world=1,
-              part_block_rows=0):
+              part_block_rows=0, atmosphere=None):
     """Marshals the native seam's arguments into f3d_terrain_desc (terrain_reference.rs:295-414).
     Returns (desc, keepalive)."""
     if earth_model not in EARTH_MODELS:
@@ -194,6 +224,10 @@ def make_desc(heightmap, width, height, cam, *, spacing, exaggeration, albedo, s
     d.device = int(device)
     d.compat_512mib_gate = int(bool(compat_512mib_gate))
     d.part_rank, d.part_world, d.part_block_rows = int(part_rank), int(part_world), int(part_block_rows)
+    if atmosphere is not None:   # an AtmosphereLutHandle (see forge3d_b200.atmosphere.resolve_atmosphere)
+        atm, atm_keep = make_atmosphere(atmosphere)
+        keep += atm_keep
+        d.atmosphere = C.pointer(atm)
     return d, keep
 
 
@@ -261,11 +295,12 @@ def hybrid_render_terrain_reference(heightmap, width, height, cam, spacing=(1.0,
                                     want_accum=False):
     """Native seam `_forge3d.hybrid_render_terrain_reference` (terrain_reference.rs:224-457) on the
     CUDA backend.  `certificate` and `cache` are accepted and ignored (the reference ignores `cache`,
-    :291; certificates are out of scope).  `atmosphere` (AETHER post) is a
-    section 8f "next" row: passing one raises instead of silently rendering without it."""
+    :291; certificates are out of scope).  `atmosphere` is an AtmosphereLutHandle, a
+    mapping or a settings object (extract_atmosphere_lut_handle, :46-210) and enables the AETHER post."""
     _ = (certificate, cache)
-    if atmosphere is not None:
-        raise NotImplementedError("atmosphere (AETHER aerial-perspective post) is not implemented by forge3d_b200 yet")
+    from .atmosphere import resolve_atmosphere
+
+    atmosphere = resolve_atmosphere(atmosphere)
     sun_rgb = (1.0, 0.97, 0.92) if sun_color is None else extract_sun_color(sun_color)
     d, keep = make_desc(heightmap, width, height, cam, spacing=spacing, exaggeration=exaggeration, albedo=albedo,
                         sun_azimuth_deg=sun_azimuth_deg, sun_elevation_deg=sun_elevation_deg,
@@ -275,7 +310,7 @@ def hybrid_render_terrain_reference(heightmap, width, height, cam, spacing=(1.0,
                         observer_latitude_deg=observer_latitude_deg, observer_longitude_deg=observer_longitude_deg,
                         earth_model=earth_model, sphere_radius_m=sphere_radius_m, refraction_model=refraction_model,
                         refraction_k=refraction_k, pressure_mbar=pressure_mbar, temperature_c=temperature_c,
-                        device=device, compat_512mib_gate=compat_512mib_gate)
+                        device=device, compat_512mib_gate=compat_512mib_gate, atmosphere=atmosphere)
     o, arrays = alloc_outputs(width, height, want_accum)
     check(lib().f3d_terrain_reference_render(C.byref(d), C.byref(o)))
     del keep

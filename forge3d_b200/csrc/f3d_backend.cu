@@ -197,6 +197,33 @@ static int validate_desc(const f3d_terrain_desc* d) {
         return fail(F3D_ERR_ARGUMENT, "image of %ux%u pixels exceeds the 2^31-pixel addressing limit", d->width, d->height);
     if (d->part_world > 1 && d->part_rank >= d->part_world)
         return fail(F3D_ERR_ARGUMENT, "part_rank (%u) must be < part_world (%u)", d->part_rank, d->part_world);
+    if (d->atmosphere && !(d->atmosphere->transmittance && d->atmosphere->scattering && d->atmosphere->aerial))
+        return fail(F3D_ERR_ARGUMENT, "atmosphere LUT pointer is null");
+    return 0;
+}
+
+// AtmosphereConfig::validate + LutDimensions::validate (src/core/atmosphere/bake.rs:75-100,165-220) as
+// AetherPostPass::new reports them (aether_post.rs:58-65), then validate_luts / upload_lut (:343-385).
+static int validate_atmosphere(const f3d_atmosphere& a) {
+    const char* pre = "invalid AETHER PT settings: invalid atmosphere configuration: ";
+    const float scalars[9] = {a.turbidity, a.ozone_du, a.mie_g, a.bottom_radius_m, a.top_radius_m, a.rayleigh_scale_height_m,
+                              a.mie_scale_height_m, a.max_aerial_distance_m, a.ground_albedo};
+    for (float v : scalars)
+        if (!isfinite(v)) return fail(F3D_ERR_RENDER, "%sall scalar parameters must be finite", pre);
+    if (!(a.turbidity >= 1.0f && a.turbidity <= 10.0f)) return fail(F3D_ERR_RENDER, "%sturbidity must be in [1, 10]", pre);
+    if (!(a.ozone_du >= 0.0f && a.ozone_du <= 600.0f)) return fail(F3D_ERR_RENDER, "%sozone must be in [0, 600] DU", pre);
+    if (!(a.mie_g >= 0.0f && a.mie_g <= 0.99f)) return fail(F3D_ERR_RENDER, "%smie_g must be in [0, 0.99]", pre);
+    if (a.bottom_radius_m <= 0.0f || a.top_radius_m <= a.bottom_radius_m)
+        return fail(F3D_ERR_RENDER, "%stop radius must exceed a positive bottom radius", pre);
+    if (a.rayleigh_scale_height_m <= 0.0f || a.mie_scale_height_m <= 0.0f || a.max_aerial_distance_m <= 0.0f)
+        return fail(F3D_ERR_RENDER, "%sscale heights and aerial distance must be positive", pre);
+    if (!(a.ground_albedo >= 0.0f && a.ground_albedo <= 1.0f)) return fail(F3D_ERR_RENDER, "%sground albedo must be in [0, 1]", pre);
+    const uint32_t axes[9] = {a.transmittance_mu, a.transmittance_height, a.scattering_mu_view, a.scattering_mu_sun,
+                              a.scattering_height, a.scattering_nu, a.aerial_distance, a.aerial_mu_view, a.aerial_height};
+    for (uint32_t ax : axes)
+        if (ax < 2u) return fail(F3D_ERR_RENDER, "%severy atmosphere LUT axis must contain at least two samples", pre);
+    for (uint32_t ax : axes)
+        if (ax > 256u) return fail(F3D_ERR_RENDER, "%satmosphere LUT axes are capped at 256 samples", pre);
     return 0;
 }
 
@@ -508,6 +535,14 @@ struct f3d_session {
     uint64_t steps = 0;
     cudaEvent_t join_ev = nullptr;
     float4* d_sstate = nullptr;
+    // AETHER post (desc.atmosphere): payloads are copied at creation (the desc is borrowed for that call only) and
+    // validated + uploaded by the first resolve, i.e. after the frame loop, as the reference does
+    // (render_terrain.rs:1246-1271: "after PROMETHEUS has finished its frame-0 AOV writes and convergence loop")
+    bool has_atmosphere = false, aether_ready = false;
+    f3d_atmosphere atm{};
+    std::vector<uint16_t> h_lut[3];
+    uint2* d_lut[3] = {nullptr, nullptr, nullptr};
+    AetherParams aether{};
 };
 
 static void session_free(f3d_session* s) {
@@ -539,6 +574,7 @@ static void session_free(f3d_session* s) {
     }
     if (s->join_ev) cudaEventDestroy(s->join_ev);
     cached_free(s->d_sstate, dv);
+    for (auto& p : s->d_lut) cached_free(p, dv);
     cached_free(s->d_rgba, dv); cached_free(s->d_albedo, dv); cached_free(s->d_normal, dv); cached_free(s->d_depth, dv);
     if (s->h_gate) cudaFreeHost(s->h_gate);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -744,6 +780,24 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
         P.sync_error = s->d_sync + 3;
     }
 
+    if (d->atmosphere) {
+        const f3d_atmosphere& a = *d->atmosphere;
+        s->has_atmosphere = true;
+        s->atm = a;
+        const size_t texels[3] = {(size_t)a.transmittance_mu * a.transmittance_height,
+                                  (size_t)a.scattering_mu_view * a.scattering_mu_sun * a.scattering_height * a.scattering_nu,
+                                  (size_t)a.aerial_distance * a.aerial_mu_view * a.aerial_height};
+        const uint16_t* src[3] = {a.transmittance, a.scattering, a.aerial};
+        for (int k = 0; k < 3; k++) {
+            if (texels[k] > (64u << 20)) return fail(F3D_ERR_RENDER, "atmosphere LUT dimensions overflow");
+            s->h_lut[k].assign(src[k], src[k] + texels[k] * 4);
+        }
+        s->atm.transmittance = s->atm.scattering = s->atm.aerial = nullptr;
+        s->aether.tan_half_fov = tanf(0.5f * fov);            // (0.5 * fov_y_radians).tan(), aether_post.rs:139
+        s->aether.aspect = (float)W / (float)H;
+        s->aether.sun_intensity = sun_intensity;
+    }
+
     // ---- one-shot G-buffer / centre-ray AOV pass (render_terrain.rs:1091-1121) ----
     GbufferOut G{s->d_pixflags, s->d_aov_normal, s->d_aov_depth};
     k_gbuffer<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P, G);
@@ -865,13 +919,44 @@ extern "C" int f3d_session_variance(f3d_session* s, float* vmax, int32_t* nonfin
     return 0;
 }
 
+// AetherPostPass::new (aether_post.rs:40-291): validate the settings and LUTs, upload the three tables.
+static int prepare_aether(f3d_session* s) {
+    if (s->aether_ready) return 0;
+    const f3d_atmosphere& a = s->atm;
+    int rc = validate_atmosphere(a);
+    if (rc) return rc;
+    if ((uint64_t)a.scattering_height * a.scattering_nu > 0xFFFFFFFFull) return fail(F3D_ERR_RENDER, "AETHER scattering depth overflow");
+    for (int k = 0; k < 3; k++) {
+        const size_t texels = s->h_lut[k].size() / 4;
+        if ((rc = dmalloc(s, &s->d_lut[k], texels, false))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s->d_lut[k], s->h_lut[k].data(), texels * sizeof(uint2), cudaMemcpyHostToDevice, s->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    AetherParams& A = s->aether;
+    A.transmittance = s->d_lut[0]; A.scattering = s->d_lut[1]; A.aerial = s->d_lut[2];
+    A.t_dims[0] = a.transmittance_mu; A.t_dims[1] = a.transmittance_height;
+    A.s_dims[0] = a.scattering_mu_view; A.s_dims[1] = a.scattering_mu_sun; A.s_dims[2] = a.scattering_height * a.scattering_nu;
+    A.s_height = a.scattering_height; A.s_nu = a.scattering_nu;
+    A.a_dims[0] = a.aerial_distance; A.a_dims[1] = a.aerial_mu_view; A.a_dims[2] = a.aerial_height;
+    A.bottom_radius_m = a.bottom_radius_m; A.top_radius_m = a.top_radius_m; A.max_aerial_distance_m = a.max_aerial_distance_m;
+    A.ozone_du = a.ozone_du; A.turbidity = a.turbidity;
+    s->aether_ready = true;
+    return 0;
+}
+
 static int resolve_device_impl(f3d_session* s, void* d_rgba, void* d_albedo, void* d_normal, void* d_depth,
                                int32_t check_validity) {
     if (s->frames == 0) return fail(F3D_ERR_ARGUMENT, "no frames rendered");
+    const bool aether = s->has_atmosphere && d_rgba != nullptr;
+    if (aether) {
+        int rc = prepare_aether(s);
+        if (rc) return rc;
+    }
     FrameParams P = s->P;
     P.resv_in = s->d_resv[(s->frames + 1u) & 1u];   // out of the last frame
     ResolveOut R{};
-    R.rgba = (uint8_t*)d_rgba; R.albedo = (float*)d_albedo; R.normal = (float*)d_normal; R.depth = (float*)d_depth;
+    R.rgba = aether ? nullptr : (uint8_t*)d_rgba;   // with AETHER the beauty comes from k_aether below
+    R.albedo = (float*)d_albedo; R.normal = (float*)d_normal; R.depth = (float*)d_depth;
     R.aov_normal = s->d_aov_normal; R.aov_depth = s->d_aov_depth;
     R.validity = s->d_gate + 2;
     R.last_frame = s->frames - 1u;
@@ -879,6 +964,10 @@ static int resolve_device_impl(f3d_session* s, void* d_rgba, void* d_albedo, voi
     if (s->n_peer_ptrs) { k_wait_peers<<<1, 32, 0, s->stream>>>(P, s->frames); s->launches++; }
     k_resolve<<<s->grid, kTileW * kTileH, 0, s->stream>>>(P, R);
     s->launches++;
+    if (aether) {   // the post pass of render_terrain.rs:1287-1311, after the traversal's own resolve work
+        k_aether<<<s->grid, kTileW * kTileH, 0, s->stream>>>(P, s->aether, s->d_aov_depth, (uint8_t*)d_rgba);
+        s->launches++;
+    }
     CUDA_TRY(cudaGetLastError());
     if (check_validity) {
         CUDA_TRY(cudaMemcpyAsync(s->h_gate + 2, s->d_gate + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));

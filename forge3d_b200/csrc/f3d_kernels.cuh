@@ -25,6 +25,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include "f3d_aether.cuh"
 #include "f3d_trace_fast.cuh"
 
 namespace f3d {
@@ -755,6 +756,34 @@ __global__ void __launch_bounds__(kThreads) k_resolve(const __grid_constant__ Fr
         if (nonfinite) atomicOr(R.validity + 0, 1u);
         if (valid) atomicOr(R.validity + 1, 1u);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_aether: AETHER aerial-perspective post (f3d_aether.cuh) over the finished accumulation, fused with the
+// beauty read-back: accum + frame-0 depth AOV + hit-type bits -> L_surface*T + L_inscatter -> Reinhard ->
+// RGBA16F rounding -> u8.  Replaces prometheus_aerial.wgsl `main` (8x8 workgroups, aether_post.rs:336-339),
+// its two texture copies (:296-331) and the out-texture read-back (render_terrain.rs:1358-1366).  One launch
+// per render; ALU-bound (two quadrilinear LUT fetches + 16 altitude samples + 11 wavelengths per hit pixel);
+// 16 B + 4 B + 1 B read and 4 B written per pixel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_aether(const __grid_constant__ FrameParams P, const AetherParams A,
+                                                    const float* __restrict__ aov_depth, uint8_t* __restrict__ rgba) {
+    uint32_t gx, gy;
+    if (!owned_pixel(P, gx, gy)) return;
+    const uint32_t pix = gy * P.W + gx;
+    AetherView V;
+    V.cam_origin = ld3(P.cam_origin); V.cam_right = ld3(P.cam_right); V.cam_up = ld3(P.cam_up); V.cam_forward = ld3(P.cam_forward);
+    V.sun_dir = normalize3(ld3(P.light_dir));
+    V.exposure = P.exposure;
+    V.W = P.W; V.H = P.H;
+    const bool visible = ((P.pixflags[pix] >> 1) & 3u) != 0u;      // frame-0 visibility AOV (:605-607)
+    const v3 ldr = aether_pixel(A, V, gx, gy, P.accum[pix], aov_depth[pix], visible);
+    uchar4 px;
+    px.x = (uint8_t)(clampf(f16_round(ldr.x), 0.0f, 1.0f) * 255.0f + 0.5f);
+    px.y = (uint8_t)(clampf(f16_round(ldr.y), 0.0f, 1.0f) * 255.0f + 0.5f);
+    px.z = (uint8_t)(clampf(f16_round(ldr.z), 0.0f, 1.0f) * 255.0f + 0.5f);
+    px.w = 255;
+    reinterpret_cast<uchar4*>(rgba)[pix] = px;
 }
 
 // ---------------------------------------------------------------------------------------------

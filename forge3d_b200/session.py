@@ -22,7 +22,9 @@ class Session:
     """A resident scene + per-pixel state on one CUDA device."""
 
     def __init__(self, heightmap, width, height, cam=None, *, device=0, cuda_stream=0, part_rank=0, part_world=1,
-                 part_block_rows=0, compat_512mib_gate=False, **kw):
+                 part_block_rows=0, compat_512mib_gate=False, atmosphere=None, **kw):
+        from .atmosphere import resolve_atmosphere
+
         args = dict(DEFAULTS)
         unknown = set(kw) - set(args)
         if unknown:
@@ -33,7 +35,8 @@ class Session:
         self._args = args
         desc, keep = _native.make_desc(heightmap, width, height, cam, device=device,
                                        compat_512mib_gate=compat_512mib_gate, part_rank=part_rank,
-                                       part_world=part_world, part_block_rows=part_block_rows, **args)
+                                       part_world=part_world, part_block_rows=part_block_rows,
+                                       atmosphere=resolve_atmosphere(atmosphere), **args)
         self._L = _native.lib()
         self._h = C.c_void_p()
         _native.check(self._L.f3d_session_create(C.byref(desc), C.c_void_p(int(cuda_stream) or None), C.byref(self._h)))

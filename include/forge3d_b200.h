@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define F3D_ABI_VERSION 1
+#define F3D_ABI_VERSION 2
 
 /* Error classes; mirror RenderError::{Render,Upload,Device,Budget}, src/core/error.rs:10-32. */
 typedef enum f3d_status {
@@ -43,8 +43,24 @@ enum { F3D_EARTH_FLAT = 0, F3D_EARTH_SPHERE = 1, F3D_EARTH_ELLIPSOID = 2 };
 enum { F3D_REFRACTION_NONE = 0, F3D_REFRACTION_BENNETT = 1, F3D_REFRACTION_SAEMUNDSSON = 2,
        F3D_REFRACTION_EFFECTIVE_RADIUS = 3 };
 
-/* Replaces TerrainReferenceDesc, render_terrain.rs:239-282.  `atmosphere` (AETHER post) is a
- * SURVEY section 8f "next" row and is not part of this ABI version. */
+/* Replaces AtmosphereLutHandle as the AETHER post consumes it (src/core/atmosphere/runtime.rs:44-90; the uniforms
+ * and LUT uploads of src/path_tracing/hybrid_compute/aether_post.rs:10-23,58-178,365-440).  The caller (the Rust
+ * side, which owns the shipped LUT bank / a baked handle) passes the three RGBA16F payloads it would have uploaded
+ * as textures: texel (x, y, z) at ((z * dim_y + y) * dim_x + x) * 4 halves, little-endian, borrowed for the call. */
+typedef struct f3d_atmosphere {
+    const uint16_t* transmittance;     /* dims transmittance_mu x transmittance_height */
+    const uint16_t* scattering;        /* accumulated scattering: scattering_mu_view x scattering_mu_sun x
+                                          (scattering_height * scattering_nu) */
+    const uint16_t* aerial;            /* aerial_distance x aerial_mu_view x aerial_height (rgb = 0, a = transmittance) */
+    uint32_t transmittance_mu, transmittance_height;
+    uint32_t scattering_mu_view, scattering_mu_sun, scattering_height, scattering_nu;
+    uint32_t aerial_distance, aerial_mu_view, aerial_height;
+    /* AtmosphereConfig (src/core/atmosphere/bake.rs:132-162) */
+    float bottom_radius_m, top_radius_m, max_aerial_distance_m, ozone_du;
+    float mie_g, turbidity, rayleigh_scale_height_m, mie_scale_height_m, ground_albedo;
+} f3d_atmosphere;
+
+/* Replaces TerrainReferenceDesc, render_terrain.rs:239-282. */
 typedef struct f3d_terrain_desc {
     const float* heights;          /* host, row-major dem_h x dem_w (desc.heights) */
     uint32_t dem_w, dem_h;
@@ -75,6 +91,9 @@ typedef struct f3d_terrain_desc {
     uint32_t part_rank, part_world;/* image-row partition: this process renders row blocks
                                       b with b % part_world == part_rank (world 0/1 = whole image) */
     uint32_t part_block_rows;      /* rows per block (0 = default 16; rounded up to a multiple of 16) */
+    /* ---- desc.atmosphere (render_terrain.rs:262-265): AETHER aerial-perspective post over the converged
+     * accumulation and the frame-0 depth AOV (:1246-1311); NULL = none.  Only `rgba` changes; AOVs do not. ---- */
+    const f3d_atmosphere* atmosphere;
 } f3d_terrain_desc;
 
 /* Replaces TerrainReferenceOutput, render_terrain.rs:285-299. */

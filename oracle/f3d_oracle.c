@@ -1224,15 +1224,46 @@ int f3do_render(const f3do_desc* d, f3do_out* out) {
         }
     }
 
+    /* AETHER post (render_terrain.rs:1246-1311): overwrites the RGBA16F output of the last frame with
+     * L_surface*T + L_inscatter resolved by the same Reinhard operator; AOVs are untouched. */
+    uint16_t* aether_out = NULL;
+    if (d->atmosphere) {
+        const char* bad = f3do_aether_validate(d->atmosphere);   /* AetherPostPass::new, aether_post.rs:58-65 */
+        if (bad) { result = fail(1, "%s", bad); goto done; }
+        f3do_aether_view V;
+        memset(&V, 0, sizeof V);
+        V.width = W; V.height = H;
+        V.cam_origin[0] = origin.x; V.cam_origin[1] = origin.y; V.cam_origin[2] = origin.z;
+        V.cam_right[0] = right.x; V.cam_right[1] = right.y; V.cam_right[2] = right.z;
+        V.cam_up[0] = up.x; V.cam_up[1] = up.y; V.cam_up[2] = up.z;
+        V.cam_forward[0] = forward.x; V.cam_forward[1] = forward.y; V.cam_forward[2] = forward.z;
+        V.tan_half_fov = tanf(0.5f * fov);                     /* (0.5 * fov_y_radians).tan(), aether_post.rs:139 */
+        V.aspect = (float)W / (float)H;
+        V.exposure = exposure;
+        V.light_dir[0] = U.light_dir.x; V.light_dir[1] = U.light_dir.y; V.light_dir[2] = U.light_dir.z;
+        V.sun_intensity = sun_intensity;
+        aether_out = (uint16_t*)malloc(npx * 4 * sizeof(uint16_t));
+        if (!aether_out) { result = fail(1, "oracle: out of memory"); goto done; }
+        if (f3do_aether_post(d->atmosphere, &V, B.accum, B.aov_depth, B.aov_vis, aether_out) != 0) {
+            free(aether_out);
+            result = fail(1, "AETHER post failed");
+            goto done;
+        }
+    }
+
     /* resolve: out_tex = reinhard(mean*exposure) as RGBA16F (hybrid_terrain_traversal.wgsl:576-579,
      * hybrid_kernel.wgsl:109-112), then f16 -> u8 (render_terrain.rs:1358-1366) */
     for (size_t i = 0; i < npx; i++) {
         const float* acc = B.accum + 4 * i;
         for (int c = 0; c < 3; c++) {
-            float mean = acc[c] / acc[3];
-            float exposed = mean * exposure;
-            float ldr = exposed / (1.0f + exposed);
-            float v = f3do_f16_to_f32(f3do_f32_to_f16(ldr));
+            float v;
+            if (aether_out) v = f3do_f16_to_f32(aether_out[4 * i + c]);
+            else {
+                float mean = acc[c] / acc[3];
+                float exposed = mean * exposure;
+                float ldr = exposed / (1.0f + exposed);
+                v = f3do_f16_to_f32(f3do_f32_to_f16(ldr));
+            }
             out->rgba[4 * i + c] = (uint8_t)(clampf(v, 0.0f, 1.0f) * 255.0f + 0.5f);
         }
         out->rgba[4 * i + 3] = 255;
@@ -1242,6 +1273,7 @@ int f3do_render(const f3do_desc* d, f3do_out* out) {
         }
         out->depth[i] = B.aov_depth[i];
     }
+    free(aether_out);
     if (out->accum) memcpy(out->accum, B.accum, npx * 4 * sizeof(float));
     out->frames = frames;
     out->variance = variance;

@@ -28,6 +28,29 @@
 extern "C" {
 #endif
 
+/* AETHER LUT handle as the post consumes it (AtmosphereLutHandle, src/core/atmosphere/runtime.rs:44-90;
+ * uniforms of src/path_tracing/hybrid_compute/aether_post.rs:10-23,131-178).  LUT payloads are RGBA16F texels,
+ * x fastest, then y, then z (write_texture layout, aether_post.rs:365-397). */
+typedef struct f3do_atmosphere {
+    const uint16_t* transmittance;    /* [height][mu] x 4 halves */
+    const uint16_t* scattering;       /* accumulated scattering, [height*nu + nu_i][mu_sun][mu_view] x 4 */
+    const uint16_t* aerial;           /* [height][mu_view][distance] x 4 (rgb = 0, a = mean transmittance) */
+    uint32_t transmittance_dims[2];   /* mu, height */
+    uint32_t scattering_dims[3];      /* mu_view, mu_sun, scattering_height * scattering_nu */
+    uint32_t scattering_height, scattering_nu;
+    uint32_t aerial_dims[3];          /* distance, mu_view, height */
+    float bottom_radius_m, top_radius_m, max_aerial_distance_m, ozone_du;
+    float mie_g, turbidity, rayleigh_scale_height_m, mie_scale_height_m, ground_albedo;
+} f3do_atmosphere;
+
+/* Camera / light block of PrometheusAetherUniforms (aether_post.rs:131-156). */
+typedef struct f3do_aether_view {
+    uint32_t width, height;
+    float cam_origin[3], cam_right[3], cam_up[3], cam_forward[3];
+    float tan_half_fov, aspect, exposure;
+    float light_dir[3], sun_intensity;
+} f3do_aether_view;
+
 /* Mirrors TerrainReferenceDesc, src/path_tracing/hybrid_compute/render_terrain.rs:239-282 */
 typedef struct f3do_desc {
     const float* heights;        /* row-major dem_h x dem_w */
@@ -53,6 +76,7 @@ typedef struct f3do_desc {
     uint32_t width, height, seed, spp, max_frames, min_frames;
     float variance_threshold;
     int32_t compat_512mib_gate;  /* 1 = enforce the reference's 512 MiB working-set gate */
+    const f3do_atmosphere* atmosphere;   /* AETHER aerial-perspective post (render_terrain.rs:262-265,1246-1311) or NULL */
 } f3do_desc;
 
 /* Mirrors TerrainReferenceOutput, render_terrain.rs:285-299 (+ ray counters). */
@@ -103,6 +127,14 @@ int f3do_trace_rays(const float* heights, uint32_t w, uint32_t h,
 int f3do_earth_curvature(int earth_model, double lat_deg, double sphere_radius_m,
                          int refraction_model, double k, double pressure_mbar, double temperature_c,
                          double azimuth_deg, float* inv_two_r_prime, uint32_t* enabled);
+
+/* AETHER aerial-perspective post (src/shaders/atmosphere/prometheus_aerial.wgsl:98-231) over a finished
+ * accumulation: accum W*H*4 (rgb sum, frame count), depth W*H (frame-0 AOV), visibility W*H (0/1), out W*H*4
+ * RGBA16F bit patterns (what textureStore writes).  f3do_aether_validate returns NULL or the reference's message. */
+int f3do_aether_post(const f3do_atmosphere* atm, const f3do_aether_view* view, const float* accum, const float* depth,
+                     const uint8_t* visibility, uint16_t* out_rgba16f);
+const char* f3do_aether_validate(const f3do_atmosphere* atm);
+float f3do_exp2(float x);   /* pinned exp2 (Cephes exp2f kernel) */
 
 /* Pinned elementary functions of the numerics contract (exposed for unit tests). */
 void  f3do_sincos(float x, float* s, float* c);

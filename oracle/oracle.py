@@ -24,6 +24,48 @@ class OracleError(RuntimeError):
     pass
 
 
+class _Atmosphere(C.Structure):
+    """f3do_atmosphere (oracle/f3d_oracle.h)."""
+    _fields_ = [
+        ("transmittance", C.POINTER(C.c_uint16)), ("scattering", C.POINTER(C.c_uint16)), ("aerial", C.POINTER(C.c_uint16)),
+        ("transmittance_dims", C.c_uint32 * 2), ("scattering_dims", C.c_uint32 * 3),
+        ("scattering_height", C.c_uint32), ("scattering_nu", C.c_uint32), ("aerial_dims", C.c_uint32 * 3),
+        ("bottom_radius_m", C.c_float), ("top_radius_m", C.c_float), ("max_aerial_distance_m", C.c_float),
+        ("ozone_du", C.c_float), ("mie_g", C.c_float), ("turbidity", C.c_float),
+        ("rayleigh_scale_height_m", C.c_float), ("mie_scale_height_m", C.c_float), ("ground_albedo", C.c_float),
+    ]
+
+
+class _AetherView(C.Structure):
+    """f3do_aether_view (oracle/f3d_oracle.h)."""
+    _fields_ = [
+        ("width", C.c_uint32), ("height", C.c_uint32),
+        ("cam_origin", C.c_float * 3), ("cam_right", C.c_float * 3), ("cam_up", C.c_float * 3), ("cam_forward", C.c_float * 3),
+        ("tan_half_fov", C.c_float), ("aspect", C.c_float), ("exposure", C.c_float),
+        ("light_dir", C.c_float * 3), ("sun_intensity", C.c_float),
+    ]
+
+
+def make_atmosphere(handle):
+    """LUT handle (anything with .config, .transmittance, .scattering, .aerial as RGBA16F uint16 arrays shaped
+    (height, mu, 4), (height*nu, mu_sun, mu_view, 4), (height, mu_view, distance, 4)) -> (f3do_atmosphere, keepalive)."""
+    t = np.ascontiguousarray(handle.transmittance, dtype=np.uint16)
+    s = np.ascontiguousarray(handle.scattering, dtype=np.uint16)
+    e = np.ascontiguousarray(handle.aerial, dtype=np.uint16)
+    a = _Atmosphere()
+    u16 = lambda arr: arr.ctypes.data_as(C.POINTER(C.c_uint16))
+    a.transmittance, a.scattering, a.aerial = u16(t), u16(s), u16(e)
+    a.transmittance_dims = (C.c_uint32 * 2)(t.shape[1], t.shape[0])
+    a.scattering_dims = (C.c_uint32 * 3)(s.shape[2], s.shape[1], s.shape[0])
+    a.aerial_dims = (C.c_uint32 * 3)(e.shape[2], e.shape[1], e.shape[0])
+    cfg = handle.config
+    a.scattering_height, a.scattering_nu = int(cfg.dimensions.scattering_height), int(cfg.dimensions.scattering_nu)
+    for name in ("bottom_radius_m", "top_radius_m", "max_aerial_distance_m", "ozone_du", "mie_g", "turbidity",
+                 "rayleigh_scale_height_m", "mie_scale_height_m", "ground_albedo"):
+        setattr(a, name, float(getattr(cfg, name)))
+    return a, [t, s, e, a]
+
+
 class _Desc(C.Structure):
     _fields_ = [
         ("heights", C.POINTER(C.c_float)), ("dem_w", C.c_uint32), ("dem_h", C.c_uint32),
@@ -43,6 +85,7 @@ class _Desc(C.Structure):
         ("width", C.c_uint32), ("height", C.c_uint32), ("seed", C.c_uint32), ("spp", C.c_uint32),
         ("max_frames", C.c_uint32), ("min_frames", C.c_uint32),
         ("variance_threshold", C.c_float), ("compat_512mib_gate", C.c_int32),
+        ("atmosphere", C.POINTER(_Atmosphere)),
     ]
 
 
@@ -66,7 +109,7 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (gcc, no FMA contraction)."""
-    src_mtime = max((_HERE / n).stat().st_mtime for n in ("f3d_oracle.c", "f3d_oracle.h", "Makefile"))
+    src_mtime = max((_HERE / n).stat().st_mtime for n in ("f3d_oracle.c", "f3d_aether_oracle.c", "f3d_oracle.h", "Makefile"))
     if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src_mtime:
         env = dict(os.environ)
         env.pop("CC", None)
@@ -107,6 +150,13 @@ def lib():
         L.f3do_f32_to_f16.restype = C.c_uint16
         L.f3do_f16_to_f32.argtypes = [C.c_uint16]
         L.f3do_f16_to_f32.restype = C.c_float
+        L.f3do_exp2.argtypes = [C.c_float]
+        L.f3do_exp2.restype = C.c_float
+        L.f3do_aether_post.argtypes = [C.POINTER(_Atmosphere), C.POINTER(_AetherView), C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_uint16)]
+        L.f3do_aether_post.restype = C.c_int
+        L.f3do_aether_validate.argtypes = [C.POINTER(_Atmosphere)]
+        L.f3do_aether_validate.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -129,7 +179,7 @@ def render(heightmap, width, height, cam=None, *, spacing=(1.0, 1.0), exaggerati
            max_frames=512, min_frames=32, variance_threshold=1e-3, seed=7, sun_color=None,
            observer_latitude_deg=0.0, observer_longitude_deg=0.0, earth_model="ellipsoid",
            sphere_radius_m=6371008.8, refraction_model="bennett", refraction_k=0.13,
-           pressure_mbar=1013.25, temperature_c=15.0, compat_512mib_gate=False, want_accum=False):
+           pressure_mbar=1013.25, temperature_c=15.0, compat_512mib_gate=False, want_accum=False, atmosphere=None):
     """Oracle render with the native seam's keyword surface; returns the reference's result dict
     (terrain_reference.rs:437-450) plus ray counters."""
     L = lib()
@@ -183,6 +233,10 @@ def render(heightmap, width, height, cam=None, *, spacing=(1.0, 1.0), exaggerati
     d.max_frames, d.min_frames = int(max_frames), int(min_frames)
     d.variance_threshold = float(variance_threshold)
     d.compat_512mib_gate = int(bool(compat_512mib_gate))
+    if atmosphere is not None:   # a resolved LUT handle (AETHER aerial-perspective post)
+        atm, atm_keep = make_atmosphere(atmosphere)
+        keep += atm_keep
+        d.atmosphere = C.pointer(atm)
 
     H, W = int(height), int(width)
     rgba = np.zeros((H, W, 4), np.uint8)
@@ -211,6 +265,40 @@ def render(heightmap, width, height, cam=None, *, spacing=(1.0, 1.0), exaggerati
     if acc is not None:
         res["accum"] = acc
     return res
+
+
+def aether_post(handle, accum, depth, visibility, *, cam_origin, cam_right, cam_up, cam_forward, tan_half_fov, aspect,
+                exposure, light_dir, sun_intensity):
+    """prometheus_aerial.wgsl `main` over given buffers -> (H, W, 4) RGBA16F bit patterns (uint16)."""
+    L = lib()
+    acc = np.ascontiguousarray(accum, np.float32)
+    H, W = acc.shape[:2]
+    dep = np.ascontiguousarray(depth, np.float32).reshape(H, W)
+    vis = np.ascontiguousarray(visibility, np.uint8).reshape(H, W)
+    atm, keep = make_atmosphere(handle)
+    v = _AetherView()
+    v.width, v.height = W, H
+    v.cam_origin = (C.c_float * 3)(*map(float, cam_origin))
+    v.cam_right = (C.c_float * 3)(*map(float, cam_right))
+    v.cam_up = (C.c_float * 3)(*map(float, cam_up))
+    v.cam_forward = (C.c_float * 3)(*map(float, cam_forward))
+    v.tan_half_fov, v.aspect, v.exposure = float(tan_half_fov), float(aspect), float(exposure)
+    v.light_dir = (C.c_float * 3)(*map(float, light_dir))
+    v.sun_intensity = float(sun_intensity)
+    out = np.zeros((H, W, 4), np.uint16)
+    bad = L.f3do_aether_validate(C.byref(atm))
+    if bad:
+        raise OracleError(bad.decode())
+    rc = L.f3do_aether_post(C.byref(atm), C.byref(v), _fp(acc), _fp(dep), vis.ctypes.data_as(C.POINTER(C.c_uint8)),
+                            out.ctypes.data_as(C.POINTER(C.c_uint16)))
+    if rc != 0:
+        raise OracleError("f3do_aether_post failed")
+    del keep
+    return out
+
+
+def exp2(x: float) -> float:
+    return float(lib().f3do_exp2(float(x)))
 
 
 def build_minmax(heights):

@@ -27,8 +27,8 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert sorted(_native.EXPORTS) == declared
     for name in declared:
         assert hasattr(L, name), f"{name} declared in the header but not exported"
-    assert L.f3d_abi_version() == 1
-    assert int(re.search(r"#define F3D_ABI_VERSION (\d+)", text).group(1)) == 1
+    assert L.f3d_abi_version() == 2
+    assert int(re.search(r"#define F3D_ABI_VERSION (\d+)", text).group(1)) == 2
 
 
 def test_struct_layout_matches_c():
@@ -37,17 +37,19 @@ def test_struct_layout_matches_c():
     #include <stddef.h>
     #include "forge3d_b200.h"
     int main(void) {
-      printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(f3d_terrain_desc), offsetof(f3d_terrain_desc, observer_lat_deg),
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(f3d_terrain_desc), offsetof(f3d_terrain_desc, observer_lat_deg),
              offsetof(f3d_terrain_desc, env_rgb), offsetof(f3d_terrain_desc, width), offsetof(f3d_terrain_desc, part_block_rows),
-             sizeof(f3d_terrain_out), offsetof(f3d_terrain_out, kernel_launches));
+             sizeof(f3d_terrain_out), offsetof(f3d_terrain_out, kernel_launches), offsetof(f3d_terrain_desc, atmosphere),
+             sizeof(f3d_atmosphere), offsetof(f3d_atmosphere, transmittance_mu), offsetof(f3d_atmosphere, ground_albedo));
       return 0; }'''
     tmp = Path("/tmp/f3d_layout.c")
     tmp.write_text(src)
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(tmp), "-o", "/tmp/f3d_layout"], check=True)
     vals = list(map(int, subprocess.run(["/tmp/f3d_layout"], check=True, capture_output=True, text=True).stdout.split()))
-    D, O = _native.TerrainDesc, _native.TerrainOut
+    D, O, A = _native.TerrainDesc, _native.TerrainOut, _native.Atmosphere
     assert vals == [C.sizeof(D), D.observer_lat_deg.offset, D.env_rgb.offset, D.width.offset, D.part_block_rows.offset,
-                    C.sizeof(O), O.kernel_launches.offset]
+                    C.sizeof(O), O.kernel_launches.offset, D.atmosphere.offset, C.sizeof(A), A.transmittance_mu.offset,
+                    A.ground_albedo.offset]
 
 
 def _build_c_consumer():
