@@ -39,6 +39,18 @@
 #ifndef F3D_ANYHIT_SIGN_ORDER
 #define F3D_ANYHIT_SIGN_ORDER 1
 #endif
+// F3D_PUSH_CLIP_FOLDED = 1 (default; 0 evaluates the WGSL's push test literally): the push test of :342-344 clips a
+//   child's span [c0, c1] to the PARENT's clipped span, ct = [max(c0, t_lo), min(c1, t_hi)], the pop test of :295-297
+//   clips it to the ray, tl/th = [max(c0, tmin), min(c1, min(tmax, best_t))].  They are the same two numbers:
+//   t_lo = max(n0, tmin) and t_hi = min(n1, min(tmax, best_t)) with [n0, n1] the parent's slab span, and c0 >= n0,
+//   c1 <= n1 hold EXACTLY in f32 because every slab plane is the same monotone expression
+//   ((origin + f32(cell) * spacing) - o) * inv of its integer cell coordinate (each rounding step preserves weak
+//   order) and the child's planes lie between the parent's.  Hence max(c0, t_lo) = max(c0, tmin) and
+//   min(c1, t_hi) = min(c1, tcap): one clipped span serves as push test, pop test and sort key, and the parent's own
+//   span is only needed when a stale closest-hit entry is re-tested.
+#ifndef F3D_PUSH_CLIP_FOLDED
+#define F3D_PUSH_CLIP_FOLDED 1
+#endif
 
 namespace f3d {
 
@@ -167,11 +179,17 @@ __device__ __forceinline__ void expand_top(const FastScene& S, TraceState& T, co
     const float b1 = ((S.oz + (float)cz1 * S.sz) - T.o.z) * T.inv_z;
     // this node's own clipped span (:288-297); needed to clip the children (:342-343)
     const float tcap = fminf(T.tmax, T.best_t);
+#if !F3D_PUSH_CLIP_FOLDED
     const float t_lo = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), T.tmin);
     const float t_hi = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), tcap);
+#endif
     if (!ANY_HIT) {
         if (T.sp < T.stale_sp) {              // entry predates the last hit: redo the pop tests (:297-304)
             T.stale_sp = T.sp;
+#if F3D_PUSH_CLIP_FOLDED
+            const float t_lo = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), T.tmin);
+            const float t_hi = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), tcap);
+#endif
             if (t_lo > t_hi) return;
             float2 mm;
             if (level == S.mip_count - 1u) mm = S.root_mm;
@@ -189,8 +207,12 @@ __device__ __forceinline__ void expand_top(const FastScene& S, TraceState& T, co
         const uint32_t cxi = c & 1u, cy = c >> 1;
         const float c0 = fmaxf(cxi ? xlo1 : xlo0, cy ? zlo1 : zlo0);
         const float c1 = fminf(cxi ? xhi1 : xhi0, cy ? zhi1 : zhi0);
-        const float ct_lo = fmaxf(c0, t_lo), ct_hi = fminf(c1, t_hi);     // push test (:342-344)
         const float tl = fmaxf(c0, T.tmin), th = fminf(c1, tcap);         // the child's own pop span (:295-297)
+#if F3D_PUSH_CLIP_FOLDED
+        const float ct_lo = tl, ct_hi = th;                               // == the push test's span, see above
+#else
+        const float ct_lo = fmaxf(c0, t_lo), ct_hi = fminf(c1, t_hi);     // push test (:342-344)
+#endif
         const float2 mm = c == 0u ? make_float2(q01.x, q01.y) : c == 1u ? make_float2(q01.z, q01.w)
                         : c == 2u ? make_float2(q23.x, q23.y) : make_float2(q23.z, q23.w);
         const bool exists = (cxi ? has_x1 : true) && (cy ? has_z1 : true);

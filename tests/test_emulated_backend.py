@@ -10,7 +10,7 @@ import _emu
 import _helpers as H
 from oracle import oracle
 
-VARIANTS = {"default": (), "anyhit_sorted": ("F3D_ANYHIT_SIGN_ORDER=0",)}
+VARIANTS = {"default": (), "anyhit_sorted": ("F3D_ANYHIT_SIGN_ORDER=0",), "literal_push_clip": ("F3D_PUSH_CLIP_FOLDED=0",)}
 
 
 def _bits(a):
