@@ -52,6 +52,26 @@ def make_atmosphere(handle) -> tuple:
     return a, [handle, a]
 
 
+class SmokeVolume(C.Structure):
+    """f3d_smoke_volume (include/forge3d_b200.h)."""
+    _fields_ = [
+        ("dims", C.c_uint32 * 3), ("voxel_size", C.c_float * 3), ("origin", C.c_float * 3),
+        ("density", C.POINTER(C.c_float)), ("temperature", C.POINTER(C.c_float)), ("soot", C.POINTER(C.c_float)),
+        ("humidity", C.POINTER(C.c_float)), ("emission_rate", C.POINTER(C.c_float)), ("particle_age", C.POINTER(C.c_float)),
+        ("frame_index", C.c_uint64),
+    ]
+
+
+class SmokeSettings(C.Structure):
+    """f3d_smoke_settings (include/forge3d_b200.h)."""
+    _fields_ = [
+        ("density_scale", C.c_float), ("extinction", C.c_float), ("scattering", C.c_float), ("absorption", C.c_float),
+        ("phase_g", C.c_float), ("step_size", C.c_float), ("max_steps", C.c_uint32), ("self_shadow", C.c_int32),
+        ("shadow_steps", C.c_uint32), ("shadow_step_size", C.c_float), ("jitter_strength", C.c_float), ("exposure", C.c_float),
+        ("thin_color", C.c_float * 3), ("dense_color", C.c_float * 3), ("soot_absorption", C.c_float), ("fire_glow", C.c_float),
+    ]
+
+
 class TerrainDesc(C.Structure):
     """f3d_terrain_desc (include/forge3d_b200.h)."""
     _fields_ = [
@@ -99,6 +119,7 @@ EXPORTS = [
     "f3d_session_resolve_device", "f3d_session_validity", "f3d_session_resolve_host", "f3d_session_frames",
     "f3d_session_stats", "f3d_session_sync", "f3d_session_last_frames_ms", "f3d_session_destroy",
     "f3d_session_ipc_export", "f3d_session_ipc_import", "f3d_trace_rays", "f3d_build_minmax",
+    "f3d_smoke_create", "f3d_smoke_destroy", "f3d_smoke_raymarch_rgba", "f3d_smoke_raymarch_projection_rgba",
 ]
 
 _lib = None
@@ -135,6 +156,14 @@ def lib():
                                  fp, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, u8p, fp, fp,
                                  C.POINTER(C.c_uint64)]
     L.f3d_build_minmax.argtypes = [fp, C.c_uint32, C.c_uint32, C.c_int32, u32p, fp, C.c_uint64]
+    f3 = C.c_float * 3
+    L.f3d_smoke_create.argtypes = [C.POINTER(SmokeVolume), C.c_int32, C.POINTER(vp)]
+    L.f3d_smoke_destroy.argtypes = [vp]
+    L.f3d_smoke_destroy.restype = None
+    L.f3d_smoke_raymarch_rgba.argtypes = [vp, C.POINTER(SmokeSettings), C.c_uint32, C.c_uint32, f3, f3, f3, C.c_float, f3, u8p,
+                                          C.POINTER(C.c_double)]
+    L.f3d_smoke_raymarch_projection_rgba.argtypes = [vp, C.POINTER(SmokeSettings), C.c_uint32, C.c_uint32, f3, f3, u8p,
+                                                     C.POINTER(C.c_double)]
     for name in EXPORTS:   # fail at load time, not at first call, if the ABI drifted
         getattr(L, name)
     _lib = L

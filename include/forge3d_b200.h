@@ -180,6 +180,43 @@ int f3d_trace_rays(const float* heights, uint32_t dem_w, uint32_t dem_h, const f
 int f3d_build_minmax(const float* heights, uint32_t dem_w, uint32_t dem_h, int32_t device,
                      uint32_t* dims, float* levels_out, uint64_t levels_capacity_floats);
 
+/* ---- smoke volume ray-march (BASELINE config 4) ----
+ * Replaces SmokeVolume::raymarch_rgba / raymarch_projection_rgba, /root/reference/src/smoke/render.rs:6-175 (the
+ * reference runs them single-threaded on the CPU behind PySmokeDomain.render_rgba / render_projection_rgba,
+ * src/smoke/py.rs:531-628).  The volume is uploaded once and stays resident; a render is one kernel launch. */
+typedef struct f3d_smoke_volume {     /* SmokeVolume + SmokeDomainConfig, src/smoke/types.rs:8-14,331-345 */
+    uint32_t dims[3];                  /* x, y, z (each >= 2); voxel (x, y, z) at (z * dims[1] + y) * dims[0] + x */
+    float voxel_size[3], origin[3];
+    const float* density;              /* host, required */
+    const float* temperature;          /* host; the remaining fields may be NULL = all zero */
+    const float* soot;
+    const float* humidity;
+    const float* emission_rate;
+    const float* particle_age;
+    uint64_t frame_index;              /* seeds the per-pixel march jitter (render.rs:76-79) */
+} f3d_smoke_volume;
+
+typedef struct f3d_smoke_settings {   /* SmokeRenderSettings, src/smoke/types.rs:225-266 (defaults there) */
+    float density_scale, extinction, scattering, absorption, phase_g, step_size;
+    uint32_t max_steps;
+    int32_t self_shadow;
+    uint32_t shadow_steps;
+    float shadow_step_size, jitter_strength, exposure;
+    float thin_color[3], dense_color[3];
+    float soot_absorption, fire_glow;
+} f3d_smoke_settings;
+
+typedef struct f3d_smoke f3d_smoke;
+int f3d_smoke_create(const f3d_smoke_volume* volume, int32_t device, f3d_smoke** out);
+void f3d_smoke_destroy(f3d_smoke* s);
+/* rgba: host, height * width * 4, caller allocated.  *kernel_ms (may be NULL) = device time of the march kernel. */
+int f3d_smoke_raymarch_rgba(f3d_smoke* s, const f3d_smoke_settings* settings, uint32_t width, uint32_t height,
+                            const float camera_pos[3], const float target[3], const float up[3], float fovy_deg,
+                            const float sun_direction[3], uint8_t* rgba, double* kernel_ms);
+int f3d_smoke_raymarch_projection_rgba(f3d_smoke* s, const f3d_smoke_settings* settings, uint32_t width, uint32_t height,
+                                       const float view_direction[3], const float sun_direction[3], uint8_t* rgba,
+                                       double* kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,6 +136,39 @@ int f3do_aether_post(const f3do_atmosphere* atm, const f3do_aether_view* view, c
 const char* f3do_aether_validate(const f3do_atmosphere* atm);
 float f3do_exp2(float x);   /* pinned exp2 (Cephes exp2f kernel) */
 
+/* ---- smoke volume ray-march (src/smoke/render.rs) ---- */
+typedef struct f3do_smoke_volume {
+    uint32_t dims[3];                  /* x, y, z; voxel (x, y, z) at (z * dims[1] + y) * dims[0] + x (sampling.rs:83-85) */
+    float voxel_size[3], origin[3];
+    const float* density;              /* any field may be NULL = all zero */
+    const float* temperature;
+    const float* soot;
+    const float* humidity;
+    const float* emission_rate;
+    const float* particle_age;
+    uint64_t frame_index;
+} f3do_smoke_volume;
+
+typedef struct f3do_smoke_settings {   /* SmokeRenderSettings, src/smoke/types.rs:225-266 */
+    float density_scale, extinction, scattering, absorption, phase_g, step_size;
+    uint32_t max_steps;
+    int32_t self_shadow;
+    uint32_t shadow_steps;
+    float shadow_step_size, jitter_strength, exposure;
+    float thin_color[3], dense_color[3];
+    float soot_absorption, fire_glow;
+} f3do_smoke_settings;
+
+/* 0 = ok, 1 = error (reference message via f3do_smoke_last_error).  rgba: height x width x 4, caller allocated. */
+int f3do_smoke_raymarch_rgba(const f3do_smoke_volume* vol, const f3do_smoke_settings* settings, uint32_t width, uint32_t height,
+                             const float camera_pos[3], const float target[3], const float up[3], float fovy_deg,
+                             const float sun_direction[3], uint8_t* rgba);
+int f3do_smoke_raymarch_projection_rgba(const f3do_smoke_volume* vol, const f3do_smoke_settings* settings, uint32_t width,
+                                        uint32_t height, const float view_direction[3], const float sun_direction[3], uint8_t* rgba);
+float f3do_smoke_sun_transmittance(const f3do_smoke_volume* vol, const f3do_smoke_settings* settings, const float start[3],
+                                   const float sun_dir[3], float step, uint32_t steps);
+const char* f3do_smoke_last_error(void);
+
 /* Pinned elementary functions of the numerics contract (exposed for unit tests). */
 void  f3do_sincos(float x, float* s, float* c);
 float f3do_atan2(float y, float x);

@@ -109,7 +109,7 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (gcc, no FMA contraction)."""
-    src_mtime = max((_HERE / n).stat().st_mtime for n in ("f3d_oracle.c", "f3d_aether_oracle.c", "f3d_oracle.h", "Makefile"))
+    src_mtime = max((_HERE / n).stat().st_mtime for n in ("f3d_oracle.c", "f3d_aether_oracle.c", "f3d_smoke_oracle.c", "f3d_oracle.h", "Makefile"))
     if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src_mtime:
         env = dict(os.environ)
         env.pop("CC", None)
@@ -293,6 +293,112 @@ def aether_post(handle, accum, depth, visibility, *, cam_origin, cam_right, cam_
                             out.ctypes.data_as(C.POINTER(C.c_uint16)))
     if rc != 0:
         raise OracleError("f3do_aether_post failed")
+    del keep
+    return out
+
+
+class _SmokeVolume(C.Structure):
+    """f3do_smoke_volume (oracle/f3d_oracle.h)."""
+    _fields_ = [
+        ("dims", C.c_uint32 * 3), ("voxel_size", C.c_float * 3), ("origin", C.c_float * 3),
+        ("density", C.POINTER(C.c_float)), ("temperature", C.POINTER(C.c_float)), ("soot", C.POINTER(C.c_float)),
+        ("humidity", C.POINTER(C.c_float)), ("emission_rate", C.POINTER(C.c_float)), ("particle_age", C.POINTER(C.c_float)),
+        ("frame_index", C.c_uint64),
+    ]
+
+
+class _SmokeSettings(C.Structure):
+    """f3do_smoke_settings (oracle/f3d_oracle.h)."""
+    _fields_ = [
+        ("density_scale", C.c_float), ("extinction", C.c_float), ("scattering", C.c_float), ("absorption", C.c_float),
+        ("phase_g", C.c_float), ("step_size", C.c_float), ("max_steps", C.c_uint32), ("self_shadow", C.c_int32),
+        ("shadow_steps", C.c_uint32), ("shadow_step_size", C.c_float), ("jitter_strength", C.c_float), ("exposure", C.c_float),
+        ("thin_color", C.c_float * 3), ("dense_color", C.c_float * 3), ("soot_absorption", C.c_float), ("fire_glow", C.c_float),
+    ]
+
+
+_SMOKE_FIELDS = ("density", "temperature", "soot", "humidity", "emission_rate", "particle_age")
+_SMOKE_SCALARS = ("density_scale", "extinction", "scattering", "absorption", "phase_g", "step_size", "shadow_step_size",
+                  "jitter_strength", "exposure", "soot_absorption", "fire_glow")
+
+
+def _smoke_structs(domain, settings):
+    """domain: .dims (x, y, z), .voxel_size, .origin, .frame_index and the six (z, y, x) float32 fields (None = zero);
+    settings: an object with SmokeRenderSettings' attributes."""
+    v = _SmokeVolume()
+    v.dims = (C.c_uint32 * 3)(*map(int, domain.dims))
+    v.voxel_size = (C.c_float * 3)(*map(float, domain.voxel_size))
+    v.origin = (C.c_float * 3)(*map(float, domain.origin))
+    keep = []
+    for name in _SMOKE_FIELDS:
+        arr = getattr(domain, name, None)
+        if arr is None:
+            continue
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        keep.append(a)
+        setattr(v, name, _fp(a))
+    v.frame_index = int(getattr(domain, "frame_index", 0))
+    s = _SmokeSettings()
+    for name in _SMOKE_SCALARS:
+        setattr(s, name, float(getattr(settings, name)))
+    s.max_steps, s.shadow_steps, s.self_shadow = int(settings.max_steps), int(settings.shadow_steps), int(bool(settings.self_shadow))
+    s.thin_color = (C.c_float * 3)(*map(float, settings.thin_color))
+    s.dense_color = (C.c_float * 3)(*map(float, settings.dense_color))
+    return v, s, keep
+
+
+def _smoke_lib():
+    L = lib()
+    if not getattr(L, "_smoke_ready", False):
+        f3 = C.c_float * 3
+        u8p = C.POINTER(C.c_uint8)
+        L.f3do_smoke_raymarch_rgba.argtypes = [C.POINTER(_SmokeVolume), C.POINTER(_SmokeSettings), C.c_uint32, C.c_uint32, f3, f3, f3,
+                                               C.c_float, f3, u8p]
+        L.f3do_smoke_raymarch_projection_rgba.argtypes = [C.POINTER(_SmokeVolume), C.POINTER(_SmokeSettings), C.c_uint32,
+                                                          C.c_uint32, f3, f3, u8p]
+        L.f3do_smoke_sun_transmittance.argtypes = [C.POINTER(_SmokeVolume), C.POINTER(_SmokeSettings), f3, f3, C.c_float, C.c_uint32]
+        L.f3do_smoke_sun_transmittance.restype = C.c_float
+        L.f3do_smoke_last_error.restype = C.c_char_p
+        L._smoke_ready = True
+    return L
+
+
+def smoke_raymarch_rgba(domain, settings, width, height, camera_pos, target, up=(0.0, 1.0, 0.0), fovy_deg=45.0,
+                        sun_direction=(0.4, 0.8, -0.2)):
+    """SmokeVolume::raymarch_rgba (src/smoke/render.rs:6-101) -> (height, width, 4) uint8."""
+    L = _smoke_lib()
+    v, s, keep = _smoke_structs(domain, settings)
+    out = np.zeros((int(height), int(width), 4), np.uint8)
+    f3 = C.c_float * 3
+    rc = L.f3do_smoke_raymarch_rgba(C.byref(v), C.byref(s), int(width), int(height), f3(*map(float, camera_pos)),
+                                    f3(*map(float, target)), f3(*map(float, up)), float(fovy_deg), f3(*map(float, sun_direction)),
+                                    out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    if rc != 0:
+        raise OracleError(L.f3do_smoke_last_error().decode())
+    del keep
+    return out
+
+
+def smoke_raymarch_projection_rgba(domain, settings, width, height, view_direction=(0.0, -1.0, 0.0), sun_direction=(0.4, 0.8, -0.2)):
+    """SmokeVolume::raymarch_projection_rgba (src/smoke/render.rs:103-175) -> (height, width, 4) uint8."""
+    L = _smoke_lib()
+    v, s, keep = _smoke_structs(domain, settings)
+    out = np.zeros((int(height), int(width), 4), np.uint8)
+    f3 = C.c_float * 3
+    rc = L.f3do_smoke_raymarch_projection_rgba(C.byref(v), C.byref(s), int(width), int(height), f3(*map(float, view_direction)),
+                                               f3(*map(float, sun_direction)), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    if rc != 0:
+        raise OracleError(L.f3do_smoke_last_error().decode())
+    del keep
+    return out
+
+
+def smoke_sun_transmittance(domain, settings, start, sun_dir, step, steps):
+    """SmokeVolume::sun_transmittance (src/smoke/render.rs:278-316)."""
+    L = _smoke_lib()
+    v, s, keep = _smoke_structs(domain, settings)
+    f3 = C.c_float * 3
+    out = float(L.f3do_smoke_sun_transmittance(C.byref(v), C.byref(s), f3(*map(float, start)), f3(*map(float, sun_dir)), float(step), int(steps)))
     del keep
     return out
 

@@ -37,6 +37,8 @@ def test_struct_layout_matches_c():
     #include <stddef.h>
     #include "forge3d_b200.h"
     int main(void) {
+      printf("%zu %zu %zu %zu ", sizeof(f3d_smoke_volume), offsetof(f3d_smoke_volume, frame_index), sizeof(f3d_smoke_settings),
+             offsetof(f3d_smoke_settings, soot_absorption));
       printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(f3d_terrain_desc), offsetof(f3d_terrain_desc, observer_lat_deg),
              offsetof(f3d_terrain_desc, env_rgb), offsetof(f3d_terrain_desc, width), offsetof(f3d_terrain_desc, part_block_rows),
              sizeof(f3d_terrain_out), offsetof(f3d_terrain_out, kernel_launches), offsetof(f3d_terrain_desc, atmosphere),
@@ -47,6 +49,9 @@ def test_struct_layout_matches_c():
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(tmp), "-o", "/tmp/f3d_layout"], check=True)
     vals = list(map(int, subprocess.run(["/tmp/f3d_layout"], check=True, capture_output=True, text=True).stdout.split()))
     D, O, A = _native.TerrainDesc, _native.TerrainOut, _native.Atmosphere
+    SV, SS = _native.SmokeVolume, _native.SmokeSettings
+    assert vals[:4] == [C.sizeof(SV), SV.frame_index.offset, C.sizeof(SS), SS.soot_absorption.offset]
+    vals = vals[4:]
     assert vals == [C.sizeof(D), D.observer_lat_deg.offset, D.env_rgb.offset, D.width.offset, D.part_block_rows.offset,
                     C.sizeof(O), O.kernel_launches.offset, D.atmosphere.offset, C.sizeof(A), A.transmittance_mu.offset,
                     A.ground_albedo.offset]

@@ -1,0 +1,204 @@
+"""Smoke volume ray-march (BASELINE config 4), CPU suite: the oracle pinned (a) arithmetically against an
+independent restatement of the Rust source and (b) against the properties the reference's own unit tests assert on the same scenes
+(src/smoke/render.rs:408-592), the host-side contract of forge3d_b200.smoke, and the product's CUDA source (k_smoke_pack,
+k_smoke_march + host driver) run under the SIMT interpreter against the oracle.  The -m gpu test makes the same comparison on the
+device through the public API."""
+import numpy as np
+import pytest
+
+import _emu
+import _rust_mirror_smoke as M
+from forge3d_b200.smoke import SmokeDomain, SmokeEmitter, SmokeRenderSettings
+from oracle import oracle
+
+
+def _box_domain(dims, lo, hi, density, **other):
+    dom = SmokeDomain(dims)
+    sl = (slice(lo[2], hi[2]), slice(lo[1], hi[1]), slice(lo[0], hi[0]))
+    d = np.zeros(dom.density.shape, np.float32)
+    d[sl] = density
+    dom.set_density(d)
+    dom.particle_age[...] = -1.0                      # the reference test writes the fields directly (age stays -1)
+    for name, value in other.items():
+        a = np.zeros(dom.density.shape, np.float32)
+        a[sl] = value
+        dom.set_field(name, a)
+    return dom
+
+
+def _random_domain(seed, dims=(20, 14, 17), voxel=(1.5, 0.8, 1.1), origin=(-7.0, 2.0, 30.0), frame_index=0):
+    rng = np.random.default_rng(seed)
+    dom = SmokeDomain(dims, voxel, origin)
+    shape = dom.density.shape
+    zz, yy, xx = np.indices(shape, dtype=np.float32)
+    blob = np.exp(-(((xx - dims[0] * 0.45) / 5.0) ** 2 + ((yy - dims[1] * 0.5) / 3.5) ** 2 + ((zz - dims[2] * 0.55) / 4.5) ** 2))
+    dom.set_density((blob * rng.uniform(0.3, 1.6, shape)).astype(np.float32) * (blob > 0.08))
+    dom.set_field("temperature", (blob * rng.uniform(0.0, 2.0, shape)).astype(np.float32))
+    dom.set_field("soot", (blob * rng.uniform(0.0, 0.6, shape)).astype(np.float32))
+    dom.set_field("humidity", rng.uniform(0.0, 1.3, shape).astype(np.float32))
+    dom.set_field("emission_rate", (blob * rng.uniform(0.0, 1.5, shape) * (rng.uniform(size=shape) < 0.3)).astype(np.float32))
+    dom.set_field("particle_age", np.where(dom.density > 1e-5, rng.uniform(0.0, 25.0, shape), -1.0).astype(np.float32))
+    dom.frame_index = frame_index
+    return dom
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle pin (b): the reference's own unit tests (src/smoke/render.rs:408-592)
+# ---------------------------------------------------------------------------------------------------------------
+def test_projected_raymarch_returns_map_aligned_smoke_layer():
+    dom = SmokeDomain((18, 12, 14))
+    dom.add_emitter(SmokeEmitter(center=(8.0, 4.0, 7.0), radius=3.5, density_rate=5.0, temperature_rate=0.8), 1.0)
+    rgba = oracle.smoke_raymarch_projection_rgba(dom, SmokeRenderSettings(), 36, 28, (0.0, -1.0, 0.0), (0.4, 0.8, -0.2))
+    assert rgba.shape == (28, 36, 4) and (rgba[..., 3] > 0).any()
+    ys, xs = np.nonzero(rgba[..., 3] > 128)          # map-aligned: the layer sits over the emitter's (x, z) footprint
+    assert abs(xs.mean() / 36 * 18 - 8.0) < 1.0 and abs(ys.mean() / 28 * 14 - 7.0) < 1.0
+
+
+def test_perspective_raymarch_returns_nonblank_smoke_layer():
+    dom = SmokeDomain((16, 16, 16))
+    dom.add_emitter(SmokeEmitter(center=(8.0, 8.0, 8.0), radius=4.0, density_rate=4.0, temperature_rate=1.0), 1.0)
+    rgba = oracle.smoke_raymarch_rgba(dom, SmokeRenderSettings(), 32, 32, (8.0, 8.0, -18.0), (8.0, 8.0, 8.0), (0.0, 1.0, 0.0), 45.0,
+                                      (0.4, 0.8, -0.2))
+    assert rgba.shape == (32, 32, 4) and (rgba[..., 3] > 0).any() and rgba[16, 16, 3] > 200 and rgba[0, 0, 3] == 0
+
+
+def test_sun_transmittance_tracks_volume_self_shadowing():
+    dom = _box_domain((24, 12, 12), (8, 3, 3), (14, 9, 9), 1.2, soot=0.18)
+    st = SmokeRenderSettings(density_scale=1.4, extinction=1.8, shadow_steps=48, shadow_step_size=0.5)
+    lit = oracle.smoke_sun_transmittance(dom, st, (15.0, 6.0, 6.0), (1.0, 0.0, 0.0), 0.5, st.shadow_steps)
+    occluded = oracle.smoke_sun_transmittance(dom, st, (15.0, 6.0, 6.0), (-1.0, 0.0, 0.0), 0.5, st.shadow_steps)
+    assert lit > 0.95 and occluded < 0.35
+
+
+def test_raymarch_emission_adds_warm_source_radiance():
+    st = SmokeRenderSettings(density_scale=1.2, extinction=1.25, fire_glow=1.25, exposure=1.15)
+    args = (32, 32, (8.0, 8.0, -18.0), (8.0, 8.0, 8.0), (0.0, 1.0, 0.0), 45.0, (0.3, 0.8, -0.2))
+    hot = oracle.smoke_raymarch_rgba(_box_domain((16, 16, 16), (5, 5, 5), (11, 11, 11), 0.55, temperature=0.85, emission_rate=1.4), st, *args)
+    cold = oracle.smoke_raymarch_rgba(_box_domain((16, 16, 16), (5, 5, 5), (11, 11, 11), 0.55), st, *args)
+    warm = lambda im: int((im[..., 0].astype(np.int16) - im[..., 2].astype(np.int16)).max())
+    assert warm(hot) > warm(cold) + 12 and int(hot[..., 0].max()) > int(cold[..., 0].max())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle pin (a): independent restatement of the Rust source, bit for bit
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,settings", [
+    (1, {}),
+    (2, dict(self_shadow=False, jitter_strength=1.0, phase_g=-0.6, exposure=2.5, fire_glow=2.0, step_size=0.9)),
+    (3, dict(density_scale=3.0, extinction=4.0, soot_absorption=1.5, shadow_steps=7, shadow_step_size=0.4, max_steps=40, jitter_strength=0.0)),
+])
+def test_oracle_matches_the_rust_mirror_bit_for_bit(seed, settings):
+    dom = _random_domain(seed, frame_index=seed * 1000003)
+    st = SmokeRenderSettings(**settings)
+    V = M.Volume(dom)
+    W, Hh = 14, 10
+    cam, target, up, fov, sun = (-20.0, 14.0, 5.0), (8.0, 7.0, 40.0), (0.1, 1.0, 0.0), 38.0, (0.4, 0.8, -0.2)
+    got = oracle.smoke_raymarch_rgba(dom, st, W, Hh, cam, target, up, fov, sun)
+    proj = oracle.smoke_raymarch_projection_rgba(dom, st, W, Hh, (0.2, -1.0, 0.1), sun)
+    with np.errstate(all="ignore"):
+        for y in range(0, Hh, 2):
+            for x in range(W):
+                assert list(got[y, x]) == M.perspective_pixel(V, st, W, Hh, x, y, cam, target, up, fov, sun), (x, y)
+                assert list(proj[y, x]) == M.projection_pixel(V, st, W, Hh, x, y, (0.2, -1.0, 0.1), sun), (x, y)
+    assert (got[..., 3] > 0).sum() > 20 and (proj[..., 3] > 0).sum() > 20 and len(np.unique(got[..., :3])) > 30
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host contract (src/smoke/types.rs validation text, src/smoke/py.rs signatures)
+# ---------------------------------------------------------------------------------------------------------------
+def test_settings_and_domain_validation_contract():
+    for kw, msg in [(dict(phase_g=1.0), r"phase_g must be in \[-0.99, 0.99\]"), (dict(max_steps=0), "max_steps and shadow_steps must be >= 1"),
+                    (dict(extinction=-1.0), "density_scale, extinction, and scattering must be >= 0"),
+                    (dict(jitter_strength=1.5), r"jitter_strength must be in \[0, 1\]"), (dict(exposure=float("nan")), "exposure must be finite"),
+                    (dict(thin_color=(0.1, -0.2, 0.3)), r"thin_color\[1\] must be finite and >= 0"), (dict(step_size=-0.1), "step sizes must be >= 0")]:
+        with pytest.raises(ValueError, match=msg):
+            SmokeRenderSettings(**kw)
+    with pytest.raises(ValueError, match=r"dims\[1\] must be >= 2"):
+        SmokeDomain((4, 1, 4))
+    with pytest.raises(ValueError, match=r"voxel_size\[2\] must be finite and > 0"):
+        SmokeDomain((4, 4, 4), voxel_size=(1.0, 1.0, 0.0))
+    dom = SmokeDomain.from_density(np.ones((5, 4, 3), np.float32), voxel_size=(2.0, 1.0, 1.0))
+    assert dom.dims == (3, 4, 5) and dom.voxel_size == (2.0, 1.0, 1.0) and (dom.to_particle_age_numpy() == 0.0).all()
+    with pytest.raises(ValueError, match="does not match voxel_count"):
+        dom.set_density(np.ones((5, 4, 4), np.float32))
+    with pytest.raises(ValueError, match="non-finite"):
+        dom.set_density(np.full((5, 4, 3), np.inf, np.float32))
+    with pytest.raises(NotImplementedError):
+        dom.step()
+    st = SmokeRenderSettings()
+    for bad, msg in [(dict(fovy_deg=179.5), r"fovy_deg must be finite and in \(0, 179\)"), (dict(target=(0.0, 0.0, -9.0)), "camera_pos and target must not be equal"),
+                     (dict(up=(0.0, 0.0, 0.0)), "up vector must not be zero"), (dict(sun_direction=(0.0, 0.0, 0.0)), "sun_direction must not be zero")]:
+        kw = dict(camera_pos=(0.0, 0.0, -9.0), target=(1.0, 1.0, 1.0), up=(0.0, 1.0, 0.0), fovy_deg=45.0, sun_direction=(0.4, 0.8, -0.2))
+        kw.update(bad)
+        with pytest.raises(oracle.OracleError, match=msg):
+            oracle.smoke_raymarch_rgba(dom, st, 8, 8, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the product's CUDA source under the SIMT interpreter vs the oracle
+# ---------------------------------------------------------------------------------------------------------------
+CASES = {
+    "defaults": (11, {}, dict(camera_pos=(-20.0, 14.0, 5.0), target=(8.0, 7.0, 40.0))),
+    "no_shadow_full_jitter": (12, dict(self_shadow=False, jitter_strength=1.0, phase_g=-0.6, exposure=2.5, fire_glow=2.0, step_size=0.9),
+                              dict(camera_pos=(5.0, 8.0, 38.0), target=(9.0, 6.0, 45.0), fovy_deg=70.0)),     # camera inside the volume
+    "dense_short_march": (13, dict(density_scale=3.0, extinction=4.0, soot_absorption=1.5, shadow_steps=7, shadow_step_size=0.4, max_steps=40,
+                                   jitter_strength=0.0), dict(camera_pos=(8.0, 40.0, 40.0), target=(8.0, 0.0, 40.5), up=(0.0, 0.0, 1.0))),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_emulated_cuda_march_is_bit_identical_to_the_oracle(case):
+    seed, skw, cam = CASES[case]
+    dom = _random_domain(seed, frame_index=7 * seed)
+    st = SmokeRenderSettings(**skw)
+    W, Hh = 45, 27                                              # not a multiple of the 16 x 8 CTA tile
+    o = oracle.smoke_raymarch_rgba(dom, st, W, Hh, **cam)
+    op = oracle.smoke_raymarch_projection_rgba(dom, st, 31, 22, (0.2, -1.0, 0.1), (0.3, 0.7, 0.2))
+    with _emu.emulated_backend():
+        g = dom.render_rgba(W, Hh, settings=st, **cam)
+        gp = dom.render_projection_rgba(31, 22, (0.2, -1.0, 0.1), (0.3, 0.7, 0.2), settings=st)
+        dom.frame_index += 1                                    # a new frame re-seeds the jitter (and re-uploads)
+        g_next = dom.render_rgba(W, Hh, settings=st, **cam)
+        dom.close()
+    assert np.array_equal(g, o) and np.array_equal(gp, op)
+    assert np.array_equal(g_next, oracle.smoke_raymarch_rgba(dom, st, W, Hh, **cam))
+    assert (o[..., 3] > 0).sum() > 100 and (op[..., 3] > 0).sum() > 100
+    if st.jitter_strength > 0:
+        assert not np.array_equal(g_next, g)
+
+
+def test_emulated_native_validation_and_missing_fields():
+    dom = SmokeDomain.from_density(np.full((6, 5, 4), 0.5, np.float32))
+    st = SmokeRenderSettings()
+    with _emu.emulated_backend() as native:
+        with pytest.raises(RuntimeError, match=r"fovy_deg must be finite and in \(0, 179\)"):
+            dom.render_rgba(8, 8, (0.0, 0.0, -9.0), (2.0, 2.0, 3.0), fovy_deg=0.0)
+        with pytest.raises(RuntimeError, match="view_direction must not be zero"):
+            dom.render_projection_rgba(8, 8, (0.0, 0.0, 0.0))
+        object.__setattr__(st, "phase_g", 2.0)                  # skip the Python check: exercise the C ABI's own
+        with pytest.raises(RuntimeError, match=r"phase_g must be in \[-0.99, 0.99\]"):
+            dom.render_rgba(8, 8, (0.0, 0.0, -9.0), (2.0, 2.0, 3.0), settings=st)
+        g = dom.render_rgba(24, 16, (-6.0, 4.0, -9.0), (2.0, 2.5, 3.0))
+        dom.close()
+    assert np.array_equal(g, oracle.smoke_raymarch_rgba(dom, SmokeRenderSettings(), 24, 16, (-6.0, 4.0, -9.0), (2.0, 2.5, 3.0)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU parity proper (run on the B200 box)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(CASES) + ["large"])
+def test_gpu_march_is_bit_identical_to_the_oracle(case):
+    if case == "large":                                          # 96 x 64 x 80 voxels, 320 x 200 px: ~10 s of oracle time
+        dom = _random_domain(21, dims=(96, 64, 80), voxel=(0.5, 0.4, 0.45), origin=(-20.0, 0.0, 10.0), frame_index=5)
+        st, cam, (W, Hh) = SmokeRenderSettings(), dict(camera_pos=(-45.0, 30.0, -10.0), target=(4.0, 12.0, 28.0)), (320, 200)
+    else:
+        seed, skw, cam = CASES[case]
+        dom, st, (W, Hh) = _random_domain(seed, frame_index=7 * seed), SmokeRenderSettings(**skw), (90, 54)
+    o = oracle.smoke_raymarch_rgba(dom, st, W, Hh, **cam)
+    op = oracle.smoke_raymarch_projection_rgba(dom, st, W, Hh, (0.2, -1.0, 0.1), (0.3, 0.7, 0.2))
+    g = dom.render_rgba(W, Hh, settings=st, **cam)
+    gp = dom.render_projection_rgba(W, Hh, (0.2, -1.0, 0.1), (0.3, 0.7, 0.2), settings=st)
+    dom.close()
+    assert np.array_equal(g, o) and np.array_equal(gp, op)
+    assert (o[..., 3] > 0).sum() > 100 and dom.last_kernel_ms > 0.0
