@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Side bench for the smoke volume ray-march (BASELINE config 4 shape: 1920x1080 perspective frame over a
+dense plume).  NOT the driver's bench (bench.py measures the headline terrain path); prints one JSON line in the same spirit:
+
+  value         Mpixels/s of k_smoke_march with the volume resident (CUDA events inside the library, best of --steps)
+  e2e           the public call SmokeDomain.render_rgba with host numpy fields: upload + pack + march + D2H
+  cpu_baseline  the CPU oracle (port of src/smoke/render.rs, which the reference runs single-threaded) on a bounded sample
+  roofline      compulsory traffic model: one read of the packed volume (24 B/voxel) + 4 B/pixel written, vs the measured HBM peak.
+                The march re-reads voxels from L1/L2 (8 taps x (1 + shadow_steps) per lit sample), so this kernel is cache- and
+                issue-bound; the HBM fraction is reported for completeness, the tap rate is the number to tune.
+
+usage: python tools/bench_smoke.py [--n 128] [--width 1920 --height 1080] [--steps 5]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def plume(n: int):
+    """Closed-form plume (no RNG): a bent column with a turbulent-looking modulation, all six fields populated."""
+    from forge3d_b200.smoke import SmokeDomain
+
+    z, y, x = np.meshgrid(*(np.arange(n, dtype=np.float32),) * 3, indexing="ij")
+    u, v, w = x / n, y / n, z / n
+    cx, cz = 0.35 + 0.30 * v * v, 0.5 + 0.08 * np.sin(9.0 * v)
+    r2 = ((u - cx) ** 2 + (w - cz) ** 2) / (0.04 + 0.10 * v) ** 2
+    mod = 0.75 + 0.25 * np.sin(23.0 * u + 7.0 * v) * np.cos(17.0 * w - 11.0 * v)
+    density = (np.exp(-r2) * mod * (v < 0.92) * 1.4).astype(np.float32)
+    density[density < 0.02] = 0.0
+    dom = SmokeDomain((n, n, n), voxel_size=(40.0 / n,) * 3, origin=(-20.0, 0.0, -20.0))
+    dom.set_density(density)
+    dom.set_field("temperature", (density * np.clip(1.0 - 2.5 * v, 0.0, 1.0) * 1.5).astype(np.float32))
+    dom.set_field("soot", (density * 0.3 * (1.0 - v)).astype(np.float32))
+    dom.set_field("humidity", (0.2 + 0.5 * v).astype(np.float32))
+    dom.set_field("emission_rate", (density * (v < 0.08) * 1.2).astype(np.float32))
+    dom.set_field("particle_age", np.where(density > 1e-5, 20.0 * v, -1.0).astype(np.float32))
+    return dom
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=128)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, nargs=2, default=(240, 135))
+    args = ap.parse_args()
+    from forge3d_b200.smoke import SmokeRenderSettings
+
+    dom = plume(args.n)
+    st = SmokeRenderSettings()
+    cam = dict(camera_pos=(-55.0, 22.0, -48.0), target=(0.0, 16.0, 0.0), fovy_deg=42.0, sun_direction=(0.4, 0.8, -0.2))
+    for _ in range(args.warmup):
+        dom.render_rgba(args.width, args.height, settings=st, **cam)
+    kernel_ms = []
+    for _ in range(args.steps):
+        img = dom.render_rgba(args.width, args.height, settings=st, **cam)
+        kernel_ms.append(dom.last_kernel_ms)
+    e2e_ms = []
+    for _ in range(args.steps):
+        dom._invalidate()                                  # host fields again: upload + pack inside the timed region
+        t0 = time.perf_counter()
+        dom.render_rgba(args.width, args.height, settings=st, **cam)
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    px = args.width * args.height
+    best = max(min(kernel_ms), 1e-9)   # (0 only under the CPU emulator, whose events do not measure time)
+    from bench import measured_hbm_peak
+
+    peak, how = measured_hbm_peak()
+    algo_bytes = 24.0 * args.n ** 3 + 4.0 * px
+    line = {"metric": "smoke ray-march Mpixels/s", "value": px / best / 1e3, "unit": "Mpx/s", "ms_per_step": best, "steps": args.steps,
+            "warmup": args.warmup, "n_gpus": 1, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.n}^3 plume, {args.width}x{args.height}, default SmokeRenderSettings (self-shadow 20 steps)",
+                       "covered_pixels": int((img[..., 3] > 0).sum())},
+            "e2e": {"value": px / min(e2e_ms) / 1e3, "unit": "Mpx/s", "h2d_bytes_per_step": 24 * args.n ** 3, "d2h_bytes_per_step": 4 * px},
+            "roofline": {"bound": "hbm", "achieved": algo_bytes / best / 1e6, "peak": peak, "unit": "GB/s", "frac": algo_bytes / best / 1e6 / peak,
+                         "traffic": None, "peak_source": how}}
+    try:
+        from oracle import oracle
+
+        w, h = args.cpu_sample
+        t0 = time.perf_counter()
+        oracle.smoke_raymarch_rgba(dom, st, w, h, cam["camera_pos"], cam["target"], (0.0, 1.0, 0.0), cam["fovy_deg"], cam["sun_direction"])
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": w * h / dt / 1e6, "unit": "Mpx/s", "cores": oracle.get_threads(), "kind": "port",
+                                "sample": f"{w}x{h} of the same view (the reference itself is single-threaded)"}
+    except Exception as exc:   # the oracle is test infrastructure; the bench line stands without it
+        line["cpu_baseline"] = {"unavailable": str(exc)}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
