@@ -31,7 +31,8 @@ def _random_domain(seed, dims=(20, 14, 17), voxel=(1.5, 0.8, 1.1), origin=(-7.0,
     dom = SmokeDomain(dims, voxel, origin)
     shape = dom.density.shape
     zz, yy, xx = np.indices(shape, dtype=np.float32)
-    blob = np.exp(-(((xx - dims[0] * 0.45) / 5.0) ** 2 + ((yy - dims[1] * 0.5) / 3.5) ** 2 + ((zz - dims[2] * 0.55) / 4.5) ** 2))
+    blob = np.exp(-(((xx - dims[0] * 0.45) / (0.25 * dims[0])) ** 2 + ((yy - dims[1] * 0.5) / (0.25 * dims[1])) ** 2
+                    + ((zz - dims[2] * 0.55) / (0.26 * dims[2])) ** 2))
     dom.set_density((blob * rng.uniform(0.3, 1.6, shape)).astype(np.float32) * (blob > 0.08))
     dom.set_field("temperature", (blob * rng.uniform(0.0, 2.0, shape)).astype(np.float32))
     dom.set_field("soot", (blob * rng.uniform(0.0, 0.6, shape)).astype(np.float32))
