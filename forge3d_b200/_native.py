@@ -72,6 +72,17 @@ class SmokeSettings(C.Structure):
     ]
 
 
+class ViewshedOptions(C.Structure):
+    """f3d_viewshed_options (include/forge3d_b200.h)."""
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32)] + [(n, C.c_float) for n in (
+        "observer_x", "observer_y", "observer_height_m", "target_height_m", "max_distance_m", "observer_latitude_rad",
+        "observer_longitude_rad", "left_unwrapped_deg", "top_deg", "longitude_step_deg", "latitude_step_deg",
+        "geodesic_sphere_radius_m")] + [
+        ("earth_model", C.c_int32), ("earth_latitude_deg", C.c_double), ("sphere_radius_m", C.c_double),
+        ("refraction_model", C.c_int32), ("refraction_k", C.c_double), ("pressure_mbar", C.c_double), ("temperature_c", C.c_double),
+        ("device", C.c_int32)]
+
+
 class TerrainDesc(C.Structure):
     """f3d_terrain_desc (include/forge3d_b200.h)."""
     _fields_ = [
@@ -120,6 +131,7 @@ EXPORTS = [
     "f3d_session_stats", "f3d_session_sync", "f3d_session_last_frames_ms", "f3d_session_destroy",
     "f3d_session_ipc_export", "f3d_session_ipc_import", "f3d_trace_rays", "f3d_build_minmax",
     "f3d_smoke_create", "f3d_smoke_destroy", "f3d_smoke_raymarch_rgba", "f3d_smoke_raymarch_projection_rgba",
+    "f3d_viewshed", "f3d_shadow_mask",
 ]
 
 _lib = None
@@ -164,6 +176,8 @@ def lib():
                                           C.POINTER(C.c_double)]
     L.f3d_smoke_raymarch_projection_rgba.argtypes = [vp, C.POINTER(SmokeSettings), C.c_uint32, C.c_uint32, f3, f3, u8p,
                                                      C.POINTER(C.c_double)]
+    L.f3d_viewshed.argtypes = [fp, fp, C.POINTER(ViewshedOptions), u8p, fp, fp, fp, C.POINTER(C.c_double)]
+    L.f3d_shadow_mask.argtypes = [fp, fp, C.POINTER(ViewshedOptions), u8p, C.POINTER(C.c_double)]
     for name in EXPORTS:   # fail at load time, not at first call, if the ABI drifted
         getattr(L, name)
     _lib = L

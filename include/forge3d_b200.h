@@ -217,6 +217,29 @@ int f3d_smoke_raymarch_projection_rgba(f3d_smoke* s, const f3d_smoke_settings* s
                                        const float view_direction[3], const float sun_direction[3], uint8_t* rgba,
                                        double* kernel_ms);
 
+/* ---- HELIOS viewshed / solar shadow mask ----
+ * Replace compute_viewshed / compute_shadow_mask, /root/reference/src/terrain/analysis/viewshed.rs:341-347,396-570 (called from
+ * src/py_functions/geodesy.rs:351,502).  Inputs are what those functions take: the DEM, the per-cell geodesic offsets (or
+ * geodetic position + sun angles) computed by the caller, and ViewshedOptions. */
+typedef struct f3d_viewshed_options {    /* ViewshedOptions, viewshed.rs:8-25 */
+    uint32_t width, height;
+    float observer_x, observer_y, observer_height_m, target_height_m, max_distance_m;
+    float observer_latitude_rad, observer_longitude_rad, left_unwrapped_deg, top_deg;
+    float longitude_step_deg, latitude_step_deg, geodesic_sphere_radius_m;
+    int32_t earth_model;                 /* F3D_EARTH_*; Ellipsoid { latitude_deg } = earth_latitude_deg */
+    double earth_latitude_deg, sphere_radius_m;
+    int32_t refraction_model;            /* F3D_REFRACTION_* */
+    double refraction_k, pressure_mbar, temperature_c;
+    int32_t device;
+} f3d_viewshed_options;
+/* heights: host height x width; positions_m: host n x 2 (east, north metres from the observer).  Outputs (host, n each):
+ * visibility 0/1, curvature drop, refraction gain, horizon distance.  *kernel_ms may be NULL. */
+int f3d_viewshed(const float* heights, const float* positions_m, const f3d_viewshed_options* options, uint8_t* visibility,
+                 float* curvature_drop_m, float* refraction_gain_m, float* horizon_distance_m, double* kernel_ms);
+/* geodetic_and_sun: host n x 4 (latitude rad, longitude rad, sun azimuth rad, launch elevation rad); lit: host n, 1 = lit. */
+int f3d_shadow_mask(const float* heights, const float* geodetic_and_sun, const f3d_viewshed_options* options, uint8_t* lit,
+                    double* kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

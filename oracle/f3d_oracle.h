@@ -169,6 +169,25 @@ float f3do_smoke_sun_transmittance(const f3do_smoke_volume* vol, const f3do_smok
                                    const float sun_dir[3], float step, uint32_t steps);
 const char* f3do_smoke_last_error(void);
 
+/* ---- HELIOS viewshed / solar shadow mask (src/terrain/analysis/viewshed.rs, src/shaders/terrain_viewshed.wgsl;
+ * SURVEY section 8f row 4) ---- */
+typedef struct f3do_viewshed_options {   /* ViewshedOptions, viewshed.rs:8-25, with physics_terms (:54-78) resolved */
+    uint32_t width, height;
+    float observer_x, observer_y, observer_height_m, target_height_m, max_distance_m;
+    float observer_latitude_rad, observer_longitude_rad, left_unwrapped_deg, top_deg;
+    float longitude_step_deg, latitude_step_deg, geodesic_sphere_radius_m;
+    float physics[4];                    /* 1/meridional, 1/prime-vertical, 1 - k, curved flag */
+} f3do_viewshed_options;
+/* 0 ok.  physics_terms: earth 0 flat / 1 sphere / 2 ellipsoid; refraction 0 none / 1 bennett / 2 saemundsson / 3 effective_radius. */
+int f3do_viewshed_physics(int earth_model, double latitude_deg, double sphere_radius_m, int refraction_model, double k,
+                          double pressure_mbar, double temperature_c, float physics[4]);
+/* positions_m: n x 2 (east, north metres from the observer); outputs n each; visible: 0 hidden, 1 visible, 2 = the geodesic
+ * left the DEM footprint (the reference turns that into an error, viewshed.rs:320-327). */
+int f3do_viewshed(const float* heights, const float* positions_m, const f3do_viewshed_options* options, uint8_t* visible,
+                  float* curvature_drop_m, float* refraction_gain_m, float* horizon_distance_m);
+/* inputs: n x 4 (latitude rad, longitude rad, sun azimuth rad, sun elevation rad); lit: n (1 = sun visible). */
+int f3do_shadow_mask(const float* heights, const float* inputs, const f3do_viewshed_options* options, uint8_t* lit);
+
 /* Pinned elementary functions of the numerics contract (exposed for unit tests). */
 void  f3do_sincos(float x, float* s, float* c);
 float f3do_atan2(float y, float x);

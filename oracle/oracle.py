@@ -109,7 +109,7 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (gcc, no FMA contraction)."""
-    src_mtime = max((_HERE / n).stat().st_mtime for n in ("f3d_oracle.c", "f3d_aether_oracle.c", "f3d_smoke_oracle.c", "f3d_oracle.h", "Makefile"))
+    src_mtime = max((_HERE / n).stat().st_mtime for n in ("f3d_oracle.c", "f3d_aether_oracle.c", "f3d_smoke_oracle.c", "f3d_viewshed_oracle.c", "f3d_oracle.h", "Makefile"))
     if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src_mtime:
         env = dict(os.environ)
         env.pop("CC", None)
@@ -401,6 +401,65 @@ def smoke_sun_transmittance(domain, settings, start, sun_dir, step, steps):
     out = float(L.f3do_smoke_sun_transmittance(C.byref(v), C.byref(s), f3(*map(float, start)), f3(*map(float, sun_dir)), float(step), int(steps)))
     del keep
     return out
+
+
+class _ViewshedOptions(C.Structure):
+    """f3do_viewshed_options (oracle/f3d_oracle.h)."""
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32)] + [(n, C.c_float) for n in (
+        "observer_x", "observer_y", "observer_height_m", "target_height_m", "max_distance_m", "observer_latitude_rad",
+        "observer_longitude_rad", "left_unwrapped_deg", "top_deg", "longitude_step_deg", "latitude_step_deg",
+        "geodesic_sphere_radius_m")] + [("physics", C.c_float * 4)]
+
+
+def _viewshed_options(opts: dict):
+    """opts: the ViewshedOptions fields + earth_model / refraction_model names and their parameters (see
+    forge3d_b200.viewshed.make_options)."""
+    L = lib()
+    o = _ViewshedOptions()
+    o.width, o.height = int(opts["width"]), int(opts["height"])
+    for name, _ in _ViewshedOptions._fields_[2:-1]:
+        setattr(o, name, float(opts[name]))
+    phys = (C.c_float * 4)()
+    L.f3do_viewshed_physics.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_float * 4]
+    rc = L.f3do_viewshed_physics(EARTH_MODELS[opts["earth_model"]], float(opts.get("earth_latitude_deg", 0.0)),
+                                 float(opts.get("sphere_radius_m", 6371008.8)), REFRACTION_MODELS[opts["refraction_model"]],
+                                 float(opts.get("refraction_k", 0.13)), float(opts.get("pressure_mbar", 1013.25)),
+                                 float(opts.get("temperature_c", 15.0)), phys)
+    if rc != 0:
+        raise OracleError({1: "flat earth only supports refraction_model='none'", 3: "refraction k must be finite and less than 1",
+                           4: "sphere radius must be finite and positive"}.get(rc, f"invalid physics ({rc})"))
+    o.physics = phys
+    return o
+
+
+def viewshed(heights, positions_m, opts: dict):
+    """compute_viewshed (viewshed.rs:161-347) -> dict(visibility bool, curvature_drop_m, refraction_gain_m, horizon_distance_m)."""
+    L = lib()
+    dem = np.ascontiguousarray(heights, np.float32)
+    pos = np.ascontiguousarray(positions_m, np.float32).reshape(dem.shape + (2,))
+    o = _viewshed_options(opts)
+    vis = np.zeros(dem.shape, np.uint8)
+    drop, gain, horizon = (np.zeros(dem.shape, np.float32) for _ in range(3))
+    L.f3do_viewshed.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(_ViewshedOptions), C.POINTER(C.c_uint8),
+                                C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    if L.f3do_viewshed(_fp(dem), _fp(pos), C.byref(o), vis.ctypes.data_as(C.POINTER(C.c_uint8)), _fp(drop), _fp(gain), _fp(horizon)) != 0:
+        raise OracleError("f3do_viewshed failed")
+    if (vis > 1).any():
+        raise OracleError("viewshed geodesic leaves the DEM footprint")
+    return dict(visibility=vis.astype(bool), curvature_drop_m=drop, refraction_gain_m=gain, horizon_distance_m=horizon)
+
+
+def shadow_mask(heights, inputs, opts: dict):
+    """compute_shadow_mask (viewshed.rs:396-570) -> bool (H, W), True = the sun is visible from the cell."""
+    L = lib()
+    dem = np.ascontiguousarray(heights, np.float32)
+    inp = np.ascontiguousarray(inputs, np.float32).reshape(dem.shape + (4,))
+    o = _viewshed_options(opts)
+    lit = np.zeros(dem.shape, np.uint8)
+    L.f3do_shadow_mask.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(_ViewshedOptions), C.POINTER(C.c_uint8)]
+    if L.f3do_shadow_mask(_fp(dem), _fp(inp), C.byref(o), lit.ctypes.data_as(C.POINTER(C.c_uint8))) != 0:
+        raise OracleError("f3do_shadow_mask failed")
+    return lit.astype(bool)
 
 
 def exp2(x: float) -> float:

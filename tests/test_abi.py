@@ -37,6 +37,7 @@ def test_struct_layout_matches_c():
     #include <stddef.h>
     #include "forge3d_b200.h"
     int main(void) {
+      printf("%zu %zu %zu ", sizeof(f3d_viewshed_options), offsetof(f3d_viewshed_options, earth_latitude_deg), offsetof(f3d_viewshed_options, device));
       printf("%zu %zu %zu %zu ", sizeof(f3d_smoke_volume), offsetof(f3d_smoke_volume, frame_index), sizeof(f3d_smoke_settings),
              offsetof(f3d_smoke_settings, soot_absorption));
       printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(f3d_terrain_desc), offsetof(f3d_terrain_desc, observer_lat_deg),
@@ -49,6 +50,9 @@ def test_struct_layout_matches_c():
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(tmp), "-o", "/tmp/f3d_layout"], check=True)
     vals = list(map(int, subprocess.run(["/tmp/f3d_layout"], check=True, capture_output=True, text=True).stdout.split()))
     D, O, A = _native.TerrainDesc, _native.TerrainOut, _native.Atmosphere
+    VO = _native.ViewshedOptions
+    assert vals[:3] == [C.sizeof(VO), VO.earth_latitude_deg.offset, VO.device.offset]
+    vals = vals[3:]
     SV, SS = _native.SmokeVolume, _native.SmokeSettings
     assert vals[:4] == [C.sizeof(SV), SV.frame_index.offset, C.sizeof(SS), SS.soot_absorption.offset]
     vals = vals[4:]
