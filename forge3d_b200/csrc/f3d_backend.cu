@@ -1238,6 +1238,21 @@ extern "C" int f3d_trace_rays(const float* heights, uint32_t w, uint32_t h, cons
     return 0;
 }
 
+#ifdef F3D_SCHED_STATS
+// Tuning builds only (see F3D_SCHED_STATS in f3d_kernels.cuh); not part of the public ABI.
+extern "C" int f3d_debug_sched_stats(unsigned long long* out8, int reset) {
+#ifdef EMU_SIMT
+    memcpy(out8, f3d::g_sched_stats, 8 * sizeof(unsigned long long));
+    if (reset) memset(f3d::g_sched_stats, 0, 8 * sizeof(unsigned long long));
+#else
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, f3d::g_sched_stats, 8 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(f3d::g_sched_stats, z, sizeof z); }
+#endif
+    return 0;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // smoke volume ray-march (src/smoke/render.rs:6-175): host set-up in Rust f32 semantics, one kernel per render
 // ------------------------------------------------------------------------------------------------

@@ -475,6 +475,61 @@ __global__ void k_wait_peers(const __grid_constant__ FrameParams P, uint32_t nee
 #endif
 constexpr int kTraceCtaThreads = F3D_TRACE_THREADS;
 constexpr int kRefillBelow = F3D_REFILL_BELOW;
+// F3D_TRACE_DEFER_LEAVES = N > 0: an any-hit lane that finds a leaf on top of its stack parks it in one of N per-lane
+// slots and keeps expanding; parked leaves are solved together once F3D_DEFER_LEAF_BATCH lanes hold one (or nobody can
+// expand any more).  Exact for the occlusion flag, which is an OR over a fixed set of leaf tests (see
+// F3D_ANYHIT_SIGN_ORDER in f3d_trace_fast.cuh): only the ORDER of those tests changes.  0 = solve leaves in stack order.
+#ifndef F3D_TRACE_DEFER_LEAVES
+#define F3D_TRACE_DEFER_LEAVES 0
+#endif
+#ifndef F3D_DEFER_LEAF_BATCH
+#define F3D_DEFER_LEAF_BATCH 20
+#endif
+#ifndef F3D_DEFER_RULE
+#define F3D_DEFER_RULE 0
+#endif
+#ifndef F3D_DEFER_LEAF_MIN
+#define F3D_DEFER_LEAF_MIN 8
+#endif
+#ifndef F3D_DEFER_STALL
+#define F3D_DEFER_STALL 8
+#endif
+constexpr int kDeferLeaves = F3D_TRACE_DEFER_LEAVES;
+constexpr int kDeferLeafBatch = F3D_DEFER_LEAF_BATCH;
+#if F3D_TRACE_DEFER_LEAVES
+// The parked-leaf slots stay in registers: every access is a compile-time index selected by a predicate.
+__device__ __forceinline__ void pend_push(uint32_t (&pend)[F3D_TRACE_DEFER_LEAVES], uint32_t& n, uint32_t v) {
+#pragma unroll
+    for (int k = 0; k < F3D_TRACE_DEFER_LEAVES; k++)
+        if (n == (uint32_t)k) pend[k] = v;
+    n++;
+}
+__device__ __forceinline__ uint32_t pend_pop(const uint32_t (&pend)[F3D_TRACE_DEFER_LEAVES], uint32_t& n) {
+    n--;
+    uint32_t v = pend[0];
+#pragma unroll
+    for (int k = 1; k < F3D_TRACE_DEFER_LEAVES; k++)
+        if (n == (uint32_t)k) v = pend[k];
+    return v;
+}
+#endif
+
+// F3D_SCHED_STATS (test / tuning builds only): SIMT-efficiency counters of the persistent scheduler, one warp-level event
+// each: [0] expansion steps [1] lanes expanding [2] leaf phases [3] lanes solving a leaf [4] refill steps [5] rays fetched.
+// Read with f3d_debug_sched_stats(); the CPU emulator (real 32-lane warps) gives the same counts the GPU would.
+#ifdef F3D_SCHED_STATS
+__device__ unsigned long long g_sched_stats[8];
+#define F3D_SCHED_STAT(i, mask)                                                                                  \
+    do {                                                                                                          \
+        const uint32_t _m = __ballot_sync(0xFFFFFFFFu, (mask));                                                   \
+        if ((threadIdx.x & 31u) == 0u && _m != 0u) {                                                              \
+            atomicAdd(&g_sched_stats[i], 1ull);                                                                   \
+            atomicAdd(&g_sched_stats[(i) + 1], (unsigned long long)__popc(_m));                                   \
+        }                                                                                                         \
+    } while (0)
+#else
+#define F3D_SCHED_STAT(i, mask) do {} while (0)
+#endif
 
 template <bool IS_SUN, bool CURV>
 __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack st) {
@@ -494,6 +549,10 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
     uint32_t pix = 0u;
     bool exhausted = false;
     uint32_t n_rays = 0, n_nodes = 0;
+#if F3D_TRACE_DEFER_LEAVES
+    uint32_t pend[F3D_TRACE_DEFER_LEAVES];
+    uint32_t npend = 0u;
+#endif
 
     while (true) {
         // ---- refill idle lanes ----
@@ -504,6 +563,7 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
             if (lane == 0u) base = atomicAdd(next, n_idle);
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if (base + n_idle >= n) exhausted = true;
+            F3D_SCHED_STAT(4, !busy && base + (uint32_t)__popc(idle & ((1u << lane) - 1u)) < n);
             if (!busy) {
                 const uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
                 if (idx < n) {
@@ -535,10 +595,52 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
             if (exhausted) break;
             continue;
         }
+#if F3D_TRACE_DEFER_LEAVES
+        // ---- traverse with parked leaves (see F3D_TRACE_DEFER_LEAVES) ----
+        while (true) {
+            while (true) {
+#pragma unroll
+                for (int k = 0; k < kDeferLeaves; k++)      // park leaf tops
+                    if (busy && T.sp > 0u && npend < (uint32_t)kDeferLeaves && top_is_leaf(T, st)) { T.sp--; pend_push(pend, npend, st.at(T.sp)); }
+                const bool can_expand = busy && T.sp > 0u && !top_is_leaf(T, st);
+                F3D_SCHED_STAT(0, can_expand);
+                if (can_expand) {
+                    expand_top<true, CURV>(F, T, st);
+                    n_nodes++;
+                    if (T.sp == 0u && npend == 0u) { occl[pix] = mesh_occl ? 1u : 0u; busy = false; }
+                }
+#pragma unroll
+                for (int k = 0; k < kDeferLeaves; k++)
+                    if (busy && T.sp > 0u && npend < (uint32_t)kDeferLeaves && top_is_leaf(T, st)) { T.sp--; pend_push(pend, npend, st.at(T.sp)); }
+                const bool expandable = busy && T.sp > 0u && !top_is_leaf(T, st);
+                const uint32_t m_exp = __ballot_sync(0xFFFFFFFFu, expandable);
+                const uint32_t m_pend = __ballot_sync(0xFFFFFFFFu, busy && npend > 0u);
+#if F3D_DEFER_RULE == 1
+                if (m_exp == 0u || __popc(m_pend) >= max(__popc(m_exp), F3D_DEFER_LEAF_MIN)) break;
+#elif F3D_DEFER_RULE == 2
+                const uint32_t m_stall = __ballot_sync(0xFFFFFFFFu, busy && !expandable);
+                if (m_exp == 0u || __popc(m_stall) >= F3D_DEFER_STALL || __popc(m_pend) >= kDeferLeafBatch) break;
+#else
+                if (m_exp == 0u || __popc(m_pend) >= kDeferLeafBatch) break;
+#endif
+            }
+            F3D_SCHED_STAT(2, busy && npend > 0u);
+            if (busy && npend > 0u) {
+                n_nodes++;
+                const bool hit = leaf_node<true, CURV>(F, T, pend_pop(pend, npend));
+                if (hit) { occl[pix] = 1u; busy = false; T.sp = 0u; npend = 0u; }
+                else if (T.sp == 0u && npend == 0u) { occl[pix] = mesh_occl ? 1u : 0u; busy = false; }
+            }
+            const uint32_t live = __ballot_sync(0xFFFFFFFFu, busy);
+            if (live == 0u) break;
+            if (!exhausted && __popc(live) < kRefillBelow) break;
+        }
+#else
         // ---- traverse until enough lanes have gone idle (bounded while-while, see trace_fast) ----
         while (true) {
             while (true) {
                 const bool can_expand = busy && !top_is_leaf(T, st);
+                F3D_SCHED_STAT(0, can_expand);
                 if (can_expand) {
                     expand_top<true, CURV>(F, T, st);
                     n_nodes++;
@@ -549,6 +651,7 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
                 const uint32_t m_leaf = __ballot_sync(0xFFFFFFFFu, busy && !expandable);
                 if (m_exp == 0u || __popc(m_leaf) >= kLeafBatch) break;
             }
+            F3D_SCHED_STAT(2, busy && top_is_leaf(T, st));
             if (busy && top_is_leaf(T, st)) {
                 n_nodes++;
                 const bool hit = leaf_top<true, CURV>(F, T, st);
@@ -558,6 +661,7 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
             if (live == 0u) break;
             if (!exhausted && __popc(live) < kRefillBelow) break;
         }
+#endif
     }
     warp_add_counters(P.counters, 0u, IS_SUN ? n_rays : 0u, IS_SUN ? 0u : n_rays, n_nodes);
 }

@@ -260,9 +260,18 @@ __device__ __forceinline__ void expand_top(const FastScene& S, TraceState& T, co
 // Pops the leaf on top of the stack and runs the exact ray / bilinear-patch solve (:167-235).
 // Returns true when the ray is finished (any-hit rays stop at their first hit).
 template <bool ANY_HIT, bool CURV>
+__device__ __forceinline__ bool leaf_node(const FastScene& S, TraceState& T, const uint32_t node);
+
+template <bool ANY_HIT, bool CURV>
 __device__ __forceinline__ bool leaf_top(const FastScene& S, TraceState& T, const SmemStack st) {
     T.sp--;
-    const uint32_t node = st.at(T.sp);
+    return leaf_node<ANY_HIT, CURV>(S, T, st.at(T.sp));
+}
+
+// The leaf solve for an already popped level-0 node (T.sp is the stack height AFTER the pop: the stale test of a
+// closest-hit ray compares against it).
+template <bool ANY_HIT, bool CURV>
+__device__ __forceinline__ bool leaf_node(const FastScene& S, TraceState& T, const uint32_t node) {
     const uint32_t cz = (node >> 13) & 0x1FFFu, cx = node & 0x1FFFu;
     const float4 h = __ldg(S.cells + (size_t)cz * S.cell_w + cx);
     const float a0 = ((S.ox + (float)cx * S.sx) - T.o.x) * T.inv_x;

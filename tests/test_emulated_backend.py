@@ -10,7 +10,8 @@ import _emu
 import _helpers as H
 from oracle import oracle
 
-VARIANTS = {"default": (), "anyhit_sorted": ("F3D_ANYHIT_SIGN_ORDER=0",), "literal_push_clip": ("F3D_PUSH_CLIP_FOLDED=0",)}
+VARIANTS = {"default": (), "anyhit_sorted": ("F3D_ANYHIT_SIGN_ORDER=0",), "literal_push_clip": ("F3D_PUSH_CLIP_FOLDED=0",),
+            "deferred_leaves": ("F3D_TRACE_DEFER_LEAVES=4", "F3D_DEFER_RULE=2", "F3D_DEFER_STALL=4", "F3D_DEFER_LEAF_BATCH=20")}
 
 
 def _bits(a):
