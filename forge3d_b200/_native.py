@@ -131,7 +131,7 @@ EXPORTS = [
     "f3d_session_stats", "f3d_session_sync", "f3d_session_last_frames_ms", "f3d_session_destroy",
     "f3d_session_ipc_export", "f3d_session_ipc_import", "f3d_trace_rays", "f3d_build_minmax",
     "f3d_smoke_create", "f3d_smoke_destroy", "f3d_smoke_raymarch_rgba", "f3d_smoke_raymarch_projection_rgba",
-    "f3d_viewshed", "f3d_shadow_mask",
+    "f3d_viewshed", "f3d_shadow_mask", "f3d_lbvh_build",
 ]
 
 _lib = None
@@ -178,6 +178,7 @@ def lib():
                                                      C.POINTER(C.c_double)]
     L.f3d_viewshed.argtypes = [fp, fp, C.POINTER(ViewshedOptions), u8p, fp, fp, fp, C.POINTER(C.c_double)]
     L.f3d_shadow_mask.argtypes = [fp, fp, C.POINTER(ViewshedOptions), u8p, C.POINTER(C.c_double)]
+    L.f3d_lbvh_build.argtypes = [fp, C.c_uint32, u32p, C.c_uint32, C.c_int32, u32p, u32p, u32p, u32p, u32p, fp]
     for name in EXPORTS:   # fail at load time, not at first call, if the ABI drifted
         getattr(L, name)
     _lib = L
@@ -402,3 +403,16 @@ def build_minmax(heights, device=0):
         levels.append(buf[off:off + lw * lh * 2].reshape(lh, lw, 2))
         off += lw * lh * 2
     return levels, w - 1, h - 1
+
+
+def lbvh_build(vertices, indices, device=0):
+    """GPU LBVH build of a triangle mesh (test seam f3d_lbvh_build) -> dict(morton, order, left, right, parent, nodes)."""
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
+    n = t.shape[0]
+    out = dict(morton=np.zeros(n, np.uint32), order=np.zeros(n, np.uint32), left=np.zeros(max(n - 1, 0), np.uint32),
+               right=np.zeros(max(n - 1, 0), np.uint32), parent=np.zeros(2 * n - 1, np.uint32), nodes=np.zeros((2 * n - 1, 8), np.float32))
+    u = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+    check(lib().f3d_lbvh_build(_fp(v), v.shape[0], u(t), n, int(device), u(out["morton"]), u(out["order"]), u(out["left"]),
+                               u(out["right"]), u(out["parent"]), _fp(out["nodes"])))
+    return out

@@ -22,6 +22,7 @@
 
 #include "../../include/forge3d_b200.h"
 #include "f3d_kernels.cuh"
+#include "f3d_lbvh.cuh"
 #include "f3d_smoke.cuh"
 #include "f3d_viewshed.cuh"
 
@@ -297,7 +298,7 @@ static void bvh_build_rec(MeshBvh& B, std::vector<uint32_t>& ids, size_t lo, siz
     if (count <= 4) {
         B.nodes[2 * node] = make_float4(mn[0], mn[1], mn[2], 0.0f);
         B.nodes[2 * node + 1] = make_float4(mx[0], mx[1], mx[2], 0.0f);
-        const uint32_t first = (uint32_t)B.tris.size(), cnt = (uint32_t)count;
+        const uint32_t first = 0x80000000u | (uint32_t)B.tris.size(), cnt = (uint32_t)count;   // leaf flag, see intersect_mesh
         for (size_t k = lo; k < hi; k++) B.tris.push_back(ids[k]);
         memcpy(&B.nodes[2 * node].w, &first, 4);
         memcpy(&B.nodes[2 * node + 1].w, &cnt, 4);
@@ -311,7 +312,7 @@ static void bvh_build_rec(MeshBvh& B, std::vector<uint32_t>& ids, size_t lo, siz
         const float ca = cen[3 * a + axis], cb = cen[3 * b + axis];
         return ca < cb || (ca == cb && a < b);
     });
-    const uint32_t left = (uint32_t)(B.nodes.size() / 2), zero = 0u;
+    const uint32_t left = (uint32_t)(B.nodes.size() / 2), zero = left + 1u;                // right child
     B.nodes.resize(B.nodes.size() + 4);
     B.nodes[2 * node] = make_float4(mn[0], mn[1], mn[2], 0.0f);
     B.nodes[2 * node + 1] = make_float4(mx[0], mx[1], mx[2], 0.0f);
@@ -346,6 +347,68 @@ static void build_mesh_bvh(const float* xyz, const uint32_t* idx, uint32_t ntris
 }
 
 static uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+// ------------------------------------------------------------------------------------------------
+// GPU LBVH build (csrc/f3d_lbvh.cuh): d_verts (float4) and d_idx already on the device; writes 2 * (2n - 1) float4 nodes in
+// the traversal format and the n triangle ids in leaf order.  The scene box is taken on the host (the vertices were just
+// scanned there by validate_desc; compute_scene_aabb, src/accel/types.rs:298-305).
+// ------------------------------------------------------------------------------------------------
+struct LbvhScratch {
+    unsigned long long* keys = nullptr;
+    float4* tri_boxes = nullptr;
+    uint32_t *left = nullptr, *right = nullptr, *parent = nullptr, *arrivals = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    ~LbvhScratch() {
+        cudaStreamSynchronize(stream);
+        cached_free(keys, device); cached_free(tri_boxes, device); cached_free(left, device); cached_free(right, device);
+        cached_free(parent, device); cached_free(arrivals, device);
+    }
+};
+
+static int build_mesh_lbvh(const float* xyz, uint32_t nverts, const uint32_t* idx, uint32_t ntris, const float4* d_verts,
+                           const uint32_t* d_idx, int device, cudaStream_t stream, float4* d_nodes, uint32_t* d_order, uint64_t* launches,
+                           LbvhScratch* keep = nullptr) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t t = 0; t < (size_t)ntris * 3; t++)               // only vertices referenced by a triangle count
+        for (int a = 0; a < 3; a++) {
+            const float v = xyz[3 * (size_t)idx[t] + a];
+            mn[a] = fminf(mn[a], v); mx[a] = fmaxf(mx[a], v);
+        }
+    (void)nverts;
+    v3 wmin, wext;                                               // MortonUniforms, lbvh_gpu/morton.rs:14-27
+    wmin.x = mn[0]; wmin.y = mn[1]; wmin.z = mn[2];
+    wext.x = fmaxf(mx[0] - mn[0], 1e-6f); wext.y = fmaxf(mx[1] - mn[1], 1e-6f); wext.z = fmaxf(mx[2] - mn[2], 1e-6f);
+    const uint32_t padded = next_pow2(ntris);
+    LbvhScratch local;
+    LbvhScratch& W = keep ? *keep : local;
+    W.device = device; W.stream = stream;
+    CUDA_TRY(cached_malloc((void**)&W.keys, (size_t)padded * sizeof(unsigned long long), device));
+    CUDA_TRY(cached_malloc((void**)&W.tri_boxes, (size_t)ntris * 2 * sizeof(float4), device));
+    CUDA_TRY(cached_malloc((void**)&W.left, (size_t)std::max(ntris, 2u) * sizeof(uint32_t), device));
+    CUDA_TRY(cached_malloc((void**)&W.right, (size_t)std::max(ntris, 2u) * sizeof(uint32_t), device));
+    CUDA_TRY(cached_malloc((void**)&W.parent, (size_t)(2 * ntris) * sizeof(uint32_t), device));
+    CUDA_TRY(cached_malloc((void**)&W.arrivals, (size_t)std::max(ntris, 2u) * sizeof(uint32_t), device));
+    CUDA_TRY(cudaMemsetAsync(W.arrivals, 0, (size_t)std::max(ntris, 2u) * sizeof(uint32_t), stream));
+    CUDA_TRY(cudaMemsetAsync(W.parent, 0xFF, (size_t)(2 * ntris) * sizeof(uint32_t), stream));
+    const unsigned tb = 256;
+    k_lbvh_prims<<<(padded + tb - 1) / tb, tb, 0, stream>>>(d_verts, d_idx, ntris, wmin, wext, W.keys, padded, W.tri_boxes);
+    (*launches)++;
+    for (uint32_t k = 2; k <= padded; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            k_lbvh_bitonic<<<(padded + tb - 1) / tb, tb, 0, stream>>>(W.keys, padded, k, j);
+            (*launches)++;
+        }
+    if (ntris > 1u) {
+        k_lbvh_link<<<(ntris - 1u + tb - 1) / tb, tb, 0, stream>>>(W.keys, ntris, W.left, W.right, W.parent);
+        (*launches)++;
+    }
+    k_lbvh_refit<<<(ntris + tb - 1) / tb, tb, 0, stream>>>(W.keys, ntris, W.left, W.right, W.parent, W.tri_boxes, W.arrivals, d_nodes, d_order);
+    (*launches)++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // device terrain: packed cells + min-max levels
@@ -468,6 +531,8 @@ static void fill_fast_scene(FastScene* F, const SceneParams& S, const DeviceTerr
     F->root_mm = T.root_mm;
     F->inv_two_r_prime = S.inv_two_r_prime;
 }
+
+constexpr uint32_t kLbvhMinTris = 4096u;
 
 static uint32_t stack_depth_for(int nlevels) { return 3u * (uint32_t)nlevels + 2u; }
 
@@ -711,7 +776,20 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         S.mesh_v = s->d_mesh_v; S.mesh_i = s->d_mesh_i;
         S.mesh_index_count = d->mesh_ntris * 3u; S.mesh_nverts = d->mesh_nverts;
-        if (d->mesh_ntris > 8u && !getenv("F3D_B200_NO_MESH_BVH")) {
+        // BVH choice: meshes above kLbvhMinTris are built on the device (LBVH, microseconds per 100 k triangles); small ones keep
+        // the host median-split tree (shallower, 4 triangles per leaf).  F3D_B200_MESH_BVH=host|lbvh|none overrides.  Either
+        // way the closest hit is the index-order sweep's (tests/test_gpu_parity.py::test_mesh_bvh_matches_index_order_sweep).
+        const char* bvh_env = getenv("F3D_B200_MESH_BVH");
+        const bool no_bvh = getenv("F3D_B200_NO_MESH_BVH") || (bvh_env && !strcmp(bvh_env, "none"));
+        const bool use_lbvh = bvh_env ? !strcmp(bvh_env, "lbvh") : d->mesh_ntris >= kLbvhMinTris;
+        if (d->mesh_ntris > 8u && !no_bvh && use_lbvh) {
+            if ((rc = dmalloc(s, &s->d_bvh_nodes, (size_t)2 * (2 * (size_t)d->mesh_ntris - 1), false))) return rc;
+            if ((rc = dmalloc(s, &s->d_bvh_tris, (size_t)d->mesh_ntris, false))) return rc;
+            if ((rc = build_mesh_lbvh(d->mesh_xyz, d->mesh_nverts, d->mesh_idx, d->mesh_ntris, s->d_mesh_v, s->d_mesh_i, s->device, s->stream,
+                                      s->d_bvh_nodes, s->d_bvh_tris, &s->launches)))
+                return rc;
+            S.bvh_nodes = s->d_bvh_nodes; S.bvh_tris = s->d_bvh_tris;
+        } else if (d->mesh_ntris > 8u && !no_bvh) {
             MeshBvh bvh;
             build_mesh_bvh(d->mesh_xyz, d->mesh_idx, d->mesh_ntris, &bvh);
             if ((rc = dmalloc(s, &s->d_bvh_nodes, bvh.nodes.size(), false))) return rc;
@@ -1632,5 +1710,46 @@ extern "C" int f3d_shadow_mask(const float* heights, const float* geodetic_and_s
     CUDA_TRY(cudaEventRecord(R.ev1, 0));
     CUDA_TRY(cudaMemcpy(lit, R.d_out, n, cudaMemcpyDeviceToHost));
     if (kernel_ms) { float ms = 0.0f; CUDA_TRY(cudaEventElapsedTime(&ms, R.ev0, R.ev1)); *kernel_ms = ms; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LBVH test seam: builds the tree for a host mesh and returns Morton order, topology and boxes
+// ------------------------------------------------------------------------------------------------
+extern "C" int f3d_lbvh_build(const float* xyz, uint32_t nverts, const uint32_t* idx, uint32_t ntris, int32_t device, uint32_t* morton,
+                              uint32_t* order, uint32_t* left, uint32_t* right, uint32_t* parent, float* nodes /* (2n-1) x 8 */) {
+    g_err[0] = 0;
+    if (!xyz || !idx || nverts == 0 || ntris == 0) return fail(F3D_ERR_ARGUMENT, "empty mesh");
+    if (ntris > (1u << 20)) return fail(F3D_ERR_RENDER, "Triangle count %u exceeds maximum of 1M triangles", ntris);   // lbvh_gpu/build.rs:11-16
+    for (size_t i = 0; i < (size_t)ntris * 3; i++)
+        if (idx[i] >= nverts) return fail(F3D_ERR_RENDER, "mesh indices reference out-of-bounds vertices");
+    int rc = select_device(device);
+    if (rc) return rc;
+    std::vector<float4> v(nverts);
+    for (uint32_t i = 0; i < nverts; i++) v[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0f);
+    float4 *d_v = nullptr, *d_nodes = nullptr;
+    uint32_t *d_i = nullptr, *d_order = nullptr;
+    struct Free { float4*& a; float4*& b; uint32_t*& c; uint32_t*& d; int dev; ~Free() { cudaDeviceSynchronize(); cached_free(a, dev); cached_free(b, dev); cached_free(c, dev); cached_free(d, dev); } }
+        guard{d_v, d_nodes, d_i, d_order, device};
+    const size_t nnodes = 2 * (size_t)ntris - 1;
+    CUDA_TRY(cached_malloc((void**)&d_v, nverts * sizeof(float4), device));
+    CUDA_TRY(cached_malloc((void**)&d_i, (size_t)ntris * 3 * sizeof(uint32_t), device));
+    CUDA_TRY(cached_malloc((void**)&d_nodes, nnodes * 2 * sizeof(float4), device));
+    CUDA_TRY(cached_malloc((void**)&d_order, (size_t)ntris * sizeof(uint32_t), device));
+    CUDA_TRY(cudaMemcpy(d_v, v.data(), nverts * sizeof(float4), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_i, idx, (size_t)ntris * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    uint64_t launches = 0;
+    LbvhScratch W;
+    if ((rc = build_mesh_lbvh(xyz, nverts, idx, ntris, d_v, d_i, device, nullptr, d_nodes, d_order, &launches, &W))) return rc;
+    std::vector<unsigned long long> keys(ntris);
+    CUDA_TRY(cudaMemcpy(keys.data(), W.keys, (size_t)ntris * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (morton) for (uint32_t i = 0; i < ntris; i++) morton[i] = (uint32_t)(keys[i] >> 32);
+    if (order) CUDA_TRY(cudaMemcpy(order, d_order, (size_t)ntris * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (ntris > 1u) {
+        if (left) CUDA_TRY(cudaMemcpy(left, W.left, (size_t)(ntris - 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (right) CUDA_TRY(cudaMemcpy(right, W.right, (size_t)(ntris - 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    if (parent) CUDA_TRY(cudaMemcpy(parent, W.parent, nnodes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (nodes) CUDA_TRY(cudaMemcpy(nodes, d_nodes, nnodes * 2 * sizeof(float4), cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -302,7 +302,7 @@ __device__ __noinline__ Hit intersect_mesh(const SceneParams& S, const Ray& r) {
         return res;
     }
     const float ix = frcp(r.d.x), iy = frcp(r.d.y), iz = frcp(r.d.z);   // +-inf for axis-parallel rays: handled by fmin/fmax
-    uint32_t stack[48];
+    uint32_t stack[64];                      // a Karras tree over 62-bit unique keys is at most 62 deep
     uint32_t sp = 0;
     stack[sp++] = 0u;
     while (sp) {
@@ -314,12 +314,14 @@ __device__ __noinline__ Hit intersect_mesh(const SceneParams& S, const Ray& r) {
         const float tnear = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), r.tmin));
         const float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), res.t));
         if (!(tnear <= tfar)) continue;
-        const uint32_t first = __float_as_uint(n0.w), count = __float_as_uint(n1.w);
-        if (count) {
-            for (uint32_t k = 0; k < count; k++) mesh_test_triangle(S, r, __ldg(S.bvh_tris + first + k), res, best_id);
-        } else if (sp + 2u <= 48u) {
-            stack[sp++] = first;
-            stack[sp++] = first + 1u;
+        // leaf: n0.w = 0x80000000 | first index into bvh_tris, n1.w = count; internal: n0.w / n1.w = left / right child
+        const uint32_t a = __float_as_uint(n0.w), b = __float_as_uint(n1.w);
+        if (a & 0x80000000u) {
+            const uint32_t first = a & 0x7FFFFFFFu;
+            for (uint32_t k = 0; k < b; k++) mesh_test_triangle(S, r, __ldg(S.bvh_tris + first + k), res, best_id);
+        } else if (sp + 2u <= 64u) {
+            stack[sp++] = a;
+            stack[sp++] = b;
         }
     }
     return res;

@@ -240,6 +240,13 @@ int f3d_viewshed(const float* heights, const float* positions_m, const f3d_views
 int f3d_shadow_mask(const float* heights, const float* geodetic_and_sun, const f3d_viewshed_options* options, uint8_t* lit,
                     double* kernel_ms);
 
+/* ---- GPU LBVH build seam (replaces GpuBvhBuilder::build, /root/reference/src/accel/lbvh_gpu/build.rs:4-76:
+ * Morton codes -> sort -> Karras link -> boxes).  Outputs (host, any may be NULL): morton[n] sorted codes, order[n] triangle ids in
+ * leaf order, left/right[n-1] child NODE indices of the internal nodes (internal i, leaf n-1+i), parent[2n-1], nodes[(2n-1)*8] =
+ * (min.xyz, w0, max.xyz, w1) per node in the traversal format (leaf boxes are padded, see csrc/f3d_lbvh.cuh). */
+int f3d_lbvh_build(const float* xyz, uint32_t nverts, const uint32_t* idx, uint32_t ntris, int32_t device, uint32_t* morton,
+                   uint32_t* order, uint32_t* left, uint32_t* right, uint32_t* parent, float* nodes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -188,6 +188,13 @@ int f3do_viewshed(const float* heights, const float* positions_m, const f3do_vie
 /* inputs: n x 4 (latitude rad, longitude rad, sun azimuth rad, sun elevation rad); lit: n (1 = sun visible). */
 int f3do_shadow_mask(const float* heights, const float* inputs, const f3do_viewshed_options* options, uint8_t* lit);
 
+/* ---- LBVH build (src/accel/lbvh_gpu, src/shaders/lbvh_morton.wgsl, lbvh_link.wgsl) ----
+ * literal_split = 1: the shader's find_split on 32-bit codes (midpoint for equal codes; boxes are not computed in this mode);
+ * 0: split on the composite key (see f3d_lbvh_oracle.c).  pad_boxes = 1: leaf boxes carry the traversal's safety pad.
+ * Outputs as f3d_lbvh_build (include/forge3d_b200.h). */
+int f3do_lbvh_build(const float* xyz, uint32_t nverts, const uint32_t* idx, uint32_t ntris, int literal_split, int pad_boxes,
+                    uint32_t* morton, uint32_t* order, uint32_t* left, uint32_t* right, uint32_t* parent, float* nodes);
+
 /* Pinned elementary functions of the numerics contract (exposed for unit tests). */
 void  f3do_sincos(float x, float* s, float* c);
 float f3do_atan2(float y, float x);

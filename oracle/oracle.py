@@ -109,7 +109,7 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (gcc, no FMA contraction)."""
-    src_mtime = max((_HERE / n).stat().st_mtime for n in ("f3d_oracle.c", "f3d_aether_oracle.c", "f3d_smoke_oracle.c", "f3d_viewshed_oracle.c", "f3d_oracle.h", "Makefile"))
+    src_mtime = max((_HERE / n).stat().st_mtime for n in ("f3d_oracle.c", "f3d_aether_oracle.c", "f3d_smoke_oracle.c", "f3d_viewshed_oracle.c", "f3d_lbvh_oracle.c", "f3d_oracle.h", "Makefile"))
     if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src_mtime:
         env = dict(os.environ)
         env.pop("CC", None)
@@ -460,6 +460,24 @@ def shadow_mask(heights, inputs, opts: dict):
     if L.f3do_shadow_mask(_fp(dem), _fp(inp), C.byref(o), lit.ctypes.data_as(C.POINTER(C.c_uint8))) != 0:
         raise OracleError("f3do_shadow_mask failed")
     return lit.astype(bool)
+
+
+def lbvh_build(vertices, indices, literal_split=False, pad_boxes=True):
+    """LBVH build restatement -> dict(morton, order, left, right, parent, nodes); see oracle/f3d_lbvh_oracle.c."""
+    L = lib()
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
+    n = t.shape[0]
+    out = dict(morton=np.zeros(n, np.uint32), order=np.zeros(n, np.uint32), left=np.zeros(max(n - 1, 0), np.uint32),
+               right=np.zeros(max(n - 1, 0), np.uint32), parent=np.zeros(2 * n - 1, np.uint32), nodes=np.zeros((2 * n - 1, 8), np.float32))
+    u = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+    u32p = C.POINTER(C.c_uint32)
+    L.f3do_lbvh_build.argtypes = [C.POINTER(C.c_float), C.c_uint32, u32p, C.c_uint32, C.c_int, C.c_int, u32p, u32p, u32p, u32p, u32p,
+                                  C.POINTER(C.c_float)]
+    if L.f3do_lbvh_build(_fp(v), v.shape[0], u(t), n, int(bool(literal_split)), int(bool(pad_boxes)), u(out["morton"]), u(out["order"]),
+                         u(out["left"]), u(out["right"]), u(out["parent"]), _fp(out["nodes"])) != 0:
+        raise OracleError("f3do_lbvh_build failed")
+    return out
 
 
 def exp2(x: float) -> float:

@@ -37,6 +37,8 @@ static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if 
 static inline unsigned atomicExch(unsigned* p, unsigned v) { unsigned o = *p; *p = v; return o; }
 static inline void __threadfence_system() {}
 static inline void __threadfence() {}
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline void __nanosleep(unsigned) {}
 static inline long long clock64() { static long long c = 0; return c += 1000; }
 
