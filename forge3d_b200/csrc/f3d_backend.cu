@@ -394,11 +394,19 @@ static int build_mesh_lbvh(const float* xyz, uint32_t nverts, const uint32_t* id
     const unsigned tb = 256;
     k_lbvh_prims<<<(padded + tb - 1) / tb, tb, 0, stream>>>(d_verts, d_idx, ntris, wmin, wext, W.keys, padded, W.tri_boxes);
     (*launches)++;
-    for (uint32_t k = 2; k <= padded; k <<= 1)
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+    // bitonic network over `padded` keys: every stage that stays inside a 2048-key tile runs in shared memory
+    // (one launch sorts all tiles; each later merge step k needs log2(k / tile) global stages and one tile launch)
+    const unsigned tiles = (padded + kBitonicTile - 1) / kBitonicTile;
+    k_lbvh_bitonic_tile<<<tiles, 1024, kBitonicTile * sizeof(unsigned long long), stream>>>(W.keys, padded, 2u);
+    (*launches)++;
+    for (uint32_t k = 2 * kBitonicTile; k <= padded; k <<= 1) {
+        for (uint32_t j = k >> 1; j >= kBitonicTile; j >>= 1) {
             k_lbvh_bitonic<<<(padded + tb - 1) / tb, tb, 0, stream>>>(W.keys, padded, k, j);
             (*launches)++;
         }
+        k_lbvh_bitonic_tile<<<tiles, 1024, kBitonicTile * sizeof(unsigned long long), stream>>>(W.keys, padded, k);
+        (*launches)++;
+    }
     if (ntris > 1u) {
         k_lbvh_link<<<(ntris - 1u + tb - 1) / tb, tb, 0, stream>>>(W.keys, ntris, W.left, W.right, W.parent);
         (*launches)++;

@@ -69,6 +69,32 @@ __global__ void k_lbvh_bitonic(unsigned long long* __restrict__ keys, uint32_t n
     if ((a > b) == ascending) { keys[i] = b; keys[partner] = a; }
 }
 
+// All stages of the network that stay inside one CTA's tile of kBitonicTile keys, in shared memory.
+//   k_from == 2: the full sort of every tile (k = 2 .. tile);  otherwise: the tail j = tile/2 .. 1 of merge step k_from.
+constexpr uint32_t kBitonicTile = 2048u;      // keys per CTA (16 KB of shared memory), 1024 threads
+__global__ void __launch_bounds__(1024) k_lbvh_bitonic_tile(unsigned long long* __restrict__ keys, uint32_t n, uint32_t k_from) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];       // kBitonicTile * 8 bytes, passed at launch
+    unsigned long long* tile = reinterpret_cast<unsigned long long*>(smem_raw);
+    const uint32_t base = blockIdx.x * kBitonicTile;
+    for (uint32_t t = threadIdx.x; t < kBitonicTile; t += blockDim.x) tile[t] = base + t < n ? keys[base + t] : 0xFFFFFFFFFFFFFFFFull;
+    __syncthreads();
+    const uint32_t k_first = k_from == 2u ? 2u : k_from, k_last = k_from == 2u ? kBitonicTile : k_from;
+    for (uint32_t k = k_first; k <= k_last; k <<= 1) {
+        for (uint32_t j = min(k >> 1, kBitonicTile >> 1); j > 0u; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < kBitonicTile / 2u; t += blockDim.x) {
+                const uint32_t lo = 2u * t - (t & (j - 1u));            // index with bit j clear
+                const uint32_t hi = lo | j;
+                const unsigned long long a = tile[lo], b = tile[hi];
+                const bool ascending = ((base + lo) & k) == 0u;
+                if ((a > b) == ascending) { tile[lo] = b; tile[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t t = threadIdx.x; t < kBitonicTile; t += blockDim.x)
+        if (base + t < n) keys[base + t] = tile[t];
+}
+
 // delta(i, j) of lbvh_link.wgsl:35-55 on the composite keys: clz of the code XOR, or 32 + clz of the index XOR when the codes
 // are equal - which is exactly the count of leading zeros of the 64-bit XOR.
 __device__ __forceinline__ int lbvh_delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
