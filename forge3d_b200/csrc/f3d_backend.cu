@@ -6,48 +6,33 @@
 // :52-84,:224-369 and src/geo/refraction.rs): Rust is not available in this image, so the layer that
 // is Rust in the reference is C++ here and exports the C ABI a Rust `extern "C"` shim would bind.
 // There is no CPU fallback anywhere in this file: every path that cannot reach a CUDA device fails.
-#include <cuda_runtime.h>
-#include <math.h>
 #include <stdarg.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
 
-#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
 #include <unordered_map>
-#include <vector>
 
-#include "../../include/forge3d_b200.h"
+#include "f3d_host.h"
 #include "f3d_kernels.cuh"
 #include "f3d_lbvh.cuh"
-#include "f3d_smoke.cuh"
-#include "f3d_viewshed.cuh"
 
 using namespace f3d;
 
 // ------------------------------------------------------------------------------------------------
 // errors
 // ------------------------------------------------------------------------------------------------
-static thread_local char g_err[640];
+thread_local char g_f3d_err[640];
+#define g_err g_f3d_err
 
-static int fail(int cls, const char* fmt, ...) {
+int f3d_fail(int cls, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
-    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    vsnprintf(g_f3d_err, sizeof g_f3d_err, fmt, ap);
     va_end(ap);
     return cls;
 }
 
-#define CUDA_TRY(expr)                                                                                     \
-    do {                                                                                                   \
-        cudaError_t _e = (expr);                                                                           \
-        if (_e != cudaSuccess)                                                                             \
-            return fail(F3D_ERR_DEVICE, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(_e), __FILE__,     \
-                        __LINE__, cudaGetErrorString(_e));                                                 \
-    } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // Device-buffer cache.  A drop-in call allocates ~0.6 GB of state per 1080p render; cudaMalloc /
@@ -64,6 +49,7 @@ struct DevCache {
     static constexpr size_t kMaxParked = 24ull << 30;
 };
 DevCache g_cache;
+}  // namespace
 
 cudaError_t cached_malloc(void** p, size_t bytes, int device) {
     bytes = std::max<size_t>((bytes + 511) & ~size_t(511), 512);
@@ -98,7 +84,7 @@ cudaError_t cached_malloc(void** p, size_t bytes, int device) {
 }
 
 // Caller guarantees no work that touches `p` is still in flight.
-void cached_free(void* p, int device, bool allow_park = true) {
+void cached_free(void* p, int device, bool allow_park) {
     if (!p) return;
     size_t bytes = 0;
     {
@@ -114,7 +100,6 @@ void cached_free(void* p, int device, bool allow_park = true) {
     }
     cudaFree(p);
 }
-}  // namespace
 
 extern "C" const char* f3d_last_error(void) { return g_err; }
 extern "C" int f3d_abi_version(void) { return F3D_ABI_VERSION; }
@@ -127,17 +112,6 @@ extern "C" int f3d_device_count(void) {
 // ------------------------------------------------------------------------------------------------
 // host math mirroring glam 0.24.2 / Rust f32 (render_terrain.rs:635-661)
 // ------------------------------------------------------------------------------------------------
-struct hv3 { float x, y, z; };
-static inline hv3 HV(const float* p) { return hv3{p[0], p[1], p[2]}; }
-static inline hv3 hsub(hv3 a, hv3 b) { return hv3{a.x - b.x, a.y - b.y, a.z - b.z}; }
-static inline float hdot(hv3 a, hv3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-static inline hv3 hcross(hv3 a, hv3 b) { return hv3{a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
-static inline float hlen(hv3 a) { return sqrtf(hdot(a, a)); }
-static inline hv3 hnorm(hv3 a) { float inv = 1.0f / hlen(a); return hv3{a.x * inv, a.y * inv, a.z * inv}; }
-static inline bool finite3(const float* v) { return isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]); }
-static inline float clamp_radiometric(float v) { return fminf(fmaxf(v, 0.0f), 65504.0f); }  // :571-576
-static inline float to_radians_f32(float d) { return d * (3.14159274101257324f / 180.0f); }
-static inline double deg2rad(double d) { return d * (3.14159265358979323846 / 180.0); }
 
 // validate_desc, render_terrain.rs:474-557 (same order, same message text)
 static int validate_desc(const f3d_terrain_desc* d) {
@@ -346,7 +320,6 @@ static void build_mesh_bvh(const float* xyz, const uint32_t* idx, uint32_t ntris
     bvh_build_rec(*B, ids, 0, ntris, tb, cen, 0);
 }
 
-static uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
 // ------------------------------------------------------------------------------------------------
 // GPU LBVH build (csrc/f3d_lbvh.cuh): d_verts (float4) and d_idx already on the device; writes 2 * (2n - 1) float4 nodes in
@@ -421,38 +394,11 @@ static int build_mesh_lbvh(const float* xyz, uint32_t nverts, const uint32_t* id
 // ------------------------------------------------------------------------------------------------
 // device terrain: packed cells + min-max levels
 // ------------------------------------------------------------------------------------------------
-struct DeviceTerrain {
-    float4* cells = nullptr;
-    float2* mm_base = nullptr;
-    int nlevels = 0;
-    uint32_t dims[kMaxLevels][2] = {};
-    size_t level_off[kMaxLevels] = {};   // in float2 units
-    size_t mm_total = 0;                 // float2 count
-    uint32_t cell_w = 0, cell_h = 0;
-    uint64_t bytes = 0;
-    // quad-packed copy of levels 0..nlevels-2 for the production traversal (f3d_trace_fast.cuh)
-    float2* quad_base = nullptr;
-    size_t quad_off[kMaxLevels] = {};
-    uint32_t quad_pitch[kMaxLevels] = {}, quad_ph[kMaxLevels] = {};
-    size_t quad_total = 0;
-    float2 root_mm = {0.0f, 0.0f};
-
-    int device = 0;
-    void release_plain() {
-        cached_free(mm_base, device);
-        mm_base = nullptr;
-    }
-    void release() {
-        cached_free(cells, device);
-        cached_free(quad_base, device);
-        cells = nullptr; quad_base = nullptr;
-        release_plain();
-    }
-};
+static_assert(kHostMaxLevels == kMaxLevels, "f3d_host.h and f3d_trace.cuh disagree on the level count");
 
 // Uploads the DEM, scans it for non-finite samples, and builds cells + pyramid on the device.
-static int build_device_terrain(const float* h_heights, uint32_t w, uint32_t h, float ex, cudaStream_t stream,
-                                DeviceTerrain* T, uint64_t* launches, bool keep_plain) {
+int build_device_terrain(const float* h_heights, uint32_t w, uint32_t h, float ex, cudaStream_t stream, DeviceTerrain* T,
+                         uint64_t* launches, bool keep_plain) {
     const uint32_t cw = w - 1, ch = h - 1;
     uint32_t lw = next_pow2(cw), lh = next_pow2(ch);
     T->cell_w = cw; T->cell_h = ch;
@@ -1241,7 +1187,7 @@ extern "C" int f3d_terrain_reference_render(const f3d_terrain_desc* desc, f3d_te
 // ------------------------------------------------------------------------------------------------
 // KAT seams
 // ------------------------------------------------------------------------------------------------
-static int select_device(int device) {
+int select_device(int device) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -1338,388 +1284,6 @@ extern "C" int f3d_debug_sched_stats(unsigned long long* out8, int reset) {
     return 0;
 }
 #endif
-
-// ------------------------------------------------------------------------------------------------
-// smoke volume ray-march (src/smoke/render.rs:6-175): host set-up in Rust f32 semantics, one kernel per render
-// ------------------------------------------------------------------------------------------------
-struct f3d_smoke {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float4* volA = nullptr;
-    float2* volB = nullptr;
-    uint8_t* d_rgba = nullptr;
-    size_t rgba_capacity = 0;
-    uint32_t dims[3] = {0, 0, 0};
-    float voxel[3] = {0, 0, 0}, origin[3] = {0, 0, 0};
-    uint32_t frame_index = 0;
-};
-
-extern "C" void f3d_smoke_destroy(f3d_smoke* s) {
-    if (!s) return;
-    cudaSetDevice(s->device);
-    if (s->stream) cudaStreamSynchronize(s->stream);
-    cached_free(s->volA, s->device); cached_free(s->volB, s->device); cached_free(s->d_rgba, s->device);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
-    if (s->stream) cudaStreamDestroy(s->stream);
-    delete s;
-}
-
-static int smoke_create_impl(const f3d_smoke_volume* v, int32_t device, f3d_smoke* s) {
-    // SmokeDomainConfig::validate, src/smoke/types.rs:29-55 (the reference's CPU voxel cap is replaced by the 2^31 index limit)
-    for (int a = 0; a < 3; a++)
-        if (v->dims[a] < 2u) return fail(F3D_ERR_RENDER, "dims[%d] must be >= 2", a);
-    const uint64_t n = (uint64_t)v->dims[0] * v->dims[1] * v->dims[2];
-    if (n > (1ull << 31)) return fail(F3D_ERR_RENDER, "smoke domain has %llu voxels, exceeding the 2^31-voxel addressing limit", (unsigned long long)n);
-    for (int a = 0; a < 3; a++)
-        if (!isfinite(v->voxel_size[a]) || v->voxel_size[a] <= 0.0f) return fail(F3D_ERR_RENDER, "voxel_size[%d] must be finite and > 0", a);
-    for (int a = 0; a < 3; a++)
-        if (!isfinite(v->origin[a])) return fail(F3D_ERR_RENDER, "origin[%d] must be finite", a);
-    if (!v->density) return fail(F3D_ERR_ARGUMENT, "density pointer is null");
-    int rc = select_device(device);
-    if (rc) return rc;
-    s->device = device;
-    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreate(&s->ev0));
-    CUDA_TRY(cudaEventCreate(&s->ev1));
-    memcpy(s->dims, v->dims, sizeof s->dims);
-    memcpy(s->voxel, v->voxel_size, sizeof s->voxel);
-    memcpy(s->origin, v->origin, sizeof s->origin);
-    s->frame_index = (uint32_t)v->frame_index;                 // `self.frame_index as u32`, render.rs:78
-    CUDA_TRY(cached_malloc((void**)&s->volA, n * sizeof(float4), device));
-    CUDA_TRY(cached_malloc((void**)&s->volB, n * sizeof(float2), device));
-    const float* host[6] = {v->density, v->temperature, v->soot, v->humidity, v->emission_rate, v->particle_age};
-    float* dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    struct Scratch {
-        float** d; cudaStream_t st; int dv;
-        ~Scratch() { cudaStreamSynchronize(st); for (int k = 0; k < 6; k++) cached_free(d[k], dv); }
-    } scratch{dev, s->stream, device};
-    for (int k = 0; k < 6; k++) {
-        if (!host[k]) continue;
-        CUDA_TRY(cached_malloc((void**)&dev[k], n * sizeof(float), device));
-        CUDA_TRY(cudaMemcpyAsync(dev[k], host[k], n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    }
-    k_smoke_pack<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], (size_t)n, s->volA, s->volB);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return 0;
-}
-
-extern "C" int f3d_smoke_create(const f3d_smoke_volume* volume, int32_t device, f3d_smoke** out) {
-    g_err[0] = 0;
-    if (!volume || !out) return fail(F3D_ERR_ARGUMENT, "null argument");
-    *out = nullptr;
-    f3d_smoke* s = new f3d_smoke();
-    int rc = smoke_create_impl(volume, device, s);
-    if (rc) { f3d_smoke_destroy(s); return rc; }
-    *out = s;
-    return 0;
-}
-
-// SmokeRenderSettings::validate, src/smoke/types.rs:268-317
-static int validate_smoke_settings(const f3d_smoke_settings* s) {
-    const char* names[11] = {"density_scale", "extinction", "scattering", "absorption", "phase_g", "step_size", "shadow_step_size",
-                             "jitter_strength", "exposure", "soot_absorption", "fire_glow"};
-    const float vals[11] = {s->density_scale, s->extinction, s->scattering, s->absorption, s->phase_g, s->step_size,
-                            s->shadow_step_size, s->jitter_strength, s->exposure, s->soot_absorption, s->fire_glow};
-    for (int i = 0; i < 11; i++)
-        if (!isfinite(vals[i])) return fail(F3D_ERR_RENDER, "%s must be finite", names[i]);
-    if (s->density_scale < 0.0f || s->extinction < 0.0f || s->scattering < 0.0f)
-        return fail(F3D_ERR_RENDER, "density_scale, extinction, and scattering must be >= 0");
-    if (s->absorption < 0.0f || s->soot_absorption < 0.0f || s->fire_glow < 0.0f)
-        return fail(F3D_ERR_RENDER, "absorption, soot_absorption, and fire_glow must be >= 0");
-    if (!(s->phase_g >= -0.99f && s->phase_g <= 0.99f)) return fail(F3D_ERR_RENDER, "phase_g must be in [-0.99, 0.99]");
-    if (s->step_size < 0.0f || s->shadow_step_size < 0.0f) return fail(F3D_ERR_RENDER, "step sizes must be >= 0");
-    if (s->max_steps == 0 || s->shadow_steps == 0) return fail(F3D_ERR_RENDER, "max_steps and shadow_steps must be >= 1");
-    if (!(s->jitter_strength >= 0.0f && s->jitter_strength <= 1.0f)) return fail(F3D_ERR_RENDER, "jitter_strength must be in [0, 1]");
-    for (int a = 0; a < 3; a++)
-        if (!isfinite(s->thin_color[a]) || s->thin_color[a] < 0.0f) return fail(F3D_ERR_RENDER, "thin_color[%d] must be finite and >= 0", a);
-    for (int a = 0; a < 3; a++)
-        if (!isfinite(s->dense_color[a]) || s->dense_color[a] < 0.0f) return fail(F3D_ERR_RENDER, "dense_color[%d] must be finite and >= 0", a);
-    return 0;
-}
-
-static hv3 hnorm_or_zero(hv3 a) {   // glam Vec3::normalize_or_zero
-    const float rcp = 1.0f / hlen(a);
-    if (isfinite(rcp) && rcp > 0.0f) return hv3{a.x * rcp, a.y * rcp, a.z * rcp};
-    return hv3{0.0f, 0.0f, 0.0f};
-}
-
-static void smoke_common_params(const f3d_smoke* s, const f3d_smoke_settings* st, SmokeParams* P) {
-    P->volA = s->volA; P->volB = s->volB;
-    for (int a = 0; a < 3; a++) {
-        P->dims[a] = s->dims[a]; P->voxel[a] = s->voxel[a]; P->origin[a] = s->origin[a];
-        P->bmax[a] = s->origin[a] + (float)s->dims[a] * s->voxel[a];                       // bounds_max, types.rs:399-405
-    }
-    SmokeSettings& S = P->s;
-    S.density_scale = st->density_scale; S.extinction = st->extinction; S.scattering = st->scattering; S.absorption = st->absorption;
-    S.phase_g = st->phase_g; S.max_steps = st->max_steps; S.self_shadow = st->self_shadow ? 1u : 0u; S.shadow_steps = st->shadow_steps;
-    S.jitter_strength = st->jitter_strength; S.exposure = st->exposure; S.soot_absorption = st->soot_absorption; S.fire_glow = st->fire_glow;
-    memcpy(S.thin_color, st->thin_color, sizeof S.thin_color);
-    memcpy(S.dense_color, st->dense_color, sizeof S.dense_color);
-    const float min_step = fmaxf(fminf(fminf(fminf(INFINITY, s->voxel[0]), s->voxel[1]), s->voxel[2]), 1.0e-4f);   // render.rs:43-59
-    P->step = st->step_size > 0.0f ? st->step_size : min_step * 0.75f;
-    P->shadow_step = st->shadow_step_size > 0.0f ? st->shadow_step_size : P->step * 2.0f;
-    P->frame_index = s->frame_index;
-}
-
-static int smoke_launch(f3d_smoke* s, SmokeParams* P, uint32_t width, uint32_t height, uint8_t* rgba, double* kernel_ms) {
-    if ((uint64_t)width * height > (1ull << 31)) return fail(F3D_ERR_ARGUMENT, "image of %ux%u pixels exceeds the 2^31-pixel addressing limit", width, height);
-    const size_t bytes = (size_t)width * height * 4;
-    CUDA_TRY(cudaSetDevice(s->device));
-    if (s->rgba_capacity < bytes) {
-        cudaStreamSynchronize(s->stream);
-        cached_free(s->d_rgba, s->device);
-        s->d_rgba = nullptr; s->rgba_capacity = 0;
-        CUDA_TRY(cached_malloc((void**)&s->d_rgba, bytes, s->device));
-        s->rgba_capacity = bytes;
-    }
-    P->W = width; P->H = height; P->rgba = s->d_rgba;
-    const dim3 grid((width + 15u) / 16u, (height + 7u) / 8u);
-    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-    k_smoke_march<<<grid, kSmokeThreads, 0, s->stream>>>(*P);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(rgba, s->d_rgba, bytes, cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    if (kernel_ms) {
-        float ms = 0.0f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-        *kernel_ms = ms;
-    }
-    return 0;
-}
-
-extern "C" int f3d_smoke_raymarch_rgba(f3d_smoke* s, const f3d_smoke_settings* st, uint32_t width, uint32_t height,
-                                       const float camera_pos[3], const float target[3], const float up_in[3], float fovy_deg,
-                                       const float sun_direction[3], uint8_t* rgba, double* kernel_ms) {
-    g_err[0] = 0;
-    if (!s || !st || !camera_pos || !target || !up_in || !sun_direction || !rgba) return fail(F3D_ERR_ARGUMENT, "null argument");
-    int rc = validate_smoke_settings(st);                                                    // render.rs:18-41, same order and text
-    if (rc) return rc;
-    if (width == 0 || height == 0) return fail(F3D_ERR_RENDER, "width and height must be >= 1");
-    if (!isfinite(fovy_deg) || fovy_deg <= 0.0f || fovy_deg >= 179.0f) return fail(F3D_ERR_RENDER, "fovy_deg must be finite and in (0, 179)");
-    const hv3 eye = HV(camera_pos);
-    const hv3 forward = hnorm_or_zero(hsub(HV(target), eye));
-    if (hdot(forward, forward) < 1.0e-12f) return fail(F3D_ERR_RENDER, "camera_pos and target must not be equal");
-    const hv3 up = hnorm_or_zero(HV(up_in));
-    if (hdot(up, up) < 1.0e-12f) return fail(F3D_ERR_RENDER, "up vector must not be zero");
-    const hv3 right = hnorm_or_zero(hcross(forward, up));
-    const hv3 camera_up = hnorm_or_zero(hcross(right, forward));
-    const hv3 sun = hnorm_or_zero(HV(sun_direction));
-    if (hdot(sun, sun) < 1.0e-12f) return fail(F3D_ERR_RENDER, "sun_direction must not be zero");
-    SmokeParams P{};
-    smoke_common_params(s, st, &P);
-    P.projection = 0u;
-    P.eye[0] = eye.x; P.eye[1] = eye.y; P.eye[2] = eye.z;
-    P.forward[0] = forward.x; P.forward[1] = forward.y; P.forward[2] = forward.z;
-    P.right[0] = right.x; P.right[1] = right.y; P.right[2] = right.z;
-    P.up[0] = camera_up.x; P.up[1] = camera_up.y; P.up[2] = camera_up.z;
-    P.tan_half_fov = tanf(to_radians_f32(fovy_deg) * 0.5f);
-    P.aspect = (float)width / (float)height;
-    P.sun_dir[0] = sun.x; P.sun_dir[1] = sun.y; P.sun_dir[2] = sun.z;
-    return smoke_launch(s, &P, width, height, rgba, kernel_ms);
-}
-
-extern "C" int f3d_smoke_raymarch_projection_rgba(f3d_smoke* s, const f3d_smoke_settings* st, uint32_t width, uint32_t height,
-                                                  const float view_direction[3], const float sun_direction[3], uint8_t* rgba,
-                                                  double* kernel_ms) {
-    g_err[0] = 0;
-    if (!s || !st || !view_direction || !sun_direction || !rgba) return fail(F3D_ERR_ARGUMENT, "null argument");
-    int rc = validate_smoke_settings(st);                                                    // render.rs:111-123
-    if (rc) return rc;
-    if (width == 0 || height == 0) return fail(F3D_ERR_RENDER, "width and height must be >= 1");
-    const hv3 dir = hnorm_or_zero(HV(view_direction));
-    if (hdot(dir, dir) < 1.0e-12f) return fail(F3D_ERR_RENDER, "view_direction must not be zero");
-    const hv3 sun = hnorm_or_zero(HV(sun_direction));
-    if (hdot(sun, sun) < 1.0e-12f) return fail(F3D_ERR_RENDER, "sun_direction must not be zero");
-    SmokeParams P{};
-    smoke_common_params(s, st, &P);
-    P.projection = 1u;
-    P.dir[0] = dir.x; P.dir[1] = dir.y; P.dir[2] = dir.z;
-    const hv3 ext = hv3{P.bmax[0] - P.origin[0], P.bmax[1] - P.origin[1], P.bmax[2] - P.origin[2]};
-    P.diagonal = fmaxf(hlen(ext), P.step * 2.0f);                                            // render.rs:138
-    P.sun_dir[0] = sun.x; P.sun_dir[1] = sun.y; P.sun_dir[2] = sun.z;
-    return smoke_launch(s, &P, width, height, rgba, kernel_ms);
-}
-
-// ------------------------------------------------------------------------------------------------
-// HELIOS viewshed / shadow mask (src/terrain/analysis/viewshed.rs): validation, physics terms, one kernel
-// ------------------------------------------------------------------------------------------------
-// physics_terms, viewshed.rs:54-78 (+ RefractionModel::k, principal_radii_m: src/geo/refraction.rs:6-13,100-144)
-static int viewshed_physics(const f3d_viewshed_options* o, float physics[4]) {
-    if (o->earth_model < 0 || o->earth_model > 2) return fail(F3D_ERR_ARGUMENT, "unsupported earth_model %d", o->earth_model);
-    if (o->refraction_model < 0 || o->refraction_model > 3) return fail(F3D_ERR_ARGUMENT, "unsupported refraction_model %d", o->refraction_model);
-    if (o->earth_model == F3D_EARTH_FLAT && o->refraction_model != F3D_REFRACTION_NONE)
-        return fail(F3D_ERR_RENDER, "flat earth only supports refraction_model='none'");
-    double k;
-    if (o->refraction_model == F3D_REFRACTION_NONE) k = 0.0;
-    else if (o->refraction_model == F3D_REFRACTION_EFFECTIVE_RADIUS) k = o->refraction_k;
-    else {
-        if (!isfinite(o->pressure_mbar) || o->pressure_mbar <= 0.0 || o->temperature_c <= -273.15)
-            return fail(F3D_ERR_RENDER, "pressure must be positive and temperature above absolute zero");
-        k = (o->refraction_model == F3D_REFRACTION_BENNETT ? 0.13 : 1.0 / 7.0) * (o->pressure_mbar / 1013.25) * (288.15 / (273.15 + o->temperature_c));
-    }
-    if (!(isfinite(k) && k < 1.0)) return fail(F3D_ERR_RENDER, "refraction k must be finite and less than 1");
-    double inv_m = 0.0, inv_p = 0.0;
-    if (o->earth_model == F3D_EARTH_SPHERE) {
-        if (!(isfinite(o->sphere_radius_m) && o->sphere_radius_m > 0.0)) return fail(F3D_ERR_RENDER, "sphere radius must be finite and positive");
-        inv_m = inv_p = 1.0 / o->sphere_radius_m;
-    } else if (o->earth_model == F3D_EARTH_ELLIPSOID) {
-        if (!isfinite(o->earth_latitude_deg) || o->earth_latitude_deg < -90.0 || o->earth_latitude_deg > 90.0)
-            return fail(F3D_ERR_RENDER, "latitude must be finite and in [-90, 90]");
-        const double a_m = 6378137.0, e2 = 6.6943799901413165e-3;
-        const double sp = sin(deg2rad(o->earth_latitude_deg));
-        const double w = sqrt(1.0 - e2 * (sp * sp));
-        inv_m = 1.0 / (a_m * (1.0 - e2) / (w * w * w));
-        inv_p = 1.0 / (a_m / w);
-    }
-    physics[0] = (float)inv_m; physics[1] = (float)inv_p; physics[2] = (float)(1.0 - k);
-    physics[3] = o->earth_model == F3D_EARTH_FLAT ? 0.0f : 1.0f;
-    return 0;
-}
-
-// validate_common, viewshed.rs:80-143 (the element counts are implied by the pointer contract here)
-static int viewshed_validate(const float* heights, const float* extra, size_t extra_per_cell, bool extra_is_position,
-                             const f3d_viewshed_options* o, float physics[4]) {
-    if (o->width < 2 || o->height < 2 || o->width - 1 > 8192u || o->height - 1 > 8192u)
-        return fail(F3D_ERR_RENDER,
-                    "DEM/position lengths do not match supported dimensions %ux%u (both dimensions must be at least 2 and packed traversal supports at most 8192 cells per axis)",
-                    o->width, o->height);
-    const size_t n = (size_t)o->width * o->height;
-    bool finite = true;
-    for (size_t i = 0; i < n && finite; i++) finite = isfinite(heights[i]);
-    for (size_t i = 0; i < n * extra_per_cell && finite; i++) finite = isfinite(extra[i]);
-    if (!finite) {
-        if (!extra_is_position) {
-            bool extra_ok = true;
-            for (size_t i = 0; i < n * extra_per_cell && extra_ok; i++) extra_ok = isfinite(extra[i]);
-            if (!extra_ok) return fail(F3D_ERR_RENDER, "shadow-mask geodetic/solar inputs do not match the DEM");
-        }
-        return fail(F3D_ERR_RENDER, "DEM heights and geodesic positions must be finite (%zu heights)", n);
-    }
-    const float f[12] = {o->observer_x, o->observer_y, o->observer_height_m, o->target_height_m, o->max_distance_m, o->observer_latitude_rad,
-                         o->observer_longitude_rad, o->left_unwrapped_deg, o->top_deg, o->longitude_step_deg, o->latitude_step_deg,
-                         o->geodesic_sphere_radius_m};
-    bool ok = true;
-    for (float v : f) ok = ok && isfinite(v);
-    if (!ok || o->observer_x < -0.5f || o->observer_x > (float)o->width - 0.5f || o->observer_y < -0.5f || o->observer_y > (float)o->height - 0.5f ||
-        o->observer_height_m < 0.0f || o->target_height_m < 0.0f || o->max_distance_m <= 0.0f || o->longitude_step_deg <= 0.0f ||
-        o->latitude_step_deg <= 0.0f || o->geodesic_sphere_radius_m < 0.0f)
-        return fail(F3D_ERR_RENDER, "viewshed dimensions, observer, heights, spacing, and distance are invalid");
-    return viewshed_physics(o, physics);
-}
-
-// height_at(observer.xy), terrain_viewshed.wgsl:24-43, on the host (one value for the whole dispatch)
-static float viewshed_height_at(const float* h, uint32_t w, uint32_t hh, float px, float py) {
-    const float x = fminf(fmaxf(px, 0.0f), (float)(w - 1u)), y = fminf(fmaxf(py, 0.0f), (float)(hh - 1u));
-    const uint32_t x0 = (uint32_t)floorf(x), y0 = (uint32_t)floorf(y);
-    const uint32_t x1 = std::min(x0 + 1u, w - 1u), y1 = std::min(y0 + 1u, hh - 1u);
-    const float fx = x - (float)x0, fy = y - (float)y0;
-    auto mix = [](float a, float b, float t) { const float d = b - a; const float s = d * t; return a + s; };
-    return mix(mix(h[(size_t)y0 * w + x0], h[(size_t)y0 * w + x1], fx), mix(h[(size_t)y1 * w + x0], h[(size_t)y1 * w + x1], fx), fy);
-}
-
-struct ViewshedRun {
-    DeviceTerrain T;
-    float* d_heights = nullptr;
-    void* d_extra = nullptr;
-    void* d_out = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int device = 0;
-    ~ViewshedRun() {
-        cudaDeviceSynchronize();
-        T.release();
-        cached_free(d_heights, device); cached_free(d_extra, device); cached_free(d_out, device);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
-    }
-};
-
-static int viewshed_setup(const float* heights, const void* extra, size_t extra_bytes, size_t out_bytes, const f3d_viewshed_options* o,
-                          const float physics[4], ViewshedRun* R, ViewshedParams* P) {
-    int rc = select_device(o->device);
-    if (rc) return rc;
-    R->device = o->device;
-    uint64_t launches = 0;
-    // the tracked DEM + min-max chain of TerrainMinMaxPyramid::from_heightfield (viewshed.rs:207-213), built on the device
-    if ((rc = build_device_terrain(heights, o->width, o->height, 1.0f, nullptr, &R->T, &launches, true))) return rc;
-    const size_t n = (size_t)o->width * o->height;
-    CUDA_TRY(cached_malloc((void**)&R->d_heights, n * sizeof(float), o->device));
-    CUDA_TRY(cached_malloc(&R->d_extra, extra_bytes, o->device));
-    CUDA_TRY(cached_malloc(&R->d_out, out_bytes, o->device));
-    CUDA_TRY(cudaMemcpy(R->d_heights, heights, n * sizeof(float), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(R->d_extra, extra, extra_bytes, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaEventCreate(&R->ev0));
-    CUDA_TRY(cudaEventCreate(&R->ev1));
-    P->w = o->width; P->h = o->height;
-    P->observer[0] = o->observer_x; P->observer[1] = o->observer_y; P->observer[2] = o->observer_height_m; P->observer[3] = o->target_height_m;
-    P->metric[0] = o->max_distance_m; P->metric[1] = o->longitude_step_deg; P->metric[2] = o->latitude_step_deg; P->metric[3] = o->geodesic_sphere_radius_m;
-    memcpy(P->physics, physics, sizeof P->physics);
-    P->geodetic[0] = o->observer_latitude_rad; P->geodetic[1] = o->observer_longitude_rad; P->geodetic[2] = o->left_unwrapped_deg; P->geodetic[3] = o->top_deg;
-    P->observer_elevation = viewshed_height_at(heights, o->width, o->height, o->observer_x, o->observer_y) + o->observer_height_m;
-    P->heights = R->d_heights; P->cells = R->T.cells;
-    for (int l = 0; l < 16; l++) {
-        P->mm[l] = l < R->T.nlevels ? R->T.mm_base + R->T.level_off[l] : nullptr;
-        P->mm_pitch[l] = l < R->T.nlevels ? R->T.dims[l][0] : 0u;
-    }
-    P->root_level = (uint32_t)R->T.nlevels - 1u;
-    return 0;
-}
-
-extern "C" int f3d_viewshed(const float* heights, const float* positions_m, const f3d_viewshed_options* o, uint8_t* visibility,
-                            float* drop, float* gain, float* horizon, double* kernel_ms) {
-    g_err[0] = 0;
-    if (!heights || !positions_m || !o || !visibility || !drop || !gain || !horizon) return fail(F3D_ERR_ARGUMENT, "null argument");
-    float physics[4];
-    int rc = viewshed_validate(heights, positions_m, 2, true, o, physics);
-    if (rc) return rc;
-    const size_t n = (size_t)o->width * o->height;
-    ViewshedRun R;
-    ViewshedParams P{};
-    if ((rc = viewshed_setup(heights, positions_m, n * sizeof(float2), n * sizeof(float4), o, physics, &R, &P))) return rc;
-    const dim3 grid((o->width + 7u) / 8u, (o->height + 7u) / 8u);
-    CUDA_TRY(cudaEventRecord(R.ev0, 0));
-    k_viewshed<<<grid, kViewshedThreads>>>(P, (const float2*)R.d_extra, (float4*)R.d_out);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(R.ev1, 0));
-    std::vector<float4> cells(n);
-    CUDA_TRY(cudaMemcpy(cells.data(), R.d_out, n * sizeof(float4), cudaMemcpyDeviceToHost));
-    if (kernel_ms) { float ms = 0.0f; CUDA_TRY(cudaEventElapsedTime(&ms, R.ev0, R.ev1)); *kernel_ms = ms; }
-    for (size_t i = 0; i < n; i++) {
-        uint32_t v;
-        memcpy(&v, &cells[i].x, 4);
-        if (v > 1u) return fail(F3D_ERR_RENDER, "viewshed geodesic leaves the DEM footprint");   // viewshed.rs:320-327
-    }
-    for (size_t i = 0; i < n; i++) {
-        uint32_t v;
-        memcpy(&v, &cells[i].x, 4);
-        visibility[i] = v != 0u; drop[i] = cells[i].y; gain[i] = cells[i].z; horizon[i] = cells[i].w;
-    }
-    return 0;
-}
-
-extern "C" int f3d_shadow_mask(const float* heights, const float* geodetic_and_sun, const f3d_viewshed_options* o, uint8_t* lit,
-                               double* kernel_ms) {
-    g_err[0] = 0;
-    if (!heights || !geodetic_and_sun || !o || !lit) return fail(F3D_ERR_ARGUMENT, "null argument");
-    float physics[4];
-    int rc = viewshed_validate(heights, geodetic_and_sun, 4, false, o, physics);
-    if (rc) return rc;
-    const size_t n = (size_t)o->width * o->height;
-    ViewshedRun R;
-    ViewshedParams P{};
-    if ((rc = viewshed_setup(heights, geodetic_and_sun, n * sizeof(float4), n, o, physics, &R, &P))) return rc;
-    const dim3 grid((o->width + 7u) / 8u, (o->height + 7u) / 8u);
-    CUDA_TRY(cudaEventRecord(R.ev0, 0));
-    k_shadow_mask<<<grid, kViewshedThreads>>>(P, (const float4*)R.d_extra, (uint8_t*)R.d_out);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(R.ev1, 0));
-    CUDA_TRY(cudaMemcpy(lit, R.d_out, n, cudaMemcpyDeviceToHost));
-    if (kernel_ms) { float ms = 0.0f; CUDA_TRY(cudaEventElapsedTime(&ms, R.ev0, R.ev1)); *kernel_ms = ms; }
-    return 0;
-}
 
 // ------------------------------------------------------------------------------------------------
 // LBVH test seam: builds the tree for a host mesh and returns Morton order, topology and boxes

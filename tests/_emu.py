@@ -73,20 +73,24 @@ def trace_rays(heights, spacing, origin_xz, exaggeration, rays, *, any_hit, appl
 # ---------------------------------------------------------------------------------------------------------------
 def build_backend(defines=()) -> Path:
     deps = [EMU / n for n in ("gen_backend.py", "simt.cpp", "simt.h", "cuda_runtime.h", "cuda_fake_runtime.h", "cuda_fp16.h")]
-    deps += sorted(CSRC.glob("f3d_*.cu*")) + [ROOT / "include" / "forge3d_b200.h"]
+    deps += sorted(CSRC.glob("f3d_*.cu*")) + [CSRC / "f3d_host.h", ROOT / "include" / "forge3d_b200.h"]
     tag = _tag(defines, deps)
     out = BUILD / f"libforge3d_b200_emu_{tag}.so"
     if out.exists():
         return out
     BUILD.mkdir(exist_ok=True)
-    gen = BUILD / f"f3d_backend_emu_{tag}.cpp"
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
     import sys
-    subprocess.run([sys.executable, str(EMU / "gen_backend.py"), str(CSRC / "f3d_backend.cu"), str(gen)], check=True, env=env)
+    from forge3d_b200.build import SOURCES
+    gens = []
+    for name in SOURCES:          # every translation unit of the product library, launches rewritten for the interpreter
+        gen = BUILD / f"{Path(name).stem}_emu_{tag}.cpp"
+        subprocess.run([sys.executable, str(EMU / "gen_backend.py"), str(CSRC / name), str(gen)], check=True, env=env)
+        gens.append(str(gen))
     cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-DEMU_SIMT", f"-I{EMU}",
-           f"-I{CSRC}", f"-I{ROOT / 'include'}", *[f"-D{d}" for d in defines], "-o", str(out), str(gen), str(EMU / "simt.cpp")]
+           f"-I{CSRC}", f"-I{ROOT / 'include'}", *[f"-D{d}" for d in defines], "-o", str(out), *gens, str(EMU / "simt.cpp")]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
     if res.returncode != 0:
         raise RuntimeError(f"g++ failed:\n{' '.join(cmd)}\n{res.stdout}")

@@ -53,6 +53,7 @@ if __name__ == "__main__":
     src_path, dst_path = Path(sys.argv[1]), Path(sys.argv[2])
     text = transform(src_path.read_text())
     assert "<<<" not in text
-    footer = "\n// dynamic shared memory of the CTA being interpreted (the kernels declare it `extern __shared__`)\n" \
-             "namespace f3d { alignas(16) unsigned char smem_raw[256 * 1024]; }\n"
+    # dynamic shared memory of the CTA being interpreted (the kernels declare it `extern __shared__`): defined once
+    footer = ("\n// dynamic shared memory of the CTA being interpreted (the kernels declare it `extern __shared__`)\n"
+              "namespace f3d { alignas(16) unsigned char smem_raw[256 * 1024]; }\n") if src_path.name == "f3d_backend.cu" else ""
     dst_path.write_text(f"// GENERATED from {src_path.name} by tests/c/emu/gen_backend.py - do not edit\n" + text + footer)

@@ -13,7 +13,7 @@ sys.path.insert(0, str(ROOT))
 def main():
     from forge3d_b200 import build as b
 
-    cmd = [b._nvcc(), "-Xptxas", "-v", *b.NVCC_FLAGS, "-o", "/tmp/_f3d_ptxas.so", str(b.CSRC / b.SOURCES[0])]
+    cmd = [b._nvcc(), "-Xptxas", "-v", *b.NVCC_FLAGS, "-o", "/tmp/_f3d_ptxas.so", *[str(b.CSRC / n) for n in b.SOURCES]]
     txt = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, check=True).stdout
     rows, cur = [], None
     for line in txt.splitlines():
