@@ -200,3 +200,52 @@ def test_gpu_viewshed_and_shadow_mask_are_bit_identical_to_the_oracle(model):
     lit = V.compute_shadow_mask(sh, sinp, sopts)
     assert np.array_equal(lit, oracle.shadow_mask(sh, sinp, sopts))
     assert 0.02 < g["visibility"].mean() < 0.98 and 0.05 < lit.mean() < 0.98 and g["kernel_ms"] > 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# oracle pin (arithmetic): an independent statement-by-statement restatement of the WGSL, bit for bit
+# ---------------------------------------------------------------------------------------------------------------
+def _physics(opts):
+    """physics_terms (viewshed.rs:54-78) in float64, independently of the C oracle."""
+    k = {"none": 0.0, "effective_radius": opts["refraction_k"]}.get(opts["refraction_model"])
+    if k is None:
+        base = 0.13 if opts["refraction_model"] == "bennett" else 1.0 / 7.0
+        k = base * (opts["pressure_mbar"] / 1013.25) * (288.15 / (273.15 + opts["temperature_c"]))
+    if opts["earth_model"] == "flat":
+        inv_m = inv_p = 0.0
+    elif opts["earth_model"] == "sphere":
+        inv_m = inv_p = 1.0 / opts["sphere_radius_m"]
+    else:
+        phi, e2 = math.radians(opts["earth_latitude_deg"]), 6.694_379_990_141_316_5e-3
+        w = math.sqrt(1.0 - e2 * math.sin(phi) ** 2)
+        inv_m, inv_p = 1.0 / (6_378_137.0 * (1.0 - e2) / w ** 3), 1.0 / (6_378_137.0 / w)
+    return [inv_m, inv_p, 1.0 - k, 0.0 if opts["earth_model"] == "flat" else 1.0]
+
+
+@pytest.mark.parametrize("model", sorted(MODELS))
+def test_oracle_matches_the_wgsl_mirror_bit_for_bit(model):
+    import _wgsl_mirror_viewshed as M
+
+    dem = _rough_dem(11, 14, 8)
+    kw = dict(bounds=(7.0, 45.9, 7.2, 46.05), height_system="ellipsoidal", observer_height=9.0, target_height=1.0, **MODELS[model])
+    h, pos, opts = V.viewshed_inputs(dem, (45.97, 7.08), **kw)
+    o = oracle.viewshed(h, pos, opts)
+    levels, _, _ = oracle.build_minmax(h)
+    atan2 = lambda y, x: np.float32(oracle.lib().f3do_atan2(float(y), float(x)))
+    S = M.Scene(h, opts, _physics(opts), levels, atan2)
+    with np.errstate(all="ignore"):
+        for y in range(h.shape[0]):
+            for x in range(h.shape[1]):
+                vis, drop, gain, horizon = M.viewshed_cell(S, pos, x, y)
+                assert vis == int(o["visibility"][y, x]), (x, y)
+                for got, want in ((drop, o["curvature_drop_m"]), (gain, o["refraction_gain_m"]), (horizon, o["horizon_distance_m"])):
+                    assert np.float32(got).tobytes() == want[y, x].tobytes(), (x, y)
+        skw = {k: v for k, v in kw.items() if k not in ("observer_height", "target_height")}
+        rng = np.random.default_rng(4)
+        sh, sinp, sopts = V.shadow_mask_inputs(dem, rng.uniform(70.0, 290.0, dem.shape), rng.uniform(-1.0, 30.0, dem.shape), **skw)
+        so = oracle.shadow_mask(sh, sinp, sopts)
+        S2 = M.Scene(sh, sopts, _physics(sopts), levels, atan2)
+        for y in range(h.shape[0]):
+            for x in range(h.shape[1]):
+                assert M.shadow_cell(S2, sinp, x, y) == bool(so[y, x]), (x, y)
+    assert 0 < o["visibility"].sum() < o["visibility"].size and 0 < so.sum() < so.size
