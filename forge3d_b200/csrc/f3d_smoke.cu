@@ -17,6 +17,8 @@ struct f3d_smoke {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float4* volA = nullptr;
     float2* volB = nullptr;
+    uint8_t* occ = nullptr;           // brick occupancy for the exact empty-space skip (NULL = disabled)
+    uint32_t occ_dims[3] = {0, 0, 0};
     uint8_t* d_rgba = nullptr;
     size_t rgba_capacity = 0;
     uint32_t dims[3] = {0, 0, 0};
@@ -29,6 +31,7 @@ extern "C" void f3d_smoke_destroy(f3d_smoke* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cached_free(s->volA, s->device); cached_free(s->volB, s->device); cached_free(s->d_rgba, s->device);
+    cached_free(s->occ, s->device);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -69,9 +72,25 @@ static int smoke_create_impl(const f3d_smoke_volume* v, int32_t device, f3d_smok
         CUDA_TRY(cached_malloc((void**)&dev[k], n * sizeof(float), device));
         CUDA_TRY(cudaMemcpyAsync(dev[k], host[k], n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     }
-    k_smoke_pack<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], (size_t)n, s->volA, s->volB);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    for (int a = 0; a < 3; a++) s->occ_dims[a] = (v->dims[a] + 3u) / 4u;
+    const size_t nbricks = (size_t)s->occ_dims[0] * s->occ_dims[1] * s->occ_dims[2];
+    uint32_t* d_huge = nullptr;
+    CUDA_TRY(cached_malloc((void**)&s->occ, nbricks, device));
+    CUDA_TRY(cached_malloc((void**)&d_huge, sizeof(uint32_t), device));
+    CUDA_TRY(cudaMemsetAsync(s->occ, 0, nbricks, s->stream));
+    CUDA_TRY(cudaMemsetAsync(d_huge, 0, sizeof(uint32_t), s->stream));
+    k_smoke_pack<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], (size_t)n, v->dims[0],
+                                                                     v->dims[1], s->volA, s->volB, s->occ, s->occ_dims[0], s->occ_dims[1], d_huge);
+    uint32_t huge = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&huge, d_huge, sizeof huge, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cached_free(d_huge, device);
+    CUDA_TRY(e);
+    if (huge || getenv("F3D_B200_SMOKE_NO_SKIP")) {         // 0 * inf would be NaN in the reference: march every step literally
+        cached_free(s->occ, device);
+        s->occ = nullptr;
+    }
     return 0;
 }
 
@@ -111,6 +130,7 @@ static int validate_smoke_settings(const f3d_smoke_settings* s) {
 
 static void smoke_common_params(const f3d_smoke* s, const f3d_smoke_settings* st, SmokeParams* P) {
     P->volA = s->volA; P->volB = s->volB;
+    P->occ = s->occ; P->occ_dims[0] = s->occ_dims[0]; P->occ_dims[1] = s->occ_dims[1];
     for (int a = 0; a < 3; a++) {
         P->dims[a] = s->dims[a]; P->voxel[a] = s->voxel[a]; P->origin[a] = s->origin[a];
         P->bmax[a] = s->origin[a] + (float)s->dims[a] * s->voxel[a];                       // bounds_max, types.rs:399-405

@@ -203,3 +203,27 @@ def test_gpu_march_is_bit_identical_to_the_oracle(case):
     dom.close()
     assert np.array_equal(g, o) and np.array_equal(gp, op)
     assert (o[..., 3] > 0).sum() > 100 and dom.last_kernel_ms > 0.0
+
+
+def test_emulated_empty_space_skip_is_exact_and_backs_off_for_huge_values(monkeypatch):
+    """The brick-occupancy skip (f3d_smoke.cuh) must not change a pixel: same image with the skip disabled, and a volume whose
+    empty region carries an absurd soot value (0 * inf = NaN in the reference's optical depth) is marched literally."""
+    dom = _random_domain(31, dims=(24, 18, 21))
+    assert (dom.density == 0).mean() > 0.3                     # a good part of the volume is empty space
+    st = SmokeRenderSettings(shadow_steps=12)
+    cam = dict(camera_pos=(-25.0, 16.0, 8.0), target=(8.0, 7.0, 40.0))
+    o = oracle.smoke_raymarch_rgba(dom, st, 40, 26, **cam)
+    with _emu.emulated_backend():
+        a = dom.render_rgba(40, 26, settings=st, **cam)
+        dom.close()
+        monkeypatch.setenv("F3D_B200_SMOKE_NO_SKIP", "1")
+        b = dom.render_rgba(40, 26, settings=st, **cam)
+        dom.close()
+        monkeypatch.delenv("F3D_B200_SMOKE_NO_SKIP")
+        soot = dom.soot.copy()
+        soot[dom.density == 0] = 3.0e38                        # finite, but 3e38 * soot_absorption * ... overflows next to density 0
+        dom.set_field("soot", soot)
+        c = dom.render_rgba(40, 26, settings=st, **cam)
+        dom.close()
+    assert np.array_equal(a, o) and np.array_equal(b, o)
+    assert np.array_equal(c, oracle.smoke_raymarch_rgba(dom, st, 40, 26, **cam))
