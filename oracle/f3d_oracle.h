@@ -195,6 +195,32 @@ int f3do_shadow_mask(const float* heights, const float* inputs, const f3do_views
 int f3do_lbvh_build(const float* xyz, uint32_t nverts, const uint32_t* idx, uint32_t ntris, int literal_split, int pad_boxes,
                     uint32_t* morton, uint32_t* order, uint32_t* left, uint32_t* right, uint32_t* parent, float* nodes);
 
+/* ---- wavefront multi-bounce path tracer (src/path_tracing/wavefront, pt_*.wgsl, adjudication.rs) ----
+ * Field for field the scene f3d_wavefront_scene of include/forge3d_b200.h describes. */
+typedef struct {
+    float cam_origin[3], cam_forward[3], cam_right[3], cam_up[3];
+    float fov_y_rad, exposure;
+    uint32_t seed_hi, seed_lo;
+    const float* spheres; uint32_t nspheres;       /* 20 floats each: WavefrontGpuSphere, reference_scene.rs:101-117 */
+    const float* dir_lights; uint32_t ndir;        /* 8 floats each: direction, intensity, colour, importance */
+    const float* area_lights; uint32_t narea;      /* 12 floats each: position, radius, normal, intensity, colour, importance */
+    const float* importance; uint32_t nimportance; /* per material slot */
+    float environment[16];                         /* env_ground, env_sky, miss_ground, miss_sky (vec4 each) */
+    const float* mesh_xyz; uint32_t mesh_nverts;
+    const uint32_t* mesh_idx; uint32_t mesh_ntris;
+    const float* instances; uint32_t ninstances;   /* 36 words each: object_to_world, world_to_object (column-major), blas, material, pad */
+} f3do_wavefront_scene;
+/* Adds frames [first_frame, first_frame + num_frames) into accum_io (W*H*4 floats, caller-zeroed before the first call); when
+ * hdr_out / rgba8_out are given they receive mean = accum / spp_frames (alpha 1) and its Reinhard + sRGB resolve.
+ * stats_out[3] = {rays traced, most rays in one frame, fewest iterations in one frame}. */
+int f3do_wavefront_render(const f3do_wavefront_scene* scene, uint32_t width, uint32_t height, uint32_t spp_frames, uint32_t first_frame,
+                          uint32_t num_frames, float* accum_io, float* hdr_out, uint8_t* rgba8_out, uint64_t* stats_out);
+const char* f3do_wavefront_last_error(void);
+void f3do_wavefront_sobol2(uint32_t i, float* x, float* y);
+uint32_t f3do_wavefront_splitmix32(uint32_t x);
+float f3do_log2(float x);          /* pinned log2 (Cephes log2f kernel), normal positive arguments */
+float f3do_pow(float x, float y);  /* f3do_exp2(y * f3do_log2(x)) */
+
 /* Pinned elementary functions of the numerics contract (exposed for unit tests). */
 void  f3do_sincos(float x, float* s, float* c);
 float f3do_atan2(float y, float x);

@@ -480,6 +480,67 @@ def lbvh_build(vertices, indices, literal_split=False, pad_boxes=True):
     return out
 
 
+class _WavefrontScene(C.Structure):
+    """f3do_wavefront_scene (oracle/f3d_oracle.h)."""
+    _fields_ = [
+        ("cam_origin", C.c_float * 3), ("cam_forward", C.c_float * 3), ("cam_right", C.c_float * 3), ("cam_up", C.c_float * 3),
+        ("fov_y_rad", C.c_float), ("exposure", C.c_float), ("seed_hi", C.c_uint32), ("seed_lo", C.c_uint32),
+        ("spheres", C.POINTER(C.c_float)), ("nspheres", C.c_uint32),
+        ("dir_lights", C.POINTER(C.c_float)), ("ndir", C.c_uint32),
+        ("area_lights", C.POINTER(C.c_float)), ("narea", C.c_uint32),
+        ("importance", C.POINTER(C.c_float)), ("nimportance", C.c_uint32),
+        ("environment", C.c_float * 16),
+        ("mesh_xyz", C.POINTER(C.c_float)), ("mesh_nverts", C.c_uint32),
+        ("mesh_idx", C.POINTER(C.c_uint32)), ("mesh_ntris", C.c_uint32),
+        ("instances", C.POINTER(C.c_float)), ("ninstances", C.c_uint32),
+    ]
+
+
+def wavefront_render(scene, width, height, spp_frames, first_frame=0, num_frames=None, accum=None, resolve=True):
+    """Wavefront path tracer restatement (oracle/f3d_wavefront_oracle.c).  `scene` carries the packed arrays of
+    forge3d_b200.wavefront.WavefrontScene.normalized().  Returns dict(accum, hdr, rgba8, rays, max_rays_per_frame, min_iterations);
+    pass `accum` back in to continue an accumulation in slices of frames."""
+    L = lib()
+    fpt, upt = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    cs = _WavefrontScene()
+    for name in ("cam_origin", "cam_forward", "cam_right", "cam_up"):
+        getattr(cs, name)[:] = [float(x) for x in getattr(scene, name)]
+    cs.fov_y_rad, cs.exposure, cs.seed_hi, cs.seed_lo = scene.fov_y_rad, scene.exposure, scene.seed_hi, scene.seed_lo
+    cs.environment[:] = [float(x) for x in scene.environment]
+    arrs = {}
+    for name, cnt, t, dt, shape in (("spheres", "nspheres", fpt, np.float32, (-1, 20)), ("dir_lights", "ndir", fpt, np.float32, (-1, 8)),
+                                    ("area_lights", "narea", fpt, np.float32, (-1, 12)), ("importance", "nimportance", fpt, np.float32, (-1,)),
+                                    ("mesh_xyz", "mesh_nverts", fpt, np.float32, (-1, 3)), ("mesh_idx", "mesh_ntris", upt, np.uint32, (-1, 3)),
+                                    ("instances", "ninstances", fpt, np.float32, (-1, 36))):
+        a = np.ascontiguousarray(np.asarray(getattr(scene, name), dtype=dt).reshape(shape))
+        arrs[name] = a
+        setattr(cs, name, a.ctypes.data_as(t) if a.size else t())
+        setattr(cs, cnt, a.shape[0])
+    if num_frames is None:
+        num_frames = spp_frames - first_frame
+    if accum is None:
+        accum = np.zeros((height, width, 4), np.float32)
+    hdr = np.zeros((height, width, 4), np.float32) if resolve else None
+    rgba = np.zeros((height, width, 4), np.uint8) if resolve else None
+    stats = (C.c_uint64 * 3)()
+    L.f3do_wavefront_render.argtypes = [C.POINTER(_WavefrontScene), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, fpt, fpt,
+                                        C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
+    L.f3do_wavefront_last_error.restype = C.c_char_p
+    rc = L.f3do_wavefront_render(C.byref(cs), width, height, spp_frames, first_frame, num_frames, accum.ctypes.data_as(fpt),
+                                 hdr.ctypes.data_as(fpt) if resolve else fpt(), rgba.ctypes.data_as(C.POINTER(C.c_uint8)) if resolve else None,
+                                 stats)
+    if rc != 0:
+        raise OracleError(L.f3do_wavefront_last_error().decode())
+    return dict(accum=accum, hdr=hdr, rgba8=rgba, rays=int(stats[0]), max_rays_per_frame=int(stats[1]), min_iterations=int(stats[2]))
+
+
+def log2(x: float) -> float:
+    L = lib()
+    L.f3do_log2.restype = C.c_float
+    L.f3do_log2.argtypes = [C.c_float]
+    return float(L.f3do_log2(float(x)))
+
+
 def exp2(x: float) -> float:
     return float(lib().f3do_exp2(float(x)))
 
