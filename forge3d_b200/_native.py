@@ -83,6 +83,57 @@ class ViewshedOptions(C.Structure):
         ("device", C.c_int32)]
 
 
+class WavefrontSceneC(C.Structure):
+    """f3d_wavefront_scene (include/forge3d_b200.h)."""
+    _fields_ = [
+        ("cam_origin", C.c_float * 3), ("cam_forward", C.c_float * 3), ("cam_right", C.c_float * 3), ("cam_up", C.c_float * 3),
+        ("fov_y_rad", C.c_float), ("exposure", C.c_float), ("seed_hi", C.c_uint32), ("seed_lo", C.c_uint32),
+        ("spheres", C.POINTER(C.c_float)), ("nspheres", C.c_uint32),
+        ("dir_lights", C.POINTER(C.c_float)), ("ndir", C.c_uint32),
+        ("area_lights", C.POINTER(C.c_float)), ("narea", C.c_uint32),
+        ("importance", C.POINTER(C.c_float)), ("nimportance", C.c_uint32),
+        ("environment", C.c_float * 16),
+        ("mesh_xyz", C.POINTER(C.c_float)), ("mesh_nverts", C.c_uint32),
+        ("mesh_idx", C.POINTER(C.c_uint32)), ("mesh_ntris", C.c_uint32),
+        ("instances", C.POINTER(C.c_float)), ("ninstances", C.c_uint32),
+    ]
+
+
+class WavefrontStats(C.Structure):
+    """f3d_wavefront_stats (include/forge3d_b200.h)."""
+    _fields_ = [("rays", C.c_uint64), ("max_rays_per_frame", C.c_uint64), ("min_iterations", C.c_uint32), ("launches", C.c_uint32),
+                ("kernel_ms", C.c_double)]
+
+
+def fill_wavefront_scene(cs, s):
+    """Fills a WavefrontSceneC-shaped ctypes struct from a normalized forge3d_b200.wavefront.WavefrontScene; returns the arrays
+    that must outlive the call."""
+    fpt, upt = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    for name in ("cam_origin", "cam_forward", "cam_right", "cam_up"):
+        getattr(cs, name)[:] = [float(x) for x in getattr(s, name)]
+    cs.fov_y_rad, cs.exposure, cs.seed_hi, cs.seed_lo = s.fov_y_rad, s.exposure, s.seed_hi, s.seed_lo
+    cs.environment[:] = [float(x) for x in s.environment]
+    keep = [s.spheres, s.dir_lights, s.area_lights, s.importance, s.mesh_xyz, s.mesh_idx, s.instances]
+    ptr = lambda a, t: a.ctypes.data_as(t) if a.size else t()
+    cs.spheres, cs.nspheres = ptr(s.spheres, fpt), s.spheres.shape[0]
+    cs.dir_lights, cs.ndir = ptr(s.dir_lights, fpt), s.dir_lights.shape[0]
+    cs.area_lights, cs.narea = ptr(s.area_lights, fpt), s.area_lights.shape[0]
+    cs.importance, cs.nimportance = ptr(s.importance, fpt), s.importance.shape[0]
+    cs.mesh_xyz, cs.mesh_nverts = ptr(s.mesh_xyz, fpt), s.mesh_xyz.shape[0]
+    cs.mesh_idx, cs.mesh_ntris = ptr(s.mesh_idx, upt), s.mesh_idx.shape[0]
+    cs.instances, cs.ninstances = ptr(s.instances, fpt), s.instances.shape[0]
+    return keep
+
+
+def make_wavefront_scene(s):
+    cs = WavefrontSceneC()
+    return cs, fill_wavefront_scene(cs, s)
+
+
+def raise_last(rc: int) -> None:
+    check(rc)
+
+
 class TerrainDesc(C.Structure):
     """f3d_terrain_desc (include/forge3d_b200.h)."""
     _fields_ = [
@@ -131,7 +182,7 @@ EXPORTS = [
     "f3d_session_stats", "f3d_session_sync", "f3d_session_last_frames_ms", "f3d_session_destroy",
     "f3d_session_ipc_export", "f3d_session_ipc_import", "f3d_trace_rays", "f3d_build_minmax",
     "f3d_smoke_create", "f3d_smoke_destroy", "f3d_smoke_raymarch_rgba", "f3d_smoke_raymarch_projection_rgba",
-    "f3d_viewshed", "f3d_shadow_mask", "f3d_lbvh_build",
+    "f3d_viewshed", "f3d_shadow_mask", "f3d_lbvh_build", "f3d_wavefront_render",
 ]
 
 _lib = None
@@ -179,6 +230,8 @@ def lib():
     L.f3d_viewshed.argtypes = [fp, fp, C.POINTER(ViewshedOptions), u8p, fp, fp, fp, C.POINTER(C.c_double)]
     L.f3d_shadow_mask.argtypes = [fp, fp, C.POINTER(ViewshedOptions), u8p, C.POINTER(C.c_double)]
     L.f3d_lbvh_build.argtypes = [fp, C.c_uint32, u32p, C.c_uint32, C.c_int32, u32p, u32p, u32p, u32p, u32p, fp]
+    L.f3d_wavefront_render.argtypes = [C.POINTER(WavefrontSceneC), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, fp, u8p,
+                                       C.POINTER(WavefrontStats)]
     for name in EXPORTS:   # fail at load time, not at first call, if the ABI drifted
         getattr(L, name)
     _lib = L

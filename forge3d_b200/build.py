@@ -14,8 +14,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libforge3d_b200.so"
-SOURCES = ["f3d_backend.cu", "f3d_smoke.cu", "f3d_viewshed.cu"]
-HEADERS = ["f3d_host.h", "f3d_math.cuh", "f3d_aether.cuh", "f3d_smoke.cuh", "f3d_viewshed.cuh", "f3d_lbvh.cuh", "f3d_trace.cuh", "f3d_trace_fast.cuh", "f3d_kernels.cuh"]
+SOURCES = ["f3d_backend.cu", "f3d_smoke.cu", "f3d_viewshed.cu", "f3d_wavefront.cu"]
+HEADERS = ["f3d_host.h", "f3d_math.cuh", "f3d_aether.cuh", "f3d_smoke.cuh", "f3d_viewshed.cuh", "f3d_lbvh.cuh", "f3d_wavefront.cuh", "f3d_trace.cuh", "f3d_trace_fast.cuh", "f3d_kernels.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

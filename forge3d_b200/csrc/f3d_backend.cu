@@ -320,6 +320,13 @@ static void build_mesh_bvh(const float* xyz, const uint32_t* idx, uint32_t ntris
     bvh_build_rec(*B, ids, 0, ntris, tb, cen, 0);
 }
 
+void host_build_mesh_bvh(const float* xyz, const uint32_t* idx, uint32_t ntris, std::vector<float4>* nodes, std::vector<uint32_t>* tris) {
+    MeshBvh B;
+    build_mesh_bvh(xyz, idx, ntris, &B);
+    nodes->swap(B.nodes);
+    tris->swap(B.tris);
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // GPU LBVH build (csrc/f3d_lbvh.cuh): d_verts (float4) and d_idx already on the device; writes 2 * (2n - 1) float4 nodes in

@@ -80,3 +80,7 @@ struct DeviceTerrain {
 // k_pack_quads).  keep_plain = keep the plain per-level chain (KAT seams, viewshed); otherwise only the quad-packed copy stays.
 int build_device_terrain(const float* h_heights, uint32_t w, uint32_t h, float ex, cudaStream_t stream, DeviceTerrain* T,
                          uint64_t* launches, bool keep_plain);
+
+// Host median-split BVH over a triangle mesh in the traversal format of intersect_mesh (f3d_trace.cuh) / wf_mesh (f3d_wavefront.cuh):
+// 2 float4 per node, leaf boxes padded against rounding, `tris` = triangle ids in leaf order.
+void host_build_mesh_bvh(const float* xyz, const uint32_t* idx, uint32_t ntris, std::vector<float4>* nodes, std::vector<uint32_t>* tris);

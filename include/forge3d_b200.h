@@ -247,6 +247,36 @@ int f3d_shadow_mask(const float* heights, const float* geodetic_and_sun, const f
 int f3d_lbvh_build(const float* xyz, uint32_t nverts, const uint32_t* idx, uint32_t ntris, int32_t device, uint32_t* morton,
                    uint32_t* order, uint32_t* left, uint32_t* right, uint32_t* parent, float* nodes);
 
+/* ---- Wavefront multi-bounce path tracer.  Replaces render_pt_reference
+ * (/root/reference/src/path_tracing/adjudication.rs:76-331) and the WavefrontScheduler frame loop behind it
+ * (src/path_tracing/wavefront/render.rs:87-209, pt_raygen / pt_intersect / pt_shade / pt_shadow / pt_scatter.wgsl), plus the
+ * Reinhard + sRGB resolve of src/core/tonemap.rs:11-32.  The buffers are the ones that function binds, in their GPU layouts. */
+typedef struct f3d_wavefront_scene {
+    float cam_origin[3], cam_forward[3], cam_right[3], cam_up[3];   /* ReferenceSceneDesc::camera_basis, reference_scene.rs:201-207 */
+    float fov_y_rad, exposure;
+    uint32_t seed_hi, seed_lo;                      /* per-frame seeds are splitmix32 hashes of these, adjudication.rs:226-236 */
+    const float* spheres; uint32_t nspheres;        /* 20 floats each: WavefrontGpuSphere (80 B), reference_scene.rs:101-117 */
+    const float* dir_lights; uint32_t ndir;         /* 8 floats each: GpuDirectionalLight, lighting.rs:88-96 */
+    const float* area_lights; uint32_t narea;       /* 12 floats each: GpuAreaLight, lighting.rs:19-28 */
+    const float* importance; uint32_t nimportance;  /* object_importance, one per material slot */
+    float environment[16];                          /* ReferenceEnvironmentRaw: env_ground, env_sky, miss_ground, miss_sky */
+    const float* mesh_xyz; uint32_t mesh_nverts;    /* one BLAS (may be empty) */
+    const uint32_t* mesh_idx; uint32_t mesh_ntris;
+    const float* instances; uint32_t ninstances;    /* 36 words each: InstanceData (transform, inv_transform column-major, blas_index,
+                                                       material_id, pad); 0 instances = the mesh is traced un-instanced with material 0 */
+} f3d_wavefront_scene;
+typedef struct f3d_wavefront_stats {
+    uint64_t rays;                 /* rays traced over all frames */
+    uint64_t max_rays_per_frame;   /* the reference's append-only ray queue holds 4 * W * H per frame (wavefront/mod.rs:34,77) */
+    uint32_t min_iterations;       /* fewest wavefront iterations in any frame */
+    uint32_t launches;             /* kernels launched */
+    double kernel_ms;              /* device time, CUDA events */
+} f3d_wavefront_stats;
+/* hdr_rgba: host W*H*4 floats (mean radiance, alpha 1) or NULL; rgba8: host W*H*4 bytes or NULL; stats may be NULL.
+ * Errors as render_pt_reference raises them: zero size, a frame with < 2 wavefront iterations, ray-queue overflow. */
+int f3d_wavefront_render(const f3d_wavefront_scene* scene, uint32_t width, uint32_t height, uint32_t spp_frames, int32_t device,
+                         float* hdr_rgba, uint8_t* rgba8, f3d_wavefront_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

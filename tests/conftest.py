@@ -15,5 +15,5 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     """GPU tests of the widened rows (AETHER post, smoke march, viewshed, LBVH: SURVEY section 8f) run after the core hot-path GPU tests, so
     that under `-x` a failure in a newer row cannot hide the state of the section 8a-e parity suite."""
-    late = {"test_aether.py", "test_smoke.py", "test_viewshed.py", "test_lbvh.py"}
+    late = {"test_aether.py", "test_smoke.py", "test_viewshed.py", "test_lbvh.py", "test_wavefront.py"}
     items.sort(key=lambda it: 1 if (it.get_closest_marker("gpu") and Path(str(it.fspath)).name in late) else 0)

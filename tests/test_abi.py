@@ -38,6 +38,8 @@ def test_struct_layout_matches_c():
     #include "forge3d_b200.h"
     int main(void) {
       printf("%zu %zu %zu ", sizeof(f3d_viewshed_options), offsetof(f3d_viewshed_options, earth_latitude_deg), offsetof(f3d_viewshed_options, device));
+      printf("%zu %zu %zu %zu %zu %zu ", sizeof(f3d_wavefront_scene), offsetof(f3d_wavefront_scene, spheres), offsetof(f3d_wavefront_scene, environment),
+             offsetof(f3d_wavefront_scene, ninstances), sizeof(f3d_wavefront_stats), offsetof(f3d_wavefront_stats, kernel_ms));
       printf("%zu %zu %zu %zu ", sizeof(f3d_smoke_volume), offsetof(f3d_smoke_volume, frame_index), sizeof(f3d_smoke_settings),
              offsetof(f3d_smoke_settings, soot_absorption));
       printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(f3d_terrain_desc), offsetof(f3d_terrain_desc, observer_lat_deg),
@@ -53,6 +55,9 @@ def test_struct_layout_matches_c():
     VO = _native.ViewshedOptions
     assert vals[:3] == [C.sizeof(VO), VO.earth_latitude_deg.offset, VO.device.offset]
     vals = vals[3:]
+    WS, WT = _native.WavefrontSceneC, _native.WavefrontStats
+    assert vals[:6] == [C.sizeof(WS), WS.spheres.offset, WS.environment.offset, WS.ninstances.offset, C.sizeof(WT), WT.kernel_ms.offset]
+    vals = vals[6:]
     SV, SS = _native.SmokeVolume, _native.SmokeSettings
     assert vals[:4] == [C.sizeof(SV), SV.frame_index.offset, C.sizeof(SS), SS.soot_absorption.offset]
     vals = vals[4:]

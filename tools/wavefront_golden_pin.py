@@ -3,6 +3,7 @@ tests/test_adjudication_gate.py:41-43) and scores it against the reference's own
 reference's drift gate (SSIM >= 0.995, mean |diff| <= 2.0; :48-49,136-153).  Writes tests/golden/wavefront_pin.json and the
 oracle's own 512 x 512 render (tests/golden/wavefront_oracle_512.png) so the GPU box can be checked against it without
 /root/reference.  Needs /root/reference; run from the repo root:  python tools/wavefront_golden_pin.py [spp]"""
+import hashlib
 import json
 import sys
 import time
@@ -34,6 +35,8 @@ out = {
     "gate": {"ssim_min": 0.995, "mean_abs_max": 2.0},
     "rays": r["rays"], "max_rays_per_frame": r["max_rays_per_frame"], "min_iterations": r["min_iterations"],
 }
+small = oracle.wavefront_render(scene, 64, 48, 6)   # arithmetic regression pin used by tests/test_wavefront.py
+out["oracle_64x48x6_hdr_sha256"] = hashlib.sha256(np.ascontiguousarray(small["hdr"]).view(np.uint8).tobytes()).hexdigest()
 print(json.dumps(out, indent=1))
 if spp == 4096:
     (ROOT / "tests/golden/wavefront_pin.json").write_text(json.dumps(out, indent=1) + "\n")
