@@ -212,7 +212,7 @@ typedef struct {
 } f3do_wavefront_scene;
 /* Adds frames [first_frame, first_frame + num_frames) into accum_io (W*H*4 floats, caller-zeroed before the first call); when
  * hdr_out / rgba8_out are given they receive mean = accum / spp_frames (alpha 1) and its Reinhard + sRGB resolve.
- * stats_out[3] = {rays traced, most rays in one frame, fewest iterations in one frame}. */
+ * stats_out[19] = {rays traced, most rays in one frame, fewest iterations in one frame, rays at depth 0..15}. */
 int f3do_wavefront_render(const f3do_wavefront_scene* scene, uint32_t width, uint32_t height, uint32_t spp_frames, uint32_t first_frame,
                           uint32_t num_frames, float* accum_io, float* hdr_out, uint8_t* rgba8_out, uint64_t* stats_out);
 const char* f3do_wavefront_last_error(void);

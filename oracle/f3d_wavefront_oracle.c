@@ -610,6 +610,7 @@ int f3do_wavefront_render(const f3do_wavefront_scene* D, uint32_t W, uint32_t H,
     const uint64_t capacity = 4ull * npx;
     uint64_t total_rays = 0, max_rays = 0;
     uint32_t min_iters = 0xFFFFFFFFu;
+    uint64_t depth_hist[16] = {0};
     for (uint32_t fr = first_frame; fr < first_frame + num_frames; fr++) {
         const uint32_t seed_hi = f3do_wavefront_splitmix32(D->seed_hi ^ fr);
         const uint32_t seed_lo = f3do_wavefront_splitmix32(D->seed_lo ^ (fr * 0x00009E3Du));
@@ -642,10 +643,14 @@ int f3do_wavefront_render(const f3do_wavefront_scene* D, uint32_t W, uint32_t H,
             return wf_fail("adjudication PT frame %u executed %u wavefront iteration(s); a multi-bounce path-traced reference requires >= 2",
                            fr, executed);
         total_rays += rays;
+        for (int k = 0; k < 16; k++) depth_hist[k] += iters[k];
         if (rays > max_rays) max_rays = rays;
         if (executed < min_iters) min_iters = executed;
     }
-    if (stats_out) { stats_out[0] = total_rays; stats_out[1] = max_rays; stats_out[2] = min_iters; }
+    if (stats_out) {
+        stats_out[0] = total_rays; stats_out[1] = max_rays; stats_out[2] = min_iters;
+        for (int k = 0; k < 16; k++) stats_out[3 + k] = depth_hist[k]; /* rays traced at each depth, summed over the frames */
+    }
     if (hdr_out || rgba8_out) { /* adjudication.rs:318-331, tonemap.rs:11-32 */
         const float inv = 1.0f / (float)spp_frames;
         for (size_t p = 0; p < npx; p++) {

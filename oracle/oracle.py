@@ -522,7 +522,7 @@ def wavefront_render(scene, width, height, spp_frames, first_frame=0, num_frames
         accum = np.zeros((height, width, 4), np.float32)
     hdr = np.zeros((height, width, 4), np.float32) if resolve else None
     rgba = np.zeros((height, width, 4), np.uint8) if resolve else None
-    stats = (C.c_uint64 * 3)()
+    stats = (C.c_uint64 * 19)()
     L.f3do_wavefront_render.argtypes = [C.POINTER(_WavefrontScene), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, fpt, fpt,
                                         C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
     L.f3do_wavefront_last_error.restype = C.c_char_p
@@ -531,7 +531,8 @@ def wavefront_render(scene, width, height, spp_frames, first_frame=0, num_frames
                                  stats)
     if rc != 0:
         raise OracleError(L.f3do_wavefront_last_error().decode())
-    return dict(accum=accum, hdr=hdr, rgba8=rgba, rays=int(stats[0]), max_rays_per_frame=int(stats[1]), min_iterations=int(stats[2]))
+    return dict(accum=accum, hdr=hdr, rgba8=rgba, rays=int(stats[0]), max_rays_per_frame=int(stats[1]), min_iterations=int(stats[2]),
+                rays_per_depth=[int(stats[3 + k]) for k in range(16)])
 
 
 def log2(x: float) -> float:
