@@ -105,6 +105,12 @@ class WavefrontStats(C.Structure):
                 ("kernel_ms", C.c_double)]
 
 
+class WavefrontPart(C.Structure):
+    """f3d_wavefront_part (include/forge3d_b200.h)."""
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("block_rows", C.c_uint32), ("frame_iterations", C.POINTER(C.c_uint32)),
+                ("frame_rays", C.POINTER(C.c_uint64))]
+
+
 def fill_wavefront_scene(cs, s):
     """Fills a WavefrontSceneC-shaped ctypes struct from a normalized forge3d_b200.wavefront.WavefrontScene; returns the arrays
     that must outlive the call."""
@@ -182,7 +188,7 @@ EXPORTS = [
     "f3d_session_stats", "f3d_session_sync", "f3d_session_last_frames_ms", "f3d_session_destroy",
     "f3d_session_ipc_export", "f3d_session_ipc_import", "f3d_trace_rays", "f3d_build_minmax",
     "f3d_smoke_create", "f3d_smoke_destroy", "f3d_smoke_raymarch_rgba", "f3d_smoke_raymarch_projection_rgba",
-    "f3d_viewshed", "f3d_shadow_mask", "f3d_lbvh_build", "f3d_wavefront_render",
+    "f3d_viewshed", "f3d_shadow_mask", "f3d_lbvh_build", "f3d_wavefront_render", "f3d_wavefront_render_part",
 ]
 
 _lib = None
@@ -232,6 +238,8 @@ def lib():
     L.f3d_lbvh_build.argtypes = [fp, C.c_uint32, u32p, C.c_uint32, C.c_int32, u32p, u32p, u32p, u32p, u32p, fp]
     L.f3d_wavefront_render.argtypes = [C.POINTER(WavefrontSceneC), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, fp, u8p,
                                        C.POINTER(WavefrontStats)]
+    L.f3d_wavefront_render_part.argtypes = [C.POINTER(WavefrontSceneC), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(WavefrontPart),
+                                            fp, u8p, C.POINTER(WavefrontStats)]
     for name in EXPORTS:   # fail at load time, not at first call, if the ABI drifted
         getattr(L, name)
     _lib = L

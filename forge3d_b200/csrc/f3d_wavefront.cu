@@ -64,8 +64,15 @@ struct WfRun {
 
 extern "C" int f3d_wavefront_render(const f3d_wavefront_scene* sc, uint32_t width, uint32_t height, uint32_t spp_frames, int32_t device,
                                     float* hdr_rgba, uint8_t* rgba8, f3d_wavefront_stats* stats) {
+    return f3d_wavefront_render_part(sc, width, height, spp_frames, device, nullptr, hdr_rgba, rgba8, stats);
+}
+
+extern "C" int f3d_wavefront_render_part(const f3d_wavefront_scene* sc, uint32_t width, uint32_t height, uint32_t spp_frames, int32_t device,
+                                         const f3d_wavefront_part* part, float* hdr_rgba, uint8_t* rgba8, f3d_wavefront_stats* stats) {
     g_err[0] = 0;
     if (!sc) return fail(F3D_ERR_ARGUMENT, "null scene");
+    if (part && (part->world == 0 || part->rank >= part->world || (part->world > 1 && part->block_rows == 0)))
+        return fail(F3D_ERR_ARGUMENT, "invalid partition: rank %u of %u, block_rows %u", part->rank, part->world, part->block_rows);
     if (width == 0 || height == 0 || spp_frames == 0)
         return fail(F3D_ERR_RENDER, "adjudication PT reference requires non-zero width/height/spp");   // adjudication.rs:85-89
     if ((uint64_t)width * height > 0x3FFFFFFFull) return fail(F3D_ERR_ARGUMENT, "image too large for the 32-bit ray queues");
@@ -87,6 +94,17 @@ extern "C" int f3d_wavefront_render(const f3d_wavefront_scene* sc, uint32_t widt
     const uint32_t npx = width * height;
     WfParams P{};
     P.w = width; P.h = height;
+    P.part_rank = part ? part->rank : 0u;
+    P.part_world = part ? part->world : 1u;
+    P.part_rows = P.part_world > 1u ? part->block_rows : height;
+    uint32_t owned_rows = 0;   // rows of this rank inside the image; local_rows also counts the ragged last block's rows past the edge
+    {
+        const uint32_t nblocks = (height + P.part_rows - 1u) / P.part_rows;
+        const uint32_t mine = nblocks > P.part_rank ? (nblocks - P.part_rank + P.part_world - 1u) / P.part_world : 0u;
+        P.local_rows = mine * P.part_rows;
+        for (uint32_t b = P.part_rank; b < nblocks; b += P.part_world) owned_rows += std::min(P.part_rows, height - b * P.part_rows);
+    }
+    const uint32_t n_primary = owned_rows * width;
     memcpy(P.cam_origin, sc->cam_origin, 12); memcpy(P.cam_forward, sc->cam_forward, 12);
     memcpy(P.cam_right, sc->cam_right, 12); memcpy(P.cam_up, sc->cam_up, 12);
     P.fov_y_rad = sc->fov_y_rad;
@@ -128,6 +146,7 @@ extern "C" int f3d_wavefront_render(const f3d_wavefront_scene* sc, uint32_t widt
     int sms = 148;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const uint32_t full = (npx + kWfThreads - 1u) / kWfThreads;
+    const uint32_t first = std::max(1u, (P.local_rows * width + kWfThreads - 1u) / kWfThreads);
     const uint32_t wide = std::min(full, (uint32_t)sms * 8u);   // grid-stride over the device-side queue length
     const uint32_t thin = std::min(full, (uint32_t)sms * 2u);
     uint32_t launches = 0;
@@ -139,7 +158,7 @@ extern "C" int f3d_wavefront_render(const f3d_wavefront_scene* sc, uint32_t widt
         F.seed_lo = splitmix32(sc->seed_lo ^ (fr * 0x00009E3Du));
         sobol2(fr, &F.u1, &F.u2);                                  // sidx = sample + frame_index * max(1, spp), spp = 1
         F.counts = d_counts + (size_t)fr * kSlots;
-        k_wf_bounce<true><<<full, kWfThreads>>>(P, F, 0u);
+        k_wf_bounce<true><<<first, kWfThreads>>>(P, F, 0u);
         for (uint32_t d = 1; d < kWfWideDepth; d++) k_wf_bounce<false><<<wide, kWfThreads>>>(P, F, d);
         k_wf_tail<<<thin, kWfThreads>>>(P, F, kWfWideDepth);
         launches += kWfWideDepth + 1u;
@@ -165,18 +184,20 @@ extern "C" int f3d_wavefront_render(const f3d_wavefront_scene* sc, uint32_t widt
         uint64_t cum = 0;
         uint32_t executed = 0;
         for (uint32_t k = 0; k < kWfMaxDepth; k++) {
-            const uint64_t rays = k == 0 ? npx : c[k];
+            const uint64_t rays = k == 0 ? n_primary : c[k];
             if (!rays) break;
             cum += rays;
-            if (cum > capacity)   // render.rs:127-137
+            if (!part && cum > capacity)   // render.rs:127-137
                 return fail(F3D_ERR_RENDER, "wavefront frame %u: wavefront ray queue overflow: %llu rays pushed into capacity %llu", fr,
                             (unsigned long long)cum, (unsigned long long)capacity);
             executed++;
         }
-        if (executed < 2u)   // adjudication.rs:259-265
+        if (!part && executed < 2u)   // adjudication.rs:259-265
             return fail(F3D_ERR_RENDER,
                         "adjudication PT frame %u executed %u wavefront iteration(s); a multi-bounce path-traced reference requires >= 2", fr,
                         executed);
+        if (part && part->frame_iterations) part->frame_iterations[fr] = executed;
+        if (part && part->frame_rays) part->frame_rays[fr] = cum;
         total += cum;
         max_rays = std::max(max_rays, cum);
         min_iters = std::min(min_iters, executed);

@@ -34,6 +34,7 @@ struct WfMesh {   // passed by value to the (non-inlined) traversal so that the 
 
 struct WfParams {
     uint32_t w, h;
+    uint32_t part_rank, part_world, part_rows, local_rows;   // image partition in interleaved blocks of part_rows rows (world 1: one block)
     float cam_origin[3], cam_forward[3], cam_right[3], cam_up[3];
     float fov_y_rad, aspect;
     const float* spheres; uint32_t nsph;        // 20 floats each
@@ -553,26 +554,32 @@ __device__ __forceinline__ bool wf_bounce(const WfParams& P, const WfFrame& F, W
 // the other queue with one atomic per warp.  Launched with a fixed grid; the queue length is read from device memory.
 template <bool PRIMARY>
 __global__ void __launch_bounds__(kWfThreads) k_wf_bounce(WfParams P, WfFrame F, uint32_t depth) {
-    const uint32_t count = PRIMARY ? P.w * P.h : F.counts[depth];
+    const uint32_t count = PRIMARY ? P.w * P.local_rows : F.counts[depth];
     const uint32_t in = depth & 1u, out = in ^ 1u;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {   // warp-uniform trip count
         const uint32_t i = base + lane;
-        bool alive = false;
+        bool alive = false, skip = false;
         WfPath p;
         if (i < count) {
             if (PRIMARY) {
-                p = wf_raygen(P, F, i);
+                // local row lr of this rank -> global row: its blocks are rank, rank + world, rank + 2 world, ...
+                const uint32_t lr = i / P.w, x = i - lr * P.w;
+                const uint32_t row = ((lr / P.part_rows) * P.part_world + P.part_rank) * P.part_rows + lr % P.part_rows;
+                skip = row >= P.h;
+                if (!skip) p = wf_raygen(P, F, row * P.w + x);
             } else {
                 const float4 a = P.qa[in][i], b = P.qb[in][i], c = P.qc[in][i];
                 p.o = V3(a.x, a.y, a.z); p.pixel = __float_as_uint(a.w);
                 p.d = V3(b.x, b.y, b.z); p.rng_hi = __float_as_uint(b.w);
                 p.thr = V3(c.x, c.y, c.z); p.tmin = 1e-3f;
             }
-            float4 acc = P.accum[p.pixel];
-            alive = wf_bounce(P, F, p, depth, acc);
-            P.accum[p.pixel] = acc;
+            if (!skip) {
+                float4 acc = P.accum[p.pixel];
+                alive = wf_bounce(P, F, p, depth, acc);
+                P.accum[p.pixel] = acc;
+            }
         }
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
         if (mask) {

@@ -107,6 +107,58 @@ def check_validity_across_ranks(any_valid: bool, required: bool, group=None, dev
         raise RuntimeError(NO_VALID_RESERVOIRS)
 
 
+def wavefront_block_rows(block_rows: int, world: int) -> int:
+    """Row-block size of the wavefront tracer's partition: any positive value works (no tile constraint); default 16."""
+    return int(block_rows) if block_rows else 16
+
+
+def wavefront_owned_rows(height: int, world: int, rank: int, block_rows: int = 0) -> np.ndarray:
+    br = wavefront_block_rows(block_rows, world)
+    rows = np.arange(height)
+    return rows if world <= 1 else rows[(rows // br) % world == rank]
+
+
+def wavefront_partitioned(scene, width: int, height: int, spp_frames: int, *, group=None, block_rows: int = 0, device: int = 0,
+                          tensor_device: str = "cpu"):
+    """The wavefront multi-bounce tracer (forge3d_b200.wavefront.render_pt_reference) over the ranks of a process group: each rank
+    traces the rows it owns (pixels are independent, so they are bit-identical to the one-GPU image; no data-path collective), then
+    ONE all-gather per image assembles (hdr f32, rgba8) on every rank, and the reference's two per-frame rules are applied to the
+    per-frame iteration counts (MAX over ranks) and ray counts (SUM over ranks).  NCCL with tensor_device="cuda", gloo on the CPU."""
+    import torch
+    import torch.distributed as dist
+
+    from . import wavefront as wf
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    br = wavefront_block_rows(block_rows, world)
+    hdr, rgba, st = wf.render_pt_reference(scene, width, height, spp_frames, device=device, return_rgba8=True, return_stats=True,
+                                           part=(rank, world, br))
+    iters = torch.from_numpy(st.frame_iterations.astype(np.int64)).to(tensor_device)
+    rays = torch.from_numpy(st.frame_rays.astype(np.int64)).to(tensor_device)
+    if world > 1:
+        dist.all_reduce(iters, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM, group=group)
+    wf.check_frame_rules(iters.cpu().numpy(), rays.cpu().numpy(), width, height)
+    if world == 1:
+        return hdr, rgba
+    rows = torch.as_tensor(wavefront_owned_rows(height, world, rank, br), device=tensor_device)
+    counts = [int(wavefront_owned_rows(height, world, r, br).size) for r in range(world)]
+    mx = max(counts)
+    out = []
+    for img in (hdr, rgba):
+        t = torch.from_numpy(img).to(tensor_device)
+        packed = t.new_zeros((mx,) + tuple(t.shape[1:]))
+        packed[: rows.numel()] = t[rows]
+        allr = t.new_empty((world * mx,) + tuple(t.shape[1:]))
+        dist.all_gather_into_tensor(allr, packed.contiguous(), group=group)
+        full = t.new_zeros(t.shape)
+        for r in range(world):
+            rr = torch.as_tensor(wavefront_owned_rows(height, world, r, br), device=tensor_device)
+            full[rr] = allr[r * mx:r * mx + rr.numel()]
+        out.append(full.cpu().numpy())
+    return out[0], out[1]
+
+
 class PartitionedRender:
     """One rank's share of a partitioned render (CUDA + NCCL)."""
 

@@ -238,11 +238,17 @@ class WavefrontStats:
     min_iterations: int       # fewest wavefront iterations any frame ran (must be >= 2, adjudication.rs:259-265)
     launches: int             # kernels launched
     kernel_ms: float          # device time of the frames + resolve (CUDA events)
+    frame_iterations: object = None   # per frame, partitioned renders only
+    frame_rays: object = None
 
 
 def render_pt_reference(scene, width: int, height: int, spp_frames: int, device: int = 0, return_rgba8: bool = False,
-                        return_stats: bool = False):
-    """Linear-HDR mean radiance over ``spp_frames`` frames, RGBA f32 (H, W, 4), alpha 1 (adjudication.rs:76-331)."""
+                        return_stats: bool = False, part=None):
+    """Linear-HDR mean radiance over ``spp_frames`` frames, RGBA f32 (H, W, 4), alpha 1 (adjudication.rs:76-331).
+
+    ``part=(rank, world, block_rows)`` renders only the rows that rank owns (interleaved blocks, see forge3d_b200.distributed); the
+    returned images are full-size with the other rows untouched, the reference's two frame rules are left to the caller, and the
+    stats carry ``frame_iterations`` / ``frame_rays`` (per frame, this rank) for the reduction over ranks."""
     if isinstance(scene, ReferenceSceneDesc):
         scene = scene_from_desc(scene)
     s = scene.normalized()
@@ -253,8 +259,17 @@ def render_pt_reference(scene, width: int, height: int, spp_frames: int, device:
     hdr = np.zeros((height, width, 4), f32)
     rgba = np.zeros((height, width, 4), np.uint8)
     st = _native.WavefrontStats()
-    rc = L.f3d_wavefront_render(C.byref(cs), width, height, spp_frames, device, hdr.ctypes.data_as(C.POINTER(C.c_float)),
-                                rgba.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(st))
+    fp, u8p = C.POINTER(C.c_float), C.POINTER(C.c_uint8)
+    if part is None:
+        rc = L.f3d_wavefront_render(C.byref(cs), width, height, spp_frames, device, hdr.ctypes.data_as(fp), rgba.ctypes.data_as(u8p),
+                                    C.byref(st))
+        frame_iters = frame_rays = None
+    else:
+        frame_iters, frame_rays = np.zeros(spp_frames, np.uint32), np.zeros(spp_frames, np.uint64)
+        cp = _native.WavefrontPart(int(part[0]), int(part[1]), int(part[2]), frame_iters.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                   frame_rays.ctypes.data_as(C.POINTER(C.c_uint64)))
+        rc = L.f3d_wavefront_render_part(C.byref(cs), width, height, spp_frames, device, C.byref(cp), hdr.ctypes.data_as(fp),
+                                         rgba.ctypes.data_as(u8p), C.byref(st))
     del keep
     if rc != 0:
         _native.raise_last(rc)
@@ -262,8 +277,21 @@ def render_pt_reference(scene, width: int, height: int, spp_frames: int, device:
     if return_rgba8:
         out.append(rgba)
     if return_stats:
-        out.append(WavefrontStats(int(st.rays), int(st.max_rays_per_frame), int(st.min_iterations), int(st.launches), float(st.kernel_ms)))
+        ws = WavefrontStats(int(st.rays), int(st.max_rays_per_frame), int(st.min_iterations), int(st.launches), float(st.kernel_ms))
+        ws.frame_iterations, ws.frame_rays = frame_iters, frame_rays
+        out.append(ws)
     return out[0] if len(out) == 1 else tuple(out)
+
+
+def check_frame_rules(frame_iterations, frame_rays, width: int, height: int) -> None:
+    """The reference's two per-frame rules on whole-image numbers (render.rs:127-137, adjudication.rs:259-265), same texts."""
+    capacity = 4 * width * height
+    for fr, (it, rays) in enumerate(zip(frame_iterations, frame_rays)):
+        if int(rays) > capacity:
+            raise RuntimeError(f"wavefront frame {fr}: wavefront ray queue overflow: {int(rays)} rays pushed into capacity {capacity}")
+        if int(it) < 2:
+            raise RuntimeError(f"adjudication PT frame {fr} executed {int(it)} wavefront iteration(s); "
+                               "a multi-bounce path-traced reference requires >= 2")
 
 
 def render_adjudication_pt(width: int, height: int, spp: int, device: int = 0):

@@ -276,6 +276,18 @@ typedef struct f3d_wavefront_stats {
  * Errors as render_pt_reference raises them: zero size, a frame with < 2 wavefront iterations, ray-queue overflow. */
 int f3d_wavefront_render(const f3d_wavefront_scene* scene, uint32_t width, uint32_t height, uint32_t spp_frames, int32_t device,
                          float* hdr_rgba, uint8_t* rgba8, f3d_wavefront_stats* stats);
+/* Multi-GPU extension (the reference is single-GPU): the same render restricted to the rows one rank owns -- interleaved blocks of
+ * block_rows rows, block b belongs to rank b % world.  Pixels are independent, so the owned rows are bit-identical to the one-GPU image.
+ * hdr_rgba / rgba8 are full-size; only owned rows are meaningful.  The two frame rules are global properties, so they are NOT applied
+ * here: frame_iterations[spp_frames] / frame_rays[spp_frames] (host, may be NULL) receive this rank's per-frame numbers for the caller to
+ * reduce over ranks (MAX / SUM) and check (forge3d_b200/distributed.py::wavefront_partitioned). */
+typedef struct f3d_wavefront_part {
+    uint32_t rank, world, block_rows;
+    uint32_t* frame_iterations;
+    uint64_t* frame_rays;
+} f3d_wavefront_part;
+int f3d_wavefront_render_part(const f3d_wavefront_scene* scene, uint32_t width, uint32_t height, uint32_t spp_frames, int32_t device,
+                              const f3d_wavefront_part* part, float* hdr_rgba, uint8_t* rgba8, f3d_wavefront_stats* stats);
 
 #ifdef __cplusplus
 }

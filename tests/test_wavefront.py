@@ -264,6 +264,89 @@ def test_emulated_frame_rules_raise_the_reference_errors():
             oracle.wavefront_render(scene, 16, 8, 2)
 
 
+# ------------------------------------------------------------------ image partition (multi-GPU extension)
+def _assemble_parts(scene, w, h, spp, world, block_rows):
+    from forge3d_b200 import distributed as D
+
+    hdr = np.zeros((h, w, 4), f32)
+    rgba = np.zeros((h, w, 4), np.uint8)
+    iters, rays = np.zeros(spp, np.int64), np.zeros(spp, np.int64)
+    for rank in range(world):
+        ph, pr, st = wf.render_pt_reference(scene, w, h, spp, return_rgba8=True, return_stats=True, part=(rank, world, block_rows))
+        rows = D.wavefront_owned_rows(h, world, rank, block_rows)
+        hdr[rows], rgba[rows] = ph[rows], pr[rows]
+        other = np.setdiff1d(np.arange(h), rows)
+        assert not ph[other, :, :3].any()                        # a rank never touches rows it does not own
+        iters = np.maximum(iters, st.frame_iterations.astype(np.int64))
+        rays += st.frame_rays.astype(np.int64)
+    return hdr, rgba, iters, rays
+
+
+@pytest.mark.parametrize("world,block_rows,h", [(2, 16, 40), (3, 4, 30), (4, 16, 24)])   # last: rank 2 and 3 own nothing or a ragged block
+def test_emulated_row_partition_is_bit_identical_to_one_device(world, block_rows, h):
+    scene = _rich_scene(True, 6)
+    o = oracle.wavefront_render(scene, 36, h, 2)
+    with _emu.emulated_backend():
+        hdr, rgba, iters, rays = _assemble_parts(scene, 36, h, 2, world, block_rows)
+    assert np.array_equal(_bits(hdr), _bits(o["hdr"])) and np.array_equal(rgba, o["rgba8"])
+    assert int(rays.sum()) == o["rays"] and int(rays.max()) == o["max_rays_per_frame"] and int(iters.min()) == o["min_iterations"]
+    wf.check_frame_rules(iters, rays, 36, h)
+
+
+def _free_port():
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import os
+    import sys
+
+    sys.path[:0] = [str(Path(__file__).parent), str(Path(__file__).parent.parent)]
+    import torch.distributed as dist
+
+    from forge3d_b200 import distributed as D
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        with _emu.emulated_backend():
+            hdr, rgba = D.wavefront_partitioned(_rich_scene(False, 6), 36, 30, 2, block_rows=4)
+            err = ""
+            try:
+                D.wavefront_partitioned(_empty_scene(), 16, 8, 1, block_rows=4)   # every rank must raise together
+            except RuntimeError as e:
+                err = str(e)
+        q.put((rank, hdr, rgba, err))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_two_ranks_assemble_the_one_device_image():
+    import torch.multiprocessing as mp
+
+    o = oracle.wavefront_render(_rich_scene(False, 6), 36, 30, 2)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, hdr, rgba, err in results:
+        assert np.array_equal(_bits(hdr), _bits(o["hdr"])) and np.array_equal(rgba, o["rgba8"]), rank
+        assert "executed 1 wavefront iteration" in err, (rank, err)
+
+
 # ------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_gpu_is_bit_identical_to_the_oracle():
@@ -282,6 +365,15 @@ def test_gpu_gate_render_equals_the_committed_oracle_render():
     assert rgba.shape == (512, 512, 4) and rgba.dtype == np.uint8
     assert np.array_equal(rgba, want)
     assert meta["pt"]["spp"] == 4096.0 and meta["pt"]["sky_b"] == float(f32(0.70))
+
+
+@pytest.mark.gpu
+def test_gpu_row_partition_is_bit_identical_to_one_device():
+    scene = _rich_scene(True, 6)
+    whole = wf.render_pt_reference(scene, 96, 70, 3)
+    hdr, rgba, iters, rays = _assemble_parts(scene, 96, 70, 3, 3, 16)
+    assert np.array_equal(_bits(hdr), _bits(whole))
+    wf.check_frame_rules(iters, rays, 96, 70)
 
 
 @pytest.mark.gpu
