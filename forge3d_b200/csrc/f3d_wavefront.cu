@@ -1,6 +1,7 @@
 // forge3d_b200/csrc/f3d_wavefront.cu
 // Host side of f3d_wavefront_render: the frame loop of render_pt_reference (/root/reference/src/path_tracing/adjudication.rs:76-331)
-// over the bounce kernels of f3d_wavefront.cuh.  Per frame: kWfWideDepth compacted bounce launches + one tail launch, all queued
+// over the bounce kernels of f3d_wavefront.cuh.  Per batch of frames: kWfWideDepth compacted bounce launches, one tail launch and the
+// in-order merge into the accumulator, all queued
 // without a host round trip (the reference reads a queue header back every bounce, wavefront/queues/types.rs:166-213); the per-frame
 // queue lengths stay in a device table that is read once at the end to apply the reference's two frame rules (>= 2 iterations,
 // ray-queue capacity 4 * W * H).  No CPU fallback.
@@ -126,43 +127,62 @@ extern "C" int f3d_wavefront_render_part(const f3d_wavefront_scene* sc, uint32_t
         if ((rc = R.upload(&P.mesh.bvh_tris, tris.data(), tris.size()))) return rc;
     }
     if ((rc = R.alloc(&P.accum, npx))) return rc;
-    for (int q = 0; q < 2; q++) {
-        if ((rc = R.alloc(&P.qa[q], npx))) return rc;
-        if ((rc = R.alloc(&P.qb[q], npx))) return rc;
-        if ((rc = R.alloc(&P.qc[q], npx))) return rc;
-    }
     constexpr uint32_t kSlots = kWfMaxDepth + 1u;
-    uint32_t* d_counts = nullptr;
+    // frames per batch: enough paths at depth 0 to keep every SM busy through the thin bounces (about 2 M), at most kWfMaxBatch
+    const uint32_t per_frame = P.local_rows * width;
+    uint32_t batch = per_frame ? (uint32_t)std::min<uint64_t>(kWfMaxBatch, std::max<uint64_t>(1u, (1ull << 21) / per_frame)) : 1u;
+    if (const char* e = getenv("F3D_B200_WF_BATCH")) batch = (uint32_t)std::min<long>(kWfMaxBatch, std::max<long>(1, atol(e)));
+    batch = std::min(batch, spp_frames);
+    const uint32_t nbatches = (spp_frames + batch - 1u) / batch;
+    if ((uint64_t)per_frame * batch > 0x7FFFFFFFull) return fail(F3D_ERR_ARGUMENT, "image too large for the 32-bit ray queues");
+    const size_t qcap = std::max<size_t>(1, (size_t)per_frame * batch);
+    for (int q = 0; q < 2; q++) {
+        if ((rc = R.alloc(&P.qa[q], qcap))) return rc;
+        if ((rc = R.alloc(&P.qb[q], qcap))) return rc;
+        if ((rc = R.alloc(&P.qc[q], qcap))) return rc;
+    }
+    if ((rc = R.alloc(&P.fsum, (size_t)npx * batch))) return rc;
+    uint32_t *d_counts = nullptr, *d_qcount = nullptr;
     if ((rc = R.alloc(&d_counts, (size_t)spp_frames * kSlots))) return rc;
+    if ((rc = R.alloc(&d_qcount, (size_t)nbatches * kSlots))) return rc;
     float4* d_hdr = nullptr;
     uchar4* d_rgba = nullptr;
     if (hdr_rgba && (rc = R.alloc(&d_hdr, npx))) return rc;
     if (rgba8 && (rc = R.alloc(&d_rgba, npx))) return rc;
     CUDA_TRY(cudaMemset(P.accum, 0, (size_t)npx * sizeof(float4)));
     CUDA_TRY(cudaMemset(d_counts, 0, (size_t)spp_frames * kSlots * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemset(d_qcount, 0, (size_t)nbatches * kSlots * sizeof(uint32_t)));
     CUDA_TRY(cudaEventCreate(&R.ev0));
     CUDA_TRY(cudaEventCreate(&R.ev1));
 
     int sms = 148;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const uint32_t full = (npx + kWfThreads - 1u) / kWfThreads;
-    const uint32_t first = std::max(1u, (P.local_rows * width + kWfThreads - 1u) / kWfThreads);
-    const uint32_t wide = std::min(full, (uint32_t)sms * 8u);   // grid-stride over the device-side queue length
-    const uint32_t thin = std::min(full, (uint32_t)sms * 2u);
+    const uint32_t owned = std::max(1u, (per_frame + kWfThreads - 1u) / kWfThreads);
+    const uint32_t first = (uint32_t)std::max<size_t>(1, (qcap + kWfThreads - 1u) / kWfThreads);
+    const uint32_t wide = std::min(first, (uint32_t)sms * 8u);   // grid-stride over the device-side queue length
+    const uint32_t thin = std::min(first, (uint32_t)sms * 4u);
     uint32_t launches = 0;
     CUDA_TRY(cudaEventRecord(R.ev0, 0));
-    for (uint32_t fr = 0; fr < spp_frames; fr++) {
-        WfFrame F;
-        F.frame = fr;
-        F.seed_hi = splitmix32(sc->seed_hi ^ fr);                  // adjudication.rs:237-239
-        F.seed_lo = splitmix32(sc->seed_lo ^ (fr * 0x00009E3Du));
-        sobol2(fr, &F.u1, &F.u2);                                  // sidx = sample + frame_index * max(1, spp), spp = 1
-        F.counts = d_counts + (size_t)fr * kSlots;
-        k_wf_bounce<true><<<first, kWfThreads>>>(P, F, 0u);
-        for (uint32_t d = 1; d < kWfWideDepth; d++) k_wf_bounce<false><<<wide, kWfThreads>>>(P, F, d);
-        k_wf_tail<<<thin, kWfThreads>>>(P, F, kWfWideDepth);
-        launches += kWfWideDepth + 1u;
-        if ((fr & 63u) == 63u) CUDA_TRY(cudaGetLastError());
+    for (uint32_t b = 0; b < nbatches; b++) {
+        WfBatch B{};
+        B.first_frame = b * batch;
+        B.nframes = std::min(batch, spp_frames - B.first_frame);
+        for (uint32_t f = 0; f < B.nframes; f++) {
+            const uint32_t fr = B.first_frame + f;
+            B.seed_hi[f] = splitmix32(sc->seed_hi ^ fr);                  // adjudication.rs:237-239
+            B.seed_lo[f] = splitmix32(sc->seed_lo ^ (fr * 0x00009E3Du));
+            sobol2(fr, &B.u1[f], &B.u2[f]);                               // sidx = sample + frame_index * max(1, spp), spp = 1
+        }
+        B.counts = d_counts;
+        B.qcount = d_qcount + (size_t)b * kSlots;
+        const uint32_t g0 = std::max(1u, (per_frame * B.nframes + kWfThreads - 1u) / kWfThreads);
+        k_wf_bounce<true><<<g0, kWfThreads>>>(P, B, 0u);
+        for (uint32_t d = 1; d < kWfWideDepth; d++) k_wf_bounce<false><<<wide, kWfThreads>>>(P, B, d);
+        k_wf_tail<<<thin, kWfThreads>>>(P, B, kWfWideDepth);
+        k_wf_merge<<<owned, kWfThreads>>>(P, B.nframes);
+        launches += kWfWideDepth + 2u;
+        if ((b & 15u) == 15u) CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaGetLastError());
     if (d_hdr || d_rgba) {

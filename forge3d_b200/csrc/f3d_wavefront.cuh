@@ -9,9 +9,11 @@
 //     reference removed (wavefront/dispatch.rs:130-138); queue lengths stay on the device (the reference reads the 16-byte header back
 //     and stalls every bounce, queues/types.rs:166-213);
 //   * the wide bounces (depth < kWfWideDepth) run as compacted waves; whatever is still alive then (a few percent of the paths) is
-//     finished by one tail kernel in which each thread walks its path to the end, so a frame is kWfWideDepth + 1 launches, not 64;
-//   * the pixel's accumulator is read once and written once per bounce, and a pixel's adds happen in push order (emissive, environment,
-//     directional, area, miss), which makes the image deterministic; the reference's non-atomic adds from different threads are not.
+//     finished by one tail kernel in which each thread walks its path to the end, so a batch of frames is kWfWideDepth + 2 launches, not 64 per frame;
+//   * consecutive frames are traced together in batches (a 512 x 512 frame is 262 k paths at depth 0 and 24 k at depth 3: one frame
+//     cannot fill 148 SMs); each frame sums its own radiance per pixel in push order (emissive, environment, directional, area, miss) and
+//     the batch adds those sums to the accumulator in frame order, so the image is deterministic and independent of the batch size;
+//     the reference's non-atomic adds from different threads of one dispatch are neither.
 //
 // Arithmetic follows pt_raygen.wgsl:74-224, pt_intersect.wgsl:84-216,374-558, pt_shade.wgsl:44-196,342-470,478-862,
 // pt_shadow.wgsl:1-58,161-294 and pt_scatter.wgsl:77-132 under the numerics contract of DESIGN.md section 4 (no FMA contraction,
@@ -23,6 +25,9 @@
 
 namespace f3d {
 
+#ifndef F3D_WF_MIN_CTAS
+#define F3D_WF_MIN_CTAS 2   // resident CTAs per SM the bounce kernels are compiled for (3 costs ~300 B of spills per thread: A/B on the GPU)
+#endif
 constexpr int kWfThreads = 256;
 constexpr uint32_t kWfWideDepth = 4;    // bounces 0..3 are compacted waves; the tail kernel takes over at depth 4
 constexpr uint32_t kWfMaxDepth = 16;    // (h.depth + 1) < 16, pt_shade.wgsl:831; MAX_DEPTH * 2 iterations, render.rs:115
@@ -44,14 +49,29 @@ struct WfParams {
     float env[16];
     WfMesh mesh;
     const float* inst; uint32_t ninst;          // 36 words each
-    float4* accum;
-    float4* qa[2]; float4* qb[2]; float4* qc[2];   // path queues, ping-pong: (o, pixel) (d, rng_hi) (throughput, -)
+    float4* accum;                              // running sum over frames, per pixel
+    float4* fsum;                               // [frame in batch][pixel] radiance sum of one frame
+    float4* qa[2]; float4* qb[2]; float4* qc[2];   // path queues, ping-pong: (o, pixel) (d, rng_hi) (throughput, frame in batch)
 };
 
 struct WfFrame {
     uint32_t frame, seed_hi, seed_lo;
     float u1, u2;                // sobol2(frame), pt_raygen.wgsl:122-153 (computed on the host: integer work)
-    uint32_t* counts;            // this frame's kWfMaxDepth + 1 queue lengths; counts[k] = rays traced at depth k (k >= 1)
+};
+
+// A batch of consecutive frames traced together: small images do not fill 148 SMs with one frame's paths, least of all at depth >= 2.
+constexpr uint32_t kWfMaxBatch = 16;
+struct WfBatch {
+    uint32_t first_frame, nframes;
+    uint32_t seed_hi[kWfMaxBatch], seed_lo[kWfMaxBatch];
+    float u1[kWfMaxBatch], u2[kWfMaxBatch];
+    uint32_t* counts;            // [frame][kWfMaxDepth + 1] rays traced at depth k of each frame (k >= 1), whole render
+    uint32_t* qcount;            // this batch's kWfMaxDepth + 1 queue lengths
+    __device__ __forceinline__ WfFrame frame(uint32_t fl) const {
+        WfFrame F;
+        F.frame = first_frame + fl; F.seed_hi = seed_hi[fl]; F.seed_lo = seed_lo[fl]; F.u1 = u1[fl]; F.u2 = u2[fl];
+        return F;
+    }
 };
 
 struct WfPath { v3 o, d, thr; uint32_t pixel, rng_hi; float tmin; };
@@ -550,46 +570,66 @@ __device__ __forceinline__ bool wf_bounce(const WfParams& P, const WfFrame& F, W
     return true;
 }
 
-// Bounce `depth` of every path in the queue (depth 0: one primary ray per pixel, generated in place).  Survivors are compacted into
-// the other queue with one atomic per warp.  Launched with a fixed grid; the queue length is read from device memory.
+// Warp-aggregated per-frame ray counter: one atomic per distinct frame among the surviving lanes (usually one or two).
+__device__ __forceinline__ void wf_count_rays(uint32_t* counts, uint32_t first_frame, uint32_t fl, bool alive, uint32_t lane, uint32_t depth) {
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, alive);
+    while (todo) {
+        const int leader = __ffs((int)todo) - 1;
+        const uint32_t f = __shfl_sync(0xFFFFFFFFu, fl, leader);
+        const uint32_t same = __ballot_sync(0xFFFFFFFFu, alive && fl == f);
+        if ((int)lane == leader) atomicAdd(counts + (size_t)(first_frame + f) * (kWfMaxDepth + 1u) + depth + 1u, (uint32_t)__popc(same));
+        todo &= ~same;
+    }
+}
+
+// Bounce `depth` of every path in the queue, for a batch of frames at once (depth 0: one primary ray per owned pixel per frame,
+// generated in place).  Survivors are compacted into the other queue with one atomic per warp.  Launched with a fixed grid; the queue
+// length is read from device memory.  A path adds into its own frame's radiance sum (fsum), never into another frame's.
 template <bool PRIMARY>
-__global__ void __launch_bounds__(kWfThreads) k_wf_bounce(WfParams P, WfFrame F, uint32_t depth) {
-    const uint32_t count = PRIMARY ? P.w * P.local_rows : F.counts[depth];
+__global__ void __launch_bounds__(kWfThreads, F3D_WF_MIN_CTAS) k_wf_bounce(WfParams P, WfBatch B, uint32_t depth) {
+    const uint32_t per_frame = P.w * P.local_rows;
+    const uint32_t count = PRIMARY ? per_frame * B.nframes : B.qcount[depth];
     const uint32_t in = depth & 1u, out = in ^ 1u;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t stride = gridDim.x * blockDim.x;
+    const size_t npx = (size_t)P.w * P.h;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {   // warp-uniform trip count
         const uint32_t i = base + lane;
-        bool alive = false, skip = false;
+        bool alive = false, skip = i >= count;
+        uint32_t fl = 0;
         WfPath p;
-        if (i < count) {
+        if (!skip) {
             if (PRIMARY) {
+                fl = i / per_frame;
+                const uint32_t li = i - fl * per_frame;
                 // local row lr of this rank -> global row: its blocks are rank, rank + world, rank + 2 world, ...
-                const uint32_t lr = i / P.w, x = i - lr * P.w;
+                const uint32_t lr = li / P.w, x = li - lr * P.w;
                 const uint32_t row = ((lr / P.part_rows) * P.part_world + P.part_rank) * P.part_rows + lr % P.part_rows;
                 skip = row >= P.h;
-                if (!skip) p = wf_raygen(P, F, row * P.w + x);
+                if (!skip) p = wf_raygen(P, B.frame(fl), row * P.w + x);
             } else {
                 const float4 a = P.qa[in][i], b = P.qb[in][i], c = P.qc[in][i];
                 p.o = V3(a.x, a.y, a.z); p.pixel = __float_as_uint(a.w);
                 p.d = V3(b.x, b.y, b.z); p.rng_hi = __float_as_uint(b.w);
-                p.thr = V3(c.x, c.y, c.z); p.tmin = 1e-3f;
+                p.thr = V3(c.x, c.y, c.z); fl = __float_as_uint(c.w); p.tmin = 1e-3f;
             }
             if (!skip) {
-                float4 acc = P.accum[p.pixel];
-                alive = wf_bounce(P, F, p, depth, acc);
-                P.accum[p.pixel] = acc;
+                float4* sum = P.fsum + fl * npx + p.pixel;
+                float4 acc = PRIMARY ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : *sum;
+                alive = wf_bounce(P, B.frame(fl), p, depth, acc);
+                *sum = acc;
             }
         }
+        wf_count_rays(B.counts, B.first_frame, fl, alive, lane, depth);
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
         if (mask) {
             uint32_t slot = 0;
-            if (lane == 0u) slot = atomicAdd(F.counts + depth + 1u, (uint32_t)__popc(mask));
+            if (lane == 0u) slot = atomicAdd(B.qcount + depth + 1u, (uint32_t)__popc(mask));
             slot = __shfl_sync(0xFFFFFFFFu, slot, 0) + (uint32_t)__popc(mask & ((1u << lane) - 1u));
             if (alive) {
                 P.qa[out][slot] = make_float4(p.o.x, p.o.y, p.o.z, __uint_as_float(p.pixel));
                 P.qb[out][slot] = make_float4(p.d.x, p.d.y, p.d.z, __uint_as_float(p.rng_hi));
-                P.qc[out][slot] = make_float4(p.thr.x, p.thr.y, p.thr.z, 0.0f);
+                P.qc[out][slot] = make_float4(p.thr.x, p.thr.y, p.thr.z, __uint_as_float(fl));
             }
         }
     }
@@ -597,22 +637,43 @@ __global__ void __launch_bounds__(kWfThreads) k_wf_bounce(WfParams P, WfFrame F,
 
 // The thin tail: every path still alive at `depth` is walked to its end by one thread (a few percent of the pixels are left by then,
 // and they die off geometrically under Russian roulette, so compacting them bounce by bounce would cost more launches than work).
-__global__ void __launch_bounds__(kWfThreads) k_wf_tail(WfParams P, WfFrame F, uint32_t depth) {
-    const uint32_t count = F.counts[depth];
+__global__ void __launch_bounds__(kWfThreads, F3D_WF_MIN_CTAS) k_wf_tail(WfParams P, WfBatch B, uint32_t depth) {
+    const uint32_t count = B.qcount[depth];
     const uint32_t in = depth & 1u;
+    const size_t npx = (size_t)P.w * P.h;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         const float4 a = P.qa[in][i], b = P.qb[in][i], c = P.qc[in][i];
         WfPath p;
         p.o = V3(a.x, a.y, a.z); p.pixel = __float_as_uint(a.w);
         p.d = V3(b.x, b.y, b.z); p.rng_hi = __float_as_uint(b.w);
         p.thr = V3(c.x, c.y, c.z); p.tmin = 1e-3f;
-        float4 acc = P.accum[p.pixel];
+        const uint32_t fl = __float_as_uint(c.w);
+        const WfFrame F = B.frame(fl);
+        float4* sum = P.fsum + fl * npx + p.pixel;
+        float4 acc = *sum;
         for (uint32_t d = depth; d < kWfMaxDepth; d++) {
             if (!wf_bounce(P, F, p, d, acc)) break;
-            atomicAdd(F.counts + d + 1u, 1u);
+            atomicAdd(B.counts + (size_t)(B.first_frame + fl) * (kWfMaxDepth + 1u) + d + 1u, 1u);
         }
-        P.accum[p.pixel] = acc;
+        *sum = acc;
     }
+}
+
+// End of a batch: every owned pixel adds its frames' radiance sums to the accumulator IN FRAME ORDER, so the image does not depend on
+// how many frames shared a batch.
+__global__ void __launch_bounds__(kWfThreads) k_wf_merge(WfParams P, uint32_t nframes) {
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= P.w * P.local_rows) return;
+    const uint32_t lr = li / P.w, x = li - lr * P.w;
+    const uint32_t row = ((lr / P.part_rows) * P.part_world + P.part_rank) * P.part_rows + lr % P.part_rows;
+    if (row >= P.h) return;
+    const size_t npx = (size_t)P.w * P.h, pix = (size_t)row * P.w + x;
+    float4 a = P.accum[pix];
+    for (uint32_t f = 0; f < nframes; f++) {
+        const float4 s = P.fsum[f * npx + pix];
+        a.x += s.x; a.y += s.y; a.z += s.z;
+    }
+    P.accum[pix] = a;
 }
 
 // adjudication.rs:318-331 (mean over frames, alpha 1) + resolve_reference_hdr_to_rgba8, src/core/tonemap.rs:11-32

@@ -24,7 +24,9 @@
  * WHERE THIS DEPARTS FROM THE SHADERS, all stated in DESIGN.md section 9e:
  *   - accumulation order.  The reference adds several shadow rays of one pixel from different threads of one dispatch with a
  *     non-atomic read-modify-write (pt_shadow.wgsl:288-291), so its own result is order- and timing-dependent.  Here (and in the
- *     CUDA build) a pixel's adds happen in push order: emissive, environment, directional, area, then the miss term.
+ *     CUDA build) a frame sums its contributions to a pixel from zero in push order (emissive, environment, directional, area, then
+ *     the miss term) and the frame sums are added to the accumulator in frame order -- the same terms as the reference's in-place
+ *     adds, associated per frame so that frames can be traced concurrently on the device.
  *   - the mesh is swept triangle by triangle (lowest index wins ties); the BVH the reference traverses only prunes that sweep.
  *   - not restated: hair segments, ReSTIR reservoirs, the fog medium, anisotropic GGX (ax != ay), debug AOV preview.
  *   - transcendental intrinsics are pinned as in the rest of the oracle: sin/cos = f3do_sincos, tan = sin/cos,
@@ -360,7 +362,9 @@ static uint32_t trace_pixel(const wf_scene* S, const f3do_wavefront_scene* D, ui
     ray.o = P3(D->cam_origin); ray.d = rd; ray.tmin = 1e-4f; ray.tmax = 1e30f;
     w3 thr = W3(1, 1, 1);
     uint32_t rng_hi = seed_hi ^ (pix * 9781u) ^ (frame * 6271u);
-    float* px_acc = accum + 4 * (size_t)pix;
+    float px_acc[3] = {0.0f, 0.0f, 0.0f}; /* this frame's radiance sum; added to the accumulator when the path ends */
+    float* px_out = accum + 4 * (size_t)pix;
+#define WF_RETURN(n) do { px_out[0] += px_acc[0]; px_out[1] += px_acc[1]; px_out[2] += px_acc[2]; return (n); } while (0)
 
     for (uint32_t depth = 0; depth < 16u; depth++) {
         iters[depth]++;
@@ -400,7 +404,7 @@ static uint32_t trace_pixel(const wf_scene* S, const f3do_wavefront_scene* D, ui
             /* ---- miss, pt_scatter.wgsl:108-131 ---- */
             w3 sky = wmix3(P3(S->env + 8), P3(S->env + 12), 0.5f * (ray.d.y + 1.0f));
             acc_add(px_acc, wmul(thr, sky));
-            return depth + 1u;
+            WF_RETURN(depth + 1u);
         }
         const w3 hp = wadd(ray.o, wscale(ray.d, t_best));
         const w3 hn = n_hit;
@@ -525,7 +529,7 @@ static uint32_t trace_pixel(const wf_scene* S, const f3do_wavefront_scene* D, ui
             w3 hw = wnormalize(to_world(&basis, W3(sh * c, sh * s, ch)));
             wi = wnormalize(reflect3(wneg(wo), hw));
             float ndl = fmaxf(wdot(n, wi), 0.0f), ndh = fmaxf(wdot(n, hw), 0.0f), vdh = fmaxf(wdot(wo, hw), 0.0f);
-            if (!(ndl > 0.0f && ndv > 0.0f)) return depth + 1u; /* invalid sample: the thread moves to its next hit, :771-774 */
+            if (!(ndl > 0.0f && ndv > 0.0f)) WF_RETURN(depth + 1u); /* invalid sample: the thread moves to its next hit, :771-774 */
             float D = a2 / fmaxf(WF_PI * pow2f((ndh * ndh) * (a2 - 1.0f) + 1.0f), 1e-6f);
             float k = pow2f(a + 1.0f) / 8.0f;
             float G = (ndl / (ndl * (1.0f - k) + k)) * (ndv / (ndv * (1.0f - k) + k));
@@ -564,10 +568,10 @@ static uint32_t trace_pixel(const wf_scene* S, const f3do_wavefront_scene* D, ui
             float q_extra = fminf(fmaxf(1.0f - max_c / 0.25f, 0.0f), 0.90f);
             q = fminf(fmaxf(q + q_extra, 0.0f), 0.95f);
             float u = wf_rand(&rng);
-            if (u < q) return depth + 1u;
+            if (u < q) WF_RETURN(depth + 1u);
             rr_scale = 1.0f / (1.0f - q);
         }
-        if (!(depth + 1u < 16u)) return depth + 1u;
+        if (!(depth + 1u < 16u)) WF_RETURN(depth + 1u);
         /* scatter, :831-848, pt_scatter.wgsl:77-106 */
         ray.o = wadd(hp, wscale(wnormalize(hn), 1e-3f));
         ray.d = wi;
@@ -576,8 +580,9 @@ static uint32_t trace_pixel(const wf_scene* S, const f3do_wavefront_scene* D, ui
         thr = wscale(nthr, rr_scale);
         rng_hi = rng;
     }
-    return 16u;
+    WF_RETURN(16u);
 }
+#undef WF_RETURN
 
 static inline float srgb_encode(float c) { /* tonemap.rs:12-18; powf pinned */
     if (c <= 0.0031308f) return 12.92f * c;

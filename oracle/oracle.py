@@ -109,7 +109,7 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (gcc, no FMA contraction)."""
-    src_mtime = max((_HERE / n).stat().st_mtime for n in ("f3d_oracle.c", "f3d_aether_oracle.c", "f3d_smoke_oracle.c", "f3d_viewshed_oracle.c", "f3d_lbvh_oracle.c", "f3d_oracle.h", "Makefile"))
+    src_mtime = max((_HERE / n).stat().st_mtime for n in ("f3d_oracle.c", "f3d_aether_oracle.c", "f3d_smoke_oracle.c", "f3d_viewshed_oracle.c", "f3d_lbvh_oracle.c", "f3d_wavefront_oracle.c", "f3d_oracle.h", "Makefile"))
     if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src_mtime:
         env = dict(os.environ)
         env.pop("CC", None)

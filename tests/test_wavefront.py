@@ -216,11 +216,15 @@ def _compare(native, scene, w, h, spp):
     return o, st
 
 
-def test_emulated_cuda_build_is_bit_identical_on_the_adjudication_scene():
+def test_emulated_cuda_build_is_bit_identical_on_the_adjudication_scene(monkeypatch):
     with _emu.emulated_backend() as native:
-        o, st = _compare(native, _adjudication(), 48, 40, 3)
-        assert st.launches == 3 * 5 + 1 and o["min_iterations"] >= 2
+        o, st = _compare(native, _adjudication(), 48, 40, 3)     # small image: all three frames share one batch
+        assert st.launches == 6 + 1 and o["min_iterations"] >= 2
         _compare(native, _adjudication(), 33, 7, 2)              # ragged: not a multiple of the warp or the block
+        for batch, launches in (("1", 5 * 6 + 1), ("2", 3 * 6 + 1), ("16", 6 + 1)):   # the image does not depend on the batch size
+            monkeypatch.setenv("F3D_B200_WF_BATCH", batch)
+            _, st = _compare(native, _adjudication(), 40, 24, 5)
+            assert st.launches == launches
 
 
 @pytest.mark.parametrize("instanced,res", [(False, 6), (True, 6), (False, 2), (True, 1)])
