@@ -4,8 +4,10 @@
 # (per-kernel gpu__time_duration of one representative call each).  Outputs land in gpurun_out/.
 TAG=${1:-x}
 mkdir -p gpurun_out
-python -m pytest tests/test_aether.py tests/test_smoke.py tests/test_viewshed.py tests/test_lbvh.py -m gpu -q 2>&1 | tail -4
+python -m pytest tests/test_aether.py tests/test_smoke.py tests/test_viewshed.py tests/test_lbvh.py tests/test_wavefront.py -m gpu -q 2>&1 | tail -4
 python tools/bench_smoke.py > gpurun_out/bench_smoke_$TAG.json 2> gpurun_out/bench_smoke_$TAG.err; tail -c 600 gpurun_out/bench_smoke_$TAG.json
+python tools/bench_wavefront.py --spp 1024 > gpurun_out/bench_wavefront_$TAG.json 2> gpurun_out/bench_wavefront_$TAG.err; tail -c 600 gpurun_out/bench_wavefront_$TAG.json
+F3D_B200_WF_BATCH=1 python tools/bench_wavefront.py --spp 256 --oracle-spp 0 > gpurun_out/bench_wavefront_batch1_$TAG.json 2>&1   # A/B: one frame per batch
 cat > /tmp/f3d_rows_once.py <<'PY'
 import sys, numpy as np
 sys.path.insert(0, "tests")
@@ -24,8 +26,10 @@ print("lit fraction", V.compute_shadow_mask(sh, sinp, sopts).mean())            
 rng = np.random.default_rng(0); m = 1 << 20
 c = rng.uniform(-100, 100, (m, 1, 3)).astype(np.float32) + rng.uniform(-0.5, 0.5, (m, 3, 3)).astype(np.float32)
 _native.lbvh_build(c.reshape(-1, 3), np.arange(3 * m, dtype=np.uint32).reshape(m, 3))                         # LBVH of 1 M triangles
+from forge3d_b200 import wavefront as wf
+wf.render_pt_reference(wf.adjudication_scene(), 512, 512, 16)                                                  # one batch of 8 + 8 frames
 PY
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_aether|k_viewshed|k_shadow_mask|k_lbvh|k_smoke" --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_aether|k_viewshed|k_shadow_mask|k_lbvh|k_smoke|k_wf_" --csv \
     --log-file gpurun_out/launches_rows_$TAG.csv python /tmp/f3d_rows_once.py > gpurun_out/rows_$TAG.log 2>&1
 tail -3 gpurun_out/rows_$TAG.log
 python - <<PY

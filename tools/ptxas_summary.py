@@ -38,7 +38,7 @@ def main():
         if m:
             name = m.group(1)
             counts[name] = 0
-        elif name and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+        elif name and re.match(r"\s+/\*[0-9a-f]{4,6}\*/", line):
             counts[name] += 1
     print(f"{'kernel':46s} {'regs':>5s} {'stack B':>8s} {'spills st/ld':>13s} {'static smem B':>14s} {'SASS instr':>11s}")
     for r in rows:
