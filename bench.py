@@ -153,6 +153,24 @@ def cpu_baseline(dem, cam, kw, threads=0):
             "ms_per_frame_sample": dt * 1e3 / frames}
 
 
+def widened_rows():
+    """Side benches of the SURVEY section 8f rows (tools/bench_*.py), each in its own process under a timeout so that nothing they do
+    can disturb the headline line; their JSON is attached under "widened_rows".  N = 1 only; F3D_BENCH_ROWS=0 skips them."""
+    rows = {}
+    for name, cmd in (("wavefront", ["tools/bench_wavefront.py", "--spp", "512", "--oracle-spp", "8", "--repeats", "2"]),
+                      ("smoke", ["tools/bench_smoke.py", "--steps", "3"]),
+                      ("viewshed", ["tools/bench_viewshed.py"])):
+        t0 = time.time()
+        try:
+            res = subprocess.run([sys.executable, *cmd], cwd=str(ROOT), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=150)
+            last = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+            rows[name] = json.loads(last[-1]) if res.returncode == 0 and last else {"error": (res.stderr or res.stdout)[-300:]}
+        except Exception as exc:   # timeout, missing file, bad JSON: the headline stands without the row
+            rows[name] = {"error": repr(exc)[:300]}
+        rows[name]["wall_s"] = round(time.time() - t0, 1)
+    return rows
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU implementation (oracle port), rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -193,6 +211,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rows", action="store_true", help="skip the side benches of the widened rows")
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     args = ap.parse_args()
@@ -334,6 +353,8 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(dem, cam, kw)
+            if os.environ.get("F3D_BENCH_ROWS", "1") != "0" and not args.no_rows:
+                line["widened_rows"] = widened_rows()
         elif not args.no_cpu_baseline:
             line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port",
                                     "sample": "reported at N=1 only"}
