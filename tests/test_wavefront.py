@@ -210,7 +210,12 @@ def test_argument_errors_need_no_device():
 def _compare(native, scene, w, h, spp):
     o = oracle.wavefront_render(scene, w, h, spp)
     hdr, rgba, st = wf.render_pt_reference(scene, w, h, spp, return_rgba8=True, return_stats=True)
-    assert np.array_equal(_bits(hdr), _bits(o["hdr"]))
+    if not np.array_equal(_bits(hdr), _bits(o["hdr"])):         # say how far apart, for whoever reads the GPU log
+        bad = (hdr.view(np.uint32) != o["hdr"].view(np.uint32)).any(axis=2)
+        rel = np.abs(hdr - o["hdr"]) / np.maximum(np.abs(o["hdr"]), 1e-12)
+        first = tuple(int(v) for v in np.argwhere(bad)[0])
+        raise AssertionError(f"radiance differs from the oracle on {int(bad.sum())} of {bad.size} pixels, max rel {float(rel.max()):.3e}, "
+                             f"first at (y, x) = {first}: got {hdr[first]}, want {o['hdr'][first]}; rays {st.rays} vs {o['rays']}")
     assert np.array_equal(rgba, o["rgba8"])
     assert (st.rays, st.max_rays_per_frame, st.min_iterations) == (o["rays"], o["max_rays_per_frame"], o["min_iterations"])
     return o, st
@@ -367,7 +372,8 @@ def test_gpu_gate_render_equals_the_committed_oracle_render():
     want = read_png(GOLDEN / "wavefront_oracle_512.png")
     rgba, meta = wf.render_adjudication_pt(512, 512, 4096)
     assert rgba.shape == (512, 512, 4) and rgba.dtype == np.uint8
-    assert np.array_equal(rgba, want)
+    diff = np.abs(rgba.astype(np.int16) - want.astype(np.int16))
+    assert np.array_equal(rgba, want), f"{int((diff > 0).any(axis=2).sum())} pixels differ, max |diff| {int(diff.max())}"
     assert meta["pt"]["spp"] == 4096.0 and meta["pt"]["sky_b"] == float(f32(0.70))
 
 
