@@ -18,8 +18,8 @@ def main():
     only = sys.argv[3] if len(sys.argv) > 3 else ""
     with tempfile.TemporaryDirectory() as d:
         subprocess.run(["cuobjdump", "-xelf", "all", str(Path(lib).resolve())], cwd=d, check=True, stdout=subprocess.DEVNULL)
-        cubin = next(Path(d).glob("*.cubin"))
-        text = subprocess.run(["nvdisasm", "--print-line-info", str(cubin)], stdout=subprocess.PIPE, text=True, check=True).stdout
+        text = "".join(subprocess.run(["nvdisasm", "--print-line-info", str(c)], stdout=subprocess.PIPE, text=True, check=True).stdout
+                       for c in sorted(Path(d).glob("*.cubin")))   # one cubin per translation unit
     counts = collections.Counter()
     in_kernel, cur = False, ("?", 0)
     for line in text.splitlines():
