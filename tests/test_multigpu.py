@@ -162,3 +162,54 @@ def test_reservoir_validity_is_checked_across_ranks(case):
             assert "produced no valid reservoirs for a sun-lit scene" in status
         else:
             assert status == "ok" and top_hits == 0 and bottom_hits > 0, (status, top_hits, bottom_hits)
+
+
+def _wavefront_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    import test_wavefront as T
+    from forge3d_b200 import distributed as D
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        hdr, rgba = D.wavefront_partitioned(T._rich_scene(True, 6), 96, 70, 3, block_rows=16, device=rank, tensor_device="cuda")
+        err = ""
+        try:
+            D.wavefront_partitioned(T._empty_scene(), 32, 32, 1, block_rows=16, device=rank, tensor_device="cuda")
+        except RuntimeError as e:      # every rank raises the reference's error together
+            err = str(e)
+        q.put((rank, hdr, rgba, err))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_wavefront_tracer_partition_over_nccl_is_bit_identical():
+    """SURVEY section 8f row 2 over 2 GPUs: rows dealt in 16-row blocks, no data-path collective, one all-gather per image."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    import test_wavefront as T
+    from forge3d_b200 import wavefront as wf
+
+    whole_hdr, whole_rgba = wf.render_pt_reference(T._rich_scene(True, 6), 96, 70, 3, return_rgba8=True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_wavefront_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, hdr, rgba, err in results:
+        assert np.array_equal(hdr.view(np.uint32), whole_hdr.view(np.uint32)) and np.array_equal(rgba, whole_rgba), rank
+        assert "executed 1 wavefront iteration" in err, (rank, err)
