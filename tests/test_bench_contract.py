@@ -47,3 +47,14 @@ def test_roofline_model_matches_survey_worked_example():
     peak, src = bench.measured_hbm_peak()
     assert peak > 1000 and ("measured" in src or "fallback" in src)
     assert (bench.WIDTH, bench.HEIGHT, bench.DEM_N) == (1920, 1080, 2048)
+
+
+def test_widened_rows_never_raise_and_report_errors_in_place():
+    """The side benches run in their own processes; without a GPU each must come back as an 'error' entry, not an exception."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    rows = bench.widened_rows()
+    assert set(rows) == {"wavefront", "smoke", "viewshed"}
+    for name, row in rows.items():
+        assert "wall_s" in row and ("error" in row or "metric" in row), (name, row)
