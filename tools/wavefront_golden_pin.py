@@ -39,5 +39,10 @@ small = oracle.wavefront_render(scene, 64, 48, 6)   # arithmetic regression pin 
 out["oracle_64x48x6_hdr_sha256"] = hashlib.sha256(np.ascontiguousarray(small["hdr"]).view(np.uint8).tobytes()).hexdigest()
 print(json.dumps(out, indent=1))
 if spp == 4096:
-    (ROOT / "tests/golden/wavefront_pin.json").write_text(json.dumps(out, indent=1) + "\n")
+    old = ROOT / "tests/golden/wavefront_pin.json"
+    if old.exists():   # keep the record of the full-size rehearsal of the CUDA build only while the oracle's image is unchanged
+        prev = json.loads(old.read_text())
+        if prev.get("ssim_vs_reference_golden") == out["ssim_vs_reference_golden"] and "cuda_source_on_simt_interpreter_byte_equal_at_gate_size" in prev:
+            out["cuda_source_on_simt_interpreter_byte_equal_at_gate_size"] = prev["cuda_source_on_simt_interpreter_byte_equal_at_gate_size"]
+    old.write_text(json.dumps(out, indent=1) + "\n")
     write_png(ROOT / "tests/golden/wavefront_oracle_512.png", r["rgba8"])
