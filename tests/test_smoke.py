@@ -227,3 +227,21 @@ def test_emulated_empty_space_skip_is_exact_and_backs_off_for_huge_values(monkey
         dom.close()
     assert np.array_equal(a, o) and np.array_equal(b, o)
     assert np.array_equal(c, oracle.smoke_raymarch_rgba(dom, st, 40, 26, **cam))
+
+
+def test_emulated_full_size_frame_is_bit_identical_to_the_oracle():
+    """BASELINE config 4's frame shape: 1920 x 1080 perspective view of a dense 64^3 plume with self-shadowing, every pixel compared."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import bench_smoke
+
+    dom, st = bench_smoke.plume(64), SmokeRenderSettings()
+    cam = dict(camera_pos=(-55.0, 22.0, -48.0), target=(0.0, 16.0, 0.0), fovy_deg=42.0, sun_direction=(0.4, 0.8, -0.2))
+    want = oracle.smoke_raymarch_rgba(dom, st, 1920, 1080, cam["camera_pos"], cam["target"], (0.0, 1.0, 0.0), cam["fovy_deg"],
+                                      cam["sun_direction"])
+    with _emu.emulated_backend():
+        got = dom.render_rgba(1920, 1080, settings=st, **cam)
+    assert np.array_equal(np.asarray(got), np.asarray(want))
+    assert (np.asarray(want)[..., 3] > 0).sum() > 100_000       # the plume really covers a tenth of the frame
