@@ -80,6 +80,8 @@ extern "C" int f3d_wavefront_render_part(const f3d_wavefront_scene* sc, uint32_t
     if ((sc->nspheres && !sc->spheres) || (sc->ndir && !sc->dir_lights) || (sc->narea && !sc->area_lights) ||
         (sc->nimportance && !sc->importance) || (sc->mesh_ntris && (!sc->mesh_xyz || !sc->mesh_idx)) || (sc->ninstances && !sc->instances))
         return fail(F3D_ERR_ARGUMENT, "null scene buffer with a non-zero count");
+    // the sphere array doubles as the material table (pt_shade.wgsl:487-493 reads slot 0 for every out-of-range id)
+    if (sc->nspheres == 0) return fail(F3D_ERR_ARGUMENT, "the scene needs at least one sphere / material slot");
     for (uint32_t i = 0; i < sc->nspheres; i++) {
         const float* s = sc->spheres + 20 * (size_t)i;
         if (fabsf(fmaxf(0.002f, s[15]) - fmaxf(0.002f, s[16])) >= 1e-4f)

@@ -593,6 +593,7 @@ int f3do_wavefront_render(const f3do_wavefront_scene* D, uint32_t W, uint32_t H,
                           uint32_t num_frames, float* accum_io, float* hdr_out, uint8_t* rgba8_out, uint64_t* stats_out) {
     g_wf_err[0] = 0;
     if (W == 0 || H == 0 || spp_frames == 0) return wf_fail("adjudication PT reference requires non-zero width/height/spp");
+    if (D->nspheres == 0) return wf_fail("the scene needs at least one sphere / material slot");
     for (uint32_t i = 0; i < D->nspheres; i++) {
         const float* s = D->spheres + 20 * (size_t)i;
         if (fabsf(fmaxf(0.002f, s[15]) - fmaxf(0.002f, s[16])) >= 1e-4f) return wf_fail("anisotropic GGX (ax != ay) is not supported");

@@ -268,6 +268,14 @@ def test_emulated_frame_rules_raise_the_reference_errors():
         s.spheres[0, 15], s.spheres[0, 16] = 0.3, 0.1
         with pytest.raises(ValueError, match="anisotropic GGX"):
             wf.render_pt_reference(s, 8, 8, 1)
+        s = _adjudication()
+        s.spheres = np.zeros((0, 20), f32)
+        with pytest.raises(ValueError, match="at least one sphere / material slot"):
+            wf.render_pt_reference(s, 8, 8, 1)
+        s = _adjudication()
+        s.mesh_idx = np.array([[0, 1, 9]], np.uint32)
+        with pytest.raises(ValueError, match="mesh index 9 out of range"):
+            wf.render_pt_reference(s, 8, 8, 1)
     for scene, text in ((_empty_scene(), "executed 1 wavefront iteration"), (_furnace_scene(), "ray queue overflow")):
         with pytest.raises(oracle.OracleError, match=text):
             oracle.wavefront_render(scene, 16, 8, 2)
