@@ -135,6 +135,9 @@ extern "C" int f3d_wavefront_render_part(const f3d_wavefront_scene* sc, uint32_t
     uint32_t batch = per_frame ? (uint32_t)std::min<uint64_t>(kWfMaxBatch, std::max<uint64_t>(1u, (1ull << 21) / per_frame)) : 1u;
     if (const char* e = getenv("F3D_B200_WF_BATCH")) batch = (uint32_t)std::min<long>(kWfMaxBatch, std::max<long>(1, atol(e)));
     batch = std::min(batch, spp_frames);
+    // bounces [0, wide_depth) run as compacted waves, the tail kernel walks the rest; any split gives the same image
+    uint32_t wide_depth = kWfWideDepth;
+    if (const char* e = getenv("F3D_B200_WF_WIDE_DEPTH")) wide_depth = (uint32_t)std::min<long>(kWfMaxDepth - 1u, std::max<long>(1, atol(e)));
     const uint32_t nbatches = (spp_frames + batch - 1u) / batch;
     if ((uint64_t)per_frame * batch > 0x7FFFFFFFull) return fail(F3D_ERR_ARGUMENT, "image too large for the 32-bit ray queues");
     const size_t qcap = std::max<size_t>(1, (size_t)per_frame * batch);
@@ -180,10 +183,10 @@ extern "C" int f3d_wavefront_render_part(const f3d_wavefront_scene* sc, uint32_t
         B.qcount = d_qcount + (size_t)b * kSlots;
         const uint32_t g0 = std::max(1u, (per_frame * B.nframes + kWfThreads - 1u) / kWfThreads);
         k_wf_bounce<true><<<g0, kWfThreads>>>(P, B, 0u);
-        for (uint32_t d = 1; d < kWfWideDepth; d++) k_wf_bounce<false><<<wide, kWfThreads>>>(P, B, d);
-        k_wf_tail<<<thin, kWfThreads>>>(P, B, kWfWideDepth);
+        for (uint32_t d = 1; d < wide_depth; d++) k_wf_bounce<false><<<wide, kWfThreads>>>(P, B, d);
+        k_wf_tail<<<thin, kWfThreads>>>(P, B, wide_depth);
         k_wf_merge<<<owned, kWfThreads>>>(P, B.nframes);
-        launches += kWfWideDepth + 2u;
+        launches += wide_depth + 2u;
         if ((b & 15u) == 15u) CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaGetLastError());

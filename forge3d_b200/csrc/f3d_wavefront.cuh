@@ -29,7 +29,7 @@ namespace f3d {
 #define F3D_WF_MIN_CTAS 2   // resident CTAs per SM the bounce kernels are compiled for (3 costs ~300 B of spills per thread: A/B on the GPU)
 #endif
 constexpr int kWfThreads = 256;
-constexpr uint32_t kWfWideDepth = 4;    // bounces 0..3 are compacted waves; the tail kernel takes over at depth 4
+constexpr uint32_t kWfWideDepth = 4;    // default: bounces 0..3 are compacted waves, the tail kernel takes over at depth 4 (F3D_B200_WF_WIDE_DEPTH)
 constexpr uint32_t kWfMaxDepth = 16;    // (h.depth + 1) < 16, pt_shade.wgsl:831; MAX_DEPTH * 2 iterations, render.rs:115
 
 struct WfMesh {   // passed by value to the (non-inlined) traversal so that the kernel parameters are never copied to local memory

@@ -230,6 +230,11 @@ def test_emulated_cuda_build_is_bit_identical_on_the_adjudication_scene(monkeypa
             monkeypatch.setenv("F3D_B200_WF_BATCH", batch)
             _, st = _compare(native, _adjudication(), 40, 24, 5)
             assert st.launches == launches
+        monkeypatch.delenv("F3D_B200_WF_BATCH")
+        for wide in ("1", "2", "9", "15"):                       # ... nor on where the compacted waves hand over to the tail kernel
+            monkeypatch.setenv("F3D_B200_WF_WIDE_DEPTH", wide)
+            _, st = _compare(native, _rich_scene(False, 2), 32, 24, 3)
+            assert st.launches == int(wide) + 2 + 1
 
 
 @pytest.mark.parametrize("instanced,res", [(False, 6), (True, 6), (False, 2), (True, 1)])

@@ -8,6 +8,7 @@ python -m pytest tests/test_aether.py tests/test_smoke.py tests/test_viewshed.py
 python tools/bench_smoke.py > gpurun_out/bench_smoke_$TAG.json 2> gpurun_out/bench_smoke_$TAG.err; tail -c 600 gpurun_out/bench_smoke_$TAG.json
 python tools/bench_wavefront.py --spp 1024 > gpurun_out/bench_wavefront_$TAG.json 2> gpurun_out/bench_wavefront_$TAG.err; tail -c 600 gpurun_out/bench_wavefront_$TAG.json
 F3D_B200_WF_BATCH=1 python tools/bench_wavefront.py --spp 256 --oracle-spp 0 > gpurun_out/bench_wavefront_batch1_$TAG.json 2>&1   # A/B: one frame per batch
+for wd in 2 3 5 8; do F3D_B200_WF_WIDE_DEPTH=$wd python tools/bench_wavefront.py --spp 256 --oracle-spp 0 > gpurun_out/bench_wavefront_wide${wd}_$TAG.json 2>&1; done
 cat > /tmp/f3d_rows_once.py <<'PY'
 import sys, numpy as np
 sys.path.insert(0, "tests")
