@@ -3,7 +3,7 @@
 // over the bounce kernels of f3d_wavefront.cuh.  Per batch of frames: kWfWideDepth compacted bounce launches, one tail launch and the
 // in-order merge into the accumulator, all queued
 // without a host round trip (the reference reads a queue header back every bounce, wavefront/queues/types.rs:166-213); the per-frame
-// queue lengths stay in a device table that is read once at the end to apply the reference's two frame rules (>= 2 iterations,
+// path-length histograms stay in a device table that is read once at the end to apply the reference's two frame rules (>= 2 iterations,
 // ray-queue capacity 4 * W * H).  No CPU fallback.
 #include "f3d_host.h"
 #include "f3d_wavefront.cuh"
@@ -179,13 +179,12 @@ extern "C" int f3d_wavefront_render_part(const f3d_wavefront_scene* sc, uint32_t
             B.seed_lo[f] = splitmix32(sc->seed_lo ^ (fr * 0x00009E3Du));
             sobol2(fr, &B.u1[f], &B.u2[f]);                               // sidx = sample + frame_index * max(1, spp), spp = 1
         }
-        B.counts = d_counts;
         B.qcount = d_qcount + (size_t)b * kSlots;
         const uint32_t g0 = std::max(1u, (per_frame * B.nframes + kWfThreads - 1u) / kWfThreads);
         k_wf_bounce<true><<<g0, kWfThreads>>>(P, B, 0u);
         for (uint32_t d = 1; d < wide_depth; d++) k_wf_bounce<false><<<wide, kWfThreads>>>(P, B, d);
         k_wf_tail<<<thin, kWfThreads>>>(P, B, wide_depth);
-        k_wf_merge<<<owned, kWfThreads>>>(P, B.nframes);
+        k_wf_merge<<<owned, kWfThreads, B.nframes * kSlots * sizeof(uint32_t)>>>(P, B.first_frame, B.nframes, d_counts);
         launches += wide_depth + 2u;
         if ((b & 15u) == 15u) CUDA_TRY(cudaGetLastError());
     }
@@ -205,17 +204,22 @@ extern "C" int f3d_wavefront_render_part(const f3d_wavefront_scene* sc, uint32_t
     uint64_t total = 0, max_rays = 0;
     uint32_t min_iters = 0xFFFFFFFFu;
     for (uint32_t fr = 0; fr < spp_frames; fr++) {
-        const uint32_t* c = counts.data() + (size_t)fr * kSlots;
-        uint64_t cum = 0;
+        // hist[w] = paths of this frame that traced exactly w rays (k_wf_merge); rays at depth k = paths with w > k
+        const uint32_t* hist = counts.data() + (size_t)fr * kSlots;
+        uint64_t alive = 0, cum = 0;
+        for (uint32_t w = 1; w <= kWfMaxDepth; w++) alive += hist[w];
+        if (alive != n_primary || hist[0])
+            return fail(F3D_ERR_DEVICE, "wavefront frame %u: %llu paths accounted for, %u traced", fr, (unsigned long long)alive, n_primary);
         uint32_t executed = 0;
         for (uint32_t k = 0; k < kWfMaxDepth; k++) {
-            const uint64_t rays = k == 0 ? n_primary : c[k];
+            const uint64_t rays = alive;               // paths still tracing at depth k
             if (!rays) break;
             cum += rays;
             if (!part && cum > capacity)   // render.rs:127-137
                 return fail(F3D_ERR_RENDER, "wavefront frame %u: wavefront ray queue overflow: %llu rays pushed into capacity %llu", fr,
                             (unsigned long long)cum, (unsigned long long)capacity);
             executed++;
+            alive -= hist[k + 1u];
         }
         if (!part && executed < 2u)   // adjudication.rs:259-265
             return fail(F3D_ERR_RENDER,

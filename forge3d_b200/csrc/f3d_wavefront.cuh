@@ -65,7 +65,6 @@ struct WfBatch {
     uint32_t first_frame, nframes;
     uint32_t seed_hi[kWfMaxBatch], seed_lo[kWfMaxBatch];
     float u1[kWfMaxBatch], u2[kWfMaxBatch];
-    uint32_t* counts;            // [frame][kWfMaxDepth + 1] rays traced at depth k of each frame (k >= 1), whole render
     uint32_t* qcount;            // this batch's kWfMaxDepth + 1 queue lengths
     __device__ __forceinline__ WfFrame frame(uint32_t fl) const {
         WfFrame F;
@@ -570,18 +569,6 @@ __device__ __forceinline__ bool wf_bounce(const WfParams& P, const WfFrame& F, W
     return true;
 }
 
-// Warp-aggregated per-frame ray counter: one atomic per distinct frame among the surviving lanes (usually one or two).
-__device__ __forceinline__ void wf_count_rays(uint32_t* counts, uint32_t first_frame, uint32_t fl, bool alive, uint32_t lane, uint32_t depth) {
-    uint32_t todo = __ballot_sync(0xFFFFFFFFu, alive);
-    while (todo) {
-        const int leader = __ffs((int)todo) - 1;
-        const uint32_t f = __shfl_sync(0xFFFFFFFFu, fl, leader);
-        const uint32_t same = __ballot_sync(0xFFFFFFFFu, alive && fl == f);
-        if ((int)lane == leader) atomicAdd(counts + (size_t)(first_frame + f) * (kWfMaxDepth + 1u) + depth + 1u, (uint32_t)__popc(same));
-        todo &= ~same;
-    }
-}
-
 // Bounce `depth` of every path in the queue, for a batch of frames at once (depth 0: one primary ray per owned pixel per frame,
 // generated in place).  Survivors are compacted into the other queue with one atomic per warp.  Launched with a fixed grid; the queue
 // length is read from device memory.  A path adds into its own frame's radiance sum (fsum), never into another frame's.
@@ -617,10 +604,10 @@ __global__ void __launch_bounds__(kWfThreads, F3D_WF_MIN_CTAS) k_wf_bounce(WfPar
                 float4* sum = P.fsum + fl * npx + p.pixel;
                 float4 acc = PRIMARY ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : *sum;
                 alive = wf_bounce(P, B.frame(fl), p, depth, acc);
+                acc.w = __uint_as_float(depth + 1u);   // rays this path has traced so far: k_wf_merge turns these into the per-frame counts
                 *sum = acc;
             }
         }
-        wf_count_rays(B.counts, B.first_frame, fl, alive, lane, depth);
         const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
         if (mask) {
             uint32_t slot = 0;
@@ -651,29 +638,41 @@ __global__ void __launch_bounds__(kWfThreads, F3D_WF_MIN_CTAS) k_wf_tail(WfParam
         const WfFrame F = B.frame(fl);
         float4* sum = P.fsum + fl * npx + p.pixel;
         float4 acc = *sum;
-        for (uint32_t d = depth; d < kWfMaxDepth; d++) {
-            if (!wf_bounce(P, F, p, d, acc)) break;
-            atomicAdd(B.counts + (size_t)(B.first_frame + fl) * (kWfMaxDepth + 1u) + d + 1u, 1u);
-        }
+        uint32_t d = depth;
+        while (wf_bounce(P, F, p, d, acc)) d++;          // wf_bounce ends every path at depth kWfMaxDepth - 1
+        acc.w = __uint_as_float(d + 1u);
         *sum = acc;
     }
 }
 
 // End of a batch: every owned pixel adds its frames' radiance sums to the accumulator IN FRAME ORDER, so the image does not depend on
-// how many frames shared a batch.
-__global__ void __launch_bounds__(kWfThreads) k_wf_merge(WfParams P, uint32_t nframes) {
+// how many frames shared a batch.  The same pass bins the paths by the number of rays they traced (left in the sums' fourth lane by the
+// bounce kernels) into a per-frame histogram - shared-memory atomics, one flush per CTA - from which the host derives the per-frame,
+// per-depth ray counts the reference's two frame rules need; the bounce kernels themselves carry no counting atomics.
+__global__ void __launch_bounds__(kWfThreads) k_wf_merge(WfParams P, uint32_t first_frame, uint32_t nframes, uint32_t* __restrict__ hist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];      // nframes * (kWfMaxDepth + 1) counters
+    uint32_t* bins = reinterpret_cast<uint32_t*>(smem_raw);
+    const uint32_t nbins = nframes * (kWfMaxDepth + 1u);
+    for (uint32_t t = threadIdx.x; t < nbins; t += blockDim.x) bins[t] = 0u;
+    __syncthreads();
     const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= P.w * P.local_rows) return;
-    const uint32_t lr = li / P.w, x = li - lr * P.w;
-    const uint32_t row = ((lr / P.part_rows) * P.part_world + P.part_rank) * P.part_rows + lr % P.part_rows;
-    if (row >= P.h) return;
-    const size_t npx = (size_t)P.w * P.h, pix = (size_t)row * P.w + x;
-    float4 a = P.accum[pix];
-    for (uint32_t f = 0; f < nframes; f++) {
-        const float4 s = P.fsum[f * npx + pix];
-        a.x += s.x; a.y += s.y; a.z += s.z;
+    if (li < P.w * P.local_rows) {
+        const uint32_t lr = li / P.w, x = li - lr * P.w;
+        const uint32_t row = ((lr / P.part_rows) * P.part_world + P.part_rank) * P.part_rows + lr % P.part_rows;
+        if (row < P.h) {
+            const size_t npx = (size_t)P.w * P.h, pix = (size_t)row * P.w + x;
+            float4 a = P.accum[pix];
+            for (uint32_t f = 0; f < nframes; f++) {
+                const float4 s = P.fsum[f * npx + pix];
+                a.x += s.x; a.y += s.y; a.z += s.z;
+                atomicAdd(bins + f * (kWfMaxDepth + 1u) + min(__float_as_uint(s.w), kWfMaxDepth), 1u);
+            }
+            P.accum[pix] = a;
+        }
     }
-    P.accum[pix] = a;
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < nbins; t += blockDim.x)
+        if (bins[t]) atomicAdd(hist + (size_t)first_frame * (kWfMaxDepth + 1u) + t, bins[t]);
 }
 
 // adjudication.rs:318-331 (mean over frames, alpha 1) + resolve_reference_hdr_to_rgba8, src/core/tonemap.rs:11-32

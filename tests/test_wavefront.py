@@ -282,8 +282,12 @@ def test_emulated_frame_rules_raise_the_reference_errors():
         with pytest.raises(ValueError, match="mesh index 9 out of range"):
             wf.render_pt_reference(s, 8, 8, 1)
     for scene, text in ((_empty_scene(), "executed 1 wavefront iteration"), (_furnace_scene(), "ray queue overflow")):
-        with pytest.raises(oracle.OracleError, match=text):
+        with pytest.raises(oracle.OracleError, match=text) as want:
             oracle.wavefront_render(scene, 16, 8, 2)
+        with _emu.emulated_backend():
+            with pytest.raises(RuntimeError) as got:
+                wf.render_pt_reference(scene, 16, 8, 2)
+        assert str(got.value) == str(want.value)                 # same frame, same ray count in the text
 
 
 # ------------------------------------------------------------------ image partition (multi-GPU extension)
