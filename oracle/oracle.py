@@ -1,7 +1,9 @@
 """ctypes loader for the CPU oracle (TEST INFRASTRUCTURE -- never imported by forge3d_b200).
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
-may import this module.  It exposes the oracle through the same keyword surface as the
+Only tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference legs and the
+cpu_baseline legs of the side benches bench.py runs (tools/bench_*.py; tools/wavefront_golden_pin.py
+is the pin generator) may import this module -- always as the checker or the timed CPU baseline,
+never as a producer of product output.  It exposes the oracle through the same keyword surface as the
 reference's native seam (src/py_functions/path_tracing/terrain_reference.rs:224-288).
 """
 from __future__ import annotations
