@@ -129,6 +129,11 @@ def test_golden_pin_record_passes_the_reference_drift_gate():
     pin = json.loads((GOLDEN / "wavefront_pin.json").read_text())
     assert (pin["width"], pin["height"], pin["spp"]) == (512, 512, 4096)
     assert pin["ssim_vs_reference_golden"] >= 0.995 and pin["mean_abs_vs_reference_golden"] <= 2.0
+    # ... and through the reference's adjudication gate itself (dE2000 < 2 on >= 95 % of lit pixels, shadow-band SSIM > 0.96,
+    # tests/test_adjudication_gate.py:156-200) against the reference's committed RASTER golden, scored with the reference's own helpers
+    adj = pin["adjudication_vs_reference_raster_golden"]
+    assert adj["oracle_pt"]["delta_e2000_below_2_fraction_of_lit"] >= 0.95 and adj["oracle_pt"]["shadow_band_ssim"] > 0.96
+    assert adj["oracle_pt"]["mean_delta_e2000_lit"] <= adj["reference_golden_pt"]["mean_delta_e2000_lit"]   # at least as close as its own PT
     img = read_png(GOLDEN / "wavefront_oracle_512.png")
     assert img.shape == (512, 512, 4) and (img[..., 3] == 255).all()
     if REF_GOLDEN.exists():                                      # in the build container the score is recomputed from the two images
