@@ -154,7 +154,7 @@ def cpu_baseline(dem, cam, kw, threads=0):
 
 
 def widened_rows():
-    """Side benches of the SURVEY section 8f rows (tools/bench_*.py), each in its own process under a timeout so that nothing they do
+    """Side benches of the SURVEY section 8f rows (tools/bench_*.py), each in its own process under a 100 s timeout so that nothing they do
     can disturb the headline line; their JSON is attached under "widened_rows".  N = 1 only; F3D_BENCH_ROWS=0 skips them."""
     rows = {}
     for name, cmd in (("wavefront", ["tools/bench_wavefront.py", "--spp", "512", "--oracle-spp", "8", "--repeats", "2"]),
@@ -162,7 +162,7 @@ def widened_rows():
                       ("viewshed", ["tools/bench_viewshed.py"])):
         t0 = time.time()
         try:
-            res = subprocess.run([sys.executable, *cmd], cwd=str(ROOT), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=150)
+            res = subprocess.run([sys.executable, *cmd], cwd=str(ROOT), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=100)
             last = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
             rows[name] = json.loads(last[-1]) if res.returncode == 0 and last else {"error": (res.stderr or res.stdout)[-300:]}
         except Exception as exc:   # timeout, missing file, bad JSON: the headline stands without the row
