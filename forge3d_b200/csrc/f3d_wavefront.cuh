@@ -4,7 +4,7 @@
 //
 //   * one kernel per bounce instead of four stages: a thread owns a path for the whole bounce -- closest hit, the NEE samples with
 //     their any-hit shadow rays traced in place, the continuation sample, Russian roulette -- so hit / shadow / scatter records never
-//     travel through HBM; only the 44-byte path state does, once per bounce;
+//     travel through HBM; only the 48-byte path state does, once per bounce;
 //   * survivors are stream-compacted into the next bounce's queue with one warp-aggregated atomic per warp (ballot + popc), the stage the
 //     reference removed (wavefront/dispatch.rs:130-138); queue lengths stay on the device (the reference reads the 16-byte header back
 //     and stalls every bounce, queues/types.rs:166-213);
