@@ -182,7 +182,7 @@ class TerrainOut(C.Structure):
 
 # every symbol include/forge3d_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "f3d_terrain_reference_render", "f3d_last_error", "f3d_abi_version", "f3d_device_count",
+    "f3d_terrain_reference_render", "f3d_last_error", "f3d_abi_version", "f3d_device_count", "f3d_build_info",
     "f3d_session_create", "f3d_session_render_frames", "f3d_session_variance",
     "f3d_session_resolve_device", "f3d_session_validity", "f3d_session_resolve_host", "f3d_session_frames",
     "f3d_session_stats", "f3d_session_sync", "f3d_session_last_frames_ms", "f3d_session_destroy",
@@ -207,6 +207,7 @@ def lib():
     vp, u8p, fp, u32p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_uint32)
     L.f3d_terrain_reference_render.argtypes = [C.POINTER(TerrainDesc), C.POINTER(TerrainOut)]
     L.f3d_last_error.restype = C.c_char_p
+    L.f3d_build_info.restype = C.c_char_p
     L.f3d_session_create.argtypes = [C.POINTER(TerrainDesc), vp, C.POINTER(vp)]
     L.f3d_session_render_frames.argtypes = [vp, C.c_uint32]
     L.f3d_session_variance.argtypes = [vp, fp, C.POINTER(C.c_int32)]

@@ -6,6 +6,7 @@ library loads through ctypes without torch.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -31,20 +32,50 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libforge3d_b200.so")
 
 
-def needs_build() -> bool:
-    if not LIB.exists():
-        return True
-    deps = [CSRC / n for n in SOURCES + HEADERS] + [PKG.parent / "include" / "forge3d_b200.h"]
-    return LIB.stat().st_mtime < max(p.stat().st_mtime for p in deps)
+def _deps():
+    return [CSRC / n for n in SOURCES + HEADERS] + [PKG.parent / "include" / "forge3d_b200.h"]
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
-        return LIB
-    # F3D_B200_DEFINES="F3D_ANYHIT_SIGN_ORDER=1 ..." builds a compile-time variant of the kernels (A/B runs; see
+def source_hash() -> str:
+    """Content hash of every source the library is made from (mtimes lie after a checkout)."""
+    h = hashlib.sha1()
+    for p in _deps():
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def built_info(lib: Path = LIB) -> str:
+    """The `f3d_build_info()` string of a built library without loading it: "src=<hash>;defines=<...>" ("" if absent)."""
+    try:
+        blob = lib.read_bytes()
+    except OSError:
+        return ""
+    i = blob.find(b"F3D_BUILD_INFO:")
+    if i < 0:
+        return ""
+    j = blob.find(b"\0", i)
+    return blob[i + len(b"F3D_BUILD_INFO:"):j].decode(errors="replace")
+
+
+def needs_build(defines: str = "") -> bool:
+    """True unless LIB was built from exactly these sources with exactly these defines (a variant build left behind by an
+    A/B run is rebuilt, not silently reused as the default)."""
+    return built_info() != f"src={source_hash()};defines={','.join(defines.split())}"
+
+
+def build(force: bool = False, verbose: bool = False, out: Path | None = None, defines: str | None = None) -> Path:
+    # defines / F3D_B200_DEFINES="F3D_CULL_FAST=0 ..." builds a compile-time variant of the kernels (A/B runs; see
     # csrc/f3d_trace_fast.cuh and tests/test_traversal_emulation.py); unset = the validated default
-    defines = [f"-D{d}" for d in os.environ.get("F3D_B200_DEFINES", "").split()]
-    cmd = [_nvcc(), *NVCC_FLAGS, *defines, "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
+    if defines is None:
+        defines = os.environ.get("F3D_B200_DEFINES", "")
+    defines = " ".join(defines.split())
+    out = Path(out) if out else LIB
+    if not force and out == LIB and not needs_build(defines):
+        return LIB
+    info = f"src={source_hash()};defines={','.join(defines.split())}"
+    dflags = [f"-D{d}" for d in defines.split()] + [f'-DF3D_BUILD_INFO_STR="{info}"']
+    cmd = [_nvcc(), *NVCC_FLAGS, *dflags, "-o", str(out)] + [str(CSRC / s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -56,7 +87,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{res.stdout}")
     if verbose:
         print(res.stdout)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

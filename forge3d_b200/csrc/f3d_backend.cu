@@ -103,6 +103,15 @@ void cached_free(void* p, int device, bool allow_park) {
 
 extern "C" const char* f3d_last_error(void) { return g_err; }
 extern "C" int f3d_abi_version(void) { return F3D_ABI_VERSION; }
+// Identifies the build: content hash of the sources and the -D variant switches it was compiled with (forge3d_b200/build.py
+// compares it to decide whether the in-tree library is the default build of the current sources; bench.py prints it).
+#ifndef F3D_BUILD_INFO_STR
+#define F3D_BUILD_INFO_STR "src=unknown;defines="
+#endif
+extern "C" const char* f3d_build_info(void) {
+    static const char tagged[] = "F3D_BUILD_INFO:" F3D_BUILD_INFO_STR;
+    return tagged + 15;
+}
 extern "C" int f3d_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -491,6 +500,7 @@ static void fill_fast_scene(FastScene* F, const SceneParams& S, const DeviceTerr
     }
     F->root_mm = T.root_mm;
     F->inv_two_r_prime = S.inv_two_r_prime;
+    fast_scene_finish(*F);
 }
 
 constexpr uint32_t kLbvhMinTris = 4096u;
@@ -692,14 +702,15 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     fill_fast_scene(&P.fast, S, s->terrain);
     P.stack_depth = stack_depth_for(s->terrain.nlevels);
     s->smem_bytes = stack_smem_bytes(P.stack_depth, kThreads);
-    s->trace_smem_bytes = stack_smem_bytes(P.stack_depth, kTraceCtaThreads);
+    s->trace_smem_bytes = trace_smem_bytes_for(P.stack_depth, kTraceCtaThreads);
     if ((rc = allow_smem(k_primary, s->smem_bytes))) return rc;
     if ((rc = allow_smem(k_gbuffer, s->smem_bytes))) return rc;
-    if ((rc = allow_smem(k_trace<true>, s->trace_smem_bytes))) return rc;
-    if ((rc = allow_smem(k_trace<false>, s->trace_smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<true, false>, s->trace_smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<true, true>, s->trace_smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<false, false>, s->trace_smem_bytes))) return rc;
     {   // persistent grid: every SM filled to the occupancy the traversal kernel reaches
         int per_sm = 0, sms = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, kTraceCtaThreads, s->trace_smem_bytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false>, kTraceCtaThreads, s->trace_smem_bytes));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
         if (const char* e = getenv("F3D_B200_TRACE_CTAS")) per_sm = std::min(std::max(atoi(e), 1), std::max(per_sm, 1));
         s->trace_grid = std::max(per_sm, 1) * std::max(sms, 1);
@@ -902,10 +913,13 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
                 CUDA_TRY(cudaEventRecord(sl.primary_done, s->stream));
                 CUDA_TRY(cudaStreamWaitEvent(ts, sl.primary_done, 0));
             }
-            if (P.scene.curvature_enabled)
-                k_trace<true><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+            // curved sun rays that descend (sun below the horizon) keep the exact expansion: see F3D_CULL_FAST
+            if (P.scene.curvature_enabled && !(P.light_dir[1] >= 0.0f))
+                k_trace<true, true><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+            else if (P.scene.curvature_enabled)
+                k_trace<true, false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
             else
-                k_trace<false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+                k_trace<false, false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
             if (pipelined && prev.used) CUDA_TRY(cudaStreamWaitEvent(ts, prev.accum_done, 0));     // accumulate in frame order
             k_accum<<<s->grid, kThreads, 0, ts>>>(P);
             if (pipelined) { CUDA_TRY(cudaEventRecord(sl.accum_done, ts)); sl.used = true; }

@@ -244,6 +244,10 @@ constexpr int kThreads = kTileW * kTileH;
 __host__ __device__ inline size_t stack_smem_bytes(uint32_t stack_depth, int threads) {
     return (size_t)stack_depth * threads * 4;
 }
+// k_trace adds one 64-entry leaf ring per warp behind the stacks (see F3D_TRACE_LEAF_QUEUE).
+__host__ __device__ inline size_t trace_smem_bytes_for(uint32_t stack_depth, int threads) {
+    return stack_smem_bytes(stack_depth, threads) + (size_t)(threads / 32) * 64 * 4;
+}
 
 // Per-pixel record written by k_primary (4 x float4, 128-bit accesses):
 //   rec[4*pix+0] = (shade_o.xyz, bits(flags))   shade_o = hit.point + n * 1e-3   (:526,:540)
@@ -531,8 +535,24 @@ __device__ unsigned long long g_sched_stats[8];
 #define F3D_SCHED_STAT(i, mask) do {} while (0)
 #endif
 
-template <bool IS_SUN, bool CURV>
-__device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack st) {
+// F3D_TRACE_LEAF_QUEUE = 1 (default; 0 = round-1 scheduling: a lane solves its own leaves, >= kLeafBatch lanes at a time).
+//   The patch solve is the one expensive step left (IEEE divisions, ~450 instructions) and under the round-1 scheduler it ran
+//   with ~8 of 32 lanes (ncu, profiles/r01_source_regions.txt).  Here leaves are WORK ITEMS of the warp: a lane that pops a
+//   leaf appends (lane, cell) to a 64-entry ring in shared memory and keeps expanding; once 32 items wait (or nobody can
+//   expand) all 32 lanes take one item each, fetch the owner's ray with shuffles and solve it, and the hits are OR-ed back
+//   to the owners.  Exact for the occlusion flag: it is an OR over a fixed set of leaf tests (see F3D_CULL_FAST (1)-(2));
+//   only the order of the tests and the lane that runs them change.  A lane keeps its ray until its last item has been
+//   served (my_last <= q_head), so an item always finds its owner's ray in the owner's registers.
+#ifndef F3D_TRACE_LEAF_QUEUE
+#define F3D_TRACE_LEAF_QUEUE 1
+#endif
+#ifndef F3D_LEAFQ_WAIT_DRAIN
+#define F3D_LEAFQ_WAIT_DRAIN 8      // serve a partial batch once this many lanes only wait for their leaves
+#endif
+constexpr uint32_t kLeafQ = 64u;    // ring entries per warp (power of two, >= 2 * 32 - 1)
+
+template <bool IS_SUN, bool CURV, bool EXACT_CULL>
+__device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack st, uint32_t* wq) {
     const uint32_t lane = threadIdx.x & 31u;
     const FastScene& F = P.fast;
     const uint32_t n = P.q_counts[IS_SUN ? 0 : 1];
@@ -543,12 +563,52 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
     const v3 wi_reuse = normalize3(wi);
     const bool has_mesh = P.scene.traversal_mode == 0u;
 
-    TraceState T;
-    T.sp = 0u;
+    TraceState T{};
     bool busy = false, mesh_occl = false;
     uint32_t pix = 0u;
     bool exhausted = false;
     uint32_t n_rays = 0, n_nodes = 0;
+#if F3D_TRACE_LEAF_QUEUE
+    uint32_t q_head = 0u, q_tail = 0u;      // absolute item counters, warp-uniform
+    uint32_t my_last = 0u;                  // 1 + sequence number of this lane's newest item
+    bool decided_hit = false;               // this lane's ray is already known to be occluded
+    // Serves the first `count` (<= 32) queued leaves, one per lane.  Called by all 32 lanes, converged.
+    auto serve = [&](uint32_t count) {
+        const bool have = lane < count;
+        const uint32_t item = have ? wq[(q_head + lane) & (kLeafQ - 1u)] : 0u;
+        const int owner = (int)(item >> 26);
+        const uint32_t dead = __ballot_sync(0xFFFFFFFFu, decided_hit);
+        TraceState L;                       // the owner's ray, fetched from its registers
+        L.o.x = __shfl_sync(0xFFFFFFFFu, T.o.x, owner); L.o.y = __shfl_sync(0xFFFFFFFFu, T.o.y, owner);
+        L.o.z = __shfl_sync(0xFFFFFFFFu, T.o.z, owner); L.d.x = __shfl_sync(0xFFFFFFFFu, T.d.x, owner);
+        L.d.y = __shfl_sync(0xFFFFFFFFu, T.d.y, owner); L.d.z = __shfl_sync(0xFFFFFFFFu, T.d.z, owner);
+        L.tmax = __shfl_sync(0xFFFFFFFFu, T.tmax, owner);
+        L.inv_x = __shfl_sync(0xFFFFFFFFu, T.inv_x, owner); L.inv_z = __shfl_sync(0xFFFFFFFFu, T.inv_z, owner);
+        L.hd2 = __shfl_sync(0xFFFFFFFFu, T.hd2, owner);
+        L.use_vertex = false; L.vertex = 0.0f; L.y_vertex = 0.0f;
+        if (CURV) {
+            L.vertex = __shfl_sync(0xFFFFFFFFu, T.vertex, owner); L.y_vertex = __shfl_sync(0xFFFFFFFFu, T.y_vertex, owner);
+            L.use_vertex = __shfl_sync(0xFFFFFFFFu, T.use_vertex ? 1 : 0, owner) != 0;
+        }
+        L.tmin = 1e-3f; L.best_t = L.tmax; L.hit = false; L.sp = 0u; L.stale_sp = 0u; L.best_cx = 0u; L.best_cz = 0u;
+        bool hit = false;
+        const bool run = have && !((dead >> owner) & 1u);
+        F3D_SCHED_STAT(2, run);
+        if (run) {
+            n_nodes++;
+            hit = leaf_node<true, CURV>(F, L, item & 0x03FFFFFFu);
+        }
+        uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit), mine = 0u;
+        while (hm != 0u) {                  // OR the hits back to their owners (hits are rare: ~1 per batch)
+            const int j = __ffs((int)hm) - 1;
+            mine |= 1u << __shfl_sync(0xFFFFFFFFu, owner, j);
+            hm &= hm - 1u;
+        }
+        if ((mine >> lane) & 1u) { decided_hit = true; T.sp = 0u; }
+        q_head += count;
+        __syncwarp();
+    };
+#endif
 #if F3D_TRACE_DEFER_LEAVES
     uint32_t pend[F3D_TRACE_DEFER_LEAVES];
     uint32_t npend = 0u;
@@ -595,7 +655,45 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
             if (exhausted) break;
             continue;
         }
-#if F3D_TRACE_DEFER_LEAVES
+#if F3D_TRACE_LEAF_QUEUE
+        // ---- traverse; leaves go through the warp's work queue (see F3D_TRACE_LEAF_QUEUE) ----
+        while (true) {
+            // (1) move leaf tops into the queue (an expansion leaves at most 4 of them on top)
+            while (true) {
+                const bool is_leaf = busy && T.sp > 0u && top_is_leaf(T, st);
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_leaf);
+                if (m == 0u) break;
+                if (is_leaf) {
+                    T.sp--;
+                    const uint32_t slot = q_tail + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                    wq[slot & (kLeafQ - 1u)] = (lane << 26) | (st.at(T.sp) & 0x03FFFFFFu);
+                    my_last = slot + 1u;
+                }
+                q_tail += (uint32_t)__popc(m);
+                __syncwarp();
+                if (q_tail - q_head >= 32u) serve(32u);
+            }
+            // (2) expand, or serve what is queued when nobody can expand / too many lanes only wait for leaves
+            const uint32_t m_exp = __ballot_sync(0xFFFFFFFFu, busy && T.sp > 0u);
+            const uint32_t m_wait = __ballot_sync(0xFFFFFFFFu, busy && T.sp == 0u && my_last > q_head);
+            if (q_tail != q_head && (m_exp == 0u || __popc(m_wait) >= F3D_LEAFQ_WAIT_DRAIN)) serve(q_tail - q_head);
+            const bool can_expand = busy && T.sp > 0u;        // after serve(): a hit empties the owner's stack
+            F3D_SCHED_STAT(0, can_expand);
+            if (can_expand) {
+                expand_node<true, CURV, EXACT_CULL>(F, T, st);
+                n_nodes++;
+            }
+            // (3) retire rays: stack empty and every queued leaf of this lane served
+            if (busy && T.sp == 0u && my_last <= q_head) {
+                occl[pix] = (decided_hit || mesh_occl) ? 1u : 0u;
+                busy = false;
+                decided_hit = false;
+            }
+            const uint32_t live = __ballot_sync(0xFFFFFFFFu, busy);
+            if (live == 0u) break;
+            if (!exhausted && __popc(live) < kRefillBelow) break;
+        }
+#elif F3D_TRACE_DEFER_LEAVES
         // ---- traverse with parked leaves (see F3D_TRACE_DEFER_LEAVES) ----
         while (true) {
             while (true) {
@@ -605,7 +703,7 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
                 const bool can_expand = busy && T.sp > 0u && !top_is_leaf(T, st);
                 F3D_SCHED_STAT(0, can_expand);
                 if (can_expand) {
-                    expand_top<true, CURV>(F, T, st);
+                    expand_node<true, CURV, EXACT_CULL>(F, T, st);
                     n_nodes++;
                     if (T.sp == 0u && npend == 0u) { occl[pix] = mesh_occl ? 1u : 0u; busy = false; }
                 }
@@ -642,7 +740,7 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
                 const bool can_expand = busy && !top_is_leaf(T, st);
                 F3D_SCHED_STAT(0, can_expand);
                 if (can_expand) {
-                    expand_top<true, CURV>(F, T, st);
+                    expand_node<true, CURV, EXACT_CULL>(F, T, st);
                     n_nodes++;
                     if (T.sp == 0u) { occl[pix] = mesh_occl ? 1u : 0u; busy = false; }
                 }
@@ -668,14 +766,17 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
 
 // One persistent launch walks the sun list, then the IBL list: a warp that runs out of sun rays moves
 // straight on to IBL rays, so there is no kernel-boundary tail between the two.
-template <bool CURV_SUN>
+// EXACT_SUN: the sun rays keep the round-1 exact expansion (curved AND descending: sun below the horizon, see F3D_CULL_FAST).
+template <bool CURV_SUN, bool EXACT_SUN = false>
 __global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemStack st;
     st.base = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
     st.stride = kTraceCtaThreads;
-    trace_list<true, CURV_SUN>(P, st);
-    trace_list<false, false>(P, st);
+    // per-warp leaf ring behind the stacks
+    uint32_t* wq = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)P.stack_depth * kTraceCtaThreads + (threadIdx.x >> 5) * kLeafQ;
+    trace_list<true, CURV_SUN, EXACT_SUN>(P, st, wq);
+    trace_list<false, false, false>(P, st, wq);
 }
 
 // ---------------------------------------------------------------------------------------------

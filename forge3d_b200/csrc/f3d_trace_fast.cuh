@@ -52,6 +52,32 @@
 #define F3D_PUSH_CLIP_FOLDED 1
 #endif
 
+// F3D_CULL_FAST = 1 (default; 0 restores the exact cull-at-push expansion of round 1): the hierarchy is walked with a CHEAP
+//   CONSERVATIVE test and only the leaves run the reference's arithmetic.  Why the outputs cannot change:
+//   (1) A leaf (level-0 node) is solved by the reference iff it is popped, and it is popped iff every ancestor passed its
+//       own pop tests.  Those tests are implied by the leaf's own: a child's clipped span lies inside its parent's
+//       EXACTLY in f32 (see F3D_PUSH_CLIP_FOLDED), a child's [min,max] lies inside its parent's, and the ray height
+//       o.y + t*d.y (+ t*t*hd2*k for an ascending curved ray) is a monotone f32 expression of t, so its range over the
+//       child's span lies inside its range over the parent's.  Hence: the set of leaves the reference solves is exactly the
+//       set of cells that pass their OWN span + band test (with the best_t current at that moment).
+//   (2) leaf_node() evaluates that own test and the patch solve with the reference's arithmetic (it recomputes the
+//       cell's slab span from the integer cell coordinates, as terrain_trace does at every pop).  Any traversal that
+//       visits a SUPERSET of those cells therefore reproduces an any-hit ray's flag (an OR over a fixed set).
+//   (3) A closest-hit ray also needs the leaves in the reference's order, because a hit shrinks best_t and best_t clips the
+//       span the next solve samples.  The reference pops children by ascending entry parameter.  The exact spans of the
+//       four children partition the parent's span, so the children with a non-degenerate span are strictly ordered along
+//       the ray: near, (at most one) side, far == the order given by the signs of the direction.  A child with an empty
+//       span is never solved; one with a single-point span samples the patch three times at the same t, gets a = b = 0
+//       and cannot produce a closest hit (leaf_intersect :196-204), so where it sits in the order is immaterial.
+//   The conservative test: plane parameters as ONE fma each, t(c) = fma(f32(c), sx*inv, (ox-o)*inv), widened by a per-ray
+//   bound on the difference to the reference's four-rounding chain (ex, ez below); ray heights as fma chains widened by a
+//   per-ray bound (ey).  Children that cannot exist hold the (+inf,-inf) sentinel and fail the band test by themselves.
+//   Curved rays that DESCEND (sun below the horizon, d.y < 0) are not monotone; the host keeps the round-1 expansion for
+//   them (f3d_backend.cu picks the kernel instance), so (1) never rests on the vertex term.
+#ifndef F3D_CULL_FAST
+#define F3D_CULL_FAST 1
+#endif
+
 namespace f3d {
 
 struct FastHit { float t; uint32_t cx, cz; bool hit; };
@@ -77,7 +103,19 @@ struct FastScene {
     QuadLevels q;
     float2 root_mm;
     float inv_two_r_prime;
+    // F3D_CULL_FAST: magnitudes that scale the per-ray padding (fast_scene_finish)
+    float mag_x, mag_z;      // |ox| + cell_w*sx, |oz| + cell_h*sz: bound on every plane coordinate
+    float mag_y;             // max(|root min|, |root max|)
 };
+
+// Fills the padding magnitudes from the fields above (host side; also used by the CPU emulation of this header).
+inline void fast_scene_finish(FastScene& F) {
+    F.mag_x = fabsf(F.ox) + (float)F.cell_w * F.sx;
+    F.mag_z = fabsf(F.oz) + (float)F.cell_h * F.sz;
+    const float a = fabsf(F.root_mm.x), b = fabsf(F.root_mm.y);
+    F.mag_y = (a > b ? a : b);
+    if (!(F.mag_y < 1e30f)) F.mag_y = 1e30f;     // flat (+inf,-inf) roots cannot occur (>= 1 cell), keep it finite anyway
+}
 
 // Per-ray traversal state.
 struct TraceState {
@@ -93,6 +131,11 @@ struct TraceState {
     bool hit;
     uint32_t sp;             // entries on the stack
     uint32_t stale_sp;       // closest-hit only: entries below this index predate the last hit
+#if F3D_CULL_FAST
+    // conservative culling (see F3D_CULL_FAST): t(c) = fma(f32(c), kx, bx) approximates the reference's plane parameter
+    // within ex; heights fma(t*t, kc, fma(t, d.y, o.y)) approximate ray_height within ey for |height| <= mag_y.
+    float kx, bx, kz, bz, ex, ez, ey, kc;
+#endif
 };
 
 template <bool CURV>
@@ -128,6 +171,24 @@ __device__ __forceinline__ void trace_begin(const FastScene& S, const Ray& r, Tr
     }
     T.best_t = r.tmax; T.best_cx = 0u; T.best_cz = 0u; T.hit = false;
     T.sp = 0u; T.stale_sp = 0u;
+#if F3D_CULL_FAST
+    {
+        // Reference chain per plane: fl(fl(fl(ox + fl(c*sx)) - o) * inv): four roundings; here one fma over two rounded
+        // constants.  With u = 2^-24 and M = |ox| + cell_w*sx the two differ by at most |inv| * u * (8 M + 5 |o|)
+        // (absolute terms 2uM + u|X-o| from the chain, u(3M + 2|o|) from kx/bx, 3u|t| with |t| <= |inv| (M + |o|));
+        // the pad below is 4x that.  The height pad covers both evaluations of a height of magnitude <= mag_y
+        // (relative error 3u each on |o.y| + |t d.y| + corr, with |t d.y| <= |y| + |o.y| + corr) with the same margin.
+        T.kx = S.sx * T.inv_x; T.bx = (S.ox - r.o.x) * T.inv_x;
+        T.kz = S.sz * T.inv_z; T.bz = (S.oz - r.o.z) * T.inv_z;
+        const float rx = S.mag_x + fabsf(r.o.x), rz = S.mag_z + fabsf(r.o.z);
+        T.ex = fabsf(T.inv_x) * rx * 1.9073486328125e-6f;      // 2^-19
+        T.ez = fabsf(T.inv_z) * rz * 1.9073486328125e-6f;
+        T.kc = CURV ? T.hd2 * S.inv_two_r_prime : 0.0f;
+        const float reach = 2.0f * (rx + rz);                  // bound on the horizontal distance travelled inside the DEM
+        const float corr_max = CURV ? fabsf(S.inv_two_r_prime) * reach * reach : 0.0f;
+        T.ey = (fabsf(r.o.y) + S.mag_y + corr_max) * 3.814697265625e-6f;   // 2^-18
+    }
+#endif
     const uint32_t level = S.mip_count - 1u;
     const uint32_t cx1 = min(1u << level, S.cell_w), cz1 = min(1u << level, S.cell_h);
     // ox + f32(0) * sx == ox exactly
@@ -257,6 +318,60 @@ __device__ __forceinline__ void expand_top(const FastScene& S, TraceState& T, co
     }
 }
 
+#if F3D_CULL_FAST
+// Conservative expansion (see F3D_CULL_FAST): pops the internal node on top of the stack and pushes, far child first, the
+// children that MAY pass the reference's pop tests.  ~3x fewer instructions than expand_top: 8 fma for the six planes,
+// no sort, no integer clamps (a far plane beyond the DEM only widens a span), children addressed in the order given by
+// the signs of the direction.  Precondition: sp > 0 and the top is not a leaf.
+template <bool ANY_HIT, bool CURV>
+__device__ __forceinline__ void expand_cull(const FastScene& S, TraceState& T, const SmemStack st) {
+    T.sp--;
+    const uint32_t node = st.at(T.sp);
+    const uint32_t level = node >> 26, ny = (node >> 13) & 0x1FFFu, nx = node & 0x1FFFu;
+    const uint32_t cl = level - 1u;
+    const float4* qp = reinterpret_cast<const float4*>(S.q.lv[cl] + ((size_t)ny * S.q.parent_pitch[cl] + nx) * 4u);
+    float4 q01 = __ldg(qp), q23 = __ldg(qp + 1);
+    // cell coordinates of the three planes per axis, exact in f32 (integers <= 2^14)
+    const float hs = __uint_as_float((127u + cl) << 23);                    // 2^cl
+    const float fx0 = (float)(nx << level), fz0 = (float)(ny << level);
+    const float fxm = fx0 + hs, fzm = fz0 + hs, fx1 = fxm + hs, fz1 = fzm + hs;
+    const float A0 = __fmaf_rn(fx0, T.kx, T.bx), Am = __fmaf_rn(fxm, T.kx, T.bx), A1 = __fmaf_rn(fx1, T.kx, T.bx);
+    const float B0 = __fmaf_rn(fz0, T.kz, T.bz), Bm = __fmaf_rn(fzm, T.kz, T.bz), B1 = __fmaf_rn(fz1, T.kz, T.bz);
+    // near / far side per axis, widened: child j (bit0: far in x, bit1: far in z) of the sign-mirrored node
+    const float xl0 = fminf(A0, A1) - T.ex, xh0 = Am + T.ex, xl1 = Am - T.ex, xh1 = fmaxf(A0, A1) + T.ex;
+    const float zl0 = fminf(B0, B1) - T.ez, zh0 = Bm + T.ez, zl1 = Bm - T.ez, zh1 = fmaxf(B0, B1) + T.ez;
+    const float tcap = fminf(T.tmax, T.best_t);
+    if (!ANY_HIT) {
+        if (fmaxf(xl0, zl0) > tcap) return;           // whole node beyond the closest hit found since it was pushed
+    }
+    // mirror the quad so that slot j holds the [min,max] of sign-ordered child j
+    const bool fx = T.inv_x < 0.0f, fz = T.inv_z < 0.0f;
+    if (fz) { const float4 t = q01; q01 = q23; q23 = t; }
+    if (fx) { q01 = make_float4(q01.z, q01.w, q01.x, q01.y); q23 = make_float4(q23.z, q23.w, q23.x, q23.y); }
+    bool ok[4];
+#pragma unroll
+    for (uint32_t j = 0; j < 4u; j++) {
+        const float tl = fmaxf(fmaxf((j & 1u) ? xl1 : xl0, (j & 2u) ? zl1 : zl0), T.tmin);
+        const float th = fminf(fminf((j & 1u) ? xh1 : xh0, (j & 2u) ? zh1 : zh0), tcap);
+        float y0 = __fmaf_rn(tl, T.d.y, T.o.y), y1 = __fmaf_rn(th, T.d.y, T.o.y);
+        if (CURV) { y0 = __fmaf_rn(tl * tl, T.kc, y0); y1 = __fmaf_rn(th * th, T.kc, y1); }
+        float lo = fminf(y0, y1) - T.ey;
+        const float hi = fmaxf(y0, y1) + T.ey;
+        if (CURV) {
+            if (T.use_vertex && T.vertex >= tl && T.vertex <= th) lo = fminf(lo, T.y_vertex - T.ey);
+        }
+        const float2 mm = j == 0u ? make_float2(q01.x, q01.y) : j == 1u ? make_float2(q01.z, q01.w)
+                        : j == 2u ? make_float2(q23.x, q23.y) : make_float2(q23.z, q23.w);
+        ok[j] = (tl <= th) & !(lo > mm.y || hi < mm.x);
+    }
+    const uint32_t bid = pack_node(cl, nx * 2u, ny * 2u) ^ ((fx ? 1u : 0u) | (fz ? (1u << 13) : 0u));
+    if (ok[3]) { st.at(T.sp) = bid ^ (1u | (1u << 13)); T.sp++; }
+    if (ok[2]) { st.at(T.sp) = bid ^ (1u << 13); T.sp++; }
+    if (ok[1]) { st.at(T.sp) = bid ^ 1u; T.sp++; }
+    if (ok[0]) { st.at(T.sp) = bid; T.sp++; }
+}
+#endif
+
 // Pops the leaf on top of the stack and runs the exact ray / bilinear-patch solve (:167-235).
 // Returns true when the ray is finished (any-hit rays stop at their first hit).
 template <bool ANY_HIT, bool CURV>
@@ -280,6 +395,13 @@ __device__ __forceinline__ bool leaf_node(const FastScene& S, TraceState& T, con
     const float b1 = ((S.oz + (float)min(cz + 1u, S.cell_h) * S.sz) - T.o.z) * T.inv_z;
     const float t_lo = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), T.tmin);
     const float t_hi = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(T.tmax, T.best_t));
+#if F3D_CULL_FAST
+    {   // the cell's own pop tests with the reference's arithmetic (:288-304): what decides whether it is solved
+        if (t_lo > t_hi) return false;
+        const float2 mm = make_float2(fminf(fminf(fminf(h.x, h.y), h.z), h.w), fmaxf(fmaxf(fmaxf(h.x, h.y), h.z), h.w));
+        if (!band_ok<CURV>(S, T, t_lo, t_hi, mm)) return false;
+    }
+#else
     if (!ANY_HIT) {
         if (T.sp < T.stale_sp) {
             T.stale_sp = T.sp;
@@ -288,6 +410,7 @@ __device__ __forceinline__ bool leaf_node(const FastScene& S, TraceState& T, con
             if (!band_ok<CURV>(S, T, t_lo, t_hi, mm)) return false;
         }
     }
+#endif
     const float tm = 0.5f * (t_lo + t_hi);
     float d3[3];
     const float fcx = (float)cx, fcz = (float)cz;
@@ -335,6 +458,15 @@ __device__ __forceinline__ bool leaf_node(const FastScene& S, TraceState& T, con
     return false;
 }
 
+// The expansion every caller uses.  EXACT_CULL = true keeps the round-1 expansion (required for descending curved rays).
+template <bool ANY_HIT, bool CURV, bool EXACT_CULL = false>
+__device__ __forceinline__ void expand_node(const FastScene& S, TraceState& T, const SmemStack st) {
+#if F3D_CULL_FAST
+    if (!EXACT_CULL) { expand_cull<ANY_HIT, CURV>(S, T, st); return; }
+#endif
+    expand_top<ANY_HIT, CURV>(S, T, st);
+}
+
 // Whole-ray traversal, warp-cooperative: must be called by all 32 lanes of a converged warp
 // (`valid` = this lane really has a ray).  Scheduling is a bounded while-while: lanes keep expanding
 // internal nodes until at least kLeafBatch lanes of the warp hold a leaf on top of their stacks (or
@@ -359,7 +491,12 @@ __device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, 
         while (true) {
             const bool can_expand = busy && !top_is_leaf(T, st);
             if (can_expand) {
-                expand_top<ANY_HIT, CURV>(S, T, st);
+                // curved rays: only ascending any-hit rays take the conservative expansion (see F3D_CULL_FAST); this
+                // per-lane choice exists for the KAT seam, the renderer's curved rays all share the sun's direction
+                if (CURV) {
+                    if (ANY_HIT && T.d.y >= 0.0f && T.tmin >= 0.0f) expand_node<ANY_HIT, CURV, false>(S, T, st);
+                    else expand_node<ANY_HIT, CURV, true>(S, T, st);
+                } else expand_node<ANY_HIT, CURV, false>(S, T, st);
                 nodes++;
                 if (T.sp == 0u) busy = false;
             }

@@ -120,6 +120,10 @@ int f3d_terrain_reference_render(const f3d_terrain_desc* desc, f3d_terrain_out* 
 const char* f3d_last_error(void);
 int f3d_abi_version(void);
 int f3d_device_count(void);
+/* "src=<content hash of the sources>;defines=<-D variant switches, comma separated>": which build this library is.
+ * No reference counterpart (the reference ships one wgpu pipeline); forge3d_b200/build.py and bench.py compare it so that
+ * an A/B variant build can never pass for the validated default. */
+const char* f3d_build_info(void);
 
 /* ---- session API: the same render split at the reference driver-loop's joints, so a host
  * (bench, multi-GPU launcher) can keep inputs resident and time the frame loop alone. ---- */

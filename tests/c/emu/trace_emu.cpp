@@ -78,6 +78,7 @@ void build(HostTerrain& T, const float* heights, uint32_t w, uint32_t h, const f
     for (uint32_t l = 0; l + 1u < mips; l++) { T.F.q.lv[l] = T.quads[l].data(); T.F.q.parent_pitch[l] = T.ppitch[l]; }
     T.F.root_mm = T.plain[mips - 1u][0];
     T.F.inv_two_r_prime = k;
+    fast_scene_finish(T.F);
 #ifdef F3D_EMU_FILL_EXTRA
     F3D_EMU_FILL_EXTRA(T.F)
 #endif

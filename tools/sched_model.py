@@ -24,7 +24,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-C_EXPAND, C_LEAF, C_REFILL, C_ITER_DEFER = 275.0, 220.0, 300.0, 14.0
+C_EXPAND, C_LEAF, C_REFILL, C_ITER_DEFER = 150.0, 330.0, 300.0, 14.0
 
 
 def main():
