@@ -554,6 +554,7 @@ struct f3d_session {
     size_t smem_bytes = 0;          // stack smem of the per-pixel kernels (kThreads)
     size_t trace_smem_bytes = 0;    // stack smem of k_trace (kTraceCtaThreads)
     int trace_grid = 0;             // persistent CTAs of k_trace
+    int ascent_grid = 0;            // grid-stride CTAs of k_ascent
     // Frame pipelining: k_primary(step+1) only depends on k_primary(step) (reservoir records) and on its
     // wavefront buffers being free; k_trace(step) only on k_primary(step); k_accum(step) on k_trace(step)
     // and k_accum(step-1).  The primary kernels run on the session stream, k_trace/k_accum of step i on
@@ -563,6 +564,7 @@ struct f3d_session {
         float4* rec = nullptr;
         uint8_t* occl_sun = nullptr; uint8_t* occl_ibl = nullptr;
         uint32_t* q_sun = nullptr; uint32_t* q_ibl = nullptr; uint32_t* q_counts = nullptr;
+        unsigned long long* qn_sun = nullptr; unsigned long long* qn_ibl = nullptr;
         cudaEvent_t primary_done = nullptr, accum_done = nullptr;
         cudaStream_t stream = nullptr;     // k_trace / k_accum of the steps that use this slot
         bool used = false;
@@ -607,6 +609,7 @@ static void session_free(f3d_session* s) {
         if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
         cached_free(sl.rec, dv); cached_free(sl.occl_sun, dv); cached_free(sl.occl_ibl, dv);
         cached_free(sl.q_sun, dv); cached_free(sl.q_ibl, dv); cached_free(sl.q_counts, dv);
+        cached_free(sl.qn_sun, dv); cached_free(sl.qn_ibl, dv);
         if (sl.primary_done) cudaEventDestroy(sl.primary_done);
         if (sl.accum_done) cudaEventDestroy(sl.accum_done);
     }
@@ -705,15 +708,17 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     s->trace_smem_bytes = trace_smem_bytes_for(P.stack_depth, kTraceCtaThreads);
     if ((rc = allow_smem(k_primary, s->smem_bytes))) return rc;
     if ((rc = allow_smem(k_gbuffer, s->smem_bytes))) return rc;
-    if ((rc = allow_smem(k_trace<true, false>, s->trace_smem_bytes))) return rc;
-    if ((rc = allow_smem(k_trace<true, true>, s->trace_smem_bytes))) return rc;
-    if ((rc = allow_smem(k_trace<false, false>, s->trace_smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<true, 1>, s->trace_smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<true, 2>, s->trace_smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<false, 1>, s->trace_smem_bytes))) return rc;
+    if ((rc = allow_smem(k_trace<false, 0>, s->trace_smem_bytes))) return rc;
     {   // persistent grid: every SM filled to the occupancy the traversal kernel reaches
         int per_sm = 0, sms = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false>, kTraceCtaThreads, s->trace_smem_bytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, 1>, kTraceCtaThreads, s->trace_smem_bytes));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
         if (const char* e = getenv("F3D_B200_TRACE_CTAS")) per_sm = std::min(std::max(atoi(e), 1), std::max(per_sm, 1));
         s->trace_grid = std::max(per_sm, 1) * std::max(sms, 1);
+        s->ascent_grid = 8 * std::max(sms, 1);
         if (getenv("F3D_B200_DEBUG"))
             fprintf(stderr, "[forge3d_b200] k_trace: %d CTAs/SM x %d SMs, %zu B smem/CTA, stack depth %u\n", per_sm, sms,
                     s->trace_smem_bytes, P.stack_depth);
@@ -813,6 +818,8 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
         if ((rc = dmalloc(s, &sl.q_sun, npx, false))) return rc;
         if ((rc = dmalloc(s, &sl.q_ibl, npx, false))) return rc;
         if ((rc = dmalloc(s, &sl.q_counts, (size_t)4, true))) return rc;
+        if ((rc = dmalloc(s, &sl.qn_sun, npx, false))) return rc;
+        if ((rc = dmalloc(s, &sl.qn_ibl, npx, false))) return rc;
         CUDA_TRY(cudaEventCreateWithFlags(&sl.primary_done, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&sl.accum_done, cudaEventDisableTiming));
         if (s->n_slots > 1) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
@@ -905,6 +912,7 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             f3d_session::Slot& sl = s->slots[s->steps % (uint64_t)s->n_slots];
             P.rec = sl.rec; P.occl_sun = sl.occl_sun; P.occl_ibl = sl.occl_ibl;
             P.q_sun = sl.q_sun; P.q_ibl = sl.q_ibl; P.q_counts = sl.q_counts;
+            P.qn_sun = sl.qn_sun; P.qn_ibl = sl.qn_ibl;
             cudaStream_t ts = pipelined ? sl.stream : s->stream;
             f3d_session::Slot& prev = s->slots[(s->steps + (uint64_t)s->n_slots - 1u) % (uint64_t)s->n_slots];
             if (pipelined && sl.used) CUDA_TRY(cudaStreamWaitEvent(s->stream, sl.accum_done, 0));   // buffer set free again
@@ -913,17 +921,21 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
                 CUDA_TRY(cudaEventRecord(sl.primary_done, s->stream));
                 CUDA_TRY(cudaStreamWaitEvent(ts, sl.primary_done, 0));
             }
-            // curved sun rays that descend (sun below the horizon) keep the exact expansion: see F3D_CULL_FAST
-            if (P.scene.curvature_enabled && !(P.light_dir[1] >= 0.0f))
-                k_trace<true, true><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
-            else if (P.scene.curvature_enabled)
-                k_trace<true, false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
-            else
-                k_trace<false, false><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+            // sun above the horizon: every sun ray ascends (monotone height tests); curved sun rays that descend keep the
+            // round-1 exact expansion (see F3D_CULL_FAST)
+            const bool curv = P.scene.curvature_enabled != 0u, asc = P.light_dir[1] >= 0.0f;
+            if (curv && asc) k_ascent<true, true><<<s->ascent_grid, 256, 0, ts>>>(P);
+            else if (curv) k_ascent<true, false><<<s->ascent_grid, 256, 0, ts>>>(P);
+            else if (asc) k_ascent<false, true><<<s->ascent_grid, 256, 0, ts>>>(P);
+            else k_ascent<false, false><<<s->ascent_grid, 256, 0, ts>>>(P);
+            if (curv && asc) k_trace<true, 1><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+            else if (curv) k_trace<true, 2><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+            else if (asc) k_trace<false, 1><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+            else k_trace<false, 0><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
             if (pipelined && prev.used) CUDA_TRY(cudaStreamWaitEvent(ts, prev.accum_done, 0));     // accumulate in frame order
             k_accum<<<s->grid, kThreads, 0, ts>>>(P);
             if (pipelined) { CUDA_TRY(cudaEventRecord(sl.accum_done, ts)); sl.used = true; }
-            s->launches += 3;
+            s->launches += 4;
             s->steps++;
         }
         s->frames++;

@@ -58,6 +58,8 @@ struct FrameParams {
     uint32_t* q_sun;           // compacted pixel indices that need a sun ray
     uint32_t* q_ibl;           // compacted pixel indices that need an IBL ray
     uint32_t* q_counts;        // [0] n_sun [1] n_ibl [2] next_sun [3] next_ibl
+    unsigned long long* qn_sun;   // per sun-list entry: seeds of the bottom-up start (ascent_seeds; k_ascent -> k_trace)
+    unsigned long long* qn_ibl;   // same for the IBL list
     float4* sstate;            // spp > 1 only: 3 x float4 per pixel (rng+cand, prev, partial radiance)
     // NVLink halo push: peer images of resv_out for the rank above / below (NULL = none)
     float4* peer_up;
@@ -244,9 +246,9 @@ constexpr int kThreads = kTileW * kTileH;
 __host__ __device__ inline size_t stack_smem_bytes(uint32_t stack_depth, int threads) {
     return (size_t)stack_depth * threads * 4;
 }
-// k_trace adds one 64-entry leaf ring per warp behind the stacks (see F3D_TRACE_LEAF_QUEUE).
+// k_trace adds one 256-entry leaf ring per warp behind the stacks (see F3D_TRACE_LEAF_QUEUE, kLeafQBU).
 __host__ __device__ inline size_t trace_smem_bytes_for(uint32_t stack_depth, int threads) {
-    return stack_smem_bytes(stack_depth, threads) + (size_t)(threads / 32) * 64 * 4;
+    return stack_smem_bytes(stack_depth, threads) + (size_t)(threads / 32) * 256 * 4;
 }
 
 // Per-pixel record written by k_primary (4 x float4, 128-bit accesses):
@@ -764,19 +766,265 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
     warp_add_counters(P.counters, 0u, IS_SUN ? n_rays : 0u, IS_SUN ? 0u : n_rays, n_nodes);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bottom-up tracer (see ascent_need in f3d_trace_fast.cuh and F3D_TRACE_LEAF_QUEUE above): the production path of k_trace.
+//   * a ray starts with the cell it begins in queued as a leaf and with the `need` mask k_ascent computed for it: its
+//     next node is the top of its stack, or - when the stack is empty - the parent named by the lowest set bit of `need`
+//     (expanded with the child that leads back to the ray's own cell masked out);
+//   * the stack holds INTERNAL nodes only: the children of a level-1 node go straight to the warp's leaf queue;
+//   * MODE_ASC: every ray of the list ascends (the sun list with the sun above the horizon): monotone height tests.
+// Exact for the occlusion flag: every cell that passes its own span + band test is solved (coverage: ascent_need),
+// with the reference's arithmetic (leaf_node), and the flag is the OR of those solves.
+// ---------------------------------------------------------------------------------------------
+#ifndef F3D_TRACE_BOTTOM_UP
+#define F3D_TRACE_BOTTOM_UP 1
+#endif
+constexpr uint32_t kLeafQBU = 256u;   // ring entries per warp: 31 waiting + 4 x 32 from one expansion step, power of two
+
+template <bool IS_SUN, bool CURV, bool ASC>
+__device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemStack st, uint32_t* wq) {
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const FastScene& F = P.fast;
+    const uint32_t n = P.q_counts[IS_SUN ? 0 : 1];
+    const uint32_t* __restrict__ queue = IS_SUN ? P.q_sun : P.q_ibl;
+    const unsigned long long* __restrict__ qseeds = IS_SUN ? P.qn_sun : P.qn_ibl;
+    uint32_t* next = P.q_counts + (IS_SUN ? 2 : 3);
+    uint8_t* __restrict__ occl = IS_SUN ? P.occl_sun : P.occl_ibl;
+    const v3 wi = normalize3(ld3(P.light_dir));
+    const v3 wi_reuse = normalize3(wi);
+    const bool has_mesh = P.scene.traversal_mode == 0u;
+
+    TraceState T{};
+    bool busy = false, mesh_occl = false, exhausted = false;
+    uint32_t pix = 0u, cell0 = 0u;
+    unsigned long long need = 0ull;      // seeds not yet expanded (bits >= 4: internal nodes)
+    uint32_t leaf_seeds = 0u;            // level-0 seeds of a ray that has just been fetched
+    uint32_t n_rays = 0, n_nodes = 0;
+    uint32_t q_head = 0u, q_tail = 0u;      // absolute item counters, warp-uniform
+    uint32_t my_last = 0u;                  // 1 + sequence number of this lane's newest item
+    bool decided_hit = false;               // this lane's ray is already known to be occluded
+
+    // Serves the first `count` (<= 32) queued leaves, one per lane.  Called by all 32 lanes, converged.
+    auto serve = [&](uint32_t count) {
+        const bool have = lane < count;
+        const uint32_t item = have ? wq[(q_head + lane) & (kLeafQBU - 1u)] : 0u;
+        const int owner = (int)(item >> 26);
+        const uint32_t dead = __ballot_sync(0xFFFFFFFFu, decided_hit);
+        TraceState L;                       // the owner's ray, fetched from its registers
+        L.o.x = __shfl_sync(0xFFFFFFFFu, T.o.x, owner); L.o.y = __shfl_sync(0xFFFFFFFFu, T.o.y, owner);
+        L.o.z = __shfl_sync(0xFFFFFFFFu, T.o.z, owner); L.d.x = __shfl_sync(0xFFFFFFFFu, T.d.x, owner);
+        L.d.y = __shfl_sync(0xFFFFFFFFu, T.d.y, owner); L.d.z = __shfl_sync(0xFFFFFFFFu, T.d.z, owner);
+        L.tmax = __shfl_sync(0xFFFFFFFFu, T.tmax, owner);
+        L.inv_x = __shfl_sync(0xFFFFFFFFu, T.inv_x, owner); L.inv_z = __shfl_sync(0xFFFFFFFFu, T.inv_z, owner);
+        L.hd2 = __shfl_sync(0xFFFFFFFFu, T.hd2, owner);
+        L.use_vertex = false; L.vertex = 0.0f; L.y_vertex = 0.0f;
+        if (CURV) {
+            L.vertex = __shfl_sync(0xFFFFFFFFu, T.vertex, owner); L.y_vertex = __shfl_sync(0xFFFFFFFFu, T.y_vertex, owner);
+            L.use_vertex = __shfl_sync(0xFFFFFFFFu, T.use_vertex ? 1 : 0, owner) != 0;
+        }
+        L.tmin = 1e-3f; L.best_t = L.tmax; L.hit = false; L.sp = 0u; L.stale_sp = 0u; L.best_cx = 0u; L.best_cz = 0u;
+        bool hit = false;
+        const bool run = have && !((dead >> owner) & 1u);
+        F3D_SCHED_STAT(2, run);
+        if (run) {
+            n_nodes++;
+            hit = leaf_node<true, CURV>(F, L, item & 0x03FFFFFFu);
+        }
+        uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit), mine = 0u;
+        while (hm != 0u) {                  // OR the hits back to their owners (hits are rare: ~1 per batch)
+            const int j = __ffs((int)hm) - 1;
+            mine |= 1u << __shfl_sync(0xFFFFFFFFu, owner, j);
+            hm &= hm - 1u;
+        }
+        if ((mine >> lane) & 1u) { decided_hit = true; T.sp = 0u; need = 0ull; }
+        q_head += count;
+        __syncwarp();
+    };
+    // Appends one leaf per lane of `m` (this lane's: `id`), then serves full batches.
+    auto enqueue = [&](uint32_t m, bool mine, uint32_t id) {
+        if (mine) {
+            const uint32_t slot = q_tail + (uint32_t)__popc(m & lt);
+            wq[slot & (kLeafQBU - 1u)] = (lane << 26) | (id & 0x03FFFFFFu);
+            my_last = slot + 1u;
+        }
+        q_tail += (uint32_t)__popc(m);
+    };
+
+    while (true) {
+        // ---- refill idle lanes ----
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !busy);
+        if (idle != 0u && !exhausted) {
+            const uint32_t n_idle = (uint32_t)__popc(idle);
+            uint32_t base = 0u;
+            if (lane == 0u) base = atomicAdd(next, n_idle);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base + n_idle >= n) exhausted = true;
+            F3D_SCHED_STAT(4, !busy && base + (uint32_t)__popc(idle & lt) < n);
+            bool started = false;
+            if (!busy) {
+                const uint32_t idx = base + (uint32_t)__popc(idle & lt);
+                if (idx < n) {
+                    pix = __ldg(queue + idx);
+                    need = __ldg(qseeds + idx);
+                    const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix);
+                    Ray r;
+                    r.o = V3(r0.x, r0.y, r0.z);
+                    r.tmin = 1e-3f;
+                    r.tmax = 1e30f;
+                    if (IS_SUN) r.d = (__float_as_uint(r0.w) & kRecSunReuseDir) ? wi_reuse : wi;
+                    else { const float4 r1 = __ldcg(P.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
+                    n_rays++;
+                    mesh_occl = false;
+                    bool decided = false;
+                    if (has_mesh) {                      // intersect_hybrid_optimized :213-221
+                        const Hit mh = intersect_mesh(P.scene, r);
+                        if (mh.hit && mh.t < 0.01f) { occl[pix] = 1u; decided = true; }
+                        else if (mh.hit && mh.t < r.tmax) { r.tmax = mh.t; mesh_occl = true; }
+                    }
+                    if (!decided) {
+                        ray_setup<CURV>(F, r, T);
+                        T.sp = 0u;
+                        cell0 = origin_cell(F, r.o);
+                        leaf_seeds = (uint32_t)need & 15u;
+                        need &= ~15ull;
+                        busy = true; started = true; decided_hit = false;
+                    }
+                }
+            }
+            // the cell each new ray starts in is its first leaf, then its level-0 seeds
+            const uint32_t ms = __ballot_sync(0xFFFFFFFFu, started);
+            if (ms != 0u) {
+                enqueue(ms, started, cell0);
+                const uint32_t sib0 = cell0 & ~(1u | (1u << 13));
+#pragma unroll
+                for (uint32_t r = 0; r < 4u; r++) {
+                    const bool mine = started && ((leaf_seeds >> r) & 1u);
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+                    if (m != 0u) enqueue(m, mine, sib0 | (r & 1u) | ((r >> 1) << 13));
+                }
+                __syncwarp();
+                while (q_tail - q_head >= 32u) serve(32u);
+            }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, busy) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        while (true) {
+            // (1) serve what is queued when nobody can expand, or when too many lanes only wait for their leaves
+            const uint32_t m_exp = __ballot_sync(0xFFFFFFFFu, busy && (T.sp > 0u || need != 0ull));
+            if (q_tail != q_head) {
+                const uint32_t m_wait = __ballot_sync(0xFFFFFFFFu, busy && T.sp == 0u && need == 0ull && my_last > q_head);
+                if (m_exp == 0u || __popc(m_wait) >= F3D_LEAFQ_WAIT_DRAIN) serve(q_tail - q_head);
+            }
+            // (2) expand the next node: top of the stack, else the next parent of the bottom-up start
+            const bool can_expand = busy && (T.sp > 0u || need != 0ull);      // after serve(): a hit clears both
+            F3D_SCHED_STAT(0, can_expand);
+            uint32_t okm = 0u, bid = 0u;
+            bool leaf_kids = false;
+            if (can_expand) {
+                uint32_t node;
+                if (T.sp > 0u) { T.sp--; node = st.at(T.sp); }
+                else {   // next seed: bit 4L + r = level-L child r of the ray's level-(L+1) ancestor
+                    const uint32_t b = (uint32_t)__ffsll((long long)need) - 1u;
+                    need &= need - 1ull;
+                    const uint32_t L = b >> 2, r = b & 3u;
+                    node = pack_node(L, (((cell0 & 0x1FFFu) >> (L + 1u)) << 1) | (r & 1u), (((cell0 >> 13) >> (L + 1u)) << 1) | (r >> 1));
+                }
+                okm = expand_core<true, CURV, ASC>(F, T, node, bid);
+                n_nodes++;
+                leaf_kids = ((bid >> 26) & 15u) == 0u;
+                if (!leaf_kids) {
+                    if (okm & 8u) { st.at(T.sp) = bid ^ (1u | (1u << 13)); T.sp++; }
+                    if (okm & 4u) { st.at(T.sp) = bid ^ (1u << 13); T.sp++; }
+                    if (okm & 2u) { st.at(T.sp) = bid ^ 1u; T.sp++; }
+                    if (okm & 1u) { st.at(T.sp) = bid; T.sp++; }
+                }
+            }
+            // (3) children of level-1 nodes are leaves: straight into the queue
+            if (__ballot_sync(0xFFFFFFFFu, leaf_kids && okm != 0u) != 0u) {
+#pragma unroll
+                for (uint32_t j = 0; j < 4u; j++) {
+                    const bool mine = leaf_kids && ((okm >> j) & 1u);
+                    enqueue(__ballot_sync(0xFFFFFFFFu, mine), mine, bid ^ (j & 1u) ^ ((j >> 1) << 13));
+                }
+                __syncwarp();
+                while (q_tail - q_head >= 32u) serve(32u);
+            }
+            // (4) retire rays: nothing left to expand and every queued leaf of this lane served
+            if (busy && T.sp == 0u && need == 0ull && my_last <= q_head) {
+                occl[pix] = (decided_hit || mesh_occl) ? 1u : 0u;
+                busy = false;
+                decided_hit = false;
+            }
+            const uint32_t live = __ballot_sync(0xFFFFFFFFu, busy);
+            if (live == 0u) break;
+            if (!exhausted && __popc(live) < kRefillBelow) break;
+        }
+    }
+    warp_add_counters(P.counters, 0u, IS_SUN ? n_rays : 0u, IS_SUN ? 0u : n_rays, n_nodes);
+}
+
+// k_ascent: one thread per listed ray, computes the `need` mask of the bottom-up start (ascent_need) for the sun list and
+// the IBL list.  Fully occupied lanes (the lists are compacted), 11 independent 8-byte loads per ray.
+template <bool CURV_SUN, bool ASC_SUN>
+__global__ void __launch_bounds__(256) k_ascent(const __grid_constant__ FrameParams P) {
+    const FastScene& F = P.fast;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    const v3 wi = normalize3(ld3(P.light_dir));
+    const v3 wi_reuse = normalize3(wi);
+    const uint32_t n_sun = P.q_counts[0], n_ibl = P.q_counts[1];
+    for (uint32_t i = gtid; i < n_sun; i += stride) {
+        const uint32_t pix = __ldg(P.q_sun + i);
+        const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix);
+        Ray r;
+        r.o = V3(r0.x, r0.y, r0.z); r.tmin = 1e-3f; r.tmax = 1e30f;
+        r.d = (__float_as_uint(r0.w) & kRecSunReuseDir) ? wi_reuse : wi;
+        TraceState T;
+        ray_setup<CURV_SUN>(F, r, T);
+        const unsigned long long nd = ascent_seeds<CURV_SUN, ASC_SUN>(F, T, origin_cell(F, r.o));
+        P.qn_sun[i] = nd;
+#ifdef F3D_SCHED_STATS
+        atomicAdd(&g_sched_stats[6], (unsigned long long)__popcll(nd) + (1ull << 32));      // low: seeds, high: rays
+#endif
+    }
+    for (uint32_t i = gtid; i < n_ibl; i += stride) {
+        const uint32_t pix = __ldg(P.q_ibl + i);
+        const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix), r1 = __ldcg(P.rec + 4 * (size_t)pix + 1);
+        Ray r;
+        r.o = V3(r0.x, r0.y, r0.z); r.tmin = 1e-3f; r.tmax = 1e30f;
+        r.d = V3(r1.x, r1.y, r1.z);
+        TraceState T;
+        ray_setup<false>(F, r, T);
+        const unsigned long long nd = ascent_seeds<false, false>(F, T, origin_cell(F, r.o));
+        P.qn_ibl[i] = nd;
+#ifdef F3D_SCHED_STATS
+        atomicAdd(&g_sched_stats[7], (unsigned long long)__popcll(nd) + (1ull << 32));
+#endif
+    }
+}
+
 // One persistent launch walks the sun list, then the IBL list: a warp that runs out of sun rays moves
 // straight on to IBL rays, so there is no kernel-boundary tail between the two.
-// EXACT_SUN: the sun rays keep the round-1 exact expansion (curved AND descending: sun below the horizon, see F3D_CULL_FAST).
-template <bool CURV_SUN, bool EXACT_SUN = false>
+// SUN_MODE: 0 = bottom-up, generic height tests; 1 = bottom-up, ascending sun rays (sun above the horizon);
+//           2 = round-1 top-down traversal with the exact expansion for the sun list (curved AND descending sun rays,
+//               see F3D_CULL_FAST; also what F3D_TRACE_BOTTOM_UP=0 builds use for both lists).
+template <bool CURV_SUN, int SUN_MODE>
 __global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(const __grid_constant__ FrameParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemStack st;
     st.base = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
     st.stride = kTraceCtaThreads;
     // per-warp leaf ring behind the stacks
-    uint32_t* wq = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)P.stack_depth * kTraceCtaThreads + (threadIdx.x >> 5) * kLeafQ;
-    trace_list<true, CURV_SUN, EXACT_SUN>(P, st, wq);
+    uint32_t* wq = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)P.stack_depth * kTraceCtaThreads + (threadIdx.x >> 5) * kLeafQBU;
+#if F3D_TRACE_BOTTOM_UP
+    if (SUN_MODE == 2) trace_list<true, CURV_SUN, true>(P, st, wq);
+    else trace_list_bu<true, CURV_SUN, SUN_MODE == 1>(P, st, wq);
+    trace_list_bu<false, false, false>(P, st, wq);
+#else
+    trace_list<true, CURV_SUN, SUN_MODE == 2>(P, st, wq);
     trace_list<false, false, false>(P, st, wq);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

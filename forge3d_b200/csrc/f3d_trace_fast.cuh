@@ -156,10 +156,31 @@ __device__ __forceinline__ bool band_ok(const FastScene& S, const TraceState& T,
     return !(lo > mm.y || hi < mm.x);
 }
 
+#if F3D_CULL_FAST
+// Per-ray constants of the conservative tests (see F3D_CULL_FAST).  Needs T.o, T.d, T.inv_x/z, T.hd2.
+// Reference chain per plane: fl(fl(fl(ox + fl(c*sx)) - o) * inv): four roundings; here one fma over two rounded
+// constants.  With u = 2^-24 and M = |ox| + cell_w*sx the two differ by at most |inv| * u * (8 M + 5 |o|)
+// (absolute terms 2uM + u|X-o| from the chain, u(3M + 2|o|) from kx/bx, 3u|t| with |t| <= |inv| (M + |o|));
+// the pad below is 4x that.  The height pad covers both evaluations of a height of magnitude <= mag_y
+// (relative error 3u each on |o.y| + |t d.y| + corr, with |t d.y| <= |y| + |o.y| + corr) with the same margin.
+template <bool CURV>
+__device__ __forceinline__ void cull_setup(const FastScene& S, TraceState& T) {
+    T.kx = S.sx * T.inv_x; T.bx = (S.ox - T.o.x) * T.inv_x;
+    T.kz = S.sz * T.inv_z; T.bz = (S.oz - T.o.z) * T.inv_z;
+    const float rx = S.mag_x + fabsf(T.o.x), rz = S.mag_z + fabsf(T.o.z);
+    T.ex = fabsf(T.inv_x) * rx * 1.9073486328125e-6f;      // 2^-19
+    T.ez = fabsf(T.inv_z) * rz * 1.9073486328125e-6f;
+    T.kc = CURV ? T.hd2 * S.inv_two_r_prime : 0.0f;
+    const float reach = 2.0f * (rx + rz);                  // bound on the horizontal distance travelled inside the DEM
+    const float corr_max = CURV ? fabsf(S.inv_two_r_prime) * reach * reach : 0.0f;
+    T.ey = (fabsf(T.o.y) + S.mag_y + corr_max) * 3.814697265625e-6f;   // 2^-18
+}
+#endif
+
 // Sets up a ray and performs the root's pop-time tests (:288-304); leaves the root on the stack if it
 // survives.
 template <bool CURV>
-__device__ __forceinline__ void trace_begin(const FastScene& S, const Ray& r, TraceState& T, const SmemStack st) {
+__device__ __forceinline__ void ray_setup(const FastScene& S, const Ray& r, TraceState& T) {
     T.o = r.o; T.d = r.d; T.tmin = r.tmin; T.tmax = r.tmax;
     T.inv_x = safe_inv(r.d.x); T.inv_z = safe_inv(r.d.z);
     T.hd2 = dot2(r.d.x, r.d.z, r.d.x, r.d.z);
@@ -172,23 +193,13 @@ __device__ __forceinline__ void trace_begin(const FastScene& S, const Ray& r, Tr
     T.best_t = r.tmax; T.best_cx = 0u; T.best_cz = 0u; T.hit = false;
     T.sp = 0u; T.stale_sp = 0u;
 #if F3D_CULL_FAST
-    {
-        // Reference chain per plane: fl(fl(fl(ox + fl(c*sx)) - o) * inv): four roundings; here one fma over two rounded
-        // constants.  With u = 2^-24 and M = |ox| + cell_w*sx the two differ by at most |inv| * u * (8 M + 5 |o|)
-        // (absolute terms 2uM + u|X-o| from the chain, u(3M + 2|o|) from kx/bx, 3u|t| with |t| <= |inv| (M + |o|));
-        // the pad below is 4x that.  The height pad covers both evaluations of a height of magnitude <= mag_y
-        // (relative error 3u each on |o.y| + |t d.y| + corr, with |t d.y| <= |y| + |o.y| + corr) with the same margin.
-        T.kx = S.sx * T.inv_x; T.bx = (S.ox - r.o.x) * T.inv_x;
-        T.kz = S.sz * T.inv_z; T.bz = (S.oz - r.o.z) * T.inv_z;
-        const float rx = S.mag_x + fabsf(r.o.x), rz = S.mag_z + fabsf(r.o.z);
-        T.ex = fabsf(T.inv_x) * rx * 1.9073486328125e-6f;      // 2^-19
-        T.ez = fabsf(T.inv_z) * rz * 1.9073486328125e-6f;
-        T.kc = CURV ? T.hd2 * S.inv_two_r_prime : 0.0f;
-        const float reach = 2.0f * (rx + rz);                  // bound on the horizontal distance travelled inside the DEM
-        const float corr_max = CURV ? fabsf(S.inv_two_r_prime) * reach * reach : 0.0f;
-        T.ey = (fabsf(r.o.y) + S.mag_y + corr_max) * 3.814697265625e-6f;   // 2^-18
-    }
+    cull_setup<CURV>(S, T);
 #endif
+}
+
+template <bool CURV>
+__device__ __forceinline__ void trace_begin(const FastScene& S, const Ray& r, TraceState& T, const SmemStack st) {
+    ray_setup<CURV>(S, r, T);
     const uint32_t level = S.mip_count - 1u;
     const uint32_t cx1 = min(1u << level, S.cell_w), cz1 = min(1u << level, S.cell_h);
     // ox + f32(0) * sx == ox exactly
@@ -319,56 +330,121 @@ __device__ __forceinline__ void expand_top(const FastScene& S, TraceState& T, co
 }
 
 #if F3D_CULL_FAST
-// Conservative expansion (see F3D_CULL_FAST): pops the internal node on top of the stack and pushes, far child first, the
-// children that MAY pass the reference's pop tests.  ~3x fewer instructions than expand_top: 8 fma for the six planes,
-// no sort, no integer clamps (a far plane beyond the DEM only widens a span), children addressed in the order given by
-// the signs of the direction.  Precondition: sp > 0 and the top is not a leaf.
-template <bool ANY_HIT, bool CURV>
-__device__ __forceinline__ void expand_cull(const FastScene& S, TraceState& T, const SmemStack st) {
-    T.sp--;
-    const uint32_t node = st.at(T.sp);
-    const uint32_t level = node >> 26, ny = (node >> 13) & 0x1FFFu, nx = node & 0x1FFFu;
+// Conservative test of the four children of an internal node (see F3D_CULL_FAST): ~3x fewer instructions than expand_top
+// (8 fma for the six planes, no sort, no integer clamps: a far plane beyond the DEM only widens a span).  Children are
+// numbered in the order given by the signs of the direction: bit0 = far half in x, bit1 = far half in z; child j is the
+// real child j ^ flip.  Returns the mask of children that MAY pass the reference's pop tests; `bid` receives the node id
+// of child 0 (the id of child j is bid ^ (j & 1) ^ ((j >> 1) << 13)).
+// ASC = the ray height is non-decreasing in t (d.y >= 0: an ascending ray, curved or not): the range over a span is
+// [y(t_lo), y(t_hi)], no min/max and no vertex term.
+template <bool ANY_HIT, bool CURV, bool ASC>
+__device__ __forceinline__ uint32_t expand_core(const FastScene& S, const TraceState& T, const uint32_t node, uint32_t& bid) {
+    const uint32_t level = (node >> 26) & 15u, ny = (node >> 13) & 0x1FFFu, nx = node & 0x1FFFu;
     const uint32_t cl = level - 1u;
-    const float4* qp = reinterpret_cast<const float4*>(S.q.lv[cl] + ((size_t)ny * S.q.parent_pitch[cl] + nx) * 4u);
-    float4 q01 = __ldg(qp), q23 = __ldg(qp + 1);
+    const bool fx = T.inv_x < 0.0f, fz = T.inv_z < 0.0f;
+    const uint32_t flip = (fx ? 1u : 0u) | (fz ? 2u : 0u);
+    // the children's [min,max]: four 8-byte loads from one 32-byte sector, already in sign order
+    const float2* qp = S.q.lv[cl] + (ny * S.q.parent_pitch[cl] + nx) * 4u;
+    const float2 m0 = __ldg(qp + flip), m1 = __ldg(qp + (flip ^ 1u)), m2 = __ldg(qp + (flip ^ 2u)), m3 = __ldg(qp + (flip ^ 3u));
     // cell coordinates of the three planes per axis, exact in f32 (integers <= 2^14)
     const float hs = __uint_as_float((127u + cl) << 23);                    // 2^cl
     const float fx0 = (float)(nx << level), fz0 = (float)(ny << level);
     const float fxm = fx0 + hs, fzm = fz0 + hs, fx1 = fxm + hs, fz1 = fzm + hs;
     const float A0 = __fmaf_rn(fx0, T.kx, T.bx), Am = __fmaf_rn(fxm, T.kx, T.bx), A1 = __fmaf_rn(fx1, T.kx, T.bx);
     const float B0 = __fmaf_rn(fz0, T.kz, T.bz), Bm = __fmaf_rn(fzm, T.kz, T.bz), B1 = __fmaf_rn(fz1, T.kz, T.bz);
-    // near / far side per axis, widened: child j (bit0: far in x, bit1: far in z) of the sign-mirrored node
+    // near / far half per axis, widened
     const float xl0 = fminf(A0, A1) - T.ex, xh0 = Am + T.ex, xl1 = Am - T.ex, xh1 = fmaxf(A0, A1) + T.ex;
     const float zl0 = fminf(B0, B1) - T.ez, zh0 = Bm + T.ez, zl1 = Bm - T.ez, zh1 = fmaxf(B0, B1) + T.ez;
     const float tcap = fminf(T.tmax, T.best_t);
+    bid = pack_node(cl, nx * 2u, ny * 2u) ^ ((fx ? 1u : 0u) | (fz ? (1u << 13) : 0u));
     if (!ANY_HIT) {
-        if (fmaxf(xl0, zl0) > tcap) return;           // whole node beyond the closest hit found since it was pushed
+        if (fmaxf(xl0, zl0) > tcap) return 0u;        // whole node beyond the closest hit found since it was pushed
     }
-    // mirror the quad so that slot j holds the [min,max] of sign-ordered child j
-    const bool fx = T.inv_x < 0.0f, fz = T.inv_z < 0.0f;
-    if (fz) { const float4 t = q01; q01 = q23; q23 = t; }
-    if (fx) { q01 = make_float4(q01.z, q01.w, q01.x, q01.y); q23 = make_float4(q23.z, q23.w, q23.x, q23.y); }
-    bool ok[4];
+    const float oy_lo = T.o.y - T.ey, oy_hi = T.o.y + T.ey;
+    uint32_t okm = 0u;
 #pragma unroll
     for (uint32_t j = 0; j < 4u; j++) {
         const float tl = fmaxf(fmaxf((j & 1u) ? xl1 : xl0, (j & 2u) ? zl1 : zl0), T.tmin);
         const float th = fminf(fminf((j & 1u) ? xh1 : xh0, (j & 2u) ? zh1 : zh0), tcap);
-        float y0 = __fmaf_rn(tl, T.d.y, T.o.y), y1 = __fmaf_rn(th, T.d.y, T.o.y);
-        if (CURV) { y0 = __fmaf_rn(tl * tl, T.kc, y0); y1 = __fmaf_rn(th * th, T.kc, y1); }
-        float lo = fminf(y0, y1) - T.ey;
-        const float hi = fmaxf(y0, y1) + T.ey;
-        if (CURV) {
-            if (T.use_vertex && T.vertex >= tl && T.vertex <= th) lo = fminf(lo, T.y_vertex - T.ey);
+        const float2 mm = j == 0u ? m0 : j == 1u ? m1 : j == 2u ? m2 : m3;
+        bool ok;
+        if (ASC) {
+            float lo = __fmaf_rn(tl, T.d.y, oy_lo), hi = __fmaf_rn(th, T.d.y, oy_hi);
+            if (CURV) { lo = __fmaf_rn(tl * tl, T.kc, lo); hi = __fmaf_rn(th * th, T.kc, hi); }
+            ok = (tl <= th) & !(lo > mm.y || hi < mm.x);
+        } else {
+            float y0 = __fmaf_rn(tl, T.d.y, T.o.y), y1 = __fmaf_rn(th, T.d.y, T.o.y);
+            if (CURV) { y0 = __fmaf_rn(tl * tl, T.kc, y0); y1 = __fmaf_rn(th * th, T.kc, y1); }
+            float lo = fminf(y0, y1) - T.ey;
+            const float hi = fmaxf(y0, y1) + T.ey;
+            if (CURV) {
+                if (T.use_vertex && T.vertex >= tl && T.vertex <= th) lo = fminf(lo, T.y_vertex - T.ey);
+            }
+            ok = (tl <= th) & !(lo > mm.y || hi < mm.x);
         }
-        const float2 mm = j == 0u ? make_float2(q01.x, q01.y) : j == 1u ? make_float2(q01.z, q01.w)
-                        : j == 2u ? make_float2(q23.x, q23.y) : make_float2(q23.z, q23.w);
-        ok[j] = (tl <= th) & !(lo > mm.y || hi < mm.x);
+        okm |= ok ? (1u << j) : 0u;
     }
-    const uint32_t bid = pack_node(cl, nx * 2u, ny * 2u) ^ ((fx ? 1u : 0u) | (fz ? (1u << 13) : 0u));
-    if (ok[3]) { st.at(T.sp) = bid ^ (1u | (1u << 13)); T.sp++; }
-    if (ok[2]) { st.at(T.sp) = bid ^ (1u << 13); T.sp++; }
-    if (ok[1]) { st.at(T.sp) = bid ^ 1u; T.sp++; }
-    if (ok[0]) { st.at(T.sp) = bid; T.sp++; }
+    return okm;
+}
+
+// Stack form: pops the internal node on top of the stack and pushes, far child first, the children that may pass.
+// Precondition: sp > 0 and the top is not a leaf.
+template <bool ANY_HIT, bool CURV>
+__device__ __forceinline__ void expand_cull(const FastScene& S, TraceState& T, const SmemStack st) {
+    T.sp--;
+    uint32_t bid;
+    const uint32_t okm = expand_core<ANY_HIT, CURV, false>(S, T, st.at(T.sp), bid);
+    if (okm & 8u) { st.at(T.sp) = bid ^ (1u | (1u << 13)); T.sp++; }
+    if (okm & 4u) { st.at(T.sp) = bid ^ (1u << 13); T.sp++; }
+    if (okm & 2u) { st.at(T.sp) = bid ^ 1u; T.sp++; }
+    if (okm & 1u) { st.at(T.sp) = bid; T.sp++; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bottom-up start for rays that begin ON the terrain (every sun / IBL ray).  A top-down descent spends one expansion per
+// level (11 for a 2048^2 DEM) just to reach the cell the ray starts in, inside the divergent traversal loop.  Instead, let
+// A_0 be a cell, A_1 .. A_top its ancestors.  The DEM is the disjoint union of A_0 and, for every level L < top, the three
+// siblings of A_L inside A_{L+1}.  ascent_seeds tests those siblings level by level with the conservative child test
+// (expand_core) - a fixed-trip loop with independent loads, run by k_ascent at full lane occupancy - and returns the
+// survivors as SEEDS: 4 bits per level, bit 4L + r = the level-L child r (real index: bit0 = x, bit1 = z) of A_{L+1}
+// may pass its pop tests.  The tracer solves A_0 and the level-0 seeds as leaves and runs its stack traversal from the
+// other seeds.  Coverage: every cell is A_0 or lies below exactly one sibling; a sibling is dropped only by the same
+// conservative test an expansion of A_{L+1} would apply, or because it lies BEHIND the ray: if the ray starts strictly
+// inside A_0's slabs (widened entry parameter < tmin; then also inside every A_L's, the near planes only move back), a
+// sibling in the half A_L's near plane cuts off ends where A_L begins, before tmin, and its clipped span is empty.
+// Any choice of A_0 is valid; if the ray does not start inside it, all three siblings of every level are tested.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t origin_cell(const FastScene& S, v3 o) {          // (cz << 13) | cx, clamped into the DEM
+    const float fx = floorf(fdiv(o.x - S.ox, S.sx)), fz = floorf(fdiv(o.z - S.oz, S.sz));
+    const uint32_t cx = fx > 0.0f ? min((uint32_t)fminf(fx, 16383.0f), S.cell_w - 1u) : 0u;    // NaN -> 0
+    const uint32_t cz = fz > 0.0f ? min((uint32_t)fminf(fz, 16383.0f), S.cell_h - 1u) : 0u;
+    return (cz << 13) | cx;
+}
+
+// Needs ray_setup() done on T (tmin/tmax as the tracer will use them, or looser).
+template <bool CURV, bool ASC>
+__device__ __forceinline__ unsigned long long ascent_seeds(const FastScene& S, const TraceState& T, const uint32_t cell0) {
+    const uint32_t cx0 = cell0 & 0x1FFFu, cz0 = cell0 >> 13;
+    const uint32_t top = S.mip_count - 1u;
+    const float fcx = (float)cx0, fcz = (float)cz0;
+    const float A0 = __fmaf_rn(fcx, T.kx, T.bx), A1 = __fmaf_rn(fcx + 1.0f, T.kx, T.bx);
+    const float B0 = __fmaf_rn(fcz, T.kz, T.bz), B1 = __fmaf_rn(fcz + 1.0f, T.kz, T.bz);
+    const bool inside = fmaxf(fminf(A0, A1) + T.ex, fminf(B0, B1) + T.ez) < T.tmin;
+    const uint32_t flip = (T.inv_x < 0.0f ? 1u : 0u) | (T.inv_z < 0.0f ? 2u : 0u);
+    unsigned long long seeds = 0ull;
+    for (uint32_t L = 0; L < top; L++) {
+        uint32_t bid;
+        uint32_t okm = expand_core<true, CURV, ASC>(S, T, pack_node(L + 1u, cx0 >> (L + 1u), cz0 >> (L + 1u)), bid);
+        const uint32_t j_own = ((((cz0 >> L) & 1u) << 1) | ((cx0 >> L) & 1u)) ^ flip;      // A_L among its parent's children, sign order
+        // siblings ahead of the ray: those that contain every "far" bit A_L has
+        const uint32_t ahead = j_own == 0u ? 0xEu : (j_own == 3u ? 0u : 0x8u);
+        okm &= inside ? ahead : ~(1u << j_own);
+        // sign order -> real child index (j ^ flip)
+        if (flip & 1u) okm = ((okm & 5u) << 1) | ((okm >> 1) & 5u);
+        if (flip & 2u) okm = ((okm & 3u) << 2) | (okm >> 2);
+        seeds |= (unsigned long long)okm << (4u * L);
+    }
+    return seeds;
 }
 #endif
 

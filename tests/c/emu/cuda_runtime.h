@@ -76,3 +76,5 @@ static inline void __syncwarp(uint32_t = 0xFFFFFFFFu) {}
 #endif
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }

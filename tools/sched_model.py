@@ -42,6 +42,9 @@ def main():
             out = (C.c_ulonglong * 8)()
             native.lib().f3d_debug_sched_stats(out, 1)
         es, el, ls, ll, rs, _ = list(out)[:6]
+        for name, v in (("sun", out[6]), ("ibl", out[7])):
+            if v >> 32:
+                print(f"    bottom-up start, {name} rays: {(v & 0xFFFFFFFF) / (v >> 32):.2f} seeds per ray ({v >> 32} rays)")
         if base is None:
             base = g["accum"].copy()
         exact = np.array_equal(g["accum"].view(np.uint32), base.view(np.uint32))
