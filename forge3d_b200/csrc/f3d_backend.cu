@@ -564,6 +564,7 @@ struct f3d_session {
         float4* rec = nullptr;
         uint8_t* occl_sun = nullptr; uint8_t* occl_ibl = nullptr;
         uint32_t* q_sun = nullptr; uint32_t* q_ibl = nullptr; uint32_t* q_counts = nullptr;
+        uint32_t* q2_sun = nullptr; uint32_t* q2_ibl = nullptr;
         unsigned long long* qn_sun = nullptr; unsigned long long* qn_ibl = nullptr;
         cudaEvent_t primary_done = nullptr, accum_done = nullptr;
         cudaStream_t stream = nullptr;     // k_trace / k_accum of the steps that use this slot
@@ -609,7 +610,7 @@ static void session_free(f3d_session* s) {
         if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
         cached_free(sl.rec, dv); cached_free(sl.occl_sun, dv); cached_free(sl.occl_ibl, dv);
         cached_free(sl.q_sun, dv); cached_free(sl.q_ibl, dv); cached_free(sl.q_counts, dv);
-        cached_free(sl.qn_sun, dv); cached_free(sl.qn_ibl, dv);
+        cached_free(sl.qn_sun, dv); cached_free(sl.qn_ibl, dv); cached_free(sl.q2_sun, dv); cached_free(sl.q2_ibl, dv);
         if (sl.primary_done) cudaEventDestroy(sl.primary_done);
         if (sl.accum_done) cudaEventDestroy(sl.accum_done);
     }
@@ -804,9 +805,9 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     CUDA_TRY(cudaMallocHost(&s->h_gate, 4 * sizeof(uint32_t)));
     s->host_visible_bytes += 4 * sizeof(uint32_t);
     {
-        // default: 4 steps in flight, fewer when the per-slot buffers (74 B/pixel) would exceed 6 GB in total
+        // default: 4 steps in flight, fewer when the per-slot buffers (98 B/pixel) would exceed 6 GB in total
         const char* e = getenv("F3D_B200_PIPELINE");
-        const int by_memory = (int)std::max<uint64_t>(1, (6ull << 30) / std::max<uint64_t>(1, (uint64_t)npx * 74));
+        const int by_memory = (int)std::max<uint64_t>(1, (6ull << 30) / std::max<uint64_t>(1, (uint64_t)npx * 98));
         s->n_slots = e ? std::min(std::max(atoi(e), 1), (int)f3d_session::kMaxSlots)
                        : std::min((int)f3d_session::kMaxSlots, by_memory);
     }
@@ -817,7 +818,9 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
         if ((rc = dmalloc(s, &sl.occl_ibl, npx, true))) return rc;
         if ((rc = dmalloc(s, &sl.q_sun, npx, false))) return rc;
         if ((rc = dmalloc(s, &sl.q_ibl, npx, false))) return rc;
-        if ((rc = dmalloc(s, &sl.q_counts, (size_t)4, true))) return rc;
+        if ((rc = dmalloc(s, &sl.q_counts, (size_t)8, true))) return rc;
+        if ((rc = dmalloc(s, &sl.q2_sun, npx, false))) return rc;
+        if ((rc = dmalloc(s, &sl.q2_ibl, npx, false))) return rc;
         if ((rc = dmalloc(s, &sl.qn_sun, npx, false))) return rc;
         if ((rc = dmalloc(s, &sl.qn_ibl, npx, false))) return rc;
         CUDA_TRY(cudaEventCreateWithFlags(&sl.primary_done, cudaEventDisableTiming));
@@ -912,7 +915,7 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             f3d_session::Slot& sl = s->slots[s->steps % (uint64_t)s->n_slots];
             P.rec = sl.rec; P.occl_sun = sl.occl_sun; P.occl_ibl = sl.occl_ibl;
             P.q_sun = sl.q_sun; P.q_ibl = sl.q_ibl; P.q_counts = sl.q_counts;
-            P.qn_sun = sl.qn_sun; P.qn_ibl = sl.qn_ibl;
+            P.qn_sun = sl.qn_sun; P.qn_ibl = sl.qn_ibl; P.q2_sun = sl.q2_sun; P.q2_ibl = sl.q2_ibl;
             cudaStream_t ts = pipelined ? sl.stream : s->stream;
             f3d_session::Slot& prev = s->slots[(s->steps + (uint64_t)s->n_slots - 1u) % (uint64_t)s->n_slots];
             if (pipelined && sl.used) CUDA_TRY(cudaStreamWaitEvent(s->stream, sl.accum_done, 0));   // buffer set free again
@@ -924,10 +927,13 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             // sun above the horizon: every sun ray ascends (monotone height tests); curved sun rays that descend keep the
             // round-1 exact expansion (see F3D_CULL_FAST)
             const bool curv = P.scene.curvature_enabled != 0u, asc = P.light_dir[1] >= 0.0f;
-            if (curv && asc) k_ascent<true, true><<<s->ascent_grid, 256, 0, ts>>>(P);
-            else if (curv) k_ascent<true, false><<<s->ascent_grid, 256, 0, ts>>>(P);
-            else if (asc) k_ascent<false, true><<<s->ascent_grid, 256, 0, ts>>>(P);
-            else k_ascent<false, false><<<s->ascent_grid, 256, 0, ts>>>(P);
+#if F3D_TRACE_BOTTOM_UP
+            if (curv && asc) k_ascent<true, 1><<<s->ascent_grid, 256, 0, ts>>>(P);
+            else if (curv) k_ascent<true, 2><<<s->ascent_grid, 256, 0, ts>>>(P);
+            else if (asc) k_ascent<false, 1><<<s->ascent_grid, 256, 0, ts>>>(P);
+            else k_ascent<false, 0><<<s->ascent_grid, 256, 0, ts>>>(P);
+            s->launches++;
+#endif
             if (curv && asc) k_trace<true, 1><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
             else if (curv) k_trace<true, 2><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
             else if (asc) k_trace<false, 1><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
@@ -935,7 +941,7 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             if (pipelined && prev.used) CUDA_TRY(cudaStreamWaitEvent(ts, prev.accum_done, 0));     // accumulate in frame order
             k_accum<<<s->grid, kThreads, 0, ts>>>(P);
             if (pipelined) { CUDA_TRY(cudaEventRecord(sl.accum_done, ts)); sl.used = true; }
-            s->launches += 4;
+            s->launches += 3;
             s->steps++;
         }
         s->frames++;

@@ -57,8 +57,10 @@ struct FrameParams {
     uint8_t* occl_ibl;         // per pixel: IBL ray occluded
     uint32_t* q_sun;           // compacted pixel indices that need a sun ray
     uint32_t* q_ibl;           // compacted pixel indices that need an IBL ray
-    uint32_t* q_counts;        // [0] n_sun [1] n_ibl [2] next_sun [3] next_ibl
-    unsigned long long* qn_sun;   // per sun-list entry: seeds of the bottom-up start (ascent_seeds; k_ascent -> k_trace)
+    uint32_t* q_counts;        // [0] n_sun [1] n_ibl [2] next_sun [3] next_ibl; stage 2: [4] n2_sun [5] n2_ibl [6] next2_sun [7] next2_ibl
+    uint32_t* q2_sun;          // stage-2 lists: rays k_ascent could not decide (pixel index; seeds in qn_*)
+    uint32_t* q2_ibl;
+    unsigned long long* qn_sun;   // per stage-2 sun entry: seeds of the bottom-up start (ascent_seeds; k_ascent -> k_trace)
     unsigned long long* qn_ibl;   // same for the IBL list
     float4* sstate;            // spp > 1 only: 3 x float4 per pixel (rng+cand, prev, partial radiance)
     // NVLink halo push: peer images of resv_out for the rank above / below (NULL = none)
@@ -785,10 +787,10 @@ template <bool IS_SUN, bool CURV, bool ASC>
 __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemStack st, uint32_t* wq) {
     const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     const FastScene& F = P.fast;
-    const uint32_t n = P.q_counts[IS_SUN ? 0 : 1];
-    const uint32_t* __restrict__ queue = IS_SUN ? P.q_sun : P.q_ibl;
+    const uint32_t n = P.q_counts[IS_SUN ? 4 : 5];
+    const uint32_t* __restrict__ queue = IS_SUN ? P.q2_sun : P.q2_ibl;
     const unsigned long long* __restrict__ qseeds = IS_SUN ? P.qn_sun : P.qn_ibl;
-    uint32_t* next = P.q_counts + (IS_SUN ? 2 : 3);
+    uint32_t* next = P.q_counts + (IS_SUN ? 6 : 7);
     uint8_t* __restrict__ occl = IS_SUN ? P.occl_sun : P.occl_ibl;
     const v3 wi = normalize3(ld3(P.light_dir));
     const v3 wi_reuse = normalize3(wi);
@@ -873,15 +875,12 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
                     r.tmax = 1e30f;
                     if (IS_SUN) r.d = (__float_as_uint(r0.w) & kRecSunReuseDir) ? wi_reuse : wi;
                     else { const float4 r1 = __ldcg(P.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
-                    n_rays++;
                     mesh_occl = false;
-                    bool decided = false;
-                    if (has_mesh) {                      // intersect_hybrid_optimized :213-221
+                    if (has_mesh) {                      // intersect_hybrid_optimized :213-221, as k_ascent did (t < 0.01 was decided there)
                         const Hit mh = intersect_mesh(P.scene, r);
-                        if (mh.hit && mh.t < 0.01f) { occl[pix] = 1u; decided = true; }
-                        else if (mh.hit && mh.t < r.tmax) { r.tmax = mh.t; mesh_occl = true; }
+                        if (mh.hit && mh.t < r.tmax) { r.tmax = mh.t; mesh_occl = true; }
                     }
-                    if (!decided) {
+                    {
                         ray_setup<CURV>(F, r, T);
                         T.sp = 0u;
                         cell0 = origin_cell(F, r.o);
@@ -891,10 +890,9 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
                     }
                 }
             }
-            // the cell each new ray starts in is its first leaf, then its level-0 seeds
-            const uint32_t ms = __ballot_sync(0xFFFFFFFFu, started);
+            // the level-0 seeds of the new rays are leaves (the cell a ray starts in was solved by k_ascent)
+            const uint32_t ms = __ballot_sync(0xFFFFFFFFu, started && leaf_seeds != 0u);
             if (ms != 0u) {
-                enqueue(ms, started, cell0);
                 const uint32_t sib0 = cell0 & ~(1u | (1u << 13));
 #pragma unroll
                 for (uint32_t r = 0; r < 4u; r++) {
@@ -965,43 +963,79 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
     warp_add_counters(P.counters, 0u, IS_SUN ? n_rays : 0u, IS_SUN ? 0u : n_rays, n_nodes);
 }
 
-// k_ascent: one thread per listed ray, computes the `need` mask of the bottom-up start (ascent_need) for the sun list and
-// the IBL list.  Fully occupied lanes (the lists are compacted), 11 independent 8-byte loads per ray.
-template <bool CURV_SUN, bool ASC_SUN>
-__global__ void __launch_bounds__(256) k_ascent(const __grid_constant__ FrameParams P) {
+// k_ascent: stage 1 of the secondary rays, one thread per listed ray at full lane occupancy (the lists are compacted):
+// the mesh test (hybrid scenes), the patch solve of the cell the ray starts in - every ray needs exactly that one - and the
+// bottom-up start (ascent_seeds).  A ray whose own cell occludes it, or that has no seed left, is DECIDED here; the others
+// are appended (warp ballot + prefix sum, one atomic per warp) to the stage-2 lists k_trace traverses.
+template <bool IS_SUN, bool CURV, bool ASC>
+__device__ __forceinline__ void ascent_list(const FrameParams& P) {
     const FastScene& F = P.fast;
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const uint32_t n = P.q_counts[IS_SUN ? 0 : 1];
+    const uint32_t* __restrict__ queue = IS_SUN ? P.q_sun : P.q_ibl;
+    uint32_t* __restrict__ queue2 = IS_SUN ? P.q2_sun : P.q2_ibl;
+    unsigned long long* __restrict__ qseeds = IS_SUN ? P.qn_sun : P.qn_ibl;
+    uint8_t* __restrict__ occl = IS_SUN ? P.occl_sun : P.occl_ibl;
     const v3 wi = normalize3(ld3(P.light_dir));
     const v3 wi_reuse = normalize3(wi);
-    const uint32_t n_sun = P.q_counts[0], n_ibl = P.q_counts[1];
-    for (uint32_t i = gtid; i < n_sun; i += stride) {
-        const uint32_t pix = __ldg(P.q_sun + i);
-        const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix);
-        Ray r;
-        r.o = V3(r0.x, r0.y, r0.z); r.tmin = 1e-3f; r.tmax = 1e30f;
-        r.d = (__float_as_uint(r0.w) & kRecSunReuseDir) ? wi_reuse : wi;
-        TraceState T;
-        ray_setup<CURV_SUN>(F, r, T);
-        const unsigned long long nd = ascent_seeds<CURV_SUN, ASC_SUN>(F, T, origin_cell(F, r.o));
-        P.qn_sun[i] = nd;
+    const bool has_mesh = P.scene.traversal_mode == 0u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t n_rays = 0u, n_nodes = 0u;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {       // warp-uniform trip count
+        const uint32_t i = base + lane;
+        bool want = false;
+        uint32_t pix = 0u;
+        unsigned long long seeds = 0ull;
+        if (i < n) {
+            pix = __ldg(queue + i);
+            const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix);
+            Ray r;
+            r.o = V3(r0.x, r0.y, r0.z); r.tmin = 1e-3f; r.tmax = 1e30f;
+            if (IS_SUN) r.d = (__float_as_uint(r0.w) & kRecSunReuseDir) ? wi_reuse : wi;
+            else { const float4 r1 = __ldcg(P.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
+            n_rays++;
+            bool mesh_occl = false, decided = false;
+            if (has_mesh) {                      // intersect_hybrid_optimized :213-221
+                const Hit mh = intersect_mesh(P.scene, r);
+                if (mh.hit && mh.t < 0.01f) { occl[pix] = 1u; decided = true; }
+                else if (mh.hit && mh.t < r.tmax) { r.tmax = mh.t; mesh_occl = true; }
+            }
+            if (!decided) {
+                TraceState T;
+                ray_setup<CURV>(F, r, T);
+                const uint32_t cell0 = origin_cell(F, r.o);
+                n_nodes++;
+                if (leaf_node<true, CURV>(F, T, cell0)) occl[pix] = 1u;
+                else {
+                    seeds = ascent_seeds<CURV, ASC>(F, T, cell0);
+                    if (seeds == 0ull) occl[pix] = mesh_occl ? 1u : 0u;
+                    else want = true;
+                }
 #ifdef F3D_SCHED_STATS
-        atomicAdd(&g_sched_stats[6], (unsigned long long)__popcll(nd) + (1ull << 32));      // low: seeds, high: rays
+                atomicAdd(&g_sched_stats[IS_SUN ? 6 : 7], (unsigned long long)__popcll(seeds) + (1ull << 32));   // low: seeds, high: rays
 #endif
+            }
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+        if (m != 0u) {
+            uint32_t b2 = 0u;
+            if (lane == 0u) b2 = atomicAdd(P.q_counts + (IS_SUN ? 4 : 5), (uint32_t)__popc(m));
+            b2 = __shfl_sync(0xFFFFFFFFu, b2, 0);
+            if (want) {
+                const uint32_t slot = b2 + (uint32_t)__popc(m & lt);
+                queue2[slot] = pix;
+                qseeds[slot] = seeds;
+            }
+        }
     }
-    for (uint32_t i = gtid; i < n_ibl; i += stride) {
-        const uint32_t pix = __ldg(P.q_ibl + i);
-        const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix), r1 = __ldcg(P.rec + 4 * (size_t)pix + 1);
-        Ray r;
-        r.o = V3(r0.x, r0.y, r0.z); r.tmin = 1e-3f; r.tmax = 1e30f;
-        r.d = V3(r1.x, r1.y, r1.z);
-        TraceState T;
-        ray_setup<false>(F, r, T);
-        const unsigned long long nd = ascent_seeds<false, false>(F, T, origin_cell(F, r.o));
-        P.qn_ibl[i] = nd;
-#ifdef F3D_SCHED_STATS
-        atomicAdd(&g_sched_stats[7], (unsigned long long)__popcll(nd) + (1ull << 32));
-#endif
-    }
+    warp_add_counters(P.counters, 0u, IS_SUN ? n_rays : 0u, IS_SUN ? 0u : n_rays, n_nodes);
+}
+
+// SUN_MODE as for k_trace: 2 = the sun list is left to the top-down tracer.
+template <bool CURV_SUN, int SUN_MODE>
+__global__ void __launch_bounds__(256) k_ascent(const __grid_constant__ FrameParams P) {
+    if (SUN_MODE != 2) ascent_list<true, CURV_SUN, SUN_MODE == 1>(P);
+    ascent_list<false, false, false>(P);
 }
 
 // One persistent launch walks the sun list, then the IBL list: a warp that runs out of sun rays moves
@@ -1033,7 +1067,7 @@ __global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_accum(const __grid_constant__ FrameParams P) {
     uint32_t gx, gy;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4u) P.q_counts[threadIdx.x] = 0u;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 8u) P.q_counts[threadIdx.x] = 0u;
     if (!owned_pixel(P, gx, gy)) return;
     const uint32_t pix = gy * P.W + gx;
     const uint32_t spp = max(P.spp, 1u), s = P.sample_index;

@@ -421,28 +421,68 @@ __device__ __forceinline__ uint32_t origin_cell(const FastScene& S, v3 o) {     
     return (cz << 13) | cx;
 }
 
+// Conservative span + band test of one sibling (see expand_core; same widening).
+template <bool CURV, bool ASC>
+__device__ __forceinline__ bool sibling_may_pass(const TraceState& T, float tl, float th, float2 mm) {
+    if (ASC) {
+        float lo = __fmaf_rn(tl, T.d.y, T.o.y - T.ey), hi = __fmaf_rn(th, T.d.y, T.o.y + T.ey);
+        if (CURV) { lo = __fmaf_rn(tl * tl, T.kc, lo); hi = __fmaf_rn(th * th, T.kc, hi); }
+        return (tl <= th) & !(lo > mm.y || hi < mm.x);
+    }
+    float y0 = __fmaf_rn(tl, T.d.y, T.o.y), y1 = __fmaf_rn(th, T.d.y, T.o.y);
+    if (CURV) { y0 = __fmaf_rn(tl * tl, T.kc, y0); y1 = __fmaf_rn(th * th, T.kc, y1); }
+    float lo = fminf(y0, y1) - T.ey;
+    const float hi = fmaxf(y0, y1) + T.ey;
+    if (CURV) {
+        if (T.use_vertex && T.vertex >= tl && T.vertex <= th) lo = fminf(lo, T.y_vertex - T.ey);
+    }
+    return (tl <= th) & !(lo > mm.y || hi < mm.x);
+}
+
 // Needs ray_setup() done on T (tmin/tmax as the tracer will use them, or looser).
+// Going up one level adds ONE new plane per axis (A_{L+1} extends A_L on its low or its high side), and only an
+// extension on the side the ray travels to can be met: per level 2 fma for the new far planes, three 8-byte loads and up
+// to three sibling tests whose spans follow from the far planes alone:
+//   x-sibling  [far_x(L), min(far_x(L+1), far_z(L))]      (shares A_L's z-slab; entered through A_L's far x plane)
+//   z-sibling  [far_z(L), min(far_z(L+1), far_x(L))]
+//   diagonal   [max(far_x(L), far_z(L)), min(far_x(L+1), far_z(L+1))]
+// each bound widened by the per-axis pad, clipped to [tmin, min(tmax, best_t)].
 template <bool CURV, bool ASC>
 __device__ __forceinline__ unsigned long long ascent_seeds(const FastScene& S, const TraceState& T, const uint32_t cell0) {
     const uint32_t cx0 = cell0 & 0x1FFFu, cz0 = cell0 >> 13;
     const uint32_t top = S.mip_count - 1u;
-    const float fcx = (float)cx0, fcz = (float)cz0;
-    const float A0 = __fmaf_rn(fcx, T.kx, T.bx), A1 = __fmaf_rn(fcx + 1.0f, T.kx, T.bx);
-    const float B0 = __fmaf_rn(fcz, T.kz, T.bz), B1 = __fmaf_rn(fcz + 1.0f, T.kz, T.bz);
-    const bool inside = fmaxf(fminf(A0, A1) + T.ex, fminf(B0, B1) + T.ez) < T.tmin;
-    const uint32_t flip = (T.inv_x < 0.0f ? 1u : 0u) | (T.inv_z < 0.0f ? 2u : 0u);
+    const bool sgx = T.inv_x < 0.0f, sgz = T.inv_z < 0.0f;
+    float lox = (float)cx0, hix = lox + 1.0f, loz = (float)cz0, hiz = loz + 1.0f;       // A_L in cell units, exact in f32
+    const float txl = __fmaf_rn(lox, T.kx, T.bx), txh = __fmaf_rn(hix, T.kx, T.bx);
+    const float tzl = __fmaf_rn(loz, T.kz, T.bz), tzh = __fmaf_rn(hiz, T.kz, T.bz);
+    float fx = sgx ? txl : txh, fz = sgz ? tzl : tzh;                                   // far planes of A_L
+    const bool inside = fmaxf((sgx ? txh : txl) + T.ex, (sgz ? tzh : tzl) + T.ez) < T.tmin;
     unsigned long long seeds = 0ull;
+    if (!inside) {                                   // rare (origin within the pad of a cell border, or outside the DEM):
+        for (uint32_t L = 0; L < top; L++)           // every sibling of every level is a seed, nothing is skipped
+            seeds |= (unsigned long long)(15u & ~(1u << ((((cz0 >> L) & 1u) << 1) | ((cx0 >> L) & 1u)))) << (4u * L);
+        return seeds;
+    }
+    const float tcap = fminf(T.tmax, T.best_t);
+    float size = 1.0f;
     for (uint32_t L = 0; L < top; L++) {
-        uint32_t bid;
-        uint32_t okm = expand_core<true, CURV, ASC>(S, T, pack_node(L + 1u, cx0 >> (L + 1u), cz0 >> (L + 1u)), bid);
-        const uint32_t j_own = ((((cz0 >> L) & 1u) << 1) | ((cx0 >> L) & 1u)) ^ flip;      // A_L among its parent's children, sign order
-        // siblings ahead of the ray: those that contain every "far" bit A_L has
-        const uint32_t ahead = j_own == 0u ? 0xEu : (j_own == 3u ? 0u : 0x8u);
-        okm &= inside ? ahead : ~(1u << j_own);
-        // sign order -> real child index (j ^ flip)
-        if (flip & 1u) okm = ((okm & 5u) << 1) | ((okm >> 1) & 5u);
-        if (flip & 2u) okm = ((okm & 3u) << 2) | (okm >> 2);
-        seeds |= (unsigned long long)okm << (4u * L);
+        const uint32_t bx = (cx0 >> L) & 1u, bz = (cz0 >> L) & 1u, own = (bz << 1) | bx;
+        const float2* qp = S.q.lv[L] + ((cz0 >> (L + 1u)) * S.q.parent_pitch[L] + (cx0 >> (L + 1u))) * 4u;
+        const float2 mx = __ldg(qp + (own ^ 1u)), mz = __ldg(qp + (own ^ 2u)), md = __ldg(qp + (own ^ 3u));
+        // the new plane of A_{L+1} per axis; it is a FAR plane iff the extension is on the side the ray travels to
+        const float nx = bx ? lox - size : hix + size, nz = bz ? loz - size : hiz + size;
+        if (bx) lox = nx; else hix = nx;
+        if (bz) loz = nz; else hiz = nz;
+        const bool ax = (bx != 0u) == sgx, az = (bz != 0u) == sgz;
+        const float fx1 = ax ? __fmaf_rn(nx, T.kx, T.bx) : fx, fz1 = az ? __fmaf_rn(nz, T.kz, T.bz) : fz;
+        const float xl = fx - T.ex, zl = fz - T.ez, xh = fx + T.ex, zh = fz + T.ez, xh1 = fx1 + T.ex, zh1 = fz1 + T.ez;
+        const bool okx = ax && sibling_may_pass<CURV, ASC>(T, fmaxf(xl, T.tmin), fminf(fminf(xh1, zh), tcap), mx);
+        const bool okz = az && sibling_may_pass<CURV, ASC>(T, fmaxf(zl, T.tmin), fminf(fminf(zh1, xh), tcap), mz);
+        const bool okd = ax && az && sibling_may_pass<CURV, ASC>(T, fmaxf(fmaxf(xl, zl), T.tmin), fminf(fminf(xh1, zh1), tcap), md);
+        const uint32_t m = (okx ? (1u << (own ^ 1u)) : 0u) | (okz ? (1u << (own ^ 2u)) : 0u) | (okd ? (1u << (own ^ 3u)) : 0u);
+        seeds |= (unsigned long long)m << (4u * L);
+        fx = fx1; fz = fz1;
+        size = size + size;
     }
     return seeds;
 }
