@@ -248,9 +248,9 @@ constexpr int kThreads = kTileW * kTileH;
 __host__ __device__ inline size_t stack_smem_bytes(uint32_t stack_depth, int threads) {
     return (size_t)stack_depth * threads * 4;
 }
-// k_trace adds one 256-entry leaf ring per warp behind the stacks (see F3D_TRACE_LEAF_QUEUE, kLeafQBU).
+// k_trace adds one leaf ring per warp behind the stacks (see F3D_TRACE_LEAF_QUEUE, kLeafQBU x kLeafQFields words).
 __host__ __device__ inline size_t trace_smem_bytes_for(uint32_t stack_depth, int threads) {
-    return stack_smem_bytes(stack_depth, threads) + (size_t)(threads / 32) * 256 * 4;
+    return stack_smem_bytes(stack_depth, threads) + (size_t)(threads / 32) * (64 * 9) * 4;
 }
 
 // Per-pixel record written by k_primary (4 x float4, 128-bit accesses):
@@ -781,7 +781,11 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
 #ifndef F3D_TRACE_BOTTOM_UP
 #define F3D_TRACE_BOTTOM_UP 1
 #endif
-constexpr uint32_t kLeafQBU = 256u;   // ring entries per warp: 31 waiting + 4 x 32 from one expansion step, power of two
+// Leaf work items of a warp: a ring of kLeafQBU self-contained records in shared memory, structure of arrays
+// [field][slot]: cell id, pixel (bit 31: the sun ray uses the re-normalised direction), origin, tmax, and for IBL rays the
+// direction.  Self-contained, so the lane that found the leaf does not have to keep its ray until the leaf is solved.
+constexpr uint32_t kLeafQBU = 64u;        // 31 waiting + 32 from one enqueue round, power of two
+constexpr uint32_t kLeafQFields = 9u;
 
 template <bool IS_SUN, bool CURV, bool ASC>
 __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemStack st, uint32_t* wq) {
@@ -797,59 +801,59 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
     const bool has_mesh = P.scene.traversal_mode == 0u;
 
     TraceState T{};
-    bool busy = false, mesh_occl = false, exhausted = false;
-    uint32_t pix = 0u, cell0 = 0u;
-    unsigned long long need = 0ull;      // seeds not yet expanded (bits >= 4: internal nodes)
-    uint32_t leaf_seeds = 0u;            // level-0 seeds of a ray that has just been fetched
-    uint32_t n_rays = 0, n_nodes = 0;
+    bool busy = false, exhausted = false;
+    uint32_t pixw = 0u;                     // pixel | reuse-direction flag << 31
+    uint32_t n_nodes = 0;
     uint32_t q_head = 0u, q_tail = 0u;      // absolute item counters, warp-uniform
-    uint32_t my_last = 0u;                  // 1 + sequence number of this lane's newest item
-    bool decided_hit = false;               // this lane's ray is already known to be occluded
 
-    // Serves the first `count` (<= 32) queued leaves, one per lane.  Called by all 32 lanes, converged.
+    // Solves the first `count` (<= 32) queued leaves, one per lane; a hit marks the pixel occluded (k_ascent wrote the
+    // "not occluded" default) and stops the lane that still traverses that ray.  Called by all 32 lanes, converged.
     auto serve = [&](uint32_t count) {
-        const bool have = lane < count;
-        const uint32_t item = have ? wq[(q_head + lane) & (kLeafQBU - 1u)] : 0u;
-        const int owner = (int)(item >> 26);
-        const uint32_t dead = __ballot_sync(0xFFFFFFFFu, decided_hit);
-        TraceState L;                       // the owner's ray, fetched from its registers
-        L.o.x = __shfl_sync(0xFFFFFFFFu, T.o.x, owner); L.o.y = __shfl_sync(0xFFFFFFFFu, T.o.y, owner);
-        L.o.z = __shfl_sync(0xFFFFFFFFu, T.o.z, owner); L.d.x = __shfl_sync(0xFFFFFFFFu, T.d.x, owner);
-        L.d.y = __shfl_sync(0xFFFFFFFFu, T.d.y, owner); L.d.z = __shfl_sync(0xFFFFFFFFu, T.d.z, owner);
-        L.tmax = __shfl_sync(0xFFFFFFFFu, T.tmax, owner);
-        L.inv_x = __shfl_sync(0xFFFFFFFFu, T.inv_x, owner); L.inv_z = __shfl_sync(0xFFFFFFFFu, T.inv_z, owner);
-        L.hd2 = __shfl_sync(0xFFFFFFFFu, T.hd2, owner);
-        L.use_vertex = false; L.vertex = 0.0f; L.y_vertex = 0.0f;
-        if (CURV) {
-            L.vertex = __shfl_sync(0xFFFFFFFFu, T.vertex, owner); L.y_vertex = __shfl_sync(0xFFFFFFFFu, T.y_vertex, owner);
-            L.use_vertex = __shfl_sync(0xFFFFFFFFu, T.use_vertex ? 1 : 0, owner) != 0;
-        }
-        L.tmin = 1e-3f; L.best_t = L.tmax; L.hit = false; L.sp = 0u; L.stale_sp = 0u; L.best_cx = 0u; L.best_cz = 0u;
         bool hit = false;
-        const bool run = have && !((dead >> owner) & 1u);
-        F3D_SCHED_STAT(2, run);
-        if (run) {
+        uint32_t hpix = 0xFFFFFFFFu;
+        F3D_SCHED_STAT(2, lane < count);
+        if (lane < count) {
+            const uint32_t slot = (q_head + lane) & (kLeafQBU - 1u);
+            const uint32_t cell = wq[slot];
+            hpix = wq[kLeafQBU + slot];
+            Ray r;
+            r.o = V3(__uint_as_float(wq[2u * kLeafQBU + slot]), __uint_as_float(wq[3u * kLeafQBU + slot]), __uint_as_float(wq[4u * kLeafQBU + slot]));
+            r.tmin = 1e-3f;
+            r.tmax = __uint_as_float(wq[5u * kLeafQBU + slot]);
+            if (IS_SUN) r.d = (hpix >> 31) ? wi_reuse : wi;
+            else r.d = V3(__uint_as_float(wq[6u * kLeafQBU + slot]), __uint_as_float(wq[7u * kLeafQBU + slot]), __uint_as_float(wq[8u * kLeafQBU + slot]));
+            TraceState L;
+            leaf_ray_setup<CURV>(F, r, L);
             n_nodes++;
-            hit = leaf_node<true, CURV>(F, L, item & 0x03FFFFFFu);
+            hit = leaf_node<true, CURV>(F, L, cell);
+            if (hit) occl[hpix & 0x7FFFFFFFu] = 1u;
         }
-        uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit), mine = 0u;
-        while (hm != 0u) {                  // OR the hits back to their owners (hits are rare: ~1 per batch)
+        uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
+        while (hm != 0u) {                  // hits are rare (~1 per batch): tell the lane that still traverses that ray
             const int j = __ffs((int)hm) - 1;
-            mine |= 1u << __shfl_sync(0xFFFFFFFFu, owner, j);
+            const uint32_t hp = __shfl_sync(0xFFFFFFFFu, hpix, j);
+            if (busy && pixw == hp) { busy = false; T.sp = 0u; }
             hm &= hm - 1u;
         }
-        if ((mine >> lane) & 1u) { decided_hit = true; T.sp = 0u; need = 0ull; }
         q_head += count;
         __syncwarp();
     };
-    // Appends one leaf per lane of `m` (this lane's: `id`), then serves full batches.
+    // Appends one leaf per lane of `m` (this lane's cell: `id`), then solves full batches.
     auto enqueue = [&](uint32_t m, bool mine, uint32_t id) {
         if (mine) {
-            const uint32_t slot = q_tail + (uint32_t)__popc(m & lt);
-            wq[slot & (kLeafQBU - 1u)] = (lane << 26) | (id & 0x03FFFFFFu);
-            my_last = slot + 1u;
+            const uint32_t slot = (q_tail + (uint32_t)__popc(m & lt)) & (kLeafQBU - 1u);
+            wq[slot] = id & 0x03FFFFFFu;
+            wq[kLeafQBU + slot] = pixw;
+            wq[2u * kLeafQBU + slot] = __float_as_uint(T.o.x); wq[3u * kLeafQBU + slot] = __float_as_uint(T.o.y);
+            wq[4u * kLeafQBU + slot] = __float_as_uint(T.o.z); wq[5u * kLeafQBU + slot] = __float_as_uint(T.tmax);
+            if (!IS_SUN) {
+                wq[6u * kLeafQBU + slot] = __float_as_uint(T.d.x); wq[7u * kLeafQBU + slot] = __float_as_uint(T.d.y);
+                wq[8u * kLeafQBU + slot] = __float_as_uint(T.d.z);
+            }
         }
         q_tail += (uint32_t)__popc(m);
+        __syncwarp();
+        if (q_tail - q_head >= 32u) serve(32u);
     };
 
     while (true) {
@@ -862,74 +866,67 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if (base + n_idle >= n) exhausted = true;
             F3D_SCHED_STAT(4, !busy && base + (uint32_t)__popc(idle & lt) < n);
-            bool started = false;
+            uint32_t leaf_seeds = 0u, cell0 = 0u;
             if (!busy) {
                 const uint32_t idx = base + (uint32_t)__popc(idle & lt);
                 if (idx < n) {
-                    pix = __ldg(queue + idx);
-                    need = __ldg(qseeds + idx);
+                    const uint32_t pix = __ldg(queue + idx);
+                    unsigned long long seeds = __ldg(qseeds + idx);
                     const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix);
                     Ray r;
                     r.o = V3(r0.x, r0.y, r0.z);
                     r.tmin = 1e-3f;
                     r.tmax = 1e30f;
-                    if (IS_SUN) r.d = (__float_as_uint(r0.w) & kRecSunReuseDir) ? wi_reuse : wi;
-                    else { const float4 r1 = __ldcg(P.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
-                    mesh_occl = false;
+                    pixw = pix;
+                    if (IS_SUN) {
+                        const bool reuse = (__float_as_uint(r0.w) & kRecSunReuseDir) != 0u;
+                        r.d = reuse ? wi_reuse : wi;
+                        pixw |= reuse ? 0x80000000u : 0u;
+                    } else { const float4 r1 = __ldcg(P.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
                     if (has_mesh) {                      // intersect_hybrid_optimized :213-221, as k_ascent did (t < 0.01 was decided there)
                         const Hit mh = intersect_mesh(P.scene, r);
-                        if (mh.hit && mh.t < r.tmax) { r.tmax = mh.t; mesh_occl = true; }
+                        if (mh.hit && mh.t < r.tmax) r.tmax = mh.t;
                     }
-                    {
-                        ray_setup<CURV>(F, r, T);
-                        T.sp = 0u;
-                        cell0 = origin_cell(F, r.o);
-                        leaf_seeds = (uint32_t)need & 15u;
-                        need &= ~15ull;
-                        busy = true; started = true; decided_hit = false;
+                    ray_setup<CURV>(F, r, T);
+                    cell0 = origin_cell(F, r.o);
+                    leaf_seeds = (uint32_t)seeds & 15u;
+                    seeds >>= 4;
+                    // the other seeds are the roots of this ray's traversal: onto the stack, coarsest first
+                    T.sp = 0u;
+                    while (seeds != 0ull) {
+                        const uint32_t b = 63u - (uint32_t)__clzll((long long)seeds);
+                        seeds &= ~(1ull << b);
+                        const uint32_t L = (b >> 2) + 1u, q = b & 3u;
+                        st.at(T.sp) = pack_node(L, (((cell0 & 0x1FFFu) >> (L + 1u)) << 1) | (q & 1u), (((cell0 >> 13) >> (L + 1u)) << 1) | (q >> 1));
+                        T.sp++;
                     }
+                    busy = T.sp > 0u;
                 }
             }
             // the level-0 seeds of the new rays are leaves (the cell a ray starts in was solved by k_ascent)
-            const uint32_t ms = __ballot_sync(0xFFFFFFFFu, started && leaf_seeds != 0u);
-            if (ms != 0u) {
+            if (__ballot_sync(0xFFFFFFFFu, leaf_seeds != 0u) != 0u) {
                 const uint32_t sib0 = cell0 & ~(1u | (1u << 13));
 #pragma unroll
-                for (uint32_t r = 0; r < 4u; r++) {
-                    const bool mine = started && ((leaf_seeds >> r) & 1u);
+                for (uint32_t q = 0; q < 4u; q++) {
+                    const bool mine = ((leaf_seeds >> q) & 1u) != 0u;
                     const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
-                    if (m != 0u) enqueue(m, mine, sib0 | (r & 1u) | ((r >> 1) << 13));
+                    if (m != 0u) enqueue(m, mine, sib0 | (q & 1u) | ((q >> 1) << 13));
                 }
-                __syncwarp();
-                while (q_tail - q_head >= 32u) serve(32u);
             }
         }
         if (__ballot_sync(0xFFFFFFFFu, busy) == 0u) {
+            if (q_tail != q_head) serve(q_tail - q_head);
             if (exhausted) break;
             continue;
         }
         while (true) {
-            // (1) serve what is queued when nobody can expand, or when too many lanes only wait for their leaves
-            const uint32_t m_exp = __ballot_sync(0xFFFFFFFFu, busy && (T.sp > 0u || need != 0ull));
-            if (q_tail != q_head) {
-                const uint32_t m_wait = __ballot_sync(0xFFFFFFFFu, busy && T.sp == 0u && need == 0ull && my_last > q_head);
-                if (m_exp == 0u || __popc(m_wait) >= F3D_LEAFQ_WAIT_DRAIN) serve(q_tail - q_head);
-            }
-            // (2) expand the next node: top of the stack, else the next parent of the bottom-up start
-            const bool can_expand = busy && (T.sp > 0u || need != 0ull);      // after serve(): a hit clears both
-            F3D_SCHED_STAT(0, can_expand);
+            // expand the node on top of every busy lane's stack (the stack holds internal nodes only)
+            F3D_SCHED_STAT(0, busy);
             uint32_t okm = 0u, bid = 0u;
             bool leaf_kids = false;
-            if (can_expand) {
-                uint32_t node;
-                if (T.sp > 0u) { T.sp--; node = st.at(T.sp); }
-                else {   // next seed: bit 4L + r = level-L child r of the ray's level-(L+1) ancestor
-                    const uint32_t b = (uint32_t)__ffsll((long long)need) - 1u;
-                    need &= need - 1ull;
-                    const uint32_t L = b >> 2, r = b & 3u;
-                    node = pack_node(L, (((cell0 & 0x1FFFu) >> (L + 1u)) << 1) | (r & 1u), (((cell0 >> 13) >> (L + 1u)) << 1) | (r >> 1));
-                }
-                okm = expand_core<true, CURV, ASC>(F, T, node, bid);
+            if (busy) {
+                T.sp--;
+                okm = expand_core<true, CURV, ASC>(F, T, st.at(T.sp), bid);
                 n_nodes++;
                 leaf_kids = ((bid >> 26) & 15u) == 0u;
                 if (!leaf_kids) {
@@ -939,28 +936,22 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
                     if (okm & 1u) { st.at(T.sp) = bid; T.sp++; }
                 }
             }
-            // (3) children of level-1 nodes are leaves: straight into the queue
+            // children of level-1 nodes are leaves: straight into the queue
             if (__ballot_sync(0xFFFFFFFFu, leaf_kids && okm != 0u) != 0u) {
 #pragma unroll
                 for (uint32_t j = 0; j < 4u; j++) {
                     const bool mine = leaf_kids && ((okm >> j) & 1u);
-                    enqueue(__ballot_sync(0xFFFFFFFFu, mine), mine, bid ^ (j & 1u) ^ ((j >> 1) << 13));
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+                    if (m != 0u) enqueue(m, mine, bid ^ (j & 1u) ^ ((j >> 1) << 13));
                 }
-                __syncwarp();
-                while (q_tail - q_head >= 32u) serve(32u);
             }
-            // (4) retire rays: nothing left to expand and every queued leaf of this lane served
-            if (busy && T.sp == 0u && need == 0ull && my_last <= q_head) {
-                occl[pix] = (decided_hit || mesh_occl) ? 1u : 0u;
-                busy = false;
-                decided_hit = false;
-            }
+            if (busy && T.sp == 0u) busy = false;          // nothing left to expand: its leaves travel on their own
             const uint32_t live = __ballot_sync(0xFFFFFFFFu, busy);
             if (live == 0u) break;
             if (!exhausted && __popc(live) < kRefillBelow) break;
         }
     }
-    warp_add_counters(P.counters, 0u, IS_SUN ? n_rays : 0u, IS_SUN ? 0u : n_rays, n_nodes);
+    warp_add_counters(P.counters, 0u, 0u, 0u, n_nodes);
 }
 
 // k_ascent: stage 1 of the secondary rays, one thread per listed ray at full lane occupancy (the lists are compacted):
@@ -1008,8 +999,8 @@ __device__ __forceinline__ void ascent_list(const FrameParams& P) {
                 if (leaf_node<true, CURV>(F, T, cell0)) occl[pix] = 1u;
                 else {
                     seeds = ascent_seeds<CURV, ASC>(F, T, cell0);
-                    if (seeds == 0ull) occl[pix] = mesh_occl ? 1u : 0u;
-                    else want = true;
+                    occl[pix] = mesh_occl ? 1u : 0u;        // stage-2 rays: the default a later leaf hit overwrites
+                    want = seeds != 0ull;
                 }
 #ifdef F3D_SCHED_STATS
                 atomicAdd(&g_sched_stats[IS_SUN ? 6 : 7], (unsigned long long)__popcll(seeds) + (1ull << 32));   // low: seeds, high: rays
@@ -1050,7 +1041,7 @@ __global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(
     st.base = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
     st.stride = kTraceCtaThreads;
     // per-warp leaf ring behind the stacks
-    uint32_t* wq = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)P.stack_depth * kTraceCtaThreads + (threadIdx.x >> 5) * kLeafQBU;
+    uint32_t* wq = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)P.stack_depth * kTraceCtaThreads + (threadIdx.x >> 5) * (kLeafQBU * kLeafQFields);
 #if F3D_TRACE_BOTTOM_UP
     if (SUN_MODE == 2) trace_list<true, CURV_SUN, true>(P, st, wq);
     else trace_list_bu<true, CURV_SUN, SUN_MODE == 1>(P, st, wq);

@@ -197,6 +197,22 @@ __device__ __forceinline__ void ray_setup(const FastScene& S, const Ray& r, Trac
 #endif
 }
 
+// The part of ray_setup a patch solve reads (leaf_node): no culling constants.
+template <bool CURV>
+__device__ __forceinline__ void leaf_ray_setup(const FastScene& S, const Ray& r, TraceState& T) {
+    T.o = r.o; T.d = r.d; T.tmin = r.tmin; T.tmax = r.tmax;
+    T.inv_x = safe_inv(r.d.x); T.inv_z = safe_inv(r.d.z);
+    T.hd2 = dot2(r.d.x, r.d.z, r.d.x, r.d.z);
+    T.use_vertex = false; T.vertex = 0.0f; T.y_vertex = 0.0f;
+    if (CURV) {
+        const float a = T.hd2 * S.inv_two_r_prime;
+        T.use_vertex = a > 0.0f;
+        if (T.use_vertex) { T.vertex = fdiv(-r.d.y, 2.0f * a); T.y_vertex = ray_height<true>(S, T, T.vertex); }
+    }
+    T.best_t = r.tmax; T.best_cx = 0u; T.best_cz = 0u; T.hit = false;
+    T.sp = 0u; T.stale_sp = 0u;
+}
+
 template <bool CURV>
 __device__ __forceinline__ void trace_begin(const FastScene& S, const Ray& r, TraceState& T, const SmemStack st) {
     ray_setup<CURV>(S, r, T);
@@ -459,8 +475,13 @@ __device__ __forceinline__ unsigned long long ascent_seeds(const FastScene& S, c
     const bool inside = fmaxf((sgx ? txh : txl) + T.ex, (sgz ? tzh : tzl) + T.ez) < T.tmin;
     unsigned long long seeds = 0ull;
     if (!inside) {                                   // rare (origin within the pad of a cell border, or outside the DEM):
-        for (uint32_t L = 0; L < top; L++)           // every sibling of every level is a seed, nothing is skipped
-            seeds |= (unsigned long long)(15u & ~(1u << ((((cz0 >> L) & 1u) << 1) | ((cx0 >> L) & 1u)))) << (4u * L);
+        for (uint32_t L = 0; L < top; L++) {         // every sibling that EXISTS is a seed, nothing is tested
+            const uint32_t own = (((cz0 >> L) & 1u) << 1) | ((cx0 >> L) & 1u);
+            for (uint32_t r = 0; r < 4u; r++) {
+                const uint32_t gx = ((((cx0 >> (L + 1u)) << 1) | (r & 1u)) << L), gz = ((((cz0 >> (L + 1u)) << 1) | (r >> 1)) << L);
+                if (r != own && gx < S.cell_w && gz < S.cell_h) seeds |= 1ull << (4u * L + r);      // :336 gx0 >= cell_w: no such child
+            }
+        }
         return seeds;
     }
     const float tcap = fminf(T.tmax, T.best_t);

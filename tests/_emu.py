@@ -67,6 +67,30 @@ def trace_rays(heights, spacing, origin_xz, exaggeration, rays, *, any_hit, appl
     return hit.astype(bool), t, nrm, int(nodes.value)
 
 
+def trace_rays_bottom_up(heights, spacing, origin_xz, exaggeration, rays, *, apply_curvature, inv_two_r_prime=0.0,
+                         curvature_enabled=False, defines=()):
+    """Any-hit rays through the bottom-up start (k_ascent + k_trace's seed traversal, one lane); returns (hit, nodes)."""
+    L = C.CDLL(str(build(defines)))
+    fp = C.POINTER(C.c_float)
+    L.emu_trace_rays_bottom_up.argtypes = [fp, C.c_uint32, C.c_uint32, fp, fp, C.c_float, C.c_float, C.c_int32, fp, C.c_uint64,
+                                           C.c_int32, C.POINTER(C.c_uint8), fp, C.POINTER(C.c_uint64)]
+    dem = np.ascontiguousarray(heights, np.float32)
+    r = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    n = r.shape[0]
+    hit = np.zeros(n, np.uint8)
+    t = np.zeros(n, np.float32)
+    nodes = C.c_uint64()
+    f = lambda a: a.ctypes.data_as(fp)
+    sp = (C.c_float * 2)(*map(float, spacing))
+    og = (C.c_float * 2)(*map(float, origin_xz))
+    rc = L.emu_trace_rays_bottom_up(f(dem), dem.shape[1], dem.shape[0], sp, og, float(exaggeration), float(inv_two_r_prime),
+                                    int(bool(curvature_enabled)), f(r), n, int(bool(apply_curvature)),
+                                    hit.ctypes.data_as(C.POINTER(C.c_uint8)), f(t), C.byref(nodes))
+    if rc != 0:
+        raise RuntimeError(f"emu_trace_rays_bottom_up failed ({rc})")
+    return hit.astype(bool), int(nodes.value)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Whole backend under the SIMT interpreter: the product's host driver (f3d_backend.cu, launches rewritten by
 # tests/c/emu/gen_backend.py) and ALL its kernels compiled by g++; every CUDA thread is a fiber (tests/c/emu/simt.h).

@@ -64,6 +64,9 @@ static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 
+#ifndef EMU_SIMT
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
+#endif
 #ifdef EMU_SIMT
 #include "simt.h"          /* 32-lane warps and CTAs as fibers; defines the *_sync collectives and dim3 */
 #include "cuda_fake_runtime.h"

@@ -104,7 +104,74 @@ void run_fast(const HostTerrain& T, const float* rays, uint64_t n, uint8_t* hit,
     if (nodes_total) *nodes_total = total;
 }
 
+#if F3D_CULL_FAST
+// Bottom-up any-hit traversal exactly as k_ascent + k_trace run it (one lane): the ray's own cell, then the seeds of
+// ascent_seeds, level-0 seeds as leaves, the others through the stack with the conservative expansion.
+template <bool CURV>
+void run_bottom_up(const HostTerrain& T, const float* rays, uint64_t n, uint8_t* hit, float* t, uint64_t* nodes_total) {
+    uint32_t stack[kStackSize];
+    SmemStack st{stack, 1u};
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const float* r = rays + 8 * i;
+        Ray ray; ray.o = V3(r[0], r[1], r[2]); ray.tmin = r[3]; ray.d = V3(r[4], r[5], r[6]); ray.tmax = r[7];
+        TraceState S;
+        ray_setup<CURV>(T.F, ray, S);
+        const uint32_t cell0 = origin_cell(T.F, ray.o);
+        const bool asc = ray.d.y >= 0.0f && ray.tmin >= 0.0f;
+        bool h = leaf_node<true, CURV>(T.F, S, cell0);
+        total++;
+        if (!h) {
+            unsigned long long seeds = asc ? ascent_seeds<CURV, true>(T.F, S, cell0) : ascent_seeds<CURV, false>(T.F, S, cell0);
+            const uint32_t sib0 = cell0 & ~(1u | (1u << 13));
+            for (uint32_t q = 0; q < 4u && !h; q++)
+                if ((seeds >> q) & 1ull) { total++; h = leaf_node<true, CURV>(T.F, S, sib0 | (q & 1u) | ((q >> 1) << 13)); }
+            seeds &= ~15ull;
+            S.sp = 0u;
+            while (!h && (S.sp > 0u || seeds != 0ull)) {
+                uint32_t node;
+                if (S.sp > 0u) node = st.at(--S.sp);
+                else {
+                    const uint32_t b = (uint32_t)__ffsll((long long)seeds) - 1u;
+                    seeds &= seeds - 1ull;
+                    const uint32_t L = b >> 2, q = b & 3u;
+                    node = pack_node(L, (((cell0 & 0x1FFFu) >> (L + 1u)) << 1) | (q & 1u), (((cell0 >> 13) >> (L + 1u)) << 1) | (q >> 1));
+                }
+                uint32_t bid;
+                const uint32_t okm = asc ? expand_core<true, CURV, true>(T.F, S, node, bid) : expand_core<true, CURV, false>(T.F, S, node, bid);
+                total++;
+                if (((bid >> 26) & 15u) == 0u) {
+                    for (uint32_t j = 0; j < 4u && !h; j++)
+                        if ((okm >> j) & 1u) { total++; h = leaf_node<true, CURV>(T.F, S, bid ^ (j & 1u) ^ ((j >> 1) << 13)); }
+                } else {
+                    if (okm & 8u) st.at(S.sp++) = bid ^ (1u | (1u << 13));
+                    if (okm & 4u) st.at(S.sp++) = bid ^ (1u << 13);
+                    if (okm & 2u) st.at(S.sp++) = bid ^ 1u;
+                    if (okm & 1u) st.at(S.sp++) = bid;
+                }
+            }
+        }
+        hit[i] = h ? 1 : 0;
+        t[i] = S.best_t;
+    }
+    if (nodes_total) *nodes_total = total;
+}
+#endif
+
 }  // namespace
+
+#if F3D_CULL_FAST
+extern "C" int emu_trace_rays_bottom_up(const float* heights, uint32_t w, uint32_t h, const float spacing[2], const float origin[2],
+                                        float exaggeration, float inv_two_r_prime, int32_t curvature_enabled, const float* rays,
+                                        uint64_t n, int32_t apply_curvature, uint8_t* hit, float* t, uint64_t* nodes) {
+    if (w < 2u || h < 2u) return 1;
+    HostTerrain T;
+    build(T, heights, w, h, spacing, origin, exaggeration, inv_two_r_prime, curvature_enabled);
+    if (apply_curvature && curvature_enabled) run_bottom_up<true>(T, rays, n, hit, t, nodes);
+    else run_bottom_up<false>(T, rays, n, hit, t, nodes);
+    return 0;
+}
+#endif
 
 extern "C" int emu_trace_rays(const float* heights, uint32_t w, uint32_t h, const float spacing[2], const float origin[2],
                               float exaggeration, float inv_two_r_prime, int32_t curvature_enabled, const float* rays,

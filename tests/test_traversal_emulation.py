@@ -74,3 +74,54 @@ def test_emulated_production_traversal_on_random_rays_over_a_ragged_dem(variant)
         if not any_hit:
             assert np.array_equal(_bits(en)[eh], _bits(on)[oh])
         assert 0.05 < eh.mean() < 0.95
+
+
+def _surface_rays(dem, spacing, n, seed):
+    """Secondary rays as the renderer makes them: origins 1e-3 above random points of the surface (many of them in the border
+    cells, where a ray can start outside every cell's slab), directions = one low sun or a hemisphere sample."""
+    rng = np.random.default_rng(seed)
+    h, w = dem.shape
+    gx = rng.uniform(0, w - 1, n)
+    gz = rng.uniform(0, h - 1, n)
+    edge = rng.uniform(size=n) < 0.25
+    gx[edge] = np.where(rng.uniform(size=edge.sum()) < 0.5, rng.uniform(0, 1.5, edge.sum()), rng.uniform(w - 2.5, w - 1, edge.sum()))
+    gz[edge & (rng.uniform(size=n) < 0.5)] = rng.uniform(h - 2.2, h - 1, 1)[0]
+    on_plane = rng.uniform(size=n) < 0.15          # exactly on a cell border: the ray starts inside no cell's open slab
+    gx[on_plane] = np.round(gx[on_plane])
+    gz[on_plane & (rng.uniform(size=n) < 0.5)] = h - 1.0
+    ix, iz = np.minimum(gx.astype(int), w - 2), np.minimum(gz.astype(int), h - 2)
+    u, v = gx - ix, gz - iz
+    y = (dem[iz, ix] * (1 - u) + dem[iz, ix + 1] * u) * (1 - v) + (dem[iz + 1, ix] * (1 - u) + dem[iz + 1, ix + 1] * u) * v
+    rays = np.zeros((n, 8), np.float32)
+    ox = -0.5 * (w - 1) * spacing
+    oz = -0.5 * (h - 1) * spacing
+    rays[:, 0] = ox + gx * spacing
+    rays[:, 2] = oz + gz * spacing
+    rays[:, 1] = y + rng.choice([1e-3, 2e-3, -1e-3, 0.05], n)
+    rays[:, 3] = 1e-3
+    rays[:, 7] = np.where(rng.uniform(size=n) < 0.2, rng.uniform(20, 3000, n), 1e30)
+    return rays, (ox, oz)
+
+
+@pytest.mark.parametrize("curv", [True, False])
+def test_emulated_bottom_up_start_matches_the_oracle(curv):
+    """k_ascent + k_trace's seed traversal (csrc/f3d_trace_fast.cuh: ascent_seeds) as a one-lane warp: the occlusion flag of
+    every ray must equal the oracle's top-down terrain_trace, for ascending sun rays (monotone tests), descending ones and
+    hemisphere rays, on a ragged DEM whose border cells are over-sampled."""
+    rng = np.random.default_rng(21)
+    w, h = 333, 190
+    dem = (rng.standard_normal((h, w)).cumsum(0).cumsum(1) * 0.4 + rng.standard_normal((h, w)) * 3.0).astype(np.float32)
+    rays, origin = _surface_rays(dem, 10.0, 90_000, 22)
+    n = rays.shape[0]
+    d = rng.standard_normal((n, 3))
+    d[:, 1] = np.abs(d[:, 1]) * rng.choice([1.0, 1.0, -0.3], n)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    az, el = np.radians(302.0), np.radians(9.0)
+    d[: n // 3] = [np.cos(az) * np.cos(el), np.sin(el), np.sin(az) * np.cos(el)]
+    d[::29, 0] = 0.0
+    rays[:, 4:7] = d
+    kw = dict(apply_curvature=curv, inv_two_r_prime=2e-6, curvature_enabled=True)
+    bh, nodes = _emu.trace_rays_bottom_up(dem, (10.0, 10.0), origin, 1.0, rays, **kw)
+    oh, _, _ = oracle.trace_rays(dem, (10.0, 10.0), origin, 1.0, rays, any_hit=True, **kw)
+    assert np.array_equal(bh, oh), int((bh != oh).sum())
+    assert 0.1 < oh.mean() < 0.9 and nodes > n
