@@ -250,7 +250,7 @@ __host__ __device__ inline size_t stack_smem_bytes(uint32_t stack_depth, int thr
 }
 // k_trace adds one leaf ring per warp behind the stacks (see F3D_TRACE_LEAF_QUEUE, kLeafQBU x kLeafQFields words).
 __host__ __device__ inline size_t trace_smem_bytes_for(uint32_t stack_depth, int threads) {
-    return stack_smem_bytes(stack_depth, threads) + (size_t)(threads / 32) * (64 * 9) * 4;
+    return stack_smem_bytes(stack_depth, threads) + (size_t)(threads / 32) * (256 * 3) * 4;
 }
 
 // Per-pixel record written by k_primary (4 x float4, 128-bit accesses):
@@ -782,10 +782,30 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
 #define F3D_TRACE_BOTTOM_UP 1
 #endif
 // Leaf work items of a warp: a ring of kLeafQBU self-contained records in shared memory, structure of arrays
-// [field][slot]: cell id, pixel (bit 31: the sun ray uses the re-normalised direction), origin, tmax, and for IBL rays the
-// direction.  Self-contained, so the lane that found the leaf does not have to keep its ray until the leaf is solved.
-constexpr uint32_t kLeafQBU = 64u;        // 31 waiting + 32 from one enqueue round, power of two
-constexpr uint32_t kLeafQFields = 9u;
+// [field][slot]: cell id, pixel (bit 31: the sun ray uses the re-normalised direction), tmax.  The solving lane re-reads the
+// ray from the pixel's record (L1/L2 hits), so the lane that found the leaf does not have to keep its ray until then.
+constexpr uint32_t kLeafQBU = 256u;       // 31 waiting + 4 x 32 from one expansion step, power of two
+constexpr uint32_t kLeafQFields = 3u;
+
+// One patch solve of a queued leaf.  Not inlined: k_trace reaches it from several places and the solve (IEEE divisions and
+// their slow paths, ~600 SASS instructions) must exist once per list, or the kernel outgrows the instruction cache
+// (measured: 39 % of the stall samples were "no instruction" with the solve inlined at every site).
+template <bool IS_SUN, bool CURV>
+__device__ __noinline__ bool solve_leaf_item(const FrameParams& P, uint32_t cell, uint32_t pixw, float tmax) {
+    const uint32_t pix = pixw & 0x7FFFFFFFu;
+    const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix);
+    Ray r;
+    r.o = V3(r0.x, r0.y, r0.z);
+    r.tmin = 1e-3f;
+    r.tmax = tmax;
+    if (IS_SUN) {
+        const v3 wi = normalize3(ld3(P.light_dir));
+        r.d = (pixw >> 31) ? normalize3(wi) : wi;
+    } else { const float4 r1 = __ldcg(P.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
+    TraceState L;
+    leaf_ray_setup<CURV>(P.fast, r, L);
+    return leaf_node<true, CURV>(P.fast, L, cell);
+}
 
 template <bool IS_SUN, bool CURV, bool ASC>
 __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemStack st, uint32_t* wq) {
@@ -814,18 +834,9 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
         F3D_SCHED_STAT(2, lane < count);
         if (lane < count) {
             const uint32_t slot = (q_head + lane) & (kLeafQBU - 1u);
-            const uint32_t cell = wq[slot];
             hpix = wq[kLeafQBU + slot];
-            Ray r;
-            r.o = V3(__uint_as_float(wq[2u * kLeafQBU + slot]), __uint_as_float(wq[3u * kLeafQBU + slot]), __uint_as_float(wq[4u * kLeafQBU + slot]));
-            r.tmin = 1e-3f;
-            r.tmax = __uint_as_float(wq[5u * kLeafQBU + slot]);
-            if (IS_SUN) r.d = (hpix >> 31) ? wi_reuse : wi;
-            else r.d = V3(__uint_as_float(wq[6u * kLeafQBU + slot]), __uint_as_float(wq[7u * kLeafQBU + slot]), __uint_as_float(wq[8u * kLeafQBU + slot]));
-            TraceState L;
-            leaf_ray_setup<CURV>(F, r, L);
             n_nodes++;
-            hit = leaf_node<true, CURV>(F, L, cell);
+            hit = solve_leaf_item<IS_SUN, CURV>(P, wq[slot], hpix, __uint_as_float(wq[2u * kLeafQBU + slot]));
             if (hit) occl[hpix & 0x7FFFFFFFu] = 1u;
         }
         uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
@@ -838,22 +849,15 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
         q_head += count;
         __syncwarp();
     };
-    // Appends one leaf per lane of `m` (this lane's cell: `id`), then solves full batches.
+    // Appends one leaf per lane of `m` (this lane's cell: `id`).
     auto enqueue = [&](uint32_t m, bool mine, uint32_t id) {
         if (mine) {
             const uint32_t slot = (q_tail + (uint32_t)__popc(m & lt)) & (kLeafQBU - 1u);
             wq[slot] = id & 0x03FFFFFFu;
             wq[kLeafQBU + slot] = pixw;
-            wq[2u * kLeafQBU + slot] = __float_as_uint(T.o.x); wq[3u * kLeafQBU + slot] = __float_as_uint(T.o.y);
-            wq[4u * kLeafQBU + slot] = __float_as_uint(T.o.z); wq[5u * kLeafQBU + slot] = __float_as_uint(T.tmax);
-            if (!IS_SUN) {
-                wq[6u * kLeafQBU + slot] = __float_as_uint(T.d.x); wq[7u * kLeafQBU + slot] = __float_as_uint(T.d.y);
-                wq[8u * kLeafQBU + slot] = __float_as_uint(T.d.z);
-            }
+            wq[2u * kLeafQBU + slot] = __float_as_uint(T.tmax);
         }
         q_tail += (uint32_t)__popc(m);
-        __syncwarp();
-        if (q_tail - q_head >= 32u) serve(32u);
     };
 
     while (true) {
@@ -912,6 +916,7 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
                     const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
                     if (m != 0u) enqueue(m, mine, sib0 | (q & 1u) | ((q >> 1) << 13));
                 }
+                __syncwarp();
             }
         }
         if (__ballot_sync(0xFFFFFFFFu, busy) == 0u) {
@@ -944,7 +949,9 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
                     const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
                     if (m != 0u) enqueue(m, mine, bid ^ (j & 1u) ^ ((j >> 1) << 13));
                 }
+                __syncwarp();
             }
+            while (q_tail - q_head >= 32u) serve(32u);     // the one place full batches are solved
             if (busy && T.sp == 0u) busy = false;          // nothing left to expand: its leaves travel on their own
             const uint32_t live = __ballot_sync(0xFFFFFFFFu, busy);
             if (live == 0u) break;
