@@ -555,25 +555,22 @@ struct f3d_session {
     size_t trace_smem_bytes = 0;    // stack smem of k_trace (kTraceCtaThreads)
     int trace_grid = 0;             // persistent CTAs of k_trace
     int ascent_grid = 0;            // grid-stride CTAs of k_ascent
-    // Frame pipelining: k_primary(step+1) only depends on k_primary(step) (reservoir records) and on its
-    // wavefront buffers being free; k_trace(step) only on k_primary(step); k_accum(step) on k_trace(step)
-    // and k_accum(step-1).  The primary kernels run on the session stream, k_trace/k_accum of step i on
-    // the stream of buffer slot i % n_slots, so consecutive frames overlap and the tail of one kernel is
-    // filled by the next step's work instead of idling SMs.
-    struct Slot {
-        float4* rec = nullptr;
-        uint8_t* occl_sun = nullptr; uint8_t* occl_ibl = nullptr;
-        uint32_t* q_sun = nullptr; uint32_t* q_ibl = nullptr; uint32_t* q_counts = nullptr;
-        uint32_t* q2_sun = nullptr; uint32_t* q2_ibl = nullptr;
-        unsigned long long* qn_sun = nullptr; unsigned long long* qn_ibl = nullptr;
+    // Frame batching + pipelining.  k_primary(step+1) only depends on k_primary(step) (reservoir records); everything after it
+    // (k_ascent, k_trace, k_accum) depends on k_primary of the same step and on k_accum of the step before.  Steps are
+    // processed in BATCHES of up to `batch` steps: their primaries run back to back on the session stream, then ONE launch of
+    // k_ascent / k_trace / k_accum serves the whole batch on the batch set's own stream, so the primaries of the next batch
+    // overlap with it.  Two batch sets alternate.  On an image partition this is what keeps 148 SMs busy: a single step of a
+    // 1/8 1080p frame is ~230 k rays.
+    struct BatchSet {
+        BatchSlot slots[kMaxBatch] = {};
         cudaEvent_t primary_done = nullptr, accum_done = nullptr;
-        cudaStream_t stream = nullptr;     // k_trace / k_accum of the steps that use this slot
+        cudaStream_t stream = nullptr;     // k_ascent / k_trace / k_accum of the batches that use this set
         bool used = false;
     };
-    static constexpr int kMaxSlots = 4;
-    Slot slots[kMaxSlots];
-    int n_slots = 1;
-    uint64_t steps = 0;
+    static constexpr int kMaxSets = 2;
+    BatchSet sets[kMaxSets];
+    int n_sets = 1, batch = 1;
+    uint64_t steps = 0, batches = 0;
     cudaEvent_t join_ev = nullptr;
     float4* d_sstate = nullptr;
     // AETHER post (desc.atmosphere): payloads are copied at creation (the desc is borrowed for that call only) and
@@ -593,8 +590,8 @@ static void session_free(f3d_session* s) {
         if (s->peer_ptrs[i]) cudaIpcCloseMemHandle(s->peer_ptrs[i]);
     // nothing may still touch buffers that get parked (render_frames joins the slot streams into the session
     // stream, but an error return in the middle of it does not)
-    for (auto& sl : s->slots)
-        if (sl.stream) cudaStreamSynchronize(sl.stream);
+    for (auto& bs : s->sets)
+        if (bs.stream) cudaStreamSynchronize(bs.stream);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->d_sync) cudaFree(s->d_sync);
     const int dv = s->device;
@@ -606,13 +603,15 @@ static void session_free(f3d_session* s) {
     cached_free(s->d_resv[0], dv, !ipc); cached_free(s->d_resv[1], dv, !ipc);
     cached_free(s->d_pixflags, dv); cached_free(s->d_aov_normal, dv); cached_free(s->d_aov_depth, dv);
     cached_free(s->d_counters, dv); cached_free(s->d_gate, dv);
-    for (auto& sl : s->slots) {
-        if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
-        cached_free(sl.rec, dv); cached_free(sl.occl_sun, dv); cached_free(sl.occl_ibl, dv);
-        cached_free(sl.q_sun, dv); cached_free(sl.q_ibl, dv); cached_free(sl.q_counts, dv);
-        cached_free(sl.qn_sun, dv); cached_free(sl.qn_ibl, dv); cached_free(sl.q2_sun, dv); cached_free(sl.q2_ibl, dv);
-        if (sl.primary_done) cudaEventDestroy(sl.primary_done);
-        if (sl.accum_done) cudaEventDestroy(sl.accum_done);
+    for (auto& bs : s->sets) {
+        if (bs.stream) { cudaStreamSynchronize(bs.stream); cudaStreamDestroy(bs.stream); }
+        for (auto& sl : bs.slots) {
+            cached_free(sl.rec, dv); cached_free(sl.occl_sun, dv); cached_free(sl.occl_ibl, dv);
+            cached_free(sl.q_sun, dv); cached_free(sl.q_ibl, dv); cached_free(sl.q_counts, dv);
+            cached_free(sl.qn_sun, dv); cached_free(sl.qn_ibl, dv); cached_free(sl.q2_sun, dv); cached_free(sl.q2_ibl, dv);
+        }
+        if (bs.primary_done) cudaEventDestroy(bs.primary_done);
+        if (bs.accum_done) cudaEventDestroy(bs.accum_done);
     }
     if (s->join_ev) cudaEventDestroy(s->join_ev);
     cached_free(s->d_sstate, dv);
@@ -805,29 +804,35 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     CUDA_TRY(cudaMallocHost(&s->h_gate, 4 * sizeof(uint32_t)));
     s->host_visible_bytes += 4 * sizeof(uint32_t);
     {
-        // default: 4 steps in flight, fewer when the per-slot buffers (98 B/pixel) would exceed 6 GB in total
-        const char* e = getenv("F3D_B200_PIPELINE");
-        const int by_memory = (int)std::max<uint64_t>(1, (6ull << 30) / std::max<uint64_t>(1, (uint64_t)npx * 98));
-        s->n_slots = e ? std::min(std::max(atoi(e), 1), (int)f3d_session::kMaxSlots)
-                       : std::min((int)f3d_session::kMaxSlots, by_memory);
+        // default: two batch sets of 4 steps; smaller batches when the per-step buffers (98 B/pixel) would exceed 8 GB in total.
+        // F3D_B200_BATCH / F3D_B200_SETS override (F3D_B200_PIPELINE=1 is the old spelling of "no overlap": 1 set of 1).
+        const int by_memory = (int)std::max<uint64_t>(1, (8ull << 30) / std::max<uint64_t>(1, (uint64_t)npx * 98));
+        const char* eb = getenv("F3D_B200_BATCH");
+        const char* es = getenv("F3D_B200_SETS");
+        s->n_sets = es ? std::min(std::max(atoi(es), 1), (int)f3d_session::kMaxSets) : (by_memory >= 2 ? 2 : 1);
+        s->batch = eb ? std::min(std::max(atoi(eb), 1), kMaxBatch) : std::min(kMaxBatch, std::max(by_memory / s->n_sets, 1));
+        if (const char* e = getenv("F3D_B200_PIPELINE")) if (atoi(e) <= 1) { s->n_sets = 1; s->batch = 1; }
     }
-    for (int k = 0; k < s->n_slots; k++) {
-        f3d_session::Slot& sl = s->slots[k];
-        if ((rc = dmalloc(s, &sl.rec, npx * 4, true))) return rc;
-        if ((rc = dmalloc(s, &sl.occl_sun, npx, true))) return rc;
-        if ((rc = dmalloc(s, &sl.occl_ibl, npx, true))) return rc;
-        if ((rc = dmalloc(s, &sl.q_sun, npx, false))) return rc;
-        if ((rc = dmalloc(s, &sl.q_ibl, npx, false))) return rc;
-        if ((rc = dmalloc(s, &sl.q_counts, (size_t)8, true))) return rc;
-        if ((rc = dmalloc(s, &sl.q2_sun, npx, false))) return rc;
-        if ((rc = dmalloc(s, &sl.q2_ibl, npx, false))) return rc;
-        if ((rc = dmalloc(s, &sl.qn_sun, npx, false))) return rc;
-        if ((rc = dmalloc(s, &sl.qn_ibl, npx, false))) return rc;
-        CUDA_TRY(cudaEventCreateWithFlags(&sl.primary_done, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&sl.accum_done, cudaEventDisableTiming));
-        if (s->n_slots > 1) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    for (int k = 0; k < s->n_sets; k++) {
+        f3d_session::BatchSet& bs = s->sets[k];
+        for (int j = 0; j < s->batch; j++) {
+            BatchSlot& sl = bs.slots[j];
+            if ((rc = dmalloc(s, &sl.rec, npx * 4, true))) return rc;
+            if ((rc = dmalloc(s, &sl.occl_sun, npx, true))) return rc;
+            if ((rc = dmalloc(s, &sl.occl_ibl, npx, true))) return rc;
+            if ((rc = dmalloc(s, &sl.q_sun, npx, false))) return rc;
+            if ((rc = dmalloc(s, &sl.q_ibl, npx, false))) return rc;
+            if ((rc = dmalloc(s, &sl.q_counts, (size_t)8, true))) return rc;
+            if ((rc = dmalloc(s, &sl.q2_sun, npx, false))) return rc;
+            if ((rc = dmalloc(s, &sl.q2_ibl, npx, false))) return rc;
+            if ((rc = dmalloc(s, &sl.qn_sun, npx, false))) return rc;
+            if ((rc = dmalloc(s, &sl.qn_ibl, npx, false))) return rc;
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&bs.primary_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&bs.accum_done, cudaEventDisableTiming));
+        if (s->n_sets > 1) CUDA_TRY(cudaStreamCreateWithFlags(&bs.stream, cudaStreamNonBlocking));
     }
-    if (s->n_slots > 1) CUDA_TRY(cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming));
+    if (s->n_sets > 1) CUDA_TRY(cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming));
     if (P.spp > 1u && (rc = dmalloc(s, &s->d_sstate, npx * 3, true))) return rc;
     P.sstate = s->d_sstate;
     P.sample_index = 0u;
@@ -892,63 +897,76 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
     if (!s) return fail(F3D_ERR_ARGUMENT, "null session");
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-    const bool pipelined = s->n_slots > 1;
-    if (pipelined) {   // the slot streams start after whatever is already queued on the session stream
+    const bool pipelined = s->n_sets > 1;
+    if (pipelined) {   // the set streams start after whatever is already queued on the session stream
         CUDA_TRY(cudaEventRecord(s->join_ev, s->stream));
-        for (int k = 0; k < s->n_slots; k++) CUDA_TRY(cudaStreamWaitEvent(s->slots[k].stream, s->join_ev, 0));
+        for (int k = 0; k < s->n_sets; k++) CUDA_TRY(cudaStreamWaitEvent(s->sets[k].stream, s->join_ev, 0));
     }
-    for (uint32_t i = 0; i < n; i++) {
-        FrameParams& P = s->P;
-        P.frame_index = s->frames;
-        P.resv_in = s->d_resv[(s->frames + 1u) & 1u];
-        P.resv_out = s->d_resv[s->frames & 1u];
-        if (s->n_peer_ptrs) {
-            // peer images of the buffer being written this frame (see f3d_session_ipc_import)
-            const uint32_t up = (P.part_rank + P.part_world - 1u) % P.part_world, down = (P.part_rank + 1u) % P.part_world;
-            P.peer_up = (float4*)s->peer_ptrs[up * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
-            P.peer_down = (float4*)s->peer_ptrs[down * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
-            P.peer_sync_up = (uint32_t*)s->peer_ptrs[up * F3D_IPC_HANDLES_PER_RANK + 2];
-            P.peer_sync_down = (uint32_t*)s->peer_ptrs[down * F3D_IPC_HANDLES_PER_RANK + 2];
-        }
-        for (uint32_t smp = 0; smp < P.spp; smp++) {
-            P.sample_index = smp;
-            f3d_session::Slot& sl = s->slots[s->steps % (uint64_t)s->n_slots];
-            P.rec = sl.rec; P.occl_sun = sl.occl_sun; P.occl_ibl = sl.occl_ibl;
-            P.q_sun = sl.q_sun; P.q_ibl = sl.q_ibl; P.q_counts = sl.q_counts;
-            P.qn_sun = sl.qn_sun; P.qn_ibl = sl.qn_ibl; P.q2_sun = sl.q2_sun; P.q2_ibl = sl.q2_ibl;
-            cudaStream_t ts = pipelined ? sl.stream : s->stream;
-            f3d_session::Slot& prev = s->slots[(s->steps + (uint64_t)s->n_slots - 1u) % (uint64_t)s->n_slots];
-            if (pipelined && sl.used) CUDA_TRY(cudaStreamWaitEvent(s->stream, sl.accum_done, 0));   // buffer set free again
-            k_primary<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P);
-            if (pipelined) {
-                CUDA_TRY(cudaEventRecord(sl.primary_done, s->stream));
-                CUDA_TRY(cudaStreamWaitEvent(ts, sl.primary_done, 0));
+    FrameParams& P = s->P;
+    const uint32_t spp = P.spp;
+    uint64_t todo = (uint64_t)n * spp;            // steps; a call always starts and ends on a frame boundary
+    uint32_t sample = 0u;
+    while (todo > 0) {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(todo, (uint64_t)s->batch);
+        f3d_session::BatchSet& bs = s->sets[s->batches % (uint64_t)s->n_sets];
+        f3d_session::BatchSet& prev = s->sets[(s->batches + (uint64_t)s->n_sets - 1u) % (uint64_t)s->n_sets];
+        cudaStream_t ts = pipelined ? bs.stream : s->stream;
+        if (pipelined && bs.used) CUDA_TRY(cudaStreamWaitEvent(s->stream, bs.accum_done, 0));   // buffer set free again
+        const uint32_t frame0 = s->frames, sample0 = sample;
+        // ---- the primaries of the batch, back to back ----
+        for (uint32_t k = 0; k < nb; k++) {
+            P.frame_index = s->frames;
+            P.sample_index = sample;
+            P.resv_in = s->d_resv[(s->frames + 1u) & 1u];
+            P.resv_out = s->d_resv[s->frames & 1u];
+            if (s->n_peer_ptrs) {
+                // peer images of the buffer being written this frame (see f3d_session_ipc_import)
+                const uint32_t up = (P.part_rank + P.part_world - 1u) % P.part_world, down = (P.part_rank + 1u) % P.part_world;
+                P.peer_up = (float4*)s->peer_ptrs[up * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
+                P.peer_down = (float4*)s->peer_ptrs[down * F3D_IPC_HANDLES_PER_RANK + (s->frames & 1u)];
+                P.peer_sync_up = (uint32_t*)s->peer_ptrs[up * F3D_IPC_HANDLES_PER_RANK + 2];
+                P.peer_sync_down = (uint32_t*)s->peer_ptrs[down * F3D_IPC_HANDLES_PER_RANK + 2];
             }
-            // sun above the horizon: every sun ray ascends (monotone height tests); curved sun rays that descend keep the
-            // round-1 exact expansion (see F3D_CULL_FAST)
-            const bool curv = P.scene.curvature_enabled != 0u, asc = P.light_dir[1] >= 0.0f;
-#if F3D_TRACE_BOTTOM_UP
-            if (curv && asc) k_ascent<true, 1><<<s->ascent_grid, 256, 0, ts>>>(P);
-            else if (curv) k_ascent<true, 2><<<s->ascent_grid, 256, 0, ts>>>(P);
-            else if (asc) k_ascent<false, 1><<<s->ascent_grid, 256, 0, ts>>>(P);
-            else k_ascent<false, 0><<<s->ascent_grid, 256, 0, ts>>>(P);
+            P.cur = bs.slots[k];
+            P.n_batch = 0u;
+            k_primary<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P);
             s->launches++;
-#endif
-            if (curv && asc) k_trace<true, 1><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
-            else if (curv) k_trace<true, 2><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
-            else if (asc) k_trace<false, 1><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
-            else k_trace<false, 0><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
-            if (pipelined && prev.used) CUDA_TRY(cudaStreamWaitEvent(ts, prev.accum_done, 0));     // accumulate in frame order
-            k_accum<<<s->grid, kThreads, 0, ts>>>(P);
-            if (pipelined) { CUDA_TRY(cudaEventRecord(sl.accum_done, ts)); sl.used = true; }
-            s->launches += 3;
             s->steps++;
+            if (++sample == spp) { sample = 0u; s->frames++; }
         }
-        s->frames++;
+        if (pipelined) {
+            CUDA_TRY(cudaEventRecord(bs.primary_done, s->stream));
+            CUDA_TRY(cudaStreamWaitEvent(ts, bs.primary_done, 0));
+        }
+        // ---- one launch of each later kernel for the whole batch ----
+        P.frame_index = frame0;
+        P.sample_index = sample0;
+        P.n_batch = nb;
+        for (uint32_t k = 0; k < nb; k++) P.slot[k] = bs.slots[k];
+        // sun above the horizon: every sun ray ascends (monotone height tests); curved sun rays that descend keep the
+        // round-1 exact expansion (see F3D_CULL_FAST)
+        const bool curv = P.scene.curvature_enabled != 0u, asc = P.light_dir[1] >= 0.0f;
+#if F3D_TRACE_BOTTOM_UP
+        if (curv && asc) k_ascent<true, 1><<<s->ascent_grid, 256, 0, ts>>>(P);
+        else if (curv) k_ascent<true, 2><<<s->ascent_grid, 256, 0, ts>>>(P);
+        else if (asc) k_ascent<false, 1><<<s->ascent_grid, 256, 0, ts>>>(P);
+        else k_ascent<false, 0><<<s->ascent_grid, 256, 0, ts>>>(P);
+        s->launches++;
+#endif
+        if (curv && asc) k_trace<true, 1><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+        else if (curv) k_trace<true, 2><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+        else if (asc) k_trace<false, 1><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+        else k_trace<false, 0><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
+        if (pipelined && prev.used && &prev != &bs) CUDA_TRY(cudaStreamWaitEvent(ts, prev.accum_done, 0));     // accumulate in frame order
+        k_accum<<<s->grid, kThreads, 0, ts>>>(P);
+        if (pipelined) { CUDA_TRY(cudaEventRecord(bs.accum_done, ts)); bs.used = true; }
+        s->launches += 2;
+        s->batches++;
+        todo -= nb;
     }
     if (pipelined)   // everything that follows on the session stream (variance, resolve, timing) sees all frames
-        for (int k = 0; k < s->n_slots; k++)
-            if (s->slots[k].used) CUDA_TRY(cudaStreamWaitEvent(s->stream, s->slots[k].accum_done, 0));
+        for (int k = 0; k < s->n_sets; k++)
+            if (s->sets[k].used) CUDA_TRY(cudaStreamWaitEvent(s->stream, s->sets[k].accum_done, 0));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
     return 0;

@@ -32,6 +32,24 @@ namespace f3d {
 
 constexpr int kTileW = 16, kTileH = 16;      // CTA pixel tile; warps own 8x4 sub-tiles
 
+// Wavefront buffers of ONE step (one camera sample of one frame).  A launch of k_ascent / k_trace / k_accum serves a BATCH of
+// consecutive steps (FrameParams::slot[0 .. n_batch)): k_primary of step i+1 only needs k_primary of step i (the reservoir
+// chain), so the primaries of a batch run back to back and one launch of each later kernel handles all their rays - on an
+// image partition (1/8 of a 1080p frame is ~230 k rays) a single step cannot fill 148 SMs, a batch can.
+constexpr int kMaxBatch = 4;
+struct BatchSlot {
+    float4* rec;               // 4 x float4 per pixel, see PixelRec
+    uint8_t* occl_sun;         // per pixel: sun ray occluded
+    uint8_t* occl_ibl;         // per pixel: IBL ray occluded
+    uint32_t* q_sun;           // compacted pixel indices that need a sun ray
+    uint32_t* q_ibl;           // compacted pixel indices that need an IBL ray
+    uint32_t* q_counts;        // [0] n_sun [1] n_ibl [2] next_sun [3] next_ibl; stage 2: [4] n2_sun [5] n2_ibl [6] next2_sun [7] next2_ibl
+    uint32_t* q2_sun;          // stage-2 lists: rays k_ascent could not decide (pixel index; seeds in qn_*)
+    uint32_t* q2_ibl;
+    unsigned long long* qn_sun;   // per stage-2 sun entry: seeds of the bottom-up start (ascent_seeds; k_ascent -> k_trace)
+    unsigned long long* qn_ibl;   // same for the IBL list
+};
+
 struct FrameParams {
     SceneParams scene;          // env / mesh / albedo (+ the plain pyramid when the KAT seam keeps it)
     FastScene fast;             // quad-packed pyramid for the production traversal
@@ -52,16 +70,9 @@ struct FrameParams {
     unsigned long long* counters;  // primary, shadow, ibl, nodes
     // wavefront state
     uint32_t sample_index;     // 0 .. spp-1 (one k_primary/k_trace/k_accum round per camera sample)
-    float4* rec;               // 4 x float4 per pixel, see PixelRec
-    uint8_t* occl_sun;         // per pixel: sun ray occluded
-    uint8_t* occl_ibl;         // per pixel: IBL ray occluded
-    uint32_t* q_sun;           // compacted pixel indices that need a sun ray
-    uint32_t* q_ibl;           // compacted pixel indices that need an IBL ray
-    uint32_t* q_counts;        // [0] n_sun [1] n_ibl [2] next_sun [3] next_ibl; stage 2: [4] n2_sun [5] n2_ibl [6] next2_sun [7] next2_ibl
-    uint32_t* q2_sun;          // stage-2 lists: rays k_ascent could not decide (pixel index; seeds in qn_*)
-    uint32_t* q2_ibl;
-    unsigned long long* qn_sun;   // per stage-2 sun entry: seeds of the bottom-up start (ascent_seeds; k_ascent -> k_trace)
-    unsigned long long* qn_ibl;   // same for the IBL list
+    BatchSlot cur;             // k_primary: the slot of the step it renders
+    BatchSlot slot[kMaxBatch]; // k_ascent / k_trace / k_accum: the steps of the batch, in order; slot[0] is step
+    uint32_t n_batch;          //   (frame_index, sample_index), step k is sample (sample_index + k) % spp of a later frame
     float4* sstate;            // spp > 1 only: 3 x float4 per pixel (rng+cand, prev, partial radiance)
     // NVLink halo push: peer images of resv_out for the rank above / below (NULL = none)
     float4* peer_up;
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(cons
         // every populated sample stores direction == wi; the shader re-normalises it (:520)
         sun_dir = prev_valid ? normalize3(wi) : wi;
         reuse_w = prev_valid ? clampf(prev_r.weight, 0.0f, 4.0f) : 1.0f;
-        float4* rec = P.rec + 4 * (size_t)pix;
+        float4* rec = P.cur.rec + 4 * (size_t)pix;
         if (!hit.hit) {
             const v3 sky = env_radiance(S, ray.d);
             st_stream(rec + 0, make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u)));
@@ -450,14 +461,14 @@ __global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(cons
         const uint32_t m_sun = __ballot_sync(0xFFFFFFFFu, want_sun), m_ibl = __ballot_sync(0xFFFFFFFFu, want_ibl);
         uint32_t b_sun = 0u, b_ibl = 0u;
         if (lane == 0u) {
-            if (m_sun) b_sun = atomicAdd(P.q_counts + 0, (uint32_t)__popc(m_sun));
-            if (m_ibl) b_ibl = atomicAdd(P.q_counts + 1, (uint32_t)__popc(m_ibl));
+            if (m_sun) b_sun = atomicAdd(P.cur.q_counts + 0, (uint32_t)__popc(m_sun));
+            if (m_ibl) b_ibl = atomicAdd(P.cur.q_counts + 1, (uint32_t)__popc(m_ibl));
         }
         b_sun = __shfl_sync(0xFFFFFFFFu, b_sun, 0);
         b_ibl = __shfl_sync(0xFFFFFFFFu, b_ibl, 0);
         const uint32_t lt = (1u << lane) - 1u;
-        if (want_sun) P.q_sun[b_sun + __popc(m_sun & lt)] = pix;
-        if (want_ibl) P.q_ibl[b_ibl + __popc(m_ibl & lt)] = pix;
+        if (want_sun) P.cur.q_sun[b_sun + __popc(m_sun & lt)] = pix;
+        if (want_ibl) P.cur.q_ibl[b_ibl + __popc(m_ibl & lt)] = pix;
     }
     warp_add_counters(P.counters, n_primary, 0u, 0u, n_nodes);
     if (s + 1u == spp) signal_neighbours(P);
@@ -473,7 +484,7 @@ __global__ void k_wait_peers(const __grid_constant__ FrameParams P, uint32_t nee
 // the idle lanes pull fresh rays (one atomic per warp).
 // ---------------------------------------------------------------------------------------------
 #ifndef F3D_REFILL_BELOW
-#define F3D_REFILL_BELOW 24
+#define F3D_REFILL_BELOW 16
 #endif
 #ifndef F3D_TRACE_MIN_CTAS
 #define F3D_TRACE_MIN_CTAS 6
@@ -556,13 +567,13 @@ __device__ unsigned long long g_sched_stats[8];
 constexpr uint32_t kLeafQ = 64u;    // ring entries per warp (power of two, >= 2 * 32 - 1)
 
 template <bool IS_SUN, bool CURV, bool EXACT_CULL>
-__device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack st, uint32_t* wq) {
+__device__ __forceinline__ void trace_list(const FrameParams& P, const BatchSlot& B, const SmemStack st, uint32_t* wq) {
     const uint32_t lane = threadIdx.x & 31u;
     const FastScene& F = P.fast;
-    const uint32_t n = P.q_counts[IS_SUN ? 0 : 1];
-    const uint32_t* __restrict__ queue = IS_SUN ? P.q_sun : P.q_ibl;
-    uint32_t* next = P.q_counts + (IS_SUN ? 2 : 3);
-    uint8_t* __restrict__ occl = IS_SUN ? P.occl_sun : P.occl_ibl;
+    const uint32_t n = B.q_counts[IS_SUN ? 0 : 1];
+    const uint32_t* __restrict__ queue = IS_SUN ? B.q_sun : B.q_ibl;
+    uint32_t* next = B.q_counts + (IS_SUN ? 2 : 3);
+    uint8_t* __restrict__ occl = IS_SUN ? B.occl_sun : B.occl_ibl;
     const v3 wi = normalize3(ld3(P.light_dir));
     const v3 wi_reuse = normalize3(wi);
     const bool has_mesh = P.scene.traversal_mode == 0u;
@@ -632,13 +643,13 @@ __device__ __forceinline__ void trace_list(const FrameParams& P, const SmemStack
                 const uint32_t idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
                 if (idx < n) {
                     pix = __ldg(queue + idx);
-                    const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix);
+                    const float4 r0 = __ldcg(B.rec + 4 * (size_t)pix);
                     Ray r;
                     r.o = V3(r0.x, r0.y, r0.z);
                     r.tmin = 1e-3f;
                     r.tmax = 1e30f;
                     if (IS_SUN) r.d = (__float_as_uint(r0.w) & kRecSunReuseDir) ? wi_reuse : wi;
-                    else { const float4 r1 = __ldcg(P.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
+                    else { const float4 r1 = __ldcg(B.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
                     n_rays++;
                     mesh_occl = false;
                     bool decided = false;
@@ -791,9 +802,9 @@ constexpr uint32_t kLeafQFields = 3u;
 // their slow paths, ~600 SASS instructions) must exist once per list, or the kernel outgrows the instruction cache
 // (measured: 39 % of the stall samples were "no instruction" with the solve inlined at every site).
 template <bool IS_SUN, bool CURV>
-__device__ __noinline__ bool solve_leaf_item(const FrameParams& P, uint32_t cell, uint32_t pixw, float tmax) {
+__device__ __noinline__ bool solve_leaf_item(const FrameParams& P, const float4* __restrict__ rec, uint32_t cell, uint32_t pixw, float tmax) {
     const uint32_t pix = pixw & 0x7FFFFFFFu;
-    const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix);
+    const float4 r0 = __ldcg(rec + 4 * (size_t)pix);
     Ray r;
     r.o = V3(r0.x, r0.y, r0.z);
     r.tmin = 1e-3f;
@@ -801,21 +812,21 @@ __device__ __noinline__ bool solve_leaf_item(const FrameParams& P, uint32_t cell
     if (IS_SUN) {
         const v3 wi = normalize3(ld3(P.light_dir));
         r.d = (pixw >> 31) ? normalize3(wi) : wi;
-    } else { const float4 r1 = __ldcg(P.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
+    } else { const float4 r1 = __ldcg(rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
     TraceState L;
     leaf_ray_setup<CURV>(P.fast, r, L);
     return leaf_node<true, CURV>(P.fast, L, cell);
 }
 
 template <bool IS_SUN, bool CURV, bool ASC>
-__device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemStack st, uint32_t* wq) {
+__device__ __forceinline__ void trace_list_bu(const FrameParams& P, const BatchSlot& B, const SmemStack st, uint32_t* wq) {
     const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     const FastScene& F = P.fast;
-    const uint32_t n = P.q_counts[IS_SUN ? 4 : 5];
-    const uint32_t* __restrict__ queue = IS_SUN ? P.q2_sun : P.q2_ibl;
-    const unsigned long long* __restrict__ qseeds = IS_SUN ? P.qn_sun : P.qn_ibl;
-    uint32_t* next = P.q_counts + (IS_SUN ? 6 : 7);
-    uint8_t* __restrict__ occl = IS_SUN ? P.occl_sun : P.occl_ibl;
+    const uint32_t n = B.q_counts[IS_SUN ? 4 : 5];
+    const uint32_t* __restrict__ queue = IS_SUN ? B.q2_sun : B.q2_ibl;
+    const unsigned long long* __restrict__ qseeds = IS_SUN ? B.qn_sun : B.qn_ibl;
+    uint32_t* next = B.q_counts + (IS_SUN ? 6 : 7);
+    uint8_t* __restrict__ occl = IS_SUN ? B.occl_sun : B.occl_ibl;
     const v3 wi = normalize3(ld3(P.light_dir));
     const v3 wi_reuse = normalize3(wi);
     const bool has_mesh = P.scene.traversal_mode == 0u;
@@ -836,7 +847,7 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
             const uint32_t slot = (q_head + lane) & (kLeafQBU - 1u);
             hpix = wq[kLeafQBU + slot];
             n_nodes++;
-            hit = solve_leaf_item<IS_SUN, CURV>(P, wq[slot], hpix, __uint_as_float(wq[2u * kLeafQBU + slot]));
+            hit = solve_leaf_item<IS_SUN, CURV>(P, B.rec, wq[slot], hpix, __uint_as_float(wq[2u * kLeafQBU + slot]));
             if (hit) occl[hpix & 0x7FFFFFFFu] = 1u;
         }
         uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
@@ -876,7 +887,7 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
                 if (idx < n) {
                     const uint32_t pix = __ldg(queue + idx);
                     unsigned long long seeds = __ldg(qseeds + idx);
-                    const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix);
+                    const float4 r0 = __ldcg(B.rec + 4 * (size_t)pix);
                     Ray r;
                     r.o = V3(r0.x, r0.y, r0.z);
                     r.tmin = 1e-3f;
@@ -886,7 +897,7 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
                         const bool reuse = (__float_as_uint(r0.w) & kRecSunReuseDir) != 0u;
                         r.d = reuse ? wi_reuse : wi;
                         pixw |= reuse ? 0x80000000u : 0u;
-                    } else { const float4 r1 = __ldcg(P.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
+                    } else { const float4 r1 = __ldcg(B.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
                     if (has_mesh) {                      // intersect_hybrid_optimized :213-221, as k_ascent did (t < 0.01 was decided there)
                         const Hit mh = intersect_mesh(P.scene, r);
                         if (mh.hit && mh.t < r.tmax) r.tmax = mh.t;
@@ -966,14 +977,14 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const SmemSt
 // bottom-up start (ascent_seeds).  A ray whose own cell occludes it, or that has no seed left, is DECIDED here; the others
 // are appended (warp ballot + prefix sum, one atomic per warp) to the stage-2 lists k_trace traverses.
 template <bool IS_SUN, bool CURV, bool ASC>
-__device__ __forceinline__ void ascent_list(const FrameParams& P) {
+__device__ __forceinline__ void ascent_list(const FrameParams& P, const BatchSlot& B) {
     const FastScene& F = P.fast;
     const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    const uint32_t n = P.q_counts[IS_SUN ? 0 : 1];
-    const uint32_t* __restrict__ queue = IS_SUN ? P.q_sun : P.q_ibl;
-    uint32_t* __restrict__ queue2 = IS_SUN ? P.q2_sun : P.q2_ibl;
-    unsigned long long* __restrict__ qseeds = IS_SUN ? P.qn_sun : P.qn_ibl;
-    uint8_t* __restrict__ occl = IS_SUN ? P.occl_sun : P.occl_ibl;
+    const uint32_t n = B.q_counts[IS_SUN ? 0 : 1];
+    const uint32_t* __restrict__ queue = IS_SUN ? B.q_sun : B.q_ibl;
+    uint32_t* __restrict__ queue2 = IS_SUN ? B.q2_sun : B.q2_ibl;
+    unsigned long long* __restrict__ qseeds = IS_SUN ? B.qn_sun : B.qn_ibl;
+    uint8_t* __restrict__ occl = IS_SUN ? B.occl_sun : B.occl_ibl;
     const v3 wi = normalize3(ld3(P.light_dir));
     const v3 wi_reuse = normalize3(wi);
     const bool has_mesh = P.scene.traversal_mode == 0u;
@@ -986,11 +997,11 @@ __device__ __forceinline__ void ascent_list(const FrameParams& P) {
         unsigned long long seeds = 0ull;
         if (i < n) {
             pix = __ldg(queue + i);
-            const float4 r0 = __ldcg(P.rec + 4 * (size_t)pix);
+            const float4 r0 = __ldcg(B.rec + 4 * (size_t)pix);
             Ray r;
             r.o = V3(r0.x, r0.y, r0.z); r.tmin = 1e-3f; r.tmax = 1e30f;
             if (IS_SUN) r.d = (__float_as_uint(r0.w) & kRecSunReuseDir) ? wi_reuse : wi;
-            else { const float4 r1 = __ldcg(P.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
+            else { const float4 r1 = __ldcg(B.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
             n_rays++;
             bool mesh_occl = false, decided = false;
             if (has_mesh) {                      // intersect_hybrid_optimized :213-221
@@ -1017,7 +1028,7 @@ __device__ __forceinline__ void ascent_list(const FrameParams& P) {
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
         if (m != 0u) {
             uint32_t b2 = 0u;
-            if (lane == 0u) b2 = atomicAdd(P.q_counts + (IS_SUN ? 4 : 5), (uint32_t)__popc(m));
+            if (lane == 0u) b2 = atomicAdd(B.q_counts + (IS_SUN ? 4 : 5), (uint32_t)__popc(m));
             b2 = __shfl_sync(0xFFFFFFFFu, b2, 0);
             if (want) {
                 const uint32_t slot = b2 + (uint32_t)__popc(m & lt);
@@ -1032,8 +1043,10 @@ __device__ __forceinline__ void ascent_list(const FrameParams& P) {
 // SUN_MODE as for k_trace: 2 = the sun list is left to the top-down tracer.
 template <bool CURV_SUN, int SUN_MODE>
 __global__ void __launch_bounds__(256) k_ascent(const __grid_constant__ FrameParams P) {
-    if (SUN_MODE != 2) ascent_list<true, CURV_SUN, SUN_MODE == 1>(P);
-    ascent_list<false, false, false>(P);
+    for (uint32_t b = 0; b < P.n_batch; b++) {
+        if (SUN_MODE != 2) ascent_list<true, CURV_SUN, SUN_MODE == 1>(P, P.slot[b]);
+        ascent_list<false, false, false>(P, P.slot[b]);
+    }
 }
 
 // One persistent launch walks the sun list, then the IBL list: a warp that runs out of sun rays moves
@@ -1049,13 +1062,16 @@ __global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(
     st.stride = kTraceCtaThreads;
     // per-warp leaf ring behind the stacks
     uint32_t* wq = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)P.stack_depth * kTraceCtaThreads + (threadIdx.x >> 5) * (kLeafQBU * kLeafQFields);
+    // every sun list of the batch, then every IBL list: a warp that runs out of rays in one list moves straight on to the next
 #if F3D_TRACE_BOTTOM_UP
-    if (SUN_MODE == 2) trace_list<true, CURV_SUN, true>(P, st, wq);
-    else trace_list_bu<true, CURV_SUN, SUN_MODE == 1>(P, st, wq);
-    trace_list_bu<false, false, false>(P, st, wq);
+    for (uint32_t b = 0; b < P.n_batch; b++) {
+        if (SUN_MODE == 2) trace_list<true, CURV_SUN, true>(P, P.slot[b], st, wq);
+        else trace_list_bu<true, CURV_SUN, SUN_MODE == 1>(P, P.slot[b], st, wq);
+    }
+    for (uint32_t b = 0; b < P.n_batch; b++) trace_list_bu<false, false, false>(P, P.slot[b], st, wq);
 #else
-    trace_list<true, CURV_SUN, SUN_MODE == 2>(P, st, wq);
-    trace_list<false, false, false>(P, st, wq);
+    for (uint32_t b = 0; b < P.n_batch; b++) trace_list<true, CURV_SUN, SUN_MODE == 2>(P, P.slot[b], st, wq);
+    for (uint32_t b = 0; b < P.n_batch; b++) trace_list<false, false, false>(P, P.slot[b], st, wq);
 #endif
 }
 
@@ -1065,49 +1081,56 @@ __global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_accum(const __grid_constant__ FrameParams P) {
     uint32_t gx, gy;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 8u) P.q_counts[threadIdx.x] = 0u;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 8u * P.n_batch) P.slot[threadIdx.x >> 3].q_counts[threadIdx.x & 7u] = 0u;
     if (!owned_pixel(P, gx, gy)) return;
     const uint32_t pix = gy * P.W + gx;
-    const uint32_t spp = max(P.spp, 1u), s = P.sample_index;
-    const float4* rec = P.rec + 4 * (size_t)pix;
-    const float4 r0 = ld_stream(rec), r2 = ld_stream(rec + 2), r3 = ld_stream(rec + 3);
-    const uint32_t flags = __float_as_uint(r0.w);
+    const uint32_t spp = max(P.spp, 1u), window = max(P.window, 2u);
+    uint32_t s = P.sample_index, frame = P.frame_index;
     v3 fr = V3(0, 0, 0);
     if (s > 0u) { const float4 c = P.sstate[3 * (size_t)pix + 2]; fr = V3(c.x, c.y, c.z); }
-    if (!(flags & kRecHit)) {
-        fr = fr + V3(r2.w, r3.x, r3.y);                       // sky radiance (:489)
-    } else {
-        const float4 r1 = ld_stream(rec + 1);
-        v3 sun = V3(0, 0, 0);
-        if (flags & kRecSun) {
-            const float vis = P.occl_sun[pix] ? 0.0f : 1.0f;
-            sun = (V3(r2.x, r2.y, r2.z) * vis) * r1.w;           // albedo*light_color*nd*vis*reuse_w (:531)
+    float4 acc = make_float4(0, 0, 0, 0);
+    float2 wf = make_float2(0, 0);
+    bool loaded = false;
+    for (uint32_t k = 0; k < P.n_batch; k++) {          // the steps of the batch in order: the per-pixel sums are order-sensitive
+        const BatchSlot& B = P.slot[k];
+        const float4* rec = B.rec + 4 * (size_t)pix;
+        const float4 r0 = ld_stream(rec), r2 = ld_stream(rec + 2), r3 = ld_stream(rec + 3);
+        const uint32_t flags = __float_as_uint(r0.w);
+        if (!(flags & kRecHit)) {
+            fr = fr + V3(r2.w, r3.x, r3.y);                       // sky radiance (:489)
+        } else {
+            const float4 r1 = ld_stream(rec + 1);
+            v3 sun = V3(0, 0, 0);
+            if (flags & kRecSun) {
+                const float vis = B.occl_sun[pix] ? 0.0f : 1.0f;
+                sun = (V3(r2.x, r2.y, r2.z) * vis) * r1.w;           // albedo*light_color*nd*vis*reuse_w (:531)
+            }
+            const float env_vis = B.occl_ibl[pix] ? 0.0f : 1.0f;
+            const v3 ibl = V3(r2.w, r3.x, r3.y) * env_vis;           // albedo*env(ei)*env_vis (:545)
+            fr = (fr + sun) + ibl;
         }
-        const float env_vis = P.occl_ibl[pix] ? 0.0f : 1.0f;
-        const v3 ibl = V3(r2.w, r3.x, r3.y) * env_vis;           // albedo*env(ei)*env_vis (:545)
-        fr = (fr + sun) + ibl;
+        if (s + 1u == spp) {                               // last sample of its frame: accumulate + windowed Welford (:557-574)
+            if (!loaded) { acc = ld_stream(P.accum + pix); wf = ld_stream(P.welford + pix); loaded = true; }
+            const float fspp = (float)spp;
+            fr = V3(fdiv(fr.x, fspp), fdiv(fr.y, fspp), fdiv(fr.z, fspp));
+            acc.x = acc.x + fr.x;
+            acc.y = acc.y + fr.y;
+            acc.z = acc.z + fr.z;
+            acc.w = acc.w + 1.0f;
+            if (frame % window == 0u) wf = make_float2(0.0f, 0.0f);
+            const float mean_lum = luminance(V3(fdiv(acc.x, acc.w), fdiv(acc.y, acc.w), fdiv(acc.z, acc.w)));
+            const float kk = (float)(frame % window) + 1.0f;
+            const float delta = mean_lum - wf.x;
+            const float mean = wf.x + fdiv(delta, kk);
+            const float m2 = wf.y + delta * (mean_lum - mean);
+            wf = make_float2(mean, m2);
+            fr = V3(0, 0, 0);
+            s = 0u;
+            frame++;
+        } else s++;
     }
-    if (s + 1u < spp) {
-        P.sstate[3 * (size_t)pix + 2] = make_float4(fr.x, fr.y, fr.z, 0.0f);
-        return;
-    }
-    const float fspp = (float)spp;
-    fr = V3(fdiv(fr.x, fspp), fdiv(fr.y, fspp), fdiv(fr.z, fspp));
-    float4 acc = ld_stream(P.accum + pix);
-    acc.x = acc.x + fr.x;
-    acc.y = acc.y + fr.y;
-    acc.z = acc.z + fr.z;
-    acc.w = acc.w + 1.0f;
-    st_stream(P.accum + pix, acc);
-    const uint32_t window = max(P.window, 2u);
-    float2 wf = ld_stream(P.welford + pix);
-    if (P.frame_index % window == 0u) wf = make_float2(0.0f, 0.0f);
-    const float mean_lum = luminance(V3(fdiv(acc.x, acc.w), fdiv(acc.y, acc.w), fdiv(acc.z, acc.w)));
-    const float k = (float)(P.frame_index % window) + 1.0f;
-    const float delta = mean_lum - wf.x;
-    const float mean = wf.x + fdiv(delta, k);
-    const float m2 = wf.y + delta * (mean_lum - mean);
-    st_stream(P.welford + pix, make_float2(mean, m2));
+    if (s > 0u) P.sstate[3 * (size_t)pix + 2] = make_float4(fr.x, fr.y, fr.z, 0.0f);      // a frame continues in the next batch
+    if (loaded) { st_stream(P.accum + pix, acc); st_stream(P.welford + pix, wf); }
 }
 
 // ---------------------------------------------------------------------------------------------
