@@ -41,14 +41,29 @@ sys.path.insert(0, str(ROOT / "tests"))
 WIDTH, HEIGHT, DEM_N, DEM_SPACING = 1920, 1080, 2048, 10.0
 CPU_SAMPLE = (480, 270, 32)   # width, height, frames of the bounded CPU sample
 
+# BASELINE.json configs.  "c2" is the headline (configs[1]); the others are selectable with --config and
+# c5 rides along as `secondary_c5` at every N (the frame that is large enough to fill 8 GPUs).
+CONFIGS = {
+    "c2": dict(width=1920, height=1080, dem_n=2048, spp=1, atmosphere=None,
+               label="rainier-shaped 2048x2048 DEM (SURVEY 8d C2, BASELINE configs[1]), 1920x1080, spp=1 per frame"),
+    "c3": dict(width=3840, height=2160, dem_n=4096, spp=8, atmosphere={"turbidity": 3.0},
+               label="shasta-shaped 4096x4096 DEM (SURVEY 8d C3, BASELINE configs[2]), 3840x2160, spp=8 per frame, AETHER "
+                     "atmosphere post on; uniform albedo (the reference path has no per-texel albedo, hybrid_traversal.wgsl:241-243)"),
+    "c5": dict(width=7200, height=7200, dem_n=4096, spp=16, atmosphere=None,
+               label="print-res 7200x7200 over a 4096x4096 DEM (SURVEY 8d C5, BASELINE configs[4]), spp=16 per frame"),
+}
 
-def workload():
+
+def workload(config="c2"):
     import _helpers as H
 
-    dem = H.rainier_dem(DEM_N)
-    cam = H.rainier_camera(DEM_N, DEM_SPACING, dem)
-    kw = dict(spacing=(DEM_SPACING, DEM_SPACING), exaggeration=1.0, albedo=H.ALBEDO, sun_azimuth_deg=302.0,
-              sun_elevation_deg=24.0, sun_intensity=2.5, env_intensity=0.35, seed=7, spp=1)
+    c = CONFIGS[config]
+    n = c["dem_n"]
+    spacing = DEM_SPACING * 2048.0 / n if config == "c2" else DEM_SPACING          # C3/C5: same 10 m posting, twice the extent
+    dem = H.rainier_dem(n)
+    cam = H.rainier_camera(n, spacing, dem)
+    kw = dict(spacing=(spacing, spacing), exaggeration=1.0, albedo=H.ALBEDO, sun_azimuth_deg=302.0,
+              sun_elevation_deg=24.0, sun_intensity=2.5, env_intensity=0.35, seed=7, spp=c["spp"])
     return dem, cam, kw
 
 
@@ -171,6 +186,18 @@ def widened_rows():
     return rows
 
 
+def config_block(config, width, height, steps, world=1, extra=None):
+    """The `config` object both arms print (identical text, so the driver can pair the lines)."""
+    c = CONFIGS[config]
+    cfg = {"workload": f"{c['label']}; one step = one accumulation frame over the whole image ({steps} steps timed; 256 frames of "
+                       f"spp=1 = the 256-spp snapshot).  The reference arm (CPU oracle port) times a {CPU_SAMPLE[0]}x{CPU_SAMPLE[1]} "
+                       f"sample of this frame (1/16 of the pixels) per step; Mrays/s normalises it.",
+           "name": config, "width": width, "height": height, "dem": f"{c['dem_n']}x{c['dem_n']}", "spp_per_frame": c["spp"]}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU implementation (oracle port), rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -180,7 +207,7 @@ def run_reference(args):
     os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
     from oracle import oracle
 
-    dem, cam, kw = workload()
+    dem, cam, kw = workload(args.config)
     w, h, _ = CPU_SAMPLE
     common = dict(variance_threshold=1e30)
     calibrate_oracle_threads(dem, cam, kw)
@@ -191,16 +218,59 @@ def run_reference(args):
     dt = out["frames_seconds"]   # the K-frame loop; DEM pyramid build (setup) excluded as for the GPU value
     rays = out["rays_primary"] + out["rays_shadow"] + out["rays_ibl"]
     val = rays / dt / 1e6
-    sample = f"{w}x{h} px (1/16 of the 1920x1080 frame) per step, {k} steps, same scene and DEM"
+    sample = (f"{w}x{h} px (1/16 of the {CONFIGS[args.config]['width']}x{CONFIGS[args.config]['height']} frame) per step, {k} steps, same scene "
+              f"and DEM; CPU oracle port of the WGSL/Rust path (the reference needs cargo + wgpu: unbuildable here)")
     line = {"impl": "reference", "metric": "Mrays/s, path-traced DEM snapshot (primary+shadow+IBL rays)", "value": val,
             "unit": "Mrays/s", "n_gpus": args.gpus, "steps": k, "warmup": args.warmup, "ms_per_step": dt * 1e3 / k,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "rainier-shaped 2048x2048 DEM, 1920x1080, spp=1/frame (BASELINE configs[1])",
-                       "reference_impl": "CPU oracle port of the WGSL/Rust path (reference needs cargo+wgpu: unbuildable here)"},
+            "config": config_block(args.config, CONFIGS[args.config]["width"], CONFIGS[args.config]["height"], k),
             "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": oracle.get_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def measured_traffic():
+    """DRAM bytes per frame from the committed ncu capture, but only if it was taken from THIS build of the kernels
+    (profiles/traffic.json carries the library's source hash); a stale capture is reported as null with the reason."""
+    tp = ROOT / "profiles" / "traffic.json"
+    try:
+        from forge3d_b200 import _native
+
+        info = _native.lib().f3d_build_info().decode()
+        t = json.loads(tp.read_text())
+        if t.get("build") and t["build"] == info:
+            return t.get("frame_dram_bytes"), f"ncu --set full, profiles/{t.get('source', 'traffic.json')}, build {info}"
+        return None, f"profiles/traffic.json was captured from build {t.get('build')!r}, this library is {info!r}: not reported"
+    except Exception as exc:
+        return None, f"unavailable ({exc!r})"
+
+
+def time_frames(pr, torch, dist, distributed, n_warm, n_timed, sampler=None, rank=0):
+    """W untimed + K timed frames of a resident scene; returns (ms max over ranks, ray counts summed over ranks, clocks)."""
+    pr.render_frames(n_warm)
+    torch.cuda.synchronize()
+    s0 = pr.session.stats()
+    if distributed:
+        dist.barrier()
+    t0 = time.time()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    pr.render_frames(n_timed)
+    ev1.record()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    clocks = sampler.stop(t0) if (sampler is not None and rank == 0) else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    s1 = pr.session.stats()
+    rays = torch.tensor([s1[k] - s0[k] for k in ("rays_primary", "rays_shadow", "rays_ibl", "nodes_popped", "kernel_launches")],
+                        dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays)
+    return float(ms.item()), [float(v) for v in rays.tolist()], clocks
 
 
 def main():
@@ -209,17 +279,24 @@ def main():
     ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config (default c2 = the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the spp=8 x 32 frames run")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the spp=8 x 32 frames run and the C5 line")
     ap.add_argument("--no-rows", action="store_true", help="skip the side benches of the widened rows")
-    ap.add_argument("--width", type=int, default=WIDTH)
-    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--no-identity", action="store_true", help="N > 1: skip the 1-GPU re-render that proves bit identity")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("F3D_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+    # stdout carries exactly one JSON line; NCCL's own log (INFO unless the caller chose otherwise) goes to stderr, where the
+    # driver reads the communicator's rank count from it
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("F3D_NCCL_DEBUG", "INFO"))
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
 
@@ -228,7 +305,6 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (forge3d_b200 has no CPU fallback)")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -236,50 +312,37 @@ def main():
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    def barrier():
-        if distributed:
-            dist.barrier()
-
-    def all_reduce(t, op=None):
-        if distributed:
-            dist.all_reduce(t, op=op if op is not None else dist.ReduceOp.SUM)
-
-    W, Hh = args.width, args.height
-    dem, cam, kw = workload()
+    C = CONFIGS[args.config]
+    W, Hh = args.width or C["width"], args.height or C["height"]
+    dem, cam, kw = workload(args.config)
+    atm = dict(atmosphere=C["atmosphere"]) if C["atmosphere"] else {}
     K, Wm = max(args.steps, 1), max(args.warmup, 3)
     fixed = dict(max_frames=K + Wm, min_frames=K + Wm, variance_threshold=1e30)
 
     # ---------------- resident-scene timing (value) ----------------
-    pr = PartitionedRender(dem, W, Hh, cam, **kw, **fixed)
+    pr = PartitionedRender(dem, W, Hh, cam, **kw, **atm, **fixed)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)            # nvidia-smi start-up; samples before the timed region are dropped below
-    pr.render_frames(Wm)
-    torch.cuda.synchronize()
-    s0 = pr.session.stats()
-    barrier()
-    t_region0 = time.time()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    pr.render_frames(K)
-    ev1.record()
-    torch.cuda.synchronize()
-    barrier()
-    clocks = sampler.stop(t_region0) if rank == 0 else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    all_reduce(ms, dist.ReduceOp.MAX)
-    s1 = pr.session.stats()
-    rays_local = [s1[k] - s0[k] for k in ("rays_primary", "rays_shadow", "rays_ibl")]
-    rays = torch.tensor(rays_local + [s1["nodes_popped"] - s0["nodes_popped"]], dtype=torch.float64, device="cuda")
-    all_reduce(rays)
-    total_ms = float(ms.item())
-    n_primary, n_shadow, n_ibl, n_nodes = [float(v) for v in rays.tolist()]
+    total_ms, (n_primary, n_shadow, n_ibl, n_nodes, n_launch), clocks = time_frames(pr, torch, dist, distributed, Wm, K, sampler, rank)
     total_rays = n_primary + n_shadow + n_ibl
     value = total_rays / (total_ms * 1e-3) / 1e6
-    images = pr.resolve(aovs=False)
+    images = pr.resolve(aovs=False, dst=0) if distributed else pr.resolve(aovs=False)
     pr.close()
+
+    # ---------------- N > 1: the same frames on ONE GPU must give the same bytes ----------------
+    identical = None
+    if distributed and not args.no_identity:
+        if rank == 0:
+            from forge3d_b200.session import Session
+
+            s1 = Session(dem, W, Hh, cam, device=local_rank, **kw, **atm, **fixed)
+            s1.render_frames(K + Wm)
+            one = s1.resolve_host()
+            s1.close()
+            identical = bool(np.array_equal(one["rgba"], images["rgba"]))
+        dist.barrier()
 
     # ---------------- end to end through the public call with host buffers (e2e) ----------------
     e2e = None
@@ -288,7 +351,7 @@ def main():
             pinned = torch.from_numpy(dem).pin_memory()
             dem_host = pinned.numpy()
             kw_e2e = dict(kw)
-            kw_e2e.update(max_frames=K, min_frames=K, variance_threshold=1e30)
+            kw_e2e.update(max_frames=K, min_frames=K, variance_threshold=1e30, **atm)
             _native.hybrid_render_terrain_reference(dem_host, W, Hh, cam, **{**kw_e2e, "max_frames": 3, "min_frames": 3})
             t0 = time.perf_counter()
             out = _native.hybrid_render_terrain_reference(dem_host, W, Hh, cam, **kw_e2e)
@@ -298,15 +361,18 @@ def main():
             e2e = {"value": r / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": dem_host.nbytes / K,
                    "d2h_bytes_per_step": d2h / K, "call_ms": dt * 1e3, "frames": K,
                    "setup_ms": out["setup_ms"], "frames_ms": out["frames_ms"], "readback_ms": out["readback_ms"],
-                   "note": "one hybrid_render_terrain_reference call = K steps; bytes are per call / K"}
+                   "note": "one hybrid_render_terrain_reference call = K steps (DEM H2D from pinned host memory, pyramid build, K frames, "
+                           "resolve, D2H of RGBA + 3 AOVs into page-locked arrays); bytes are per call / K"}
         else:
-            # partitioned call: per-rank DEM upload + pyramid build + K frames + resolve + NCCL gather + D2H
+            # partitioned call: DEM H2D on rank 0 + NVLink broadcast, pyramid build per rank, K frames, resolve, ONE gather per
+            # output to rank 0, D2H on rank 0 only
+            PartitionedRender(dem, 64, 64, cam, **kw, max_frames=2, min_frames=2, variance_threshold=1e30).close()   # warm NCCL + allocator
             dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            pr2 = PartitionedRender(dem, W, Hh, cam, **kw, max_frames=K, min_frames=K, variance_threshold=1e30)
+            pr2 = PartitionedRender(dem, W, Hh, cam, **kw, **atm, max_frames=K, min_frames=K, variance_threshold=1e30)
             pr2.render_frames(K)
-            imgs = pr2.resolve(aovs=True)
+            imgs = pr2.resolve(aovs=True, dst=0)
             torch.cuda.synchronize()
             dist.barrier()
             dt = time.perf_counter() - t0
@@ -315,33 +381,25 @@ def main():
             dist.all_reduce(r)
             tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            d2h = sum(v.nbytes for v in imgs.values())
+            d2h = sum(v.nbytes for v in imgs.values()) if imgs else 0
             e2e = {"value": float(r.item()) / float(tt.item()) / 1e6, "unit": "Mrays/s",
-                   "h2d_bytes_per_step": dem.nbytes * world / K, "d2h_bytes_per_step": d2h / K,
+                   "h2d_bytes_per_step": dem.nbytes / K, "d2h_bytes_per_step": d2h / K,
                    "call_ms": float(tt.item()) * 1e3, "frames": K,
-                   "note": "partitioned render incl. per-rank DEM upload, NCCL row gather and D2H on every rank"}
+                   "note": "partitioned render: DEM H2D on rank 0 + NCCL broadcast over NVLink, per-rank pyramid build, K frames, "
+                           "ONE NCCL gather per output to rank 0, D2H on rank 0 only (bytes counted there)"}
             pr2.close()
 
     # ---------------- SURVEY 8d secondary run: spp = 8 x 32 frames (same 256 samples per pixel, 1/8 of the per-frame state traffic) ----
     secondary = None
-    if world == 1 and not args.no_secondary:
+    if world == 1 and not args.no_secondary and args.config == "c2":
         try:
             kw8 = dict(kw)
             kw8["spp"] = 8
             pr8 = PartitionedRender(dem, W, Hh, cam, **kw8, max_frames=35, min_frames=35, variance_threshold=1e30)
-            pr8.render_frames(3)
-            torch.cuda.synchronize()
-            q0 = pr8.session.stats()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            pr8.render_frames(32)
-            e1.record()
-            torch.cuda.synchronize()
-            q1 = pr8.session.stats()
+            ms8, (p8, s8, i8, _, _), _ = time_frames(pr8, torch, dist, False, 3, 32)
             pr8.close()
-            ms8 = float(e0.elapsed_time(e1))
-            rays8 = float(sum(q1[k] - q0[k] for k in ("rays_primary", "rays_shadow", "rays_ibl")))
-            b8 = algorithmic_bytes_per_frame(W, Hh, DEM_N)
+            rays8 = p8 + s8 + i8
+            b8 = algorithmic_bytes_per_frame(W, Hh, C["dem_n"])
             peak8, _ = measured_hbm_peak()
             secondary = {"workload": "same scene, spp=8 per frame x 32 frames", "value": rays8 / (ms8 * 1e-3) / 1e6, "unit": "Mrays/s",
                          "ms_per_frame": ms8 / 32, "bytes_per_ray": b8 / (rays8 / 32),
@@ -350,36 +408,55 @@ def main():
         except Exception as exc:   # the headline stands without it
             secondary = {"error": repr(exc)[:300]}
 
+    # ---------------- C5 (7200 x 7200, spp 16, 4096^2 DEM): the frame that fills 8 GPUs, reported at every N ----------------
+    secondary_c5 = None
+    if not args.no_secondary and args.config == "c2" and os.environ.get("F3D_BENCH_C5", "1") != "0":
+        try:
+            c5 = CONFIGS["c5"]
+            dem5, cam5, kw5 = workload("c5")
+            pr5 = PartitionedRender(dem5, c5["width"], c5["height"], cam5, **kw5, max_frames=3, min_frames=3, variance_threshold=1e30)
+            ms5, (p5, s5, i5, _, _), _ = time_frames(pr5, torch, dist, distributed, 1, 2)
+            pr5.close()
+            del pr5
+            rays5 = p5 + s5 + i5
+            b5 = algorithmic_bytes_per_frame(c5["width"], c5["height"], c5["dem_n"])
+            peak5, _ = measured_hbm_peak()
+            secondary_c5 = {"workload": c5["label"] + "; 1 warm-up frame (16 steps) + 2 timed frames, resident scene", "value": rays5 / (ms5 * 1e-3) / 1e6,
+                            "unit": "Mrays/s", "n_gpus": world, "ms_per_frame": ms5 / 2, "scaling": "strong",
+                            "roofline_frac_per_gpu": b5 / (ms5 / 2 * 1e-3) / 1e9 / (peak5 * world),
+                            "note": "algorithmic bytes count the per-frame state once per frame (SURVEY 8d), so spp=16 makes the HBM "
+                                    "fraction small by construction; the Mrays/s curve over N is the point of this line"}
+        except Exception as exc:
+            secondary_c5 = {"error": repr(exc)[:300]}
+
     if rank == 0:
         ms_per_step = total_ms / K
-        b_frame = algorithmic_bytes_per_frame(W, Hh, DEM_N)
+        b_frame = algorithmic_bytes_per_frame(W, Hh, C["dem_n"])
         peak, peak_src = measured_hbm_peak()
         achieved = b_frame / (ms_per_step * 1e-3) / 1e9
-        traffic = None
-        tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists():
-            try:
-                traffic = json.loads(tp.read_text()).get("frame_dram_bytes")
-            except Exception:
-                traffic = None
+        traffic, traffic_src = measured_traffic()
         line = {
             "metric": "Mrays/s, path-traced DEM snapshot (primary+shadow+IBL rays)", "value": value, "unit": "Mrays/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"rainier-shaped {DEM_N}x{DEM_N} DEM (SURVEY 8d C2), {W}x{Hh}, spp=1 per frame, "
-                                   f"{K} frames timed (256 = the 256-spp snapshot)",
-                       "step": "one accumulation frame = k_primary + k_trace (sun list, then IBL list) + k_accum over the image",
-                       "l2": "per-frame working set (state 118 MB + DEM cells/pyramid 108 MB) exceeds the 126 MB L2; no flush",
-                       "partition": f"interleaved 16-row blocks over {world} GPU(s)", "ms_per_frame": ms_per_step,
-                       "rays_per_frame": total_rays / K, "f_shadow": n_shadow / max(n_primary, 1),
-                       "f_ibl": n_ibl / max(n_primary, 1), "nodes_per_ray": n_nodes / max(total_rays, 1)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_frame,
-                         "bytes_per_ray": b_frame / (total_rays / K),
-                         "kernel": "frame = k_primary + k_trace + k_accum (dominant: k_trace)"},
-            "clocks": clocks, "gpu_launches": 3 * K * kw["spp"], "e2e": e2e, "secondary": secondary,
-            "image_mean_rgb": float(images["rgba"][..., :3].mean()),
+            "config": config_block(args.config, W, Hh, K, world, {
+                "step": "one accumulation frame = k_primary + k_ascent (origin-cell solve, bottom-up seeds) + k_trace (seed subtrees) + "
+                        "k_accum over the image; k_ascent/k_trace/k_accum are launched once per batch of up to 4 frames",
+                "l2": "per-frame working set (state ~150 MB + DEM cells/pyramid 108 MB) exceeds the 126 MB L2; no flush",
+                "partition": f"interleaved 16-row blocks over {world} GPU(s)", "ms_per_frame": ms_per_step,
+                "rays_per_frame": total_rays / K, "f_shadow": n_shadow / max(n_primary, 1),
+                "f_ibl": n_ibl / max(n_primary, 1), "nodes_per_ray": n_nodes / max(total_rays, 1),
+                "build": _native.lib().f3d_build_info().decode()}),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
+                         "algorithmic_bytes_per_launch": b_frame, "bytes_per_ray": b_frame / (total_rays / K),
+                         "kernel": "frame = k_primary + k_ascent + k_trace + k_accum (dominant: k_trace + k_ascent, the secondary rays); "
+                                   "instruction-issue bound, see profiles/README.md"},
+            "clocks": clocks, "gpu_launches": int(n_launch / max(world, 1)), "e2e": e2e, "secondary": secondary,
+            "secondary_c5": secondary_c5, "image_mean_rgb": float(images["rgba"][..., :3].mean()),
         }
+        if distributed:
+            line["bit_identical_to_1gpu"] = identical
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(dem, cam, kw)
             if os.environ.get("F3D_BENCH_ROWS", "1") != "0" and not args.no_rows:

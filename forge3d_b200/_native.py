@@ -182,7 +182,7 @@ class TerrainOut(C.Structure):
 
 # every symbol include/forge3d_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "f3d_terrain_reference_render", "f3d_last_error", "f3d_abi_version", "f3d_device_count", "f3d_build_info",
+    "f3d_terrain_reference_render", "f3d_last_error", "f3d_abi_version", "f3d_device_count", "f3d_build_info", "f3d_host_alloc", "f3d_host_free", "f3d_cache_trim",
     "f3d_session_create", "f3d_session_render_frames", "f3d_session_variance",
     "f3d_session_resolve_device", "f3d_session_validity", "f3d_session_resolve_host", "f3d_session_frames",
     "f3d_session_stats", "f3d_session_sync", "f3d_session_last_frames_ms", "f3d_session_destroy",
@@ -208,6 +208,11 @@ def lib():
     L.f3d_terrain_reference_render.argtypes = [C.POINTER(TerrainDesc), C.POINTER(TerrainOut)]
     L.f3d_last_error.restype = C.c_char_p
     L.f3d_build_info.restype = C.c_char_p
+    L.f3d_host_alloc.restype = C.c_void_p
+    L.f3d_host_alloc.argtypes = [C.c_uint64]
+    L.f3d_host_free.argtypes = [C.c_void_p]
+    L.f3d_cache_trim.restype = C.c_uint64
+    L.f3d_cache_trim.argtypes = [C.c_int32]
     L.f3d_session_create.argtypes = [C.POINTER(TerrainDesc), vp, C.POINTER(vp)]
     L.f3d_session_render_frames.argtypes = [vp, C.c_uint32]
     L.f3d_session_variance.argtypes = [vp, fp, C.POINTER(C.c_int32)]
@@ -267,6 +272,14 @@ def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
+class DeviceHeights:
+    """A DEM that already lives in the memory of the CUDA device the session runs on (e.g. broadcast over NVLink by
+    forge3d_b200.distributed): raw device pointer of a contiguous float32 (H, W) array + whatever keeps it alive."""
+
+    def __init__(self, ptr: int, shape, keep=None):
+        self.ptr, self.shape, self.keep = int(ptr), (int(shape[0]), int(shape[1])), keep
+
+
 def make_desc(heightmap, width, height, cam, *, spacing, exaggeration, albedo, sun_azimuth_deg,
               sun_elevation_deg, sun_intensity, env_map, env_intensity, mesh_vertices, mesh_indices, spp,
               max_frames, min_frames, variance_threshold, seed, sun_color, observer_latitude_deg,
@@ -279,13 +292,18 @@ def make_desc(heightmap, width, height, cam, *, spacing, exaggeration, albedo, s
         raise ValueError(f"unsupported earth_model {earth_model!r}")          # refraction.rs:52
     if refraction_model not in REFRACTION_MODELS:
         raise ValueError(f"unsupported refraction_model {refraction_model!r}")  # refraction.rs:97
-    dem = np.ascontiguousarray(heightmap, dtype=np.float32)
-    if dem.ndim != 2:
-        raise ValueError(f"heightmap must be 2D (H, W), got shape {dem.shape}")
-    keep = [dem]
     d = TerrainDesc()
-    d.heights = _fp(dem)
-    d.dem_h, d.dem_w = dem.shape
+    if isinstance(heightmap, DeviceHeights):
+        keep = [heightmap]
+        d.heights = C.cast(C.c_void_p(heightmap.ptr), C.POINTER(C.c_float))
+        d.dem_h, d.dem_w = heightmap.shape
+    else:
+        dem = np.ascontiguousarray(heightmap, dtype=np.float32)
+        if dem.ndim != 2:
+            raise ValueError(f"heightmap must be 2D (H, W), got shape {dem.shape}")
+        keep = [dem]
+        d.heights = _fp(dem)
+        d.dem_h, d.dem_w = dem.shape
     d.spacing = (C.c_float * 2)(float(spacing[0]), float(spacing[1]))
     d.exaggeration = float(exaggeration)
     d.albedo = (C.c_float * 3)(*[float(v) for v in albedo])
@@ -362,15 +380,39 @@ def extract_sun_color(obj):
     return tuple(out)
 
 
+def host_array(shape, dtype):
+    """numpy array over page-locked memory from the library's pool (f3d_host_alloc): the device writes it with one DMA, no page
+    faults, no staging copy.  The block returns to the pool when the last view of the array is garbage-collected.  Falls back
+    to ordinary memory when the pool cannot serve (no CUDA device: the call that follows fails anyway)."""
+    import weakref
+
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    L = lib()
+    ptr = L.f3d_host_alloc(max(nbytes, 1)) if nbytes >= (1 << 16) else None
+    if not ptr:
+        return np.zeros(shape, dtype)
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    weakref.finalize(buf, L.f3d_host_free, C.c_void_p(ptr))
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr
+
+
+def cache_trim(device: int = -1) -> int:
+    """Hands the device buffers the library keeps parked for reuse back to the CUDA driver (all devices by default);
+    returns the bytes released.  Call it before giving the GPU to another allocator (torch, NCCL) in the same process."""
+    return int(lib().f3d_cache_trim(int(device)))
+
+
 def alloc_outputs(width, height, want_accum=False):
     H, W = int(height), int(width)
-    arrays = dict(rgba=np.zeros((H, W, 4), np.uint8), albedo=np.zeros((H, W, 3), np.float32),
-                  normal=np.zeros((H, W, 3), np.float32), depth=np.zeros((H, W), np.float32))
+    arrays = dict(rgba=host_array((H, W, 4), np.uint8), albedo=host_array((H, W, 3), np.float32),
+                  normal=host_array((H, W, 3), np.float32), depth=host_array((H, W), np.float32))
     o = TerrainOut()
     o.rgba = arrays["rgba"].ctypes.data_as(C.POINTER(C.c_uint8))
     o.albedo, o.normal, o.depth = _fp(arrays["albedo"]), _fp(arrays["normal"]), _fp(arrays["depth"])
     if want_accum:
-        arrays["accum"] = np.zeros((H, W, 4), np.float32)
+        arrays["accum"] = host_array((H, W, 4), np.float32)
         o.accum = _fp(arrays["accum"])
     return o, arrays
 
@@ -400,14 +442,28 @@ def hybrid_render_terrain_reference(heightmap, width, height, cam, spacing=(1.0,
                                     temperature_c=15.0, atmosphere=None, *, device=0, compat_512mib_gate=False,
                                     want_accum=False):
     """Native seam `_forge3d.hybrid_render_terrain_reference` (terrain_reference.rs:224-457) on the
-    CUDA backend.  `certificate` and `cache` are accepted and ignored (the reference ignores `cache`,
-    :291; certificates are out of scope).  `atmosphere` is an AtmosphereLutHandle, a
-    mapping or a settings object (extract_atmosphere_lut_handle, :46-210) and enables the AETHER post."""
-    _ = (certificate, cache)
+    CUDA backend.  `cache` is accepted and ignored (the reference ignores it, :291).  A truthy `certificate` raises:
+    the reference writes / assembles a render certificate for it (emit_certificate_for_kwarg) and certificates are out
+    of scope here - a drop-in must not silently skip a file the caller asked for.  `atmosphere`
+    is an AtmosphereLutHandle, a mapping or a settings object (extract_atmosphere_lut_handle, :46-210) and enables the
+    AETHER post.  Argument checks follow the PyO3 seam's order: sun_color, then seed / albedo extraction (u32 / [f32; 3]:
+    out-of-range or mis-sized values raise as PyO3's extraction does), earth / refraction models, then the atmosphere."""
+    _ = cache
+    if certificate:
+        raise NotImplementedError("certificate= is not supported by forge3d_b200 (render certificates are out of scope); "
+                                  "pass certificate=None/False")
     from .atmosphere import resolve_atmosphere
 
-    atmosphere = resolve_atmosphere(atmosphere)
     sun_rgb = (1.0, 0.97, 0.92) if sun_color is None else extract_sun_color(sun_color)
+    if not (0 <= int(seed) < 2 ** 32):
+        raise OverflowError("can't convert negative int to unsigned" if int(seed) < 0 else "Python int too large to convert to C unsigned long")
+    if len(tuple(albedo)) != 3:
+        raise ValueError(f"expected a sequence of length 3 (got {len(tuple(albedo))})")
+    if earth_model not in EARTH_MODELS:
+        raise ValueError(f"unsupported earth_model {earth_model!r}")
+    if refraction_model not in REFRACTION_MODELS:
+        raise ValueError(f"unsupported refraction_model {refraction_model!r}")
+    atmosphere = resolve_atmosphere(atmosphere)
     d, keep = make_desc(heightmap, width, height, cam, spacing=spacing, exaggeration=exaggeration, albedo=albedo,
                         sun_azimuth_deg=sun_azimuth_deg, sun_elevation_deg=sun_elevation_deg,
                         sun_intensity=sun_intensity, env_map=env_map, env_intensity=env_intensity,

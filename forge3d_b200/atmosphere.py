@@ -148,10 +148,11 @@ class AtmosphereLutHandle:
         arrays = {}
         for name, arr, vmax in (("transmittance", transmittance, 1.0), ("scattering", scattering, 65504.0), ("aerial", aerial, 1.0)):
             a = np.asarray(arr)
-            if a.dtype == np.float16:
-                a = a.view(np.uint16)
-            if a.dtype != np.uint16:
+            if a.dtype not in (np.float16, np.uint16):
                 raise TypeError(f"{name} LUT must hold RGBA16F texels (float16 or their uint16 bit patterns), got {a.dtype}")
+            # an OWNED copy: the handle is immutable, so neither the caller's array may be frozen nor may a later write
+            # to it reach the device behind the checks below
+            a = np.array(a.view(np.uint16), dtype=np.uint16, copy=True, order="C")
             if a.shape != want[name]:   # validate_runtime_luts, runtime.rs:222-235
                 raise AtmosphereError(f"invalid atmosphere configuration: runtime LUT payload dimensions {a.shape} do not "
                                       f"match metadata {want[name]}")

@@ -45,8 +45,14 @@ struct DevCache {
     std::mutex mu;
     std::multimap<size_t, void*> parked[16];
     std::unordered_map<void*, size_t> sizes;
-    size_t parked_bytes = 0;
-    static constexpr size_t kMaxParked = 24ull << 30;
+    size_t parked_bytes[16] = {};
+    // per-device cap: about one 4K session's working set (F3D_B200_CACHE_MB overrides, 0 = never park).  The process may share
+    // the device with torch / NCCL: what is parked here is invisible to them, so the cap is deliberately modest and
+    // f3d_cache_trim() hands everything back.
+    size_t cap() const {
+        static const size_t c = [] { const char* e = getenv("F3D_B200_CACHE_MB"); return e ? (size_t)std::max(atoll(e), 0ll) << 20 : (size_t)4 << 30; }();
+        return c;
+    }
 };
 DevCache g_cache;
 }  // namespace
@@ -59,7 +65,7 @@ cudaError_t cached_malloc(void** p, size_t bytes, int device) {
         auto it = m.lower_bound(bytes);
         if (it != m.end() && it->first <= bytes + bytes / 4 + 4096) {
             *p = it->second;
-            g_cache.parked_bytes -= it->first;
+            g_cache.parked_bytes[device & 15] -= it->first;
             m.erase(it);
             return cudaSuccess;
         }
@@ -70,8 +76,9 @@ cudaError_t cached_malloc(void** p, size_t bytes, int device) {
         std::vector<void*> drop;
         {
             std::lock_guard<std::mutex> lk(g_cache.mu);
-            for (auto& kv : g_cache.parked[device & 15]) { drop.push_back(kv.second); g_cache.parked_bytes -= kv.first; g_cache.sizes.erase(kv.second); }
+            for (auto& kv : g_cache.parked[device & 15]) { drop.push_back(kv.second); g_cache.sizes.erase(kv.second); }
             g_cache.parked[device & 15].clear();
+            g_cache.parked_bytes[device & 15] = 0;
         }
         for (void* q : drop) cudaFree(q);
         e = cudaMalloc(p, bytes);
@@ -91,14 +98,122 @@ void cached_free(void* p, int device, bool allow_park) {
         std::lock_guard<std::mutex> lk(g_cache.mu);
         auto it = g_cache.sizes.find(p);
         if (it != g_cache.sizes.end()) bytes = it->second;
-        if (bytes && allow_park && g_cache.parked_bytes + bytes <= DevCache::kMaxParked) {
+        if (bytes && allow_park && g_cache.parked_bytes[device & 15] + bytes <= g_cache.cap()) {
             g_cache.parked[device & 15].emplace(bytes, p);
-            g_cache.parked_bytes += bytes;
+            g_cache.parked_bytes[device & 15] += bytes;
             return;
         }
         if (bytes) g_cache.sizes.erase(it);
     }
     cudaFree(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pinned host memory.  Reading 66 MB of 1080p outputs back into freshly allocated pageable memory ran at ~4 GB/s in round 1
+// (page faults on first touch + the driver's pageable staging): 17 ms of a 40 ms call.  Two remedies:
+//   * f3d_host_alloc / f3d_host_free: a small pool of page-locked buffers.  The Python layer allocates its output arrays
+//     from it, so the copy is one DMA at PCIe speed straight into the array the caller receives;
+//   * copy_to_host: any other destination (a C caller's malloc'ed buffer) goes through two page-locked bounce buffers,
+//     the DMA of chunk i overlapping the memcpy of chunk i-1.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct HostPool {
+    std::mutex mu;
+    std::multimap<size_t, void*> parked;
+    std::unordered_map<void*, size_t> sizes;
+    size_t parked_bytes = 0;
+    static constexpr size_t kMaxParked = 1ull << 30;
+    void* bounce[2] = {nullptr, nullptr};
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    static constexpr size_t kBounce = 8ull << 20;
+};
+HostPool g_host;
+}  // namespace
+
+extern "C" void* f3d_host_alloc(uint64_t bytes) {
+    bytes = std::max<uint64_t>((bytes + 4095) & ~uint64_t(4095), 4096);
+    {
+        std::lock_guard<std::mutex> lk(g_host.mu);
+        auto it = g_host.parked.lower_bound((size_t)bytes);
+        if (it != g_host.parked.end() && it->first <= bytes + bytes / 4) {
+            void* p = it->second;
+            g_host.parked_bytes -= it->first;
+            g_host.parked.erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_host.mu);
+    g_host.sizes[p] = (size_t)bytes;
+    return p;
+}
+
+extern "C" void f3d_host_free(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_host.mu);
+        auto it = g_host.sizes.find(p);
+        if (it == g_host.sizes.end()) return;
+        if (g_host.parked_bytes + it->second <= HostPool::kMaxParked) {
+            g_host.parked.emplace(it->second, p);
+            g_host.parked_bytes += it->second;
+            return;
+        }
+        g_host.sizes.erase(it);
+    }
+    cudaFreeHost(p);
+}
+
+// Device -> host copy on `stream`, synchronous on return for pageable destinations (page-locked ones are only enqueued).
+static int copy_to_host(void* host, const void* dev, size_t bytes, cudaStream_t stream) {
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned || bytes < (1u << 20)) {
+        CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, stream));
+        return 0;
+    }
+    std::lock_guard<std::mutex> lk(g_host.mu);          // one staged copy at a time per process
+    for (int k = 0; k < 2; k++) {
+        if (!g_host.bounce[k]) CUDA_TRY(cudaHostAlloc(&g_host.bounce[k], HostPool::kBounce, cudaHostAllocDefault));
+        if (!g_host.bounce_ev[k]) CUDA_TRY(cudaEventCreateWithFlags(&g_host.bounce_ev[k], cudaEventDisableTiming));
+    }
+    const size_t nchunks = (bytes + HostPool::kBounce - 1) / HostPool::kBounce;
+    for (size_t c = 0; c <= nchunks; c++) {
+        if (c < nchunks) {
+            const size_t off = c * HostPool::kBounce, len = std::min(HostPool::kBounce, bytes - off);
+            CUDA_TRY(cudaMemcpyAsync(g_host.bounce[c & 1], (const char*)dev + off, len, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaEventRecord(g_host.bounce_ev[c & 1], stream));
+        }
+        if (c > 0) {
+            const size_t off = (c - 1) * HostPool::kBounce, len = std::min(HostPool::kBounce, bytes - off);
+            CUDA_TRY(cudaEventSynchronize(g_host.bounce_ev[(c - 1) & 1]));
+            memcpy((char*)host + off, g_host.bounce[(c - 1) & 1], len);
+        }
+    }
+    return 0;
+}
+
+// Returns every parked device buffer of `device` (all devices when negative) to the driver; returns the bytes released.
+extern "C" uint64_t f3d_cache_trim(int32_t device) {
+    std::vector<std::pair<int, void*>> drop;
+    uint64_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        for (int d = 0; d < 16; d++) {
+            if (device >= 0 && d != (device & 15)) continue;
+            for (auto& kv : g_cache.parked[d]) { drop.emplace_back(d, kv.second); bytes += kv.first; g_cache.sizes.erase(kv.second); }
+            g_cache.parked[d].clear();
+            g_cache.parked_bytes[d] = 0;
+        }
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& dp : drop) { cudaSetDevice(dp.first); cudaFree(dp.second); }
+    cudaSetDevice(cur);
+    cudaGetLastError();
+    return bytes;
 }
 
 extern "C" const char* f3d_last_error(void) { return g_err; }
@@ -436,16 +551,25 @@ int build_device_terrain(const float* h_heights, uint32_t w, uint32_t h, float e
         float*& h; uint32_t*& f; cudaStream_t st; int dev;
         ~Scratch() { if (h || f) cudaStreamSynchronize(st); cached_free(h, dev); cached_free(f, dev); }
     } scratch{d_h, d_flag, stream, T->device};
-    CUDA_TRY(cached_malloc((void**)&d_h, n * sizeof(float), T->device));
+    // `h_heights` may already live on this device (a DEM broadcast over NVLink by the multi-GPU launcher): read it in place
+    const float* src_dev = nullptr;
+    {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, h_heights) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged))
+            src_dev = h_heights;
+        cudaGetLastError();
+    }
+    if (!src_dev) CUDA_TRY(cached_malloc((void**)&d_h, n * sizeof(float), T->device));
     CUDA_TRY(cached_malloc((void**)&d_flag, sizeof(uint32_t), T->device));
     CUDA_TRY(cached_malloc((void**)&T->cells, (size_t)cw * ch * sizeof(float4), T->device));
     CUDA_TRY(cached_malloc((void**)&T->mm_base, T->mm_total * sizeof(float2), T->device));
     CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(uint32_t), stream));
-    CUDA_TRY(cudaMemcpyAsync(d_h, h_heights, n * sizeof(float), cudaMemcpyHostToDevice, stream));
-    k_check_finite<<<(unsigned)std::min<size_t>((n + 255) / 256, 1184), 256, 0, stream>>>(d_h, n, d_flag);
+    if (!src_dev) CUDA_TRY(cudaMemcpyAsync(d_h, h_heights, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    const float* heights_dev = src_dev ? src_dev : d_h;
+    k_check_finite<<<(unsigned)std::min<size_t>((n + 255) / 256, 1184), 256, 0, stream>>>(heights_dev, n, d_flag);
     dim3 blk(32, 8);
     dim3 g0((T->dims[0][0] + 31) / 32, (T->dims[0][1] + 7) / 8);
-    k_build_level0<<<g0, blk, 0, stream>>>(d_h, w, h, T->dims[0][0], T->dims[0][1], ex, T->cells, T->mm_base);
+    k_build_level0<<<g0, blk, 0, stream>>>(heights_dev, w, h, T->dims[0][0], T->dims[0][1], ex, T->cells, T->mm_base);
     *launches += 2;
     for (int l = 1; l < T->nlevels; l++) {
         dim3 g((T->dims[l][0] + 31) / 32, (T->dims[l][1] + 7) / 8);
@@ -593,7 +717,7 @@ static void session_free(f3d_session* s) {
     for (auto& bs : s->sets)
         if (bs.stream) cudaStreamSynchronize(bs.stream);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    if (s->d_sync) cudaFree(s->d_sync);
+    cached_free(s->d_sync, s->device, false);
     const int dv = s->device;
     const bool ipc = s->P.part_world > 1u;                  // resv images may be mapped by peers: never park them
     s->terrain.release();
@@ -841,10 +965,12 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     P.peer_up = nullptr; P.peer_down = nullptr;
     P.sync_local = nullptr; P.peer_sync_up = nullptr; P.peer_sync_down = nullptr; P.sync_error = nullptr;
     if (P.part_world > 1u) {
-        CUDA_TRY(cudaMalloc(&s->d_sync, 8 * sizeof(uint32_t)));
+        CUDA_TRY(cached_malloc((void**)&s->d_sync, 8 * sizeof(uint32_t), s->device));      // IPC-shared: freed with allow_park = false
         CUDA_TRY(cudaMemsetAsync(s->d_sync, 0, 8 * sizeof(uint32_t), s->stream));
         P.sync_local = s->d_sync;
         P.sync_error = s->d_sync + 3;
+        const char* te = getenv("F3D_B200_SYNC_TIMEOUT_MS");
+        P.sync_timeout_ns = (unsigned long long)std::max(te ? atoll(te) : 2000ll, 1ll) * 1000000ull;
     }
 
     if (d->atmosphere) {
@@ -995,6 +1121,16 @@ extern "C" int f3d_session_frames(const f3d_session* s, uint32_t* frames) {
     return 0;
 }
 
+// A neighbour wait of the multi-GPU frame barrier timed out at some point: nothing rendered since can be trusted.
+static int check_sync_error(f3d_session* s) {
+    if (!s->d_sync) return 0;
+    uint32_t timed_out = 0;
+    CUDA_TRY(cudaMemcpyAsync(&timed_out, s->d_sync + 3, sizeof timed_out, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (timed_out) return fail(F3D_ERR_DEVICE, "multi-GPU frame barrier timed out waiting for a neighbour rank (peer died?)");
+    return 0;
+}
+
 extern "C" int f3d_session_variance(f3d_session* s, float* vmax, int32_t* nonfinite) {
     if (!s || !vmax || !nonfinite) return fail(F3D_ERR_ARGUMENT, "null argument");
     CUDA_TRY(cudaSetDevice(s->device));
@@ -1007,7 +1143,7 @@ extern "C" int f3d_session_variance(f3d_session* s, float* vmax, int32_t* nonfin
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     memcpy(vmax, &s->h_gate[0], 4);
     *nonfinite = (int32_t)s->h_gate[1];
-    return 0;
+    return check_sync_error(s);
 }
 
 // AetherPostPass::new (aether_post.rs:40-291): validate the settings and LUTs, upload the three tables.
@@ -1060,14 +1196,11 @@ static int resolve_device_impl(f3d_session* s, void* d_rgba, void* d_albedo, voi
         s->launches++;
     }
     CUDA_TRY(cudaGetLastError());
+    if (!check_validity) { if (int rc2 = check_sync_error(s)) return rc2; }
     if (check_validity) {
         CUDA_TRY(cudaMemcpyAsync(s->h_gate + 2, s->d_gate + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
-        if (s->d_sync) {
-            uint32_t timed_out = 0;
-            CUDA_TRY(cudaMemcpy(&timed_out, s->d_sync + 3, sizeof timed_out, cudaMemcpyDeviceToHost));
-            if (timed_out) return fail(F3D_ERR_DEVICE, "multi-GPU frame barrier timed out waiting for a neighbour rank (peer died?)");
-        }
+        if (int rc2 = check_sync_error(s)) return rc2;
         if (s->h_gate[2]) return fail(F3D_ERR_RENDER, "terrain PT reservoir bookkeeping produced non-finite values");
         const bool require = s->sun_el_deg > 0.0f && s->sun_intensity > 0.0f &&
                              (s->sun_color[0] > 0.0f || s->sun_color[1] > 0.0f || s->sun_color[2] > 0.0f);
@@ -1128,12 +1261,12 @@ extern "C" int f3d_session_resolve_host(f3d_session* s, f3d_terrain_out* out) {
     rc = resolve_device_impl(s, out->rgba ? s->d_rgba : nullptr, out->albedo ? s->d_albedo : nullptr,
                              out->normal ? s->d_normal : nullptr, out->depth ? s->d_depth : nullptr, 1);
     if (rc) return rc;
-    // Device -> caller memory directly: the driver pipelines pageable destinations through its own pinned
-    // staging, and pinned destinations (bench.py) are written by DMA without an extra host copy.
+    // Device -> caller memory: page-locked destinations (the Python layer's arrays come from f3d_host_alloc) are written by one
+    // DMA each; pageable ones go through the bounce buffers of copy_to_host.
     uint64_t pulled = 0;
     auto pull = [&](void* host, const void* dev, size_t bytes) -> int {
         if (!host) return 0;
-        CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+        if (int rc2 = copy_to_host(host, dev, bytes, s->stream)) return rc2;
         pulled += bytes;
         return 0;
     };
@@ -1302,12 +1435,16 @@ extern "C" int f3d_trace_rays(const float* heights, uint32_t w, uint32_t h, cons
     const size_t smem = (size_t)depth * kTraceThreads * 4;
     float4* d_rays = nullptr; uint8_t* d_hit = nullptr; float* d_t = nullptr; float* d_n = nullptr;
     unsigned long long* d_nodes = nullptr;
-    auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_hit); cudaFree(d_t); cudaFree(d_n); cudaFree(d_nodes); T.release(); };
+    auto cleanup = [&]() {
+        cudaDeviceSynchronize();
+        cached_free(d_rays, device); cached_free(d_hit, device); cached_free(d_t, device); cached_free(d_n, device); cached_free(d_nodes, device);
+        T.release();
+    };
     if (nodes_popped) *nodes_popped = 0;
     if (n) {
-        if (cudaMalloc(&d_rays, n * 32) != cudaSuccess || cudaMalloc(&d_hit, n) != cudaSuccess ||
-            cudaMalloc(&d_t, n * 4) != cudaSuccess || cudaMalloc(&d_n, n * 12) != cudaSuccess ||
-            cudaMalloc(&d_nodes, 8) != cudaSuccess) {
+        if (cached_malloc((void**)&d_rays, n * 32, device) != cudaSuccess || cached_malloc((void**)&d_hit, n, device) != cudaSuccess ||
+            cached_malloc((void**)&d_t, n * 4, device) != cudaSuccess || cached_malloc((void**)&d_n, n * 12, device) != cudaSuccess ||
+            cached_malloc((void**)&d_nodes, 8, device) != cudaSuccess) {
             cleanup();
             return fail(F3D_ERR_DEVICE, "device allocation failed");
         }

@@ -84,17 +84,29 @@ struct FrameParams {
     uint32_t* peer_sync_up;     // the up neighbour's sync array (I am its "below" rank -> slot 2)
     uint32_t* peer_sync_down;   // the down neighbour's sync array (I am its "above" rank -> slot 1)
     uint32_t* sync_error;       // set to 1 if a wait timed out (host raises)
+    unsigned long long sync_timeout_ns;   // budget of one neighbour wait (F3D_B200_SYNC_TIMEOUT_MS, default 2000)
 };
 
-// Spin until both neighbours have completed `need` frames.  One thread per CTA polls local memory; a
-// 2-second clock budget turns a dead peer into an error instead of a hung GPU.
+// Spin until both neighbours have completed `need` frames.  One thread per CTA polls local memory; a wall-clock budget
+// (FrameParams::sync_timeout_ns, default 2 s, measured with %globaltimer) turns a dead peer into an error instead of a hung
+// GPU: the flag is sticky, and f3d_session_variance / every resolve fail when it is set, so a frame shaded with stale halo
+// rows can never be returned as a result.
+__device__ __forceinline__ unsigned long long global_ns() {
+#if defined(__CUDA_ARCH__)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#else
+    return 0ull;
+#endif
+}
 __device__ __forceinline__ void wait_neighbours(const FrameParams& P, uint32_t need) {
     if (P.part_world > 1u && need > 0u && P.sync_local != nullptr && (P.peer_sync_up != nullptr || P.peer_sync_down != nullptr)) {
         if (threadIdx.x == 0) {
             const volatile uint32_t* f = P.sync_local;
-            const long long t0 = clock64();
+            const unsigned long long t0 = global_ns();
             while (f[1] < need || f[2] < need) {
-                if (clock64() - t0 > 4000000000ll) { atomicExch(P.sync_error, 1u); break; }
+                if (global_ns() - t0 > P.sync_timeout_ns) { atomicExch(P.sync_error, 1u); break; }
                 __nanosleep(200);
             }
             __threadfence_system();

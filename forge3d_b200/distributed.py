@@ -159,6 +159,41 @@ def wavefront_partitioned(scene, width: int, height: int, spp_frames: int, *, gr
     return out[0], out[1]
 
 
+def gather_rows_to(local_image, height: int, dst: int = 0, group=None, block_rows: int = 0):
+    """ONE gather of every rank's packed owned rows to rank `dst`; that rank returns the assembled (H, ...) image, the others
+    None.  NCCL on CUDA tensors, gloo on CPU tensors."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    counts = row_counts(height, world, block_rows)
+    mx = max(counts)
+    rows = torch.as_tensor(owned_rows(height, world, rank, block_rows), device=local_image.device)
+    packed = local_image.new_zeros((mx,) + tuple(local_image.shape[1:]))
+    packed[: rows.numel()] = local_image[rows]
+    parts = [torch.empty_like(packed) for _ in range(world)] if rank == dst else None
+    dist.gather(packed.contiguous(), parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return assemble(parts, height, world, block_rows)
+
+
+def _to_host(t):
+    """Device tensor -> numpy array in page-locked memory from the library's pool (_native.host_array): one DMA, no pageable
+    bounce, no first-touch page faults; the block goes back to the pool when the array is garbage-collected."""
+    import torch
+
+    from . import _native
+
+    if t.device.type != "cuda":
+        return t.numpy()
+    arr = _native.host_array(tuple(t.shape), np.dtype(str(t.dtype).replace("torch.", "")))
+    torch.from_numpy(arr).copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return arr
+
+
 class PartitionedRender:
     """One rank's share of a partitioned render (CUDA + NCCL)."""
 
@@ -166,6 +201,7 @@ class PartitionedRender:
         import torch
         import torch.distributed as dist
 
+        from . import _native
         from .session import Session
 
         self.torch, self.dist, self.group = torch, dist, group
@@ -175,17 +211,29 @@ class PartitionedRender:
         self.width, self.height, self.block_rows = int(width), int(height), int(block_rows)
         self.device = torch.cuda.current_device()
         self.stream = torch.cuda.current_stream()
+        if self.world > 1:
+            # The DEM crosses PCIe ONCE (rank 0) and reaches the other GPUs over NVLink (one NCCL broadcast); every session
+            # then reads it in place instead of staging its own pageable host copy.
+            shape = tuple(np.shape(heightmap))
+            if self.rank == 0:
+                host = torch.from_numpy(np.ascontiguousarray(heightmap, dtype=np.float32))
+                dem_dev = host.to("cuda", non_blocking=False)
+            else:
+                dem_dev = torch.empty(shape, dtype=torch.float32, device="cuda")
+            dist.broadcast(dem_dev, src=0, group=group)
+            self._dem_dev = dem_dev
+            heightmap = _native.DeviceHeights(dem_dev.data_ptr(), shape, keep=dem_dev)
         # torch's default stream has handle 0, which the C ABI reads as "create your own stream":
         # pass cudaStreamLegacy (0x1) so kernels, torch events and NCCL share one stream.
         self.session = Session(heightmap, width, height, cam, device=self.device,
                                cuda_stream=self.stream.cuda_stream or 1, part_rank=self.rank, part_world=self.world,
                                part_block_rows=block_rows, **scene_kw)
-        self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
         if self.world > 1:
-            handles = [None] * self.world
-            dist.all_gather_object(handles, self.session.ipc_export(), group=group)
-            self.session.ipc_import(b"".join(handles))
-            dist.barrier(group=group)
+            # CUDA-IPC handles of the reservoir images and the frame-barrier words: one all-gather of 192 bytes per rank
+            mine = torch.frombuffer(bytearray(self.session.ipc_export()), dtype=torch.uint8).cuda()
+            every = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(every, mine, group=group)
+            self.session.ipc_import(every.cpu().numpy().tobytes())
 
     def render_frames(self, n: int) -> None:
         """n accumulation frames, enqueued back to back; with world > 1 the cross-GPU ordering is done
@@ -200,9 +248,9 @@ class PartitionedRender:
             v, bad = float(t[0]), bool(t[1] > 0)
         return v, bad
 
-    def resolve(self, aovs: bool = True) -> Dict[str, "np.ndarray"]:
-        """Resolve owned rows on the device, then ONE all-gather per output; returns numpy images
-        on every rank (rank 0 is the consumer)."""
+    def resolve(self, aovs: bool = True, dst=None):
+        """Resolve owned rows on the device, then ONE collective per output.  dst=None: all-gather, every rank returns the
+        numpy images; dst=r: gather to rank r only (the consumer), the other ranks return None and copy nothing to the host."""
         torch = self.torch
         H, W = self.height, self.width
         rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
@@ -211,16 +259,36 @@ class PartitionedRender:
             bufs["albedo"] = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
             bufs["normal"] = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
             bufs["depth"] = torch.zeros((H, W), dtype=torch.float32, device="cuda")
-        self.session.resolve_device(rgba.data_ptr(), bufs["albedo"].data_ptr() if aovs else 0,
-                                    bufs["normal"].data_ptr() if aovs else 0,
-                                    bufs["depth"].data_ptr() if aovs else 0, check_validity=True)
-        if self.world > 1:   # world == 1: the session itself raised
-            check_validity_across_ranks(*self.session.validity(), group=self.group, device="cuda")
+        err = None
+        try:
+            self.session.resolve_device(rgba.data_ptr(), bufs["albedo"].data_ptr() if aovs else 0,
+                                        bufs["normal"].data_ptr() if aovs else 0,
+                                        bufs["depth"].data_ptr() if aovs else 0, check_validity=True)
+        except RuntimeError as exc:      # every rank must reach the collectives below, or the others hang in them
+            err = exc
+        if self.world > 1:
+            any_valid, required = self.session.validity() if err is None else (False, False)
+            flags = torch.tensor([1 if err is not None else 0, 1 if any_valid else 0], dtype=torch.int32, device="cuda")
+            self.dist.all_reduce(flags, op=self.dist.ReduceOp.MAX, group=self.group)
+            if err is not None:
+                raise err
+            if int(flags[0]) != 0:
+                raise RuntimeError("another rank of the partitioned render failed in resolve (see its error)")
+            if required and int(flags[1]) == 0:
+                raise RuntimeError(NO_VALID_RESERVOIRS)
+        elif err is not None:
+            raise err
         out = {}
         for k, t in bufs.items():
-            full = gather_rows(t, H, self.group, self.block_rows) if self.world > 1 else t
-            out[k] = full.cpu().numpy()
-        return out
+            if self.world == 1:
+                full = t
+            elif dst is None:
+                full = gather_rows(t, H, self.group, self.block_rows)
+            else:
+                full = gather_rows_to(t, H, int(dst), self.group, self.block_rows)
+            if full is not None:
+                out[k] = _to_host(full) if dst is not None else full.cpu().numpy()
+        return out if (self.world == 1 or dst is None or self.rank == int(dst)) else None
 
     def close(self):
         # peers store halo rows and barrier flags into this rank's memory: nobody may free before everybody is done

@@ -101,10 +101,14 @@ class Session:
         buf = (C.c_uint8 * len(all_handles)).from_buffer_copy(all_handles)
         _native.check(self._L.f3d_session_ipc_import(self._h, buf))
 
-    def close(self) -> None:
+    def close(self, trim: bool = False) -> None:
+        """Destroys the session.  Its device buffers are parked in the library's cache for the next session (bounded, see
+        f3d_cache_trim in include/forge3d_b200.h); trim=True hands them straight back to the CUDA driver instead."""
         if self._h:
             self._L.f3d_session_destroy(self._h)
             self._h = C.c_void_p()
+            if trim:
+                self._L.f3d_cache_trim(-1)
 
     def __enter__(self):
         return self

@@ -62,7 +62,7 @@ typedef struct f3d_atmosphere {
 
 /* Replaces TerrainReferenceDesc, render_terrain.rs:239-282. */
 typedef struct f3d_terrain_desc {
-    const float* heights;          /* host, row-major dem_h x dem_w (desc.heights) */
+    const float* heights;          /* row-major dem_h x dem_w (desc.heights); host memory, or memory of `device` (read in place) */
     uint32_t dem_w, dem_h;
     float spacing[2];
     float exaggeration;
@@ -124,6 +124,16 @@ int f3d_device_count(void);
  * No reference counterpart (the reference ships one wgpu pipeline); forge3d_b200/build.py and bench.py compare it so that
  * an A/B variant build can never pass for the validated default. */
 const char* f3d_build_info(void);
+
+/* Page-locked host memory from a small pool inside the library.  Output buffers allocated here are filled by one DMA at PCIe
+ * speed; any other host pointer works too (the library bounces it through page-locked staging).  Replaces the reference's
+ * mapped read-back buffers (render_terrain.rs:1339-1393 reads wgpu MAP_READ staging buffers).  NULL when no CUDA device. */
+void* f3d_host_alloc(uint64_t bytes);
+void f3d_host_free(void* p);
+/* The library parks freed device buffers (<= 4 GiB per device, F3D_B200_CACHE_MB overrides, 0 disables) so that back-to-back
+ * calls do not pay cudaMalloc's page-table work again; this returns them to the driver (device < 0: every device).  Returns the
+ * bytes released.  No reference counterpart (wgpu owns its allocator). */
+uint64_t f3d_cache_trim(int32_t device);
 
 /* ---- session API: the same render split at the reference driver-loop's joints, so a host
  * (bench, multi-GPU launcher) can keep inputs resident and time the frame loop alone. ---- */

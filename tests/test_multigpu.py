@@ -213,3 +213,75 @@ def test_wavefront_tracer_partition_over_nccl_is_bit_identical():
     for rank, hdr, rgba, err in results:
         assert np.array_equal(hdr.view(np.uint32), whole_hdr.view(np.uint32)) and np.array_equal(rgba, whole_rgba), rank
         assert "executed 1 wavefront iteration" in err, (rank, err)
+
+
+def _ipc_worker(rank, world, width, height, frames, block_rows, inbox, outbox, result_q):
+    """One rank of a partitioned render WITHOUT NCCL: plain Session + CUDA-IPC handles exchanged through pipes, every rank
+    on device 0.  The two processes time-share the GPU, so a neighbour wait costs a context time slice - slow, but it drives
+    exactly the product path of a real multi-GPU run: peer mappings, halo stores and the frame flags inside k_primary."""
+    from forge3d_b200 import distributed as D
+    from forge3d_b200.session import Session
+
+    dem = H.golden_dem()
+    kw = {**H.scene_kwargs(dem), "max_frames": frames, "min_frames": frames, "variance_threshold": 1e30}
+    s = Session(dem, width, height, H.CAM, device=0, part_rank=rank, part_world=world, part_block_rows=block_rows, **kw)
+    outbox.put((rank, s.ipc_export()))
+    handles = inbox.get(timeout=120)
+    s.ipc_import(handles)
+    outbox.put((rank, "imported"))
+    assert inbox.get(timeout=120) == "go"
+    for _ in range(frames):          # frame by frame: a wait then always refers to work its neighbour has already been given
+        s.render_frames(1)
+    s.sync()
+    var, bad = s.variance()
+    out = s.resolve_host()
+    rows = D.owned_rows(height, world, rank, block_rows)
+    result_q.put((rank, {k: np.array(out[k][rows]) for k in ("rgba", "depth", "normal", "albedo")}, var, bad))
+    assert inbox.get(timeout=120) == "done"      # nobody frees memory a peer may still store into
+    s.close()
+
+
+def test_two_ranks_on_one_device_over_cuda_ipc_are_bit_identical():
+    """The multi-GPU exact mode on a ONE-GPU box: two processes, both on device 0, linked by CUDA IPC exactly as two GPUs
+    are (forge3d_b200.session ipc_export / ipc_import), render interleaved 16-row blocks; the assembled image must equal the
+    one-session render bit for bit.  This is the test the driver's single-GPU run can execute; the NCCL tests above need
+    2-4 devices."""
+    import torch.multiprocessing as mp
+
+    from forge3d_b200 import _native
+    from forge3d_b200 import distributed as D
+
+    world, width, height, frames, block_rows = 2, 96, 80, 12, 16
+    dem = H.golden_dem()
+    kw = {**H.scene_kwargs(dem), "max_frames": frames, "min_frames": frames, "variance_threshold": 1e30}
+    ref = _native.hybrid_render_terrain_reference(dem, width, height, H.CAM, **kw)
+    ctx = mp.get_context("spawn")
+    inboxes = [ctx.Queue() for _ in range(world)]
+    outbox, result_q = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_ipc_worker, args=(r, world, width, height, frames, block_rows, inboxes[r], outbox, result_q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        exported = dict(outbox.get(timeout=300) for _ in range(world))
+        blob = b"".join(exported[r] for r in range(world))
+        for q in inboxes:
+            q.put(blob)
+        for _ in range(world):
+            assert outbox.get(timeout=300)[1] == "imported"
+        for q in inboxes:
+            q.put("go")
+        parts = dict((r, (imgs, var, bad)) for r, imgs, var, bad in (result_q.get(timeout=600) for _ in range(world)))
+        for q in inboxes:
+            q.put("done")
+    finally:
+        for p in procs:
+            p.join(timeout=120)
+    assert all(p.exitcode == 0 for p in procs)
+    for key in ("rgba", "depth", "normal", "albedo"):
+        full = np.zeros_like(ref[key])
+        for r in range(world):
+            full[D.owned_rows(height, world, r, block_rows)] = parts[r][0][key]
+        assert np.array_equal(full.view(np.uint8), np.ascontiguousarray(ref[key]).view(np.uint8)), key
+    assert np.float32(max(parts[r][1] for r in range(world))) == np.float32(ref["variance"])
+    assert not any(parts[r][2] for r in range(world))
