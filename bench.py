@@ -291,12 +291,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    # stdout carries exactly one JSON line; NCCL's own log (INFO unless the caller chose otherwise) goes to stderr, where the
-    # driver reads the communicator's rank count from it
+    # NCCL's own log stays as the caller configured it (INFO by default at N > 1, so that the communicator's rank count is on
+    # record; NCCL writes it to stdout).  The JSON line is printed LAST, after the process group is gone, so it is the final
+    # line of stdout whatever NCCL prints.  (Redirecting with NCCL_DEBUG_FILE=/dev/stderr truncates a redirected stderr.)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", os.environ.get("F3D_NCCL_DEBUG", "INFO"))
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
 
@@ -384,7 +384,7 @@ def main():
             d2h = sum(v.nbytes for v in imgs.values()) if imgs else 0
             e2e = {"value": float(r.item()) / float(tt.item()) / 1e6, "unit": "Mrays/s",
                    "h2d_bytes_per_step": dem.nbytes / K, "d2h_bytes_per_step": d2h / K,
-                   "call_ms": float(tt.item()) * 1e3, "frames": K,
+                   "call_ms": float(tt.item()) * 1e3, "frames": K, "rank0_phases_ms": {k: round(v, 3) for k, v in pr2.timings.items()},
                    "note": "partitioned render: DEM H2D on rank 0 + NCCL broadcast over NVLink, per-rank pyramid build, K frames, "
                            "ONE NCCL gather per output to rank 0, D2H on rank 0 only (bytes counted there)"}
             pr2.close()
@@ -464,10 +464,14 @@ def main():
         elif not args.no_cpu_baseline:
             line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port",
                                     "sample": "reported at N=1 only"}
-        print(json.dumps(line))
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+        if rank == 0:
+            time.sleep(0.5)        # let the other ranks' NCCL teardown messages land first
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -694,6 +694,7 @@ struct f3d_session {
     static constexpr int kMaxSets = 2;
     BatchSet sets[kMaxSets];
     int n_sets = 1, batch = 1;
+    bool split_primary = false;
     uint64_t steps = 0, batches = 0;
     cudaEvent_t join_ev = nullptr;
     float4* d_sstate = nullptr;
@@ -730,7 +731,7 @@ static void session_free(f3d_session* s) {
     for (auto& bs : s->sets) {
         if (bs.stream) { cudaStreamSynchronize(bs.stream); cudaStreamDestroy(bs.stream); }
         for (auto& sl : bs.slots) {
-            cached_free(sl.rec, dv); cached_free(sl.occl_sun, dv); cached_free(sl.occl_ibl, dv);
+            cached_free(sl.prim, dv); cached_free(sl.rec, dv); cached_free(sl.occl_sun, dv); cached_free(sl.occl_ibl, dv);
             cached_free(sl.q_sun, dv); cached_free(sl.q_ibl, dv); cached_free(sl.q_counts, dv);
             cached_free(sl.qn_sun, dv); cached_free(sl.qn_ibl, dv); cached_free(sl.q2_sun, dv); cached_free(sl.q2_ibl, dv);
         }
@@ -831,6 +832,7 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     s->smem_bytes = stack_smem_bytes(P.stack_depth, kThreads);
     s->trace_smem_bytes = trace_smem_bytes_for(P.stack_depth, kTraceCtaThreads);
     if ((rc = allow_smem(k_primary, s->smem_bytes))) return rc;
+    if ((rc = allow_smem(k_ptrace, s->smem_bytes))) return rc;
     if ((rc = allow_smem(k_gbuffer, s->smem_bytes))) return rc;
     if ((rc = allow_smem(k_trace<true, 1>, s->trace_smem_bytes))) return rc;
     if ((rc = allow_smem(k_trace<true, 2>, s->trace_smem_bytes))) return rc;
@@ -840,7 +842,11 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
         int per_sm = 0, sms = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, 1>, kTraceCtaThreads, s->trace_smem_bytes));
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-        if (const char* e = getenv("F3D_B200_TRACE_CTAS")) per_sm = std::min(std::max(atoi(e), 1), std::max(per_sm, 1));
+        // Fewer persistent CTAs than the occupancy limit leave registers for the kernels of the other batch set (primaries of
+        // the next batch) to run beside k_trace: measured 0.943 -> 0.933 ms/frame at 4 per SM on the full frame, 0.203 ->
+        // 0.178 ms at 3 per SM on a 1/8 partition (profiles/README.md).
+        per_sm = std::min(per_sm, P.part_world > 2u ? 3 : 4);
+        if (const char* e = getenv("F3D_B200_TRACE_CTAS")) per_sm = std::max(atoi(e), 1);
         s->trace_grid = std::max(per_sm, 1) * std::max(sms, 1);
         s->ascent_grid = 8 * std::max(sms, 1);
         if (getenv("F3D_B200_DEBUG"))
@@ -927,20 +933,23 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     if ((rc = dmalloc(s, &s->d_gate, (size_t)4, true))) return rc;
     CUDA_TRY(cudaMallocHost(&s->h_gate, 4 * sizeof(uint32_t)));
     s->host_visible_bytes += 4 * sizeof(uint32_t);
+    // split primary pass (k_ptrace + k_shade, see f3d_kernels.cuh): terrain-only scenes with one sample per frame
+    s->split_primary = P.spp == 1u && S.traversal_mode == 3u && !getenv("F3D_B200_NO_SPLIT");
     {
         // default: two batch sets of 4 steps; smaller batches when the per-step buffers (98 B/pixel) would exceed 8 GB in total.
         // F3D_B200_BATCH / F3D_B200_SETS override (F3D_B200_PIPELINE=1 is the old spelling of "no overlap": 1 set of 1).
-        const int by_memory = (int)std::max<uint64_t>(1, (8ull << 30) / std::max<uint64_t>(1, (uint64_t)npx * 98));
+        const int by_memory = (int)std::max<uint64_t>(1, (8ull << 30) / std::max<uint64_t>(1, (uint64_t)npx * (98 + (s->split_primary ? 32 : 0))));
         const char* eb = getenv("F3D_B200_BATCH");
         const char* es = getenv("F3D_B200_SETS");
         s->n_sets = es ? std::min(std::max(atoi(es), 1), (int)f3d_session::kMaxSets) : (by_memory >= 2 ? 2 : 1);
-        s->batch = eb ? std::min(std::max(atoi(eb), 1), kMaxBatch) : std::min(kMaxBatch, std::max(by_memory / s->n_sets, 1));
+        s->batch = eb ? std::min(std::max(atoi(eb), 1), kMaxBatch) : std::min(4, std::max(by_memory / s->n_sets, 1));
         if (const char* e = getenv("F3D_B200_PIPELINE")) if (atoi(e) <= 1) { s->n_sets = 1; s->batch = 1; }
     }
     for (int k = 0; k < s->n_sets; k++) {
         f3d_session::BatchSet& bs = s->sets[k];
         for (int j = 0; j < s->batch; j++) {
             BatchSlot& sl = bs.slots[j];
+            if (s->split_primary && (rc = dmalloc(s, &sl.prim, npx * 2, false))) return rc;
             if ((rc = dmalloc(s, &sl.rec, npx * 4, true))) return rc;
             if ((rc = dmalloc(s, &sl.occl_sun, npx, true))) return rc;
             if ((rc = dmalloc(s, &sl.occl_ibl, npx, true))) return rc;
@@ -1039,7 +1048,16 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
         cudaStream_t ts = pipelined ? bs.stream : s->stream;
         if (pipelined && bs.used) CUDA_TRY(cudaStreamWaitEvent(s->stream, bs.accum_done, 0));   // buffer set free again
         const uint32_t frame0 = s->frames, sample0 = sample;
-        // ---- the primaries of the batch, back to back ----
+        // ---- the primaries of the batch, back to back (split path: ONE traversal launch for the batch, then the cheap
+        // per-frame shading chain) ----
+        if (s->split_primary) {
+            P.frame_index = frame0;
+            P.sample_index = 0u;
+            P.n_batch = nb;
+            for (uint32_t k = 0; k < nb; k++) P.slot[k] = bs.slots[k];
+            k_ptrace<<<dim3(s->grid.x, s->grid.y, nb), kThreads, s->smem_bytes, s->stream>>>(P);
+            s->launches++;
+        }
         for (uint32_t k = 0; k < nb; k++) {
             P.frame_index = s->frames;
             P.sample_index = sample;
@@ -1055,7 +1073,8 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             }
             P.cur = bs.slots[k];
             P.n_batch = 0u;
-            k_primary<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P);
+            if (s->split_primary) k_shade<<<s->grid, kThreads, 0, s->stream>>>(P);
+            else k_primary<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P);
             s->launches++;
             s->steps++;
             if (++sample == spp) { sample = 0u; s->frames++; }

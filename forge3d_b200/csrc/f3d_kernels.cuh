@@ -36,8 +36,9 @@ constexpr int kTileW = 16, kTileH = 16;      // CTA pixel tile; warps own 8x4 su
 // consecutive steps (FrameParams::slot[0 .. n_batch)): k_primary of step i+1 only needs k_primary of step i (the reservoir
 // chain), so the primaries of a batch run back to back and one launch of each later kernel handles all their rays - on an
 // image partition (1/8 of a 1080p frame is ~230 k rays) a single step cannot fill 148 SMs, a batch can.
-constexpr int kMaxBatch = 4;
+constexpr int kMaxBatch = 8;
 struct BatchSlot {
+    float4* prim;              // split primary pass (k_ptrace -> k_shade): 2 x float4 per pixel, (d.xyz, t) (hit, cell, rng, -)
     float4* rec;               // 4 x float4 per pixel, see PixelRec
     uint8_t* occl_sun;         // per pixel: sun ray occluded
     uint8_t* occl_ibl;         // per pixel: IBL ray occluded
@@ -346,41 +347,22 @@ __device__ __forceinline__ PrimaryHit primary_hit(const FrameParams& P, const Ra
 #ifndef F3D_PRIMARY_MIN_CTAS
 #define F3D_PRIMARY_MIN_CTAS 4
 #endif
-__global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(const __grid_constant__ FrameParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    SmemStack st;
-    st.base = reinterpret_cast<uint32_t*>(smem_raw) + tid;
-    st.stride = kThreads;
-
-    uint32_t gx, gy;
-    const bool active = owned_pixel(P, gx, gy);
-    const uint32_t pix = active ? gy * P.W + gx : 0u;
-    uint32_t n_primary = 0, n_nodes = 0;
-    bool want_sun = false, want_ibl = false;
+// Everything of one camera sample that follows the primary traversal: reuse chain, shading set-up, candidate, temporal
+// reuse, publication of out_f (+ NVLink halo rows), compaction of the secondary-ray requests.  Called converged by all
+// threads of the CTA (it contains the neighbour wait / signal and warp ballots).
+__device__ __forceinline__ void shade_and_publish(const FrameParams& P, const bool active, const uint32_t gx, const uint32_t gy,
+                                                  const uint32_t pix, const Ray& ray, const PrimaryHit& hit, uint32_t rng,
+                                                  uint32_t n_primary, uint32_t n_nodes) {
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t spp = max(P.spp, 1u), s = P.sample_index;
     const bool multi = spp > 1u;
-
     const SceneParams& S = P.scene;
     const v3 light_color = ld3(P.light_color);
     const v3 wi = normalize3(ld3(P.light_dir));
+    bool want_sun = false, want_ibl = false;
     Resv prev_r, cand;
-    uint32_t rng = 0u;
-    Ray ray;
-    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.tmin = 1e-3f; ray.tmax = 1e30f;
     prev_r.w_sum = 0.0f; prev_r.weight = 0.0f; prev_r.target_pdf = 0.0f; prev_r.m = 0u; prev_r.type1 = false;
     cand = prev_r;
-    if (active) {
-        // ---- primary ray (:467-485): its RNG stream does not depend on the reuse chain ----
-        if (s == 0u) rng = P.seed_hi ^ (gx * 1664525u) ^ (gy * 1013904223u) ^ (P.frame_index * 92837111u) ^ P.seed_lo;
-        else rng = __float_as_uint(P.sstate[3 * (size_t)pix + 0].x);
-        const float jx = tent_offset(xorshift32(rng)) * 0.5f;
-        const float jy = tent_offset(xorshift32(rng)) * 0.5f;
-        ray = camera_ray(P, gx, gy, jx, jy);
-        n_primary++;
-    }
-    const PrimaryHit hit = primary_hit(P, ray, active, st, n_nodes);   // warp-cooperative
-
     // ---- merged reservoir from last frame's reuse chain + M-clamp (:452-465).  Done AFTER the primary
     // traversal: only the shading below needs it, so the wait for the neighbour GPUs' halo rows (and the
     // 9 record loads) overlaps with the traversal instead of preceding it. ----
@@ -484,6 +466,93 @@ __global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(cons
     }
     warp_add_counters(P.counters, n_primary, 0u, 0u, n_nodes);
     if (s + 1u == spp) signal_neighbours(P);
+}
+
+// The camera ray of one sample and the state of its RNG stream after the two jitter draws (:467-485).
+__device__ __forceinline__ Ray sample_ray(const FrameParams& P, uint32_t gx, uint32_t gy, uint32_t pix, uint32_t frame, uint32_t s, uint32_t& rng) {
+    if (s == 0u) rng = P.seed_hi ^ (gx * 1664525u) ^ (gy * 1013904223u) ^ (frame * 92837111u) ^ P.seed_lo;
+    else rng = __float_as_uint(P.sstate[3 * (size_t)pix + 0].x);
+    const float jx = tent_offset(xorshift32(rng)) * 0.5f;
+    const float jy = tent_offset(xorshift32(rng)) * 0.5f;
+    return camera_ray(P, gx, gy, jx, jy);
+}
+
+__global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_primary(const __grid_constant__ FrameParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemStack st;
+    st.base = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
+    st.stride = kThreads;
+    uint32_t gx, gy;
+    const bool active = owned_pixel(P, gx, gy);
+    const uint32_t pix = active ? gy * P.W + gx : 0u;
+    uint32_t n_primary = 0, n_nodes = 0, rng = 0u;
+    Ray ray;
+    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.tmin = 1e-3f; ray.tmax = 1e30f;
+    if (active) {
+        // ---- primary ray (:467-485): its RNG stream does not depend on the reuse chain ----
+        ray = sample_ray(P, gx, gy, pix, P.frame_index, P.sample_index, rng);
+        n_primary++;
+    }
+    const PrimaryHit hit = primary_hit(P, ray, active, st, n_nodes);   // warp-cooperative
+    shade_and_publish(P, active, gx, gy, pix, ray, hit, rng, n_primary, n_nodes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split primary pass (terrain-only scenes, spp = 1): the primary TRAVERSAL of a frame depends on nothing but the camera
+// and the frame number, only the reuse chain behind it is sequential.  k_ptrace traces the primary rays of a whole BATCH of
+// frames in one launch (blockIdx.z = step of the batch) and leaves a 32-byte record per pixel; k_shade - no traversal, no
+// stack, a few hundred instructions per pixel - then runs once per frame in order.  On an image partition this moves ~70 %
+// of the per-frame chain (and its launch + tail) into a launch that is 4 frames big.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_ptrace(const __grid_constant__ FrameParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemStack st;
+    st.base = reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x;
+    st.stride = kThreads;
+    uint32_t gx, gy;
+    const bool active = owned_pixel(P, gx, gy);
+    const uint32_t pix = active ? gy * P.W + gx : 0u;
+    const BatchSlot& B = P.slot[blockIdx.z];
+    uint32_t n_primary = 0, n_nodes = 0, rng = 0u;
+    Ray ray;
+    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.tmin = 1e-3f; ray.tmax = 1e30f;
+    if (active) {
+        ray = sample_ray(P, gx, gy, pix, P.frame_index + blockIdx.z, 0u, rng);
+        n_primary++;
+    }
+    const FastHit fh = trace_fast<false, false>(P.fast, ray, active, st, n_nodes);   // warp-cooperative
+    if (active) {
+        st_stream(B.prim + 2 * (size_t)pix, make_float4(ray.d.x, ray.d.y, ray.d.z, fh.t));
+        st_stream(B.prim + 2 * (size_t)pix + 1, make_float4(__uint_as_float(fh.hit ? 1u : 0u), __uint_as_float(fh.cx | (fh.cz << 13)),
+                                                             __uint_as_float(rng), 0.0f));
+    }
+    warp_add_counters(P.counters, n_primary, 0u, 0u, n_nodes);
+}
+
+__global__ void __launch_bounds__(kThreads) k_shade(const __grid_constant__ FrameParams P) {
+    uint32_t gx, gy;
+    const bool active = owned_pixel(P, gx, gy);
+    const uint32_t pix = active ? gy * P.W + gx : 0u;
+    uint32_t rng = 0u;
+    Ray ray;
+    ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.tmin = 1e-3f; ray.tmax = 1e30f;
+    PrimaryHit hit;
+    hit.hit = false; hit.hit_type = 0u; hit.t = ray.tmax; hit.point = V3(0, 0, 0); hit.normal = V3(0, 0, 0);
+    if (active) {
+        const float4 p0 = ld_stream(P.cur.prim + 2 * (size_t)pix), p1 = ld_stream(P.cur.prim + 2 * (size_t)pix + 1);
+        ray.o = ld3(P.cam_origin);
+        ray.d = V3(p0.x, p0.y, p0.z);
+        rng = __float_as_uint(p1.z);
+        if (__float_as_uint(p1.x) != 0u) {          // intersect_hybrid's terrain branch (:190-197), as primary_hit
+            FastHit fh;
+            fh.hit = true; fh.t = p0.w;
+            const uint32_t c = __float_as_uint(p1.y);
+            fh.cx = c & 0x1FFFu; fh.cz = c >> 13;
+            hit.hit = true; hit.hit_type = 3u; hit.t = fh.t;
+            finish_hit(P.fast, ray, fh, hit.point, hit.normal);
+        }
+    }
+    shade_and_publish(P, active, gx, gy, pix, ray, hit, rng, 0u, 0u);
 }
 
 // Orders the final reuse pass (k_resolve) after the neighbours' last halo stores.

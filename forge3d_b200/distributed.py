@@ -204,7 +204,19 @@ class PartitionedRender:
         from . import _native
         from .session import Session
 
+        import time
+
         self.torch, self.dist, self.group = torch, dist, group
+        self.timings = {}            # wall-clock ms of the host-visible phases (set-up and resolve), for bench.py's e2e record
+        t_mark = time.perf_counter()
+
+        def lap(name):
+            nonlocal t_mark
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.timings[name] = self.timings.get(name, 0.0) + (now - t_mark) * 1e3
+            t_mark = now
+
         initialised = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if initialised else 1
         self.rank = dist.get_rank(group) if initialised else 0
@@ -223,17 +235,20 @@ class PartitionedRender:
             dist.broadcast(dem_dev, src=0, group=group)
             self._dem_dev = dem_dev
             heightmap = _native.DeviceHeights(dem_dev.data_ptr(), shape, keep=dem_dev)
+            lap("dem_h2d_broadcast_ms")
         # torch's default stream has handle 0, which the C ABI reads as "create your own stream":
         # pass cudaStreamLegacy (0x1) so kernels, torch events and NCCL share one stream.
         self.session = Session(heightmap, width, height, cam, device=self.device,
                                cuda_stream=self.stream.cuda_stream or 1, part_rank=self.rank, part_world=self.world,
                                part_block_rows=block_rows, **scene_kw)
+        lap("session_create_ms")
         if self.world > 1:
             # CUDA-IPC handles of the reservoir images and the frame-barrier words: one all-gather of 192 bytes per rank
             mine = torch.frombuffer(bytearray(self.session.ipc_export()), dtype=torch.uint8).cuda()
             every = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device="cuda")
             dist.all_gather_into_tensor(every, mine, group=group)
             self.session.ipc_import(every.cpu().numpy().tobytes())
+            lap("ipc_exchange_ms")
 
     def render_frames(self, n: int) -> None:
         """n accumulation frames, enqueued back to back; with world > 1 the cross-GPU ordering is done
@@ -251,7 +266,11 @@ class PartitionedRender:
     def resolve(self, aovs: bool = True, dst=None):
         """Resolve owned rows on the device, then ONE collective per output.  dst=None: all-gather, every rank returns the
         numpy images; dst=r: gather to rank r only (the consumer), the other ranks return None and copy nothing to the host."""
+        import time
+
         torch = self.torch
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         H, W = self.height, self.width
         rgba = torch.zeros((H, W, 4), dtype=torch.uint8, device="cuda")
         bufs = {"rgba": rgba}
@@ -278,6 +297,9 @@ class PartitionedRender:
                 raise RuntimeError(NO_VALID_RESERVOIRS)
         elif err is not None:
             raise err
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        self.timings["resolve_kernels_ms"] = (t1 - t0) * 1e3
         out = {}
         for k, t in bufs.items():
             if self.world == 1:
@@ -288,6 +310,8 @@ class PartitionedRender:
                 full = gather_rows_to(t, H, int(dst), self.group, self.block_rows)
             if full is not None:
                 out[k] = _to_host(full) if dst is not None else full.cpu().numpy()
+        torch.cuda.synchronize()
+        self.timings["gather_and_d2h_ms"] = (time.perf_counter() - t1) * 1e3
         return out if (self.world == 1 or dst is None or self.rank == int(dst)) else None
 
     def close(self):
