@@ -160,7 +160,7 @@ class TerrainDesc(C.Structure):
         ("width", C.c_uint32), ("height", C.c_uint32), ("seed", C.c_uint32), ("spp", C.c_uint32),
         ("max_frames", C.c_uint32), ("min_frames", C.c_uint32), ("variance_threshold", C.c_float),
         ("device", C.c_int32), ("compat_512mib_gate", C.c_int32),
-        ("part_rank", C.c_uint32), ("part_world", C.c_uint32), ("part_block_rows", C.c_uint32),
+        ("part_rank", C.c_uint32), ("part_world", C.c_uint32), ("part_block_rows", C.c_uint32), ("part_mode", C.c_uint32),
         ("atmosphere", C.POINTER(Atmosphere)),
     ]
 
@@ -187,23 +187,35 @@ EXPORTS = [
     "f3d_session_resolve_device", "f3d_session_validity", "f3d_session_resolve_host", "f3d_session_frames",
     "f3d_session_stats", "f3d_session_sync", "f3d_session_last_frames_ms", "f3d_session_destroy",
     "f3d_session_ipc_export", "f3d_session_ipc_import", "f3d_trace_rays", "f3d_build_minmax",
-    "f3d_smoke_create", "f3d_smoke_destroy", "f3d_smoke_raymarch_rgba", "f3d_smoke_raymarch_projection_rgba",
+    "f3d_smoke_create", "f3d_smoke_destroy", "f3d_smoke_raymarch_rgba", "f3d_smoke_raymarch_over_rgba", "f3d_smoke_raymarch_projection_rgba",
     "f3d_viewshed", "f3d_shadow_mask", "f3d_lbvh_build", "f3d_wavefront_render", "f3d_wavefront_render_part",
 ]
 
-_lib = None
+_libs = {}
+NUMERICS = ("exact", "fast")
 
 
-def lib():
-    """Loads the in-tree CUDA backend; fails loudly when it is missing (no fallback)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not LIB_PATH.exists():
+def default_numerics() -> str:
+    """"exact" (bit-identical to the oracle: the numerics contract of DESIGN.md section 4) unless F3D_B200_NUMERICS=fast selects
+    the throughput build (csrc/f3d_math.cuh F3D_FAST_NUMERICS; accepted by tolerance, tests/test_fast_numerics.py)."""
+    return os.environ.get("F3D_B200_NUMERICS", "exact") or "exact"
+
+
+def lib(numerics: str | None = None):
+    """Loads the in-tree CUDA backend; fails loudly when it is missing (no fallback).  `numerics` picks the build: "exact"
+    (libforge3d_b200.so) or "fast" (libforge3d_b200_fast.so); None = default_numerics().  Only the terrain session /
+    render entry points are meant to be used from the fast build; the widened rows always bind the exact one."""
+    numerics = numerics or default_numerics()
+    if numerics not in NUMERICS:
+        raise ValueError(f"numerics must be one of {NUMERICS}, got {numerics!r}")
+    if numerics in _libs:
+        return _libs[numerics]
+    path = LIB_PATH if numerics == "exact" else _PKG / "libforge3d_b200_fast.so"
+    if not path.exists():
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build the CUDA backend with `python -m forge3d_b200.build` "
+            f"{path} is missing: build the CUDA backend with `python -m forge3d_b200.build`{' --fast' if numerics == 'fast' else ''} "
             "(or __graft_entry__.build()); forge3d_b200 has no CPU fallback")
-    L = C.CDLL(str(LIB_PATH))
+    L = C.CDLL(str(path))
     vp, u8p, fp, u32p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_uint32)
     L.f3d_terrain_reference_render.argtypes = [C.POINTER(TerrainDesc), C.POINTER(TerrainOut)]
     L.f3d_last_error.restype = C.c_char_p
@@ -237,6 +249,8 @@ def lib():
     L.f3d_smoke_destroy.restype = None
     L.f3d_smoke_raymarch_rgba.argtypes = [vp, C.POINTER(SmokeSettings), C.c_uint32, C.c_uint32, f3, f3, f3, C.c_float, f3, u8p,
                                           C.POINTER(C.c_double)]
+    L.f3d_smoke_raymarch_over_rgba.argtypes = [vp, C.POINTER(SmokeSettings), C.c_uint32, C.c_uint32, f3, f3, f3, C.c_float, f3, u8p, fp, u8p,
+                                               C.POINTER(C.c_double)]
     L.f3d_smoke_raymarch_projection_rgba.argtypes = [vp, C.POINTER(SmokeSettings), C.c_uint32, C.c_uint32, f3, f3, u8p,
                                                      C.POINTER(C.c_double)]
     L.f3d_viewshed.argtypes = [fp, fp, C.POINTER(ViewshedOptions), u8p, fp, fp, fp, C.POINTER(C.c_double)]
@@ -248,19 +262,20 @@ def lib():
                                             fp, u8p, C.POINTER(WavefrontStats)]
     for name in EXPORTS:   # fail at load time, not at first call, if the ABI drifted
         getattr(L, name)
-    _lib = L
+    _libs[numerics] = L
     return L
 
 
-def last_error() -> str:
-    return lib().f3d_last_error().decode("utf-8", "replace")
+def last_error(L=None) -> str:
+    return (L or lib()).f3d_last_error().decode("utf-8", "replace")
 
 
-def check(rc: int) -> None:
-    """Maps f3d_status to the exception types PyO3 raises for RenderError (src/core/error.rs)."""
+def check(rc: int, L=None) -> None:
+    """Maps f3d_status to the exception types PyO3 raises for RenderError (src/core/error.rs).  L = the library the call
+    went to (the error text lives there); None = the default build."""
     if rc == 0:
         return
-    msg = last_error()
+    msg = last_error(L)
     if rc == 5:
         raise ValueError(msg)
     if rc == 4:
@@ -285,7 +300,7 @@ def make_desc(heightmap, width, height, cam, *, spacing, exaggeration, albedo, s
               max_frames, min_frames, variance_threshold, seed, sun_color, observer_latitude_deg,
               observer_longitude_deg, earth_model, sphere_radius_m, refraction_model, refraction_k,
               pressure_mbar, temperature_c, device=0, compat_512mib_gate=False, part_rank=0, part_world=1,
-              part_block_rows=0, atmosphere=None):
+              part_block_rows=0, atmosphere=None, part_mode=0):
     """Marshals the native seam's arguments into f3d_terrain_desc (terrain_reference.rs:295-414).
     Returns (desc, keepalive)."""
     if earth_model not in EARTH_MODELS:
@@ -348,6 +363,7 @@ def make_desc(heightmap, width, height, cam, *, spacing, exaggeration, albedo, s
     d.device = int(device)
     d.compat_512mib_gate = int(bool(compat_512mib_gate))
     d.part_rank, d.part_world, d.part_block_rows = int(part_rank), int(part_world), int(part_block_rows)
+    d.part_mode = int(part_mode)
     if atmosphere is not None:   # an AtmosphereLutHandle (see forge3d_b200.atmosphere.resolve_atmosphere)
         atm, atm_keep = make_atmosphere(atmosphere)
         keep += atm_keep

@@ -18,11 +18,21 @@ LIB = PKG / "libforge3d_b200.so"
 SOURCES = ["f3d_backend.cu", "f3d_smoke.cu", "f3d_viewshed.cu", "f3d_wavefront.cu"]
 HEADERS = ["f3d_host.h", "f3d_math.cuh", "f3d_aether.cuh", "f3d_smoke.cuh", "f3d_viewshed.cuh", "f3d_lbvh.cuh", "f3d_wavefront.cuh", "f3d_trace.cuh", "f3d_trace_fast.cuh", "f3d_kernels.cuh"]
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
-]
+LIB_FAST = PKG / "libforge3d_b200_fast.so"     # the throughput-numerics variant (csrc/f3d_math.cuh F3D_FAST_NUMERICS)
+
+_COMMON_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17"]
+_LINK_FLAGS = ["-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-ldl"]
+_NUMERICS_FLAGS = {
+    "exact": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"],
+    "fast": ["-fmad=true", "-prec-div=false", "-prec-sqrt=false", "-ftz=true", "-DF3D_FAST_NUMERICS=1"],
+}
+NVCC_FLAGS = [*_COMMON_FLAGS, *_NUMERICS_FLAGS["exact"], *_LINK_FLAGS]
+
+
+def lib_path(numerics: str = "exact") -> Path:
+    if numerics not in _NUMERICS_FLAGS:
+        raise ValueError(f"numerics must be 'exact' or 'fast', got {numerics!r}")
+    return LIB if numerics == "exact" else LIB_FAST
 
 
 def _nvcc() -> str:
@@ -58,24 +68,30 @@ def built_info(lib: Path = LIB) -> str:
     return blob[i + len(b"F3D_BUILD_INFO:"):j].decode(errors="replace")
 
 
-def needs_build(defines: str = "") -> bool:
-    """True unless LIB was built from exactly these sources with exactly these defines (a variant build left behind by an
-    A/B run is rebuilt, not silently reused as the default)."""
-    return built_info() != f"src={source_hash()};defines={','.join(defines.split())}"
+def _info(defines: str, numerics: str) -> str:
+    return f"src={source_hash()};defines={','.join(defines.split())}" + (";numerics=fast" if numerics == "fast" else "")
 
 
-def build(force: bool = False, verbose: bool = False, out: Path | None = None, defines: str | None = None) -> Path:
+def needs_build(defines: str = "", numerics: str = "exact") -> bool:
+    """True unless the library was built from exactly these sources with exactly these defines (a variant build left behind
+    by an A/B run is rebuilt, not silently reused as the default)."""
+    return built_info(lib_path(numerics)) != _info(defines, numerics)
+
+
+def build(force: bool = False, verbose: bool = False, out: Path | None = None, defines: str | None = None,
+          numerics: str = "exact") -> Path:
     # defines / F3D_B200_DEFINES="F3D_CULL_FAST=0 ..." builds a compile-time variant of the kernels (A/B runs; see
     # csrc/f3d_trace_fast.cuh and tests/test_traversal_emulation.py); unset = the validated default
     if defines is None:
         defines = os.environ.get("F3D_B200_DEFINES", "")
     defines = " ".join(defines.split())
-    out = Path(out) if out else LIB
-    if not force and out == LIB and not needs_build(defines):
-        return LIB
-    info = f"src={source_hash()};defines={','.join(defines.split())}"
+    default_out = lib_path(numerics)
+    out = Path(out) if out else default_out
+    if not force and out == default_out and not needs_build(defines, numerics):
+        return out
+    info = _info(defines, numerics)
     dflags = [f"-D{d}" for d in defines.split()] + [f'-DF3D_BUILD_INFO_STR="{info}"']
-    cmd = [_nvcc(), *NVCC_FLAGS, *dflags, "-o", str(out)] + [str(CSRC / s) for s in SOURCES]
+    cmd = [_nvcc(), *_COMMON_FLAGS, *_NUMERICS_FLAGS[numerics], *_LINK_FLAGS, *dflags, "-o", str(out)] + [str(CSRC / s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -90,5 +106,36 @@ def build(force: bool = False, verbose: bool = False, out: Path | None = None, d
     return out
 
 
+VARIANT_DIR = PKG.parent / "variants"
+# Compile-time variants that ship beside the default library: measured alternatives kept buildable and bit-exact
+# (tests/test_gpu_parity.py::test_compile_time_variants_are_bit_identical), named by what they switch.
+VARIANTS = {
+    "tma": "F3D_TMA_STAGE=1",            # TMA (cp.async.bulk + mbarrier) staging of the top pyramid levels: measured slower
+}
+
+
+def variant_path(name: str) -> Path:
+    return VARIANT_DIR / f"lib_{name}.so"
+
+
+def build_variant(name: str, force: bool = False) -> Path:
+    """Builds variants/lib_<name>.so from the current sources with VARIANTS[name] (no-op when it is up to date)."""
+    defines = " ".join(VARIANTS[name].split())
+    out = variant_path(name)
+    if not force and built_info(out) == _info(defines, "exact"):
+        return out
+    VARIANT_DIR.mkdir(exist_ok=True)
+    return build(force=True, out=out, defines=defines)
+
+
+def build_all(force: bool = False) -> list:
+    """Everything the GPU box needs: the exact library, the throughput-numerics library, the shipped variants."""
+    outs = [build(force=force, defines=""), build(force=force, defines="", numerics="fast")]
+    outs += [build_variant(n, force=force) for n in VARIANTS]
+    return outs
+
+
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+
+    print(build(force=True, verbose=True, numerics="fast" if "--fast" in sys.argv else "exact"))

@@ -6,6 +6,12 @@
 // :52-84,:224-369 and src/geo/refraction.rs): Rust is not available in this image, so the layer that
 // is Rust in the reference is C++ here and exports the C ABI a Rust `extern "C"` shim would bind.
 // There is no CPU fallback anywhere in this file: every path that cannot reach a CUDA device fails.
+#ifndef EMU_SIMT
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+#else
+static inline void nvtxRangePushA(const char*) {}
+static inline void nvtxRangePop() {}
+#endif
 #include <stdarg.h>
 
 #include <map>
@@ -298,6 +304,7 @@ static int validate_desc(const f3d_terrain_desc* d) {
         return fail(F3D_ERR_ARGUMENT, "image of %ux%u pixels exceeds the 2^31-pixel addressing limit", d->width, d->height);
     if (d->part_world > 1 && d->part_rank >= d->part_world)
         return fail(F3D_ERR_ARGUMENT, "part_rank (%u) must be < part_world (%u)", d->part_rank, d->part_world);
+    if (d->part_mode > 1) return fail(F3D_ERR_ARGUMENT, "unsupported part_mode %u", d->part_mode);
     if (d->atmosphere && !(d->atmosphere->transmittance && d->atmosphere->scattering && d->atmosphere->aerial))
         return fail(F3D_ERR_ARGUMENT, "atmosphere LUT pointer is null");
     return 0;
@@ -677,6 +684,10 @@ struct f3d_session {
     dim3 grid;
     size_t smem_bytes = 0;          // stack smem of the per-pixel kernels (kThreads)
     size_t trace_smem_bytes = 0;    // stack smem of k_trace (kTraceCtaThreads)
+    float* d_hz = nullptr;          // sun horizon strips (SunHorizon::S)
+    float* d_esc = nullptr;         // escape map (EscapeMap::E)
+    size_t ptrace_smem_bytes = 0;   // k_ptrace: stacks + staged top levels (F3D_TMA_STAGE)
+    size_t ascent_smem_bytes = 0;   // k_ascent: leaf rings of the near-field walk (+ staged top levels)
     int trace_grid = 0;             // persistent CTAs of k_trace
     int ascent_grid = 0;            // grid-stride CTAs of k_ascent
     // Frame batching + pipelining.  k_primary(step+1) only depends on k_primary(step) (reservoir records); everything after it
@@ -720,9 +731,9 @@ static void session_free(f3d_session* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     cached_free(s->d_sync, s->device, false);
     const int dv = s->device;
-    const bool ipc = s->P.part_world > 1u;                  // resv images may be mapped by peers: never park them
+    const bool ipc = s->P.part_world > 1u && s->P.part_mode == 0u;     // resv images may be mapped by peers: never park them
     s->terrain.release();
-    cached_free(s->d_env, dv); cached_free(s->d_mesh_v, dv); cached_free(s->d_mesh_i, dv);
+    cached_free(s->d_env, dv); cached_free(s->d_mesh_v, dv); cached_free(s->d_mesh_i, dv); cached_free(s->d_hz, dv); cached_free(s->d_esc, dv);
     cached_free(s->d_bvh_nodes, dv); cached_free(s->d_bvh_tris, dv);
     cached_free(s->d_accum, dv); cached_free(s->d_welford, dv);
     cached_free(s->d_resv[0], dv, !ipc); cached_free(s->d_resv[1], dv, !ipc);
@@ -732,7 +743,7 @@ static void session_free(f3d_session* s) {
         if (bs.stream) { cudaStreamSynchronize(bs.stream); cudaStreamDestroy(bs.stream); }
         for (auto& sl : bs.slots) {
             cached_free(sl.prim, dv); cached_free(sl.rec, dv); cached_free(sl.occl_sun, dv); cached_free(sl.occl_ibl, dv);
-            cached_free(sl.q_sun, dv); cached_free(sl.q_ibl, dv); cached_free(sl.q_counts, dv);
+            cached_free(sl.q_sun, dv); cached_free(sl.q_ibl, dv); cached_free(sl.q_counts, dv); cached_free(sl.qf_sun, dv); cached_free(sl.qf_ibl, dv);
             cached_free(sl.qn_sun, dv); cached_free(sl.qn_ibl, dv); cached_free(sl.q2_sun, dv); cached_free(sl.q2_ibl, dv);
         }
         if (bs.primary_done) cudaEventDestroy(bs.primary_done);
@@ -756,6 +767,88 @@ static int dmalloc(f3d_session* s, T** p, size_t count, bool zero) {
     if (zero) CUDA_TRY(cudaMemsetAsync(*p, 0, count * sizeof(T), s->stream));
     return 0;
 }
+
+// Sun horizon strips (SunHorizon, f3d_trace_fast.cuh): built once, for the direction every sun ray of the session shares.
+// Not built (hz.S stays NULL, the tracer then behaves as before) for a sun below the horizon, a (near-)vertical sun, a
+// negative curvature term, or when F3D_B200_SUN_HORIZON=0.
+static int build_sun_horizon(f3d_session* s) {
+    FrameParams& P = s->P;
+    P.hz = SunHorizon{};
+#if F3D_SUN_HORIZON
+    if (const char* e = getenv("F3D_B200_SUN_HORIZON")) if (atoi(e) == 0) return 0;
+    const double lx = P.light_dir[0], ly = P.light_dir[1], lz = P.light_dir[2];
+    const double n = std::sqrt(lx * lx + ly * ly + lz * lz);
+    if (!(n > 0.0) || ly < 0.0) return 0;
+    if (P.scene.curvature_enabled && !(P.fast.inv_two_r_prime >= 0.0f)) return 0;
+    const double du = lx / n / (double)P.fast.sx, dv = lz / n / (double)P.fast.sz, dy = ly / n;
+    const bool xmajor = std::fabs(du) >= std::fabs(dv);
+    const double da = xmajor ? du : dv, db = xmajor ? dv : du;
+    if (!(std::fabs(da) > 0.0)) return 0;
+    const double m = db / da, g = dy / std::fabs(da);
+    if (!(g < 1.0e6)) return 0;                                   // the sun is (almost) overhead: every ray leaves its column upwards
+    const uint32_t ncols = xmajor ? P.fast.cell_w : P.fast.cell_h, nrows = xmajor ? P.fast.cell_h : P.fast.cell_w;
+    const double w_min = std::min(0.0, -m * (double)ncols), w_max = (double)nrows + std::max(0.0, -m * (double)ncols);
+    const int32_t j0 = (int32_t)std::floor(w_min) - 1;
+    const uint32_t nstrips = (uint32_t)((int32_t)std::floor(w_max) + 2 - j0);
+    const size_t bytes = (size_t)ncols * nstrips * sizeof(float);
+    if (bytes > ((size_t)1 << 30)) return 0;
+    CUDA_TRY(cached_malloc((void**)&s->d_hz, bytes, s->device));
+    SunHorizon Z{};
+    Z.S = s->d_hz; Z.nstrips = nstrips; Z.ncols = ncols; Z.j0 = j0;
+    Z.m = (float)m; Z.g = (float)g;
+    Z.pad_rel = 1.9073486328125e-6f;                               // 2^-19, see the error budget in DESIGN.md section 6
+    Z.mag = P.fast.mag_y + (float)ncols * (float)g;
+    Z.xmajor = xmajor ? 1u : 0u; Z.forward = da > 0.0 ? 1u : 0u;
+    k_hz_build<<<dim3((nstrips + 255u) / 256u, ncols), 256, 0, s->stream>>>(P.fast.cells, P.fast.cell_w, P.fast.cell_h, Z, m, g, s->d_hz);
+    k_hz_suffix<<<(nstrips + 7u) / 8u, 256, 0, s->stream>>>(s->d_hz, nstrips, ncols);          // one warp per strip
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 2;
+    s->gpu_bytes += bytes;
+    P.hz = Z;
+    if (getenv("F3D_B200_DEBUG"))
+        fprintf(stderr, "[forge3d_b200] sun horizon: %u strips x %u columns (%.1f MB), %s-major, m %.4f, g %.3f per column\n", nstrips, ncols,
+                bytes / 1048576.0, xmajor ? "x" : "z", m, g);
+#endif
+    return 0;
+}
+
+// Escape map (EscapeMap, f3d_trace_fast.cuh): 32 bytes per DEM cell, built once per session from the min-max pyramid.
+// Off unless F3D_B200_ESCAPE=1 (see below); without it the IBL rays all take the bottom-up start.
+static int build_escape_map(f3d_session* s) {
+    FrameParams& P = s->P;
+    P.esc = EscapeMap{};
+#if F3D_ESCAPE
+    // OPT-IN (F3D_B200_ESCAPE=1).  Measured on the B200, C2 (profiles/r02_walks.md): the map takes 4.2 ms to build and saves
+    // 0.008 ms per 1080p frame (0.859 -> 0.851 ms: k_trace -15 % warp-instructions, but the classify pass that reads the map
+    // is latency-bound), i.e. it pays for itself only beyond ~500 frames of this size.  Bit-exact either way
+    // (tests/test_gpu_parity.py::test_escape_map_is_exact_and_culls).
+    const char* e = getenv("F3D_B200_ESCAPE");
+    if (!e || atoi(e) == 0) return 0;
+    const size_t ncells = (size_t)P.fast.cell_w * P.fast.cell_h;
+    const size_t bytes = ncells * 8 * sizeof(float);
+    if (bytes > ((size_t)4 << 30)) return 0;
+    CUDA_TRY(cached_malloc((void**)&s->d_esc, bytes, s->device));
+    // height pad: covers the rounding of the reference's ray height at the span start (2 ulp of |o.y| + the gain) and of
+    // the ray origin against the cell's corner heights
+    const float pad_abs = 1.52587890625e-5f * (P.fast.mag_y + 1.0f);          // 2^-16
+    k_escape_build<<<dim3((P.fast.cell_w + 127u) / 128u, P.fast.cell_h), 128, 0, s->stream>>>(P.fast, escape_oct_table(), pad_abs, s->d_esc);
+    CUDA_TRY(cudaGetLastError());
+    s->launches += 1;
+    s->gpu_bytes += bytes;
+    P.esc.E = s->d_esc;
+    if (getenv("F3D_B200_DEBUG"))
+        fprintf(stderr, "[forge3d_b200] escape map: %zu cells x 8 octants (%.1f MB), near block radius %d\n", ncells, bytes / 1048576.0, kEscR);
+#endif
+    return 0;
+}
+
+// NVTX ranges carry the pass labels of the reference's render certificate (terrain_reference.rs:1410-1420:
+// hybrid_pt.terrain_gbuffer | terrain | restir_temporal | restir_spatial | aether_aerial), so an nsys / ncu timeline of
+// this backend lines up with the reference's own timing table.  Temporal + spatial reuse are fused into the shading kernel.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d_session* s) {
     int ndev = 0;
@@ -807,6 +900,7 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
 
     // ---- partition ----
     P.part_world = std::max(d->part_world, 1u);
+    P.part_mode = P.part_world > 1u ? d->part_mode : 0u;
     P.part_rank = P.part_world > 1 ? d->part_rank : 0u;
     uint32_t block_rows = d->part_block_rows ? d->part_block_rows : 16u;
     block_rows = ((block_rows + kTileH - 1) / kTileH) * kTileH;
@@ -829,10 +923,47 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     S.oz = -0.5f * ((float)d->dem_h - 1.0f) * S.sz;
     fill_fast_scene(&P.fast, S, s->terrain);
     P.stack_depth = stack_depth_for(s->terrain.nlevels);
+    if ((rc = build_sun_horizon(s))) return rc;
+    if ((rc = build_escape_map(s))) return rc;
     s->smem_bytes = stack_smem_bytes(P.stack_depth, kThreads);
     s->trace_smem_bytes = trace_smem_bytes_for(P.stack_depth, kTraceCtaThreads);
+    s->ptrace_smem_bytes = s->smem_bytes;
+    s->ascent_smem_bytes = kAscentRingBytes;
+#if F3D_TMA_STAGE
+    {   // TMA staging of the top pyramid levels (f3d_trace_fast.cuh): per kernel, as many whole levels from the top as fit the
+        // kernel's shared-memory budget (k_ptrace 4 CTAs/SM beside 39 KB of stacks, k_ascent 3 CTAs/SM with nothing else,
+        // k_trace 6 CTAs/SM beside 31 KB of stacks + leaf rings).  F3D_B200_TMA_STAGE=0 keeps the level table but stages nothing.
+        const DeviceTerrain& T = s->terrain;
+        const bool on = !(getenv("F3D_B200_TMA_STAGE") && atoi(getenv("F3D_B200_TMA_STAGE")) == 0);
+        const uint32_t budget[3] = {12u << 10, 44u << 10, 3u << 10};
+        for (int k = 0; k < 3; k++) {
+            StageParams sp{};
+            sp.first = (uint32_t)std::max(T.nlevels - 1, 0);
+            sp.bytes = 0u;
+            sp.src = T.quad_base;
+            for (int l = T.nlevels - 2; l >= 0 && on; l--) {        // levels l .. nlevels-2 are the END of the quad arena
+                const size_t bytes = (T.quad_total - T.quad_off[l]) * sizeof(float2);
+                if (bytes > budget[k]) break;
+                sp.first = (uint32_t)l; sp.bytes = (uint32_t)bytes; sp.src = T.quad_base + T.quad_off[l];
+            }
+            P.stage[k] = sp;
+        }
+        s->ptrace_smem_bytes = ((s->smem_bytes + 15) & ~(size_t)15) + stage_smem_bytes(P.stage[0].bytes);
+        s->ascent_smem_bytes = kAscentRingBytes + stage_smem_bytes(P.stage[1].bytes);
+        s->trace_smem_bytes = ((s->trace_smem_bytes + 15) & ~(size_t)15) + stage_smem_bytes(P.stage[2].bytes);
+#define F3D_ALLOW_ASCENT(...) if ((rc = allow_smem(k_ascent<__VA_ARGS__>, s->ascent_smem_bytes))) return rc
+        F3D_ALLOW_ASCENT(true, true, 1, 0); F3D_ALLOW_ASCENT(true, true, 1, 1); F3D_ALLOW_ASCENT(true, true, 1, 2);
+        F3D_ALLOW_ASCENT(true, false, 1, 0); F3D_ALLOW_ASCENT(true, false, 1, 1); F3D_ALLOW_ASCENT(true, false, 1, 2);
+        F3D_ALLOW_ASCENT(true, false, 0, 2);
+        F3D_ALLOW_ASCENT(false, false, 0, 0); F3D_ALLOW_ASCENT(false, false, 0, 1); F3D_ALLOW_ASCENT(false, false, 0, 2);
+#undef F3D_ALLOW_ASCENT
+        if (getenv("F3D_B200_DEBUG"))
+            fprintf(stderr, "[forge3d_b200] TMA staging: k_ptrace levels >= %u (%u B), k_ascent >= %u (%u B), k_trace >= %u (%u B)\n",
+                    P.stage[0].first, P.stage[0].bytes, P.stage[1].first, P.stage[1].bytes, P.stage[2].first, P.stage[2].bytes);
+    }
+#endif
     if ((rc = allow_smem(k_primary, s->smem_bytes))) return rc;
-    if ((rc = allow_smem(k_ptrace, s->smem_bytes))) return rc;
+    if ((rc = allow_smem(k_ptrace, s->ptrace_smem_bytes))) return rc;
     if ((rc = allow_smem(k_gbuffer, s->smem_bytes))) return rc;
     if ((rc = allow_smem(k_trace<true, 1>, s->trace_smem_bytes))) return rc;
     if ((rc = allow_smem(k_trace<true, 2>, s->trace_smem_bytes))) return rc;
@@ -938,11 +1069,11 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     {
         // default: two batch sets of 4 steps; smaller batches when the per-step buffers (98 B/pixel) would exceed 8 GB in total.
         // F3D_B200_BATCH / F3D_B200_SETS override (F3D_B200_PIPELINE=1 is the old spelling of "no overlap": 1 set of 1).
-        const int by_memory = (int)std::max<uint64_t>(1, (8ull << 30) / std::max<uint64_t>(1, (uint64_t)npx * (98 + (s->split_primary ? 32 : 0))));
+        const int by_memory = (int)std::max<uint64_t>(1, (8ull << 30) / std::max<uint64_t>(1, (uint64_t)npx * (106 + (s->split_primary ? 32 : 0))));
         const char* eb = getenv("F3D_B200_BATCH");
         const char* es = getenv("F3D_B200_SETS");
         s->n_sets = es ? std::min(std::max(atoi(es), 1), (int)f3d_session::kMaxSets) : (by_memory >= 2 ? 2 : 1);
-        s->batch = eb ? std::min(std::max(atoi(eb), 1), kMaxBatch) : std::min(4, std::max(by_memory / s->n_sets, 1));
+        s->batch = eb ? std::min(std::max(atoi(eb), 1), kMaxBatch) : std::min(P.part_world > 2u ? 8 : 4, std::max(by_memory / s->n_sets, 1));   // small partitions: bigger batches
         if (const char* e = getenv("F3D_B200_PIPELINE")) if (atoi(e) <= 1) { s->n_sets = 1; s->batch = 1; }
     }
     for (int k = 0; k < s->n_sets; k++) {
@@ -955,7 +1086,9 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
             if ((rc = dmalloc(s, &sl.occl_ibl, npx, true))) return rc;
             if ((rc = dmalloc(s, &sl.q_sun, npx, false))) return rc;
             if ((rc = dmalloc(s, &sl.q_ibl, npx, false))) return rc;
-            if ((rc = dmalloc(s, &sl.q_counts, (size_t)8, true))) return rc;
+            if ((rc = dmalloc(s, &sl.q_counts, (size_t)kQCounts, true))) return rc;
+            if ((rc = dmalloc(s, &sl.qf_sun, npx, false))) return rc;
+            if ((rc = dmalloc(s, &sl.qf_ibl, npx, false))) return rc;
             if ((rc = dmalloc(s, &sl.q2_sun, npx, false))) return rc;
             if ((rc = dmalloc(s, &sl.q2_ibl, npx, false))) return rc;
             if ((rc = dmalloc(s, &sl.qn_sun, npx, false))) return rc;
@@ -973,7 +1106,7 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
     P.resv_in = s->d_resv[1]; P.resv_out = s->d_resv[0];
     P.peer_up = nullptr; P.peer_down = nullptr;
     P.sync_local = nullptr; P.peer_sync_up = nullptr; P.peer_sync_down = nullptr; P.sync_error = nullptr;
-    if (P.part_world > 1u) {
+    if (P.part_world > 1u && P.part_mode == 0u) {
         CUDA_TRY(cached_malloc((void**)&s->d_sync, 8 * sizeof(uint32_t), s->device));      // IPC-shared: freed with allow_park = false
         CUDA_TRY(cudaMemsetAsync(s->d_sync, 0, 8 * sizeof(uint32_t), s->stream));
         P.sync_local = s->d_sync;
@@ -1002,6 +1135,7 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
 
     // ---- one-shot G-buffer / centre-ray AOV pass (render_terrain.rs:1091-1121) ----
     GbufferOut G{s->d_pixflags, s->d_aov_normal, s->d_aov_depth};
+    NvtxRange nvtx_gbuffer("hybrid_pt.terrain_gbuffer");
     k_gbuffer<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P, G);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1031,6 +1165,7 @@ extern "C" void f3d_session_destroy(f3d_session* s) { session_free(s); }
 extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
     if (!s) return fail(F3D_ERR_ARGUMENT, "null session");
     CUDA_TRY(cudaSetDevice(s->device));
+    NvtxRange nvtx_frames("hybrid_pt.terrain");
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     const bool pipelined = s->n_sets > 1;
     if (pipelined) {   // the set streams start after whatever is already queued on the session stream
@@ -1055,7 +1190,7 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             P.sample_index = 0u;
             P.n_batch = nb;
             for (uint32_t k = 0; k < nb; k++) P.slot[k] = bs.slots[k];
-            k_ptrace<<<dim3(s->grid.x, s->grid.y, nb), kThreads, s->smem_bytes, s->stream>>>(P);
+            k_ptrace<<<dim3(s->grid.x, s->grid.y, nb), kThreads, s->ptrace_smem_bytes, s->stream>>>(P);
             s->launches++;
         }
         for (uint32_t k = 0; k < nb; k++) {
@@ -1073,6 +1208,7 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             }
             P.cur = bs.slots[k];
             P.n_batch = 0u;
+            NvtxRange nvtx_shade("hybrid_pt.restir_temporal+restir_spatial");
             if (s->split_primary) k_shade<<<s->grid, kThreads, 0, s->stream>>>(P);
             else k_primary<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P);
             s->launches++;
@@ -1092,10 +1228,22 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
         // round-1 exact expansion (see F3D_CULL_FAST)
         const bool curv = P.scene.curvature_enabled != 0u, asc = P.light_dir[1] >= 0.0f;
 #if F3D_TRACE_BOTTOM_UP
-        if (curv && asc) k_ascent<true, 1><<<s->ascent_grid, 256, 0, ts>>>(P);
-        else if (curv) k_ascent<true, 2><<<s->ascent_grid, 256, 0, ts>>>(P);
-        else if (asc) k_ascent<false, 1><<<s->ascent_grid, 256, 0, ts>>>(P);
-        else k_ascent<false, 0><<<s->ascent_grid, 256, 0, ts>>>(P);
+        // one launch per list (instruction-cache fit, see k_ascent); SUN_MODE 2 leaves the sun list to the top-down tracer
+        // a list with a walk structure (sun horizon strips / escape map) takes two passes: classify + walk, then the far list
+        {
+            const size_t sm = s->ascent_smem_bytes;
+            const int g = s->ascent_grid;
+            const bool sun_walk = F3D_SUN_HORIZON && F3D_SUN_NEAR && asc && P.hz.S != nullptr, ibl_walk = F3D_ESCAPE && P.esc.E != nullptr;
+            if (curv && asc) {
+                if (sun_walk) { k_ascent<true, true, 1, 0><<<g, 256, sm, ts>>>(P); k_ascent<true, true, 1, 1><<<g, 256, sm, ts>>>(P); s->launches += 2; }
+                else { k_ascent<true, true, 1, 2><<<g, 256, sm, ts>>>(P); s->launches++; }
+            } else if (!curv && asc) {
+                if (sun_walk) { k_ascent<true, false, 1, 0><<<g, 256, sm, ts>>>(P); k_ascent<true, false, 1, 1><<<g, 256, sm, ts>>>(P); s->launches += 2; }
+                else { k_ascent<true, false, 1, 2><<<g, 256, sm, ts>>>(P); s->launches++; }
+            } else if (!curv) { k_ascent<true, false, 0, 2><<<g, 256, sm, ts>>>(P); s->launches++; }
+            if (ibl_walk) { k_ascent<false, false, 0, 0><<<g, 256, sm, ts>>>(P); k_ascent<false, false, 0, 1><<<g, 256, sm, ts>>>(P); s->launches += 2; }
+            else { k_ascent<false, false, 0, 2><<<g, 256, sm, ts>>>(P); s->launches++; }
+        }
         s->launches++;
 #endif
         if (curv && asc) k_trace<true, 1><<<s->trace_grid, kTraceCtaThreads, s->trace_smem_bytes, ts>>>(P);
@@ -1211,6 +1359,7 @@ static int resolve_device_impl(f3d_session* s, void* d_rgba, void* d_albedo, voi
     k_resolve<<<s->grid, kTileW * kTileH, 0, s->stream>>>(P, R);
     s->launches++;
     if (aether) {   // the post pass of render_terrain.rs:1287-1311, after the traversal's own resolve work
+        NvtxRange nvtx_aether("hybrid_pt.aether_aerial");
         k_aether<<<s->grid, kTileW * kTileH, 0, s->stream>>>(P, s->aether, s->d_aov_depth, (uint8_t*)d_rgba);
         s->launches++;
     }
@@ -1326,7 +1475,7 @@ extern "C" int f3d_session_ipc_import(f3d_session* s, const uint8_t* all) {
     if (!s || !all) return fail(F3D_ERR_ARGUMENT, "null argument");
     CUDA_TRY(cudaSetDevice(s->device));
     const uint32_t world = s->P.part_world;
-    if (world < 2) return 0;
+    if (world < 2 || s->P.part_mode == 1u) return 0;
     if (world > 8) return fail(F3D_ERR_ARGUMENT, "part_world > 8 not supported");
     for (uint32_t r = 0; r < world; r++) {
         if (r == s->P.part_rank) continue;
@@ -1485,14 +1634,14 @@ extern "C" int f3d_trace_rays(const float* heights, uint32_t w, uint32_t h, cons
 
 #ifdef F3D_SCHED_STATS
 // Tuning builds only (see F3D_SCHED_STATS in f3d_kernels.cuh); not part of the public ABI.
-extern "C" int f3d_debug_sched_stats(unsigned long long* out8, int reset) {
+extern "C" int f3d_debug_sched_stats(unsigned long long* out40, int reset) {
 #ifdef EMU_SIMT
-    memcpy(out8, f3d::g_sched_stats, 8 * sizeof(unsigned long long));
-    if (reset) memset(f3d::g_sched_stats, 0, 8 * sizeof(unsigned long long));
+    memcpy(out40, f3d::g_sched_stats, 40 * sizeof(unsigned long long));
+    if (reset) memset(f3d::g_sched_stats, 0, 40 * sizeof(unsigned long long));
 #else
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out8, f3d::g_sched_stats, 8 * sizeof(unsigned long long));
-    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(f3d::g_sched_stats, z, sizeof z); }
+    cudaMemcpyFromSymbol(out40, f3d::g_sched_stats, 40 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[40] = {}; cudaMemcpyToSymbol(f3d::g_sched_stats, z, sizeof z); }
 #endif
     return 0;
 }

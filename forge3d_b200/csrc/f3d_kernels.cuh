@@ -37,6 +37,7 @@ constexpr int kTileW = 16, kTileH = 16;      // CTA pixel tile; warps own 8x4 su
 // chain), so the primaries of a batch run back to back and one launch of each later kernel handles all their rays - on an
 // image partition (1/8 of a 1080p frame is ~230 k rays) a single step cannot fill 148 SMs, a batch can.
 constexpr int kMaxBatch = 8;
+constexpr uint32_t kQCounts = 12u;     // counters per BatchSlot (q_counts)
 struct BatchSlot {
     float4* prim;              // split primary pass (k_ptrace -> k_shade): 2 x float4 per pixel, (d.xyz, t) (hit, cell, rng, -)
     float4* rec;               // 4 x float4 per pixel, see PixelRec
@@ -44,17 +45,22 @@ struct BatchSlot {
     uint8_t* occl_ibl;         // per pixel: IBL ray occluded
     uint32_t* q_sun;           // compacted pixel indices that need a sun ray
     uint32_t* q_ibl;           // compacted pixel indices that need an IBL ray
-    uint32_t* q_counts;        // [0] n_sun [1] n_ibl [2] next_sun [3] next_ibl; stage 2: [4] n2_sun [5] n2_ibl [6] next2_sun [7] next2_ibl
+    uint32_t* q_counts;        // [0] n_sun [1] n_ibl [2] next_sun [3] next_ibl; stage 2: [4] n2_sun [5] n2_ibl [6] next2_sun [7] next2_ibl; far lists: [8] nf_sun [9] nf_ibl
     uint32_t* q2_sun;          // stage-2 lists: rays k_ascent could not decide (pixel index; seeds in qn_*)
     uint32_t* q2_ibl;
     unsigned long long* qn_sun;   // per stage-2 sun entry: seeds of the bottom-up start (ascent_seeds; k_ascent -> k_trace)
     unsigned long long* qn_ibl;   // same for the IBL list
+    uint32_t* qf_sun;          // far lists (k_ascent pass 0 -> pass 1): undecided rays no near-field walk can decide
+    uint32_t* qf_ibl;
 };
 
 struct FrameParams {
     SceneParams scene;          // env / mesh / albedo (+ the plain pyramid when the KAT seam keeps it)
     FastScene fast;             // quad-packed pyramid for the production traversal
     uint32_t stack_depth;       // shared-memory stack entries per thread (3 * mip_count + 2)
+    SunHorizon hz;              // sun horizon strips (F3D_SUN_HORIZON); hz.S == nullptr: none
+    EscapeMap esc;              // per-cell, per-octant horizon slopes (F3D_ESCAPE); esc.E == nullptr: none
+    StageParams stage[3];       // TMA staging of the top pyramid levels (F3D_TMA_STAGE): [0] k_ptrace [1] k_ascent [2] k_trace
     uint32_t W, H, frame_index, spp, window;
     float cam_origin[3], cam_right[3], cam_up[3], cam_forward[3];
     float half_w, half_h, exposure;
@@ -62,6 +68,7 @@ struct FrameParams {
     float light_dir[3], light_color[3];
     // image-row partition: this device owns row blocks b with b % world == rank
     uint32_t part_rank, part_world, block_rows, tiles_per_block, nblocks;
+    uint32_t part_mode;         // 1 = gather-only partition: spatial reuse never leaves the row block (no halo, no frame flags)
     // per-pixel state (full-image arrays, only owned rows + 3/4-row halos are touched)
     float4* accum;
     float2* welford;
@@ -220,6 +227,10 @@ __device__ __forceinline__ Resv spatial_reuse(const FrameParams& P, const float4
         if (rx == 0 && ry == 0) continue;
         int nxi = min(max((int)x + rx, 0), (int)W - 1);
         int nyi = min(max((int)y + ry, 0), (int)H - 1);
+        if (P.part_mode == 1u && P.part_world > 1u) {          // gather-only partition: clamp to the rows of this block
+            const int y0 = (int)((y / P.block_rows) * P.block_rows);
+            nyi = min(max(nyi, y0), min(y0 + (int)P.block_rows, (int)H) - 1);
+        }
         const Resv rn = unpack_resv(__ldcg(resv + (uint32_t)nyi * W + (uint32_t)nxi));
         consider_candidate(rn, facing, Wsum, chosen_type1, chosen_pdf, seed);
         m_total += rn.m;
@@ -513,6 +524,10 @@ __global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_ptrace(const
     const bool active = owned_pixel(P, gx, gy);
     const uint32_t pix = active ? gy * P.W + gx : 0u;
     const BatchSlot& B = P.slot[blockIdx.z];
+#if F3D_TMA_STAGE
+    // top pyramid levels -> shared memory, one bulk async copy per CTA (behind the stacks)
+    const QStaged qs = stage_top_levels(P.fast, P.stage[0], smem_raw + ((stack_smem_bytes(P.stack_depth, kThreads) + 15) & ~(size_t)15));
+#endif
     uint32_t n_primary = 0, n_nodes = 0, rng = 0u;
     Ray ray;
     ray.o = V3(0, 0, 0); ray.d = V3(0, 0, 1); ray.tmin = 1e-3f; ray.tmax = 1e30f;
@@ -520,7 +535,11 @@ __global__ void __launch_bounds__(kThreads, F3D_PRIMARY_MIN_CTAS) k_ptrace(const
         ray = sample_ray(P, gx, gy, pix, P.frame_index + blockIdx.z, 0u, rng);
         n_primary++;
     }
+#if F3D_TMA_STAGE
+    const FastHit fh = trace_fast<false, false, QStaged>(P.fast, ray, active, st, n_nodes, qs);   // warp-cooperative
+#else
     const FastHit fh = trace_fast<false, false>(P.fast, ray, active, st, n_nodes);   // warp-cooperative
+#endif
     if (active) {
         st_stream(B.prim + 2 * (size_t)pix, make_float4(ray.d.x, ray.d.y, ray.d.z, fh.t));
         st_stream(B.prim + 2 * (size_t)pix + 1, make_float4(__uint_as_float(fh.hit ? 1u : 0u), __uint_as_float(fh.cx | (fh.cz << 13)),
@@ -618,7 +637,7 @@ __device__ __forceinline__ uint32_t pend_pop(const uint32_t (&pend)[F3D_TRACE_DE
 // each: [0] expansion steps [1] lanes expanding [2] leaf phases [3] lanes solving a leaf [4] refill steps [5] rays fetched.
 // Read with f3d_debug_sched_stats(); the CPU emulator (real 32-lane warps) gives the same counts the GPU would.
 #ifdef F3D_SCHED_STATS
-__device__ unsigned long long g_sched_stats[8];
+__device__ unsigned long long g_sched_stats[40];    // [8 + kidx]: sun rays per horizon index, [24 + kidx]: their seeds
 #define F3D_SCHED_STAT(i, mask)                                                                                  \
     do {                                                                                                          \
         const uint32_t _m = __ballot_sync(0xFFFFFFFFu, (mask));                                                   \
@@ -882,8 +901,22 @@ constexpr uint32_t kLeafQFields = 3u;
 // One patch solve of a queued leaf.  Not inlined: k_trace reaches it from several places and the solve (IEEE divisions and
 // their slow paths, ~600 SASS instructions) must exist once per list, or the kernel outgrows the instruction cache
 // (measured: 39 % of the stall samples were "no instruction" with the solve inlined at every site).
+// The patch solve itself, once per CURV instance and kernel: solve_leaf_item and k_ascent's origin-cell solve share it.
+template <bool CURV>
+__device__ __noinline__ bool solve_cell_anyhit(const FastScene& F, float ox, float oy, float oz, float dx, float dy, float dz, float tmax, uint32_t cell) {
+    Ray r;
+    r.o = V3(ox, oy, oz); r.d = V3(dx, dy, dz); r.tmin = 1e-3f; r.tmax = tmax;
+    TraceState L;
+    leaf_ray_setup<CURV>(F, r, L);
+    return leaf_node<true, CURV>(F, L, cell);
+}
+template <bool CURV>
+__device__ __forceinline__ bool solve_origin_cell(const FastScene& F, const TraceState& T, uint32_t cell) {
+    return solve_cell_anyhit<CURV>(F, T.o.x, T.o.y, T.o.z, T.d.x, T.d.y, T.d.z, T.tmax, cell);
+}
+
 template <bool IS_SUN, bool CURV>
-__device__ __noinline__ bool solve_leaf_item(const FrameParams& P, const float4* __restrict__ rec, uint32_t cell, uint32_t pixw, float tmax) {
+__device__ __forceinline__ bool solve_leaf_item(const FrameParams& P, const float4* __restrict__ rec, uint32_t cell, uint32_t pixw, float tmax) {
     const uint32_t pix = pixw & 0x7FFFFFFFu;
     const float4 r0 = __ldcg(rec + 4 * (size_t)pix);
     Ray r;
@@ -894,13 +927,11 @@ __device__ __noinline__ bool solve_leaf_item(const FrameParams& P, const float4*
         const v3 wi = normalize3(ld3(P.light_dir));
         r.d = (pixw >> 31) ? normalize3(wi) : wi;
     } else { const float4 r1 = __ldcg(rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
-    TraceState L;
-    leaf_ray_setup<CURV>(P.fast, r, L);
-    return leaf_node<true, CURV>(P.fast, L, cell);
+    return solve_cell_anyhit<CURV>(P.fast, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, r.tmax, cell);
 }
 
-template <bool IS_SUN, bool CURV, bool ASC>
-__device__ __forceinline__ void trace_list_bu(const FrameParams& P, const BatchSlot& B, const SmemStack st, uint32_t* wq) {
+template <bool IS_SUN, bool CURV, bool ASC, class Q = QGlobal>
+__device__ __forceinline__ void trace_list_bu(const FrameParams& P, const BatchSlot& B, const SmemStack st, uint32_t* wq, const Q qsrc = Q()) {
     const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     const FastScene& F = P.fast;
     const uint32_t n = B.q_counts[IS_SUN ? 4 : 5];
@@ -985,6 +1016,16 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const BatchS
                     }
                     ray_setup<CURV>(F, r, T);
                     cell0 = origin_cell(F, r.o);
+#if F3D_SUN_HORIZON
+                    if (IS_SUN && ASC) {        // the cleared distance k_ascent found (see SunHorizon)
+                        const uint32_t kidx = (uint32_t)(seeds >> 60);
+                        const uint32_t c0maj = P.hz.xmajor ? (cell0 & 0x1FFFu) : (cell0 >> 13);
+                        const int32_t q0 = P.hz.forward ? (int32_t)c0maj : (int32_t)P.hz.ncols - 1 - (int32_t)c0maj;
+                        T.hz_qclear = kidx == kHzNone ? kHzNoClear : q0 + (int32_t)hz_k(kidx);
+                        if (kidx != kHzNone) T.best_t = fminf(T.best_t, horizon_t_clear(P.hz, T, T.hz_qclear));    // caps the conservative tests only
+                        seeds &= 0x0FFFFFFFFFFFFFFFull;
+                    }
+#endif
                     leaf_seeds = (uint32_t)seeds & 15u;
                     seeds >>= 4;
                     // the other seeds are the roots of this ray's traversal: onto the stack, coarsest first
@@ -1023,7 +1064,11 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const BatchS
             bool leaf_kids = false;
             if (busy) {
                 T.sp--;
-                okm = expand_core<true, CURV, ASC>(F, T, st.at(T.sp), bid);
+#if F3D_SUN_HORIZON
+                okm = expand_core<true, CURV, ASC, Q, IS_SUN && ASC>(F, T, st.at(T.sp), bid, qsrc, &P.hz);
+#else
+                okm = expand_core<true, CURV, ASC, Q>(F, T, st.at(T.sp), bid, qsrc);
+#endif
                 n_nodes++;
                 leaf_kids = ((bid >> 26) & 15u) == 0u;
                 if (!leaf_kids) {
@@ -1057,12 +1102,51 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const BatchS
 // the mesh test (hybrid scenes), the patch solve of the cell the ray starts in - every ray needs exactly that one - and the
 // bottom-up start (ascent_seeds).  A ray whose own cell occludes it, or that has no seed left, is DECIDED here; the others
 // are appended (warp ballot + prefix sum, one atomic per warp) to the stage-2 lists k_trace traverses.
-template <bool IS_SUN, bool CURV, bool ASC>
-__device__ __forceinline__ void ascent_list(const FrameParams& P, const BatchSlot& B) {
+// Leaf work items of one k_ascent warp (the near-field walk): same records as k_trace's ring, 64 entries (<= 31 waiting +
+// 32 from one walk step).  All members are called by the 32 lanes of a converged warp.
+constexpr uint32_t kWalkMaxCols = kSunNearMaxCols > kEscNearCols ? kSunNearMaxCols : kEscNearCols;
+constexpr uint32_t kLeafQA = 64u;
+constexpr size_t kAscentRingBytes = (256 / 32) * 3 * kLeafQA * sizeof(uint32_t);     // k_ascent runs 256-thread CTAs
+struct AscentRing {
+    uint32_t* wq;               // [3][kLeafQA] in shared memory: cell id, pixel word, tmax
+    uint32_t head, tail;        // absolute item counters, warp-uniform
+    __device__ __forceinline__ uint32_t size() const { return tail - head; }
+    __device__ __forceinline__ void enqueue(uint32_t m, bool mine, uint32_t lt, uint32_t id, uint32_t pixw, float tmax) {
+        if (mine) {
+            const uint32_t slot = (tail + (uint32_t)__popc(m & lt)) & (kLeafQA - 1u);
+            wq[slot] = id & 0x03FFFFFFu;
+            wq[kLeafQA + slot] = pixw;
+            wq[2u * kLeafQA + slot] = __float_as_uint(tmax);
+        }
+        tail += (uint32_t)__popc(m);
+        __syncwarp();
+    }
+    template <bool IS_SUN, bool CURV>
+    __device__ __forceinline__ void serve(const FrameParams& P, const BatchSlot& B, uint8_t* __restrict__ occl, uint32_t count, uint32_t lane, uint32_t& n_nodes) {
+        if (lane < count) {
+            const uint32_t slot = (head + lane) & (kLeafQA - 1u);
+            const uint32_t hpix = wq[kLeafQA + slot];
+            n_nodes++;
+            if (solve_leaf_item<IS_SUN, CURV>(P, B.rec, wq[slot], hpix, __uint_as_float(wq[2u * kLeafQA + slot]))) occl[hpix & 0x7FFFFFFFu] = 1u;
+        }
+        head += count;
+        __syncwarp();
+    }
+};
+
+// PASS 0 = classify: origin-cell solve, then the rays a near-field walk can decide (sun horizon / escape map) are walked
+//          right here and every other undecided ray goes to the FAR list (compacted: warp ballot + one atomic per warp);
+// PASS 1 = the far list: bottom-up start (ascent_seeds) at full lane occupancy -> the stage-2 lists k_trace traverses;
+// PASS 2 = single pass (no walk structure exists for this list): origin-cell solve + bottom-up start, as before the walks.
+// Two passes because the walk and the 11-level seed loop are both long: run in one warp for a mixed set of rays, each
+// executes at partial occupancy (measured: IBL list 16 lanes, +30 % warp-instructions; profiles/r02_walks.md).
+template <bool IS_SUN, bool CURV, bool ASC, int PASS, class Q = QGlobal>
+__device__ __forceinline__ void ascent_list(const FrameParams& P, const BatchSlot& B, uint32_t* wq_warp, const Q qsrc = Q()) {
     const FastScene& F = P.fast;
     const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    const uint32_t n = B.q_counts[IS_SUN ? 0 : 1];
-    const uint32_t* __restrict__ queue = IS_SUN ? B.q_sun : B.q_ibl;
+    const uint32_t n = B.q_counts[PASS == 1 ? (IS_SUN ? 8 : 9) : (IS_SUN ? 0 : 1)];
+    const uint32_t* __restrict__ queue = PASS == 1 ? (IS_SUN ? B.qf_sun : B.qf_ibl) : (IS_SUN ? B.q_sun : B.q_ibl);
+    uint32_t* __restrict__ queue_far = IS_SUN ? B.qf_sun : B.qf_ibl;
     uint32_t* __restrict__ queue2 = IS_SUN ? B.q2_sun : B.q2_ibl;
     unsigned long long* __restrict__ qseeds = IS_SUN ? B.qn_sun : B.qn_ibl;
     uint8_t* __restrict__ occl = IS_SUN ? B.occl_sun : B.occl_ibl;
@@ -1071,11 +1155,15 @@ __device__ __forceinline__ void ascent_list(const FrameParams& P, const BatchSlo
     const bool has_mesh = P.scene.traversal_mode == 0u;
     const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t n_rays = 0u, n_nodes = 0u;
+    AscentRing ring;
+    ring.wq = wq_warp; ring.head = 0u; ring.tail = 0u;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {       // warp-uniform trip count
         const uint32_t i = base + lane;
-        bool want = false;
-        uint32_t pix = 0u;
-        unsigned long long seeds = 0ull;
+        bool want = false, far = false, all_siblings = false;
+        uint32_t pix = 0u, cell0 = 0u;
+        unsigned long long seeds = 0ull, kbits = 0ull;
+        uint32_t near_cols = 0u, near_pixw = 0u;      // near-field walk: columns to visit, 0 = not a walk ray
+        TraceState T{};
         if (i < n) {
             pix = __ldg(queue + i);
             const float4 r0 = __ldcg(B.rec + 4 * (size_t)pix);
@@ -1083,51 +1171,179 @@ __device__ __forceinline__ void ascent_list(const FrameParams& P, const BatchSlo
             r.o = V3(r0.x, r0.y, r0.z); r.tmin = 1e-3f; r.tmax = 1e30f;
             if (IS_SUN) r.d = (__float_as_uint(r0.w) & kRecSunReuseDir) ? wi_reuse : wi;
             else { const float4 r1 = __ldcg(B.rec + 4 * (size_t)pix + 1); r.d = V3(r1.x, r1.y, r1.z); }
-            n_rays++;
+            if (PASS != 1) n_rays++;
             bool mesh_occl = false, decided = false;
-            if (has_mesh) {                      // intersect_hybrid_optimized :213-221
+            if (has_mesh) {                      // intersect_hybrid_optimized :213-221 (PASS 1 only needs the clipped tmax again)
                 const Hit mh = intersect_mesh(P.scene, r);
-                if (mh.hit && mh.t < 0.01f) { occl[pix] = 1u; decided = true; }
+                if (mh.hit && mh.t < 0.01f) { if (PASS != 1) occl[pix] = 1u; decided = true; }
                 else if (mh.hit && mh.t < r.tmax) { r.tmax = mh.t; mesh_occl = true; }
             }
             if (!decided) {
-                TraceState T;
                 ray_setup<CURV>(F, r, T);
-                const uint32_t cell0 = origin_cell(F, r.o);
-                n_nodes++;
-                if (leaf_node<true, CURV>(F, T, cell0)) occl[pix] = 1u;
-                else {
-                    seeds = ascent_seeds<CURV, ASC>(F, T, cell0);
-                    occl[pix] = mesh_occl ? 1u : 0u;        // stage-2 rays: the default a later leaf hit overwrites
-                    want = seeds != 0ull;
+                cell0 = origin_cell(F, r.o);
+                bool open = true;                // the origin cell does not occlude the ray (PASS 1: known from PASS 0)
+                if (PASS != 1) {
+                    n_nodes++;
+                    open = !solve_origin_cell<CURV>(F, T, cell0);
+                    occl[pix] = (!open || mesh_occl) ? 1u : 0u;        // undecided rays: the default a later leaf hit overwrites
                 }
-#ifdef F3D_SCHED_STATS
-                atomicAdd(&g_sched_stats[IS_SUN ? 6 : 7], (unsigned long long)__popcll(seeds) + (1ull << 32));   // low: seeds, high: rays
+                if (open) {
+                    uint32_t kidx = kHzNone;
+#if F3D_SUN_HORIZON
+                    if (IS_SUN && ASC) {        // ascending sun rays: how far does the near field reach? (see SunHorizon)
+                        kidx = horizon_lookup(P.hz, F, r.o, cell0);
+                        const uint32_t c0maj = P.hz.xmajor ? (cell0 & 0x1FFFu) : (cell0 >> 13);
+                        const int32_t q0 = P.hz.forward ? (int32_t)c0maj : (int32_t)P.hz.ncols - 1 - (int32_t)c0maj;
+                        T.hz_qclear = kidx == kHzNone ? kHzNoClear : q0 + (int32_t)hz_k(kidx);
+                        if (kidx != kHzNone) T.best_t = fminf(T.best_t, horizon_t_clear(P.hz, T, T.hz_qclear));    // after the solve of cell0
+                    }
 #endif
+                    if (PASS == 0) {             // a walk ray is decided below and never reaches k_trace
+#if F3D_SUN_HORIZON && F3D_SUN_NEAR
+                        if (IS_SUN && ASC && kidx <= kSunNearMaxIdx && !mesh_occl && starts_inside(T, cell0)) {
+                            near_cols = hz_k(kidx);
+                            near_pixw = pix | ((__float_as_uint(r0.w) & kRecSunReuseDir) ? 0x80000000u : 0u);
+                        }
+#endif
+#if F3D_ESCAPE
+                        if (!IS_SUN && !mesh_occl && starts_inside(T, cell0) && escape_cleared(P.esc, F, T, cell0)) {
+                            near_cols = kEscNearCols;
+                            near_pixw = pix;
+                        }
+#endif
+                        far = near_cols == 0u;
+                    } else {
+#if F3D_SUN_HORIZON
+                        if (IS_SUN && ASC) {
+                            seeds = ascent_seeds<CURV, ASC, Q, true>(F, T, cell0, qsrc, &P.hz, &all_siblings);
+                            kbits = (unsigned long long)kidx << 60;           // travels to k_trace with the seeds
+                        } else
+#endif
+                            seeds = ascent_seeds<CURV, ASC, Q>(F, T, cell0, qsrc, nullptr, &all_siblings);
+                        want = true;
+                    }
+                }
             }
         }
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
-        if (m != 0u) {
-            uint32_t b2 = 0u;
-            if (lane == 0u) b2 = atomicAdd(B.q_counts + (IS_SUN ? 4 : 5), (uint32_t)__popc(m));
-            b2 = __shfl_sync(0xFFFFFFFFu, b2, 0);
-            if (want) {
-                const uint32_t slot = b2 + (uint32_t)__popc(m & lt);
-                queue2[slot] = pix;
-                qseeds[slot] = seeds;
+        if (PASS == 0) {                         // far rays: compacted into the far list
+            const uint32_t mf = __ballot_sync(0xFFFFFFFFu, far);
+            if (mf != 0u) {
+                uint32_t bf = 0u;
+                if (lane == 0u) bf = atomicAdd(B.q_counts + (IS_SUN ? 8 : 9), (uint32_t)__popc(mf));
+                bf = __shfl_sync(0xFFFFFFFFu, bf, 0);
+                if (far) queue_far[bf + (uint32_t)__popc(mf & lt)] = pix;
+            }
+        } else {
+            // rays that start within the pad of a cell border (or outside the DEM): every existing sibling is a seed (warp-cooperative)
+            for (uint32_t fb = __ballot_sync(0xFFFFFFFFu, all_siblings); fb != 0u; fb &= fb - 1u) {
+                const int src = __ffs((int)fb) - 1;
+                const unsigned long long sd = all_sibling_seeds_warp(F, __shfl_sync(0xFFFFFFFFu, cell0, src));
+                if ((int)lane == src) seeds = sd;
+            }
+            want = want && seeds != 0ull;
+#ifdef F3D_SCHED_STATS
+            if (i < n) {
+                atomicAdd(&g_sched_stats[IS_SUN ? 6 : 7], (unsigned long long)__popcll(seeds) + (1ull << 32));   // low: seeds, high: rays
+                if (IS_SUN) { atomicAdd(&g_sched_stats[8 + (kbits >> 60)], 1ull); atomicAdd(&g_sched_stats[24 + (kbits >> 60)], (unsigned long long)__popcll(seeds)); }
+            }
+#endif
+            seeds |= kbits;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+            if (m != 0u) {
+                uint32_t b2 = 0u;
+                if (lane == 0u) b2 = atomicAdd(B.q_counts + (IS_SUN ? 4 : 5), (uint32_t)__popc(m));
+                b2 = __shfl_sync(0xFFFFFFFFu, b2, 0);
+                if (want) {
+                    const uint32_t slot = b2 + (uint32_t)__popc(m & lt);
+                    queue2[slot] = pix;
+                    qseeds[slot] = seeds;
+                }
             }
         }
+#if (F3D_SUN_HORIZON && F3D_SUN_NEAR) || F3D_ESCAPE
+        // near-field walk, warp-convergent: column by column every walk ray of the warp tests the (at most three) cells its line
+        // touches there; survivors of the conservative test are queued and solved 32 at a time
+        if (PASS == 0 && __ballot_sync(0xFFFFFFFFu, near_cols != 0u) != 0u) {
+            constexpr bool WALK_ASC = IS_SUN ? ASC : true;        // escape-map rays ascend (escape_cleared)
+            WalkDir wd{};
+            NearWalk N{};
+            if (near_cols != 0u) {
+                wd = IS_SUN ? walk_dir(P.hz) : walk_dir(F, T.d);
+                N = near_walk_setup(wd, F, T.o, cell0);
+            }
+            const int32_t nrows = (int32_t)(wd.xmajor ? F.cell_h : F.cell_w);
+            const float2* __restrict__ lv0 = F.q.lv[0];            // the global arena (a staged copy needs no prefetch)
+            // every [min,max] the walk will read is requested up front (one prefetch per column end: rows r_lo and r_hi sit in
+            // the same or in adjacent 32-byte quads), so the column steps below do not each wait for their own L2 round trip
+            for (uint32_t c = 0; c < kWalkMaxCols; c++) {
+                int32_t cmaj = 0, r_lo = 0, r_hi = -1;
+                if (c < near_cols && near_walk_column(wd, N, c, cmaj, r_lo, r_hi)) {
+                    const uint32_t ra = (uint32_t)min(max(r_lo, 0), nrows - 1), rb = (uint32_t)min(max(r_hi, 0), nrows - 1);
+                    const uint32_t xa = wd.xmajor ? (uint32_t)cmaj : ra, za = wd.xmajor ? ra : (uint32_t)cmaj;
+                    const uint32_t xb = wd.xmajor ? (uint32_t)cmaj : rb, zb = wd.xmajor ? rb : (uint32_t)cmaj;
+                    prefetch_l1(lv0 + ((za >> 1) * F.q.parent_pitch[0] + (xa >> 1)) * 4u);
+                    prefetch_l1(lv0 + ((zb >> 1) * F.q.parent_pitch[0] + (xb >> 1)) * 4u);
+                }
+            }
+            for (uint32_t c = 0; c < kWalkMaxCols; c++) {
+                if (__ballot_sync(0xFFFFFFFFu, c < near_cols) == 0u) break;
+                int32_t cmaj = 0, r_lo = 0, r_hi = -1;
+                const bool col_on = c < near_cols && near_walk_column(wd, N, c, cmaj, r_lo, r_hi);
+                uint32_t pass = 0u;
+                if (col_on) {
+#pragma unroll
+                    for (int32_t rr = 0; rr < 3; rr++) {
+                        const int32_t r = r_lo + rr;
+                        if (r <= r_hi && r >= 0 && r < nrows) {
+                            const uint32_t cx = wd.xmajor ? (uint32_t)cmaj : (uint32_t)r, cz = wd.xmajor ? (uint32_t)r : (uint32_t)cmaj;
+                            if (((cz << 13) | cx) != cell0 && cell_may_pass<CURV, WALK_ASC, Q>(F, T, cx, cz, qsrc)) pass |= 1u << rr;
+                        }
+                    }
+                }
+                if (__ballot_sync(0xFFFFFFFFu, pass != 0u) == 0u) continue;
+#pragma unroll
+                for (int32_t rr = 0; rr < 3; rr++) {
+                    const bool mine = ((pass >> rr) & 1u) != 0u;
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+                    if (m != 0u) {
+                        const uint32_t r = (uint32_t)(r_lo + rr);
+                        const uint32_t id = wd.xmajor ? ((r << 13) | (uint32_t)cmaj) : (((uint32_t)cmaj << 13) | r);
+                        ring.enqueue(m, mine, lt, id, near_pixw, T.tmax);
+                        if (ring.size() >= 32u) ring.template serve<IS_SUN, CURV>(P, B, occl, 32u, lane, n_nodes);
+                    }
+                }
+            }
+        }
+#endif
     }
+    if (ring.size() != 0u) ring.template serve<IS_SUN, CURV>(P, B, occl, ring.size(), lane, n_nodes);
     warp_add_counters(P.counters, 0u, IS_SUN ? n_rays : 0u, IS_SUN ? 0u : n_rays, n_nodes);
 }
 
 // SUN_MODE as for k_trace: 2 = the sun list is left to the top-down tracer.
-template <bool CURV_SUN, int SUN_MODE>
-__global__ void __launch_bounds__(256) k_ascent(const __grid_constant__ FrameParams P) {
+#ifndef F3D_ASCENT_MIN_CTAS
+#define F3D_ASCENT_MIN_CTAS 3       // 85 registers: the near-field walk keeps the ray's culling constants live
+#endif
+// One kernel per LIST (IS_SUN): the exact patch solve, the walk and the bottom-up start of one list are ~3 k SASS
+// instructions; both lists in one kernel (6.2 k, 99 KB) outgrew the instruction cache - measured: 4.1 of 12 stall cycles per
+// issued instruction were "no instruction", k_ascent 0.75 -> 1.16 ms per batch (profiles/r02_ascent_icache.md).
+template <bool IS_SUN, bool CURV_SUN, int SUN_MODE, int PASS>
+__global__ void __launch_bounds__(256, F3D_ASCENT_MIN_CTAS) k_ascent(const __grid_constant__ FrameParams P) {
+    // dynamic shared memory: one AscentRing per warp (kAscentRingBytes), then the staged top levels (F3D_TMA_STAGE)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* wq_warp = reinterpret_cast<uint32_t*>(smem_raw) + (threadIdx.x >> 5) * (3u * kLeafQA);
+#if F3D_TMA_STAGE
+    const QStaged qs = stage_top_levels(P.fast, P.stage[1], smem_raw + kAscentRingBytes);
     for (uint32_t b = 0; b < P.n_batch; b++) {
-        if (SUN_MODE != 2) ascent_list<true, CURV_SUN, SUN_MODE == 1>(P, P.slot[b]);
-        ascent_list<false, false, false>(P, P.slot[b]);
+        if (IS_SUN) ascent_list<true, CURV_SUN, SUN_MODE == 1, PASS, QStaged>(P, P.slot[b], wq_warp, qs);
+        else ascent_list<false, false, false, PASS, QStaged>(P, P.slot[b], wq_warp, qs);
     }
+#else
+    for (uint32_t b = 0; b < P.n_batch; b++) {
+        if (IS_SUN) ascent_list<true, CURV_SUN, SUN_MODE == 1, PASS>(P, P.slot[b], wq_warp);
+        else ascent_list<false, false, false, PASS>(P, P.slot[b], wq_warp);
+    }
+#endif
 }
 
 // One persistent launch walks the sun list, then the IBL list: a warp that runs out of sun rays moves
@@ -1144,7 +1360,14 @@ __global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(
     // per-warp leaf ring behind the stacks
     uint32_t* wq = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)P.stack_depth * kTraceCtaThreads + (threadIdx.x >> 5) * (kLeafQBU * kLeafQFields);
     // every sun list of the batch, then every IBL list: a warp that runs out of rays in one list moves straight on to the next
-#if F3D_TRACE_BOTTOM_UP
+#if F3D_TRACE_BOTTOM_UP && F3D_TMA_STAGE
+    const QStaged qs = stage_top_levels(P.fast, P.stage[2], smem_raw + ((trace_smem_bytes_for(P.stack_depth, kTraceCtaThreads) + 15) & ~(size_t)15));
+    for (uint32_t b = 0; b < P.n_batch; b++) {
+        if (SUN_MODE == 2) trace_list<true, CURV_SUN, true>(P, P.slot[b], st, wq);
+        else trace_list_bu<true, CURV_SUN, SUN_MODE == 1, QStaged>(P, P.slot[b], st, wq, qs);
+    }
+    for (uint32_t b = 0; b < P.n_batch; b++) trace_list_bu<false, false, false, QStaged>(P, P.slot[b], st, wq, qs);
+#elif F3D_TRACE_BOTTOM_UP
     for (uint32_t b = 0; b < P.n_batch; b++) {
         if (SUN_MODE == 2) trace_list<true, CURV_SUN, true>(P, P.slot[b], st, wq);
         else trace_list_bu<true, CURV_SUN, SUN_MODE == 1>(P, P.slot[b], st, wq);
@@ -1162,7 +1385,7 @@ __global__ void __launch_bounds__(kTraceCtaThreads, F3D_TRACE_MIN_CTAS) k_trace(
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_accum(const __grid_constant__ FrameParams P) {
     uint32_t gx, gy;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 8u * P.n_batch) P.slot[threadIdx.x >> 3].q_counts[threadIdx.x & 7u] = 0u;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < kQCounts * P.n_batch) P.slot[threadIdx.x / kQCounts].q_counts[threadIdx.x % kQCounts] = 0u;
     if (!owned_pixel(P, gx, gy)) return;
     const uint32_t pix = gy * P.W + gx;
     const uint32_t spp = max(P.spp, 1u), window = max(P.window, 2u);
@@ -1417,6 +1640,105 @@ __global__ void k_reduce_level(const float2* __restrict__ prev, uint32_t lw, uin
 // Quad-packs one plain level for the production traversal: slot (x, y) of the level goes to
 // quads[((y>>1) * parent_pitch + (x>>1)) * 4 + ((y&1)*2 + (x&1))]; slots outside the level hold the
 // (+inf, -inf) sentinel (never visited: their cells lie outside the DEM).
+// ---------------------------------------------------------------------------------------------
+// Sun horizon strips (see SunHorizon in f3d_trace_fast.cuh), built once per session.
+// k_hz_build: one thread per (travel column q, strip j): F = Hs[j][q] - q g in double, rounded UP to f32.
+// k_hz_suffix: one thread per strip: in-place suffix maximum over the columns (coalesced across strips).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_hz_build(const float4* __restrict__ cells, uint32_t cell_w, uint32_t cell_h, const SunHorizon Z, double m, double g,
+                           float* __restrict__ F) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
+    if (j >= Z.nstrips) return;
+    const uint32_t nrows = Z.xmajor ? cell_h : cell_w;
+    const uint32_t i = Z.forward ? q : Z.ncols - 1u - q;
+    const double jw = (double)((int32_t)j + Z.j0), d = 1.0 / 64.0;
+    const double lo = jw - d + fmin(m * (double)i, m * ((double)i + 1.0)), hi = jw + 1.0 + d + fmax(m * (double)i, m * ((double)i + 1.0));
+    long long r0 = (long long)floor(lo), r1 = (long long)floor(hi);
+    if (r0 < 0) r0 = 0;
+    if (r1 > (long long)nrows - 1) r1 = (long long)nrows - 1;
+    float hs = -3.0e38f;
+    for (long long r = r0; r <= r1; r++) {
+        const uint32_t cx = Z.xmajor ? i : (uint32_t)r, cz = Z.xmajor ? (uint32_t)r : i;
+        const float4 h = cells[(size_t)cz * cell_w + cx];
+        hs = fmaxf(hs, fmaxf(fmaxf(h.x, h.y), fmaxf(h.z, h.w)));
+    }
+    F[(size_t)q * Z.nstrips + j] = hs > -1.0e38f ? __double2float_ru((double)hs - (double)q * g) : -3.0e38f;
+}
+
+// One WARP per strip (a thread per strip walked 2047 columns serially: 0.93 ms of every session's 1.07 ms set-up): each lane
+// takes a contiguous chunk of columns, reduces it, the 32 chunk maxima are suffix-scanned with shuffles, then every lane
+// rewrites its chunk seeded with the maximum of all later chunks.  max is exact in any order: same bytes as the serial scan.
+__global__ void __launch_bounds__(256) k_hz_suffix(float* __restrict__ S, uint32_t nstrips, uint32_t ncols) {
+    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (j >= nstrips) return;                                  // warp-uniform
+    const uint32_t chunk = (ncols + 31u) / 32u;
+    const uint32_t q0 = min(lane * chunk, ncols), q1 = min(q0 + chunk, ncols);
+    float mine = -3.0e38f;
+    for (uint32_t q = q0; q < q1; q++) mine = fmaxf(mine, S[(size_t)q * nstrips + j]);
+    float later = -3.0e38f;                                    // maximum over the chunks of the lanes above this one
+    float run = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {                         // inclusive suffix maximum over lanes
+        const float o = __shfl_down_sync(0xFFFFFFFFu, run, d);
+        if (lane + (uint32_t)d < 32u) run = fmaxf(run, o);
+    }
+    later = __shfl_down_sync(0xFFFFFFFFu, run, 1);
+    if (lane == 31u) later = -3.0e38f;
+    float acc = later;
+    for (uint32_t q = q1; q > q0; q--) {
+        const size_t k = (size_t)(q - 1u) * nstrips + j;
+        acc = fmaxf(acc, S[k]);
+        S[k] = acc;
+    }
+}
+
+// Escape map (see EscapeMap in f3d_trace_fast.cuh), built once per session: one thread per DEM cell, 32 consecutive cells of
+// a row per warp (they share the coarse levels' ring nodes: broadcast loads).  Per level the ring of (2 kEscOuter + 1)^2 -
+// (2 kEscR + 1)^2 nodes around the cell's ancestor; per node one load of its maximum, the smallest distance from the
+// (widened) cell to the node's rectangle, one rsqrt, and a running maximum per octant the node can be reached in.
+__global__ void __launch_bounds__(128) k_escape_build(const FastScene F, const EscapeOctTable O, const float pad_abs, float* __restrict__ E) {
+    const uint32_t cx = blockIdx.x * blockDim.x + threadIdx.x, cz = blockIdx.y;
+    if (cx >= F.cell_w || cz >= F.cell_h) return;
+    const float4 h = F.cells[(size_t)cz * F.cell_w + cx];
+    const float href = fminf(fminf(h.x, h.y), fminf(h.z, h.w)) - pad_abs;
+    float e[8];
+#pragma unroll
+    for (int o = 0; o < 8; o++) e[o] = 0.0f;         // slopes <= 0 are never needed: only ascending rays ask
+    for (uint32_t k = 0; k + 1u < F.mip_count; k++) {
+        const int32_t lw = (int32_t)((F.cell_w + (1u << k) - 1u) >> k), lh = (int32_t)((F.cell_h + (1u << k) - 1u) >> k);
+        if (lw <= kEscR + 1 && lh <= kEscR + 1) break;          // the inner block is the whole level: everything is covered
+        const int32_t px = (int32_t)(cx >> k), pz = (int32_t)(cz >> k);
+        const float2* __restrict__ lv = F.q.lv[k];
+        const uint32_t pitch = F.q.parent_pitch[k];
+        for (int32_t oz = -kEscOuter; oz <= kEscOuter; oz++) {
+            const int32_t jz = pz + oz;
+            if (jz < 0 || jz >= lh) continue;
+            const int32_t z0 = jz << k, z1 = min((jz + 1) << k, (int32_t)F.cell_h);
+            const float gz = fmaxf((float)max(max(z0 - (int32_t)(cz + 1u), (int32_t)cz - z1), 0) - 0.015625f, 0.0f) * F.sz;
+            const bool inner_z = oz >= -kEscR && oz <= kEscR;
+            for (int32_t ox = -kEscOuter; ox <= kEscOuter; ox++) {
+                if (inner_z && ox >= -kEscR && ox <= kEscR) continue;
+                const int32_t jx = px + ox;
+                if (jx < 0 || jx >= lw) continue;
+                const float mx = __ldg(&lv[((size_t)(jz >> 1) * pitch + (size_t)(jx >> 1)) * 4u + ((jz & 1) * 2 + (jx & 1))].y);
+                const int32_t x0 = jx << k, x1 = min((jx + 1) << k, (int32_t)F.cell_w);
+                const float gx = fmaxf((float)max(max(x0 - (int32_t)(cx + 1u), (int32_t)cx - x1), 0) - 0.015625f, 0.0f) * F.sx;
+                const float num = mx - href;                     // pad_abs on both ends
+                if (!(num > 0.0f)) continue;
+                float sl = num * rsqrtf(gx * gx + gz * gz);      // D > 0: a ring node is >= kEscR whole nodes away on one axis
+                sl = sl * 1.00001f;                              // rsqrt.approx (2^-22) and the products above, rounded up
+                const uint32_t mask = O.m[oz + kEscOuter][ox + kEscOuter];
+#pragma unroll
+                for (int o = 0; o < 8; o++)
+                    if ((mask >> o) & 1u) e[o] = fmaxf(e[o], sl);
+            }
+        }
+    }
+    float4* out = reinterpret_cast<float4*>(E + ((size_t)cz * F.cell_w + cx) * 8u);
+    out[0] = make_float4(e[0], e[1], e[2], e[3]);
+    out[1] = make_float4(e[4], e[5], e[6], e[7]);
+}
+
 __global__ void k_pack_quads(const float2* __restrict__ plain, uint32_t lw, uint32_t lh, float2* __restrict__ quads,
                              uint32_t parent_pitch, uint32_t parent_h) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;

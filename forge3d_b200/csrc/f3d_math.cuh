@@ -21,15 +21,39 @@ __device__ __forceinline__ v3 operator-(v3 a, v3 b) { return V3(a.x - b.x, a.y -
 __device__ __forceinline__ v3 operator*(v3 a, v3 b) { return V3(a.x * b.x, a.y * b.y, a.z * b.z); }
 __device__ __forceinline__ v3 operator*(v3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ v3 operator-(v3 a) { return V3(-a.x, -a.y, -a.z); }
+// F3D_FAST_NUMERICS = 1 builds the THROUGHPUT variant of the library (libforge3d_b200_fast.so, forge3d_b200/build.py
+// numerics="fast": also -fmad=true): division, reciprocal and square root are the SFU approximations (2 ulp / 1 ulp) instead
+// of the correctly rounded sequences, normalize uses rsqrt, and the compiler may contract a*b+c.  Outputs are then no longer
+// bit-identical to the oracle; the variant is accepted by the north-star tolerance instead (RGBA RMSE <= 1e-3 against the exact
+// build, tests/test_gpu_parity.py).  0 (default) = the numerics contract above.
+#ifndef F3D_FAST_NUMERICS
+#define F3D_FAST_NUMERICS 0
+#endif
+#if F3D_FAST_NUMERICS && defined(__CUDA_ARCH__)
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float frcp(float a) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float fsqrt(float a) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+__device__ __forceinline__ float frsqrt(float a) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r; }
+#else
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }
 __device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float frsqrt(float a) { return __frcp_rn(__fsqrt_rn(a)); }
+#endif
+// Requests a line into L1 without a destination register (no-op on the host builds of this header).
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 __device__ __forceinline__ float dot3(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 __device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) { return ax * bx + ay * by; }
 __device__ __forceinline__ v3 cross3(v3 a, v3 b) {
     return V3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
 }
-__device__ __forceinline__ v3 normalize3(v3 a) { return a * frcp(fsqrt(dot3(a, a))); }
+__device__ __forceinline__ v3 normalize3(v3 a) { return a * frsqrt(dot3(a, a)); }
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ float luminance(v3 c) { return dot3(c, V3(0.2126f, 0.7152f, 0.0722f)); }

@@ -21,6 +21,11 @@ struct f3d_smoke {
     uint32_t occ_dims[3] = {0, 0, 0};
     uint8_t* d_rgba = nullptr;
     size_t rgba_capacity = 0;
+    uint8_t* d_base = nullptr;        // smoke over terrain: staged base RGBA and depth (f3d_smoke_raymarch_over_rgba)
+    float* d_depth = nullptr;
+    size_t base_capacity = 0;
+    const uint8_t* over_base = nullptr;   // host pointers of the call in flight
+    const float* over_depth = nullptr;
     uint32_t dims[3] = {0, 0, 0};
     float voxel[3] = {0, 0, 0}, origin[3] = {0, 0, 0};
     uint32_t frame_index = 0;
@@ -31,7 +36,7 @@ extern "C" void f3d_smoke_destroy(f3d_smoke* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cached_free(s->volA, s->device); cached_free(s->volB, s->device); cached_free(s->d_rgba, s->device);
-    cached_free(s->occ, s->device);
+    cached_free(s->occ, s->device); cached_free(s->d_base, s->device); cached_free(s->d_depth, s->device);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -147,7 +152,8 @@ static void smoke_common_params(const f3d_smoke* s, const f3d_smoke_settings* st
     P->frame_index = s->frame_index;
 }
 
-static int smoke_launch(f3d_smoke* s, SmokeParams* P, uint32_t width, uint32_t height, uint8_t* rgba, double* kernel_ms) {
+static int smoke_launch(f3d_smoke* s, SmokeParams* P, uint32_t width, uint32_t height, uint8_t* rgba, double* kernel_ms,
+                        const uint8_t* base_rgba = nullptr, const float* base_depth = nullptr) {
     if ((uint64_t)width * height > (1ull << 31)) return fail(F3D_ERR_ARGUMENT, "image of %ux%u pixels exceeds the 2^31-pixel addressing limit", width, height);
     const size_t bytes = (size_t)width * height * 4;
     CUDA_TRY(cudaSetDevice(s->device));
@@ -159,6 +165,19 @@ static int smoke_launch(f3d_smoke* s, SmokeParams* P, uint32_t width, uint32_t h
         s->rgba_capacity = bytes;
     }
     P->W = width; P->H = height; P->rgba = s->d_rgba;
+    P->base = nullptr; P->depth = nullptr;
+    if (base_rgba || base_depth) {           // the terrain frame the layer goes over: staged beside the output
+        if (s->base_capacity < bytes) {
+            cudaStreamSynchronize(s->stream);
+            cached_free(s->d_base, s->device); cached_free(s->d_depth, s->device);
+            s->d_base = nullptr; s->d_depth = nullptr; s->base_capacity = 0;
+            CUDA_TRY(cached_malloc((void**)&s->d_base, bytes, s->device));
+            CUDA_TRY(cached_malloc((void**)&s->d_depth, bytes, s->device));
+            s->base_capacity = bytes;
+        }
+        if (base_rgba) { CUDA_TRY(cudaMemcpyAsync(s->d_base, base_rgba, bytes, cudaMemcpyHostToDevice, s->stream)); P->base = (const uchar4*)s->d_base; }
+        if (base_depth) { CUDA_TRY(cudaMemcpyAsync(s->d_depth, base_depth, bytes, cudaMemcpyHostToDevice, s->stream)); P->depth = s->d_depth; }
+    }
     const dim3 grid((width + 15u) / 16u, (height + 7u) / 8u);
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     k_smoke_march<<<grid, kSmokeThreads, 0, s->stream>>>(*P);
@@ -202,7 +221,19 @@ extern "C" int f3d_smoke_raymarch_rgba(f3d_smoke* s, const f3d_smoke_settings* s
     P.tan_half_fov = tanf(to_radians_f32(fovy_deg) * 0.5f);
     P.aspect = (float)width / (float)height;
     P.sun_dir[0] = sun.x; P.sun_dir[1] = sun.y; P.sun_dir[2] = sun.z;
-    return smoke_launch(s, &P, width, height, rgba, kernel_ms);
+    return smoke_launch(s, &P, width, height, rgba, kernel_ms, s->over_base, s->over_depth);
+}
+
+extern "C" int f3d_smoke_raymarch_over_rgba(f3d_smoke* s, const f3d_smoke_settings* st, uint32_t width, uint32_t height,
+                                            const float camera_pos[3], const float target[3], const float up_in[3], float fovy_deg,
+                                            const float sun_direction[3], const uint8_t* base_rgba, const float* base_depth,
+                                            uint8_t* rgba, double* kernel_ms) {
+    g_err[0] = 0;
+    if (!base_rgba) return fail(F3D_ERR_ARGUMENT, "null argument");
+    s->over_base = base_rgba; s->over_depth = base_depth;
+    const int rc = f3d_smoke_raymarch_rgba(s, st, width, height, camera_pos, target, up_in, fovy_deg, sun_direction, rgba, kernel_ms);
+    s->over_base = nullptr; s->over_depth = nullptr;
+    return rc;
 }
 
 extern "C" int f3d_smoke_raymarch_projection_rgba(f3d_smoke* s, const f3d_smoke_settings* st, uint32_t width, uint32_t height,

@@ -49,6 +49,9 @@ struct SmokeParams {
     float dir[3], diagonal;                                            // projection
     float sun_dir[3];
     uint8_t* rgba;          // H x W x 4
+    // smoke over a terrain frame (BASELINE config 4): both NULL = the bare layer, exactly the reference's raymarch_rgba
+    const uchar4* base;     // H x W RGBA8 the layer is composited over (straight-alpha "over", map_scene.py:1588-1604), or NULL
+    const float* depth;     // H x W distance along the camera ray to the opaque surface (NaN / <= 0 = none): clips the march, or NULL
     const uint8_t* occ;     // per 4x4x4 brick of sample cells: 1 = some corner density is non-zero; NULL = no skipping
     uint32_t occ_dims[2];   // bricks along x, y
 };
@@ -141,6 +144,17 @@ __device__ __forceinline__ float smoke_sun_transmittance(const SmokeParams& P, v
 }
 
 // march_ray_rgba, render.rs:190-276
+// Straight-alpha "over" of `top` on `bottom`, the reference's _alpha_composite_rgba (python/forge3d/map_scene.py:1588-1604):
+// alpha = a / 255 in f32, rgb = u8(clip(dst * (1 - alpha) + src * alpha, 0, 255)) (truncation), a = max(dst.a, src.a).
+__device__ __forceinline__ uchar4 composite_over(uchar4 bottom, uchar4 top) {
+    const float alpha = fdiv((float)top.w, 255.0f), keep = 1.0f - alpha;
+    const float r = (float)bottom.x * keep + (float)top.x * alpha;
+    const float g = (float)bottom.y * keep + (float)top.y * alpha;
+    const float b = (float)bottom.z * keep + (float)top.z * alpha;
+    return make_uchar4((unsigned char)rs_clamp(r, 0.0f, 255.0f), (unsigned char)rs_clamp(g, 0.0f, 255.0f),
+                       (unsigned char)rs_clamp(b, 0.0f, 255.0f), bottom.w > top.w ? bottom.w : top.w);
+}
+
 __device__ __forceinline__ uchar4 smoke_march(const SmokeParams& P, v3 origin, v3 dir, float t0, float t1, uint32_t seed, v3 sun_dir) {
     const SmokeSettings& S = P.s;
     const float step = P.step;
@@ -239,7 +253,14 @@ __global__ void __launch_bounds__(kSmokeThreads) k_smoke_march(const SmokeParams
     }
     uchar4 out = make_uchar4(0, 0, 0, 0);
     float t0, t1;
-    if (smoke_ray_box(origin, dir, bmin, bmax, t0, t1)) out = smoke_march(P, origin, dir, fmaxf(t0, 0.0f), t1, seed, sun_dir);
+    if (smoke_ray_box(origin, dir, bmin, bmax, t0, t1)) {
+        if (P.depth != nullptr) {        // smoke behind the terrain is not seen: the march ends at the surface
+            const float d = P.depth[(size_t)y * P.W + x];
+            if (d > 0.0f) t1 = fminf(t1, d);
+        }
+        out = smoke_march(P, origin, dir, fmaxf(t0, 0.0f), t1, seed, sun_dir);
+    }
+    if (P.base != nullptr) out = composite_over(P.base[(size_t)y * P.W + x], out);
     reinterpret_cast<uchar4*>(P.rgba)[(size_t)y * P.W + x] = out;
 }
 

@@ -117,6 +117,125 @@ inline void fast_scene_finish(FastScene& F) {
     if (!(F.mag_y < 1e30f)) F.mag_y = 1e30f;     // flat (+inf,-inf) roots cannot occur (>= 1 cell), keep it finite anyway
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sun horizon strips (F3D_SUN_HORIZON, default 1): an acceleration structure for the ONE direction every sun ray shares.
+// In cell units a sun ray is the line b = w + m a (a = coordinate along the MAJOR axis of the direction, b along the
+// minor one, |m| <= 1), so w = b - m a is constant along the ray: rays with floor(w) = j form STRIP j, and inside the
+// column of cells a in [i, i+1] a ray of strip j can only touch rows floor(j - d + min(m i, m (i+1))) ..
+// floor(j + 1 + d + max(m i, m (i+1))) (at most four; d = 1/64 cell absorbs every rounding of w).  Let Hs[j][q] be the
+// largest corner height of those cells, columns numbered q = 0, 1, .. in TRAVEL order.  An ascending ray (d.y >= 0, the
+// curvature term only lifts it) that starts at travel coordinate e0 and height y0 enters column q at height
+// y0 + (q - e0) g, g = height gained per column, and that is its LOWEST height inside the column.  Hence with
+//     S[q][j] = max over q' >= q of (Hs[j][q'] - q' g)         (one suffix maximum per strip, built once per session)
+// the test  y0 - e0 g - pad > S[q][j]  proves: in every cell of every column >= q the ray's height range lies above the
+// cell's maximum, i.e. the reference's own band test (hybrid_terrain_traversal.wgsl:303-304) rejects each of those leaves
+// without solving it.  Such cells cannot contribute to the occlusion flag, so the tracer may skip every node that lies
+// entirely in columns >= q ("cleared"): an INTEGER test on cell coordinates, no float pads.  What remains is the near
+// field: the origin column and the next k-1 columns, k the smallest of kHzK that clears the ray.  On the C2 scene (sun
+// elevation 24 deg) 69 % of the sun rays are cleared from the second column on, 86 % from the eighth; only 10 % are
+// occluded at all.  Exactness: the flag is an OR over the leaves that pass their own tests (F3D_CULL_FAST (1)-(2)); a
+// cleared leaf fails its band test in the reference's arithmetic - pad covers the f32 evaluation errors of both sides -
+// so dropping it leaves the OR unchanged.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef F3D_SUN_HORIZON
+#define F3D_SUN_HORIZON 1
+#endif
+constexpr int kHzN = 8;
+__host__ __device__ inline uint32_t hz_k(uint32_t idx) {
+    return idx == 0u ? 1u : idx == 1u ? 2u : idx == 2u ? 3u : idx == 3u ? 4u : idx == 4u ? 6u : idx == 5u ? 8u : idx == 6u ? 12u : 16u;
+}
+constexpr uint32_t kHzNone = 15u;
+constexpr int32_t kHzNoClear = 0x7FFFFFFF;
+struct SunHorizon {
+    const float* S;          // [ncols][nstrips]; nullptr = no horizon (descending sun, vertical sun, switched off)
+    uint32_t nstrips, ncols; // ncols = cells along the major axis
+    int32_t j0;              // strip index = floor(w) - j0
+    float m, g;              // minor-per-major slope in cell units; height gained per column of travel (>= 0)
+    float pad_rel, mag;      // pad = pad_rel * (|y0| + e0 g + mag)
+    uint32_t xmajor;         // 1: the major axis is x
+    uint32_t forward;        // 1: the rays travel towards increasing major coordinate
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA staging of the top pyramid levels (F3D_TMA_STAGE, default 0: measured slower, see below).  The quad-packed levels live in ONE arena, finest
+// level first, so the top K levels (everything from level `first` up to the root's children) are one contiguous block
+// at its end: 4^0 + 4^1 + ... quads of 32 bytes, 10.9 KB for the top 5 levels of a 2048^2 DEM.  Every ray of a top-down
+// traversal reads exactly these nodes first, every bottom-up ray reads them last.  Each CTA of the ray kernels copies
+// the block into shared memory ONCE with a single 1-D bulk async copy (cp.async.bulk.shared::cluster.global, the TMA
+// engine: SASS UBLKCP) that signals an mbarrier, and builds a table of per-level base pointers (generic addresses:
+// staged levels point into shared memory, the others into the arena), so a node fetch is one table lookup + plain
+// loads with no "is it staged" branch.  QGlobal / QStaged are the two ways expand_core & co. fetch a quad.
+// ---------------------------------------------------------------------------------------------------------------
+// MEASURED on the B200 (gpurun_out r02l, profiles/r02_tma_staging.md), C2 frame loop, bit-identical images:
+//   staging on 0.961 ms/frame | table only (F3D_B200_TMA_STAGE=0) 0.904 | compiled out (F3D_TMA_STAGE=0) 0.883.
+// The staged nodes are the ones every ray shares, i.e. exactly the lines that already sit in L1 (hit rate 69-75 % in
+// k_ptrace); a per-CTA private copy takes 11-44 KB per CTA out of the SM's unified L1/shared array (k_ascent L1 hit
+// 48 % -> 38 %) and out of the co-residency of the other batch set's kernels.  Default therefore 0; build with
+// -DF3D_TMA_STAGE=1 (forge3d_b200/build.py defines="F3D_TMA_STAGE=1") for the staged variant, which stays bit-exact
+// (tests/test_gpu_parity.py::test_tma_staged_variant_is_bit_identical).
+#ifndef F3D_TMA_STAGE
+#define F3D_TMA_STAGE 0
+#endif
+struct StageParams {
+    const float2* src;       // first staged quad in the arena (16-byte aligned)
+    uint32_t first;          // lowest staged level (levels first .. mip_count-2 are staged); >= mip_count-1: none
+    uint32_t bytes;          // size of the staged block (multiple of 32); 0 = table only
+};
+struct LevelTable { const float2* lv[kMaxLevels]; };
+
+struct QGlobal {
+    __device__ __forceinline__ const float2* base(const FastScene& S, uint32_t cl) const { return S.q.lv[cl]; }
+    __device__ __forceinline__ float2 ld(const float2* p) const { return __ldg(p); }
+};
+struct QStaged {
+    const LevelTable* tab;   // in shared memory
+    __device__ __forceinline__ const float2* base(const FastScene&, uint32_t cl) const { return tab->lv[cl]; }
+    __device__ __forceinline__ float2 ld(const float2* p) const { return *p; }
+};
+__host__ __device__ inline size_t stage_smem_bytes(uint32_t staged_bytes) {      // data + table + mbarrier
+    return (size_t)((staged_bytes + 15u) & ~15u) + sizeof(LevelTable) + 16u;
+}
+
+// Called by EVERY thread of the CTA at kernel entry, converged.  `area` = 16-byte aligned shared memory of
+// stage_smem_bytes(sp.bytes).  Returns the accessor; the staged data is visible to all threads on return.
+__device__ __forceinline__ QStaged stage_top_levels(const FastScene& F, const StageParams sp, unsigned char* area) {
+    const uint32_t data_bytes = (sp.bytes + 15u) & ~15u;
+    LevelTable* tab = reinterpret_cast<LevelTable*>(area + data_bytes);
+    const uint32_t top = F.mip_count - 1u;                 // levels 0 .. top-1 have quads
+    if (threadIdx.x < (uint32_t)kMaxLevels) {
+        const uint32_t l = threadIdx.x;
+        const float2* g = F.q.lv[l];
+        const bool staged = sp.bytes != 0u && l >= sp.first && l < top;
+        tab->lv[l] = staged ? reinterpret_cast<const float2*>(area) + (g - sp.src) : g;
+    }
+#if defined(__CUDA_ARCH__)
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(area + data_bytes + sizeof(LevelTable));
+    const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(mbar);
+    if (sp.bytes != 0u) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(sp.bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(area)), "l"(sp.src), "r"(sp.bytes), "r"(mbar_s) : "memory");
+        }
+        __syncthreads();                                    // the barrier is initialised for everybody (and the table written)
+        uint32_t done = 0u;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar_s) : "memory");
+        }
+    } else __syncthreads();
+#else
+    if (threadIdx.x == 0)
+        for (uint32_t i = 0; i < sp.bytes / 8u; i++) reinterpret_cast<float2*>(area)[i] = sp.src[i];
+    __syncthreads();
+#endif
+    QStaged q;
+    q.tab = tab;
+    return q;
+}
+
 // Per-ray traversal state.
 struct TraceState {
     v3 o, d;
@@ -136,6 +255,7 @@ struct TraceState {
     // within ex; heights fma(t*t, kc, fma(t, d.y, o.y)) approximate ray_height within ey for |height| <= mag_y.
     float kx, bx, kz, bz, ex, ez, ey, kc;
 #endif
+    int32_t hz_qclear;       // sun horizon: every cell in travel columns >= hz_qclear is cleared (kHzNoClear: none)
 };
 
 template <bool CURV>
@@ -353,15 +473,16 @@ __device__ __forceinline__ void expand_top(const FastScene& S, TraceState& T, co
 // of child 0 (the id of child j is bid ^ (j & 1) ^ ((j >> 1) << 13)).
 // ASC = the ray height is non-decreasing in t (d.y >= 0: an ascending ray, curved or not): the range over a span is
 // [y(t_lo), y(t_hi)], no min/max and no vertex term.
-template <bool ANY_HIT, bool CURV, bool ASC>
-__device__ __forceinline__ uint32_t expand_core(const FastScene& S, const TraceState& T, const uint32_t node, uint32_t& bid) {
+template <bool ANY_HIT, bool CURV, bool ASC, class Q = QGlobal, bool HZ = false>
+__device__ __forceinline__ uint32_t expand_core(const FastScene& S, const TraceState& T, const uint32_t node, uint32_t& bid, const Q q = Q(),
+                                                const SunHorizon* Z = nullptr) {
     const uint32_t level = (node >> 26) & 15u, ny = (node >> 13) & 0x1FFFu, nx = node & 0x1FFFu;
     const uint32_t cl = level - 1u;
     const bool fx = T.inv_x < 0.0f, fz = T.inv_z < 0.0f;
     const uint32_t flip = (fx ? 1u : 0u) | (fz ? 2u : 0u);
     // the children's [min,max]: four 8-byte loads from one 32-byte sector, already in sign order
-    const float2* qp = S.q.lv[cl] + (ny * S.q.parent_pitch[cl] + nx) * 4u;
-    const float2 m0 = __ldg(qp + flip), m1 = __ldg(qp + (flip ^ 1u)), m2 = __ldg(qp + (flip ^ 2u)), m3 = __ldg(qp + (flip ^ 3u));
+    const float2* qp = q.base(S, cl) + (ny * S.q.parent_pitch[cl] + nx) * 4u;
+    const float2 m0 = q.ld(qp + flip), m1 = q.ld(qp + (flip ^ 1u)), m2 = q.ld(qp + (flip ^ 2u)), m3 = q.ld(qp + (flip ^ 3u));
     // cell coordinates of the three planes per axis, exact in f32 (integers <= 2^14)
     const float hs = __uint_as_float((127u + cl) << 23);                    // 2^cl
     const float fx0 = (float)(nx << level), fz0 = (float)(ny << level);
@@ -400,16 +521,21 @@ __device__ __forceinline__ uint32_t expand_core(const FastScene& S, const TraceS
         }
         okm |= ok ? (1u << j) : 0u;
     }
+    if (HZ) {   // sun horizon: children that lie entirely in cleared columns (see SunHorizon) - an integer test
+        const uint32_t nmaj = Z->xmajor ? nx : ny;
+        const int32_t ts = Z->forward ? (int32_t)(nmaj << level) : (int32_t)Z->ncols - (int32_t)((nmaj + 1u) << level);   // first travel column of the node
+        if (ts + (int32_t)(1u << cl) >= T.hz_qclear) okm &= Z->xmajor ? 0x5u : 0x3u;     // drop the far half along the major axis
+    }
     return okm;
 }
 
 // Stack form: pops the internal node on top of the stack and pushes, far child first, the children that may pass.
 // Precondition: sp > 0 and the top is not a leaf.
-template <bool ANY_HIT, bool CURV>
-__device__ __forceinline__ void expand_cull(const FastScene& S, TraceState& T, const SmemStack st) {
+template <bool ANY_HIT, bool CURV, class Q = QGlobal>
+__device__ __forceinline__ void expand_cull(const FastScene& S, TraceState& T, const SmemStack st, const Q q = Q()) {
     T.sp--;
     uint32_t bid;
-    const uint32_t okm = expand_core<ANY_HIT, CURV, false>(S, T, st.at(T.sp), bid);
+    const uint32_t okm = expand_core<ANY_HIT, CURV, false, Q>(S, T, st.at(T.sp), bid, q);
     if (okm & 8u) { st.at(T.sp) = bid ^ (1u | (1u << 13)); T.sp++; }
     if (okm & 4u) { st.at(T.sp) = bid ^ (1u << 13); T.sp++; }
     if (okm & 2u) { st.at(T.sp) = bid ^ 1u; T.sp++; }
@@ -437,6 +563,43 @@ __device__ __forceinline__ uint32_t origin_cell(const FastScene& S, v3 o) {     
     return (cz << 13) | cx;
 }
 
+// Sun horizon lookup for a ray that starts at `o` inside cell `cell0` (origin_cell): the index into kHzK of the smallest
+// k for which every column from q0 + k on is cleared (see SunHorizon), or kHzNone.  All loads are issued together.
+__device__ __forceinline__ uint32_t horizon_lookup(const SunHorizon& Z, const FastScene& S, v3 o, uint32_t cell0) {
+    if (Z.S == nullptr) return kHzNone;
+    const float ua = fdiv(o.x - S.ox, S.sx), ub = fdiv(o.z - S.oz, S.sz);
+    const float a0 = Z.xmajor ? ua : ub, b0 = Z.xmajor ? ub : ua;
+    const uint32_t c0maj = Z.xmajor ? (cell0 & 0x1FFFu) : (cell0 >> 13);
+    const int32_t q0 = Z.forward ? (int32_t)c0maj : (int32_t)Z.ncols - 1 - (int32_t)c0maj;
+    const float e0 = Z.forward ? a0 : (float)Z.ncols - a0;                  // travel coordinate of the origin, in [q0, q0 + 1]
+    if (!(e0 >= (float)q0 - 0.01f && e0 <= (float)q0 + 1.01f)) return kHzNone;     // origin outside the DEM (cell0 is clamped): no claim
+    const float w = b0 - Z.m * a0;
+    const int32_t j = (int32_t)floorf(w) - Z.j0;
+    if (j < 0 || j >= (int32_t)Z.nstrips) return kHzNone;
+    const float eg = e0 * Z.g;
+    const float Y = (o.y - eg) - Z.pad_rel * (fabsf(o.y) + eg + Z.mag);
+    float sv[kHzN];
+#pragma unroll
+    for (int i = 0; i < kHzN; i++) {
+        const int32_t q = q0 + (int32_t)hz_k((uint32_t)i);
+        sv[i] = q < (int32_t)Z.ncols ? __ldg(Z.S + (size_t)q * Z.nstrips + (uint32_t)j) : -3.0e38f;      // beyond the DEM: nothing there
+    }
+    uint32_t idx = kHzNone;
+#pragma unroll
+    for (int i = kHzN - 1; i >= 0; i--)
+        if (Y > sv[i]) idx = (uint32_t)i;
+    return idx;
+}
+
+// The ray parameter at which a sun ray enters travel column q_clear, rounded UP by the culling pad: everything the ray
+// meets after it lies in cleared columns.  Used as the cap of the CONSERVATIVE span tests only (expand_core, ascent_seeds:
+// tcap = min(tmax, best_t)); a node is then dropped iff a lower bound of its entry parameter exceeds the cap, i.e. iff the
+// ray is inside it only beyond the cleared boundary.  Needs cull_setup() done on T.
+__device__ __forceinline__ float horizon_t_clear(const SunHorizon& Z, const TraceState& T, int32_t q_clear) {
+    const float ap = (float)(Z.forward ? q_clear : (int32_t)Z.ncols - q_clear);      // cell coordinate of the boundary plane
+    return Z.xmajor ? __fmaf_rn(ap, T.kx, T.bx) + T.ex : __fmaf_rn(ap, T.kz, T.bz) + T.ez;
+}
+
 // Conservative span + band test of one sibling (see expand_core; same widening).
 template <bool CURV, bool ASC>
 __device__ __forceinline__ bool sibling_may_pass(const TraceState& T, float tl, float th, float2 mm) {
@@ -455,6 +618,144 @@ __device__ __forceinline__ bool sibling_may_pass(const TraceState& T, float tl, 
     return (tl <= th) & !(lo > mm.y || hi < mm.x);
 }
 
+// Conservative own test of ONE cell (span + band, same widening as expand_core): may the reference's pop tests of the
+// level-0 node (cx, cz) pass for this ray?  Used by the near-field walks of k_ascent, which hand the survivors to the exact
+// patch solve (leaf_node re-does the test with the reference's arithmetic).
+template <bool CURV, bool ASC, class Q = QGlobal>
+__device__ __forceinline__ bool cell_may_pass(const FastScene& S, const TraceState& T, const uint32_t cx, const uint32_t cz, const Q q = Q()) {
+    const float2 mm = q.ld(q.base(S, 0u) + ((cz >> 1) * S.q.parent_pitch[0] + (cx >> 1)) * 4u + ((cz & 1u) * 2u + (cx & 1u)));
+    const float fx = (float)cx, fz = (float)cz;
+    const float a0 = __fmaf_rn(fx, T.kx, T.bx), a1 = __fmaf_rn(fx + 1.0f, T.kx, T.bx);
+    const float b0 = __fmaf_rn(fz, T.kz, T.bz), b1 = __fmaf_rn(fz + 1.0f, T.kz, T.bz);
+    const float tl = fmaxf(fmaxf(fminf(a0, a1) - T.ex, fminf(b0, b1) - T.ez), T.tmin);
+    const float th = fminf(fminf(fmaxf(a0, a1) + T.ex, fmaxf(b0, b1) + T.ez), fminf(T.tmax, T.best_t));
+    return sibling_may_pass<CURV, ASC>(T, tl, th, mm);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Near-field walk (F3D_SUN_NEAR, default 1).  A sun ray whose horizon lookup says "cleared from travel column q0 + k on"
+// with a small k can only be occluded inside the k columns it starts in.  In cell units the ray is the line b = w + m a
+// (see SunHorizon), so in the column of cells a in [i, i+1] it can only touch rows floor(w - d + min(m i, m (i+1))) ..
+// floor(w + d + max(m i, m (i+1))): at most three (|m| <= 1; d = 1/32 cell absorbs every rounding of w and of the
+// reference's slab arithmetic, which moves a plane by ~1e-4 cell at most).  k_ascent walks those <= 3 k cells directly -
+// no bottom-up seeds, no k_trace - tests each with cell_may_pass and queues the survivors for the exact patch solve.
+// Exactness: the occlusion flag is the OR of the leaf solves over the cells that pass their OWN span + band test
+// (F3D_CULL_FAST (1)-(2)); every such cell lies in a column the ray touches: columns >= q0 + k are cleared (SunHorizon),
+// columns < q0 are behind the origin (empty clipped span, as for the siblings ascent_seeds drops), and inside the near
+// columns the walk visits a superset of the rows the ray touches.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef F3D_SUN_NEAR
+#define F3D_SUN_NEAR 1
+#endif
+#ifndef F3D_SUN_NEAR_MAX_IDX
+#define F3D_SUN_NEAR_MAX_IDX 3          // index into hz_k: rays cleared within hz_k(3) = 4 columns take the walk
+#endif
+constexpr uint32_t kSunNearMaxIdx = F3D_SUN_NEAR_MAX_IDX;
+constexpr uint32_t kSunNearMaxCols = 4u;    // >= hz_k(kSunNearMaxIdx)
+static_assert(F3D_SUN_NEAR_MAX_IDX <= 3, "the walk visits at most kSunNearMaxCols columns");
+
+// The walk may only replace the bottom-up start for a ray that starts strictly inside its origin cell's slabs (the same
+// condition, with the same widening, under which ascent_seeds drops the siblings behind the ray): then every cell behind
+// the origin cell's entry planes has an empty clipped span in the reference's arithmetic as well.
+__device__ __forceinline__ bool starts_inside(const TraceState& T, const uint32_t cell0) {
+    const float lox = (float)(cell0 & 0x1FFFu), loz = (float)(cell0 >> 13);
+    const bool sgx = T.inv_x < 0.0f, sgz = T.inv_z < 0.0f;
+    const float ex_in = __fmaf_rn(sgx ? lox + 1.0f : lox, T.kx, T.bx), ez_in = __fmaf_rn(sgz ? loz + 1.0f : loz, T.kz, T.bz);
+    return fmaxf(ex_in + T.ex, ez_in + T.ez) < T.tmin;
+}
+// The line a walk follows, in cell units: b = w + m a with a along the major axis (sun rays: shared, from SunHorizon;
+// escape-map rays: per ray).
+struct WalkDir { float m; uint32_t xmajor, forward, ncols; };
+__device__ __forceinline__ WalkDir walk_dir(const SunHorizon& Z) { WalkDir D; D.m = Z.m; D.xmajor = Z.xmajor; D.forward = Z.forward; D.ncols = Z.ncols; return D; }
+__device__ __forceinline__ WalkDir walk_dir(const FastScene& S, v3 d) {
+    WalkDir D;
+    const float du = d.x * S.sz, dv = d.z * S.sx;                    // (d.x / sx, d.z / sz) scaled by sx sz > 0
+    D.xmajor = fabsf(du) >= fabsf(dv) ? 1u : 0u;
+    D.m = D.xmajor ? fdiv(dv, du) : fdiv(du, dv);                    // |m| <= 1 up to rounding; the walk's pad absorbs it
+    D.forward = (D.xmajor ? d.x : d.z) > 0.0f ? 1u : 0u;
+    D.ncols = D.xmajor ? S.cell_w : S.cell_h;
+    return D;
+}
+// Per-ray constants of the walk: major-axis cell of the origin, line offset w.
+struct NearWalk { float w; uint32_t c0maj; };
+__device__ __forceinline__ NearWalk near_walk_setup(const WalkDir& Z, const FastScene& S, v3 o, uint32_t cell0) {
+    const float ua = fdiv(o.x - S.ox, S.sx), ub = fdiv(o.z - S.oz, S.sz);
+    NearWalk N;
+    N.w = (Z.xmajor ? ub : ua) - Z.m * (Z.xmajor ? ua : ub);
+    N.c0maj = Z.xmajor ? (cell0 & 0x1FFFu) : (cell0 >> 13);
+    return N;
+}
+// Rows the ray can touch in travel column q0 + i (absolute major cell index returned in `cmaj`); false: the column lies
+// outside the DEM.  r_lo .. r_hi may reach outside [0, nrows): the caller clips.
+__device__ __forceinline__ bool near_walk_column(const WalkDir& Z, const NearWalk& N, uint32_t i, int32_t& cmaj, int32_t& r_lo, int32_t& r_hi) {
+    cmaj = Z.forward ? (int32_t)N.c0maj + (int32_t)i : (int32_t)N.c0maj - (int32_t)i;
+    if (cmaj < 0 || cmaj >= (int32_t)Z.ncols) return false;
+    const float e0 = Z.m * (float)cmaj, e1 = Z.m * (float)(cmaj + 1);
+    r_lo = (int32_t)floorf(N.w - 0.03125f + fminf(e0, e1));
+    r_hi = (int32_t)floorf(N.w + 0.03125f + fmaxf(e0, e1));
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Escape map (F3D_ESCAPE, default 1): the directional generalisation of the sun horizon, for rays of ANY direction (the IBL
+// rays).  Per DEM cell c and per octant o of the horizontal direction (sign of x, sign of z, which axis is the major one, in
+// cell units) the map holds E[c][o] >= (hmax(c') + pad - hmin(c)) / D(c, c') for EVERY cell c' that (a) lies further than
+// kEscR cells (Chebyshev) from c and (b) can be reached from a point of c along a direction of octant o; D = the smallest
+// horizontal distance between a point of c (widened by 1/64 cell) and a point of c'.  An ascending ray (d.y > 0, no
+// curvature term) that starts inside c at a height >= hmin(c) with slope d.y / |d.xz| > E[c][o] is, inside every such c',
+// above hmax(c'): its clipped span there starts no earlier than D / |d.xz| along the ray (the slab planes are the
+// reference's, moved by <= 1e-3 cell by its rounding), its height is non-decreasing, so the low end of the reference's
+// band test (hybrid_terrain_traversal.wgsl:303-304) exceeds the cell's maximum and the cell is never solved.  What is left
+// is the near field: the (2 kEscR + 1)^2 block around c, walked like the sun's near field (kEscR + 1 columns of <= 3 rows).
+// The map is built once per session from the min-max pyramid (k_escape_build): level by level the ring of nodes at index
+// distance kEscR+1 .. 2 kEscR+1 around c's ancestor - a level's inner block is covered by the next finer level's inner
+// block plus ring, so the rings of all levels plus the finest inner block (the near field) cover the DEM.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef F3D_ESCAPE
+#define F3D_ESCAPE 1
+#endif
+constexpr int kEscR = 2;
+constexpr int kEscOuter = 2 * kEscR + 1;
+constexpr uint32_t kEscNearCols = (uint32_t)kEscR + 1u;
+struct EscapeMap { const float* E; };       // [cell][8]; nullptr = none
+struct EscapeOctTable { uint8_t m[2 * kEscOuter + 1][2 * kEscOuter + 1]; };   // octant mask of a ring node by its index offset [oz][ox]
+
+// Octants a ring node at index offset (ox, oz) (in units of its level's node size) can be reached in: the offsets between a
+// point of the origin's node and a point of that node fill [ox-1, ox+1] x [oz-1, oz+1].  Octant = sx | sz << 1 | xmajor << 2.
+inline EscapeOctTable escape_oct_table() {
+    EscapeOctTable T{};
+    for (int oz = -kEscOuter; oz <= kEscOuter; oz++)
+        for (int ox = -kEscOuter; ox <= kEscOuter; ox++) {
+            uint8_t mask = 0;
+            for (int sx = 0; sx < 2; sx++)
+                for (int sz = 0; sz < 2; sz++) {
+                    int a0 = sx ? -(ox + 1) : ox - 1, a1 = sx ? -(ox - 1) : ox + 1;
+                    int b0 = sz ? -(oz + 1) : oz - 1, b1 = sz ? -(oz - 1) : oz + 1;
+                    if (a1 < 0 || b1 < 0) continue;
+                    if (a0 < 0) a0 = 0;
+                    if (b0 < 0) b0 = 0;
+                    if (a1 >= b0) mask |= (uint8_t)(1u << (sx | (sz << 1) | 4));       // |dx| >= |dz| somewhere in the box
+                    if (b1 >= a0) mask |= (uint8_t)(1u << (sx | (sz << 1)));
+                }
+            T.m[oz + kEscOuter][ox + kEscOuter] = mask;
+        }
+    return T;
+}
+
+// May the bottom-up start of this ray be replaced by the near-field walk?  (see EscapeMap; T after ray_setup)
+__device__ __forceinline__ bool escape_cleared(const EscapeMap& M, const FastScene& S, const TraceState& T, const uint32_t cell0) {
+    if (M.E == nullptr || !(T.d.y > 0.0f)) return false;
+    const uint32_t cx = cell0 & 0x1FFFu, cz = cell0 >> 13;
+    const float ua = fdiv(T.o.x - S.ox, S.sx), ub = fdiv(T.o.z - S.oz, S.sz);       // the origin really lies in cell0 (it is clamped)
+    const float e = 0.0078125f, fx = (float)cx, fz = (float)cz;
+    if (!(ua >= fx - e && ua <= fx + 1.0f + e && ub >= fz - e && ub <= fz + 1.0f + e)) return false;
+    const float4 h = __ldg(S.cells + (size_t)cz * S.cell_w + cx);
+    if (!(T.o.y >= fminf(fminf(h.x, h.y), fminf(h.z, h.w)))) return false;
+    const uint32_t oct = (T.d.x < 0.0f ? 1u : 0u) | (T.d.z < 0.0f ? 2u : 0u) | (fabsf(T.d.x) * S.sz >= fabsf(T.d.z) * S.sx ? 4u : 0u);
+    const float slope = (T.d.y * frsqrt(T.hd2)) * 0.999755859375f;                  // 1 - 2^-12: lower bound of d.y / |d.xz|
+    return slope > __ldg(M.E + ((size_t)cz * S.cell_w + cx) * 8u + oct);
+}
+
 // Needs ray_setup() done on T (tmin/tmax as the tracer will use them, or looser).
 // Going up one level adds ONE new plane per axis (A_{L+1} extends A_L on its low or its high side), and only an
 // extension on the side the ray travels to can be met: per level 2 fma for the new far planes, three 8-byte loads and up
@@ -463,8 +764,9 @@ __device__ __forceinline__ bool sibling_may_pass(const TraceState& T, float tl, 
 //   z-sibling  [far_z(L), min(far_z(L+1), far_x(L))]
 //   diagonal   [max(far_x(L), far_z(L)), min(far_x(L+1), far_z(L+1))]
 // each bound widened by the per-axis pad, clipped to [tmin, min(tmax, best_t)].
-template <bool CURV, bool ASC>
-__device__ __forceinline__ unsigned long long ascent_seeds(const FastScene& S, const TraceState& T, const uint32_t cell0) {
+template <bool CURV, bool ASC, class Q = QGlobal, bool HZ = false>
+__device__ __forceinline__ unsigned long long ascent_seeds(const FastScene& S, const TraceState& T, const uint32_t cell0, const Q q = Q(),
+                                                           const SunHorizon* Z = nullptr, bool* defer_all_siblings = nullptr) {
     const uint32_t cx0 = cell0 & 0x1FFFu, cz0 = cell0 >> 13;
     const uint32_t top = S.mip_count - 1u;
     const bool sgx = T.inv_x < 0.0f, sgz = T.inv_z < 0.0f;
@@ -474,7 +776,17 @@ __device__ __forceinline__ unsigned long long ascent_seeds(const FastScene& S, c
     float fx = sgx ? txl : txh, fz = sgz ? tzl : tzh;                                   // far planes of A_L
     const bool inside = fmaxf((sgx ? txh : txl) + T.ex, (sgz ? tzh : tzl) + T.ez) < T.tmin;
     unsigned long long seeds = 0ull;
+    // sun horizon: travel column of the origin cell and how many columns remain to the far end of A_L
+    uint32_t hz_c0 = 0u;
+    int32_t hz_k = kHzNoClear;                       // cleared from travel column q0 + hz_k on
+    if (HZ) {
+        const uint32_t c0maj = Z->xmajor ? cx0 : cz0;
+        hz_c0 = Z->forward ? c0maj : ~c0maj;         // low L bits: offset inside A_L along the direction of travel
+        const int32_t q0 = Z->forward ? (int32_t)c0maj : (int32_t)Z->ncols - 1 - (int32_t)c0maj;
+        hz_k = T.hz_qclear == kHzNoClear ? kHzNoClear : T.hz_qclear - q0;
+    }
     if (!inside) {                                   // rare (origin within the pad of a cell border, or outside the DEM):
+        if (defer_all_siblings != nullptr) { *defer_all_siblings = true; return 0ull; }    // the caller runs all_sibling_seeds_warp
         for (uint32_t L = 0; L < top; L++) {         // every sibling that EXISTS is a seed, nothing is tested
             const uint32_t own = (((cz0 >> L) & 1u) << 1) | ((cx0 >> L) & 1u);
             for (uint32_t r = 0; r < 4u; r++) {
@@ -488,8 +800,8 @@ __device__ __forceinline__ unsigned long long ascent_seeds(const FastScene& S, c
     float size = 1.0f;
     for (uint32_t L = 0; L < top; L++) {
         const uint32_t bx = (cx0 >> L) & 1u, bz = (cz0 >> L) & 1u, own = (bz << 1) | bx;
-        const float2* qp = S.q.lv[L] + ((cz0 >> (L + 1u)) * S.q.parent_pitch[L] + (cx0 >> (L + 1u))) * 4u;
-        const float2 mx = __ldg(qp + (own ^ 1u)), mz = __ldg(qp + (own ^ 2u)), md = __ldg(qp + (own ^ 3u));
+        const float2* qp = q.base(S, L) + ((cz0 >> (L + 1u)) * S.q.parent_pitch[L] + (cx0 >> (L + 1u))) * 4u;
+        const float2 mx = q.ld(qp + (own ^ 1u)), mz = q.ld(qp + (own ^ 2u)), md = q.ld(qp + (own ^ 3u));
         // the new plane of A_{L+1} per axis; it is a FAR plane iff the extension is on the side the ray travels to
         const float nx = bx ? lox - size : hix + size, nz = bz ? loz - size : hiz + size;
         if (bx) lox = nx; else hix = nx;
@@ -497,13 +809,35 @@ __device__ __forceinline__ unsigned long long ascent_seeds(const FastScene& S, c
         const bool ax = (bx != 0u) == sgx, az = (bz != 0u) == sgz;
         const float fx1 = ax ? __fmaf_rn(nx, T.kx, T.bx) : fx, fz1 = az ? __fmaf_rn(nz, T.kz, T.bz) : fz;
         const float xl = fx - T.ex, zl = fz - T.ez, xh = fx + T.ex, zh = fz + T.ez, xh1 = fx1 + T.ex, zh1 = fz1 + T.ez;
-        const bool okx = ax && sibling_may_pass<CURV, ASC>(T, fmaxf(xl, T.tmin), fminf(fminf(xh1, zh), tcap), mx);
-        const bool okz = az && sibling_may_pass<CURV, ASC>(T, fmaxf(zl, T.tmin), fminf(fminf(zh1, xh), tcap), mz);
-        const bool okd = ax && az && sibling_may_pass<CURV, ASC>(T, fmaxf(fmaxf(xl, zl), T.tmin), fminf(fminf(xh1, zh1), tcap), md);
+        bool okx = ax && sibling_may_pass<CURV, ASC>(T, fmaxf(xl, T.tmin), fminf(fminf(xh1, zh), tcap), mx);
+        bool okz = az && sibling_may_pass<CURV, ASC>(T, fmaxf(zl, T.tmin), fminf(fminf(zh1, xh), tcap), mz);
+        bool okd = ax && az && sibling_may_pass<CURV, ASC>(T, fmaxf(fmaxf(xl, zl), T.tmin), fminf(fminf(xh1, zh1), tcap), md);
+        if (HZ) {   // the siblings beyond A_L's far plane on the major axis start at travel column q0 + rem: cleared?
+            const int32_t rem = (int32_t)((1u << L) - (hz_c0 & ((1u << L) - 1u)));
+            if (rem >= hz_k) { okd = false; if (Z->xmajor) okx = false; else okz = false; }
+        }
         const uint32_t m = (okx ? (1u << (own ^ 1u)) : 0u) | (okz ? (1u << (own ^ 2u)) : 0u) | (okd ? (1u << (own ^ 3u)) : 0u);
         seeds |= (unsigned long long)m << (4u * L);
         fx = fx1; fz = fz1;
         size = size + size;
+    }
+    return seeds;
+}
+
+// The "every sibling that exists" seeds of one ray (the !inside case above), computed by a whole warp: lane 4 L' + r owns
+// sibling r of level L' (two passes cover 16 levels), the ballots ARE the seed bits.  ~1 % of the rays take this path;
+// run per lane it cost 10 % of k_ascent's warp-instructions at 1.4 active lanes.  Called converged by all 32 lanes.
+__device__ __forceinline__ unsigned long long all_sibling_seeds_warp(const FastScene& S, const uint32_t cell0) {
+    const uint32_t lane = threadIdx.x & 31u, r = lane & 3u;
+    const uint32_t cx0 = cell0 & 0x1FFFu, cz0 = cell0 >> 13, top = S.mip_count - 1u;
+    unsigned long long seeds = 0ull;
+#pragma unroll
+    for (uint32_t pass = 0; pass < 2u; pass++) {
+        const uint32_t L = pass * 8u + (lane >> 2);
+        const uint32_t own = (((cz0 >> L) & 1u) << 1) | ((cx0 >> L) & 1u);
+        const uint32_t gx = ((((cx0 >> (L + 1u)) << 1) | (r & 1u)) << L), gz = ((((cz0 >> (L + 1u)) << 1) | (r >> 1)) << L);
+        const bool bit = L < top && r != own && gx < S.cell_w && gz < S.cell_h;
+        seeds |= (unsigned long long)__ballot_sync(0xFFFFFFFFu, bit) << (32u * pass);
     }
     return seeds;
 }
@@ -596,10 +930,10 @@ __device__ __forceinline__ bool leaf_node(const FastScene& S, TraceState& T, con
 }
 
 // The expansion every caller uses.  EXACT_CULL = true keeps the round-1 expansion (required for descending curved rays).
-template <bool ANY_HIT, bool CURV, bool EXACT_CULL = false>
-__device__ __forceinline__ void expand_node(const FastScene& S, TraceState& T, const SmemStack st) {
+template <bool ANY_HIT, bool CURV, bool EXACT_CULL = false, class Q = QGlobal>
+__device__ __forceinline__ void expand_node(const FastScene& S, TraceState& T, const SmemStack st, const Q q = Q()) {
 #if F3D_CULL_FAST
-    if (!EXACT_CULL) { expand_cull<ANY_HIT, CURV>(S, T, st); return; }
+    if (!EXACT_CULL) { expand_cull<ANY_HIT, CURV, Q>(S, T, st, q); return; }
 #endif
     expand_top<ANY_HIT, CURV>(S, T, st);
 }
@@ -618,8 +952,8 @@ constexpr int kLeafBatch = F3D_LEAF_BATCH;
 #endif
 constexpr int kLeafBatchCoop = F3D_LEAF_BATCH_COOP;   // static-lane traversal (primary / G-buffer rays)
 
-template <bool ANY_HIT, bool CURV>
-__device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, bool valid, const SmemStack st, uint32_t& nodes) {
+template <bool ANY_HIT, bool CURV, class Q = QGlobal>
+__device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, bool valid, const SmemStack st, uint32_t& nodes, const Q q = Q()) {
     TraceState T;
     T.sp = 0u; T.hit = false; T.best_t = r.tmax; T.best_cx = 0u; T.best_cz = 0u;
     if (valid) trace_begin<CURV>(S, r, T, st);
@@ -631,9 +965,9 @@ __device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, 
                 // curved rays: only ascending any-hit rays take the conservative expansion (see F3D_CULL_FAST); this
                 // per-lane choice exists for the KAT seam, the renderer's curved rays all share the sun's direction
                 if (CURV) {
-                    if (ANY_HIT && T.d.y >= 0.0f && T.tmin >= 0.0f) expand_node<ANY_HIT, CURV, false>(S, T, st);
-                    else expand_node<ANY_HIT, CURV, true>(S, T, st);
-                } else expand_node<ANY_HIT, CURV, false>(S, T, st);
+                    if (ANY_HIT && T.d.y >= 0.0f && T.tmin >= 0.0f) expand_node<ANY_HIT, CURV, false, Q>(S, T, st, q);
+                    else expand_node<ANY_HIT, CURV, true, Q>(S, T, st, q);
+                } else expand_node<ANY_HIT, CURV, false, Q>(S, T, st, q);
                 nodes++;
                 if (T.sp == 0u) busy = false;
             }

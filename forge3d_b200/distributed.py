@@ -197,7 +197,11 @@ def _to_host(t):
 class PartitionedRender:
     """One rank's share of a partitioned render (CUDA + NCCL)."""
 
-    def __init__(self, heightmap, width, height, cam=None, *, block_rows: int = 0, group=None, **scene_kw):
+    def __init__(self, heightmap, width, height, cam=None, *, block_rows: int = 0, group=None, mode: str = "exact", **scene_kw):
+        """mode="exact" (default): bit-identical to one GPU - halo rows of the reservoir image and the frame flags travel over
+        NVLink peer memory inside k_shade / k_primary.  mode="gather_only" (SURVEY section 8e-ii): the spatial reuse pass stays
+        inside each row block, ranks exchange NOTHING during the frame loop, the only collective is the final gather; pixels
+        within 4 rows of a block border differ slightly from the one-GPU image (tests/test_multigpu.py bounds the RMSE)."""
         import torch
         import torch.distributed as dist
 
@@ -220,6 +224,9 @@ class PartitionedRender:
         initialised = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size(group) if initialised else 1
         self.rank = dist.get_rank(group) if initialised else 0
+        if mode not in ("exact", "gather_only"):
+            raise ValueError(f"mode must be 'exact' or 'gather_only', got {mode!r}")
+        self.mode = mode
         self.width, self.height, self.block_rows = int(width), int(height), int(block_rows)
         self.device = torch.cuda.current_device()
         self.stream = torch.cuda.current_stream()
@@ -240,9 +247,9 @@ class PartitionedRender:
         # pass cudaStreamLegacy (0x1) so kernels, torch events and NCCL share one stream.
         self.session = Session(heightmap, width, height, cam, device=self.device,
                                cuda_stream=self.stream.cuda_stream or 1, part_rank=self.rank, part_world=self.world,
-                               part_block_rows=block_rows, **scene_kw)
+                               part_block_rows=block_rows, part_mode=1 if mode == "gather_only" else 0, **scene_kw)
         lap("session_create_ms")
-        if self.world > 1:
+        if self.world > 1 and mode == "exact":
             # CUDA-IPC handles of the reservoir images and the frame-barrier words: one all-gather of 192 bytes per rank
             mine = torch.frombuffer(bytearray(self.session.ipc_export()), dtype=torch.uint8).cuda()
             every = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device="cuda")

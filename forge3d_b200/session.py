@@ -22,7 +22,7 @@ class Session:
     """A resident scene + per-pixel state on one CUDA device."""
 
     def __init__(self, heightmap, width, height, cam=None, *, device=0, cuda_stream=0, part_rank=0, part_world=1,
-                 part_block_rows=0, compat_512mib_gate=False, atmosphere=None, **kw):
+                 part_block_rows=0, part_mode=0, compat_512mib_gate=False, atmosphere=None, numerics=None, **kw):
         from .atmosphere import resolve_atmosphere
 
         args = dict(DEFAULTS)
@@ -35,57 +35,61 @@ class Session:
         self._args = args
         desc, keep = _native.make_desc(heightmap, width, height, cam, device=device,
                                        compat_512mib_gate=compat_512mib_gate, part_rank=part_rank,
-                                       part_world=part_world, part_block_rows=part_block_rows,
+                                       part_world=part_world, part_block_rows=part_block_rows, part_mode=part_mode,
                                        atmosphere=resolve_atmosphere(atmosphere), **args)
-        self._L = _native.lib()
+        self.numerics = numerics or _native.default_numerics()
+        self._L = _native.lib(self.numerics)
         self._h = C.c_void_p()
-        _native.check(self._L.f3d_session_create(C.byref(desc), C.c_void_p(int(cuda_stream) or None), C.byref(self._h)))
+        self._check(self._L.f3d_session_create(C.byref(desc), C.c_void_p(int(cuda_stream) or None), C.byref(self._h)))
         del keep
 
     # -- frame loop -------------------------------------------------------------------------------
+    def _check(self, rc):
+        _native.check(rc, self._L)
+
     def render_frames(self, n: int) -> None:
-        _native.check(self._L.f3d_session_render_frames(self._h, int(n)))
+        self._check(self._L.f3d_session_render_frames(self._h, int(n)))
 
     def sync(self) -> None:
-        _native.check(self._L.f3d_session_sync(self._h))
+        self._check(self._L.f3d_session_sync(self._h))
 
     def last_frames_ms(self) -> float:
         ms = C.c_double()
-        _native.check(self._L.f3d_session_last_frames_ms(self._h, C.byref(ms)))
+        self._check(self._L.f3d_session_last_frames_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
     @property
     def frames(self) -> int:
         n = C.c_uint32()
-        _native.check(self._L.f3d_session_frames(self._h, C.byref(n)))
+        self._check(self._L.f3d_session_frames(self._h, C.byref(n)))
         return int(n.value)
 
     def variance(self):
         v, bad = C.c_float(), C.c_int32()
-        _native.check(self._L.f3d_session_variance(self._h, C.byref(v), C.byref(bad)))
+        self._check(self._L.f3d_session_variance(self._h, C.byref(v), C.byref(bad)))
         return float(v.value), bool(bad.value)
 
     # -- outputs ----------------------------------------------------------------------------------
     def resolve_device(self, rgba=0, albedo=0, normal=0, depth=0, check_validity=True) -> None:
         """Resolve owned rows into device buffers given as raw pointers (e.g. torch .data_ptr())."""
         p = lambda v: C.c_void_p(int(v) or None)
-        _native.check(self._L.f3d_session_resolve_device(self._h, p(rgba), p(albedo), p(normal), p(depth),
+        self._check(self._L.f3d_session_resolve_device(self._h, p(rgba), p(albedo), p(normal), p(depth),
                                                          int(bool(check_validity))))
 
     def validity(self):
         """(any_valid, required) of the last resolve_device(check_validity=True): see f3d_session_validity."""
         any_valid, required = C.c_int32(), C.c_int32()
-        _native.check(self._L.f3d_session_validity(self._h, C.byref(any_valid), C.byref(required)))
+        self._check(self._L.f3d_session_validity(self._h, C.byref(any_valid), C.byref(required)))
         return bool(any_valid.value), bool(required.value)
 
     def resolve_host(self, want_accum=False) -> dict:
         o, arrays = _native.alloc_outputs(self.width, self.height, want_accum)
-        _native.check(self._L.f3d_session_resolve_host(self._h, C.byref(o)))
+        self._check(self._L.f3d_session_resolve_host(self._h, C.byref(o)))
         return _native.result_dict(o, arrays, self._args["sun_azimuth_deg"], self._args["sun_elevation_deg"])
 
     def stats(self) -> dict:
         o = _native.TerrainOut()
-        _native.check(self._L.f3d_session_stats(self._h, C.byref(o)))
+        self._check(self._L.f3d_session_stats(self._h, C.byref(o)))
         return dict(frames=int(o.frames), rays_primary=int(o.rays_primary), rays_shadow=int(o.rays_shadow),
                     rays_ibl=int(o.rays_ibl), nodes_popped=int(o.nodes_popped), setup_ms=float(o.setup_ms),
                     gpu_resource_bytes=int(o.gpu_resource_bytes), minmax_pyramid_bytes=int(o.minmax_pyramid_bytes),
@@ -94,12 +98,12 @@ class Session:
     # -- NVLink peer halo exchange ------------------------------------------------------------------
     def ipc_export(self) -> bytes:
         buf = (C.c_uint8 * (_native.IPC_HANDLE_BYTES * _native.IPC_HANDLES_PER_RANK))()
-        _native.check(self._L.f3d_session_ipc_export(self._h, buf))
+        self._check(self._L.f3d_session_ipc_export(self._h, buf))
         return bytes(buf)
 
     def ipc_import(self, all_handles: bytes) -> None:
         buf = (C.c_uint8 * len(all_handles)).from_buffer_copy(all_handles)
-        _native.check(self._L.f3d_session_ipc_import(self._h, buf))
+        self._check(self._L.f3d_session_ipc_import(self._h, buf))
 
     def close(self, trim: bool = False) -> None:
         """Destroys the session.  Its device buffers are parked in the library's cache for the next session (bounded, see

@@ -276,6 +276,33 @@ class SmokeDomain:
         self.last_kernel_ms = float(ms.value)
         return out
 
+    def render_over_rgba(self, base_rgba, camera_pos, target, up=(0.0, 1.0, 0.0), fovy_deg=45.0, sun_direction=(0.4, 0.8, -0.2),
+                         settings=None, base_depth=None) -> np.ndarray:
+        """BASELINE config 4: the smoke layer composited over a terrain frame, one kernel.  `base_rgba` = (H, W, 4) uint8 terrain
+        snapshot (e.g. hybrid_render_terrain_reference(...)["rgba"] from the SAME camera); the composite is the reference's
+        `_alpha_composite_rgba` (python/forge3d/map_scene.py:1588-1604).  `base_depth` = (H, W) float32 depth AOV of that
+        snapshot (optional): ends each ray's march at the terrain, which the reference's caller-side composite cannot do."""
+        settings = settings or SmokeRenderSettings()
+        base = np.ascontiguousarray(base_rgba, np.uint8)
+        if base.ndim != 3 or base.shape[2] != 4:
+            raise ValueError(f"base_rgba must have shape (height, width, 4), got {base.shape}")
+        height, width = base.shape[:2]
+        depth = None
+        if base_depth is not None:
+            depth = np.ascontiguousarray(base_depth, np.float32)
+            if depth.shape != (height, width):
+                raise ValueError(f"base_depth must have shape {(height, width)}, got {depth.shape}")
+        out = np.zeros((height, width, 4), np.uint8)
+        ms = C.c_double()
+        f3 = C.c_float * 3
+        _native.check(_native.lib().f3d_smoke_raymarch_over_rgba(
+            self._resident(), C.byref(settings._native()), int(width), int(height), f3(*_tuple3(camera_pos, "camera_pos")),
+            f3(*_tuple3(target, "target")), f3(*_tuple3(up, "up")), float(fovy_deg), f3(*_tuple3(sun_direction, "sun_direction")),
+            base.ctypes.data_as(C.POINTER(C.c_uint8)), depth.ctypes.data_as(C.POINTER(C.c_float)) if depth is not None else None,
+            out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(ms)))
+        self.last_kernel_ms = float(ms.value)
+        return out
+
     def render_projection_rgba(self, width, height, view_direction=(0.0, -1.0, 0.0), sun_direction=(0.4, 0.8, -0.2),
                                settings=None, certificate=None, cache=None) -> np.ndarray:
         """Map-aligned parallel projection of the volume -> (height, width, 4) uint8."""

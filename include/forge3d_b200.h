@@ -91,6 +91,11 @@ typedef struct f3d_terrain_desc {
     uint32_t part_rank, part_world;/* image-row partition: this process renders row blocks
                                       b with b % part_world == part_rank (world 0/1 = whole image) */
     uint32_t part_block_rows;      /* rows per block (0 = default 16; rounded up to a multiple of 16) */
+    uint32_t part_mode;            /* 0 = exact: border rows of the reservoir image and a per-frame flag travel over peer
+                                      memory, the result is bit-identical to one GPU;
+                                      1 = gather-only: the spatial reuse pass clamps its neighbours to the row block it
+                                      renders, ranks never talk during the frame loop; pixels within 4 rows
+                                      of a block border differ slightly from the one-GPU image */
     /* ---- desc.atmosphere (render_terrain.rs:262-265): AETHER aerial-perspective post over the converged
      * accumulation and the frame-0 depth AOV (:1246-1311); NULL = none.  Only `rgba` changes; AOVs do not. ---- */
     const f3d_atmosphere* atmosphere;
@@ -227,6 +232,16 @@ void f3d_smoke_destroy(f3d_smoke* s);
 int f3d_smoke_raymarch_rgba(f3d_smoke* s, const f3d_smoke_settings* settings, uint32_t width, uint32_t height,
                             const float camera_pos[3], const float target[3], const float up[3], float fovy_deg,
                             const float sun_direction[3], uint8_t* rgba, double* kernel_ms);
+/* BASELINE config 4 ("volumetric smoke frame over terrain"): the perspective march and the composite over a terrain frame in
+ * ONE kernel.  base_rgba = the terrain snapshot (same width x height, e.g. f3d_terrain_reference_render's rgba); the layer goes
+ * over it with the reference's straight-alpha compositor (python/forge3d/map_scene.py:1588-1604 _alpha_composite_rgba:
+ * rgb = u8(clip(dst (1 - a) + src a)), a = max).  base_depth (nullable) = distance along the camera ray to the terrain
+ * (the depth AOV; NaN / <= 0 = sky): when given, each ray's march ends at the surface, so smoke behind a ridge is hidden -
+ * an extension the reference's caller-side composite cannot do; NULL reproduces the reference pixel for pixel. */
+int f3d_smoke_raymarch_over_rgba(f3d_smoke* s, const f3d_smoke_settings* settings, uint32_t width, uint32_t height,
+                                 const float camera_pos[3], const float target[3], const float up[3], float fovy_deg,
+                                 const float sun_direction[3], const uint8_t* base_rgba, const float* base_depth,
+                                 uint8_t* rgba, double* kernel_ms);
 int f3d_smoke_raymarch_projection_rgba(f3d_smoke* s, const f3d_smoke_settings* settings, uint32_t width, uint32_t height,
                                        const float view_direction[3], const float sun_direction[3], uint8_t* rgba,
                                        double* kernel_ms);

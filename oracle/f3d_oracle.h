@@ -163,6 +163,10 @@ typedef struct f3do_smoke_settings {   /* SmokeRenderSettings, src/smoke/types.r
 int f3do_smoke_raymarch_rgba(const f3do_smoke_volume* vol, const f3do_smoke_settings* settings, uint32_t width, uint32_t height,
                              const float camera_pos[3], const float target[3], const float up[3], float fovy_deg,
                              const float sun_direction[3], uint8_t* rgba);
+/* the layer composited over a terrain frame (python/forge3d/map_scene.py:1588-1604); base_depth nullable */
+int f3do_smoke_raymarch_over_rgba(const f3do_smoke_volume* vol, const f3do_smoke_settings* settings, uint32_t width, uint32_t height,
+                                  const float camera_pos[3], const float target[3], const float up[3], float fovy_deg,
+                                  const float sun_direction[3], const uint8_t* base_rgba, const float* base_depth, uint8_t* rgba);
 int f3do_smoke_raymarch_projection_rgba(const f3do_smoke_volume* vol, const f3do_smoke_settings* settings, uint32_t width,
                                         uint32_t height, const float view_direction[3], const float sun_direction[3], uint8_t* rgba);
 float f3do_smoke_sun_transmittance(const f3do_smoke_volume* vol, const f3do_smoke_settings* settings, const float start[3],

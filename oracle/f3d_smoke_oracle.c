@@ -279,6 +279,64 @@ int f3do_smoke_raymarch_rgba(const f3do_smoke_volume* V, const f3do_smoke_settin
     return 0;
 }
 
+/* Straight-alpha "over", python/forge3d/map_scene.py:1588-1604 (_alpha_composite_rgba): numpy float32 arithmetic,
+ * truncating cast, alpha = max.  dst is updated in place. */
+static void composite_over(uint8_t* dst, const uint8_t* src) {
+    float alpha = (float)src[3] / 255.0f, keep = 1.0f - alpha;
+    for (int c = 0; c < 3; c++) {
+        float v = (float)dst[c] * keep + (float)src[c] * alpha;
+        v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);
+        dst[c] = (uint8_t)v;
+    }
+    dst[3] = dst[3] > src[3] ? dst[3] : src[3];
+}
+
+/* The smoke layer over a terrain frame (BASELINE config 4): SmokeVolume::raymarch_rgba (render.rs:6-101) per pixel, the march
+ * optionally ended at the terrain depth (NaN / <= 0 = sky; NULL = the reference's bare layer), then _alpha_composite_rgba. */
+int f3do_smoke_raymarch_over_rgba(const f3do_smoke_volume* V, const f3do_smoke_settings* st, uint32_t width, uint32_t height,
+                                  const float camera_pos[3], const float target[3], const float up_in[3], float fovy_deg,
+                                  const float sun_direction[3], const uint8_t* base_rgba, const float* base_depth, uint8_t* rgba) {
+    g_smoke_err[0] = 0;
+    if (validate_settings(st)) return 1;
+    if (width == 0 || height == 0) return sfail("width and height must be >= 1");
+    if (!isfinite(fovy_deg) || fovy_deg <= 0.0f || fovy_deg >= 179.0f) return sfail("fovy_deg must be finite and in (0, 179)");
+    s3 eye = S3(camera_pos[0], camera_pos[1], camera_pos[2]);
+    s3 forward = snormalize_or_zero(ssub(S3(target[0], target[1], target[2]), eye));
+    if (sdot(forward, forward) < 1.0e-12f) return sfail("camera_pos and target must not be equal");
+    s3 up = snormalize_or_zero(S3(up_in[0], up_in[1], up_in[2]));
+    if (sdot(up, up) < 1.0e-12f) return sfail("up vector must not be zero");
+    s3 right = snormalize_or_zero(scross(forward, up));
+    s3 camera_up = snormalize_or_zero(scross(right, forward));
+    s3 sun_dir = snormalize_or_zero(S3(sun_direction[0], sun_direction[1], sun_direction[2]));
+    if (sdot(sun_dir, sun_dir) < 1.0e-12f) return sfail("sun_direction must not be zero");
+    float step, shadow_step;
+    steps_for(V, st, &step, &shadow_step);
+    float tan_half_fov = tanf(fovy_deg * (3.14159274101257324f / 180.0f) * 0.5f);
+    float aspect = (float)width / (float)height;
+    s3 bmin = S3(V->origin[0], V->origin[1], V->origin[2]), bmax = bounds_max(V);
+    memcpy(rgba, base_rgba, (size_t)width * height * 4);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t y = 0; y < (int64_t)height; y++)
+        for (uint32_t x = 0; x < width; x++) {
+            float px = (((float)x + 0.5f) / (float)width * 2.0f - 1.0f) * aspect * tan_half_fov;
+            float py = (1.0f - ((float)y + 0.5f) / (float)height * 2.0f) * tan_half_fov;
+            s3 dir = snormalize(sadd(sadd(forward, sscale(right, px)), sscale(camera_up, py)));
+            uint8_t layer[4] = {0, 0, 0, 0};
+            float t0, t1;
+            if (ray_box(eye, dir, bmin, bmax, &t0, &t1)) {
+                if (base_depth) {
+                    float d = base_depth[(size_t)y * width + x];
+                    if (d > 0.0f) t1 = fminf(t1, d);
+                }
+                t0 = fmaxf(t0, 0.0f);
+                uint32_t seed = x * 73856093u + (uint32_t)y * 19349663u + (uint32_t)V->frame_index;
+                march_ray_rgba(V, eye, dir, t0, t1, seed, step, shadow_step, sun_dir, st, layer);
+            }
+            composite_over(rgba + ((size_t)y * width + x) * 4, layer);
+        }
+    return 0;
+}
+
 int f3do_smoke_raymarch_projection_rgba(const f3do_smoke_volume* V, const f3do_smoke_settings* st, uint32_t width, uint32_t height,
                                         const float view_direction[3], const float sun_direction[3], uint8_t* rgba) {
     g_smoke_err[0] = 0;

@@ -356,6 +356,8 @@ def _smoke_lib():
         u8p = C.POINTER(C.c_uint8)
         L.f3do_smoke_raymarch_rgba.argtypes = [C.POINTER(_SmokeVolume), C.POINTER(_SmokeSettings), C.c_uint32, C.c_uint32, f3, f3, f3,
                                                C.c_float, f3, u8p]
+        L.f3do_smoke_raymarch_over_rgba.argtypes = [C.POINTER(_SmokeVolume), C.POINTER(_SmokeSettings), C.c_uint32, C.c_uint32, f3, f3, f3,
+                                                    C.c_float, f3, C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_uint8)]
         L.f3do_smoke_raymarch_projection_rgba.argtypes = [C.POINTER(_SmokeVolume), C.POINTER(_SmokeSettings), C.c_uint32,
                                                           C.c_uint32, f3, f3, u8p]
         L.f3do_smoke_sun_transmittance.argtypes = [C.POINTER(_SmokeVolume), C.POINTER(_SmokeSettings), f3, f3, C.c_float, C.c_uint32]
@@ -375,6 +377,27 @@ def smoke_raymarch_rgba(domain, settings, width, height, camera_pos, target, up=
     rc = L.f3do_smoke_raymarch_rgba(C.byref(v), C.byref(s), int(width), int(height), f3(*map(float, camera_pos)),
                                     f3(*map(float, target)), f3(*map(float, up)), float(fovy_deg), f3(*map(float, sun_direction)),
                                     out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    if rc != 0:
+        raise OracleError(L.f3do_smoke_last_error().decode())
+    del keep
+    return out
+
+
+def smoke_raymarch_over_rgba(domain, settings, width, height, camera_pos, target, base_rgba, base_depth=None, up=(0.0, 1.0, 0.0),
+                             fovy_deg=45.0, sun_direction=(0.4, 0.8, -0.2)):
+    """The smoke layer (render.rs:6-101) composited over a terrain frame with _alpha_composite_rgba
+    (python/forge3d/map_scene.py:1588-1604); base_depth (optional) ends each march at the terrain."""
+    L = _smoke_lib()
+    v, s, keep = _smoke_structs(domain, settings)
+    f3 = C.c_float * 3
+    base = np.ascontiguousarray(base_rgba, np.uint8)
+    depth = None if base_depth is None else np.ascontiguousarray(base_depth, np.float32)
+    out = np.zeros((int(height), int(width), 4), np.uint8)
+    rc = L.f3do_smoke_raymarch_over_rgba(C.byref(v), C.byref(s), int(width), int(height), f3(*map(float, camera_pos)),
+                                         f3(*map(float, target)), f3(*map(float, up)), float(fovy_deg), f3(*map(float, sun_direction)),
+                                         base.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                         depth.ctypes.data_as(C.POINTER(C.c_float)) if depth is not None else None,
+                                         out.ctypes.data_as(C.POINTER(C.c_uint8)))
     if rc != 0:
         raise OracleError(L.f3do_smoke_last_error().decode())
     del keep

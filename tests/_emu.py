@@ -132,12 +132,14 @@ class emulated_backend:
         from forge3d_b200 import _native
 
         self._native = _native
-        self._saved = (_native.LIB_PATH, _native._lib)
+        self._saved = (_native.LIB_PATH, dict(_native._libs))
         _native.LIB_PATH = build_backend(self.defines)
-        _native._lib = None
+        _native._libs.clear()
         _native.lib()
         return _native
 
     def __exit__(self, *exc):
-        self._native.LIB_PATH, self._native._lib = self._saved
+        self._native.LIB_PATH = self._saved[0]
+        self._native._libs.clear()
+        self._native._libs.update(self._saved[1])
         return False

@@ -54,6 +54,8 @@ static inline float emu_fmaxf(float a, float b) {
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
+static inline float __double2float_ru(double x) { float f = (float)x; if ((double)f < x) f = nextafterf(f, INFINITY); return f; }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }   /* glibc fmaf is correctly rounded */
@@ -76,6 +78,10 @@ static inline uint32_t __ballot_sync(uint32_t, int pred) { return pred ? 1u : 0u
 static inline uint32_t __activemask() { return 1u; }
 template <class T> static inline T __shfl_sync(uint32_t, T v, int, int = 32) { return v; }
 static inline void __syncwarp(uint32_t = 0xFFFFFFFFu) {}
+/* the CTA-wide helpers of f3d_trace_fast.cuh (stage_top_levels, all_sibling_seeds_warp) only have to COMPILE here:
+ * trace_emu.cpp runs trace_fast, which calls neither */
+static const struct { uint32_t x, y, z; } threadIdx = {0u, 0u, 0u};
+static inline void __syncthreads() {}
 #endif
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, frames, width, height, block_rows, q, seed=7):
+def _worker(rank, world, port, frames, width, height, block_rows, q, seed=7, mode="exact"):
     import torch
     import torch.distributed as dist
 
@@ -33,7 +33,7 @@ def _worker(rank, world, port, frames, width, height, block_rows, q, seed=7):
     try:
         dem = H.golden_dem()
         kw = {**H.scene_kwargs(dem), "max_frames": frames, "min_frames": frames, "variance_threshold": 1e30, "seed": seed}
-        pr = PartitionedRender(dem, width, height, H.CAM, block_rows=block_rows, **kw)
+        pr = PartitionedRender(dem, width, height, H.CAM, block_rows=block_rows, mode=mode, **kw)
         pr.render_frames(frames)
         var, bad = pr.variance()
         out = pr.resolve(aovs=True)
@@ -285,3 +285,90 @@ def test_two_ranks_on_one_device_over_cuda_ipc_are_bit_identical():
         assert np.array_equal(full.view(np.uint8), np.ascontiguousarray(ref[key]).view(np.uint8)), key
     assert np.float32(max(parts[r][1] for r in range(world))) == np.float32(ref["variance"])
     assert not any(parts[r][2] for r in range(world))
+
+
+# ---- gather-only partition: no exchange during the frame loop ----
+# MEASURED AND REJECTED as a default: clamping the spatial reuse pass to the row block changes the
+# reservoir chain (the reference's M-weighted combination is not invariant to the neighbour set), the change feeds back
+# through the temporal pass and spreads ~4 rows per frame: against the one-GPU image of the same seed the RGB RMSE is
+# 1.6e-2 (2 bands) to 2.6e-2 (16-row blocks) where two different SEEDS of the one-GPU render differ by 2e-3, and a
+# ~6 % darker band follows every seam.  That is 20x the north-star tolerance (1e-3), so the mode stays opt-in and the
+# exact mode (peer-memory halo, no NCCL call in the frame loop either) is what bench.py and PartitionedRender default to.
+# The tests below pin what the mode does guarantee.
+GATHER_ONLY_SANITY_RMSE = 5e-2
+
+
+def _rgb_rmse(a, b):
+    d = a[..., :3].astype(np.float64) - b[..., :3].astype(np.float64)
+    return float(np.sqrt(np.mean((d / 255.0) ** 2)))
+
+
+def _gather_only_rank_by_rank(dem, width, height, world, block_rows, kw):
+    """Every rank of a gather-only partition rendered in turn on ONE device (the mode has no communication, so this is the
+    real computation), rows assembled as the final gather would."""
+    from forge3d_b200 import distributed as D
+    from forge3d_b200.session import Session
+
+    got = None
+    for r in range(world):
+        s = Session(dem, width, height, H.CAM, part_rank=r, part_world=world, part_block_rows=block_rows, part_mode=1, **kw)
+        s.render_frames(kw["max_frames"])
+        out = s.resolve_host()
+        if got is None:
+            got = {k: np.zeros_like(out[k]) for k in ("rgba", "depth", "normal", "albedo")}
+        rows = D.owned_rows(height, world, r, block_rows)
+        for k in got:
+            got[k][rows] = out[k][rows]
+        s.close()
+    return got
+
+
+@pytest.mark.parametrize("world,block_rows,frames", [(2, 64, 8), (4, 16, 24)])
+def test_gather_only_partition_keeps_aovs_exact_and_rgb_close(world, block_rows, frames):
+    from forge3d_b200 import _native
+
+    width, height = 128, 128
+    dem = H.golden_dem()
+    kw = {**H.scene_kwargs(dem), "max_frames": frames, "min_frames": frames, "variance_threshold": 1e30}
+    ref = _native.hybrid_render_terrain_reference(dem, width, height, H.CAM, **kw)
+    got = _gather_only_rank_by_rank(dem, width, height, world, block_rows, kw)
+    for k in ("depth", "normal", "albedo"):          # the AOVs never read a neighbour: identical
+        assert np.array_equal(np.ascontiguousarray(got[k]).view(np.uint8), np.ascontiguousarray(ref[k]).view(np.uint8)), k
+    rmse = _rgb_rmse(got["rgba"], ref["rgba"])
+    assert 0.0 < rmse <= GATHER_ONLY_SANITY_RMSE, rmse      # close, but NOT the same image (see the note above)
+    # the change starts at the seams and can travel at most 4 rows per frame: rows further away are the one-GPU rows
+    from forge3d_b200 import distributed as D
+
+    br = D.effective_block_rows(block_rows, height, world)
+    seams = np.arange(br, height, br)
+    y = np.arange(height)
+    untouched = np.abs(y[:, None] - seams[None, :] + 0.5).min(axis=1) > 4 * frames + 4
+    if untouched.any():
+        assert np.array_equal(got["rgba"][untouched], ref["rgba"][untouched])
+
+
+def test_gather_only_partition_over_nccl_matches_the_rank_by_rank_render():
+    """Two GPUs, mode="gather_only": PartitionedRender exchanges nothing but the final gather; the image equals the one the
+    single-device rank-by-rank render of the same partition produces, bit for bit."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    world, width, height, block_rows, frames = 2, 96, 80, 16, 40
+    dem = H.golden_dem()
+    kw = {**H.scene_kwargs(dem), "max_frames": frames, "min_frames": frames, "variance_threshold": 1e30}
+    local = _gather_only_rank_by_rank(dem, width, height, world, block_rows, kw)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, frames, width, height, block_rows, q, 7, "gather_only")) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.array_equal(got["rgba"], local["rgba"])
+    assert np.array_equal(got["depth"].view(np.uint32), local["depth"].view(np.uint32))

@@ -39,12 +39,15 @@ def main():
         with _emu.emulated_backend(defs) as native:
             g = native.hybrid_render_terrain_reference(dem, W, H, cam, max_frames=frames, min_frames=frames, variance_threshold=1e30,
                                                        want_accum=True, **kw)
-            out = (C.c_ulonglong * 8)()
+            out = (C.c_ulonglong * 40)()
             native.lib().f3d_debug_sched_stats(out, 1)
         es, el, ls, ll, rs, _ = list(out)[:6]
         for name, v in (("sun", out[6]), ("ibl", out[7])):
             if v >> 32:
                 print(f"    bottom-up start, {name} rays: {(v & 0xFFFFFFFF) / (v >> 32):.2f} seeds per ray ({v >> 32} rays)")
+        if sum(out[8:24]):
+            print("    sun horizon: cleared from column k on -> rays (seeds/ray): " + "  ".join(
+                f"{'none' if i == 15 else [1, 2, 3, 4, 6, 8, 12, 16][i]}: {out[8 + i]} ({out[24 + i] / max(out[8 + i], 1):.2f})" for i in range(16) if out[8 + i]))
         if base is None:
             base = g["accum"].copy()
         exact = np.array_equal(g["accum"].view(np.uint32), base.view(np.uint32))
