@@ -171,8 +171,31 @@ __device__ __forceinline__ bool vs_trace_segment(const ViewshedParams& P, float 
                                                  const float c[3], float tol) {
     const float dx = ex - ox, dy = ey - oy;
     const float ix = vs_safe_inv(dx), iz = vs_safe_inv(dy);
-    const uint32_t cw = P.w - 1u, ch = P.h - 1u, root = P.root_level;
+    const uint32_t cw = P.w - 1u, ch = P.h - 1u;
+    // START BELOW THE ROOT.  The reference walks every segment down from the root (:247), ten levels for a half-cell chord.
+    // A node that contains the whole segment with a margin yields t0 = 0 and t1 = 1 EXACTLY (its entry planes lie behind the
+    // origin: sign-exact products <= 0; its exit planes lie >= 1/256 cell beyond the end point: products >= 1 after rounding),
+    // so every such ancestor evaluates the SAME hmin and compares it with a maximum that only grows towards the root: the
+    // lowest containing node passes its height test iff all its ancestors do, the root-to-there descent is forced (no other
+    // node meets the segment), and nothing outside that node's subtree can be visited.  Starting there - and ending the
+    // sibling search there - therefore returns the reference's flag.  A segment that touches the DEM border (clipped nodes)
+    // or straddles a high-level split keeps the walk from the root.
+    uint32_t root = P.root_level;
     uint32_t node = vs_pack(root, 0u, 0u);
+    {
+        const float m = 0.00390625f;
+        const float lx = fminf(ox, ex) - m, hx = fmaxf(ox, ex) + m, ly = fminf(oy, ey) - m, hy = fmaxf(oy, ey) + m;
+        if (lx >= 0.0f && ly >= 0.0f && hx <= (float)cw && hy <= (float)ch) {
+            const uint32_t ax = (uint32_t)lx, bx = (uint32_t)hx, ay = (uint32_t)ly, by = (uint32_t)hy;   // truncation == floor (>= 0)
+            const uint32_t diff = (ax ^ bx) | (ay ^ by);
+            const uint32_t lv = 32u - (uint32_t)__clz((int)diff);             // 0 when both ends share a cell
+            // the node's far planes must not be the clipped DEM edge (a clipped plane has no margin argument)
+            if (lv < root && (((ax >> lv) + 1u) << lv) <= cw && (((ay >> lv) + 1u) << lv) <= ch) {
+                root = lv;
+                node = vs_pack(lv, ax >> lv, ay >> lv);
+            }
+        }
+    }
     while (true) {
         const uint32_t level = node >> 26, ny = (node >> 13) & 0x1FFFu, nx = node & 0x1FFFu;
         const uint32_t x0 = nx << level, y0 = ny << level;
@@ -219,49 +242,65 @@ __device__ __forceinline__ void vs_latlon_to_pixel(const ViewshedParams& P, floa
     px = vdet_div(lon_deg - P.geodetic[2], P.metric[1]) - 0.5f;
     py = vdet_div(P.geodetic[3] - vdegrees(lat), P.metric[2]) - 0.5f;
 }
-// geodesic_sample_pixel, :389-468: direct geodesic on the sphere (metric.w > 0) or Vincenty's direct formula on WGS84
-__device__ __forceinline__ void vs_geodesic_pixel(const ViewshedParams& P, float lat0, float lon0, float azimuth, float distance_m,
+// geodesic_sample_pixel, :389-468: direct geodesic on the sphere (metric.w > 0) or Vincenty's direct formula on WGS84.
+// The reference re-derives everything that depends on (lat0, azimuth) alone - reduced latitude, sigma1, alpha, u^2, A, B, C:
+// ten polynomial trig evaluations - for EVERY half-cell segment of a chord; a chord has one start and one azimuth, so they
+// are computed once per cell here (vs_geodesic_setup) with the same expressions in the same order.
+struct VsGeodesic {
+    float sin_lat0, cos_lat0, sin_az, cos_az;                      // sphere branch
+    float flattening, semi_minor, sin_u1, cos_u1, sigma1, sin_alpha, cos_sq_alpha, ca, cb, cc;   // WGS84 branch
+};
+__device__ __forceinline__ VsGeodesic vs_geodesic_setup(const ViewshedParams& P, float lat0, float azimuth) {
+    VsGeodesic G{};
+    if (P.metric[3] > 0.0f) {
+        G.sin_lat0 = vdet_sin(lat0); G.cos_lat0 = vdet_cos(lat0); G.sin_az = vdet_sin(azimuth); G.cos_az = vdet_cos(azimuth);
+        return G;
+    }
+    G.flattening = fdiv(1.0f, 298.257223563f);
+    const float semi_major = 6378137.0f;
+    G.semi_minor = semi_major * (1.0f - G.flattening);
+    const float reduced = vdet_atan2((1.0f - G.flattening) * vdet_sin(lat0), vdet_cos(lat0));
+    G.sin_u1 = vdet_sin(reduced); G.cos_u1 = vdet_cos(reduced);
+    G.sin_az = vdet_sin(azimuth); G.cos_az = vdet_cos(azimuth);
+    G.sigma1 = vdet_atan2(G.sin_u1, G.cos_u1 * G.cos_az);
+    G.sin_alpha = G.cos_u1 * G.sin_az;
+    G.cos_sq_alpha = 1.0f - G.sin_alpha * G.sin_alpha;
+    const float u_sq = fdiv(G.cos_sq_alpha * (semi_major * semi_major - G.semi_minor * G.semi_minor), G.semi_minor * G.semi_minor);
+    G.ca = 1.0f + fdiv(u_sq, 16384.0f) * (4096.0f + u_sq * (-768.0f + u_sq * (320.0f - 175.0f * u_sq)));
+    G.cb = fdiv(u_sq, 1024.0f) * (256.0f + u_sq * (-128.0f + u_sq * (74.0f - 47.0f * u_sq)));
+    G.cc = fdiv(G.flattening, 16.0f) * G.cos_sq_alpha * (4.0f + G.flattening * (4.0f - 3.0f * G.cos_sq_alpha));
+    return G;
+}
+__device__ __forceinline__ void vs_geodesic_pixel(const ViewshedParams& P, const VsGeodesic& G, float lon0, float distance_m,
                                                   float& px, float& py) {
     if (P.metric[3] > 0.0f) {
         const float ad = vdet_div(distance_m, P.metric[3]);
-        const float sin_lat = vdet_fma(vdet_sin(lat0), vdet_cos(ad), vdet_sin(ad) * vdet_cos(lat0) * vdet_cos(azimuth));
+        const float sin_lat = vdet_fma(G.sin_lat0, vdet_cos(ad), vdet_sin(ad) * G.cos_lat0 * G.cos_az);
         const float lat = 1.5707963267948966f - vdet_acos(fminf(fmaxf(sin_lat, -1.0f), 1.0f));
-        const float lon = lon0 + vdet_atan2(vdet_sin(azimuth) * vdet_sin(ad) * vdet_cos(lat0), vdet_cos(ad) - vdet_sin(lat0) * vdet_sin(lat));
+        const float lon = lon0 + vdet_atan2(G.sin_az * vdet_sin(ad) * G.cos_lat0, vdet_cos(ad) - G.sin_lat0 * vdet_sin(lat));
         vs_latlon_to_pixel(P, lat, lon, px, py);
         return;
     }
-    const float flattening = fdiv(1.0f, 298.257223563f);
-    const float semi_major = 6378137.0f;
-    const float semi_minor = semi_major * (1.0f - flattening);
-    const float reduced = vdet_atan2((1.0f - flattening) * vdet_sin(lat0), vdet_cos(lat0));
-    const float sin_u1 = vdet_sin(reduced), cos_u1 = vdet_cos(reduced);
-    const float sin_az = vdet_sin(azimuth), cos_az = vdet_cos(azimuth);
-    const float sigma1 = vdet_atan2(sin_u1, cos_u1 * cos_az);
-    const float sin_alpha = cos_u1 * sin_az;
-    const float cos_sq_alpha = 1.0f - sin_alpha * sin_alpha;
-    const float u_sq = fdiv(cos_sq_alpha * (semi_major * semi_major - semi_minor * semi_minor), semi_minor * semi_minor);
-    const float ca = 1.0f + fdiv(u_sq, 16384.0f) * (4096.0f + u_sq * (-768.0f + u_sq * (320.0f - 175.0f * u_sq)));
-    const float cb = fdiv(u_sq, 1024.0f) * (256.0f + u_sq * (-128.0f + u_sq * (74.0f - 47.0f * u_sq)));
-    float sigma = vdet_div(distance_m, semi_minor * ca);
+    const float sigma0 = vdet_div(distance_m, G.semi_minor * G.ca);
+    float sigma = sigma0;
 #pragma unroll 1
     for (int it = 0; it < 4; it++) {
-        const float two_sigma_m = 2.0f * sigma1 + sigma;
+        const float two_sigma_m = 2.0f * G.sigma1 + sigma;
         const float ss = vdet_sin(sigma), cs = vdet_cos(sigma), c2 = vdet_cos(two_sigma_m);
-        const float delta = cb * ss * (c2 + fdiv(cb, 4.0f) * (cs * (-1.0f + 2.0f * c2 * c2) -
-                                                              fdiv(cb, 6.0f) * c2 * (-3.0f + 4.0f * ss * ss) * (-3.0f + 4.0f * c2 * c2)));
-        sigma = vdet_div(distance_m, semi_minor * ca) + delta;
+        const float delta = G.cb * ss * (c2 + fdiv(G.cb, 4.0f) * (cs * (-1.0f + 2.0f * c2 * c2) -
+                                                                  fdiv(G.cb, 6.0f) * c2 * (-3.0f + 4.0f * ss * ss) * (-3.0f + 4.0f * c2 * c2)));
+        sigma = sigma0 + delta;
     }
     const float ss = vdet_sin(sigma), cs = vdet_cos(sigma);
-    const float two_sigma_m = 2.0f * sigma1 + sigma;
-    const float tmp = sin_u1 * ss - cos_u1 * cs * cos_az;
-    const float lat = vdet_atan2(sin_u1 * cs + cos_u1 * ss * cos_az, (1.0f - flattening) * vdet_sqrt(sin_alpha * sin_alpha + tmp * tmp));
-    const float lambda = vdet_atan2(ss * sin_az, cos_u1 * cs - sin_u1 * ss * cos_az);
-    const float cc = fdiv(flattening, 16.0f) * cos_sq_alpha * (4.0f + flattening * (4.0f - 3.0f * cos_sq_alpha));
+    const float two_sigma_m = 2.0f * G.sigma1 + sigma;
+    const float tmp = G.sin_u1 * ss - G.cos_u1 * cs * G.cos_az;
+    const float lat = vdet_atan2(G.sin_u1 * cs + G.cos_u1 * ss * G.cos_az, (1.0f - G.flattening) * vdet_sqrt(G.sin_alpha * G.sin_alpha + tmp * tmp));
+    const float lambda = vdet_atan2(ss * G.sin_az, G.cos_u1 * cs - G.sin_u1 * ss * G.cos_az);
     const float c2 = vdet_cos(two_sigma_m);
-    const float dlon = lambda - (1.0f - cc) * flattening * sin_alpha * (sigma + cc * ss * (c2 + cc * cs * (-1.0f + 2.0f * c2 * c2)));
+    const float dlon = lambda - (1.0f - G.cc) * G.flattening * G.sin_alpha * (sigma + G.cc * ss * (c2 + G.cc * cs * (-1.0f + 2.0f * c2 * c2)));
     vs_latlon_to_pixel(P, lat, lon0 + dlon, px, py);
 }
-__device__ __forceinline__ float vs_shadow_step_m(const ViewshedParams& P, float lat, float azimuth) {   // :584-606
+__device__ __forceinline__ float vs_shadow_step_m(const ViewshedParams& P, float lat, float sin_az, float cos_az) {   // :584-606 (sin / cos of the azimuth hoisted: VsGeodesic)
     const float sl = vdet_sin(lat);
     const float ft = 1.0f - 0.0066943799901413165f * sl * sl;
     const float root = vdet_sqrt(ft);
@@ -270,8 +309,8 @@ __device__ __forceinline__ float vs_shadow_step_m(const ViewshedParams& P, float
     const float hm = P.metric[3] > 0.0f ? P.metric[3] : meridional, hp = P.metric[3] > 0.0f ? P.metric[3] : prime_vertical;
     const float north_cell = hm * vradians(P.metric[2]);
     const float east_cell = hp * vdet_cos(lat) * vradians(P.metric[1]);
-    const float east_cross = vdet_div(east_cell, fmaxf(fabsf(vdet_sin(azimuth)), 1e-6f));
-    const float north_cross = vdet_div(north_cell, fmaxf(fabsf(vdet_cos(azimuth)), 1e-6f));
+    const float east_cross = vdet_div(east_cell, fmaxf(fabsf(sin_az), 1e-6f));
+    const float north_cross = vdet_div(north_cell, fmaxf(fabsf(cos_az), 1e-6f));
     return fmaxf(0.1f, 0.5f * fminf(north_cross, east_cross));
 }
 
@@ -306,11 +345,12 @@ __global__ void __launch_bounds__(kViewshedThreads) k_viewshed(const ViewshedPar
         visible = 1u;
         float start_d = 0.0f, spx = P.observer[0], spy = P.observer[1];
         const float maxx = (float)P.w - 0.5f, maxy = (float)P.h - 0.5f;
+        const VsGeodesic G = vs_geodesic_setup(P, P.geodetic[0], azimuth);
         while (true) {
             const float seg_lat = vradians(vdet_fma(-(spy + 0.5f), P.metric[2], P.geodetic[3]));
-            const float end_d = fminf(start_d + vs_shadow_step_m(P, seg_lat, azimuth), distance_m);
+            const float end_d = fminf(start_d + vs_shadow_step_m(P, seg_lat, G.sin_az, G.cos_az), distance_m);
             float epx, epy;
-            vs_geodesic_pixel(P, P.geodetic[0], P.geodetic[1], azimuth, end_d, epx, epy);
+            vs_geodesic_pixel(P, G, P.geodetic[1], end_d, epx, epy);
             if (epx < -0.5f || epy < -0.5f || epx > maxx || epy > maxy) { visible = 2u; break; }
             if (vs_trace_segment(P, spx, spy, epx, epy, start_d, end_d, c, 0.001f)) { visible = 0u; break; }
             if (end_d >= distance_m) break;
@@ -347,10 +387,11 @@ __global__ void __launch_bounds__(kViewshedThreads) k_shadow_mask(const Viewshed
         float start_d = 0.0f, spx = (float)x, spy = (float)y, seg_lat = lat0;
         const float maxx = (float)P.w - 0.5f, maxy = (float)P.h - 0.5f;
         out = 1u;
+        const VsGeodesic G = vs_geodesic_setup(P, lat0, azimuth);
         while (true) {
-            const float end_d = fminf(start_d + vs_shadow_step_m(P, seg_lat, azimuth), P.metric[0]);
+            const float end_d = fminf(start_d + vs_shadow_step_m(P, seg_lat, G.sin_az, G.cos_az), P.metric[0]);
             float epx, epy;
-            vs_geodesic_pixel(P, lat0, lon0, azimuth, end_d, epx, epy);
+            vs_geodesic_pixel(P, G, lon0, end_d, epx, epy);
             if (vs_trace_segment(P, spx, spy, epx, epy, start_d, end_d, c, 0.01f)) { out = 0u; break; }
             if (epx < -0.5f || epy < -0.5f || epx > maxx || epy > maxy) break;
             if (end_d >= P.metric[0]) break;

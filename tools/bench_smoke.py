@@ -25,8 +25,9 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-def plume(n: int):
-    """Closed-form plume (no RNG): a bent column with a turbulent-looking modulation, all six fields populated."""
+def plume(n: int, extent: float = 40.0, origin=(-20.0, 0.0, -20.0)):
+    """Closed-form plume (no RNG): a bent column with a turbulent-looking modulation, all six fields populated.
+    `extent` = edge length of the cubic domain in world units, `origin` = its minimum corner."""
     from forge3d_b200.smoke import SmokeDomain
 
     z, y, x = np.meshgrid(*(np.arange(n, dtype=np.float32),) * 3, indexing="ij")
@@ -36,7 +37,7 @@ def plume(n: int):
     mod = 0.75 + 0.25 * np.sin(23.0 * u + 7.0 * v) * np.cos(17.0 * w - 11.0 * v)
     density = (np.exp(-r2) * mod * (v < 0.92) * 1.4).astype(np.float32)
     density[density < 0.02] = 0.0
-    dom = SmokeDomain((n, n, n), voxel_size=(40.0 / n,) * 3, origin=(-20.0, 0.0, -20.0))
+    dom = SmokeDomain((n, n, n), voxel_size=(float(extent) / n,) * 3, origin=tuple(float(c) for c in origin))
     dom.set_density(density)
     dom.set_field("temperature", (density * np.clip(1.0 - 2.5 * v, 0.0, 1.0) * 1.5).astype(np.float32))
     dom.set_field("soot", (density * 0.3 * (1.0 - v)).astype(np.float32))
