@@ -55,6 +55,19 @@ def source_hash() -> str:
     return h.hexdigest()[:16]
 
 
+HOT_SOURCES = ["f3d_backend.cu", "f3d_host.h", "f3d_math.cuh", "f3d_trace.cuh", "f3d_trace_fast.cuh", "f3d_kernels.cuh", "f3d_aether.cuh", "f3d_lbvh.cuh"]
+
+
+def hot_hash() -> str:
+    """Content hash of the sources the TERRAIN path's kernels are made from (what an ncu capture of the frame kernels depends
+    on); a change to the smoke / viewshed / wavefront rows does not invalidate profiles/traffic.json."""
+    h = hashlib.sha1()
+    for n in HOT_SOURCES:
+        h.update(n.encode())
+        h.update((CSRC / n).read_bytes())
+    return h.hexdigest()[:16]
+
+
 def built_info(lib: Path = LIB) -> str:
     """The `f3d_build_info()` string of a built library without loading it: "src=<hash>;defines=<...>" ("" if absent)."""
     try:
@@ -69,7 +82,7 @@ def built_info(lib: Path = LIB) -> str:
 
 
 def _info(defines: str, numerics: str) -> str:
-    return f"src={source_hash()};defines={','.join(defines.split())}" + (";numerics=fast" if numerics == "fast" else "")
+    return f"src={source_hash()};hot={hot_hash()};defines={','.join(defines.split())}" + (";numerics=fast" if numerics == "fast" else "")
 
 
 def needs_build(defines: str = "", numerics: str = "exact") -> bool:

@@ -690,6 +690,7 @@ struct f3d_session {
     size_t ascent_smem_bytes = 0;   // k_ascent: leaf rings of the near-field walk (+ staged top levels)
     int trace_grid = 0;             // persistent CTAs of k_trace
     int ascent_grid = 0;            // grid-stride CTAs of k_ascent
+    cudaStream_t prim_stream = nullptr;   // optional high-priority stream of the primary pass (F3D_B200_PRIM_PRIORITY=1)
     // Frame batching + pipelining.  k_primary(step+1) only depends on k_primary(step) (reservoir records); everything after it
     // (k_ascent, k_trace, k_accum) depends on k_primary of the same step and on k_accum of the step before.  Steps are
     // processed in BATCHES of up to `batch` steps: their primaries run back to back on the session stream, then ONE launch of
@@ -756,6 +757,7 @@ static void session_free(f3d_session* s) {
     if (s->h_gate) cudaFreeHost(s->h_gate);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->prim_stream) { cudaStreamSynchronize(s->prim_stream); cudaStreamDestroy(s->prim_stream); }
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -980,6 +982,7 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
         if (const char* e = getenv("F3D_B200_TRACE_CTAS")) per_sm = std::max(atoi(e), 1);
         s->trace_grid = std::max(per_sm, 1) * std::max(sms, 1);
         s->ascent_grid = 8 * std::max(sms, 1);
+        if (const char* e = getenv("F3D_B200_ASCENT_CTAS")) s->ascent_grid = std::max(atoi(e), 1) * std::max(sms, 1);   // grid-stride CTAs per SM (tuning)
         if (getenv("F3D_B200_DEBUG"))
             fprintf(stderr, "[forge3d_b200] k_trace: %d CTAs/SM x %d SMs, %zu B smem/CTA, stack depth %u\n", per_sm, sms,
                     s->trace_smem_bytes, P.stack_depth);
@@ -1099,6 +1102,17 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
         if (s->n_sets > 1) CUDA_TRY(cudaStreamCreateWithFlags(&bs.stream, cudaStreamNonBlocking));
     }
     if (s->n_sets > 1) CUDA_TRY(cudaEventCreateWithFlags(&s->join_ev, cudaEventDisableTiming));
+    if (s->n_sets > 1) {
+        // The k_ptrace / k_shade chain is the only frame-to-frame (and, partitioned, GPU-to-GPU) dependency; on its own
+        // high-priority stream its CTAs are scheduled ahead of the secondary-ray kernels of the other batch set whenever an SM has
+        // room.  Opt-in until measured at N = 8 (F3D_B200_PRIM_PRIORITY=1).
+        const char* e = getenv("F3D_B200_PRIM_PRIORITY");
+        if (e && atoi(e) != 0) {
+            int least = 0, greatest = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CUDA_TRY(cudaStreamCreateWithPriority(&s->prim_stream, cudaStreamNonBlocking, greatest));
+        }
+    }
     if (P.spp > 1u && (rc = dmalloc(s, &s->d_sstate, npx * 3, true))) return rc;
     P.sstate = s->d_sstate;
     P.sample_index = 0u;
@@ -1168,9 +1182,11 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
     NvtxRange nvtx_frames("hybrid_pt.terrain");
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     const bool pipelined = s->n_sets > 1;
+    cudaStream_t ps = (pipelined && s->prim_stream) ? s->prim_stream : s->stream;      // stream of the primary pass
     if (pipelined) {   // the set streams start after whatever is already queued on the session stream
         CUDA_TRY(cudaEventRecord(s->join_ev, s->stream));
         for (int k = 0; k < s->n_sets; k++) CUDA_TRY(cudaStreamWaitEvent(s->sets[k].stream, s->join_ev, 0));
+        if (ps != s->stream) CUDA_TRY(cudaStreamWaitEvent(ps, s->join_ev, 0));
     }
     FrameParams& P = s->P;
     const uint32_t spp = P.spp;
@@ -1181,7 +1197,7 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
         f3d_session::BatchSet& bs = s->sets[s->batches % (uint64_t)s->n_sets];
         f3d_session::BatchSet& prev = s->sets[(s->batches + (uint64_t)s->n_sets - 1u) % (uint64_t)s->n_sets];
         cudaStream_t ts = pipelined ? bs.stream : s->stream;
-        if (pipelined && bs.used) CUDA_TRY(cudaStreamWaitEvent(s->stream, bs.accum_done, 0));   // buffer set free again
+        if (pipelined && bs.used) CUDA_TRY(cudaStreamWaitEvent(ps, bs.accum_done, 0));   // buffer set free again
         const uint32_t frame0 = s->frames, sample0 = sample;
         // ---- the primaries of the batch, back to back (split path: ONE traversal launch for the batch, then the cheap
         // per-frame shading chain) ----
@@ -1190,7 +1206,7 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             P.sample_index = 0u;
             P.n_batch = nb;
             for (uint32_t k = 0; k < nb; k++) P.slot[k] = bs.slots[k];
-            k_ptrace<<<dim3(s->grid.x, s->grid.y, nb), kThreads, s->ptrace_smem_bytes, s->stream>>>(P);
+            k_ptrace<<<dim3(s->grid.x, s->grid.y, nb), kThreads, s->ptrace_smem_bytes, ps>>>(P);
             s->launches++;
         }
         for (uint32_t k = 0; k < nb; k++) {
@@ -1209,14 +1225,14 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
             P.cur = bs.slots[k];
             P.n_batch = 0u;
             NvtxRange nvtx_shade("hybrid_pt.restir_temporal+restir_spatial");
-            if (s->split_primary) k_shade<<<s->grid, kThreads, 0, s->stream>>>(P);
-            else k_primary<<<s->grid, kThreads, s->smem_bytes, s->stream>>>(P);
+            if (s->split_primary) k_shade<<<s->grid, kThreads, 0, ps>>>(P);
+            else k_primary<<<s->grid, kThreads, s->smem_bytes, ps>>>(P);
             s->launches++;
             s->steps++;
             if (++sample == spp) { sample = 0u; s->frames++; }
         }
         if (pipelined) {
-            CUDA_TRY(cudaEventRecord(bs.primary_done, s->stream));
+            CUDA_TRY(cudaEventRecord(bs.primary_done, ps));
             CUDA_TRY(cudaStreamWaitEvent(ts, bs.primary_done, 0));
         }
         // ---- one launch of each later kernel for the whole batch ----
