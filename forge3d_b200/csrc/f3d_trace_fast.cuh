@@ -951,13 +951,64 @@ constexpr int kLeafBatch = F3D_LEAF_BATCH;
 #define F3D_LEAF_BATCH_COOP F3D_LEAF_BATCH
 #endif
 constexpr int kLeafBatchCoop = F3D_LEAF_BATCH_COOP;   // static-lane traversal (primary / G-buffer rays)
+#ifndef F3D_LEAF_BATCH_PARK
+#define F3D_LEAF_BATCH_PARK 12
+#endif
+constexpr int kLeafBatchPark = F3D_LEAF_BATCH_PARK;   // F3D_PRIMARY_PARK: lanes that can do nothing but wait for their parked leaf
 
+// F3D_PRIMARY_PARK = 1: a lane that meets a leaf PARKS it (one slot, a register) and keeps expanding until it meets its next
+// leaf; the solve phase then finds more lanes with a leaf, and fewer lanes idle through the expansion steps.  Exact for
+// closest-hit rays too: the clipped spans of the leaves a ray visits are disjoint and ordered (F3D_CULL_FAST (3)), so until the
+// first hit every solve sees best_t = tmax and is independent of the others, and after the first hit at t* every later leaf
+// has t_lo >= t* = best_t, i.e. an empty (or single-point) clipped span: the first hit in visit order IS the closest hit and
+// the ray can stop there.  One parked leaf keeps the per-ray solve order (the parked leaf is always the oldest unsolved one).
+#ifndef F3D_PRIMARY_PARK
+#define F3D_PRIMARY_PARK 0
+#endif
 template <bool ANY_HIT, bool CURV, class Q = QGlobal>
 __device__ __forceinline__ FastHit trace_fast(const FastScene& S, const Ray& r, bool valid, const SmemStack st, uint32_t& nodes, const Q q = Q()) {
     TraceState T;
     T.sp = 0u; T.hit = false; T.best_t = r.tmax; T.best_cx = 0u; T.best_cz = 0u;
     if (valid) trace_begin<CURV>(S, r, T, st);
     bool busy = T.sp != 0u;
+#if F3D_PRIMARY_PARK
+    if (!CURV || ANY_HIT) {      // (curved closest-hit rays keep the exact expansion with its stale re-tests: not used by the renderer)
+        constexpr uint32_t kNone = 0xFFFFFFFFu;
+        uint32_t parked = kNone;
+        while (__ballot_sync(0xFFFFFFFFu, busy || parked != kNone) != 0u) {
+            while (true) {
+                if (busy && parked == kNone && top_is_leaf(T, st)) {       // park the leaf, go on with what lies behind it
+                    T.sp--;
+                    parked = st.at(T.sp);
+                    if (T.sp == 0u) busy = false;
+                }
+                const bool can_expand = busy && !top_is_leaf(T, st);
+                if (can_expand) {
+                    if (CURV) {
+                        if (ANY_HIT && T.d.y >= 0.0f && T.tmin >= 0.0f) expand_node<ANY_HIT, CURV, false, Q>(S, T, st, q);
+                        else expand_node<ANY_HIT, CURV, true, Q>(S, T, st, q);
+                    } else expand_node<ANY_HIT, CURV, false, Q>(S, T, st, q);
+                    nodes++;
+                    if (T.sp == 0u) busy = false;
+                }
+                // a lane can go on if it can expand, or if it can still park the leaf it just reached
+                const bool more = busy && (!top_is_leaf(T, st) || parked == kNone);
+                const uint32_t m_more = __ballot_sync(0xFFFFFFFFu, more);
+                const uint32_t m_leaf = __ballot_sync(0xFFFFFFFFu, parked != kNone && !more);
+                if (m_more == 0u || __popc(m_leaf) >= kLeafBatchPark) break;
+            }
+            if (parked != kNone) {
+                nodes++;
+                const bool done = leaf_node<ANY_HIT, CURV>(S, T, parked);
+                parked = kNone;
+                if (done || T.hit) { busy = false; T.sp = 0u; }       // first hit in visit order = the closest hit (see above)
+            }
+        }
+        FastHit res;
+        res.hit = T.hit; res.t = T.best_t; res.cx = T.best_cx; res.cz = T.best_cz;
+        return res;
+    }
+#endif
     while (__ballot_sync(0xFFFFFFFFu, busy) != 0u) {
         while (true) {
             const bool can_expand = busy && !top_is_leaf(T, st);

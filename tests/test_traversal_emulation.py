@@ -10,7 +10,8 @@ import _helpers as H
 from oracle import oracle
 
 # compile-time variants of the traversal that must all be exact (the default build is the first one)
-VARIANTS = {"default": (), "anyhit_sorted": ("F3D_ANYHIT_SIGN_ORDER=0",), "literal_push_clip": ("F3D_PUSH_CLIP_FOLDED=0",)}
+VARIANTS = {"default": (), "anyhit_sorted": ("F3D_ANYHIT_SIGN_ORDER=0",), "literal_push_clip": ("F3D_PUSH_CLIP_FOLDED=0",),
+            "parked_leaf": ("F3D_PRIMARY_PARK=1",)}
 # variants whose any-hit rays may report a different (equally valid) first hit: flags are compared, not t
 FLAG_ONLY_ANYHIT = {"default", "literal_push_clip"}
 

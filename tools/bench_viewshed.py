@@ -49,6 +49,18 @@ def main():
             "config": {"workload": f"rainier-shaped {args.n}x{args.n} DEM, WGS84 ellipsoid + standard refraction", "visible_fraction": float(np.mean(out["visibility"]))},
             "e2e": {"viewshed_ms": e2e["viewshed"], "shadow_mask_ms": e2e["shadow_mask"], "viewshed_mcells_per_s": cells / e2e["viewshed"] / 1e3,
                     "shadow_mask_mcells_per_s": cells / e2e["shadow_mask"] / 1e3, "h2d_bytes_per_step": 12 * cells, "d2h_bytes_per_step": 13 * cells}}
+    # issue-slot roofline: warp-instructions of this exact workload (ncu smsp__inst_executed.sum of k_viewshed on the B200, the count
+    # is deterministic for a fixed DEM / observer; profiles/r02_rows_instr.json) over the SM issue rate 148 SMs x 4 schedulers x 1.965 GHz
+    try:
+        rows = json.loads((ROOT / "profiles" / "r02_rows_instr.json").read_text())
+        wi = rows.get(f"k_viewshed_{args.n}")
+        if wi:
+            peak = 148 * 4 * 1.965e9
+            line["roofline"] = {"bound": "issue", "achieved": wi / (best["viewshed"] * 1e-3), "peak": peak, "unit": "warp-instr/s",
+                                "frac": wi / (best["viewshed"] * 1e-3) / peak, "traffic": None,
+                                "model": f"{wi:.4g} warp-instructions per launch (ncu, 27.1 of 32 lanes active) / kernel time / (148 x 4 x 1.965e9)"}
+    except Exception:
+        pass
     try:
         from oracle import oracle
 
