@@ -52,11 +52,13 @@ struct DevCache {
     std::multimap<size_t, void*> parked[16];
     std::unordered_map<void*, size_t> sizes;
     size_t parked_bytes[16] = {};
-    // per-device cap: about one 4K session's working set (F3D_B200_CACHE_MB overrides, 0 = never park).  The process may share
-    // the device with torch / NCCL: what is parked here is invisible to them, so the cap is deliberately modest and
-    // f3d_cache_trim() hands everything back.
+    // per-device cap: one session's working set (F3D_B200_CACHE_MB overrides, 0 = never park).  The per-step buffers of a session
+    // are budgeted at 8 GB (session_create_impl), so a 4 GB cap made every partitioned 1080p session with batches of 8 steps
+    // (4.6 GB) cudaMalloc / cudaFree its overflow on every call: 11-19 ms of session creation at N = 4 / 8 against 1.6 ms at
+    // N = 2 (gpurun call X).  10 GB of a 180 GB device covers it.  The process may share the device with torch / NCCL: what is
+    // parked here is invisible to them, so f3d_cache_trim() hands everything back on request.
     size_t cap() const {
-        static const size_t c = [] { const char* e = getenv("F3D_B200_CACHE_MB"); return e ? (size_t)std::max(atoll(e), 0ll) << 20 : (size_t)4 << 30; }();
+        static const size_t c = [] { const char* e = getenv("F3D_B200_CACHE_MB"); return e ? (size_t)std::max(atoll(e), 0ll) << 20 : (size_t)10 << 30; }();
         return c;
     }
 };

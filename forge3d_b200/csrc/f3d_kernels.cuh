@@ -1104,6 +1104,10 @@ __device__ __forceinline__ void trace_list_bu(const FrameParams& P, const BatchS
 // are appended (warp ballot + prefix sum, one atomic per warp) to the stage-2 lists k_trace traverses.
 // Leaf work items of one k_ascent warp (the near-field walk): same records as k_trace's ring, 64 entries (<= 31 waiting +
 // 32 from one walk step).  All members are called by the 32 lanes of a converged warp.
+// F3D_ASCENT_PREFETCH = 1: k_ascent requests the next iteration's ray record into L2 one iteration ahead (A/B: profiles/).
+#ifndef F3D_ASCENT_PREFETCH
+#define F3D_ASCENT_PREFETCH 0
+#endif
 constexpr uint32_t kWalkMaxCols = kSunNearMaxCols > kEscNearCols ? kSunNearMaxCols : kEscNearCols;
 constexpr uint32_t kLeafQA = 64u;
 constexpr size_t kAscentRingBytes = (256 / 32) * 3 * kLeafQA * sizeof(uint32_t);     // k_ascent runs 256-thread CTAs
@@ -1164,6 +1168,12 @@ __device__ __forceinline__ void ascent_list(const FrameParams& P, const BatchSlo
         unsigned long long seeds = 0ull, kbits = 0ull;
         uint32_t near_cols = 0u, near_pixw = 0u;      // near-field walk: columns to visit, 0 = not a walk ray
         TraceState T{};
+#if F3D_ASCENT_PREFETCH
+        // the NEXT iteration's record (64 B per pixel, written by k_shade of up to 4 frames ago: DRAM, not L2) is requested now;
+        // its list entry is loaded here and consumed by the prefetch below, after the patch solve has covered the load's latency
+        uint32_t pix_next = 0xFFFFFFFFu;
+        if (i + stride < n) pix_next = __ldg(queue + i + stride);
+#endif
         if (i < n) {
             pix = __ldg(queue + i);
             const float4 r0 = __ldcg(B.rec + 4 * (size_t)pix);
@@ -1225,6 +1235,9 @@ __device__ __forceinline__ void ascent_list(const FrameParams& P, const BatchSlo
                 }
             }
         }
+#if F3D_ASCENT_PREFETCH
+        if (pix_next != 0xFFFFFFFFu) prefetch_l2(B.rec + 4 * (size_t)pix_next);
+#endif
         if (PASS == 0) {                         // far rays: compacted into the far list
             const uint32_t mf = __ballot_sync(0xFFFFFFFFu, far);
             if (mf != 0u) {

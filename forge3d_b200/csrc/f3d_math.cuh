@@ -48,6 +48,13 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
     (void)p;
 #endif
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 __device__ __forceinline__ float dot3(v3 a, v3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 __device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) { return ax * bx + ay * by; }
 __device__ __forceinline__ v3 cross3(v3 a, v3 b) {

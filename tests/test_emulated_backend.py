@@ -11,7 +11,8 @@ import _helpers as H
 from oracle import oracle
 
 VARIANTS = {"default": (), "anyhit_sorted": ("F3D_ANYHIT_SIGN_ORDER=0",), "literal_push_clip": ("F3D_PUSH_CLIP_FOLDED=0",),
-            "deferred_leaves": ("F3D_TRACE_DEFER_LEAVES=4", "F3D_DEFER_RULE=2", "F3D_DEFER_STALL=4", "F3D_DEFER_LEAF_BATCH=20")}
+            "deferred_leaves": ("F3D_TRACE_DEFER_LEAVES=4", "F3D_DEFER_RULE=2", "F3D_DEFER_STALL=4", "F3D_DEFER_LEAF_BATCH=20"),
+            "parked_primary_leaf": ("F3D_PRIMARY_PARK=1",), "no_sun_walk": ("F3D_SUN_NEAR=0",), "tma_staging": ("F3D_TMA_STAGE=1",)}
 
 
 def _bits(a):
@@ -36,6 +37,28 @@ def test_emulated_render_is_bit_identical_to_the_oracle(variant):
         g = native.hybrid_render_terrain_reference(dem, 56, 40, H.CAM, want_accum=True, **kw)
     _same_render(g, o)
     assert o["rays_shadow"] > 1000 and np.isfinite(o["depth"]).any() and np.isnan(o["depth"]).any()
+
+
+@pytest.mark.parametrize("az,el,earth,escape", [(20.0, 35.0, "flat", "1"), (110.0, 12.0, "wgs84", "0"), (200.0, 60.0, "flat", "1"), (290.0, 3.0, "wgs84", "1"),
+                                                (135.0, 0.5, "flat", "0"), (270.0, 89.97, "flat", "1")])
+def test_emulated_near_field_walks_are_bit_identical_to_the_oracle(az, el, earth, escape, monkeypatch):
+    """The CPU twin of tests/test_gpu_parity.py::test_sun_horizon_strips_are_exact_in_every_octant / test_escape_map_is_exact_and_culls:
+    sun horizon strips + the near-field walk of k_ascent (two passes per list, far lists) and, with F3D_B200_ESCAPE=1, the escape map
+    for the IBL rays, over a rough, ragged, non-square DEM for several octants of the sun direction - under the SIMT interpreter, so
+    that the warp-convergent walk loops and the leaf rings are exercised with real 32-lane collectives before any GPU time."""
+    rng = np.random.default_rng(int(az * 7 + el * 13))
+    shape = (83, 121)
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+    dem = (0.6 * np.sin(xx / 9.0) * np.cos(yy / 7.0) + 0.4 * np.sin((xx + 2 * yy) / 17.0) + 0.35 * rng.uniform(0.0, 1.0, shape)).astype(np.float32)
+    span = 120.0
+    kw = dict(spacing=(span / (shape[1] - 1), 0.8 * span / (shape[0] - 1)), exaggeration=14.0, albedo=H.ALBEDO, sun_azimuth_deg=az,
+              sun_elevation_deg=el, earth_model=earth, refraction_model="none" if earth == "flat" else "bennett", max_frames=3, min_frames=3,
+              variance_threshold=1e30)
+    monkeypatch.setenv("F3D_B200_ESCAPE", escape)
+    o = oracle.render(dem, 72, 48, H.CAM, want_accum=True, **kw)
+    with _emu.emulated_backend() as native:
+        g = native.hybrid_render_terrain_reference(dem, 72, 48, H.CAM, want_accum=True, **kw)
+    _same_render(g, o)
 
 
 def test_emulated_render_with_mesh_env_map_spp_and_curvature():

@@ -86,6 +86,18 @@ def main():
             "e2e": {"value": px / min(e2e_ms) / 1e3, "unit": "Mpx/s", "h2d_bytes_per_step": 24 * args.n ** 3, "d2h_bytes_per_step": 4 * px},
             "roofline": {"bound": "hbm", "achieved": algo_bytes / best / 1e6, "peak": peak, "unit": "GB/s", "frac": algo_bytes / best / 1e6 / peak,
                          "traffic": None, "peak_source": how}}
+    # the kernel is cache- and issue-bound: second roofline against the SM issue rate (warp-instructions of this exact frame from ncu
+    # on the B200, profiles/r02_rows_instr.json)
+    try:
+        rows = json.loads((ROOT / "profiles" / "r02_rows_instr.json").read_text())
+        wi = rows.get(f"k_smoke_march_{args.width}x{args.height}_{args.n}")
+        if wi:
+            ipeak = 148 * 4 * 1.965e9
+            line["roofline_issue"] = {"bound": "issue", "achieved": wi / (best * 1e-3), "peak": ipeak, "unit": "warp-instr/s",
+                                      "frac": wi / (best * 1e-3) / ipeak,
+                                      "model": f"{wi:.4g} warp-instructions per frame (ncu, {rows.get('k_smoke_lanes', 0):.1f} of 32 lanes active) / kernel time / (148 x 4 x 1.965e9)"}
+    except Exception:
+        pass
     try:
         from oracle import oracle
 

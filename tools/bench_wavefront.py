@@ -42,6 +42,17 @@ def main():
            "kernel_ms": round(st.kernel_ms, 3), "e2e_ms": round(wall * 1e3, 3),
            "device_mrays_per_s": round(st.rays / max(st.kernel_ms, 1e-9) / 1e3, 1), "e2e_mrays_per_s": round(st.rays / wall / 1e6, 1),
            "us_per_frame": round(st.kernel_ms * 1e3 / a.spp, 2)}
+    # issue-slot roofline: warp-instructions per 512 x 512 frame of this scene (ncu smsp__inst_executed.sum summed over the k_wf_*
+    # launches of a 16-frame render on the B200, profiles/r02_rows_instr.json) over the SM issue rate 148 x 4 x 1.965 GHz
+    try:
+        rows = json.loads((ROOT / "profiles" / "r02_rows_instr.json").read_text())
+        if a.size == 512 and rows.get("k_wf_per_frame_512"):
+            wi, peak = rows["k_wf_per_frame_512"] * a.spp, 148 * 4 * 1.965e9
+            out["roofline"] = {"bound": "issue", "achieved": wi / (st.kernel_ms * 1e-3), "peak": peak, "unit": "warp-instr/s",
+                               "frac": wi / (st.kernel_ms * 1e-3) / peak, "traffic": None,
+                               "model": f"{rows['k_wf_per_frame_512']:.4g} warp-instructions per frame (ncu, {rows.get('k_wf_lanes', 0):.1f} of 32 lanes active) x spp / kernel time / (148 x 4 x 1.965e9)"}
+    except Exception:
+        pass
     if a.oracle_spp > 0:
         from oracle import oracle
         t0 = time.perf_counter()
