@@ -163,6 +163,8 @@ typedef struct f3do_smoke_settings {   /* SmokeRenderSettings, src/smoke/types.r
 int f3do_smoke_raymarch_rgba(const f3do_smoke_volume* vol, const f3do_smoke_settings* settings, uint32_t width, uint32_t height,
                              const float camera_pos[3], const float target[3], const float up[3], float fovy_deg,
                              const float sun_direction[3], uint8_t* rgba);
+/* straight-alpha over, python/forge3d/map_scene.py:1588-1604 (_alpha_composite_rgba), n pixels */
+void f3do_composite_over_rgba(const uint8_t* bottom, const uint8_t* top, uint64_t n, uint8_t* out);
 /* the layer composited over a terrain frame (python/forge3d/map_scene.py:1588-1604); base_depth nullable */
 int f3do_smoke_raymarch_over_rgba(const f3do_smoke_volume* vol, const f3do_smoke_settings* settings, uint32_t width, uint32_t height,
                                   const float camera_pos[3], const float target[3], const float up[3], float fovy_deg,

@@ -291,6 +291,13 @@ static void composite_over(uint8_t* dst, const uint8_t* src) {
     dst[3] = dst[3] > src[3] ? dst[3] : src[3];
 }
 
+/* The compositor alone, n pixels: out = over(bottom, top).  Pinned by tests/golden/alpha_composite_vectors.npz, which the
+ * reference's own function produced (tools/make_composite_golden.py). */
+void f3do_composite_over_rgba(const uint8_t* bottom, const uint8_t* top, uint64_t n, uint8_t* out) {
+    memcpy(out, bottom, (size_t)n * 4);
+    for (uint64_t i = 0; i < n; i++) composite_over(out + i * 4, top + i * 4);
+}
+
 /* The smoke layer over a terrain frame (BASELINE config 4): SmokeVolume::raymarch_rgba (render.rs:6-101) per pixel, the march
  * optionally ended at the terrain depth (NaN / <= 0 = sky; NULL = the reference's bare layer), then _alpha_composite_rgba. */
 int f3do_smoke_raymarch_over_rgba(const f3do_smoke_volume* V, const f3do_smoke_settings* st, uint32_t width, uint32_t height,

@@ -383,6 +383,20 @@ def smoke_raymarch_rgba(domain, settings, width, height, camera_pos, target, up=
     return out
 
 
+def composite_over_rgba(bottom, top):
+    """_alpha_composite_rgba (python/forge3d/map_scene.py:1588-1604) on two (H, W, 4) uint8 images."""
+    L = _smoke_lib()
+    b, t = np.ascontiguousarray(bottom, np.uint8), np.ascontiguousarray(top, np.uint8)
+    if b.shape != t.shape or b.shape[-1] != 4:
+        raise OracleError("composite_over_rgba needs two RGBA images of the same shape")
+    out = np.empty_like(b)
+    L.f3do_composite_over_rgba.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_uint64, C.POINTER(C.c_uint8)]
+    L.f3do_composite_over_rgba.restype = None
+    L.f3do_composite_over_rgba(b.ctypes.data_as(C.POINTER(C.c_uint8)), t.ctypes.data_as(C.POINTER(C.c_uint8)), b.size // 4,
+                               out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return out
+
+
 def smoke_raymarch_over_rgba(domain, settings, width, height, camera_pos, target, base_rgba, base_depth=None, up=(0.0, 1.0, 0.0),
                              fovy_deg=45.0, sun_direction=(0.4, 0.8, -0.2)):
     """The smoke layer (render.rs:6-101) composited over a terrain frame with _alpha_composite_rgba

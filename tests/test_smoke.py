@@ -178,6 +178,19 @@ def _reference_alpha_composite(bottom, top):
     return out
 
 
+def test_compositor_matches_vectors_produced_by_the_reference_function():
+    """tests/golden/alpha_composite_vectors.npz was written by the REFERENCE's own `_alpha_composite_rgba`
+    (python/forge3d/map_scene.py:1588-1603, cut out and executed by tools/make_composite_golden.py): every alpha value, both
+    orderings of the two alphas, saturated colours.  The C oracle's compositor and the numpy restatement used by the tests above
+    must reproduce it byte for byte - this pins config 4's composite to the reference, not to a restatement."""
+    from pathlib import Path
+
+    v = np.load(Path(__file__).parent / "golden" / "alpha_composite_vectors.npz")
+    assert np.array_equal(oracle.composite_over_rgba(v["bottom"], v["top"]), v["out"])
+    assert np.array_equal(_reference_alpha_composite(v["bottom"], v["top"]), v["out"])
+    assert (v["out"][..., :3] != v["bottom"][..., :3]).any() and len(np.unique(v["top"][..., 3])) == 256
+
+
 def _terrain_like_frame(seed, W, Hh, near, far):
     rng = np.random.default_rng(seed)
     base = rng.integers(0, 256, (Hh, W, 4), dtype=np.uint8)
