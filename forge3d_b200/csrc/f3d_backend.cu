@@ -692,6 +692,7 @@ struct f3d_session {
     size_t ascent_smem_bytes = 0;   // k_ascent: leaf rings of the near-field walk (+ staged top levels)
     int trace_grid = 0;             // persistent CTAs of k_trace
     int ascent_grid = 0;            // grid-stride CTAs of k_ascent
+    bool ramp = true;               // half-size first batch of every render_frames call (F3D_B200_RAMP)
     cudaStream_t prim_stream = nullptr;   // optional high-priority stream of the primary pass (F3D_B200_PRIM_PRIORITY=1)
     // Frame batching + pipelining.  k_primary(step+1) only depends on k_primary(step) (reservoir records); everything after it
     // (k_ascent, k_trace, k_accum) depends on k_primary of the same step and on k_accum of the step before.  Steps are
@@ -1080,6 +1081,7 @@ static int session_create_impl(const f3d_terrain_desc* d, void* cuda_stream, f3d
         s->n_sets = es ? std::min(std::max(atoi(es), 1), (int)f3d_session::kMaxSets) : (by_memory >= 2 ? 2 : 1);
         s->batch = eb ? std::min(std::max(atoi(eb), 1), kMaxBatch) : std::min(P.part_world > 2u ? 8 : 4, std::max(by_memory / s->n_sets, 1));   // small partitions: bigger batches
         if (const char* e = getenv("F3D_B200_PIPELINE")) if (atoi(e) <= 1) { s->n_sets = 1; s->batch = 1; }
+        if (const char* e = getenv("F3D_B200_RAMP")) s->ramp = atoi(e) != 0;
     }
     for (int k = 0; k < s->n_sets; k++) {
         f3d_session::BatchSet& bs = s->sets[k];
@@ -1194,8 +1196,15 @@ extern "C" int f3d_session_render_frames(f3d_session* s, uint32_t n) {
     const uint32_t spp = P.spp;
     uint64_t todo = (uint64_t)n * spp;            // steps; a call always starts and ends on a frame boundary
     uint32_t sample = 0u;
+    bool first_batch = true;
     while (todo > 0) {
-        const uint32_t nb = (uint32_t)std::min<uint64_t>(todo, (uint64_t)s->batch);
+        // Ramp: the FIRST batch of a call is half a batch.  Its primaries run alone (nothing to overlap with yet), and the steps it
+        // leaves over make the LAST batch, whose secondary rays run alone, half a batch as well: 20 frames = 2 + 4 x 4 + 2.
+        // (F3D_B200_RAMP=0: full batches from the start.)
+        uint32_t cap = (uint32_t)s->batch;
+        if (pipelined && s->ramp && first_batch && s->batch >= 4 && todo > (uint64_t)s->batch) cap = (uint32_t)s->batch / 2u;
+        first_batch = false;
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(todo, (uint64_t)cap);
         f3d_session::BatchSet& bs = s->sets[s->batches % (uint64_t)s->n_sets];
         f3d_session::BatchSet& prev = s->sets[(s->batches + (uint64_t)s->n_sets - 1u) % (uint64_t)s->n_sets];
         cudaStream_t ts = pipelined ? bs.stream : s->stream;
