@@ -693,6 +693,9 @@ struct f3d_session {
     int trace_grid = 0;             // persistent CTAs of k_trace
     int ascent_grid = 0;            // grid-stride CTAs of k_ascent
     bool ramp = true;               // half-size first batch of every render_frames call (F3D_B200_RAMP)
+    cudaStream_t copy_stream = nullptr;   // one-call path: AOV decode + D2H beside the frame loop (early_aov_readback)
+    bool aovs_early = false;              // the AOVs of this session are already on their way to the caller's arrays
+    uint64_t aovs_early_bytes = 0;
     cudaStream_t prim_stream = nullptr;   // optional high-priority stream of the primary pass (F3D_B200_PRIM_PRIORITY=1)
     // Frame batching + pipelining.  k_primary(step+1) only depends on k_primary(step) (reservoir records); everything after it
     // (k_ascent, k_trace, k_accum) depends on k_primary of the same step and on k_accum of the step before.  Steps are
@@ -761,6 +764,7 @@ static void session_free(f3d_session* s) {
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->prim_stream) { cudaStreamSynchronize(s->prim_stream); cudaStreamDestroy(s->prim_stream); }
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -1443,6 +1447,42 @@ extern "C" int f3d_session_stats(f3d_session* s, f3d_terrain_out* out) {
     return fill_stats(s, out);
 }
 
+// One-call path: the three AOVs are frame-0 data (G-buffer pass of session creation).  When the caller's AOV arrays are page-locked
+// (the Python seam allocates them with f3d_host_alloc) they are decoded and copied on a side stream while the frames render, and
+// f3d_session_resolve_host only has the 4 B/pixel beauty image left.  Pageable destinations keep the old path (bounce buffers).
+// F3D_B200_EARLY_AOVS=0 switches it off.
+static int early_aov_readback(f3d_session* s, f3d_terrain_out* out) {
+    if (const char* e = getenv("F3D_B200_EARLY_AOVS")) if (atoi(e) == 0) return 0;
+    if (!out->albedo && !out->normal && !out->depth) return 0;
+    void* dst[3] = {out->albedo, out->normal, out->depth};
+    for (void* p : dst) {
+        if (!p) continue;
+        cudaPointerAttributes at{};
+        const bool pinned = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (!pinned) return 0;
+    }
+    const size_t npx = (size_t)s->P.W * s->P.H;
+    int rc;
+    if (out->albedo && !s->d_albedo && (rc = dmalloc(s, &s->d_albedo, npx * 3, false))) return rc;
+    if (out->normal && !s->d_normal && (rc = dmalloc(s, &s->d_normal, npx * 3, false))) return rc;
+    if (out->depth && !s->d_depth && (rc = dmalloc(s, &s->d_depth, npx, false))) return rc;
+    if (!s->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));          // the G-buffer pass and the allocations' memsets are done
+    ResolveOut R{};
+    R.albedo = out->albedo ? s->d_albedo : nullptr; R.normal = out->normal ? s->d_normal : nullptr; R.depth = out->depth ? s->d_depth : nullptr;
+    R.aov_normal = s->d_aov_normal; R.aov_depth = s->d_aov_depth;
+    k_resolve_aovs<<<s->grid, kTileW * kTileH, 0, s->copy_stream>>>(s->P, R);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (out->albedo) CUDA_TRY(cudaMemcpyAsync(out->albedo, s->d_albedo, npx * 12, cudaMemcpyDeviceToHost, s->copy_stream));
+    if (out->normal) CUDA_TRY(cudaMemcpyAsync(out->normal, s->d_normal, npx * 12, cudaMemcpyDeviceToHost, s->copy_stream));
+    if (out->depth) CUDA_TRY(cudaMemcpyAsync(out->depth, s->d_depth, npx * 4, cudaMemcpyDeviceToHost, s->copy_stream));
+    s->aovs_early = true;
+    s->aovs_early_bytes = (out->albedo ? npx * 12 : 0) + (out->normal ? npx * 12 : 0) + (out->depth ? npx * 4 : 0);
+    return 0;
+}
+
 extern "C" int f3d_session_resolve_host(f3d_session* s, f3d_terrain_out* out) {
     if (!s || !out) return fail(F3D_ERR_ARGUMENT, "null argument");
     CUDA_TRY(cudaSetDevice(s->device));
@@ -1450,11 +1490,12 @@ extern "C" int f3d_session_resolve_host(f3d_session* s, f3d_terrain_out* out) {
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     int rc;
     if (out->rgba && !s->d_rgba && (rc = dmalloc(s, &s->d_rgba, npx * 4, false))) return rc;
-    if (out->albedo && !s->d_albedo && (rc = dmalloc(s, &s->d_albedo, npx * 3, false))) return rc;
-    if (out->normal && !s->d_normal && (rc = dmalloc(s, &s->d_normal, npx * 3, false))) return rc;
-    if (out->depth && !s->d_depth && (rc = dmalloc(s, &s->d_depth, npx, false))) return rc;
-    rc = resolve_device_impl(s, out->rgba ? s->d_rgba : nullptr, out->albedo ? s->d_albedo : nullptr,
-                             out->normal ? s->d_normal : nullptr, out->depth ? s->d_depth : nullptr, 1);
+    const bool early = s->aovs_early;                    // the AOVs already travel on the copy stream (early_aov_readback)
+    if (!early && out->albedo && !s->d_albedo && (rc = dmalloc(s, &s->d_albedo, npx * 3, false))) return rc;
+    if (!early && out->normal && !s->d_normal && (rc = dmalloc(s, &s->d_normal, npx * 3, false))) return rc;
+    if (!early && out->depth && !s->d_depth && (rc = dmalloc(s, &s->d_depth, npx, false))) return rc;
+    rc = resolve_device_impl(s, out->rgba ? s->d_rgba : nullptr, (!early && out->albedo) ? s->d_albedo : nullptr,
+                             (!early && out->normal) ? s->d_normal : nullptr, (!early && out->depth) ? s->d_depth : nullptr, 1);
     if (rc) return rc;
     // Device -> caller memory: page-locked destinations (the Python layer's arrays come from f3d_host_alloc) are written by one
     // DMA each; pageable ones go through the bounce buffers of copy_to_host.
@@ -1466,9 +1507,15 @@ extern "C" int f3d_session_resolve_host(f3d_session* s, f3d_terrain_out* out) {
         return 0;
     };
     if ((rc = pull(out->rgba, s->d_rgba, npx * 4))) return rc;
-    if ((rc = pull(out->albedo, s->d_albedo, npx * 12))) return rc;
-    if ((rc = pull(out->normal, s->d_normal, npx * 12))) return rc;
-    if ((rc = pull(out->depth, s->d_depth, npx * 4))) return rc;
+    if (!early) {
+        if ((rc = pull(out->albedo, s->d_albedo, npx * 12))) return rc;
+        if ((rc = pull(out->normal, s->d_normal, npx * 12))) return rc;
+        if ((rc = pull(out->depth, s->d_depth, npx * 4))) return rc;
+    } else {
+        pulled += s->aovs_early_bytes;
+        CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+        s->aovs_early = false;                           // a later resolve of the same session takes the ordinary path
+    }
     if ((rc = pull(out->accum, s->d_accum, npx * 16))) return rc;
     s->host_visible_bytes = std::max<uint64_t>(s->host_visible_bytes, pulled + 16);
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
@@ -1529,6 +1576,7 @@ extern "C" int f3d_terrain_reference_render(const f3d_terrain_desc* desc, f3d_te
     f3d_session* s = nullptr;
     int rc = f3d_session_create(desc, nullptr, &s);
     if (rc) return rc;
+    if ((rc = early_aov_readback(s, out))) { f3d_session_destroy(s); return rc; }
     float variance = INFINITY;
     bool converged = false;
     cudaEvent_t t0, t1;

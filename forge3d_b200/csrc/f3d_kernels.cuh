@@ -1583,6 +1583,29 @@ __global__ void __launch_bounds__(kThreads) k_resolve(const __grid_constant__ Fr
     }
 }
 
+// The AOV half of k_resolve alone: albedo / normal / depth come from the one-shot G-buffer pass (frame 0, render_terrain.rs:1091-1121),
+// so the one-call path decodes them right after set-up and copies them to the host WHILE the frames render (f3d_backend.cu
+// early_aov_readback): 58 of the 66 MB of a 1080p read-back leave the critical path.  Same expressions as k_resolve.
+__global__ void __launch_bounds__(kThreads) k_resolve_aovs(const __grid_constant__ FrameParams P, ResolveOut R) {
+    uint32_t gx, gy;
+    if (!owned_pixel(P, gx, gy)) return;
+    const uint32_t pix = gy * P.W + gx;
+    const uint32_t hit_type = (P.pixflags[pix] >> 1) & 3u;
+    if (R.albedo) {
+        v3 a = hit_type == 1u ? ld3(P.scene.albedo) : (hit_type == 2u ? V3(0.7f, 0.7f, 0.8f) : V3(0, 0, 0));
+        R.albedo[3 * (size_t)pix + 0] = f16_round(a.x);
+        R.albedo[3 * (size_t)pix + 1] = f16_round(a.y);
+        R.albedo[3 * (size_t)pix + 2] = f16_round(a.z);
+    }
+    if (R.normal) {
+        const ushort4 n16 = R.aov_normal[pix];
+        R.normal[3 * (size_t)pix + 0] = __half2float(__ushort_as_half(n16.x));
+        R.normal[3 * (size_t)pix + 1] = __half2float(__ushort_as_half(n16.y));
+        R.normal[3 * (size_t)pix + 2] = __half2float(__ushort_as_half(n16.z));
+    }
+    if (R.depth) R.depth[pix] = R.aov_depth[pix];
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_aether: AETHER aerial-perspective post (f3d_aether.cuh) over the finished accumulation, fused with the
 // beauty read-back: accum + frame-0 depth AOV + hit-type bits -> L_surface*T + L_inscatter -> Reinhard ->

@@ -74,7 +74,12 @@ static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
 enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
 struct cudaPointerAttributes { cudaMemoryType type; int device; void* devicePointer; void* hostPointer; };
-static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
+/* F3D_EMU_HOST_PINNED=1: report every host pointer as page-locked, so that the paths reserved for pinned destinations (one-DMA
+ * read-back, early AOV read-back) run under the interpreter too */
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) {
+    a->type = getenv("F3D_EMU_HOST_PINNED") ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered;
+    return cudaSuccess;
+}
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }

@@ -61,6 +61,22 @@ def test_emulated_near_field_walks_are_bit_identical_to_the_oracle(az, el, earth
     _same_render(g, o)
 
 
+def test_emulated_early_aov_readback_matches_the_ordinary_path(monkeypatch):
+    """With page-locked output arrays the one-call path decodes and copies the three AOVs on a side stream right after set-up
+    (csrc/f3d_backend.cu early_aov_readback, k_resolve_aovs) while the frames render: same bytes as k_resolve's AOV half."""
+    dem = H.golden_dem()
+    kw = {**H.scene_kwargs(dem), "max_frames": 4, "min_frames": 4, "variance_threshold": 1e30}
+    o = oracle.render(dem, 56, 40, H.CAM, want_accum=True, **kw)
+    monkeypatch.setenv("F3D_EMU_HOST_PINNED", "1")
+    with _emu.emulated_backend() as native:
+        g = native.hybrid_render_terrain_reference(dem, 56, 40, H.CAM, want_accum=True, **kw)
+        monkeypatch.setenv("F3D_B200_EARLY_AOVS", "0")
+        g_off = native.hybrid_render_terrain_reference(dem, 56, 40, H.CAM, want_accum=True, **kw)
+    _same_render(g, o)
+    _same_render(g_off, o)
+    assert g["kernel_launches"] == g_off["kernel_launches"] + 1          # k_resolve_aovs ran
+
+
 def test_emulated_render_with_mesh_env_map_spp_and_curvature():
     dem = H.sine_dem(64)
     rng = np.random.default_rng(2)
