@@ -66,9 +66,9 @@ def test_partition_is_bit_identical(world, width, height, block_rows, frames):
     procs = [ctx.Process(target=_worker, args=(r, world, port, frames, width, height, block_rows, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = q.get(timeout=300)
+    got = q.get(timeout=900)
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=300)
         assert p.exitcode == 0
     assert np.array_equal(got["rgba"], ref["rgba"])
     assert np.array_equal(got["depth"].view(np.uint32), ref["depth"].view(np.uint32))
@@ -98,9 +98,9 @@ def test_plus4_offset_needs_a_four_row_halo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, frames, width, height, block_rows, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=300)
+    got = q.get(timeout=900)
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=300)
         assert p.exitcode == 0
     assert np.array_equal(got["rgba"], ref["rgba"])
     assert np.float32(got["variance"]) == np.float32(ref["variance"])
@@ -153,9 +153,9 @@ def test_reservoir_validity_is_checked_across_ranks(case):
     procs = [ctx.Process(target=_validity_worker, args=(r, 2, port, cam, 32, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=300) for _ in range(2)]
+    results = [q.get(timeout=900) for _ in range(2)]
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=300)
         assert p.exitcode == 0
     for rank, status, top_hits, bottom_hits in results:
         if case == "all_sky":
@@ -206,9 +206,9 @@ def test_wavefront_tracer_partition_over_nccl_is_bit_identical():
     procs = [ctx.Process(target=_wavefront_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=300) for _ in range(2)]
+    results = [q.get(timeout=900) for _ in range(2)]
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=300)
         assert p.exitcode == 0
     for rank, hdr, rgba, err in results:
         assert np.array_equal(hdr.view(np.uint32), whole_hdr.view(np.uint32)) and np.array_equal(rgba, whole_rgba), rank
@@ -276,7 +276,7 @@ def test_two_ranks_on_one_device_over_cuda_ipc_are_bit_identical():
             q.put("done")
     finally:
         for p in procs:
-            p.join(timeout=120)
+            p.join(timeout=300)
     assert all(p.exitcode == 0 for p in procs)
     for key in ("rgba", "depth", "normal", "albedo"):
         full = np.zeros_like(ref[key])
@@ -366,9 +366,9 @@ def test_gather_only_partition_over_nccl_matches_the_rank_by_rank_render():
     procs = [ctx.Process(target=_worker, args=(r, world, port, frames, width, height, block_rows, q, 7, "gather_only")) for r in range(world)]
     for p in procs:
         p.start()
-    got = q.get(timeout=300)
+    got = q.get(timeout=900)
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=300)
         assert p.exitcode == 0
     assert np.array_equal(got["rgba"], local["rgba"])
     assert np.array_equal(got["depth"].view(np.uint32), local["depth"].view(np.uint32))
