@@ -235,12 +235,13 @@ __device__ __forceinline__ bool vs_trace_segment(const ViewshedParams& P, float 
     return false;
 }
 
-__device__ __forceinline__ void vs_latlon_to_pixel(const ViewshedParams& P, float lat, float lon, float& px, float& py) {   // :375-387
+__device__ __forceinline__ void vs_latlon_to_pixel(const ViewshedParams& P, float rcp_lon_step, float rcp_lat_step, float lat, float lon,
+                                                   float& px, float& py) {   // :375-387; det_div(x, step) = x * det_rcp(step), reciprocals hoisted
     float lon_deg = vdegrees(lon);
     if (lon_deg < P.geodetic[2]) lon_deg += 360.0f;
     if (lon_deg > P.geodetic[2] + 180.0f) lon_deg -= 360.0f;
-    px = vdet_div(lon_deg - P.geodetic[2], P.metric[1]) - 0.5f;
-    py = vdet_div(P.geodetic[3] - vdegrees(lat), P.metric[2]) - 0.5f;
+    px = (lon_deg - P.geodetic[2]) * rcp_lon_step - 0.5f;
+    py = (P.geodetic[3] - vdegrees(lat)) * rcp_lat_step - 0.5f;
 }
 // geodesic_sample_pixel, :389-468: direct geodesic on the sphere (metric.w > 0) or Vincenty's direct formula on WGS84.
 // The reference re-derives everything that depends on (lat0, azimuth) alone - reduced latitude, sigma1, alpha, u^2, A, B, C:
@@ -249,11 +250,18 @@ __device__ __forceinline__ void vs_latlon_to_pixel(const ViewshedParams& P, floa
 struct VsGeodesic {
     float sin_lat0, cos_lat0, sin_az, cos_az;                      // sphere branch
     float flattening, semi_minor, sin_u1, cos_u1, sigma1, sin_alpha, cos_sq_alpha, ca, cb, cc;   // WGS84 branch
+    // det_div(a, b) IS a * det_rcp(b) (determinism.wgsl:204): the reciprocals of per-chord constants are taken once
+    float rcp_sigma_den;            // det_rcp(semi_minor * A)            (WGS84)  |  det_rcp(sphere radius)  (sphere)
+    float rcp_lon_step, rcp_lat_step;   // det_rcp(metric.y), det_rcp(metric.z)   (latlon_to_pixel)
+    float rcp_abs_sin_az, rcp_abs_cos_az;   // det_rcp(max(|sin az|, 1e-6)), det_rcp(max(|cos az|, 1e-6))   (shadow_step_m)
 };
 __device__ __forceinline__ VsGeodesic vs_geodesic_setup(const ViewshedParams& P, float lat0, float azimuth) {
     VsGeodesic G{};
+    G.rcp_lon_step = vdet_rcp(P.metric[1]); G.rcp_lat_step = vdet_rcp(P.metric[2]);
     if (P.metric[3] > 0.0f) {
         G.sin_lat0 = vdet_sin(lat0); G.cos_lat0 = vdet_cos(lat0); G.sin_az = vdet_sin(azimuth); G.cos_az = vdet_cos(azimuth);
+        G.rcp_sigma_den = vdet_rcp(P.metric[3]);
+        G.rcp_abs_sin_az = vdet_rcp(fmaxf(fabsf(G.sin_az), 1e-6f)); G.rcp_abs_cos_az = vdet_rcp(fmaxf(fabsf(G.cos_az), 1e-6f));
         return G;
     }
     G.flattening = fdiv(1.0f, 298.257223563f);
@@ -269,19 +277,21 @@ __device__ __forceinline__ VsGeodesic vs_geodesic_setup(const ViewshedParams& P,
     G.ca = 1.0f + fdiv(u_sq, 16384.0f) * (4096.0f + u_sq * (-768.0f + u_sq * (320.0f - 175.0f * u_sq)));
     G.cb = fdiv(u_sq, 1024.0f) * (256.0f + u_sq * (-128.0f + u_sq * (74.0f - 47.0f * u_sq)));
     G.cc = fdiv(G.flattening, 16.0f) * G.cos_sq_alpha * (4.0f + G.flattening * (4.0f - 3.0f * G.cos_sq_alpha));
+    G.rcp_sigma_den = vdet_rcp(G.semi_minor * G.ca);
+    G.rcp_abs_sin_az = vdet_rcp(fmaxf(fabsf(G.sin_az), 1e-6f)); G.rcp_abs_cos_az = vdet_rcp(fmaxf(fabsf(G.cos_az), 1e-6f));
     return G;
 }
 __device__ __forceinline__ void vs_geodesic_pixel(const ViewshedParams& P, const VsGeodesic& G, float lon0, float distance_m,
                                                   float& px, float& py) {
     if (P.metric[3] > 0.0f) {
-        const float ad = vdet_div(distance_m, P.metric[3]);
+        const float ad = distance_m * G.rcp_sigma_den;                      // det_div(distance, radius)
         const float sin_lat = vdet_fma(G.sin_lat0, vdet_cos(ad), vdet_sin(ad) * G.cos_lat0 * G.cos_az);
         const float lat = 1.5707963267948966f - vdet_acos(fminf(fmaxf(sin_lat, -1.0f), 1.0f));
         const float lon = lon0 + vdet_atan2(G.sin_az * vdet_sin(ad) * G.cos_lat0, vdet_cos(ad) - G.sin_lat0 * vdet_sin(lat));
-        vs_latlon_to_pixel(P, lat, lon, px, py);
+        vs_latlon_to_pixel(P, G.rcp_lon_step, G.rcp_lat_step, lat, lon, px, py);
         return;
     }
-    const float sigma0 = vdet_div(distance_m, G.semi_minor * G.ca);
+    const float sigma0 = distance_m * G.rcp_sigma_den;                     // det_div(distance, semi_minor * A)
     float sigma = sigma0;
 #pragma unroll 1
     for (int it = 0; it < 4; it++) {
@@ -298,9 +308,9 @@ __device__ __forceinline__ void vs_geodesic_pixel(const ViewshedParams& P, const
     const float lambda = vdet_atan2(ss * G.sin_az, G.cos_u1 * cs - G.sin_u1 * ss * G.cos_az);
     const float c2 = vdet_cos(two_sigma_m);
     const float dlon = lambda - (1.0f - G.cc) * G.flattening * G.sin_alpha * (sigma + G.cc * ss * (c2 + G.cc * cs * (-1.0f + 2.0f * c2 * c2)));
-    vs_latlon_to_pixel(P, lat, lon0 + dlon, px, py);
+    vs_latlon_to_pixel(P, G.rcp_lon_step, G.rcp_lat_step, lat, lon0 + dlon, px, py);
 }
-__device__ __forceinline__ float vs_shadow_step_m(const ViewshedParams& P, float lat, float sin_az, float cos_az) {   // :584-606 (sin / cos of the azimuth hoisted: VsGeodesic)
+__device__ __forceinline__ float vs_shadow_step_m(const ViewshedParams& P, float lat, float rcp_abs_sin_az, float rcp_abs_cos_az) {   // :584-606 (sin / cos of the azimuth hoisted: VsGeodesic)
     const float sl = vdet_sin(lat);
     const float ft = 1.0f - 0.0066943799901413165f * sl * sl;
     const float root = vdet_sqrt(ft);
@@ -309,8 +319,8 @@ __device__ __forceinline__ float vs_shadow_step_m(const ViewshedParams& P, float
     const float hm = P.metric[3] > 0.0f ? P.metric[3] : meridional, hp = P.metric[3] > 0.0f ? P.metric[3] : prime_vertical;
     const float north_cell = hm * vradians(P.metric[2]);
     const float east_cell = hp * vdet_cos(lat) * vradians(P.metric[1]);
-    const float east_cross = vdet_div(east_cell, fmaxf(fabsf(sin_az), 1e-6f));
-    const float north_cross = vdet_div(north_cell, fmaxf(fabsf(cos_az), 1e-6f));
+    const float east_cross = east_cell * rcp_abs_sin_az;         // det_div(east_cell, max(|sin az|, 1e-6))
+    const float north_cross = north_cell * rcp_abs_cos_az;      // det_div(north_cell, max(|cos az|, 1e-6))
     return fmaxf(0.1f, 0.5f * fminf(north_cross, east_cross));
 }
 
@@ -348,7 +358,7 @@ __global__ void __launch_bounds__(kViewshedThreads) k_viewshed(const ViewshedPar
         const VsGeodesic G = vs_geodesic_setup(P, P.geodetic[0], azimuth);
         while (true) {
             const float seg_lat = vradians(vdet_fma(-(spy + 0.5f), P.metric[2], P.geodetic[3]));
-            const float end_d = fminf(start_d + vs_shadow_step_m(P, seg_lat, G.sin_az, G.cos_az), distance_m);
+            const float end_d = fminf(start_d + vs_shadow_step_m(P, seg_lat, G.rcp_abs_sin_az, G.rcp_abs_cos_az), distance_m);
             float epx, epy;
             vs_geodesic_pixel(P, G, P.geodetic[1], end_d, epx, epy);
             if (epx < -0.5f || epy < -0.5f || epx > maxx || epy > maxy) { visible = 2u; break; }
@@ -389,7 +399,7 @@ __global__ void __launch_bounds__(kViewshedThreads) k_shadow_mask(const Viewshed
         out = 1u;
         const VsGeodesic G = vs_geodesic_setup(P, lat0, azimuth);
         while (true) {
-            const float end_d = fminf(start_d + vs_shadow_step_m(P, seg_lat, G.sin_az, G.cos_az), P.metric[0]);
+            const float end_d = fminf(start_d + vs_shadow_step_m(P, seg_lat, G.rcp_abs_sin_az, G.rcp_abs_cos_az), P.metric[0]);
             float epx, epy;
             vs_geodesic_pixel(P, G, lon0, end_d, epx, epy);
             if (vs_trace_segment(P, spx, spy, epx, epy, start_d, end_d, c, 0.01f)) { out = 0u; break; }
