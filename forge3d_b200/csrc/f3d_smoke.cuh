@@ -143,7 +143,6 @@ __device__ __forceinline__ float smoke_sun_transmittance(const SmokeParams& P, v
     return rs_clamp(exp_pinned(-optical_depth), 0.0f, 1.0f);
 }
 
-// march_ray_rgba, render.rs:190-276
 // Straight-alpha "over" of `top` on `bottom`, the reference's _alpha_composite_rgba (python/forge3d/map_scene.py:1588-1604):
 // alpha = a / 255 in f32, rgb = u8(clip(dst * (1 - alpha) + src * alpha, 0, 255)) (truncation), a = max(dst.a, src.a).
 __device__ __forceinline__ uchar4 composite_over(uchar4 bottom, uchar4 top) {
@@ -155,6 +154,7 @@ __device__ __forceinline__ uchar4 composite_over(uchar4 bottom, uchar4 top) {
                        (unsigned char)rs_clamp(b, 0.0f, 255.0f), bottom.w > top.w ? bottom.w : top.w);
 }
 
+// march_ray_rgba, render.rs:190-276
 __device__ __forceinline__ uchar4 smoke_march(const SmokeParams& P, v3 origin, v3 dir, float t0, float t1, uint32_t seed, v3 sun_dir) {
     const SmokeSettings& S = P.s;
     const float step = P.step;
